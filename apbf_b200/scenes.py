@@ -1,0 +1,159 @@
+"""Synthetic particle states for the BASELINE.json configs (host-side numpy, no device work).
+
+Seeding restates pbd::initialize::add_box_shape (source/initialize.cpp:5-33 with
+shaders/initialize_box.comp:30-50): a regular lattice with spacing 2r, positions stored as
+int32 fixed point = trunc(pos * 2^18), inverse mass 1/(2r)^D, radius r, velocity 0; fluid arrays as in
+pool::pool (source/pool.cpp:20-25): kernel_width = 4r, target_radius = r, boundariness = 1,
+boundary_distance = uint(r * 2^18).  Pool walls follow source/pool.cpp:30-40.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+POS_RESOLUTION = 262144.0
+KERNEL_SCALE = 4.0
+
+
+@dataclass
+class Scene:
+    name: str
+    dims: int
+    arrays: dict                 # the reference's lists as numpy arrays (see oracle.State.FIELDS)
+    min_pos: tuple               # Green grid bounds (neighborhood_green::set_position_range)
+    max_pos: tuple
+    res_log2: int
+    box_min: np.ndarray = field(default_factory=lambda: np.zeros((0, 4), np.float32))
+    box_max: np.ndarray = field(default_factory=lambda: np.zeros((0, 4), np.float32))
+    basic_pbf: bool = True
+    solver_iterations: int = 4
+    smallest_target_radius: float = 1.0
+
+    @property
+    def n(self):
+        return self.arrays["index_list"].shape[0]
+
+
+def _lattice_state(counts, origin, r, jitter=0.0, seed=1234, dims=3, radius_of=None):
+    """counts particles per axis starting at `origin` (float32 arithmetic as initialize_box.comp:43-45)."""
+    cx, cy, cz = [int(c) for c in counts]
+    n = cx * cy * cz
+    ids = np.arange(n, dtype=np.uint32)
+    gx = ids // (cz * cy)
+    rem = ids - gx * (cz * cy)
+    gy = rem // cz
+    gz = rem - gy * cz
+    g = np.stack([gx, gy, gz], axis=1).astype(np.float32)
+    pos = np.asarray(origin, np.float32)[None, :] + np.float32(2.0) * np.float32(r) * g
+    if jitter:
+        rng = np.random.default_rng(seed)
+        pos = pos + rng.uniform(-jitter, jitter, size=pos.shape).astype(np.float32)
+    ipos = np.zeros((n, 4), np.int32)
+    ipos[:, :3] = np.trunc(pos.astype(np.float32) * np.float32(POS_RESOLUTION)).astype(np.int32)
+    if dims < 3:
+        ipos[:, 2] = 0
+    radius = np.full(n, r, np.float32) if radius_of is None else radius_of(pos).astype(np.float32)
+    inv_mass = (np.float32(1.0) / np.power(np.float32(2.0) * radius, np.float32(dims))).astype(np.float32)
+    return dict(
+        index_list=ids.copy(),
+        position=ipos,
+        velocity=np.zeros((n, 4), np.float32),
+        inverse_mass=inv_mass,
+        radius=radius,
+        pos_backup=ipos.copy(),
+        transferring=np.zeros(n, np.uint32),
+        target_radius=radius.copy(),
+        kernel_width=(radius * np.float32(KERNEL_SCALE)).astype(np.float32),
+        boundariness=np.ones(n, np.float32),
+        boundary_distance=np.trunc(radius * np.float32(POS_RESOLUTION)).astype(np.uint32),
+    )
+
+
+def _res_for(extent, cell):
+    """smallest res with 2^res cells of size >= cell covering extent... i.e. cell size extent/2^res >= cell"""
+    res = 1
+    while extent / (1 << (res + 1)) >= cell:
+        res += 1
+    return res
+
+
+def pool_walls(mn, mx, r, dims=3, wall=4.0):
+    """source/pool.cpp:30-40"""
+    mn = np.asarray(mn, np.float32); mx = np.asarray(mx, np.float32)
+    w_min = mn - np.float32(wall)
+    w_max = mx + np.float32(wall) + np.array([0, 2 * r, 0], np.float32)
+    boxes = [
+        (w_min, (w_min[0] + wall, w_max[1], w_max[2])),
+        (w_min, (w_max[0], w_min[1] + wall, w_max[2])),
+        ((w_max[0] - wall, w_min[1], w_min[2]), w_max),
+        ((w_min[0], w_max[1] - wall, w_min[2]), w_max),
+    ]
+    if dims > 2:
+        boxes += [(w_min, (w_max[0], w_max[1], w_min[2] + wall)), ((w_min[0], w_min[1], w_max[2] - wall), w_max)]
+    bmin = np.zeros((len(boxes), 4), np.float32); bmax = np.zeros((len(boxes), 4), np.float32)
+    for i, (a, b) in enumerate(boxes):
+        bmin[i, :3] = a; bmax[i, :3] = b
+    return bmin, bmax
+
+
+def uniform_block(side=64, r=1.0, jitter=0.0, seed=1234, dims=3, res_log2=None, shuffle=False):
+    """configs[0]/[4]: side^D lattice centred on the origin, fixed kernel width 4r, basic PBF, 4 iterations.
+    Grid bounds = particle bounds +- 4r."""
+    counts = (side, side, side if dims == 3 else 1)
+    half = side * r  # particle centres span [-(side-1)r, (side-1)r]
+    origin = (-(side - 1) * r, -(side - 1) * r, -(side - 1) * r if dims == 3 else 0.0)
+    arrays = _lattice_state(counts, origin, r, jitter, seed, dims)
+    lo = -(half + 4 * r); hi = half + 4 * r
+    if res_log2 is None:
+        res_log2 = _res_for(hi - lo, 4.0 * r)
+    if shuffle:
+        arrays = shuffle_state(arrays, seed)
+    sc = Scene(name=f"uniform_{side}^{dims}" + ("_jitter" if jitter else ""), dims=dims, arrays=arrays,
+               min_pos=(lo, lo, lo), max_pos=(hi, hi, hi), res_log2=res_log2, basic_pbf=True,
+               solver_iterations=4, smallest_target_radius=r)
+    sc.box_min, sc.box_max = pool_walls((-half,) * 3, (half,) * 3, r, dims)
+    return sc
+
+
+def shuffle_state(arrays, seed=7):
+    """Random permutation of the hidden slots (index list stays the identity): exercises the sort/reorder."""
+    n = arrays["index_list"].shape[0]
+    perm = np.random.default_rng(seed).permutation(n)
+    out = {}
+    for k, v in arrays.items():
+        out[k] = v.copy() if k == "index_list" else v[perm].copy()
+    return out
+
+
+def dam_break(nx=100, ny=100, nz=100, r=1.0, jitter=0.05, seed=99, adaptive=True):
+    """configs[1]: a block occupying one third of a pool floor (walls per pool.cpp:30-40), adaptive widths."""
+    ext = np.array([nx, ny, nz], np.float32) * 2 * r
+    pool_min = np.array([0, 0, 0], np.float32)
+    pool_max = np.array([3 * ext[0], 1.5 * ext[1], ext[2]], np.float32)
+    arrays = _lattice_state((nx, ny, nz), pool_min + r, r, jitter, seed)
+    margin = 6.0 * r + 4.0
+    lo = float(min(pool_min) - margin)
+    hi = float(max(pool_max) + margin)
+    sc = Scene(name=f"dam_break_{nx}x{ny}x{nz}", dims=3, arrays=shuffle_state(arrays, seed),
+               min_pos=(lo, lo, lo), max_pos=(hi, hi, hi), res_log2=_res_for(hi - lo, 6.0 * r),
+               basic_pbf=not adaptive, solver_iterations=4, smallest_target_radius=r)
+    sc.box_min, sc.box_max = pool_walls(pool_min, pool_max, r, 3)
+    return sc
+
+
+def waterdrop(side=160, r=1.0, jitter=0.05, seed=5):
+    """configs[2]: per-particle radius classes {r, 2^(1/3) r, 2^(2/3) r, 2r} by depth (emulates split/merge
+    output) -> variable kernel widths and neighbour-count skew."""
+    def radius_of(pos):
+        y = pos[:, 1]
+        t = (y - y.min()) / max(float(y.max() - y.min()), 1e-6)
+        cls = np.minimum((t * 4).astype(np.int32), 3)
+        return (np.float32(r) * np.power(np.float32(2.0), (3 - cls).astype(np.float32) / np.float32(3.0)))
+    half = side * r
+    origin = (-(side - 1) * r,) * 3
+    arrays = _lattice_state((side,) * 3, origin, r, jitter, seed, 3, radius_of)
+    lo = -(half + 12 * r); hi = half + 12 * r
+    sc = Scene(name=f"waterdrop_{side}^3", dims=3, arrays=shuffle_state(arrays, seed), min_pos=(lo,) * 3, max_pos=(hi,) * 3,
+               res_log2=_res_for(hi - lo, 8.0 * r), basic_pbf=False, solver_iterations=4, smallest_target_radius=r)
+    sc.box_min, sc.box_max = pool_walls((-half,) * 3, (half,) * 3, r, 3)
+    return sc
+
