@@ -1,0 +1,444 @@
+"""apbf_b200 -- B200 (sm_100a) implementation of APBF's per-substep particle hot path.
+
+The product is libapbf_b200.so (C-ABI in include/apbf_b200.h, CUDA sources in apbf_b200/csrc).  This module is the
+thin Python front-end used by tests/ and bench.py: it mirrors the reference's operator interface (same class and method
+names as source/neighborhood_green.h, incompressibility.h, spread_kernel_width.h, box_collision.h,
+velocity_handling.h) on top of device arrays held in torch tensors.  PyTorch is plumbing only (device memory, streams,
+torch.distributed); every computation goes through the C-ABI.  There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import Settings
+
+__all__ = ["Context", "ParticleLists", "neighborhood_green", "neighborhood_binary_search", "incompressibility",
+           "spread_kernel_width", "box_collision", "velocity_handling", "algorithms", "Sim", "Settings"]
+
+_HIDDEN = (("position", np.int32, 4), ("velocity", np.float32, 4), ("inverse_mass", np.float32, 1),
+           ("radius", np.float32, 1), ("pos_backup", np.int32, 4), ("transferring", np.uint32, 1))
+_PER_ID = (("target_radius", np.float32, 1), ("kernel_width", np.float32, 1), ("boundariness", np.float32, 1),
+           ("boundary_distance", np.uint32, 1))
+FIELDS = (("index_list", np.uint32, 1),) + _HIDDEN + _PER_ID
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("apbf_b200 needs a CUDA device (no CPU fallback)")
+    return torch
+
+
+def _check(ctx, rc):
+    if rc != 0:
+        msg = _capi.load().apbf_ctx_last_error(ctx.handle) if ctx is not None and ctx.handle else b""
+        raise RuntimeError(f"apbf_b200 call failed with status {rc}: {msg.decode() if msg else ''}")
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+_TORCH_DT = {np.dtype(np.int32): "int32", np.dtype(np.float32): "float32", np.dtype(np.uint32): "int32"}
+
+
+class Context:
+    """apbf_ctx: one ordered CUDA stream of work (replaces shader_provider's recording state)."""
+
+    def __init__(self, device=0, stream=None, dims=3, settings=None):
+        torch = _torch()
+        self.lib = _capi.load()
+        self.device = device
+        torch.cuda.set_device(device)
+        if stream is None:
+            stream = torch.cuda.current_stream(device).cuda_stream
+        h = C.c_void_p()
+        rc = self.lib.apbf_ctx_create(device, C.c_void_p(stream), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"apbf_ctx_create failed with status {rc} (no CUDA device? there is no CPU fallback)")
+        self.handle = h
+        self.dims = dims
+        _check(self, self.lib.apbf_ctx_set_dimensions(self.handle, dims))
+        self.settings = Settings()
+        self.lib.apbf_default_settings(C.byref(self.settings))
+        if settings is not None:
+            self.set_settings(settings)
+
+    def set_settings(self, s=None, **kw):
+        if s is not None:
+            self.settings = s
+        for k, v in kw.items():
+            setattr(self.settings, k, v)
+        _check(self, self.lib.apbf_ctx_set_settings(self.handle, C.byref(self.settings)))
+
+    def set_dimensions(self, dims):
+        self.dims = dims
+        _check(self, self.lib.apbf_ctx_set_dimensions(self.handle, dims))
+
+    def synchronize(self):
+        _check(self, self.lib.apbf_ctx_synchronize(self.handle))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.apbf_ctx_launch_count(self.handle))
+
+    def profile(self, enable=True):
+        _check(self, self.lib.apbf_ctx_profile(self.handle, int(enable)))
+
+    def profile_read(self):
+        """{category: (milliseconds, spans)} accumulated since profile(True)"""
+        out, i = {}, 0
+        while True:
+            name, ms, calls = C.c_char_p(), C.c_double(), C.c_uint64()
+            if self.lib.apbf_ctx_profile_read(self.handle, i, C.byref(name), C.byref(ms), C.byref(calls)) != 0:
+                return out
+            out[name.value.decode()] = (ms.value, calls.value)
+            i += 1
+
+    def device_flags(self):
+        f = C.c_uint32()
+        _check(self, self.lib.apbf_ctx_device_flags(self.handle, C.byref(f)))
+        return f.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.apbf_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ParticleLists:
+    """The scene's lists (pbd::particles + pbd::fluid + pbd::neighbors, source/list_definitions.h:9-20) in device memory.
+    Every re-orderable array has a second buffer, the copy-on-write target of gpu_list::apply_edit."""
+
+    def __init__(self, ctx, arrays, capacity=None, neighbor_capacity=None):
+        torch = _torch()
+        self.ctx = ctx
+        n = int(np.asarray(arrays["index_list"]).shape[0])
+        nh = int(np.asarray(arrays["position"]).reshape(-1, 4).shape[0])
+        self.capacity = int(capacity or max(n, nh, 1))
+        self.neighbor_capacity = int(neighbor_capacity or 64 * self.capacity)
+        dev = torch.device("cuda", ctx.device)
+        self.buf = {}
+        for name, dt, w in FIELDS:
+            src = np.ascontiguousarray(arrays[name], dtype=dt).reshape(-1, w)
+            a = torch.zeros((self.capacity, w), dtype=getattr(torch, _TORCH_DT[np.dtype(dt)]), device=dev)
+            b = torch.zeros_like(a)
+            if src.shape[0]:
+                a[:src.shape[0]].copy_(torch.from_numpy(src.view(np.int32) if dt == np.uint32 else src).to(dev))
+            self.buf[name] = [a, b]
+        self.words = torch.zeros(16, dtype=torch.int32, device=dev)  # [0] index length, [1] hidden length, [2] pair count
+        self.words[0] = n
+        self.words[1] = nh
+        self.pairs = torch.zeros((self.neighbor_capacity, 2), dtype=torch.int32, device=dev)
+
+    # ---- C views --------------------------------------------------------------------------------------------------
+    def _arr(self, name):
+        a, b = self.buf[name]
+        return _capi.Array(a.data_ptr(), b.data_ptr())
+
+    def fluid(self):
+        p = _capi.Particles()
+        p.index_list = self._arr("index_list")
+        p.length = self.words.data_ptr()
+        p.capacity = self.capacity
+        p.hidden_length = self.words.data_ptr() + 4
+        p.hidden_capacity = self.capacity
+        for name, _, _ in _HIDDEN:
+            setattr(p, name, self._arr(name))
+        f = _capi.Fluid()
+        f.particle = p
+        for name, _, _ in _PER_ID:
+            setattr(f, name, self._arr(name))
+        return f
+
+    def neighbors(self):
+        return _capi.Neighbors(self.pairs.data_ptr(), self.words.data_ptr() + 8, self.neighbor_capacity)
+
+    def swap(self):
+        """after a search: the reorder_out buffers hold the lists"""
+        for v in self.buf.values():
+            v.reverse()
+
+    # ---- read-back (gpu_list::read, debugging only) --------------------------------------------------------------
+    def length(self):
+        return int(self.words[0].item())
+
+    def pair_count(self):
+        return int(self.words[2].item())
+
+    def read(self, name):
+        _, dt, w = next(f for f in FIELDS if f[0] == name)
+        n = self.length() if name not in [h[0] for h in _HIDDEN] else int(self.words[1].item())
+        a = self.buf[name][0][:n].cpu().numpy()
+        a = a.view(np.uint32) if dt == np.uint32 else a
+        return a.reshape(-1, w) if w > 1 else a.reshape(-1)
+
+    def read_all(self):
+        return {name: self.read(name) for name, _, _ in FIELDS}
+
+    def read_pairs(self):
+        return self.pairs[:self.pair_count()].cpu().numpy().view(np.uint32)
+
+
+class _Operator:
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.lib = ctx.lib
+
+
+class neighborhood_green(_Operator):
+    """pbd::neighborhood_green (source/neighborhood_green.h:8-24)"""
+
+    def set_data(self, lists):
+        self.lists = lists
+        return self
+
+    def set_range_scale(self, scale):
+        self.scale = float(scale)
+        return self
+
+    def set_position_range(self, min_pos, max_pos, resolution_log2):
+        self.min_pos, self.max_pos, self.res = tuple(min_pos), tuple(max_pos), int(resolution_log2)
+        return self
+
+    def apply(self, debug=False):
+        torch = _torch()
+        L = self.lists
+        fl, nb = L.fluid(), L.neighbors()
+        rng = fl.kernel_width  # pool.cpp:45: the range list is fluid.kernel_width
+        dbg, keep = None, {}
+        if debug:
+            dev = L.words.device
+            n_cells = 1 << (self.res * self.ctx.dims)
+            keep = dict(sorted_key=torch.zeros(L.capacity, dtype=torch.int32, device=dev),
+                        sorted_index=torch.zeros(L.capacity, dtype=torch.int32, device=dev),
+                        cell_start=torch.zeros(n_cells, dtype=torch.int32, device=dev),
+                        cell_end=torch.zeros(n_cells, dtype=torch.int32, device=dev))
+            dbg = _capi.SearchDebug(keep["sorted_key"].data_ptr(), keep["sorted_index"].data_ptr(),
+                                    keep["cell_start"].data_ptr(), keep["cell_end"].data_ptr())
+        _check(self.ctx, self.lib.apbf_neighborhood_green_apply(
+            self.ctx.handle, C.byref(fl), C.byref(rng), C.byref(nb), self.scale, _f3(self.min_pos), _f3(self.max_pos),
+            self.res, C.byref(dbg) if dbg else None))
+        L.swap()
+        if debug:
+            nh = int(L.words[1].item())
+            out = {k: v.cpu().numpy().view(np.uint32) for k, v in keep.items()}
+            out["sorted_key"] = out["sorted_key"][:nh]
+            out["sorted_index"] = out["sorted_index"][:nh]
+            return out
+
+
+class neighborhood_binary_search(_Operator):
+    """pbd::neighborhood_binary_search (source/neighborhood_binary_search.h:8-21)"""
+
+    def set_data(self, lists):
+        self.lists = lists
+        return self
+
+    def set_range_scale(self, scale):
+        self.scale = float(scale)
+        return self
+
+    def apply(self, debug=False):
+        torch = _torch()
+        L = self.lists
+        fl, nb = L.fluid(), L.neighbors()
+        rng = fl.kernel_width
+        dbg, keep = None, {}
+        if debug:
+            dev = L.words.device
+            keep = {k: torch.zeros(L.capacity, dtype=torch.int32, device=dev) for k in ("sorted_index", "code0", "code1", "code2")}
+            dbg = _capi.SearchDebug()
+            dbg.sorted_index = keep["sorted_index"].data_ptr()
+            dbg.code[0], dbg.code[1], dbg.code[2] = keep["code0"].data_ptr(), keep["code1"].data_ptr(), keep["code2"].data_ptr()
+        _check(self.ctx, self.lib.apbf_neighborhood_binary_search_apply(
+            self.ctx.handle, C.byref(fl), C.byref(rng), C.byref(nb), self.scale, C.byref(dbg) if dbg else None))
+        L.swap()
+        if debug:
+            n = L.length()
+            return {k: v.cpu().numpy().view(np.uint32)[:n] for k, v in keep.items()}
+
+
+class incompressibility(_Operator):
+    """pbd::incompressibility (source/incompressibility.h:8-18)"""
+
+    def set_data(self, lists):
+        self.lists = lists
+        return self
+
+    def apply(self, debug=False):
+        torch = _torch()
+        L = self.lists
+        fl, nb = L.fluid(), L.neighbors()
+        lam = inc = None
+        if debug:
+            lam = torch.zeros(L.capacity, dtype=torch.float32, device=L.words.device)
+            inc = torch.zeros((L.capacity, 8), dtype=torch.int32, device=L.words.device)
+        _check(self.ctx, self.lib.apbf_incompressibility_apply(
+            self.ctx.handle, C.byref(fl), C.byref(nb), lam.data_ptr() if debug else None, inc.data_ptr() if debug else None))
+        if debug:
+            n = L.length()
+            inc = inc[:n].cpu().numpy()
+            return dict(lam=lam[:n].cpu().numpy(), grad_sum=inc[:, 0:3].copy(), density=inc[:, 3].view(np.uint32).copy(),
+                        sq_grad_sum=inc[:, 4].view(np.uint32).copy())
+
+
+class spread_kernel_width(_Operator):
+    """pbd::spread_kernel_width (source/spread_kernel_width.h:7-17)"""
+
+    def set_data(self, lists):
+        self.lists = lists
+        return self
+
+    def apply(self, debug=False):
+        torch = _torch()
+        L = self.lists
+        fl, nb = L.fluid(), L.neighbors()
+        kwfx = torch.zeros(L.capacity, dtype=torch.int32, device=L.words.device) if debug else None
+        _check(self.ctx, self.lib.apbf_spread_kernel_width_apply(self.ctx.handle, C.byref(fl), C.byref(nb),
+                                                                 kwfx.data_ptr() if debug else None))
+        if debug:
+            return kwfx[:L.length()].cpu().numpy().view(np.uint32)
+
+
+class box_collision(_Operator):
+    """pbd::box_collision (source/box_collision.h:8-18)"""
+
+    def set_data(self, lists, box_min, box_max):
+        torch = _torch()
+        self.lists = lists
+        dev = lists.words.device
+        self.box_min = torch.from_numpy(np.ascontiguousarray(box_min, np.float32).reshape(-1, 4)).to(dev)
+        self.box_max = torch.from_numpy(np.ascontiguousarray(box_max, np.float32).reshape(-1, 4)).to(dev)
+        return self
+
+    def apply(self):
+        fl = self.lists.fluid()
+        _check(self.ctx, self.lib.apbf_box_collision_apply(self.ctx.handle, C.byref(fl.particle), self.box_min.data_ptr(),
+                                                           self.box_max.data_ptr(), self.box_min.shape[0]))
+
+
+class velocity_handling(_Operator):
+    """pbd::velocity_handling (source/velocity_handling.h:7-19)"""
+
+    def set_data(self, lists):
+        self.lists = lists
+        self.last_dt = 1.0
+        self.accel = (0.0, 0.0, 0.0)
+        return self
+
+    def set_acceleration(self, accel=(0.0, 0.0, 0.0)):
+        self.accel = tuple(accel)
+        return self
+
+    def apply(self, dt):
+        fl = self.lists.fluid()
+        _check(self.ctx, self.lib.apbf_velocity_handling_apply(self.ctx.handle, C.byref(fl.particle), float(dt),
+                                                               float(self.last_dt), _f3(self.accel)))
+        if dt != 0.0:
+            self.last_dt = dt
+
+
+class algorithms:
+    """pbd::algorithms (source/algorithms.h:12-17) on torch int32 tensors holding u32 values."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.lib = ctx.lib
+
+    def sort(self, keys, values, count, max_count, out_keys, out_values, upper_bound=0xFFFFFFFF):
+        _check(self.ctx, self.lib.apbf_sort(self.ctx.handle, keys.data_ptr(), values.data_ptr(), count.data_ptr(), max_count,
+                                            out_keys.data_ptr(), out_values.data_ptr(), upper_bound))
+
+    def prefix_sum(self, values, count, max_count, result=None):
+        result = values if result is None else result
+        _check(self.ctx, self.lib.apbf_prefix_sum(self.ctx.handle, values.data_ptr(), count.data_ptr(), max_count, result.data_ptr()))
+
+    def sort_calculate_needed_helper_list_length(self, n):
+        return self.lib.apbf_sort_calculate_needed_helper_list_length(n)
+
+    def prefix_sum_calculate_needed_helper_list_length(self, n):
+        return self.lib.apbf_prefix_sum_calculate_needed_helper_list_length(n)
+
+
+class Sim:
+    """apbf_sim: the lists of one scene resident in HBM and pool::update (source/pool.cpp:67-106) over them.
+    upload()/download() move the lists between host memory and the device (the end-to-end path)."""
+
+    def __init__(self, ctx, scene, capacity=None, neighbor_capacity=None, use_binary_search=False, integrate=False,
+                 dt=1.0 / 60.0, accel=(0.0, -10.0, 0.0), solver_iterations=None, basic_pbf=None):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.capacity = int(capacity or scene.n)
+        self.neighbor_capacity = int(neighbor_capacity or 40 * self.capacity)
+        cfg = _capi.SimConfig()
+        cfg.particle_capacity, cfg.neighbor_capacity = self.capacity, self.neighbor_capacity
+        cfg.dims = scene.dims
+        cfg.basic_pbf = int(scene.basic_pbf if basic_pbf is None else basic_pbf)
+        cfg.solver_iterations = int(scene.solver_iterations if solver_iterations is None else solver_iterations)
+        cfg.use_binary_search, cfg.integrate, cfg.dt = int(use_binary_search), int(integrate), dt
+        cfg.accel, cfg.min_pos, cfg.max_pos = _f3(accel), _f3(scene.min_pos), _f3(scene.max_pos)
+        cfg.res_log2 = scene.res_log2
+        bmin = np.ascontiguousarray(scene.box_min, np.float32).reshape(-1, 4)
+        bmax = np.ascontiguousarray(scene.box_max, np.float32).reshape(-1, 4)
+        cfg.n_boxes = bmin.shape[0]
+        cfg.box_min4_host, cfg.box_max4_host = bmin.ctypes.data, bmax.ctypes.data
+        h = C.c_void_p()
+        _check(ctx, self.lib.apbf_sim_create(ctx.handle, C.byref(cfg), C.byref(h)))
+        self.handle = h
+
+    @staticmethod
+    def host_state(arrays, n=None):
+        """arrays: name -> numpy array or (pinned) torch CPU tensor"""
+        hs = _capi.HostState()
+        hs.n = int(n if n is not None else len(arrays["position"]))
+        for name, _, _ in FIELDS:
+            a = arrays.get(name)
+            if a is None:
+                continue
+            ptr = a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr()
+            setattr(hs, name, ptr)
+        return hs
+
+    def upload(self, arrays, n=None):
+        hs = self.host_state(arrays, n)
+        _check(self.ctx, self.lib.apbf_sim_upload(self.handle, C.byref(hs)))
+
+    def download(self, arrays):
+        hs = self.host_state(arrays, 0)
+        _check(self.ctx, self.lib.apbf_sim_download(self.handle, C.byref(hs)))
+        return hs.n
+
+    def substep(self, n=1):
+        _check(self.ctx, self.lib.apbf_sim_substep(self.handle, n))
+
+    def stats(self):
+        w = (C.c_uint32 * 4)()
+        _check(self.ctx, self.lib.apbf_sim_stats(self.handle, w))
+        return dict(n=w[0], pairs_searched=w[1], pairs_kept=w[2], pairs_unmirrored=w[3])
+
+    def neighbor_count(self):
+        c = C.c_uint32()
+        _check(self.ctx, self.lib.apbf_sim_neighbor_count(self.handle, C.byref(c)))
+        return c.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.apbf_sim_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def empty_host_arrays(n):
+    return {name: np.zeros((n, w) if w > 1 else (n,), dt) for name, dt, w in FIELDS}

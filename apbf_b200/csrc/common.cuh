@@ -1,0 +1,139 @@
+// common.cuh -- context, scratch memory and small device helpers shared by all translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/apbf_b200.h"
+
+#define APBF_NUM_SMS_DEFAULT 148
+
+// named scratch slots (grown on demand, never shrunk: the steady state allocates nothing)
+enum apbf_scratch_slot {
+	SLOT_SORT_KEYS_A = 0, SLOT_SORT_KEYS_B, SLOT_SORT_VALS_A, SLOT_SORT_VALS_B, SLOT_SORT_HIST, SLOT_SORT_STATUS,
+	SLOT_SCAN_STATUS, SLOT_MISC_WORDS, SLOT_CELL_START, SLOT_CELL_END, SLOT_COUNTS, SLOT_OFFSETS, SLOT_SYMBITS,
+	SLOT_INV_PERM, SLOT_TMP_KEYS, SLOT_TMP_VALS, SLOT_TMP_VALS2, SLOT_CODE0, SLOT_CODE1, SLOT_CODE2,
+	SLOT_P4, SLOT_L4, SLOT_G4, SLOT_DELTA, SLOT_PUSH, SLOT_RADIUS_ID, SLOT_KWFX, SLOT_KEEP_COUNTS, SLOT_KEEP_OFFSETS,
+	SLOT_PAIRS_TMP, SLOT_SYMBITS_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4,
+	SLOT_COUNT
+};
+
+struct apbf_scratch {
+	void*  ptr = nullptr;
+	size_t bytes = 0;
+};
+
+struct apbf_pool_block {
+	void*  ptr;
+	size_t bytes;
+	bool   in_use;
+};
+
+// words in the SLOT_MISC_WORDS buffer (device-side scalars)
+enum apbf_misc_word {
+	MW_FLAGS = 0,        // sticky status bits (bit 0: neighbour list overflow)
+	MW_N_ASYM = 1,       // number of pairs (a,b) without a mirrored pair (b,a) in the current neighbour list
+	MW_TOTAL_PAIRS = 2,  // unclamped pair count of the last search
+	MW_IDENTITY = 3,     // 1 if the index list is the identity over all hidden particles
+	MW_KEPT_PAIRS = 4,   // pair count after the last spread_kernel_width prune
+	MW_TICKET0 = 8,      // tile tickets of the chained-scan kernels (8 words)
+	MW_SCAN_TOTAL = 16,
+	MW_WORDS = 64
+};
+
+// per-kernel-category device timing (CUDA events on the context stream), off by default
+enum apbf_prof_cat {
+	PROF_HASH_SORT = 0, PROF_REORDER, PROF_CELL_RANGES, PROF_EMIT_COUNT, PROF_EMIT_SCAN, PROF_EMIT_FILL, PROF_KW_SPREAD,
+	PROF_KW_COMPACT, PROF_KW_MISC, PROF_BOX, PROF_DENSITY_LAMBDA, PROF_APPLY_DELTA, PROF_COMMIT, PROF_VELOCITY, PROF_COUNT
+};
+struct apbf_prof_span { int cat; cudaEvent_t beg, end; };
+
+struct apbf_ctx {
+	bool          prof_on = false;
+	std::vector<apbf_prof_span> prof_spans;
+	std::vector<cudaEvent_t>    prof_free;
+	double        prof_ms[PROF_COUNT] = {};
+	uint64_t      prof_calls[PROF_COUNT] = {};
+	int           prof_open = -1;
+	int           device = 0;
+	cudaStream_t  stream = nullptr;
+	int           num_sms = APBF_NUM_SMS_DEFAULT;
+	int           dims = 3;
+	apbf_settings settings;
+	uint64_t      launches = 0;
+	std::string   last_error;
+	apbf_scratch  scratch[SLOT_COUNT];
+	std::vector<apbf_pool_block> pool;
+	// provenance of the neighbour list structure built by the last search (offsets/symbits valid for this buffer)
+	const uint32_t* nbr_struct_pairs = nullptr;
+	uint32_t        nbr_struct_n_cap = 0;
+
+	void* scratch_get(int slot, size_t bytes);
+	uint32_t* misc() { return (uint32_t*)scratch_get(SLOT_MISC_WORDS, MW_WORDS * sizeof(uint32_t)); }
+};
+
+int apbf_fail(apbf_ctx* ctx, int code, const char* what, const char* file, int line);
+void apbf_prof_begin(apbf_ctx* ctx, int cat);
+void apbf_prof_end(apbf_ctx* ctx);
+struct apbf_prof_scope { // RAII: times everything enqueued while it is alive
+	apbf_ctx* c;
+	apbf_prof_scope(apbf_ctx* ctx, int cat) : c(ctx) { if (c->prof_on) apbf_prof_begin(c, cat); }
+	~apbf_prof_scope() { if (c->prof_on) apbf_prof_end(c); }
+};
+
+#define APBF_CUDA(ctx, expr)                                                                   \
+	do {                                                                                       \
+		cudaError_t e__ = (expr);                                                              \
+		if (e__ != cudaSuccess) return apbf_fail(ctx, APBF_ERR_CUDA, cudaGetErrorString(e__), __FILE__, __LINE__); \
+	} while (0)
+#define APBF_REQUIRE(ctx, cond)                                                                \
+	do {                                                                                       \
+		if (!(cond)) return apbf_fail(ctx, APBF_ERR_INVALID, #cond, __FILE__, __LINE__);       \
+	} while (0)
+#define APBF_TRY(expr)                                                                         \
+	do {                                                                                       \
+		int r__ = (expr);                                                                      \
+		if (r__ != 0) return r__;                                                              \
+	} while (0)
+// after a kernel launch
+#define APBF_LAUNCHED(ctx)                                                                     \
+	do {                                                                                       \
+		(ctx)->launches++;                                                                     \
+		cudaError_t e__ = cudaGetLastError();                                                  \
+		if (e__ != cudaSuccess) return apbf_fail(ctx, APBF_ERR_CUDA, cudaGetErrorString(e__), __FILE__, __LINE__); \
+	} while (0)
+
+static inline unsigned apbf_div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+// grid for a grid-stride kernel over up to `n` items: enough CTAs for n, capped at a multiple of the SM count
+static inline unsigned apbf_grid(const apbf_ctx* ctx, size_t n, unsigned block, unsigned ctas_per_sm = 8)
+{
+	size_t need = (n + block - 1) / block;
+	size_t cap = (size_t)ctx->num_sms * ctas_per_sm;
+	if (need < 1) need = 1;
+	return (unsigned)(need < cap ? need : cap);
+}
+
+// ---- device helpers ---------------------------------------------------------------------------------------
+// The library is compiled with -fmad=false: a*b+c is never contracted, like the oracle's -ffp-contract=off.
+#ifdef __CUDACC__
+#define R_POS APBF_POS_RESOLUTION
+#define INV_R_POS (1.0f / 262144.0f) // exact power of two: x / 2^18 == x * 2^-18 bit for bit
+
+__device__ __forceinline__ float glsl_min(float x, float y) { return y < x ? y : x; }
+__device__ __forceinline__ float glsl_max(float x, float y) { return x < y ? y : x; }
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz)
+{
+	return (ax * bx + ay * by) + az * bz;
+}
+__device__ __forceinline__ uint32_t f2u(float f) { return (uint32_t)f; } // cvt.rzi.u32.f32: negative/NaN -> 0, saturating
+__device__ __forceinline__ int32_t f2i(float f) { return (int32_t)f; }   // cvt.rzi.s32.f32: NaN -> 0, saturating
+
+__device__ __forceinline__ int4 ldg_int4(const int32_t* p4, uint32_t i) { return __ldg((const int4*)p4 + i); }
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+#endif

@@ -1,0 +1,120 @@
+// kernels.cuh -- the SPH kernel functions of shaders/kernels.glsl:3-123 as device templates.
+//
+// Everything that depends only on the kernel width is hoisted into per-particle constants (kpar); the per-pair part
+// keeps the reference's expression order so that results differ from the oracle only through libm (powf/expf).
+// Kernel ids: height {0 cubic, 1 gauss, 2 poly6, 3 cone, 4 quadratic spike},
+//             gradient {0 cubic, 1 gauss, 2 spiky, 3 cone, 4 quadratic spike}   (kernels.glsl:99-123)
+#pragma once
+#include "common.cuh"
+
+#define APBF_PI 3.14159265f // kernels.glsl:1
+
+struct kpar {
+	float w;      // kernel width h
+	float c0, c1; // per-particle constants, meaning depends on the kernel
+};
+
+struct vec3f { float x, y, z; };
+
+// ---- per-particle constants ------------------------------------------------------------------------------------------
+template <int HK>
+__device__ __forceinline__ kpar height_params(float w, float D)
+{
+	kpar p; p.w = w; p.c0 = 0.f; p.c1 = 0.f;
+	if (HK == 0) p.c0 = 8.0f / (APBF_PI * w * w * w);                      // k, kernels.glsl:23
+	if (HK == 1) {                                                          // :104 + :86-88
+		float height = 0.6f / powf(w / 2.0f, D);
+		float iv = powf(height, 2.0f / D);
+		p.c0 = iv * APBF_PI;          // invDoubleVariance
+		p.c1 = powf(iv, D / 2.0f);    // normalisation
+	}
+	if (HK == 2) { p.c0 = w * w; p.c1 = 64.0f * APBF_PI * powf(w, 9.0f); } // :6,8
+	if (HK == 3) p.c0 = 3.0f / (APBF_PI * powf(w, D));                     // :50
+	if (HK == 4) p.c0 = (D == 3.0f) ? 15.0f / (2.0f * APBF_PI * powf(w, 5.0f)) : 6.0f / (APBF_PI * powf(w, 4.0f)); // :64-68
+	return p;
+}
+
+template <int GK>
+__device__ __forceinline__ kpar grad_params(float w, float D)
+{
+	kpar p; p.w = w; p.c0 = 0.f; p.c1 = 0.f;
+	if (GK == 0) p.c0 = 48.0f / (APBF_PI * w * w * w);                     // l, :39
+	if (GK == 1) {                                                          // :117 + :93-96 (+ :86-88 via gauss_kernel_height)
+		float height = 0.6f / powf(w / 2.0f, D);
+		float iv = powf(height, 2.0f / D);
+		p.c0 = iv * APBF_PI;
+		p.c1 = powf(iv, D / 2.0f);
+	}
+	if (GK == 2) p.c0 = APBF_PI * powf(w, 6.0f);                           // :15
+	if (GK == 3) p.c0 = 3.0f / (APBF_PI * powf(w, D + 1.0f));              // :56
+	if (GK == 4) p.c0 = (D == 3.0f) ? 15.0f / (2.0f * APBF_PI * powf(w, 5.0f)) : 6.0f / (APBF_PI * powf(w, 4.0f));
+	return p;
+}
+
+// ---- per-pair evaluation: r = diff vector, r2 = dot(r, r), dist = sqrt(r2) ---------------------------------------------
+template <int HK>
+__device__ __forceinline__ float kheight(const kpar& p, float r2, float dist)
+{
+	const float h = p.w;
+	if (HK == 0) { // cubic_kernel_height :18-31
+		if (dist > h) return 0.0f;
+		float q = dist / h;
+		if (q <= 0.5f) {
+			float q2 = q * q;
+			float q3 = q * q2;
+			return p.c0 * (6.0f * q3 - 6.0f * q2 + 1.0f);
+		}
+		return p.c0 * (2.0f * powf(1.0f - q, 3.0f));
+	}
+	if (HK == 1) return expf(-r2 * p.c0) * p.c1; // gauss_kernel_height :84-89
+	if (HK == 2) { // poly6 :3-9
+		if (r2 > p.c0) return 0.0f;
+		return 315.0f * powf(p.c0 - r2, 3.0f) / p.c1;
+	}
+	if (HK == 3) return glsl_max(0.0f, (1.0f - dist / h) * p.c0); // cone :48-52
+	if (HK == 4) return p.c0 * powf(glsl_min(0.0f, dist - h), 2.0f); // quadratic spike :62-70
+	return 0.0f;
+}
+
+template <int GK>
+__device__ __forceinline__ vec3f kgrad(const kpar& p, float rx, float ry, float rz, float r2, float dist)
+{
+	const float h = p.w;
+	vec3f o; o.x = 0.f; o.y = 0.f; o.z = 0.f;
+	if (GK == 0) { // cubic_kernel_gradient :33-46
+		if (dist > h || dist < 0.0001f) return o;
+		float q = dist / h;
+		float s = 1.0f / (dist * h);
+		float f;
+		if (q <= 0.5f) f = p.c0 * q * (3.0f * q - 2.0f);
+		else { float factor = 1.0f - q; f = p.c0 * (-factor * factor); }
+		o.x = f * (rx * s); o.y = f * (ry * s); o.z = f * (rz * s);
+		return o;
+	}
+	if (GK == 1) { // gauss_kernel_gradient :91-97
+		if (dist < 0.0001f) return o;
+		float W = expf(-r2 * p.c0) * p.c1;
+		float f = -W * 2.0f * dist * p.c0;
+		o.x = f * (rx / dist); o.y = f * (ry / dist); o.z = f * (rz / dist); // normalize(r) = r / length(r)
+		return o;
+	}
+	if (GK == 2) { // spiky_kernel_gradient :11-16
+		if (dist > h || dist < 0.0001f) return o;
+		float f = -45.0f * powf(h - dist, 2.0f) / p.c0;
+		o.x = f * (rx / dist); o.y = f * (ry / dist); o.z = f * (rz / dist);
+		return o;
+	}
+	if (GK == 3) { // cone_kernel_gradient :54-60
+		if (dist > h || dist < 0.0001f) return o;
+		float f = p.c0 / dist;
+		o.x = -rx * f; o.y = -ry * f; o.z = -rz * f;
+		return o;
+	}
+	if (GK == 4) { // quadratic_spike_kernel_gradient :72-82
+		if (dist > h || dist < 0.0001f) return o;
+		float f = -2.0f * p.c0 * glsl_max(0.0f, h - dist) / dist;
+		o.x = f * rx; o.y = f * ry; o.z = f * rz;
+		return o;
+	}
+	return o;
+}

@@ -1,0 +1,498 @@
+// neighbors.cu -- neighbour searches: uniform grid on the Z-curve hash (neighborhood_green) and 96-bit Morton code with
+// per-particle power-of-two cells (neighborhood_binary_search).
+//
+// Replaces source/neighborhood_green.cpp:27-77 and source/neighborhood_binary_search.cpp:22-75 with their shaders
+// (calculate_position_hash/_code, radix_sort_*, prefix_sum_*, copy_scattered_read, atomic_swap,
+// generate_new_index_and_edit_list, find_value_ranges, neighborhood_green, neighborhood_binary_search,
+// copy_with_differing_stride, linked_list_to_neighbor_list).
+//
+// Pipeline: key -> onesweep sort (key, slot) -> one fused gather of every hidden array -> index list / per-id arrays
+// follow -> cell ranges -> count / scan / fill.  The pair list comes out grouped by id in the reference's discovery
+// order, together with CSR offsets and one "mirrored" bit per pair that the solver sweeps use (solver.cu).
+#include "keys.cuh"
+#include "neighbors.cuh"
+#include "sort.cuh"
+
+namespace {
+
+// ---- fused reorder of all hidden arrays -------------------------------------------------------------------------------
+struct reorder_table {
+	int          n16, n4;
+	const int4*  src16[4];
+	int4*        dst16[4];
+	const uint32_t* src4[8];
+	uint32_t*    dst4[8];
+};
+
+__global__ void __launch_bounds__(256) k_reorder(reorder_table t, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ len)
+{
+	const uint32_t n = *len;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t s = perm[i];
+		int4 v16[4];
+		uint32_t v4[8];
+#pragma unroll
+		for (int a = 0; a < 4; a++) if (a < t.n16) v16[a] = __ldg(t.src16[a] + s);
+#pragma unroll
+		for (int a = 0; a < 8; a++) if (a < t.n4) v4[a] = __ldg(t.src4[a] + s);
+#pragma unroll
+		for (int a = 0; a < 4; a++) if (a < t.n16) t.dst16[a][i] = v16[a];
+#pragma unroll
+		for (int a = 0; a < 8; a++) if (a < t.n4) t.dst4[a][i] = v4[a];
+	}
+}
+
+// ---- index list after the hidden permutation (indexed_list.h:289-308 + :276-286 for a permutation edit) ------------------
+__global__ void k_mark_members(const uint32_t* __restrict__ index_list, const uint32_t* __restrict__ len, uint32_t* __restrict__ mark)
+{
+	const uint32_t n = *len;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mark[index_list[i]] = i + 1u;
+}
+
+__global__ void k_member_flags(const uint32_t* __restrict__ sorted_index, const uint32_t* __restrict__ mark,
+                               const uint32_t* __restrict__ hidden_len, uint32_t* __restrict__ flags)
+{
+	const uint32_t n = *hidden_len;
+	for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < n; h += gridDim.x * blockDim.x)
+		flags[h] = mark[sorted_index[h]] != 0u ? 1u : 0u;
+}
+
+__global__ void k_compact_members(const uint32_t* __restrict__ sorted_index, const uint32_t* __restrict__ mark,
+                                  const uint32_t* __restrict__ offs, const uint32_t* __restrict__ hidden_len,
+                                  const uint32_t* __restrict__ index_len, uint32_t* __restrict__ new_index_list,
+                                  uint32_t* __restrict__ id_perm, uint32_t index_cap, uint32_t* misc)
+{
+	const uint32_t n = *hidden_len;
+	for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < n; h += gridDim.x * blockDim.x) {
+		uint32_t m = mark[sorted_index[h]];
+		if (m != 0u) {
+			uint32_t o = offs[h];
+			if (o < index_cap) {
+				new_index_list[o] = h;
+				id_perm[o] = m - 1u;
+			}
+		}
+		if (h == 0) misc[MW_IDENTITY] = (offs[n] == n && *index_len == n) ? 1u : 0u;
+	}
+}
+
+struct gather_table {
+	int n4;
+	const uint32_t* src4[8];
+	uint32_t*       dst4[8];
+};
+
+__global__ void k_gather_ids(gather_table t, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ len)
+{
+	const uint32_t n = *len;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t s = perm[i];
+#pragma unroll
+		for (int a = 0; a < 8; a++) if (a < t.n4) t.dst4[a][i] = __ldg(t.src4[a] + s);
+	}
+}
+
+// ---- Green pair emit (neighborhood_green.comp:50-87) ----------------------------------------------------------------
+// One thread per particle.  FILL == false counts the accepted candidates, FILL == true writes them at the scanned offsets.
+__device__ __forceinline__ float dist_rn(float px, float py, float pz, float qx, float qy, float qz)
+{
+	// distance(pos, posN) = sqrt(dot(d, d)), d = pos - posN, unfused, left to right (oracle convention)
+	float dx = __fsub_rn(px, qx), dy = __fsub_rn(py, qy), dz = __fsub_rn(pz, qz);
+	float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+	return __fsqrt_rn(s);
+}
+
+struct sym_writer { // accumulates "mirrored" bits of one particle's segment and flushes whole words with atomicOr
+	uint32_t* bits;
+	uint32_t  word_idx, word;
+	__device__ __forceinline__ void begin(uint32_t* b, uint32_t first_bit) { bits = b; word_idx = first_bit >> 5; word = 0u; }
+	__device__ __forceinline__ void put(uint32_t bit_idx, bool v)
+	{
+		uint32_t w = bit_idx >> 5;
+		if (w != word_idx) { flush(); word_idx = w; }
+		if (v) word |= 1u << (bit_idx & 31u);
+	}
+	__device__ __forceinline__ void flush()
+	{
+		if (word) atomicOr(bits + word_idx, word);
+		word = 0u;
+	}
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_green_emit(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const float* __restrict__ range,
+             const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, const uint32_t* __restrict__ len,
+             apbf_grid_params g, float range_scale, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+             uint32_t* __restrict__ pairs, uint32_t cap, uint32_t* __restrict__ symbits, uint32_t* misc)
+{
+	const uint32_t n = *len;
+	const bool ident = misc[MW_IDENTITY] != 0u;
+	for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+		const float r = range[id] * range_scale;
+		const uint32_t idx = ident ? id : index_list[id];
+		const int4 ip = ldg_int4(pos4, idx);
+		const float px = (float)ip.x * INV_R_POS, py = (float)ip.y * INV_R_POS, pz = (float)ip.z * INV_R_POS;
+		uint32_t gmin[3], gmax[3];
+		gmin[0] = apbf_map_axis(px - r, g, 0); gmax[0] = apbf_map_axis(px + r, g, 0);
+		gmin[1] = apbf_map_axis(py - r, g, 1); gmax[1] = apbf_map_axis(py + r, g, 1);
+		gmin[2] = apbf_map_axis(pz - r, g, 2); gmax[2] = apbf_map_axis(pz + r, g, 2);
+		if (g.dims < 3) { gmin[2] = 0u; gmax[2] = 0u; } // * uvec3(1, D > 1, D > 2), neighborhood_green.comp:36
+		uint32_t cnt = 0, out = 0, n_asym = 0;
+		sym_writer sw;
+		if (FILL) { out = offsets[id]; sw.begin(symbits, out); }
+		for (uint32_t cz = gmin[2];; cz++) {
+			for (uint32_t cy = gmin[1];; cy++) {
+				for (uint32_t cx = gmin[0];; cx++) {
+					const uint32_t h = apbf_zhash(cx, cy, cz, g.res, g.dims);
+					const uint32_t s = __ldg(cell_start + h), e = __ldg(cell_end + h);
+					for (uint32_t idN = s; idN < e; idN++) {
+						const uint32_t idxN = ident ? idN : index_list[idN];
+						const int4 iq = ldg_int4(pos4, idxN);
+						const float d = dist_rn(px, py, pz, (float)iq.x * INV_R_POS, (float)iq.y * INV_R_POS, (float)iq.z * INV_R_POS);
+						if (id == idN || d > r) continue;
+						if (FILL) {
+							const uint32_t o = out + cnt;
+							if (o < cap) {
+								*(uint2*)(pairs + 2 * (size_t)o) = make_uint2(id, idN);
+								const bool mirrored = !(d > range[idN] * range_scale); // (idN, id) is in the list too
+								sw.put(o, mirrored);
+								n_asym += mirrored ? 0u : 1u;
+							}
+						}
+						cnt++;
+					}
+					if (cx >= gmax[0]) break;
+				}
+				if (cy >= gmax[1]) break;
+			}
+			if (cz >= gmax[2]) break;
+		}
+		if (FILL) {
+			sw.flush();
+			if (n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
+		} else {
+			counts[id] = cnt;
+		}
+	}
+}
+
+// ---- binary-search pair emit (neighborhood_binary_search.comp:166-276) ----------------------------------------------
+struct u96 { uint32_t v[3]; };
+__device__ __forceinline__ u96 mk96(uint32_t a, uint32_t b, uint32_t c) { u96 r; r.v[0] = a; r.v[1] = b; r.v[2] = c; return r; }
+__device__ __forceinline__ u96 plus96(u96 a, u96 b)
+{
+	u96 r = mk96(a.v[0] + b.v[0], a.v[1] + b.v[1], a.v[2] + b.v[2]);
+	bool y = r.v[0] < a.v[0];
+	bool z = r.v[1] < a.v[1] || (y && r.v[1] == 0xFFFFFFFFu);
+	r.v[1] += y ? 1u : 0u; r.v[2] += z ? 1u : 0u;
+	return r;
+}
+__device__ __forceinline__ u96 minus96(u96 a, u96 b)
+{
+	bool y = a.v[0] < b.v[0];
+	bool z = a.v[1] < b.v[1] || (y && a.v[1] == b.v[1]);
+	return mk96(a.v[0] - b.v[0], a.v[1] - b.v[1] - (y ? 1u : 0u), a.v[2] - b.v[2] - (z ? 1u : 0u));
+}
+__device__ __forceinline__ u96 shl96_small(u96 a, uint32_t s) // s in {1, 2}
+{
+	return mk96(a.v[0] << s, (a.v[1] << s) | (a.v[0] >> (32u - s)), (a.v[2] << s) | (a.v[1] >> (32u - s)));
+}
+__device__ __forceinline__ bool greater96(u96 a, u96 b)
+{
+	if (a.v[2] != b.v[2]) return a.v[2] > b.v[2];
+	if (a.v[1] != b.v[1]) return a.v[1] > b.v[1];
+	return a.v[0] > b.v[0];
+}
+__device__ __forceinline__ u96 and96(u96 a, u96 b) { return mk96(a.v[0] & b.v[0], a.v[1] & b.v[1], a.v[2] & b.v[2]); }
+__device__ __forceinline__ u96 or96(u96 a, u96 b) { return mk96(a.v[0] | b.v[0], a.v[1] | b.v[1], a.v[2] | b.v[2]); }
+__device__ __forceinline__ u96 not96(u96 a) { return mk96(~a.v[0], ~a.v[1], ~a.v[2]); }
+
+__device__ __forceinline__ uint32_t lower_bound96(const uint32_t* __restrict__ c0, const uint32_t* __restrict__ c1,
+                                                  const uint32_t* __restrict__ c2, uint32_t n, u96 code)
+{
+	uint32_t lo = 0u, hi = n;
+	while (lo < hi) {
+		uint32_t mid = lo + ((hi - lo) >> 1);
+		if (greater96(code, mk96(__ldg(c0 + mid), __ldg(c1 + mid), __ldg(c2 + mid)))) lo = mid + 1u; else hi = mid;
+	}
+	return lo;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_bsearch_emit(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const uint32_t* __restrict__ c0,
+               const uint32_t* __restrict__ c1, const uint32_t* __restrict__ c2, const float* __restrict__ range,
+               const uint32_t* __restrict__ len, float range_scale, uint32_t* __restrict__ counts,
+               const uint32_t* __restrict__ offsets, uint32_t* __restrict__ pairs, uint32_t cap, uint32_t* __restrict__ symbits,
+               uint32_t* misc)
+{
+	const uint32_t n = *len;
+	const bool ident = misc[MW_IDENTITY] != 0u;
+	const u96 xMask3 = mk96(011111111111u, 022222222222u, 04444444444u);
+	const u96 yMask3 = mk96(022222222222u, 04444444444u, 011111111111u);
+	const u96 zMask3 = mk96(04444444444u, 011111111111u, 022222222222u);
+	for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+		const float r = range[id] * range_scale;
+		const uint32_t idx = ident ? id : index_list[id];
+		const int4 ip = ldg_int4(pos4, idx);
+		u96 code;
+		apbf_encode96(ip.x, ip.y, ip.z, code.v);
+		const uint32_t digits = f2u(ceilf(log2f(r * R_POS))) * 3u; // :183
+		u96 mask;
+		mask.v[0] = (digits < 32u ? 1u << digits : 0u) - 1u;
+		mask.v[1] = (digits < 64u ? 1u << (max(digits, 32u) - 32u) : 0u) - 1u;
+		mask.v[2] = (digits < 96u ? 1u << (max(digits, 64u) - 64u) : 0u) - 1u;
+		const u96 center = mk96(code.v[0] - (code.v[0] & mask.v[0]), code.v[1] - (code.v[1] & mask.v[1]), code.v[2] - (code.v[2] & mask.v[2]));
+		const u96 step = plus96(mask, mk96(1u, 0u, 0u));
+		u96 xs[3], ys[3], zs[3];
+		xs[0] = and96(minus96(and96(center, xMask3), step), xMask3);
+		xs[2] = and96(plus96(or96(center, not96(xMask3)), step), xMask3);
+		ys[0] = and96(minus96(and96(center, yMask3), shl96_small(step, 1u)), yMask3);
+		ys[2] = and96(plus96(or96(center, not96(yMask3)), shl96_small(step, 1u)), yMask3);
+		zs[0] = and96(minus96(and96(center, zMask3), shl96_small(step, 2u)), zMask3);
+		zs[2] = and96(plus96(or96(center, not96(zMask3)), shl96_small(step, 2u)), zMask3);
+		xs[1] = and96(center, xMask3);
+		ys[1] = and96(center, yMask3);
+		zs[1] = and96(center, zMask3);
+		const float px = (float)ip.x * INV_R_POS, py = (float)ip.y * INV_R_POS, pz = (float)ip.z * INV_R_POS;
+		uint32_t cnt = 0, out = 0, n_asym = 0;
+		sym_writer sw;
+		if (FILL) { out = offsets[id]; sw.begin(symbits, out); }
+		for (int cz = 0; cz < 3; cz++) for (int cy = 0; cy < 3; cy++) for (int cx = 0; cx < 3; cx++) {
+			const u96 cellCode = or96(or96(xs[cx], ys[cy]), zs[cz]);
+			const u96 cellLast = or96(cellCode, mask);
+			for (uint32_t idN = lower_bound96(c0, c1, c2, n, cellCode); idN < n; idN++) {
+				if (greater96(mk96(__ldg(c0 + idN), __ldg(c1 + idN), __ldg(c2 + idN)), cellLast)) break;
+				const uint32_t idxN = ident ? idN : index_list[idN];
+				const int4 iq = ldg_int4(pos4, idxN);
+				const float d = dist_rn(px, py, pz, (float)iq.x * INV_R_POS, (float)iq.y * INV_R_POS, (float)iq.z * INV_R_POS);
+				if (id != idN && d <= r) {
+					if (FILL) {
+						const uint32_t o = out + cnt;
+						if (o < cap) {
+							*(uint2*)(pairs + 2 * (size_t)o) = make_uint2(id, idN);
+							const bool mirrored = d <= range[idN] * range_scale;
+							sw.put(o, mirrored);
+							n_asym += mirrored ? 0u : 1u;
+						}
+					}
+					cnt++;
+				}
+			}
+		}
+		if (FILL) {
+			sw.flush();
+			if (n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
+		} else {
+			counts[id] = cnt;
+		}
+	}
+}
+
+__global__ void k_clear_search_words(uint32_t* misc) { misc[MW_N_ASYM] = 0u; misc[MW_TOTAL_PAIRS] = 0u; misc[MW_KEPT_PAIRS] = 0xFFFFFFFFu; }
+
+// shared front half of both searches: gather hidden arrays by sorted_index, rebuild the index list, gather per-id arrays
+int reorder_lists(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, const uint32_t* sorted_index)
+{
+	apbf_particles& p = fluid->particle;
+	cudaStream_t st = ctx->stream;
+	const uint32_t nh_cap = p.hidden_capacity, n_cap = p.capacity;
+	reorder_table t;
+	memset(&t, 0, sizeof t);
+	const apbf_array* a16[3] = { &p.position, &p.velocity, &p.pos_backup };
+	const apbf_array* a4[3] = { &p.inverse_mass, &p.radius, &p.transferring };
+	for (auto a : a16) {
+		APBF_REQUIRE(ctx, a->data && a->reorder_out && a->data != a->reorder_out);
+		t.src16[t.n16] = (const int4*)a->data; t.dst16[t.n16] = (int4*)a->reorder_out; t.n16++;
+	}
+	for (auto a : a4) {
+		APBF_REQUIRE(ctx, a->data && a->reorder_out && a->data != a->reorder_out);
+		t.src4[t.n4] = (const uint32_t*)a->data; t.dst4[t.n4] = (uint32_t*)a->reorder_out; t.n4++;
+	}
+	k_reorder<<<apbf_grid(ctx, nh_cap, 256), 256, 0, st>>>(t, sorted_index, p.hidden_length);
+	APBF_LAUNCHED(ctx);
+
+	// index list and the permutation of the ids
+	APBF_REQUIRE(ctx, p.index_list.data && p.index_list.reorder_out && p.index_list.data != p.index_list.reorder_out);
+	uint32_t* mark = (uint32_t*)ctx->scratch_get(SLOT_INV_PERM, sizeof(uint32_t) * (size_t)nh_cap);
+	uint32_t* flags = (uint32_t*)ctx->scratch_get(SLOT_HIDDEN_FLAGS, sizeof(uint32_t) * (size_t)(nh_cap + 1));
+	uint32_t* offs = (uint32_t*)ctx->scratch_get(SLOT_HIDDEN_OFFS, sizeof(uint32_t) * (size_t)(nh_cap + 1));
+	uint32_t* id_perm = (uint32_t*)ctx->scratch_get(SLOT_TMP_VALS2, sizeof(uint32_t) * (size_t)n_cap);
+	if (!mark || !flags || !offs || !id_perm) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+	APBF_CUDA(ctx, cudaMemsetAsync(mark, 0, sizeof(uint32_t) * (size_t)nh_cap, st));
+	k_mark_members<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>((const uint32_t*)p.index_list.data, p.length, mark);
+	APBF_LAUNCHED(ctx);
+	k_member_flags<<<apbf_grid(ctx, nh_cap, 256), 256, 0, st>>>(sorted_index, mark, p.hidden_length, flags);
+	APBF_LAUNCHED(ctx);
+	APBF_TRY(apbf_scan_u32(ctx, flags, offs, p.hidden_length, nh_cap, false, nullptr, 0xFFFFFFFFu, nullptr, nullptr));
+	k_compact_members<<<apbf_grid(ctx, nh_cap, 256), 256, 0, st>>>(sorted_index, mark, offs, p.hidden_length, p.length,
+	                                                               (uint32_t*)p.index_list.reorder_out, id_perm, n_cap, ctx->misc());
+	APBF_LAUNCHED(ctx);
+
+	gather_table gt;
+	memset(&gt, 0, sizeof gt);
+	const apbf_array* ids[5] = { &fluid->target_radius, &fluid->kernel_width, &fluid->boundariness, &fluid->boundary_distance, range };
+	for (int i = 0; i < 5; i++) {
+		const apbf_array* a = ids[i];
+		if (!a || !a->data) continue;
+		bool dup = false;
+		for (int j = 0; j < gt.n4; j++) dup = dup || gt.src4[j] == (const uint32_t*)a->data;
+		if (dup) continue;
+		APBF_REQUIRE(ctx, a->reorder_out && a->data != a->reorder_out);
+		gt.src4[gt.n4] = (const uint32_t*)a->data; gt.dst4[gt.n4] = (uint32_t*)a->reorder_out; gt.n4++;
+	}
+	if (gt.n4 > 0) {
+		k_gather_ids<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>(gt, id_perm, p.length);
+		APBF_LAUNCHED(ctx);
+	}
+	return APBF_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb,
+                                  float range_scale, const float min_pos[3], const float max_pos[3], uint32_t res_log2,
+                                  const apbf_search_debug* dbg)
+{
+	if (!ctx) return APBF_ERR_INVALID;
+	APBF_REQUIRE(ctx, fluid && range && nb && min_pos && max_pos);
+	APBF_REQUIRE(ctx, nb->pairs && nb->length && fluid->particle.length && fluid->particle.hidden_length);
+	apbf_particles& p = fluid->particle;
+	cudaStream_t st = ctx->stream;
+	const uint32_t nh_cap = p.hidden_capacity, n_cap = p.capacity;
+	if (nh_cap == 0 || n_cap == 0) { APBF_CUDA(ctx, cudaMemsetAsync(nb->length, 0, 4, st)); return APBF_OK; }
+	apbf_grid_params g;
+	APBF_TRY(apbf_make_grid_params(ctx, min_pos, max_pos, res_log2, &g));
+	const uint32_t max_hash = 1u << (res_log2 * (uint32_t)ctx->dims); // neighborhood_green.cpp:31
+	uint32_t* misc = ctx->misc();
+
+	uint32_t* keys = (uint32_t*)ctx->scratch_get(SLOT_SORT_KEYS_A, sizeof(uint32_t) * (size_t)nh_cap);
+	uint32_t* skeys = (uint32_t*)ctx->scratch_get(SLOT_TMP_KEYS, sizeof(uint32_t) * (size_t)nh_cap);
+	uint32_t* sidx = (uint32_t*)ctx->scratch_get(SLOT_TMP_VALS, sizeof(uint32_t) * (size_t)nh_cap);
+	uint32_t* cs = (uint32_t*)ctx->scratch_get(SLOT_CELL_START, sizeof(uint32_t) * (size_t)max_hash);
+	uint32_t* ce = (uint32_t*)ctx->scratch_get(SLOT_CELL_END, sizeof(uint32_t) * (size_t)max_hash);
+	uint32_t* counts = (uint32_t*)ctx->scratch_get(SLOT_COUNTS, sizeof(uint32_t) * (size_t)(n_cap + 1));
+	uint32_t* offsets = (uint32_t*)ctx->scratch_get(SLOT_OFFSETS, sizeof(uint32_t) * (size_t)(n_cap + 1));
+	const size_t sym_words = ((size_t)nb->capacity + 31) / 32 + 1;
+	uint32_t* symbits = (uint32_t*)ctx->scratch_get(SLOT_SYMBITS, sizeof(uint32_t) * sym_words);
+	if (!keys || !skeys || !sidx || !cs || !ce || !counts || !offsets || !symbits || !misc)
+		return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+
+	// hash all hidden particles (neighborhood_green.cpp:50-52), sort by hash with the slot as payload (:53)
+	{
+		apbf_prof_scope ps(ctx, PROF_HASH_SORT);
+		APBF_TRY(apbf_launch_position_hash(ctx, (const int32_t*)p.position.data, keys, p.hidden_length, nh_cap, g));
+		APBF_TRY(apbf_radix_sort_pairs(ctx, keys, nullptr, skeys, sidx, p.hidden_length, nh_cap, apbf_reference_sort_bits(max_hash)));
+	}
+	// permute hidden arrays, index list and per-id arrays (:54-56)
+	{
+		apbf_prof_scope ps(ctx, PROF_REORDER);
+		APBF_TRY(reorder_lists(ctx, fluid, range, sidx));
+	}
+	const uint32_t* new_index = (const uint32_t*)p.index_list.reorder_out;
+	const int32_t* new_pos = (const int32_t*)p.position.reorder_out;
+	const float* new_range = (const float*)range->reorder_out;
+	// cell ranges (:58-63)
+	{
+		apbf_prof_scope ps(ctx, PROF_CELL_RANGES);
+		APBF_TRY(apbf_launch_find_value_ranges(ctx, new_index, skeys, cs, ce, p.length, n_cap, max_hash));
+	}
+	// pairs (:64-74): count, scan, fill
+	k_clear_search_words<<<1, 1, 0, st>>>(misc);
+	APBF_LAUNCHED(ctx);
+	const unsigned grid = apbf_grid(ctx, n_cap, 128, 16);
+	{
+		apbf_prof_scope ps(ctx, PROF_EMIT_COUNT);
+		k_green_emit<false><<<grid, 128, 0, st>>>(new_index, new_pos, new_range, cs, ce, p.length, g, range_scale, counts, nullptr,
+		                                          nullptr, 0u, nullptr, misc);
+		APBF_LAUNCHED(ctx);
+	}
+	{
+		apbf_prof_scope ps(ctx, PROF_EMIT_SCAN);
+		APBF_TRY(apbf_scan_u32(ctx, counts, offsets, p.length, n_cap, false, nb->length, nb->capacity, misc + MW_FLAGS, misc + MW_TOTAL_PAIRS));
+		APBF_CUDA(ctx, cudaMemsetAsync(symbits, 0, sizeof(uint32_t) * sym_words, st));
+	}
+	{
+		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
+		k_green_emit<true><<<grid, 128, 0, st>>>(new_index, new_pos, new_range, cs, ce, p.length, g, range_scale, nullptr, offsets,
+		                                         nb->pairs, nb->capacity, symbits, misc);
+		APBF_LAUNCHED(ctx);
+	}
+	ctx->nbr_struct_pairs = nb->pairs;
+	ctx->nbr_struct_n_cap = n_cap;
+
+	if (dbg) {
+		if (dbg->sorted_key) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->sorted_key, skeys, sizeof(uint32_t) * (size_t)nh_cap, cudaMemcpyDeviceToDevice, st));
+		if (dbg->sorted_index) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->sorted_index, sidx, sizeof(uint32_t) * (size_t)nh_cap, cudaMemcpyDeviceToDevice, st));
+		if (dbg->cell_start) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->cell_start, cs, sizeof(uint32_t) * (size_t)max_hash, cudaMemcpyDeviceToDevice, st));
+		if (dbg->cell_end) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->cell_end, ce, sizeof(uint32_t) * (size_t)max_hash, cudaMemcpyDeviceToDevice, st));
+	}
+	return APBF_OK;
+}
+
+int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb,
+                                          float range_scale, const apbf_search_debug* dbg)
+{
+	if (!ctx) return APBF_ERR_INVALID;
+	APBF_REQUIRE(ctx, fluid && range && nb);
+	APBF_REQUIRE(ctx, nb->pairs && nb->length && fluid->particle.length && fluid->particle.hidden_length);
+	apbf_particles& p = fluid->particle;
+	cudaStream_t st = ctx->stream;
+	const uint32_t nh_cap = p.hidden_capacity, n_cap = p.capacity;
+	if (nh_cap == 0 || n_cap == 0) { APBF_CUDA(ctx, cudaMemsetAsync(nb->length, 0, 4, st)); return APBF_OK; }
+	uint32_t* misc = ctx->misc();
+	uint32_t* code = (uint32_t*)ctx->scratch_get(SLOT_SORT_KEYS_A, sizeof(uint32_t) * (size_t)nh_cap);
+	uint32_t* scode = (uint32_t*)ctx->scratch_get(SLOT_TMP_KEYS, sizeof(uint32_t) * (size_t)nh_cap);
+	uint32_t* idx_a = (uint32_t*)ctx->scratch_get(SLOT_TMP_VALS, sizeof(uint32_t) * (size_t)nh_cap);
+	uint32_t* idx_b = (uint32_t*)ctx->scratch_get(SLOT_SORT_VALS_A, sizeof(uint32_t) * (size_t)nh_cap);
+	uint32_t* c[3] = { (uint32_t*)ctx->scratch_get(SLOT_CODE0, sizeof(uint32_t) * (size_t)nh_cap),
+	                   (uint32_t*)ctx->scratch_get(SLOT_CODE1, sizeof(uint32_t) * (size_t)nh_cap),
+	                   (uint32_t*)ctx->scratch_get(SLOT_CODE2, sizeof(uint32_t) * (size_t)nh_cap) };
+	uint32_t* counts = (uint32_t*)ctx->scratch_get(SLOT_COUNTS, sizeof(uint32_t) * (size_t)(n_cap + 1));
+	uint32_t* offsets = (uint32_t*)ctx->scratch_get(SLOT_OFFSETS, sizeof(uint32_t) * (size_t)(n_cap + 1));
+	const size_t sym_words = ((size_t)nb->capacity + 31) / 32 + 1;
+	uint32_t* symbits = (uint32_t*)ctx->scratch_get(SLOT_SYMBITS, sizeof(uint32_t) * sym_words);
+	if (!code || !scode || !idx_a || !idx_b || !c[0] || !c[1] || !c[2] || !counts || !offsets || !symbits || !misc)
+		return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+
+	// three stable 32-bit sorts, least significant section first (neighborhood_binary_search.cpp:45-51)
+	const uint32_t* cur = nullptr; // nullptr == identity payload
+	uint32_t* ping[2] = { idx_a, idx_b };
+	for (uint32_t sec = 0; sec < 3u; sec++) {
+		APBF_TRY(apbf_launch_position_code(ctx, cur, (const int32_t*)p.position.data, code, p.hidden_length, nh_cap, sec));
+		uint32_t* dst = ping[sec & 1u];
+		APBF_TRY(apbf_radix_sort_pairs(ctx, code, cur, scode, dst, p.hidden_length, nh_cap, 32));
+		cur = dst;
+	}
+	const uint32_t* sidx = cur;
+	APBF_TRY(reorder_lists(ctx, fluid, range, sidx)); // :53-54
+	const uint32_t* new_index = (const uint32_t*)p.index_list.reorder_out;
+	const int32_t* new_pos = (const int32_t*)p.position.reorder_out;
+	const float* new_range = (const float*)range->reorder_out;
+	for (uint32_t sec = 0; sec < 3u; sec++) // :58-60
+		APBF_TRY(apbf_launch_position_code(ctx, new_index, new_pos, c[sec], p.length, n_cap, sec));
+	k_clear_search_words<<<1, 1, 0, st>>>(misc);
+	APBF_LAUNCHED(ctx);
+	const unsigned grid = apbf_grid(ctx, n_cap, 128, 16);
+	k_bsearch_emit<false><<<grid, 128, 0, st>>>(new_index, new_pos, c[0], c[1], c[2], new_range, p.length, range_scale, counts,
+	                                            nullptr, nullptr, 0u, nullptr, misc);
+	APBF_LAUNCHED(ctx);
+	APBF_TRY(apbf_scan_u32(ctx, counts, offsets, p.length, n_cap, false, nb->length, nb->capacity, misc + MW_FLAGS, misc + MW_TOTAL_PAIRS));
+	APBF_CUDA(ctx, cudaMemsetAsync(symbits, 0, sizeof(uint32_t) * sym_words, st));
+	k_bsearch_emit<true><<<grid, 128, 0, st>>>(new_index, new_pos, c[0], c[1], c[2], new_range, p.length, range_scale, nullptr,
+	                                           offsets, nb->pairs, nb->capacity, symbits, misc);
+	APBF_LAUNCHED(ctx);
+	ctx->nbr_struct_pairs = nb->pairs;
+	ctx->nbr_struct_n_cap = n_cap;
+	if (dbg) {
+		if (dbg->sorted_index) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->sorted_index, sidx, sizeof(uint32_t) * (size_t)nh_cap, cudaMemcpyDeviceToDevice, st));
+		for (int s = 0; s < 3; s++)
+			if (dbg->code[s]) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->code[s], c[s], sizeof(uint32_t) * (size_t)n_cap, cudaMemcpyDeviceToDevice, st));
+	}
+	return APBF_OK;
+}
+
+} // extern "C"

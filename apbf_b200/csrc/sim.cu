@@ -1,0 +1,228 @@
+// sim.cu -- a whole scene resident in HBM and one substep in the reference's order (source/pool.cpp:67-106):
+//   [velocity_handling] -> neighbour search -> [spread_kernel_width] -> solverIterations x (box_collision, incompressibility)
+// plus host <-> device transfer of the lists (the reference-facing call with host buffers).
+#include "common.cuh"
+
+struct apbf_sim {
+	apbf_ctx*       ctx;
+	apbf_sim_config cfg;
+	apbf_fluid      fluid;
+	apbf_neighbors  nb;
+	float*          boxes;    // [2 * n_boxes * 4]
+	float           last_dt;  // velocity_handling::mLastDeltaTime (velocity_handling.h:18)
+	std::vector<void*> owned;
+};
+
+namespace {
+
+int alloc_array(apbf_sim* sim, apbf_array* a, size_t bytes)
+{
+	for (void** p : { &a->data, &a->reorder_out }) {
+		if (cudaMalloc(p, bytes ? bytes : 16) != cudaSuccess) return apbf_fail(sim->ctx, APBF_ERR_OOM, "cudaMalloc", __FILE__, __LINE__);
+		cudaMemsetAsync(*p, 0, bytes ? bytes : 16, sim->ctx->stream);
+		sim->owned.push_back(*p);
+	}
+	return APBF_OK;
+}
+
+void swap_array(apbf_array* a)
+{
+	void* t = a->data; a->data = a->reorder_out; a->reorder_out = t;
+}
+
+void swap_after_search(apbf_sim* sim)
+{
+	apbf_fluid& f = sim->fluid;
+	apbf_array* all[] = { &f.particle.index_list, &f.particle.position, &f.particle.velocity, &f.particle.inverse_mass,
+	                      &f.particle.radius, &f.particle.pos_backup, &f.particle.transferring, &f.target_radius,
+	                      &f.kernel_width, &f.boundariness, &f.boundary_distance };
+	for (apbf_array* a : all) swap_array(a);
+}
+
+__global__ void k_set_lengths(uint32_t* a, uint32_t* b, uint32_t n) { *a = n; *b = n; }
+
+} // namespace
+
+extern "C" {
+
+int apbf_sim_create(apbf_ctx* ctx, const apbf_sim_config* cfg, apbf_sim** out_sim)
+{
+	if (!ctx || !cfg || !out_sim) return APBF_ERR_INVALID;
+	APBF_REQUIRE(ctx, cfg->dims == 2 || cfg->dims == 3);
+	APBF_REQUIRE(ctx, cfg->n_boxes <= 64 && (cfg->n_boxes == 0 || (cfg->box_min4_host && cfg->box_max4_host)));
+	*out_sim = nullptr;
+	apbf_sim* sim = new apbf_sim();
+	sim->ctx = ctx;
+	sim->cfg = *cfg;
+	sim->last_dt = 1.0f;
+	sim->boxes = nullptr;
+	memset(&sim->fluid, 0, sizeof sim->fluid);
+	memset(&sim->nb, 0, sizeof sim->nb);
+	const size_t n = cfg->particle_capacity;
+	apbf_particles& p = sim->fluid.particle;
+	p.capacity = p.hidden_capacity = cfg->particle_capacity;
+	int rc = APBF_OK;
+	rc = rc ? rc : alloc_array(sim, &p.index_list, 4 * n);
+	rc = rc ? rc : alloc_array(sim, &p.position, 16 * n);
+	rc = rc ? rc : alloc_array(sim, &p.velocity, 16 * n);
+	rc = rc ? rc : alloc_array(sim, &p.inverse_mass, 4 * n);
+	rc = rc ? rc : alloc_array(sim, &p.radius, 4 * n);
+	rc = rc ? rc : alloc_array(sim, &p.pos_backup, 16 * n);
+	rc = rc ? rc : alloc_array(sim, &p.transferring, 4 * n);
+	rc = rc ? rc : alloc_array(sim, &sim->fluid.target_radius, 4 * n);
+	rc = rc ? rc : alloc_array(sim, &sim->fluid.kernel_width, 4 * n);
+	rc = rc ? rc : alloc_array(sim, &sim->fluid.boundariness, 4 * n);
+	rc = rc ? rc : alloc_array(sim, &sim->fluid.boundary_distance, 4 * n);
+	void* words = nullptr;
+	if (!rc && cudaMalloc(&words, 64) != cudaSuccess) rc = APBF_ERR_OOM;
+	if (!rc) {
+		sim->owned.push_back(words);
+		cudaMemsetAsync(words, 0, 64, ctx->stream);
+		p.length = (uint32_t*)words;
+		p.hidden_length = (uint32_t*)words + 1;
+		sim->nb.length = (uint32_t*)words + 2;
+		sim->nb.capacity = cfg->neighbor_capacity;
+		void* pairs = nullptr;
+		if (cudaMalloc(&pairs, 8 * (size_t)(cfg->neighbor_capacity ? cfg->neighbor_capacity : 1)) != cudaSuccess) rc = APBF_ERR_OOM;
+		else { sim->owned.push_back(pairs); sim->nb.pairs = (uint32_t*)pairs; }
+	}
+	if (!rc && cfg->n_boxes) {
+		void* b = nullptr;
+		if (cudaMalloc(&b, 32 * (size_t)cfg->n_boxes) != cudaSuccess) rc = APBF_ERR_OOM;
+		else {
+			sim->owned.push_back(b);
+			sim->boxes = (float*)b;
+			cudaMemcpyAsync(sim->boxes, cfg->box_min4_host, 16 * (size_t)cfg->n_boxes, cudaMemcpyHostToDevice, ctx->stream);
+			cudaMemcpyAsync(sim->boxes + 4 * (size_t)cfg->n_boxes, cfg->box_max4_host, 16 * (size_t)cfg->n_boxes, cudaMemcpyHostToDevice, ctx->stream);
+			cudaStreamSynchronize(ctx->stream); // the host box arrays need not outlive this call
+		}
+	}
+	sim->cfg.box_min4_host = sim->cfg.box_max4_host = nullptr;
+	if (rc) { apbf_sim_destroy(sim); return apbf_fail(ctx, rc, "sim allocation failed", __FILE__, __LINE__); }
+	*out_sim = sim;
+	return APBF_OK;
+}
+
+void apbf_sim_destroy(apbf_sim* sim)
+{
+	if (!sim) return;
+	cudaStreamSynchronize(sim->ctx->stream);
+	for (void* p : sim->owned) cudaFree(p);
+	if (sim->ctx->nbr_struct_pairs == sim->nb.pairs) sim->ctx->nbr_struct_pairs = nullptr;
+	delete sim;
+}
+
+int apbf_sim_upload(apbf_sim* sim, const apbf_host_state* h)
+{
+	if (!sim || !h) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	APBF_REQUIRE(ctx, h->n <= sim->cfg.particle_capacity);
+	cudaStream_t st = ctx->stream;
+	apbf_fluid& f = sim->fluid;
+	const size_t n = h->n;
+	struct { const void* src; void* dst; size_t stride; } items[] = {
+		{ h->position, f.particle.position.data, 16 }, { h->velocity, f.particle.velocity.data, 16 },
+		{ h->inverse_mass, f.particle.inverse_mass.data, 4 }, { h->radius, f.particle.radius.data, 4 },
+		{ h->pos_backup, f.particle.pos_backup.data, 16 }, { h->transferring, f.particle.transferring.data, 4 },
+		{ h->target_radius, f.target_radius.data, 4 }, { h->kernel_width, f.kernel_width.data, 4 },
+		{ h->boundariness, f.boundariness.data, 4 }, { h->boundary_distance, f.boundary_distance.data, 4 },
+		{ h->index_list, f.particle.index_list.data, 4 },
+	};
+	for (auto& it : items)
+		if (it.src && n) APBF_CUDA(ctx, cudaMemcpyAsync(it.dst, it.src, it.stride * n, cudaMemcpyHostToDevice, st));
+	k_set_lengths<<<1, 1, 0, st>>>(f.particle.length, f.particle.hidden_length, (uint32_t)n);
+	APBF_LAUNCHED(ctx);
+	if (!h->index_list) APBF_TRY(apbf_write_sequence(ctx, (uint32_t*)f.particle.index_list.data, f.particle.length, sim->cfg.particle_capacity, 0u, 1u, 1u));
+	return APBF_OK;
+}
+
+int apbf_sim_download(apbf_sim* sim, apbf_host_state* h)
+{
+	if (!sim || !h) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	cudaStream_t st = ctx->stream;
+	apbf_fluid& f = sim->fluid;
+	uint32_t n = 0;
+	APBF_CUDA(ctx, cudaMemcpyAsync(&n, f.particle.length, 4, cudaMemcpyDeviceToHost, st));
+	APBF_CUDA(ctx, cudaStreamSynchronize(st));
+	h->n = n;
+	struct { void* dst; const void* src; size_t stride; } items[] = {
+		{ h->position, f.particle.position.data, 16 }, { h->velocity, f.particle.velocity.data, 16 },
+		{ h->inverse_mass, f.particle.inverse_mass.data, 4 }, { h->radius, f.particle.radius.data, 4 },
+		{ h->pos_backup, f.particle.pos_backup.data, 16 }, { h->transferring, f.particle.transferring.data, 4 },
+		{ h->target_radius, f.target_radius.data, 4 }, { h->kernel_width, f.kernel_width.data, 4 },
+		{ h->boundariness, f.boundariness.data, 4 }, { h->boundary_distance, f.boundary_distance.data, 4 },
+		{ h->index_list, f.particle.index_list.data, 4 },
+	};
+	for (auto& it : items)
+		if (it.dst && n) APBF_CUDA(ctx, cudaMemcpyAsync(it.dst, it.src, it.stride * (size_t)n, cudaMemcpyDeviceToHost, st));
+	APBF_CUDA(ctx, cudaStreamSynchronize(st));
+	return APBF_OK;
+}
+
+int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
+{
+	if (!sim) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	const apbf_sim_config& c = sim->cfg;
+	APBF_TRY(apbf_ctx_set_dimensions(ctx, c.dims));
+	const apbf_settings& s = ctx->settings;
+	const bool unit_scale = c.basic_pbf || s.mBaseKernelWidthOnBoundaryDistance;     // pool.cpp:83
+	const bool adaptive = !c.basic_pbf && !s.mBaseKernelWidthOnBoundaryDistance;     // pool.cpp:87
+	for (uint32_t step = 0; step < n_substeps; step++) {
+		if (c.integrate) {                                                            // pool.cpp:71
+			APBF_TRY(apbf_velocity_handling_apply(ctx, &sim->fluid.particle, c.dt, sim->last_dt, c.accel));
+			sim->last_dt = c.dt;
+		}
+		const float scale = unit_scale ? 1.0f : 1.5f;
+		if (c.use_binary_search)                                                      // pool.cpp:83-84
+			APBF_TRY(apbf_neighborhood_binary_search_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, nullptr));
+		else
+			APBF_TRY(apbf_neighborhood_green_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, nullptr));
+		swap_after_search(sim);
+		if (adaptive) APBF_TRY(apbf_spread_kernel_width_apply(ctx, &sim->fluid, &sim->nb, nullptr)); // pool.cpp:87-89
+		for (int it = 0; it < c.solver_iterations; it++) {                           // pool.cpp:92-95
+			APBF_TRY(apbf_box_collision_apply(ctx, &sim->fluid.particle, sim->boxes, sim->boxes ? sim->boxes + 4 * (size_t)c.n_boxes : nullptr, c.n_boxes));
+			APBF_TRY(apbf_incompressibility_apply(ctx, &sim->fluid, &sim->nb, nullptr, nullptr));
+		}
+	}
+	return APBF_OK;
+}
+
+int apbf_sim_fluid(apbf_sim* sim, apbf_fluid* out)
+{
+	if (!sim || !out) return APBF_ERR_INVALID;
+	*out = sim->fluid;
+	return APBF_OK;
+}
+
+int apbf_sim_neighbors(apbf_sim* sim, apbf_neighbors* out)
+{
+	if (!sim || !out) return APBF_ERR_INVALID;
+	*out = sim->nb;
+	return APBF_OK;
+}
+
+int apbf_sim_stats(apbf_sim* sim, uint32_t out[4])
+{
+	if (!sim || !out) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	uint32_t words[8];
+	APBF_CUDA(ctx, cudaMemcpyAsync(words, ctx->misc(), sizeof words, cudaMemcpyDeviceToHost, ctx->stream));
+	APBF_CUDA(ctx, cudaMemcpyAsync(&out[0], sim->fluid.particle.length, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	APBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	out[1] = words[MW_TOTAL_PAIRS];
+	out[2] = words[MW_KEPT_PAIRS] == 0xFFFFFFFFu ? words[MW_TOTAL_PAIRS] : words[MW_KEPT_PAIRS];
+	out[3] = words[MW_N_ASYM];
+	return APBF_OK;
+}
+
+int apbf_sim_neighbor_count(apbf_sim* sim, uint32_t* out_count)
+{
+	if (!sim || !out_count) return APBF_ERR_INVALID;
+	APBF_CUDA(sim->ctx, cudaMemcpyAsync(out_count, sim->nb.length, 4, cudaMemcpyDeviceToHost, sim->ctx->stream));
+	APBF_CUDA(sim->ctx, cudaStreamSynchronize(sim->ctx->stream));
+	return APBF_OK;
+}
+
+} // extern "C"

@@ -131,10 +131,11 @@ def dam_break(nx=100, ny=100, nz=100, r=1.0, jitter=0.05, seed=99, adaptive=True
     pool_max = np.array([3 * ext[0], 1.5 * ext[1], ext[2]], np.float32)
     arrays = _lattice_state((nx, ny, nz), pool_min + r, r, jitter, seed)
     margin = 6.0 * r + 4.0
-    lo = float(min(pool_min) - margin)
-    hi = float(max(pool_max) + margin)
+    lo = tuple(float(v - margin) for v in pool_min)
+    hi = tuple(float(v + margin) for v in pool_max)
+    # per-axis grid bounds (cells need not be cubes); resolution so that the widest cell is about 0.75 x search range
     sc = Scene(name=f"dam_break_{nx}x{ny}x{nz}", dims=3, arrays=shuffle_state(arrays, seed),
-               min_pos=(lo, lo, lo), max_pos=(hi, hi, hi), res_log2=_res_for(hi - lo, 6.0 * r),
+               min_pos=lo, max_pos=hi, res_log2=_res_for(max(h - l for l, h in zip(lo, hi)), 4.5 * r),
                basic_pbf=not adaptive, solver_iterations=4, smallest_target_radius=r)
     sc.box_min, sc.box_max = pool_walls(pool_min, pool_max, r, 3)
     return sc

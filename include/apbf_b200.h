@@ -1,0 +1,289 @@
+/*
+ * apbf_b200.h -- C-ABI of libapbf_b200.so: the B200 (sm_100a) implementation of APBF's per-substep
+ * particle hot path (neighbour search -> PBF incompressibility solve -> adaptive kernel width).
+ *
+ * Boundary.  The reference (cg-tuwien/APBF) has no FFI; its hot path is reached through
+ *   (1) pbd::shader_provider::<shader>(avk::buffer...)   source/shader_provider.h:15-72  (one static function per
+ *       compute shader, list lengths passed as device buffers), and
+ *   (2) the operator objects' apply()                     source/neighborhood_green.h:11-14,
+ *       neighborhood_binary_search.h:11-13, incompressibility.h:11-12, spread_kernel_width.h:10-11,
+ *       box_collision.h:11-12, velocity_handling.h:11-13, algorithms.h:12-17.
+ * Every entry point below names the reference interface it replaces.  avk::buffer becomes a plain device
+ * pointer; a list length stays a 4-byte word in device memory (the host never reads it on the hot path,
+ * SURVEY 3.1); *_capacity arguments are the host-known upper bounds (gpu_list::requested_length()).
+ * INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions: all functions return 0 on success or a negative apbf_status; all work is enqueued on the
+ * context's CUDA stream and is asynchronous unless stated otherwise; pointers are device pointers unless the
+ * name says host.  There is no CPU fallback: without a CUDA device apbf_ctx_create fails with
+ * APBF_ERR_NO_DEVICE.
+ */
+#ifndef APBF_B200_H
+#define APBF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APBF_POS_RESOLUTION 262144.0f                 /* shaders/cpu_gpu_shared_config.h:7 */
+#define APBF_KERNEL_WIDTH_RESOLUTION 262144.0f        /* :8 */
+#define APBF_INCOMPRESSIBILITY_DATA_RESOLUTION 262144.0f /* :9 */
+#define APBF_KERNEL_SCALE 4.0f                        /* :14 */
+#define APBF_KERNEL_WIDTH_PROPAGATION_FACTOR 0.5f     /* :15 */
+
+typedef enum apbf_status {
+	APBF_OK = 0,
+	APBF_ERR_NO_DEVICE = -1,
+	APBF_ERR_CUDA = -2,
+	APBF_ERR_INVALID = -3,
+	APBF_ERR_OOM = -4,
+	APBF_ERR_UNSUPPORTED = -5
+} apbf_status;
+
+/* shaders/cpu_gpu_shared_config.h:74-94 -- same fields, same order (the reference's UBO) */
+typedef struct apbf_settings {
+	int   mHeightKernelId;
+	int   mGradientKernelId;
+	int   mMerge;
+	int   mSplit;
+	int   mBaseKernelWidthOnTargetRadius;
+	int   mBaseKernelWidthOnBoundaryDistance;
+	int   mUpdateTargetRadius;
+	int   mUpdateBoundariness;
+	int   mNeighborListSorted;
+	int   mBoundarinessCalculationMethod;
+	float mBoundarinessAdaptionSpeed;
+	float mKernelWidthAdaptionSpeed;
+	float mBoundarinessSelfGradLengthFactor;
+	float mBoundarinessUnderpressureFactor;
+	float mMergeDuration;
+	float mSmallestTargetRadius;
+	float mTargetRadiusOffset;
+	float mTargetRadiusScaleFactor;
+} apbf_settings;
+
+typedef struct apbf_ctx apbf_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+/* Replaces shader_provider::set_queue / start_recording / end_recording (source/shader_provider.cpp:10-37):
+ * one ordered stream of work.  `cuda_stream` is a cudaStream_t (NULL = the legacy default stream). */
+int  apbf_ctx_create(int device, void* cuda_stream, apbf_ctx** out_ctx);
+void apbf_ctx_destroy(apbf_ctx* ctx);
+int  apbf_ctx_set_stream(apbf_ctx* ctx, void* cuda_stream);
+int  apbf_ctx_synchronize(apbf_ctx* ctx);
+const char* apbf_ctx_last_error(apbf_ctx* ctx);
+/* settings::update_apbf_settings_buffer (source/settings.cpp:66-90); the default is settings.cpp:5-31 */
+void apbf_default_settings(apbf_settings* out);
+int  apbf_ctx_set_settings(apbf_ctx* ctx, const apbf_settings* s);
+/* DIMENSIONS (cpu_gpu_shared_config.h:2) as a runtime value, 2 or 3 */
+int  apbf_ctx_set_dimensions(apbf_ctx* ctx, int dims);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t apbf_ctx_launch_count(apbf_ctx* ctx);
+/* Per-pass device timing with CUDA events on the context stream (replaces measurements::record_timing_interval_*,
+ * source/measurements.cpp:27-62).  apbf_ctx_profile(ctx, 1) clears and starts, (ctx, 0) stops; apbf_ctx_profile_read
+ * returns the accumulated milliseconds and span count of category 0 .. n-1 (APBF_ERR_INVALID past the last one) and
+ * synchronises with the recorded events. */
+int  apbf_ctx_profile(apbf_ctx* ctx, int enable);
+int  apbf_ctx_profile_read(apbf_ctx* ctx, int category, const char** out_name, double* out_ms, uint64_t* out_calls);
+/* sticky device-side status word: bit 0 = neighbour list overflow (neighbor_add.glsl:23-24 clamp hit). Synchronises. */
+int  apbf_ctx_device_flags(apbf_ctx* ctx, uint32_t* out_flags);
+
+/* ---- buffers: gpu_list_data::get_list best-fit pool (source/gpu_list_data.cpp:6-45) + algorithms::copy_bytes -- */
+int apbf_buffer_acquire(apbf_ctx* ctx, size_t bytes, void** out_dev_ptr);
+int apbf_buffer_release(apbf_ctx* ctx, void* dev_ptr);
+int apbf_copy_bytes(apbf_ctx* ctx, const void* src_dev, void* dst_dev, size_t bytes);        /* algorithms.cpp:4-18 */
+int apbf_copy_bytes_from_host(apbf_ctx* ctx, const void* src_host, void* dst_dev, size_t bytes); /* algorithms.cpp:20-36 */
+int apbf_copy_bytes_to_host(apbf_ctx* ctx, const void* src_dev, void* dst_host, size_t bytes);   /* gpu_list::read, synchronises */
+
+/* ---- list helper kernels (shader_provider, "gpu_lists" group) ------------------------------------------ */
+/* write_sequence.comp:21-28: out[i] = start + i*step for i < *len * len_scale */
+int apbf_write_sequence(apbf_ctx* ctx, uint32_t* out, const uint32_t* len, uint32_t capacity,
+                        uint32_t start, uint32_t step, uint32_t len_scale);
+/* write_sequence_float.comp */
+int apbf_write_sequence_float(apbf_ctx* ctx, float* out, const uint32_t* len, uint32_t capacity, float start, float step);
+/* copy_scattered_read.comp:21-30 (gpu_list::apply_edit, gpu_list.h:126-135): dst[i] = src[edit[i]], i < *edit_len */
+int apbf_copy_scattered_read(apbf_ctx* ctx, const void* src, void* dst, const uint32_t* edit,
+                             const uint32_t* edit_len, uint32_t capacity, uint32_t stride_bytes);
+/* scattered_write.comp: target[index[i]] = value, i < *len */
+int apbf_scattered_write(apbf_ctx* ctx, const uint32_t* index, uint32_t* target, const uint32_t* len,
+                         uint32_t capacity, uint32_t value);
+/* append_list.comp:21-29: target[*target_len ...] = appending[0 .. *appending_len); *new_len = min(sum, target_capacity) */
+int apbf_append_list(apbf_ctx* ctx, void* target, const void* appending, const uint32_t* target_len,
+                     const uint32_t* appending_len, uint32_t* new_len, uint32_t target_capacity,
+                     uint32_t appending_capacity, uint32_t stride_bytes);
+/* copy_with_differing_stride.comp:21-32 */
+int apbf_copy_with_differing_stride(apbf_ctx* ctx, const void* src, void* dst, const uint32_t* len, uint32_t capacity,
+                                    uint32_t src_stride_bytes, uint32_t dst_stride_bytes);
+/* indexed_list::apply_hidden_edit (source/indexed_list.h:289-308: atomic_swap.comp + generate_new_index_and_edit_list.comp)
+ * followed by the index-list sort of indexed_list::sort (:276-286): for every new hidden slot h (ascending) and every
+ * entry i of index_list with index_list[i] == edit[h], emit new_index = h and new_edit = i.  Result is ascending in
+ * new_index (the order the reference reaches after its sort).  *new_len = number emitted (clamped to index_capacity). */
+int apbf_apply_hidden_edit(apbf_ctx* ctx, const uint32_t* edit, const uint32_t* edit_len, uint32_t edit_capacity,
+                           const uint32_t* index_list, const uint32_t* index_len, uint32_t index_capacity,
+                           uint32_t hidden_capacity, uint32_t* new_index_list, uint32_t* new_edit_list, uint32_t* new_len);
+
+/* ---- algorithms (source/algorithms.h:12-17) ------------------------------------------------------------- */
+/* algorithms::sort: stable ascending sort of u32 keys with u32 payload; like the reference it may clobber the inputs
+ * and only looks at the key bits below the highest set bit of upper_bound (algorithms.cpp:73).  Implemented as an
+ * onesweep radix sort (8-bit digits, decoupled look-back); no helper list is needed. */
+int apbf_sort(apbf_ctx* ctx, uint32_t* keys, uint32_t* values, const uint32_t* count, uint32_t max_count,
+              uint32_t* out_keys, uint32_t* out_values, uint32_t upper_bound);
+/* algorithms::prefix_sum: inclusive scan, in place when result == values (algorithms.cpp:93-101) */
+int apbf_prefix_sum(apbf_ctx* ctx, const uint32_t* values, const uint32_t* count, uint32_t max_count, uint32_t* result);
+size_t apbf_sort_calculate_needed_helper_list_length(size_t max_count);       /* algorithms.cpp:38-46 (kept for callers) */
+size_t apbf_prefix_sum_calculate_needed_helper_list_length(size_t max_count); /* algorithms.cpp:48-58 */
+
+/* ---- position keys --------------------------------------------------------------------------------------- */
+/* shader_provider::calculate_position_hash (shader_provider.cpp:805; calculate_position_hash.comp:23-46) */
+int apbf_calculate_position_hash(apbf_ctx* ctx, const int32_t* position4, uint32_t* out_hash, const uint32_t* len,
+                                 uint32_t capacity, const float min_pos[3], const float max_pos[3], uint32_t res_log2);
+/* shader_provider::calculate_position_code (shader_provider.cpp:782; calculate_position_code.comp:23-72) */
+int apbf_calculate_position_code(apbf_ctx* ctx, const uint32_t* index_list, const int32_t* position4, uint32_t* out_code,
+                                 const uint32_t* len, uint32_t capacity, uint32_t code_section);
+/* shader_provider::find_value_ranges (shader_provider.cpp:221; find_value_ranges.comp:16-31); zero-fills both tables
+ * first like neighborhood_green.cpp:61-62 */
+int apbf_find_value_ranges(apbf_ctx* ctx, const uint32_t* index_list, const uint32_t* values, uint32_t* range_start,
+                           uint32_t* range_end, const uint32_t* len, uint32_t capacity, uint32_t n_ranges);
+
+/* ---- the reference's list schema as raw arrays (source/list_definitions.h:9-20) --------------------------- */
+/* One array of a list that the search re-orders: `data` holds the current content; the permuted content is written
+ * to `reorder_out` (a second buffer of the same capacity -- the gpu_list copy-on-write target of
+ * gpu_list::apply_edit, gpu_list.h:131-133).  After a search the caller uses reorder_out as the list's buffer. */
+typedef struct apbf_array {
+	void* data;
+	void* reorder_out;
+} apbf_array;
+
+/* pbd::particles = indexed_list<hidden_particles> */
+typedef struct apbf_particles {
+	apbf_array index_list;      /* u32   [capacity]          position in the index list = particle id          */
+	uint32_t*  length;          /* device word: index list length                                             */
+	uint32_t   capacity;
+	uint32_t*  hidden_length;   /* device word: hidden list length                                            */
+	uint32_t   hidden_capacity;
+	apbf_array position;        /* ivec4 [hidden_capacity]   fixed point * 2^18, w unused                     */
+	apbf_array velocity;        /* vec4                                                                       */
+	apbf_array inverse_mass;    /* f32                                                                        */
+	apbf_array radius;          /* f32                                                                        */
+	apbf_array pos_backup;      /* ivec4                                                                      */
+	apbf_array transferring;    /* u32                                                                        */
+} apbf_particles;
+
+/* pbd::fluid = uninterleaved_list<fluid_enum, particles, gpu_list<4> x4>; per-id arrays share particles.length */
+typedef struct apbf_fluid {
+	apbf_particles particle;
+	apbf_array target_radius;      /* f32 [capacity] */
+	apbf_array kernel_width;       /* f32 */
+	apbf_array boundariness;       /* f32 */
+	apbf_array boundary_distance;  /* u32 */
+} apbf_fluid;
+
+/* pbd::neighbors = gpu_list<8>: (id, idN) pairs of index-list positions */
+typedef struct apbf_neighbors {
+	uint32_t* pairs;      /* uvec2 [capacity] */
+	uint32_t* length;     /* device word      */
+	uint32_t  capacity;
+} apbf_neighbors;
+
+/* Optional read-outs of the search's intermediate results (any member may be NULL) */
+typedef struct apbf_search_debug {
+	uint32_t* sorted_key;     /* [hidden_capacity] sorted cell hash (Green) / unused (binary search)              */
+	uint32_t* sorted_index;   /* [hidden_capacity] new hidden slot -> old hidden slot                             */
+	uint32_t* cell_start;     /* [1 << (res*dims)] (Green)                                                        */
+	uint32_t* cell_end;
+	uint32_t* code[3];        /* [capacity] sorted 96-bit Morton code sections (binary search)                    */
+} apbf_search_debug;
+
+/* ---- operators --------------------------------------------------------------------------------------------- */
+/* pbd::neighborhood_green::set_data(...).set_range_scale(s).set_position_range(min,max,res).apply()
+ * (source/neighborhood_green.cpp:27-77).  `range` is the per-id range list (pool.cpp:45 passes fluid.kernel_width;
+ * pass the same apbf_array so that it is re-ordered with the particles).  Re-orders every array of `fluid` into its
+ * reorder_out buffer, rewrites the index list, and fills `neighbors` grouped by id in the reference's discovery
+ * order (valid for both values of mNeighborListSorted).  Particles must lie inside [min,max). */
+int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* neighbors,
+                                  float range_scale, const float min_pos[3], const float max_pos[3], uint32_t res_log2,
+                                  const apbf_search_debug* debug);
+/* pbd::neighborhood_binary_search::set_data(...).set_range_scale(s).apply() (source/neighborhood_binary_search.cpp:22-75) */
+int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range,
+                                          apbf_neighbors* neighbors, float range_scale, const apbf_search_debug* debug);
+/* pbd::incompressibility::set_data(fluid, neighbors).apply() (source/incompressibility.cpp:12-45).  Works on the
+ * arrays' `data` buffers in place.  Optional outputs (may be NULL): lambda[capacity], incomp_data[capacity*8]
+ * ({ivec3 gradSum; uint density; uint sqGradSum; pad x3}, incompressibility_0.comp:6-13). */
+int apbf_incompressibility_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors* neighbors,
+                                 float* out_lambda, uint32_t* out_incomp_data);
+/* pbd::spread_kernel_width::set_data(fluid, neighbors).apply() (source/spread_kernel_width.cpp:12-26); the pruned pair
+ * list replaces the content of `neighbors`.  Optional output kw_fixed[capacity] (the atomicMax target). */
+int apbf_spread_kernel_width_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighbors* neighbors, uint32_t* out_kw_fixed);
+/* pbd::box_collision::set_data(particles, boxMin, boxMax).apply() (source/box_collision.cpp:12-24); boxes are vec4
+ * device arrays, n_boxes host-known (user_controlled_boxes owns them, <= 64) */
+int apbf_box_collision_apply(apbf_ctx* ctx, apbf_particles* particles, const float* box_min4, const float* box_max4,
+                             uint32_t n_boxes);
+/* pbd::velocity_handling::apply(dt) (source/velocity_handling.cpp:15-31); last_dt is the class's mLastDeltaTime */
+int apbf_velocity_handling_apply(apbf_ctx* ctx, apbf_particles* particles, float dt, float last_dt, const float accel[3]);
+
+/* ---- a whole scene: lists resident in HBM, one substep in pool::update order (source/pool.cpp:67-106) -------- */
+typedef struct apbf_sim apbf_sim;
+
+typedef struct apbf_sim_config {
+	uint32_t particle_capacity;    /* pool.cpp:7,12 (100000 there) */
+	uint32_t neighbor_capacity;    /* pool.cpp:15 (10000000 there) */
+	int      dims;
+	int      basic_pbf;            /* settings::basicPbf */
+	int      solver_iterations;    /* settings::solverIterations */
+	int      use_binary_search;    /* NEIGHBORHOOD_TYPE 3 instead of 1 */
+	int      integrate;            /* run velocity_handling at the start of each substep */
+	float    dt;                   /* FIXED_TIME_STEP */
+	float    accel[3];             /* pool.cpp:28 */
+	float    min_pos[3], max_pos[3];
+	uint32_t res_log2;             /* neighborhood_green::set_position_range */
+	uint32_t n_boxes;
+	const float* box_min4_host;    /* vec4 [n_boxes] */
+	const float* box_max4_host;
+} apbf_sim_config;
+
+/* host-side view of the scene's lists (the reference's list schema, plain host arrays) */
+typedef struct apbf_host_state {
+	uint32_t  n;                /* number of particles (hidden length == index length == fluid length) */
+	uint32_t* index_list;       /* may be NULL on upload: identity */
+	int32_t*  position;         /* [n*4] */
+	float*    velocity;         /* [n*4] */
+	float*    inverse_mass;
+	float*    radius;
+	int32_t*  pos_backup;       /* [n*4] */
+	uint32_t* transferring;
+	float*    target_radius;
+	float*    kernel_width;
+	float*    boundariness;
+	uint32_t* boundary_distance;
+} apbf_host_state;
+
+int  apbf_sim_create(apbf_ctx* ctx, const apbf_sim_config* cfg, apbf_sim** out_sim);
+void apbf_sim_destroy(apbf_sim* sim);
+/* host -> device copy of all lists (members that are NULL are skipped); async on the context stream when the host
+ * memory is pinned */
+int  apbf_sim_upload(apbf_sim* sim, const apbf_host_state* host);
+/* device -> host copy (members that are NULL are skipped); synchronises */
+int  apbf_sim_download(apbf_sim* sim, apbf_host_state* host);
+/* n_substeps x pool::update: [velocity_handling] -> neighbour search -> [spread_kernel_width] ->
+ * solver_iterations x (box_collision, incompressibility).  Fully asynchronous. */
+int  apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps);
+/* views of the device-resident lists for callers that want to run single operators on them */
+int  apbf_sim_fluid(apbf_sim* sim, apbf_fluid* out_fluid);
+int  apbf_sim_neighbors(apbf_sim* sim, apbf_neighbors* out_neighbors);
+/* pair count of the last search (device -> host read, synchronises) */
+int  apbf_sim_neighbor_count(apbf_sim* sim, uint32_t* out_count);
+/* counters of the last substep (device -> host read, synchronises):
+ * out[0] particles, out[1] pairs found by the search (unclamped), out[2] pairs after the spread_kernel_width prune
+ * (== out[1] when it did not run), out[3] pairs without a mirrored pair */
+int  apbf_sim_stats(apbf_sim* sim, uint32_t out[4]);
+/* pinned host memory helpers for callers without a CUDA runtime of their own */
+int  apbf_host_alloc_pinned(size_t bytes, void** out_host_ptr);
+int  apbf_host_free_pinned(void* host_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APBF_B200_H */

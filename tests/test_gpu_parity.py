@@ -1,0 +1,403 @@
+"""GPU parity tests (run on the B200 box with -m gpu): every pass of the CUDA path, called through the C-ABI,
+against the CPU oracle on the same seeded inputs.
+
+Bars: bit-exact for keys, sort order, cell ranges, index lists, re-ordered arrays and neighbour sets; for the
+floating-point passes the north_star's 1e-5 relative tolerance, applied as written in each test.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from apbf_b200 import scenes
+from conftest import oracle_state
+
+pytestmark = pytest.mark.gpu
+LSB = 1.0 / 262144.0
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import apbf_b200
+    return apbf_b200
+
+
+def _t(torch, a):
+    a = np.ascontiguousarray(a)
+    return torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).cuda()
+
+
+def _u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+# ---- algorithms -------------------------------------------------------------------------------------------------------
+def _gpu_sort(gpu, keys, vals, cap=None, upper_bound=0xFFFFFFFF):
+    import torch
+    ctx = gpu.Context()
+    n = len(keys)
+    cap = cap or max(n, 1)
+    k = torch.zeros(cap, dtype=torch.int32, device="cuda"); v = torch.zeros_like(k)
+    k[:n] = _t(torch, np.asarray(keys, np.uint32)); v[:n] = _t(torch, np.asarray(vals, np.uint32))
+    ok = torch.zeros_like(k); ov = torch.zeros_like(k)
+    cnt = torch.tensor([n], dtype=torch.int32, device="cuda")
+    gpu.algorithms(ctx).sort(k, v, cnt, cap, ok, ov, upper_bound)
+    ctx.synchronize()
+    return _u32(ok)[:n], _u32(ov)[:n]
+
+
+def test_sort_kats(gpu):  # source/test.cpp:284-305, 343-364, 402-425
+    k, v = _gpu_sort(gpu, [15, 2, 1234, 2, 0, 4294967295, 1, 4294967294], range(8))
+    assert k.tolist() == [0, 1, 2, 2, 15, 1234, 4294967294, 4294967295] and v.tolist() == [4, 6, 1, 3, 0, 2, 7, 5]
+    k, v = _gpu_sort(gpu, [15, 2, 3, 2, 0, 14, 1, 14], range(8))
+    assert k.tolist() == [0, 1, 2, 2, 3, 14, 14, 15] and v.tolist() == [4, 6, 1, 3, 2, 5, 7, 0]
+    k, v = _gpu_sort(gpu, [15, 2, 1234, 2, 0, 4294967295, 1, 4294967294], range(8), cap=10000)  # few values in a long buffer
+    assert v.tolist() == [4, 6, 1, 3, 0, 2, 7, 5]
+
+
+@pytest.mark.parametrize("n,mask,ub", [(512 * 512 + 123, 0xFFFFFFFF, 0xFFFFFFFF), (512 * 512 + 1000, 15, 0xFFFFFFFF),
+                                       (3_000_001, 0xFFFFFFFF, 0xFFFFFFFF), (100_000, 0x7FFF, 1 << 15), (5000, 0xFFFF, 255),
+                                       (1, 0xFF, 0xFFFFFFFF), (0, 0xFF, 0xFFFFFFFF)])
+def test_sort_matches_oracle(gpu, orc, n, mask, ub):  # test.cpp:307-341, 366-400 + algorithms.cpp:73 pass limit
+    keys = (np.random.default_rng(n).integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32) & np.uint32(mask))
+    vals = np.random.default_rng(n + 1).permutation(n).astype(np.uint32)
+    k, v = _gpu_sort(gpu, keys, vals, upper_bound=ub)
+    ek, ev = orc.sort(keys, vals, ub)
+    assert np.array_equal(k, ek) and np.array_equal(v, ev)
+
+
+@pytest.mark.parametrize("n", [7, 1000, 512 * 512 + 1000, 5_000_003, 0])
+def test_prefix_sum_matches_oracle(gpu, orc, n):  # test.cpp:186-282
+    import torch
+    ctx = gpu.Context()
+    v = np.array([43, 1, 4567, 0, 1, 0, 84523487], np.uint32) if n == 7 else \
+        np.random.default_rng(n).integers(0, 4, n, dtype=np.uint32)
+    cap = max(n, 1) + 100
+    t = torch.zeros(cap, dtype=torch.int32, device="cuda"); t[:n] = _t(torch, v)
+    cnt = torch.tensor([n], dtype=torch.int32, device="cuda")
+    out = torch.zeros_like(t)
+    gpu.algorithms(ctx).prefix_sum(t, cnt, cap, out)
+    gpu.algorithms(ctx).prefix_sum(t, cnt, cap)  # in place
+    ctx.synchronize()
+    exp = orc.prefix_sum(v)
+    assert np.array_equal(_u32(out)[:n], exp) and np.array_equal(_u32(t)[:n], exp)
+    if n == 7:
+        assert exp.tolist() == [43, 44, 4611, 4611, 4612, 4612, 84528099]
+
+
+def test_list_helpers(gpu, orc):  # test.cpp:47-105 (append, apply_edit) + indexed_list hidden edits :117-184
+    import torch
+    ctx = gpu.Context()
+    lib, h = ctx.lib, ctx.handle
+    src = _t(torch, np.array([77, 3, 9999, 4294967295, 0], np.uint32)); edit = _t(torch, np.array([1, 3, 1, 4], np.uint32))
+    dst = torch.zeros(4, dtype=torch.int32, device="cuda"); ln = torch.tensor([4], dtype=torch.int32, device="cuda")
+    assert lib.apbf_copy_scattered_read(h, src.data_ptr(), dst.data_ptr(), edit.data_ptr(), ln.data_ptr(), 4, 4) == 0
+    assert _u32(dst).tolist() == [3, 4294967295, 3, 0]
+    # gpu_list concatenation (test.cpp:47-59)
+    a = torch.zeros(7, dtype=torch.int32, device="cuda"); a[:4] = _t(torch, np.array([3, 64, 12683, 4294967295], np.uint32))
+    b = _t(torch, np.array([432587, 0, 5436], np.uint32))
+    la = torch.tensor([4], dtype=torch.int32, device="cuda"); lb = torch.tensor([3], dtype=torch.int32, device="cuda")
+    assert lib.apbf_append_list(h, a.data_ptr(), b.data_ptr(), la.data_ptr(), lb.data_ptr(), la.data_ptr(), 7, 3, 4) == 0
+    assert _u32(a).tolist() == [3, 64, 12683, 4294967295, 432587, 0, 5436] and la.item() == 7
+    # 16-byte stride gather == oracle
+    rng = np.random.default_rng(0)
+    s16 = rng.integers(-1000, 1000, (1000, 4), dtype=np.int32); e = rng.integers(0, 1000, 777).astype(np.uint32)
+    d16 = torch.zeros((777, 4), dtype=torch.int32, device="cuda"); le = torch.tensor([777], dtype=torch.int32, device="cuda")
+    assert lib.apbf_copy_scattered_read(h, _t(torch, s16).data_ptr(), d16.data_ptr(), _t(torch, e).data_ptr(), le.data_ptr(), 777, 16) == 0
+    assert np.array_equal(d16.cpu().numpy(), orc.apply_edit(s16, e))
+    # indexed_list::apply_hidden_edit (test.cpp:165-184): B = {4,2,4}, edit {2,1,2,4,1} -> {0,2,3,3}
+    edit = _t(torch, np.array([2, 1, 2, 4, 1], np.uint32)); idx = _t(torch, np.array([4, 2, 4], np.uint32))
+    le = torch.tensor([5], dtype=torch.int32, device="cuda"); li = torch.tensor([3], dtype=torch.int32, device="cuda")
+    ni = torch.zeros(5, dtype=torch.int32, device="cuda"); ne = torch.zeros(5, dtype=torch.int32, device="cuda"); nl = torch.zeros(1, dtype=torch.int32, device="cuda")
+    assert lib.apbf_apply_hidden_edit(h, edit.data_ptr(), le.data_ptr(), 5, idx.data_ptr(), li.data_ptr(), 5, 5, ni.data_ptr(), ne.data_ptr(), nl.data_ptr()) == 0
+    assert nl.item() == 4 and _u32(ni)[:4].tolist() == [0, 2, 3, 3]
+    assert sorted(_u32(ne)[:2].tolist()) == [1, 1] and sorted(_u32(ne)[2:4].tolist()) == [0, 2]
+    # test.cpp:139-163: B = {0,3,1}, edit {0,1,3,4} -> {0,1,2}
+    edit = _t(torch, np.array([0, 1, 3, 4], np.uint32)); idx = _t(torch, np.array([0, 3, 1], np.uint32)); le[0] = 4
+    assert lib.apbf_apply_hidden_edit(h, edit.data_ptr(), le.data_ptr(), 4, idx.data_ptr(), li.data_ptr(), 5, 5, ni.data_ptr(), ne.data_ptr(), nl.data_ptr()) == 0
+    assert nl.item() == 3 and _u32(ni)[:3].tolist() == [0, 1, 2] and _u32(ne)[:3].tolist() == [0, 2, 1]
+    ctx.synchronize()
+
+
+# ---- keys ---------------------------------------------------------------------------------------------------------------
+def test_position_hash_and_code(gpu, orc):
+    import torch
+    ctx = gpu.Context()
+    lib, h = ctx.lib, ctx.handle
+    rng = np.random.default_rng(5)
+    n = 100_003
+    pos = np.zeros((n, 4), np.int32)
+    pos[:, :3] = rng.integers(-60 * 262144, 60 * 262144, (n, 3))
+    pos[:8, :3] = [[0, 0, 0], [-1, -1, -1], [1, 2, 4], [2 ** 31 - 1, -2 ** 31, 12345], [1 << 21, 1 << 22, 1 << 23], [7, 0, 0], [0, 7, 0], [0, 0, 7]]
+    tp = _t(torch, pos); ln = torch.tensor([n], dtype=torch.int32, device="cuda")
+    out = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for dims, res in ((3, 5), (3, 10), (2, 7), (2, 15)):
+        ctx.set_dimensions(dims)
+        mn, mx = (C.c_float * 3)(-64, -64, -64), (C.c_float * 3)(64.5, 64, 66)
+        assert lib.apbf_calculate_position_hash(h, tp.data_ptr(), out.data_ptr(), ln.data_ptr(), n, mn, mx, res) == 0
+        exp = orc.position_hash(pos[8:], (-64, -64, -64), (64.5, 64, 66), res, dims)
+        assert np.array_equal(_u32(out)[8:], exp), (dims, res)
+    ctx.set_dimensions(3)
+    idx = np.random.default_rng(6).permutation(n).astype(np.uint32)
+    for sec in range(3):
+        assert lib.apbf_calculate_position_code(h, _t(torch, idx).data_ptr(), tp.data_ptr(), out.data_ptr(), ln.data_ptr(), n, sec) == 0
+        assert np.array_equal(_u32(out), orc.position_code(idx, pos, sec)), sec
+    # Z-curve convention, test.cpp:623
+    cells = np.array([[2, 5, 1], [7, 0, 0], [0, 1, 0], [63, 0, 62]], np.float32)
+    p4 = np.zeros((4, 4), np.int32); p4[:, :3] = ((cells + 0.5) * 262144.0).astype(np.int32)
+    l4 = torch.tensor([4], dtype=torch.int32, device="cuda")
+    assert lib.apbf_calculate_position_hash(h, _t(torch, p4).data_ptr(), out.data_ptr(), l4.data_ptr(), 4, (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(64, 64, 64), 6) == 0
+    assert _u32(out)[:4].tolist() == [142, 73, 2, 187241]
+
+
+# ---- searches -------------------------------------------------------------------------------------------------------------
+def _scene(name):
+    if name == "block24_jitter":
+        return scenes.uniform_block(24, jitter=0.1, shuffle=True)
+    if name == "block20_lattice":   # exact distance == range ties of the regular lattice
+        return scenes.uniform_block(20, jitter=0.0, shuffle=True)
+    if name == "block2d":
+        return scenes.uniform_block(96, jitter=0.2, dims=2, shuffle=True)
+    if name == "waterdrop16":       # four radius classes: unmirrored pairs
+        return scenes.waterdrop(16, jitter=0.05)
+    raise KeyError(name)
+
+
+def _scale(sc):
+    return 1.0 if sc.basic_pbf else 1.5
+
+
+@pytest.mark.parametrize("name", ["block24_jitter", "block20_lattice", "block2d", "waterdrop16"])
+def test_green_search_bit_exact(gpu, orc, name):
+    sc = _scene(name)
+    s = orc.default_settings()
+    cap = sc.n * (700 if not sc.basic_pbf else 80)
+    st = oracle_state(orc, sc)
+    epairs, eaux = orc.green_apply(st, s, sc.dims, _scale(sc), sc.min_pos, sc.max_pos, sc.res_log2, cap, want_aux=True)
+    ctx = gpu.Context(dims=sc.dims)
+    L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=cap)
+    aux = gpu.neighborhood_green(ctx).set_data(L).set_range_scale(_scale(sc)).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply(debug=True)
+    ctx.synchronize()
+    assert ctx.device_flags() == 0
+    assert np.array_equal(aux["sorted_key"], eaux["sorted_hash"])
+    assert np.array_equal(aux["sorted_index"], eaux["sorted_index"])
+    assert np.array_equal(aux["cell_start"], eaux["cell_start"]) and np.array_equal(aux["cell_end"], eaux["cell_end"])
+    got = L.read_all()
+    for fname, _, _ in orc.State.FIELDS:
+        assert np.array_equal(got[fname], getattr(st, fname)), fname
+    pairs = L.read_pairs()
+    assert len(pairs) == len(epairs)
+    assert np.array_equal(pairs, epairs)  # same grouped discovery order as the oracle, hence equal as sets too
+
+
+@pytest.mark.parametrize("name", ["block24_jitter", "waterdrop16"])
+def test_binary_search_bit_exact(gpu, orc, name):
+    sc = _scene(name)
+    s = orc.default_settings()
+    cap = sc.n * (700 if not sc.basic_pbf else 80)
+    st = oracle_state(orc, sc)
+    epairs, eaux = orc.binary_search_apply(st, s, _scale(sc), cap, want_aux=True)
+    ctx = gpu.Context(dims=3)
+    L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=cap)
+    aux = gpu.neighborhood_binary_search(ctx).set_data(L).set_range_scale(_scale(sc)).apply(debug=True)
+    ctx.synchronize()
+    assert np.array_equal(aux["sorted_index"], eaux["sorted_index"])
+    for sec in range(3):
+        assert np.array_equal(aux[f"code{sec}"], eaux[f"code{sec}"])
+    got = L.read_all()
+    for fname, _, _ in orc.State.FIELDS:
+        assert np.array_equal(got[fname], getattr(st, fname)), fname
+    assert np.array_equal(L.read_pairs(), epairs)
+
+
+def test_search_with_subset_index_list(gpu, orc):
+    """index list = a permuted subset of the hidden particles: the general re-order chain (indexed_list.h:289-308)"""
+    sc = scenes.uniform_block(12, jitter=0.1, shuffle=True)
+    rng = np.random.default_rng(11)
+    sub = rng.permutation(sc.n)[: sc.n * 3 // 4].astype(np.uint32)
+    arrays = {k: v.copy() for k, v in sc.arrays.items()}
+    arrays["index_list"] = sub
+    for k in ("target_radius", "kernel_width", "boundariness", "boundary_distance"):
+        arrays[k] = arrays[k][: len(sub)].copy()
+    arrays["kernel_width"] *= rng.uniform(0.8, 1.2, len(sub)).astype(np.float32)
+    st = orc.State(**{k: v.copy() for k, v in arrays.items()})
+    epairs = orc.green_apply(st, orc.default_settings(), 3, 1.0, sc.min_pos, sc.max_pos, sc.res_log2, sc.n * 80)
+    ctx = gpu.Context()
+    L = gpu.ParticleLists(ctx, arrays, capacity=sc.n, neighbor_capacity=sc.n * 80)
+    gpu.neighborhood_green(ctx).set_data(L).set_range_scale(1.0).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply()
+    got = L.read_all()
+    for fname, _, _ in orc.State.FIELDS:
+        assert np.array_equal(got[fname], getattr(st, fname)), fname
+    assert np.array_equal(L.read_pairs(), epairs)
+    # the solver on a non-identity index list
+    ea = orc.incompressibility_apply(st, orc.default_settings(), 3, epairs, want_aux=True)
+    ga = gpu.incompressibility(ctx).set_data(L).apply(debug=True)
+    assert np.abs(ga["density"].astype(np.int64) - ea["density"]).max() <= 2
+    assert np.abs(L.read("position").astype(np.int64) - st.position).max() <= 4
+
+
+def test_neighbor_overflow_clamps(gpu, orc):  # neighbor_add.glsl:23-24
+    sc = scenes.uniform_block(10, jitter=0.1)
+    ctx = gpu.Context()
+    L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=1000)
+    gpu.neighborhood_green(ctx).set_data(L).set_range_scale(1.0).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply()
+    assert L.pair_count() == 1000 and ctx.device_flags() & 1
+
+
+def test_empty_lists(gpu):
+    sc = scenes.uniform_block(4)
+    arrays = {k: v[:0].copy() for k, v in sc.arrays.items()}
+    ctx = gpu.Context()
+    L = gpu.ParticleLists(ctx, arrays, capacity=64, neighbor_capacity=64)
+    gpu.neighborhood_green(ctx).set_data(L).set_range_scale(1.0).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply()
+    gpu.incompressibility(ctx).set_data(L).apply()
+    ctx.synchronize()
+    assert L.pair_count() == 0 and L.length() == 0
+
+
+# ---- solver -----------------------------------------------------------------------------------------------------------------
+def _search_both(gpu, orc, sc, s, scale, cap):
+    st = oracle_state(orc, sc)
+    epairs = orc.green_apply(st, s, sc.dims, scale, sc.min_pos, sc.max_pos, sc.res_log2, cap)
+    ctx = gpu.Context(dims=sc.dims)
+    gs = gpu.Settings.from_buffer_copy(bytes(s))
+    ctx.set_settings(gs)
+    L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=cap)
+    gpu.neighborhood_green(ctx).set_data(L).set_range_scale(scale).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply()
+    assert np.array_equal(L.read_pairs(), epairs)
+    return st, epairs, ctx, L
+
+
+def _check_incompressibility(ga, ea, got_pos, exp_pos, before_pos):
+    """Tolerances.  The accumulators are integers in units of 2^-18; a last-bit difference between CUDA's and glibc's
+    expf/powf moves a pair's truncated contribution by one unit.  Bar: every accumulator within 1e-5 relative
+    (+1 unit), lambda within 1e-5 relative wherever the accumulators agree exactly, and every position shift within
+    1e-5 of the largest shift (+2 units)."""
+    for k in ("density", "sq_grad_sum"):
+        d = np.abs(ga[k].astype(np.int64) - ea[k].astype(np.int64))
+        assert np.all(d <= 1 + 1e-5 * ea[k].astype(np.float64)), (k, d.max())
+    d = np.abs(ga["grad_sum"].astype(np.int64) - ea["grad_sum"].astype(np.int64))
+    assert np.all(d <= 1 + 1e-5 * np.abs(ea["grad_sum"]).max()), d.max()
+    same = (ga["density"] == ea["density"]) & (ga["sq_grad_sum"] == ea["sq_grad_sum"]) & np.all(ga["grad_sum"] == ea["grad_sum"], axis=1)
+    assert same.mean() > 0.9
+    rel = np.abs(ga["lam"][same] - ea["lam"][same]) / np.maximum(np.abs(ea["lam"][same]), 1e-30)
+    assert rel.max() <= 1e-5, rel.max()
+    shift_e = exp_pos[:, :3].astype(np.int64) - before_pos[:, :3]
+    shift_g = got_pos[:, :3].astype(np.int64) - before_pos[:, :3]
+    assert np.abs(shift_e).max() > 100  # the case really moves particles
+    err = np.abs(shift_g - shift_e)
+    assert err.max() <= 2 + 1e-5 * np.abs(shift_e).max(), (err.max(), np.abs(shift_e).max())
+    assert np.array_equal(got_pos[:, 3], exp_pos[:, 3])
+    return dict(acc_same=float(same.mean()), lam_rel=float(rel.max()), pos_err_units=int(err.max()), max_shift_units=int(np.abs(shift_e).max()))
+
+
+@pytest.mark.parametrize("hk,gk,method", [(1, 1, 2), (0, 0, 0), (2, 2, 1), (3, 3, 2), (4, 4, 2), (1, 2, 2)])
+def test_incompressibility_matches_oracle(gpu, orc, hk, gk, method):
+    sc = scenes.uniform_block(20, jitter=0.25, shuffle=True)
+    s = orc.default_settings()
+    s.mHeightKernelId, s.mGradientKernelId, s.mBoundarinessCalculationMethod = hk, gk, method
+    st, epairs, ctx, L = _search_both(gpu, orc, sc, s, 1.0, sc.n * 80)
+    before = st.position.copy()
+    for it in range(2):
+        ea = orc.incompressibility_apply(st, s, 3, epairs, want_aux=True)
+        ga = gpu.incompressibility(ctx).set_data(L).apply(debug=True)
+        if it == 0:
+            _check_incompressibility(ga, ea, L.read("position"), st.position, before)
+            assert np.abs(L.read("boundariness") - st.boundariness).max() <= 1e-6
+    # after two iterations the states may have drifted apart by the per-iteration tolerance only
+    assert np.abs(L.read("position").astype(np.int64) - st.position).max() <= 8
+
+
+def test_incompressibility_variable_widths(gpu, orc):
+    """waterdrop radius classes: unmirrored pairs take the atomic push path"""
+    sc = scenes.waterdrop(14, jitter=0.2)
+    s = orc.default_settings()
+    st, epairs, ctx, L = _search_both(gpu, orc, sc, s, 1.0, sc.n * 300)
+    mirrored = set(map(tuple, epairs.tolist()))
+    assert any((b, a) not in mirrored for a, b in list(mirrored)[:5000])
+    before = st.position.copy()
+    ea = orc.incompressibility_apply(st, s, 3, epairs, want_aux=True)
+    ga = gpu.incompressibility(ctx).set_data(L).apply(debug=True)
+    _check_incompressibility(ga, ea, L.read("position"), st.position, before)
+
+
+def test_spread_kernel_width_matches_oracle(gpu, orc):
+    sc = scenes.waterdrop(14, jitter=0.1)
+    s = orc.default_settings()
+    s.mBaseKernelWidthOnBoundaryDistance = 0
+    st, epairs, ctx, L = _search_both(gpu, orc, sc, s, 1.5, sc.n * 700)
+    ekept, ekw = orc.spread_kernel_width_apply(st, s, epairs)
+    gkw = gpu.spread_kernel_width(ctx).set_data(L).apply(debug=True)
+    assert np.array_equal(gkw, ekw)                          # atomicMax targets: exact
+    assert np.array_equal(L.read_pairs(), ekept)             # kept pairs, in order
+    assert np.array_equal(L.read("kernel_width"), st.kernel_width)
+    # and the solver runs on the pruned list (its mirrored bits were rebuilt)
+    before = st.position.copy()
+    ea = orc.incompressibility_apply(st, s, 3, ekept, want_aux=True)
+    ga = gpu.incompressibility(ctx).set_data(L).apply(debug=True)
+    _check_incompressibility(ga, ea, L.read("position"), st.position, before)
+
+
+def test_box_collision_matches_oracle(gpu, orc):
+    sc = scenes.uniform_block(16, jitter=0.3, shuffle=True)
+    st = oracle_state(orc, sc)
+    st.position[:, :3] += (np.random.default_rng(2).integers(-3, 4, (sc.n, 3)) * 262144 // 2).astype(np.int32)
+    arrays = {k: getattr(st, k).copy() for k, _, _ in orc.State.FIELDS}
+    ctx = gpu.Context()
+    L = gpu.ParticleLists(ctx, arrays)
+    orc.box_collision(st, sc.box_min, sc.box_max)
+    gpu.box_collision(ctx).set_data(L, sc.box_min, sc.box_max).apply()
+    moved = np.any(st.position != arrays["position"], axis=1).mean()
+    assert moved > 0.05
+    # fp32 elementwise arithmetic without library calls except floor: bit exact
+    assert np.array_equal(L.read("position"), st.position)
+
+
+def test_velocity_handling_matches_oracle(gpu, orc):
+    sc = scenes.uniform_block(12, jitter=0.3, shuffle=True)
+    st = oracle_state(orc, sc)
+    st.pos_backup[:, :3] -= np.random.default_rng(4).integers(-2000, 2000, (sc.n, 3)).astype(np.int32)
+    arrays = {k: getattr(st, k).copy() for k, _, _ in orc.State.FIELDS}
+    ctx = gpu.Context()
+    L = gpu.ParticleLists(ctx, arrays)
+    vh = gpu.velocity_handling(ctx).set_data(L).set_acceleration((0, -10, 0))
+    vh.last_dt = 1.0 / 60.0
+    orc.velocity_handling(st, 1.0 / 60.0, (0, -10, 0))
+    vh.apply(1.0 / 60.0)
+    for k in ("position", "velocity", "pos_backup"):
+        assert np.array_equal(L.read(k), getattr(st, k)), k
+
+
+@pytest.mark.parametrize("adaptive,bsearch", [(False, False), (True, False), (False, True)])
+def test_substeps_match_oracle(gpu, orc, adaptive, bsearch):
+    """pool::update order through apbf_sim_*: host buffers in, host buffers out; 3 substeps with the integrator on"""
+    sc = scenes.waterdrop(12, jitter=0.1) if adaptive else scenes.uniform_block(16, jitter=0.2, shuffle=True)
+    s = orc.default_settings()
+    s.mBaseKernelWidthOnBoundaryDistance = 0 if adaptive else 1
+    cap = sc.n * (700 if adaptive else 80)
+    st = oracle_state(orc, sc)
+    ctx = gpu.Context(dims=3)
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    sim = gpu.Sim(ctx, sc, neighbor_capacity=cap, use_binary_search=bsearch, integrate=True, basic_pbf=not adaptive)
+    sim.upload(sc.arrays)
+    n_pairs = 0
+    for step in range(3):
+        if step == 0:  # velocity_handling::mLastDeltaTime starts at 1.0f (velocity_handling.h:18); pos == backup -> velocity 0
+            pass
+        ep = orc.substep(st, s, dims=3, basic_pbf=not adaptive, solver_iterations=4, min_pos=sc.min_pos, max_pos=sc.max_pos,
+                         res_log2=sc.res_log2, box_min4=sc.box_min, box_max4=sc.box_max, cap=cap, use_binary_search=bsearch,
+                         integrate=True)
+        n_pairs = len(ep)
+        sim.substep(1)
+    from apbf_b200 import empty_host_arrays
+    out = empty_host_arrays(sc.n)
+    assert sim.download(out) == sc.n
+    assert sim.neighbor_count() == n_pairs
+    # positions after 3 substeps x 4 iterations: both sides accumulate the per-iteration tolerance; particles are
+    # matched by slot because the sort orders stay identical as long as no particle changes its cell differently
+    d = np.abs(out["position"][:, :3].astype(np.int64) - st.position[:, :3])
+    assert np.percentile(d, 99) <= 8 and d.max() <= 64, (np.percentile(d, 99), d.max())
+    assert np.allclose(out["kernel_width"], st.kernel_width, rtol=1e-5)

@@ -1,0 +1,217 @@
+"""CPU tests: the oracle against the reference's own known-answer vectors and cross-checks (no GPU).
+
+KAT sources (paths relative to the reference tree): source/test.cpp:91-105 (apply_edit), :186-197 / :269-282
+(prefix sum), :199-267 (long prefix sums, property), :284-305 / :402-425 (sort), :343-364 (sort small values),
+:307-341 / :366-400 (sort many values, property = std::stable_sort), :560-563 (three-particle neighbour set-up of the
+disabled search tests), :623 (Z-curve cell codes of the dead sortByPositions test).
+"""
+import numpy as np
+import pytest
+
+from apbf_b200 import scenes
+from conftest import oracle_state
+
+
+def test_apply_edit_kat(orc):  # test.cpp:91-105
+    out = orc.apply_edit(np.array([77, 3, 9999, 4294967295, 0], np.uint32), [1, 3, 1, 4])
+    assert out.tolist() == [3, 4294967295, 3, 0]
+
+
+def test_prefix_sum_kat(orc):  # test.cpp:186-197, 269-282 (inclusive)
+    out = orc.prefix_sum([43, 1, 4567, 0, 1, 0, 84523487])
+    assert out.tolist() == [43, 44, 4611, 4611, 4612, 4612, 84528099]
+
+
+@pytest.mark.parametrize("n,mask", [(1000, 3), (512 * 512 + 1000, 1)])  # test.cpp:199-267
+def test_long_prefix_sum(orc, n, mask):
+    v = (np.random.default_rng(0).integers(0, 1 << 31, n, dtype=np.uint32) & mask).astype(np.uint32)
+    assert np.array_equal(orc.prefix_sum(v), np.cumsum(v, dtype=np.uint64).astype(np.uint32))
+
+
+def test_prefix_sum_helper_layout(orc):  # test.cpp:225-267: helper = group sums per level + 10 words
+    n = 512 * 512 + 1000
+    assert orc.prefix_sum_helper_length(n) == 514 + 2 + 1 + 10
+    assert orc.prefix_sum_helper_length(7) == 1 + 10
+    assert orc.sort_helper_length(8) == 16 + orc.prefix_sum_helper_length(16)
+
+
+def test_sort_kat(orc):  # test.cpp:284-305, 402-425: stability pinned by the two 2s
+    k, v = orc.sort([15, 2, 1234, 2, 0, 4294967295, 1, 4294967294], range(8))
+    assert k.tolist() == [0, 1, 2, 2, 15, 1234, 4294967294, 4294967295]
+    assert v.tolist() == [4, 6, 1, 3, 0, 2, 7, 5]
+
+
+def test_sort_small_values_kat(orc):  # test.cpp:343-364
+    k, v = orc.sort([15, 2, 3, 2, 0, 14, 1, 14], range(8))
+    assert k.tolist() == [0, 1, 2, 2, 3, 14, 14, 15]
+    assert v.tolist() == [4, 6, 1, 3, 2, 5, 7, 0]
+
+
+@pytest.mark.parametrize("n,mask", [(512 * 512 + 123, 0xFFFFFFFF), (512 * 512 + 1000, 15)])  # test.cpp:307-341, 366-400
+def test_sort_many_values(orc, n, mask):
+    keys = (np.random.default_rng(0).integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32) & np.uint32(mask))
+    k, v = orc.sort(keys, np.arange(n, dtype=np.uint32))
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(v, order.astype(np.uint32))
+    assert np.array_equal(k, keys[order])
+
+
+def test_sort_upper_bound_limits_passes(orc):  # algorithms.cpp:73: only the digits below the bound are sorted
+    keys = np.array([0x15, 0x21, 0x13, 0x02], np.uint32)
+    k, v = orc.sort(keys, np.arange(4, dtype=np.uint32), upper_bound=15)
+    assert v.tolist() == [1, 3, 2, 0]  # ordered by the low 4 bits only, stable
+
+
+def test_zcurve_vectors(orc):  # test.cpp:623: cells (2,5,1),(7,0,0),(0,1,0),(63,0,62) -> 142,73,2,187241 (6 bits per axis)
+    cells = np.array([[2, 5, 1], [7, 0, 0], [0, 1, 0], [63, 0, 62]], np.float32)
+    # one cell per unit: min 0, max 64, res 6 -> cell index = floor(pos)
+    pos = np.zeros((4, 4), np.int32)
+    pos[:, :3] = ((cells + 0.5) * 262144.0).astype(np.int32)
+    h = orc.position_hash(pos, (0, 0, 0), (64, 64, 64), 6, 3)
+    assert h.tolist() == [142, 73, 2, 187241]
+
+
+def test_position_code_vector(orc):  # calculate_position_code.comp:28-30: raw (1,2,4) -> section 0 = 1 + 16 + 256
+    pos = np.array([[1, 2, 4, 0], [-1, -1, -1, 0], [1 << 21, 0, 0, 0], [0, 1 << 21, 0, 0]], np.int32)
+    idx = np.arange(4, dtype=np.uint32)
+    assert orc.position_code(idx, pos, 0).tolist() == [273, 0xFFFFFFFF, 0, 0]
+    assert orc.position_code(idx, pos, 1).tolist() == [0, 0xFFFFFFFF, 1 << 31, 0]
+    assert orc.position_code(idx, pos, 2).tolist() == [0, 0xFFFFFFFF, 0, 1]
+
+
+def test_find_value_ranges(orc):
+    s, e = orc.find_value_ranges(np.arange(7), [1, 1, 4, 4, 4, 6, 6], 8)
+    assert s.tolist() == [0, 0, 0, 0, 2, 0, 5, 0]
+    assert e.tolist() == [0, 2, 0, 0, 5, 0, 7, 0]
+
+
+def _three_particles():  # test.cpp:560-563
+    R = 262144
+    return dict(index_list=np.arange(3, dtype=np.uint32), position=np.array([[0, 0, 0, 1], [R, 0, 0, 1], [0, R, 0, 1]], np.int32),
+                velocity=np.zeros((3, 4), np.float32), inverse_mass=np.full(3, 0.125, np.float32), radius=np.ones(3, np.float32),
+                pos_backup=np.zeros((3, 4), np.int32), transferring=np.zeros(3, np.uint32), target_radius=np.ones(3, np.float32),
+                kernel_width=np.array([1.0, 1.0, 2.0], np.float32), boundariness=np.ones(3, np.float32),
+                boundary_distance=np.zeros(3, np.uint32))
+
+
+def _pairs_by_position(st, pairs):
+    """pair list as a set of (position of id, position of idN) -- independent of the re-ordering"""
+    pos = st.position[st.index_list][:, :3]
+    return sorted((tuple(pos[a]), tuple(pos[b])) for a, b in pairs)
+
+
+def test_three_particle_neighbours(orc):
+    """ranges 1,1,2 -> {(0,1),(0,2),(1,0),(2,0),(2,1)}: particle 2 reaches particle 1 at distance sqrt(2), not vice versa"""
+    s = orc.default_settings()
+    R = 262144
+    P = [(0, 0, 0), (R, 0, 0), (0, R, 0)]
+    expected = sorted((P[a], P[b]) for a, b in [(0, 1), (0, 2), (1, 0), (2, 0), (2, 1)])
+    st = orc.State(**_three_particles())
+    bf = orc.brute_force_pairs(st.index_list, st.position, st.kernel_width, 1.0, 16)
+    assert _pairs_by_position(st, bf) == expected
+    st = orc.State(**_three_particles())
+    g = orc.green_apply(st, s, 3, 1.0, (-10, -10, -10), (10, 10, 10), 6, 16)  # test.cpp:572
+    assert _pairs_by_position(st, g) == expected
+    st = orc.State(**_three_particles())
+    b = orc.binary_search_apply(st, s, 1.0, 16)
+    assert _pairs_by_position(st, b) == expected
+
+
+@pytest.mark.parametrize("dims", [2, 3])
+def test_searches_agree_with_brute_force(orc, dims):
+    sc = scenes.uniform_block(10 if dims == 3 else 40, jitter=0.3, dims=dims, shuffle=True)
+    s = orc.default_settings()
+    cap = sc.n * 700
+    st = oracle_state(orc, sc)
+    # variable ranges: unmirrored pairs must show up
+    st.kernel_width *= np.random.default_rng(3).uniform(0.6, 1.4, sc.n).astype(np.float32)
+    st2, st3 = st.copy(), st.copy()
+    g = orc.green_apply(st, s, dims, 1.5, sc.min_pos, sc.max_pos, sc.res_log2, cap)
+    bf = orc.brute_force_pairs(st.index_list, st.position, st.kernel_width, 1.5, cap)
+    assert len(g) == len(bf) and len(np.unique(g, axis=0)) == len(g)
+    assert np.array_equal(np.unique(g, axis=0), np.unique(bf, axis=0))
+    assert np.all(np.diff(g[:, 0].astype(np.int64)) >= 0)  # grouped by id
+    if dims == 3:
+        b = orc.binary_search_apply(st2, s, 1.5, cap)
+        assert _pairs_by_position(st2, b) == _pairs_by_position(st, g)
+    # the re-ordering is a permutation that keeps every particle's attributes together
+    key = lambda t: np.lexsort(t.position[:, :3].T[::-1])
+    a, c = key(st3), key(st)
+    for name in ("position", "inverse_mass", "radius"):
+        assert np.array_equal(getattr(st3, name)[a], getattr(st, name)[c])
+    assert np.array_equal(st3.kernel_width[a], st.kernel_width[c])  # per-id arrays follow (index list is the identity)
+    assert np.array_equal(st.index_list, np.arange(sc.n))
+
+
+def test_green_sorted_hash_and_cells(orc):
+    sc = scenes.uniform_block(10, jitter=0.2, shuffle=True)
+    st = oracle_state(orc, sc)
+    pairs, aux = orc.green_apply(st, orc.default_settings(), 3, 1.0, sc.min_pos, sc.max_pos, sc.res_log2, sc.n * 64, want_aux=True)
+    assert np.all(np.diff(aux["sorted_hash"].astype(np.int64)) >= 0)
+    h = orc.position_hash(st.position, sc.min_pos, sc.max_pos, sc.res_log2, 3)
+    assert np.array_equal(h, aux["sorted_hash"])
+    occ = aux["cell_end"].astype(np.int64) - aux["cell_start"]
+    assert occ.sum() == sc.n and occ.min() >= 0
+
+
+def test_kernel_functions_basic(orc):
+    s = orc.default_settings()
+    for hk in range(5):
+        s.mHeightKernelId = hk
+        w0 = orc.kernel_height(s, 3, [0, 0, 0], 4.0)
+        w1 = orc.kernel_height(s, 3, [1.0, 1.0, 1.0], 4.0)
+        assert w0 > w1 >= 0.0
+    for gk in range(5):
+        s.mGradientKernelId = gk
+        g = orc.kernel_gradient(s, 3, [1.0, 0.5, -0.25], 4.0)
+        assert np.dot(g, [1.0, 0.5, -0.25]) < 0  # points towards the centre
+        assert np.all(orc.kernel_gradient(s, 3, [0, 0, 0], 4.0) == 0)
+
+
+def test_incompressibility_pushes_compressed_particles_apart(orc):
+    sc = scenes.uniform_block(8, jitter=0.0)
+    st = oracle_state(orc, sc)
+    st.position[:, :3] = (st.position[:, :3].astype(np.float64) * 0.8).astype(np.int32)  # 20 % compression
+    s = orc.default_settings()
+    pairs = orc.green_apply(st, s, 3, 1.0, sc.min_pos, sc.max_pos, sc.res_log2, sc.n * 128)
+    before = st.position.copy()
+    aux = orc.incompressibility_apply(st, s, 3, pairs, want_aux=True)
+    centre = np.argmin(np.abs(before[:, :3]).sum(1))
+    assert aux["lam"][centre] < 0
+    r0 = np.linalg.norm(before[:, :3].astype(np.float64), axis=1)
+    r1 = np.linalg.norm(st.position[:, :3].astype(np.float64), axis=1)
+    assert (r1 - r0)[r0 > 0].mean() > 0  # the block expands
+    assert np.array_equal(st.position[:, 3], before[:, 3])
+
+
+def test_spread_kernel_width_prunes_and_spreads(orc):
+    sc = scenes.waterdrop(10, jitter=0.05)
+    st = oracle_state(orc, sc)
+    s = orc.default_settings()
+    s.mBaseKernelWidthOnBoundaryDistance = 0
+    pairs = orc.green_apply(st, s, 3, 1.5, sc.min_pos, sc.max_pos, sc.res_log2, sc.n * 400)
+    old_kw = st.kernel_width.copy()
+    kept, kwfx = orc.spread_kernel_width_apply(st, s, pairs)
+    assert 0 < len(kept) < len(pairs)
+    assert np.all(kwfx >= np.trunc(np.maximum(st.radius, st.target_radius) * 4 * 262144).astype(np.uint32))
+    assert np.all(np.abs(st.kernel_width / old_kw - 1) <= s.mKernelWidthAdaptionSpeed * 1.0001)
+
+
+def test_box_collision_keeps_particles_outside_walls(orc):
+    sc = scenes.uniform_block(8)
+    st = oracle_state(orc, sc)
+    st.position[:, 0] -= 3 * 262144 // 2  # push the outermost layer 1.5 units into the (radius-inflated) -x wall
+    orc.box_collision(st, sc.box_min, sc.box_max)
+    x = st.position[:, 0] / 262144.0
+    assert x.min() >= sc.box_max[0, 0] + 1.0 - 1e-3  # back at wall face + radius (the hash jitter only widens the wall)
+    assert x.min() <= sc.box_max[0, 0] + 1.0 + 0.05 + 1e-3
+
+
+def test_substep_runs_and_conserves_particles(orc):
+    sc = scenes.uniform_block(8, jitter=0.2, shuffle=True)
+    st = oracle_state(orc, sc)
+    s = orc.default_settings()
+    pairs = orc.substep(st, s, dims=3, basic_pbf=True, solver_iterations=4, min_pos=sc.min_pos, max_pos=sc.max_pos,
+                        res_log2=sc.res_log2, box_min4=sc.box_min, box_max4=sc.box_max, cap=sc.n * 64)
+    assert len(pairs) > 0 and st.n == sc.n
+    assert sorted(st.inverse_mass.tolist()) == sorted(sc.arrays["inverse_mass"].tolist())
