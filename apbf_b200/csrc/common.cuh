@@ -131,6 +131,10 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
 {
 	return (ax * bx + ay * by) + az * bz;
 }
+// pow(x, y) rounded once from double precision: equals a correctly rounded powf (what glibc's powf returns, error
+// < 0.52 ulp) except on near-ties, whereas CUDA's powf is only good to a few ulp.  Every value derived from it feeds a
+// float -> fixed-point truncation, where a last-bit difference becomes a whole unit.
+__device__ __forceinline__ float pow_rn(float x, float y) { return (float)pow((double)x, (double)y); }
 __device__ __forceinline__ uint32_t f2u(float f) { return (uint32_t)f; } // cvt.rzi.u32.f32: negative/NaN -> 0, saturating
 __device__ __forceinline__ int32_t f2i(float f) { return (int32_t)f; }   // cvt.rzi.s32.f32: NaN -> 0, saturating
 

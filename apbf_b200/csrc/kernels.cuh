@@ -23,14 +23,14 @@ __device__ __forceinline__ kpar height_params(float w, float D)
 	kpar p; p.w = w; p.c0 = 0.f; p.c1 = 0.f;
 	if (HK == 0) p.c0 = 8.0f / (APBF_PI * w * w * w);                      // k, kernels.glsl:23
 	if (HK == 1) {                                                          // :104 + :86-88
-		float height = 0.6f / powf(w / 2.0f, D);
-		float iv = powf(height, 2.0f / D);
+		float height = 0.6f / pow_rn(w / 2.0f, D);
+		float iv = pow_rn(height, 2.0f / D);
 		p.c0 = iv * APBF_PI;          // invDoubleVariance
-		p.c1 = powf(iv, D / 2.0f);    // normalisation
+		p.c1 = pow_rn(iv, D / 2.0f);    // normalisation
 	}
-	if (HK == 2) { p.c0 = w * w; p.c1 = 64.0f * APBF_PI * powf(w, 9.0f); } // :6,8
-	if (HK == 3) p.c0 = 3.0f / (APBF_PI * powf(w, D));                     // :50
-	if (HK == 4) p.c0 = (D == 3.0f) ? 15.0f / (2.0f * APBF_PI * powf(w, 5.0f)) : 6.0f / (APBF_PI * powf(w, 4.0f)); // :64-68
+	if (HK == 2) { p.c0 = w * w; p.c1 = 64.0f * APBF_PI * pow_rn(w, 9.0f); } // :6,8
+	if (HK == 3) p.c0 = 3.0f / (APBF_PI * pow_rn(w, D));                     // :50
+	if (HK == 4) p.c0 = (D == 3.0f) ? 15.0f / (2.0f * APBF_PI * pow_rn(w, 5.0f)) : 6.0f / (APBF_PI * pow_rn(w, 4.0f)); // :64-68
 	return p;
 }
 
@@ -40,14 +40,14 @@ __device__ __forceinline__ kpar grad_params(float w, float D)
 	kpar p; p.w = w; p.c0 = 0.f; p.c1 = 0.f;
 	if (GK == 0) p.c0 = 48.0f / (APBF_PI * w * w * w);                     // l, :39
 	if (GK == 1) {                                                          // :117 + :93-96 (+ :86-88 via gauss_kernel_height)
-		float height = 0.6f / powf(w / 2.0f, D);
-		float iv = powf(height, 2.0f / D);
+		float height = 0.6f / pow_rn(w / 2.0f, D);
+		float iv = pow_rn(height, 2.0f / D);
 		p.c0 = iv * APBF_PI;
-		p.c1 = powf(iv, D / 2.0f);
+		p.c1 = pow_rn(iv, D / 2.0f);
 	}
-	if (GK == 2) p.c0 = APBF_PI * powf(w, 6.0f);                           // :15
-	if (GK == 3) p.c0 = 3.0f / (APBF_PI * powf(w, D + 1.0f));              // :56
-	if (GK == 4) p.c0 = (D == 3.0f) ? 15.0f / (2.0f * APBF_PI * powf(w, 5.0f)) : 6.0f / (APBF_PI * powf(w, 4.0f));
+	if (GK == 2) p.c0 = APBF_PI * pow_rn(w, 6.0f);                           // :15
+	if (GK == 3) p.c0 = 3.0f / (APBF_PI * pow_rn(w, D + 1.0f));              // :56
+	if (GK == 4) p.c0 = (D == 3.0f) ? 15.0f / (2.0f * APBF_PI * pow_rn(w, 5.0f)) : 6.0f / (APBF_PI * pow_rn(w, 4.0f));
 	return p;
 }
 
@@ -64,15 +64,15 @@ __device__ __forceinline__ float kheight(const kpar& p, float r2, float dist)
 			float q3 = q * q2;
 			return p.c0 * (6.0f * q3 - 6.0f * q2 + 1.0f);
 		}
-		return p.c0 * (2.0f * powf(1.0f - q, 3.0f));
+		return p.c0 * (2.0f * pow_rn(1.0f - q, 3.0f));
 	}
 	if (HK == 1) return expf(-r2 * p.c0) * p.c1; // gauss_kernel_height :84-89
 	if (HK == 2) { // poly6 :3-9
 		if (r2 > p.c0) return 0.0f;
-		return 315.0f * powf(p.c0 - r2, 3.0f) / p.c1;
+		return 315.0f * pow_rn(p.c0 - r2, 3.0f) / p.c1;
 	}
 	if (HK == 3) return glsl_max(0.0f, (1.0f - dist / h) * p.c0); // cone :48-52
-	if (HK == 4) return p.c0 * powf(glsl_min(0.0f, dist - h), 2.0f); // quadratic spike :62-70
+	if (HK == 4) return p.c0 * pow_rn(glsl_min(0.0f, dist - h), 2.0f); // quadratic spike :62-70
 	return 0.0f;
 }
 
@@ -100,7 +100,7 @@ __device__ __forceinline__ vec3f kgrad(const kpar& p, float rx, float ry, float 
 	}
 	if (GK == 2) { // spiky_kernel_gradient :11-16
 		if (dist > h || dist < 0.0001f) return o;
-		float f = -45.0f * powf(h - dist, 2.0f) / p.c0;
+		float f = -45.0f * pow_rn(h - dist, 2.0f) / p.c0;
 		o.x = f * (rx / dist); o.y = f * (ry / dist); o.z = f * (rz / dist);
 		return o;
 	}

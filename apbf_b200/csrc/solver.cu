@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
 			o[1] = make_uint4(sq, 0u, 0u, 0u);
 		}
 		// incompressibility_2.comp:72-110
-		const float invRestDensity = powf(2.0f * radius, A.D) * invMass;
+		const float invRestDensity = pow_rn(2.0f * radius, A.D) * invMass;
 		const float density = (float)dens / R_INC;
 		const float wx = (float)gx / R_INC, wy = (float)gy / R_INC, wz = (float)gz / R_INC;
 		float squaredGradSum = (float)sq / R_INC;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
 			A.boundariness[a] = glsl_min(1.0f, bn);
 		}
 		float lam = underpressure / (invRestDensity * invRestDensity * (squaredGradSum + 0.01f));
-		lam /= powf(2.0f * A.s.mSmallestTargetRadius, A.D) / invRestDensity * invMass;
+		lam /= pow_rn(2.0f * A.s.mSmallestTargetRadius, A.D) / invRestDensity * invMass;
 		if (A.out_lambda) A.out_lambda[a] = lam;
 		A.L4[a] = make_float4(lam, gp.w, gp.c0, gp.c1);
 		A.G4[a] = make_int4(gx, gy, gz, __float_as_int(invRestDensity));

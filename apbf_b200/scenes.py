@@ -95,9 +95,11 @@ def pool_walls(mn, mx, r, dims=3, wall=4.0):
     return bmin, bmax
 
 
-def uniform_block(side=64, r=1.0, jitter=0.0, seed=1234, dims=3, res_log2=None, shuffle=False):
+def uniform_block(side=64, r=1.0, jitter=0.0, seed=1234, dims=3, res_log2=None, shuffle=False, wall_gap=0.0):
     """configs[0]/[4]: side^D lattice centred on the origin, fixed kernel width 4r, basic PBF, 4 iterations.
-    Grid bounds = particle bounds +- 4r."""
+    Grid bounds = particle bounds +- 4r.  wall_gap moves the pool walls away from the block: the wall
+    jitter of box_collision.comp:46-47 is a chaotic hash of the position, so parity runs over several iterations keep
+    the particles out of wall contact (box collision itself is compared on identical inputs)."""
     counts = (side, side, side if dims == 3 else 1)
     half = side * r  # particle centres span [-(side-1)r, (side-1)r]
     origin = (-(side - 1) * r, -(side - 1) * r, -(side - 1) * r if dims == 3 else 0.0)
@@ -110,7 +112,7 @@ def uniform_block(side=64, r=1.0, jitter=0.0, seed=1234, dims=3, res_log2=None, 
     sc = Scene(name=f"uniform_{side}^{dims}" + ("_jitter" if jitter else ""), dims=dims, arrays=arrays,
                min_pos=(lo, lo, lo), max_pos=(hi, hi, hi), res_log2=res_log2, basic_pbf=True,
                solver_iterations=4, smallest_target_radius=r)
-    sc.box_min, sc.box_max = pool_walls((-half,) * 3, (half,) * 3, r, dims)
+    sc.box_min, sc.box_max = pool_walls((-half - wall_gap,) * 3, (half + wall_gap,) * 3, r, dims)
     return sc
 
 
@@ -141,7 +143,7 @@ def dam_break(nx=100, ny=100, nz=100, r=1.0, jitter=0.05, seed=99, adaptive=True
     return sc
 
 
-def waterdrop(side=160, r=1.0, jitter=0.05, seed=5):
+def waterdrop(side=160, r=1.0, jitter=0.05, seed=5, wall_gap=0.0):
     """configs[2]: per-particle radius classes {r, 2^(1/3) r, 2^(2/3) r, 2r} by depth (emulates split/merge
     output) -> variable kernel widths and neighbour-count skew."""
     def radius_of(pos):
@@ -155,6 +157,6 @@ def waterdrop(side=160, r=1.0, jitter=0.05, seed=5):
     lo = -(half + 12 * r); hi = half + 12 * r
     sc = Scene(name=f"waterdrop_{side}^3", dims=3, arrays=shuffle_state(arrays, seed), min_pos=(lo,) * 3, max_pos=(hi,) * 3,
                res_log2=_res_for(hi - lo, 8.0 * r), basic_pbf=False, solver_iterations=4, smallest_target_radius=r)
-    sc.box_min, sc.box_max = pool_walls((-half,) * 3, (half,) * 3, r, 3)
+    sc.box_min, sc.box_max = pool_walls((-half - wall_gap,) * 3, (half + wall_gap,) * 3, r, 3)
     return sc
 
