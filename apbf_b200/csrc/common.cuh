@@ -20,7 +20,7 @@ enum apbf_scratch_slot {
 	SLOT_SCAN_STATUS, SLOT_MISC_WORDS, SLOT_CELL_START, SLOT_CELL_END, SLOT_COUNTS, SLOT_OFFSETS, SLOT_SYMBITS,
 	SLOT_INV_PERM, SLOT_TMP_KEYS, SLOT_TMP_VALS, SLOT_TMP_VALS2, SLOT_CODE0, SLOT_CODE1, SLOT_CODE2,
 	SLOT_P4, SLOT_L4, SLOT_G4, SLOT_DELTA, SLOT_PUSH, SLOT_RADIUS_ID, SLOT_KWFX, SLOT_KEEP_COUNTS, SLOT_KEEP_OFFSETS,
-	SLOT_PAIRS_TMP, SLOT_SYMBITS_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4,
+	SLOT_PAIRS_TMP, SLOT_SYMBITS_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4, SLOT_KG, SLOT_KH, SLOT_Q4,
 	SLOT_COUNT
 };
 
@@ -50,7 +50,7 @@ enum apbf_misc_word {
 // per-kernel-category device timing (CUDA events on the context stream), off by default
 enum apbf_prof_cat {
 	PROF_HASH_SORT = 0, PROF_REORDER, PROF_CELL_RANGES, PROF_EMIT_COUNT, PROF_EMIT_SCAN, PROF_EMIT_FILL, PROF_KW_SPREAD,
-	PROF_KW_COMPACT, PROF_KW_MISC, PROF_BOX, PROF_DENSITY_LAMBDA, PROF_APPLY_DELTA, PROF_COMMIT, PROF_VELOCITY, PROF_COUNT
+	PROF_KW_COMPACT, PROF_KW_MISC, PROF_BOX, PROF_DENSITY_LAMBDA, PROF_APPLY_DELTA, PROF_COMMIT, PROF_VELOCITY, PROF_SOLVER_PREPARE, PROF_COUNT
 };
 struct apbf_prof_span { int cat; cudaEvent_t beg, end; };
 

@@ -1,0 +1,485 @@
+// incompress.cu -- the PBF incompressibility constraint (source/incompressibility.cpp:12-45, incompressibility_0..3.comp)
+// as two sweeps over the grouped neighbour list.
+//
+// The reference scatters every pair's contribution with integer atomics (5 per pair in pass 1, 3 per pair in pass 3) and
+// spills a 16-byte gradient per pair between the passes.  All accumulators are integers, so any summation order gives
+// the same bits.  Here a warp owns 32 consecutive particles; 8 lanes walk one particle's contiguous pair segment at a
+// time and accumulate in registers, then the per-particle sums are transposed so that all 32 lanes finish one particle
+// each:
+//   prologue  (k_begin_iteration): [pending deltas] + [box_collision] + pack {position, mass} per id into P4
+//   sweep T1  (k_density_lambda) = passes 0+1+2: density, gradient sums, lambda, boundariness, the particle's own shift
+//   sweep T2  (k_apply_delta)    = pass 3 as a GATHER: a particle collects the shifts its neighbours push onto it through
+//             the mirrored pairs ((b,a) exists iff the bit of (a,b) is set), recomputing the gradient from the packed
+//             positions; only unmirrored pairs (variable kernel widths) still use integer atomics
+//   epilogue  (k_commit_delta): position += delta.  Positions stay untouched between T1 and T2, as they are between the
+//             reference's passes 1 and 3.
+#include "box.cuh"
+#include "neighbors.cuh"
+#include "solver.cuh"
+
+namespace {
+
+constexpr int SWEEP_THREADS = 256; // 8 warps = 256 particles per CTA tile
+#define R_INC APBF_INCOMPRESSIBILITY_DATA_RESOLUTION
+#define FULL 0xffffffffu
+
+struct sweep_args {
+	const uint32_t* index_list;
+	const uint32_t* len;
+	int32_t*        pos4;          // hidden
+	const float*    inv_mass;      // hidden
+	const float*    radius;        // hidden
+	const float*    kernel_width;  // per id
+	float*          boundariness;  // per id
+	const uint32_t* pairs;
+	const uint32_t* offsets;
+	const uint32_t* symbits;
+	uint32_t        pair_cap;
+	int4*           P4;   // {x, y, z, bits(1 / inverse mass)} per id
+	float4*         KG;   // {h, gradient c0, gradient c1, invRestDensity}
+	float4*         KH;   // {height c0, height c1, lambda divisor, inverse mass}
+	float4*         L4;   // {lambda, h, gradient c0, gradient c1}
+	float4*         E4;   // {emptyDirection.xyz, 0}  (boundariness method 2)
+	int4*           delta;
+	int4*           push;
+	const float4*   bmin;
+	const float4*   bmax;
+	uint32_t        n_boxes;
+	uint32_t*       misc;
+	float*          out_lambda;
+	uint32_t*       out_incomp;
+	apbf_settings   s;
+	float           D;
+};
+
+__device__ __forceinline__ float move_towards_abs(float oldValue, float newValue, float maxStep) // incompressibility_2.comp:37-41
+{
+	float step = newValue - oldValue;
+	return oldValue + glsl_min(maxStep, glsl_max(-maxStep, step));
+}
+
+__device__ __forceinline__ int sum8(int v) // the 8 lanes of a group hold the same total afterwards
+{
+	v += __shfl_xor_sync(FULL, v, 1);
+	v += __shfl_xor_sync(FULL, v, 2);
+	v += __shfl_xor_sync(FULL, v, 4);
+	return v;
+}
+
+// ---- per-particle constants (exact: double-precision pow rounded once) ------------------------------------------------------
+template <int HK, int GK>
+__global__ void k_prepare_consts(sweep_args A)
+{
+	const uint32_t n = *A.len;
+	const bool ident = A.misc[MW_IDENTITY] != 0u;
+	for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+		const uint32_t idx = ident ? a : A.index_list[a];
+		const float w = A.kernel_width[a], invMass = A.inv_mass[idx], radius = A.radius[idx];
+		const kpar hp = height_params<HK>(w, A.D);
+		const kpar gp = grad_params<GK>(w, A.D);
+		const float invRestDensity = pow_rn(2.0f * radius, A.D) * invMass;                                   // incompressibility_2.comp:81
+		const float lamDiv = pow_rn(2.0f * A.s.mSmallestTargetRadius, A.D) / invRestDensity * invMass;      // :98
+		A.KG[a] = make_float4(w, gp.c0, gp.c1, invRestDensity);
+		A.KH[a] = make_float4(hp.c0, hp.c1, lamDiv, invMass);
+	}
+}
+
+// ---- prologue: [commit pending deltas] [box collision] pack -------------------------------------------------------------------
+template <bool COMMIT, bool BOX>
+__global__ void k_begin_iteration(sweep_args A)
+{
+	const uint32_t n = *A.len;
+	const bool ident = A.misc[MW_IDENTITY] != 0u;
+	const bool has_asym = A.misc[MW_N_ASYM] != 0u;
+	for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+		const uint32_t idx = ident ? a : A.index_list[a];
+		int4 p = *((const int4*)A.pos4 + idx);
+		if (COMMIT) {
+			int4 d = A.delta[a];
+			if (has_asym) { const int4 q = A.push[a]; d.x += q.x; d.y += q.y; d.z += q.z; }
+			p.x += d.x; p.y += d.y; p.z += d.z;
+		}
+		if (BOX) { // box_collision.comp:36-60
+			float px = (float)p.x * INV_R_POS, py = (float)p.y * INV_R_POS, pz = (float)p.z * INV_R_POS;
+			box_push(px, py, pz, a, A.radius[idx], A.bmin, A.bmax, A.n_boxes);
+			p.x = f2i(px * R_POS); p.y = f2i(py * R_POS); p.z = f2i(pz * R_POS);
+		}
+		if (COMMIT || BOX) *((int4*)A.pos4 + idx) = p;
+		A.P4[a] = make_int4(p.x, p.y, p.z, __float_as_int(1.0f / A.KH[a].w));
+	}
+}
+
+// ---- T1 -------------------------------------------------------------------------------------------------------------------------
+template <int HK, int GK, bool COM>
+__global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
+{
+	const uint32_t n = *A.len;
+	const bool has_asym = A.misc[MW_N_ASYM] != 0u;
+	const unsigned lane = threadIdx.x & 31u, sub = lane & 7u, grp = lane >> 3;
+	const uint32_t warps_per_grid = gridDim.x * (SWEEP_THREADS / 32);
+	for (uint32_t tile = blockIdx.x * (SWEEP_THREADS / 32) + (threadIdx.x >> 5); (size_t)tile * 32 < n; tile += warps_per_grid) {
+		const uint32_t base = tile * 32u;
+		int my_dens = 0, my_sq = 0, my_gx = 0, my_gy = 0, my_gz = 0, my_cx = 0, my_cy = 0, my_cz = 0, my_cw = 0;
+#pragma unroll 1
+		for (int r = 0; r < 8; r++) { // round r: group g sweeps particle base + 4r + g
+			const uint32_t a = base + r * 4 + grp;
+			int dens = 0, sq = 0, gx = 0, gy = 0, gz = 0, cx = 0, cy = 0, cz = 0, cw = 0;
+			if (a < n) {
+				const int4 ip = A.P4[a];
+				const float4 kg = A.KG[a], kh = A.KH[a];
+				kpar hp, gp;
+				hp.w = kg.x; hp.c0 = kh.x; hp.c1 = kh.y;
+				gp.w = kg.x; gp.c0 = kg.y; gp.c1 = kg.z;
+				const uint32_t beg = min(A.offsets[a], A.pair_cap), end = min(A.offsets[a + 1], A.pair_cap);
+				for (uint32_t e = beg + sub; e < end; e += 16) { // two pairs per lane in flight
+					const bool two = e + 8 < end;
+					const uint32_t b0 = A.pairs[2 * (size_t)e + 1];
+					const uint32_t b1 = two ? A.pairs[2 * (size_t)(e + 8) + 1] : b0;
+					const int4 q0 = A.P4[b0];
+					const int4 q1 = A.P4[b1];
+#pragma unroll
+					for (int u = 0; u < 2; u++) {
+						if (u == 1 && !two) break;
+						const int4 iq = u ? q1 : q0;
+						const float mN = __int_as_float(iq.w); // neighbour's mass = 1 / inverse mass
+						const int dxi = iq.x - ip.x, dyi = iq.y - ip.y, dzi = iq.z - ip.z; // int subtract first, incompressibility_1.comp:51
+						const float rx = (float)dxi * INV_R_POS, ry = (float)dyi * INV_R_POS, rz = (float)dzi * INV_R_POS;
+						const float r2 = dot3(rx, ry, rz, rx, ry, rz);
+						float W; vec3f g;
+						pair_eval<HK, GK>(hp, gp, rx, ry, rz, r2, W, g);
+						dens += (int)f2u(W * mN * R_INC);                                        // :55
+						gx += f2i(g.x * mN * R_INC); gy += f2i(g.y * mN * R_INC); gz += f2i(g.z * mN * R_INC); // :56-58
+						sq += (int)f2u(dot3(g.x, g.y, g.z, g.x, g.y, g.z) * mN * R_INC);         // :59
+						if (COM) { // boundariness method 1, :62-68
+							const float div = kg.x / mN; // invMassN * kernelWidth
+							cx += f2i((float)dxi / div); cy += f2i((float)dyi / div); cz += f2i((float)dzi / div);
+							cw += f2i(R_INC * mN);
+						}
+					}
+				}
+			}
+			dens = sum8(dens); sq = sum8(sq); gx = sum8(gx); gy = sum8(gy); gz = sum8(gz);
+			if (COM) { cx = sum8(cx); cy = sum8(cy); cz = sum8(cz); cw = sum8(cw); }
+			// transpose: lane j finishes particle base + j; its sums sit in group j & 3 during round j >> 2
+			const int src = (int)(lane & 3u) * 8;
+			const bool mine = (lane >> 2) == (unsigned)r;
+			int t;
+			t = __shfl_sync(FULL, dens, src); if (mine) my_dens = t;
+			t = __shfl_sync(FULL, sq, src);   if (mine) my_sq = t;
+			t = __shfl_sync(FULL, gx, src);   if (mine) my_gx = t;
+			t = __shfl_sync(FULL, gy, src);   if (mine) my_gy = t;
+			t = __shfl_sync(FULL, gz, src);   if (mine) my_gz = t;
+			if (COM) {
+				t = __shfl_sync(FULL, cx, src); if (mine) my_cx = t;
+				t = __shfl_sync(FULL, cy, src); if (mine) my_cy = t;
+				t = __shfl_sync(FULL, cz, src); if (mine) my_cz = t;
+				t = __shfl_sync(FULL, cw, src); if (mine) my_cw = t;
+			}
+		}
+		const uint32_t a = base + lane;
+		if (a >= n) continue;
+
+		const float4 kg = A.KG[a], kh = A.KH[a];
+		const float kw = kg.x, invRestDensity = kg.w, invMass = kh.w;
+		kpar hp; hp.w = kw; hp.c0 = kh.x; hp.c1 = kh.y;
+		// incompressibility_0.comp:33-45: the particle's own contribution
+		uint32_t dens = (uint32_t)my_dens + f2u(kheight<HK>(hp, 0.0f, 0.0f) / invMass * R_INC);
+		const uint32_t sq = (uint32_t)my_sq;
+		if (A.out_incomp) {
+			uint4* o = (uint4*)A.out_incomp + 2 * (size_t)a;
+			o[0] = make_uint4((uint32_t)my_gx, (uint32_t)my_gy, (uint32_t)my_gz, dens);
+			o[1] = make_uint4(sq, 0u, 0u, 0u);
+		}
+		// incompressibility_2.comp:72-110
+		const float density = (float)dens / R_INC;
+		const float wx = (float)my_gx / R_INC, wy = (float)my_gy / R_INC, wz = (float)my_gz / R_INC;
+		float squaredGradSum = (float)sq / R_INC;
+		const float wgs2 = dot3(wx, wy, wz, wx, wy, wz);
+		const float selfGradLength = sqrtf(wgs2) * invRestDensity;
+		squaredGradSum += wgs2 * invMass;
+		const float underpressure = 1.0f - density * invRestDensity;
+		if (A.s.mUpdateBoundariness) { // compute_boundariness :43-69
+			float sgl = selfGradLength * kw, up = underpressure, bn = 0.0f;
+			if (COM) {
+				float totalMass = (float)my_cw / R_INC + 1.0f / invMass;
+				float fx = (float)my_cx, fy = (float)my_cy, fz = (float)my_cz;
+				float dev = sqrtf(dot3(fx, fy, fz, fx, fy, fz)) / (R_POS * totalMass);
+				bn = dev * A.s.mBoundarinessSelfGradLengthFactor;
+			} else {
+				sgl *= A.s.mBoundarinessSelfGradLengthFactor;
+				up = glsl_max(0.0f, up) * A.s.mBoundarinessUnderpressureFactor;
+				bn = sgl + up;
+			}
+			bn = bn >= 1.0f ? 1.0f : 0.0f;
+			bn = move_towards_abs(A.boundariness[a], bn, A.s.mBoundarinessAdaptionSpeed);
+			A.boundariness[a] = glsl_min(1.0f, bn);
+		}
+		float lam = underpressure / (invRestDensity * invRestDensity * (squaredGradSum + 0.01f)); // :96
+		lam /= kh.z;                                                                              // :97-98
+		if (A.out_lambda) A.out_lambda[a] = lam;
+		A.L4[a] = make_float4(lam, kw, kg.y, kg.z);
+		// the particle's own shift (:100-109); the neighbours' shifts are added by T2
+		int sx = 0, sy = 0, sz = 0;
+		if (lam < 0.0f) {
+			const float f = lam * invMass * R_POS;
+			sx = f2i(-wx * invRestDensity * f); sy = f2i(-wy * invRestDensity * f); sz = f2i(-wz * invRestDensity * f);
+		}
+		A.delta[a] = make_int4(sx, sy, sz, 0);
+		if (A.s.mBoundarinessCalculationMethod == 2) { // emptyDirection = -normalize(vec3(gradSum)), incompressibility_3.comp:43
+			const float ex = (float)my_gx, ey = (float)my_gy, ez = (float)my_gz;
+			const float l = sqrtf(dot3(ex, ey, ez, ex, ey, ez));
+			A.E4[a] = make_float4(-(ex / l), -(ey / l), -(ez / l), 0.0f);
+		}
+		if (has_asym) A.push[a] = make_int4(0, 0, 0, 0);
+	}
+}
+
+// ---- T2 -------------------------------------------------------------------------------------------------------------------------
+template <int GK>
+__global__ void __launch_bounds__(SWEEP_THREADS) k_apply_delta(sweep_args A)
+{
+	const uint32_t n = *A.len;
+	const bool filter = A.s.mBoundarinessCalculationMethod == 2;
+	const bool has_asym = A.misc[MW_N_ASYM] != 0u;
+	const unsigned lane = threadIdx.x & 31u, sub = lane & 7u, grp = lane >> 3;
+	const uint32_t warps_per_grid = gridDim.x * (SWEEP_THREADS / 32);
+	for (uint32_t tile = blockIdx.x * (SWEEP_THREADS / 32) + (threadIdx.x >> 5); (size_t)tile * 32 < n; tile += warps_per_grid) {
+		const uint32_t base = tile * 32u;
+		int my_sx = 0, my_sy = 0, my_sz = 0, my_hit = 0;
+#pragma unroll 1
+		for (int r = 0; r < 8; r++) {
+			const uint32_t a = base + r * 4 + grp;
+			int sx = 0, sy = 0, sz = 0, hit = 0;
+			if (a < n) {
+				const int4 ip = A.P4[a];
+				const float4 la = A.L4[a];
+				float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (filter) e0 = A.E4[a];
+				const bool push_a = has_asym && la.x < 0.0f;
+				const uint32_t beg = min(A.offsets[a], A.pair_cap), end = min(A.offsets[a + 1], A.pair_cap);
+				for (uint32_t e = beg + sub; e < end; e += 8) {
+					const uint32_t b = A.pairs[2 * (size_t)e + 1];
+					const int4 iq = A.P4[b];
+					const float4 lb = A.L4[b];
+					const bool mirrored = !has_asym || ((A.symbits[e >> 5] >> (e & 31u)) & 1u);
+					const int dxi = iq.x - ip.x, dyi = iq.y - ip.y, dzi = iq.z - ip.z;
+					const float rx = (float)dxi * INV_R_POS, ry = (float)dyi * INV_R_POS, rz = (float)dzi * INV_R_POS;
+					const float r2 = dot3(rx, ry, rz, rx, ry, rz);
+					if (filter) {
+						// filter_boundariness (incompressibility_3.comp:41-46): dot(emptyDirection, normalize(gradient)) > 0.6.
+						// Every kernel's gradient is a non-positive multiple of r, so normalize(gradient) = -r / |r| wherever
+						// the gradient is not zero: the test is dot(e0, r) < -0.6 |r|, evaluated without the square root.
+						bool nz = r2 >= 1.0e-8f;
+						// compact support: the gradient is zero outside h, and at |r| == h for all but the cone kernel
+						if (GK != 1) nz = nz && (GK == 3 ? !(sqrtf(r2) > la.y) : sqrtf(r2) < la.y);
+						const float d = dot3(e0.x, e0.y, e0.z, rx, ry, rz);
+						if (nz && d < 0.0f && d * d > 0.36f * r2) hit = 1;
+					}
+					if (mirrored) { // the pair (b, a): b shifts a with b's lambda and b's kernel width, diff = pos_a - pos_b
+						if (lb.x < 0.0f) {
+							kpar gp_b; gp_b.w = lb.y; gp_b.c0 = lb.z; gp_b.c1 = lb.w;
+							const vec3f g = kgrad_fast<GK>(gp_b, -rx, -ry, -rz, r2);
+							const float f = lb.x * R_POS;
+							sx += f2i(g.x * f); sy += f2i(g.y * f); sz += f2i(g.z * f);
+						}
+					} else if (push_a) { // nobody gathers (a, b): push it like the reference does (:63-66)
+						kpar gp_a; gp_a.w = la.y; gp_a.c0 = la.z; gp_a.c1 = la.w;
+						const vec3f g = kgrad_fast<GK>(gp_a, rx, ry, rz, r2);
+						const float f = la.x * R_POS;
+						atomicAdd(&A.push[b].x, f2i(g.x * f));
+						atomicAdd(&A.push[b].y, f2i(g.y * f));
+						atomicAdd(&A.push[b].z, f2i(g.z * f));
+					}
+				}
+			}
+			sx = sum8(sx); sy = sum8(sy); sz = sum8(sz); hit = sum8(hit);
+			const int src = (int)(lane & 3u) * 8;
+			const bool mine = (lane >> 2) == (unsigned)r;
+			int t;
+			t = __shfl_sync(FULL, sx, src);  if (mine) my_sx = t;
+			t = __shfl_sync(FULL, sy, src);  if (mine) my_sy = t;
+			t = __shfl_sync(FULL, sz, src);  if (mine) my_sz = t;
+			t = __shfl_sync(FULL, hit, src); if (mine) my_hit = t;
+		}
+		const uint32_t a = base + lane;
+		if (a >= n) continue;
+		int4 d = A.delta[a]; // the particle's own shift from T1
+		d.x += my_sx; d.y += my_sy; d.z += my_sz;
+		A.delta[a] = d;
+		if (filter && my_hit) A.boundariness[a] = 0.0f;
+	}
+}
+
+// position += delta (+ pushes); xyz only, w is the caller's
+__global__ void k_commit_delta(sweep_args A)
+{
+	const uint32_t n = *A.len;
+	const bool ident = A.misc[MW_IDENTITY] != 0u;
+	const bool has_asym = A.misc[MW_N_ASYM] != 0u;
+	for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+		const uint32_t idx = ident ? a : A.index_list[a];
+		int4 d = A.delta[a];
+		if (has_asym) { const int4 q = A.push[a]; d.x += q.x; d.y += q.y; d.z += q.z; }
+		int4 p = *((int4*)A.pos4 + idx);
+		p.x += d.x; p.y += d.y; p.z += d.z;
+		*((int4*)A.pos4 + idx) = p;
+	}
+}
+
+int fill_args(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors* nb, sweep_args& A)
+{
+	apbf_particles& p = fluid->particle;
+	APBF_REQUIRE(ctx, p.index_list.data && p.length && p.position.data && p.inverse_mass.data && p.radius.data);
+	APBF_REQUIRE(ctx, fluid->kernel_width.data && fluid->boundariness.data);
+	const uint32_t n_cap = p.capacity;
+	memset(&A, 0, sizeof A);
+	A.index_list = (const uint32_t*)p.index_list.data;
+	A.len = p.length;
+	A.pos4 = (int32_t*)p.position.data;
+	A.inv_mass = (const float*)p.inverse_mass.data;
+	A.radius = (const float*)p.radius.data;
+	A.kernel_width = (const float*)fluid->kernel_width.data;
+	A.boundariness = (float*)fluid->boundariness.data;
+	if (nb) {
+		A.pairs = nb->pairs;
+		A.pair_cap = nb->capacity;
+	}
+	A.offsets = (const uint32_t*)ctx->scratch_get(SLOT_OFFSETS, sizeof(uint32_t) * (size_t)(n_cap + 1));
+	A.symbits = (const uint32_t*)ctx->scratch_get(SLOT_SYMBITS, 4);
+	A.P4 = (int4*)ctx->scratch_get(SLOT_P4, sizeof(int4) * (size_t)n_cap);
+	A.KG = (float4*)ctx->scratch_get(SLOT_KG, sizeof(float4) * (size_t)n_cap);
+	A.KH = (float4*)ctx->scratch_get(SLOT_KH, sizeof(float4) * (size_t)n_cap);
+	A.L4 = (float4*)ctx->scratch_get(SLOT_L4, sizeof(float4) * (size_t)n_cap);
+	A.E4 = (float4*)ctx->scratch_get(SLOT_G4, sizeof(float4) * (size_t)n_cap);
+	A.delta = (int4*)ctx->scratch_get(SLOT_DELTA, sizeof(int4) * (size_t)n_cap);
+	A.push = (int4*)ctx->scratch_get(SLOT_PUSH, sizeof(int4) * (size_t)n_cap);
+	A.misc = ctx->misc();
+	A.s = ctx->settings;
+	A.D = (float)ctx->dims;
+	if (!A.offsets || !A.symbits || !A.P4 || !A.KG || !A.KH || !A.L4 || !A.E4 || !A.delta || !A.push || !A.misc)
+		return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+	return APBF_OK;
+}
+
+template <int HK>
+int launch_prepare(apbf_ctx* ctx, const sweep_args& A, unsigned grid)
+{
+	switch (A.s.mGradientKernelId) {
+		case 0: k_prepare_consts<HK, 0><<<grid, 256, 0, ctx->stream>>>(A); break;
+		case 1: k_prepare_consts<HK, 1><<<grid, 256, 0, ctx->stream>>>(A); break;
+		case 2: k_prepare_consts<HK, 2><<<grid, 256, 0, ctx->stream>>>(A); break;
+		case 3: k_prepare_consts<HK, 3><<<grid, 256, 0, ctx->stream>>>(A); break;
+		case 4: k_prepare_consts<HK, 4><<<grid, 256, 0, ctx->stream>>>(A); break;
+		default: return apbf_fail(ctx, APBF_ERR_INVALID, "gradient kernel id", __FILE__, __LINE__);
+	}
+	APBF_LAUNCHED(ctx);
+	return APBF_OK;
+}
+
+template <int HK, int GK>
+void launch_t1(apbf_ctx* ctx, const sweep_args& A, unsigned grid)
+{
+	if (A.s.mBoundarinessCalculationMethod == 1) k_density_lambda<HK, GK, true><<<grid, SWEEP_THREADS, 0, ctx->stream>>>(A);
+	else k_density_lambda<HK, GK, false><<<grid, SWEEP_THREADS, 0, ctx->stream>>>(A);
+}
+
+template <int HK>
+int launch_density_lambda(apbf_ctx* ctx, const sweep_args& A, unsigned grid)
+{
+	switch (A.s.mGradientKernelId) {
+		case 0: launch_t1<HK, 0>(ctx, A, grid); break;
+		case 1: launch_t1<HK, 1>(ctx, A, grid); break;
+		case 2: launch_t1<HK, 2>(ctx, A, grid); break;
+		case 3: launch_t1<HK, 3>(ctx, A, grid); break;
+		case 4: launch_t1<HK, 4>(ctx, A, grid); break;
+		default: return apbf_fail(ctx, APBF_ERR_INVALID, "gradient kernel id", __FILE__, __LINE__);
+	}
+	APBF_LAUNCHED(ctx);
+	return APBF_OK;
+}
+
+} // namespace
+
+int apbf_solver_prepare(apbf_ctx* ctx, apbf_fluid* fluid)
+{
+	sweep_args A;
+	APBF_TRY(fill_args(ctx, fluid, nullptr, A));
+	const uint32_t n_cap = fluid->particle.capacity;
+	if (n_cap == 0) return APBF_OK;
+	apbf_prof_scope ps(ctx, PROF_SOLVER_PREPARE);
+	const unsigned grid = apbf_grid(ctx, n_cap, 256);
+	switch (A.s.mHeightKernelId) {
+		case 0: return launch_prepare<0>(ctx, A, grid);
+		case 1: return launch_prepare<1>(ctx, A, grid);
+		case 2: return launch_prepare<2>(ctx, A, grid);
+		case 3: return launch_prepare<3>(ctx, A, grid);
+		case 4: return launch_prepare<4>(ctx, A, grid);
+	}
+	return apbf_fail(ctx, APBF_ERR_INVALID, "height kernel id", __FILE__, __LINE__);
+}
+
+int apbf_solver_iteration(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors* nb, int flags, const float* box_min4,
+                          const float* box_max4, uint32_t n_boxes, float* out_lambda, uint32_t* out_incomp)
+{
+	if (!apbf_nbr_struct_valid(ctx, nb))
+		return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, "neighbour list was not produced by this context's search", __FILE__, __LINE__);
+	sweep_args A;
+	APBF_TRY(fill_args(ctx, fluid, nb, A));
+	const uint32_t n_cap = fluid->particle.capacity;
+	if (n_cap == 0) return APBF_OK;
+	A.bmin = (const float4*)box_min4;
+	A.bmax = (const float4*)box_max4;
+	A.n_boxes = n_boxes;
+	A.out_lambda = out_lambda;
+	A.out_incomp = out_incomp;
+	cudaStream_t st = ctx->stream;
+	const unsigned egrid = apbf_grid(ctx, n_cap, 256);
+	{
+		apbf_prof_scope ps(ctx, (flags & ITER_BEGIN_BOX) ? PROF_BOX : PROF_COMMIT);
+		const bool c = flags & ITER_BEGIN_COMMIT, b = flags & ITER_BEGIN_BOX;
+		if (c && b) k_begin_iteration<true, true><<<egrid, 256, 0, st>>>(A);
+		else if (c) k_begin_iteration<true, false><<<egrid, 256, 0, st>>>(A);
+		else if (b) k_begin_iteration<false, true><<<egrid, 256, 0, st>>>(A);
+		else k_begin_iteration<false, false><<<egrid, 256, 0, st>>>(A);
+		APBF_LAUNCHED(ctx);
+	}
+	const unsigned grid = apbf_grid(ctx, n_cap, SWEEP_THREADS, 8);
+	{
+		apbf_prof_scope ps(ctx, PROF_DENSITY_LAMBDA);
+		switch (A.s.mHeightKernelId) {
+			case 0: APBF_TRY(launch_density_lambda<0>(ctx, A, grid)); break;
+			case 1: APBF_TRY(launch_density_lambda<1>(ctx, A, grid)); break;
+			case 2: APBF_TRY(launch_density_lambda<2>(ctx, A, grid)); break;
+			case 3: APBF_TRY(launch_density_lambda<3>(ctx, A, grid)); break;
+			case 4: APBF_TRY(launch_density_lambda<4>(ctx, A, grid)); break;
+			default: return apbf_fail(ctx, APBF_ERR_INVALID, "height kernel id", __FILE__, __LINE__);
+		}
+	}
+	{
+		apbf_prof_scope ps(ctx, PROF_APPLY_DELTA);
+		switch (A.s.mGradientKernelId) {
+			case 0: k_apply_delta<0><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+			case 1: k_apply_delta<1><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+			case 2: k_apply_delta<2><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+			case 3: k_apply_delta<3><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+			case 4: k_apply_delta<4><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+		}
+		APBF_LAUNCHED(ctx);
+	}
+	if (flags & ITER_END_COMMIT) {
+		apbf_prof_scope ps(ctx, PROF_COMMIT);
+		k_commit_delta<<<egrid, 256, 0, st>>>(A);
+		APBF_LAUNCHED(ctx);
+	}
+	return APBF_OK;
+}
+
+extern "C" int apbf_incompressibility_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors* nb, float* out_lambda,
+                                            uint32_t* out_incomp_data)
+{
+	if (!ctx) return APBF_ERR_INVALID;
+	APBF_REQUIRE(ctx, fluid && nb);
+	// a stand-alone call knows nothing about what changed since the last one: recompute the constants every time
+	APBF_TRY(apbf_solver_prepare(ctx, fluid));
+	return apbf_solver_iteration(ctx, fluid, nb, ITER_END_COMMIT, nullptr, nullptr, 0u, out_lambda, out_incomp_data);
+}

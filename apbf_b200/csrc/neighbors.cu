@@ -127,7 +127,8 @@ k_green_emit(const uint32_t* __restrict__ index_list, const int32_t* __restrict_
              uint32_t* __restrict__ pairs, uint32_t cap, uint32_t* __restrict__ symbits, uint32_t* misc)
 {
 	const uint32_t n = *len;
-	const bool ident = misc[MW_IDENTITY] != 0u;
+	if (misc[MW_IDENTITY] != 0u) return; // k_green_emit_tiled handles identity index lists
+	const bool ident = false;
 	for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
 		const float r = range[id] * range_scale;
 		const uint32_t idx = ident ? id : index_list[id];
@@ -172,6 +173,137 @@ k_green_emit(const uint32_t* __restrict__ index_list, const int32_t* __restrict_
 			sw.flush();
 			if (n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
 		} else {
+			counts[id] = cnt;
+		}
+	}
+}
+
+// ---- Green pair emit, warp-tiled (the fast path when the index list is the identity) -----------------------------------
+// Q4[id] = {pos.x, pos.y, pos.z, T}: float position (vec3(ipos) / 2^18) and the acceptance threshold on the SQUARED
+// distance.  sqrt is monotone, so "distance(pos, posN) > range" (neighborhood_green.comp:83) is the same predicate as
+// "d2 > T" with T = the largest float whose correctly rounded square root is still <= range: no square root per
+// candidate, bit-identical decisions.
+__device__ __forceinline__ float sqrt_threshold(float r)
+{
+	if (r != r) return INFINITY;  // d > NaN is false: everything is accepted
+	if (r < 0.0f) return -1.0f;   // d > r always: nothing is accepted
+	float x = __fmul_rn(r, r);
+	if (x > 3.0e38f) return 3.4028234e38f;
+	for (int i = 0; i < 8 && __fsqrt_rn(x) > r; i++) x = __uint_as_float(__float_as_uint(x) - 1u);
+	for (int i = 0; i < 8; i++) {
+		const float y = __uint_as_float(__float_as_uint(x) + 1u);
+		if (__fsqrt_rn(y) <= r) x = y; else break;
+	}
+	return x;
+}
+
+__global__ void k_build_q4(const int32_t* __restrict__ pos4, const float* __restrict__ range, float range_scale,
+                           const uint32_t* __restrict__ len, float4* __restrict__ q4, const uint32_t* __restrict__ misc)
+{
+	if (misc[MW_IDENTITY] == 0u) return;
+	const uint32_t n = *len;
+	for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+		const int4 ip = ldg_int4(pos4, id);
+		q4[id] = make_float4((float)ip.x * INV_R_POS, (float)ip.y * INV_R_POS, (float)ip.z * INV_R_POS,
+		                     sqrt_threshold(range[id] * range_scale));
+	}
+}
+
+__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+
+// A warp owns 32 consecutive particles (a few neighbouring cells of the Z-curve).  It walks the union of their cell
+// boxes in the reference's order (x fastest); each cell's particles are contiguous in the sorted arrays, so they are
+// staged once per warp in shared memory by a coalesced 16-byte load and then broadcast to all lanes.  A lane only tests
+// the cells inside its own [gridMin, gridMax] box, which keeps every particle's pair order exactly the reference's.
+constexpr int TILED_WARPS = 4;
+template <bool FILL>
+__global__ void __launch_bounds__(TILED_WARPS * 32)
+k_green_emit_tiled(const float4* __restrict__ q4, const float* __restrict__ range, const uint32_t* __restrict__ cell_start,
+                   const uint32_t* __restrict__ cell_end, const uint32_t* __restrict__ len, apbf_grid_params g, float range_scale,
+                   uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ pairs, uint32_t cap,
+                   uint32_t* __restrict__ symbits, uint32_t* misc)
+{
+	if (misc[MW_IDENTITY] == 0u) return; // the generic kernel handles index lists that are not the identity
+	__shared__ float4 s_slab[TILED_WARPS][32];
+	const uint32_t n = *len;
+	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+	const uint32_t total_warps = gridDim.x * TILED_WARPS;
+	for (uint32_t tile = blockIdx.x * TILED_WARPS + w; (size_t)tile * 32 < n; tile += total_warps) {
+		const uint32_t id = tile * 32u + lane;
+		const bool valid = id < n;
+		float4 me = make_float4(0.f, 0.f, 0.f, -1.0f);
+		uint32_t gmin[3] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, gmax[3] = { 0u, 0u, 0u };
+		if (valid) {
+			me = q4[id];
+			const float r = range[id] * range_scale;
+			gmin[0] = apbf_map_axis(me.x - r, g, 0); gmax[0] = apbf_map_axis(me.x + r, g, 0);
+			gmin[1] = apbf_map_axis(me.y - r, g, 1); gmax[1] = apbf_map_axis(me.y + r, g, 1);
+			gmin[2] = apbf_map_axis(me.z - r, g, 2); gmax[2] = apbf_map_axis(me.z + r, g, 2);
+			if (g.dims < 3) { gmin[2] = 0u; gmax[2] = 0u; }
+			// the reference visits gridMin once even when gridMax < gridMin (its ++cell > gridMax wrap)
+			gmax[0] = max(gmax[0], gmin[0]); gmax[1] = max(gmax[1], gmin[1]); gmax[2] = max(gmax[2], gmin[2]);
+		}
+		uint32_t umin[3], umax[3];
+#pragma unroll
+		for (int d = 0; d < 3; d++) { umin[d] = warp_min_u32(gmin[d]); umax[d] = warp_max_u32(gmax[d]); }
+		uint32_t cnt = 0, out = 0, n_asym = 0;
+		sym_writer sw;
+		if (FILL && valid) { out = offsets[id]; sw.begin(symbits, out); }
+		for (uint32_t cz = umin[2]; cz <= umax[2]; cz++) {
+			const bool inz = cz >= gmin[2] && cz <= gmax[2];
+			for (uint32_t cy = umin[1]; cy <= umax[1]; cy++) {
+				const bool inzy = inz && cy >= gmin[1] && cy <= gmax[1];
+				for (uint32_t cx = umin[0]; cx <= umax[0]; cx++) {
+					const bool inbox = inzy && cx >= gmin[0] && cx <= gmax[0];
+					const uint32_t h = apbf_zhash(cx, cy, cz, g.res, g.dims);
+					const uint32_t s = __ldg(cell_start + h), e = __ldg(cell_end + h);
+					for (uint32_t c0 = s; c0 < e; c0 += 32) {
+						const uint32_t m = min(32u, e - c0);
+						if (lane < m) s_slab[w][lane] = q4[c0 + lane];
+						__syncwarp();
+						if (inbox) {
+							for (uint32_t j = 0; j < m; j++) {
+								const float4 q = s_slab[w][j];
+								const uint32_t idN = c0 + j;
+								const float dx = __fsub_rn(me.x, q.x), dy = __fsub_rn(me.y, q.y), dz = __fsub_rn(me.z, q.z);
+								const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+								if (id == idN || d2 > me.w) continue;
+								if (FILL) {
+									const uint32_t o = out + cnt;
+									if (o < cap) {
+										*(uint2*)(pairs + 2 * (size_t)o) = make_uint2(id, idN);
+										const bool mirrored = !(d2 > q.w); // (idN, id) is in the list too
+										sw.put(o, mirrored);
+										n_asym += mirrored ? 0u : 1u;
+									}
+								}
+								cnt++;
+							}
+						}
+						__syncwarp();
+					}
+					if (cx == 0xFFFFFFFFu) break;
+				}
+				if (cy == 0xFFFFFFFFu) break;
+			}
+			if (cz == 0xFFFFFFFFu) break;
+		}
+		if (FILL) {
+			if (valid) sw.flush();
+			n_asym = __reduce_add_sync(0xffffffffu, n_asym);
+			if (lane == 0 && n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
+		} else if (valid) {
 			counts[id] = cnt;
 		}
 	}
@@ -378,7 +510,8 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 	uint32_t* offsets = (uint32_t*)ctx->scratch_get(SLOT_OFFSETS, sizeof(uint32_t) * (size_t)(n_cap + 1));
 	const size_t sym_words = ((size_t)nb->capacity + 31) / 32 + 1;
 	uint32_t* symbits = (uint32_t*)ctx->scratch_get(SLOT_SYMBITS, sizeof(uint32_t) * sym_words);
-	if (!keys || !skeys || !sidx || !cs || !ce || !counts || !offsets || !symbits || !misc)
+	float4* q4 = (float4*)ctx->scratch_get(SLOT_Q4, sizeof(float4) * (size_t)n_cap);
+	if (!keys || !skeys || !sidx || !cs || !ce || !counts || !offsets || !symbits || !misc || !q4)
 		return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 
 	// hash all hidden particles (neighborhood_green.cpp:50-52), sort by hash with the slot as payload (:53)
@@ -403,9 +536,17 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 	// pairs (:64-74): count, scan, fill
 	k_clear_search_words<<<1, 1, 0, st>>>(misc);
 	APBF_LAUNCHED(ctx);
+	// Two kernels per pass, selected on the device by the identity flag (the host never reads it): the warp-tiled one
+	// when the index list is the identity over the sorted particles, the generic one otherwise.
 	const unsigned grid = apbf_grid(ctx, n_cap, 128, 16);
+	const unsigned tgrid = apbf_grid(ctx, n_cap, TILED_WARPS * 32, 12);
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_COUNT);
+		k_build_q4<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>(new_pos, new_range, range_scale, p.length, q4, misc);
+		APBF_LAUNCHED(ctx);
+		k_green_emit_tiled<false><<<tgrid, TILED_WARPS * 32, 0, st>>>(q4, new_range, cs, ce, p.length, g, range_scale, counts, nullptr,
+		                                                              nullptr, 0u, nullptr, misc);
+		APBF_LAUNCHED(ctx);
 		k_green_emit<false><<<grid, 128, 0, st>>>(new_index, new_pos, new_range, cs, ce, p.length, g, range_scale, counts, nullptr,
 		                                          nullptr, 0u, nullptr, misc);
 		APBF_LAUNCHED(ctx);
@@ -417,6 +558,9 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 	}
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
+		k_green_emit_tiled<true><<<tgrid, TILED_WARPS * 32, 0, st>>>(q4, new_range, cs, ce, p.length, g, range_scale, nullptr, offsets,
+		                                                             nb->pairs, nb->capacity, symbits, misc);
+		APBF_LAUNCHED(ctx);
 		k_green_emit<true><<<grid, 128, 0, st>>>(new_index, new_pos, new_range, cs, ce, p.length, g, range_scale, nullptr, offsets,
 		                                         nb->pairs, nb->capacity, symbits, misc);
 		APBF_LAUNCHED(ctx);

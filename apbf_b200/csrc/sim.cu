@@ -2,6 +2,7 @@
 //   [velocity_handling] -> neighbour search -> [spread_kernel_width] -> solverIterations x (box_collision, incompressibility)
 // plus host <-> device transfer of the lists (the reference-facing call with host buffers).
 #include "common.cuh"
+#include "solver.cuh"
 
 struct apbf_sim {
 	apbf_ctx*       ctx;
@@ -181,9 +182,14 @@ int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
 			APBF_TRY(apbf_neighborhood_green_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, nullptr));
 		swap_after_search(sim);
 		if (adaptive) APBF_TRY(apbf_spread_kernel_width_apply(ctx, &sim->fluid, &sim->nb, nullptr)); // pool.cpp:87-89
-		for (int it = 0; it < c.solver_iterations; it++) {                           // pool.cpp:92-95
-			APBF_TRY(apbf_box_collision_apply(ctx, &sim->fluid.particle, sim->boxes, sim->boxes ? sim->boxes + 4 * (size_t)c.n_boxes : nullptr, c.n_boxes));
-			APBF_TRY(apbf_incompressibility_apply(ctx, &sim->fluid, &sim->nb, nullptr, nullptr));
+		// pool.cpp:92-95: solverIterations x (box_collision, incompressibility).  Same results as calling the two
+		// operators in turn; the per-particle constants are computed once (kernel widths are fixed from here on) and
+		// box collision + the previous iteration's position update ride in the next iteration's prologue.
+		if (c.solver_iterations > 0) APBF_TRY(apbf_solver_prepare(ctx, &sim->fluid));
+		for (int it = 0; it < c.solver_iterations; it++) {
+			const int flags = ITER_BEGIN_BOX | (it > 0 ? ITER_BEGIN_COMMIT : 0) | (it == c.solver_iterations - 1 ? ITER_END_COMMIT : 0);
+			APBF_TRY(apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, flags, sim->boxes,
+			                               sim->boxes ? sim->boxes + 4 * (size_t)c.n_boxes : nullptr, c.n_boxes, nullptr, nullptr));
 		}
 	}
 	return APBF_OK;
