@@ -213,8 +213,8 @@ def run_gpu(args, rank, world, local_rank):
         ms = float(t.item())
 
     # ---- end to end: host buffers in, host buffers out, every step ---------------------------------------------------
-    e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(2):
+    e2e_steps = 0 if args.no_e2e else max(3, min(args.steps, 20))
+    for _ in range(2 if e2e_steps else 0):
         sim.upload(host); sim.substep(1); sim.download({"position": out_pos, "kernel_width": out_kw})
     barrier()
     t0 = time.perf_counter()
@@ -265,7 +265,7 @@ def run_gpu(args, rank, world, local_rank):
                    "l2": "working set (lists + pair list) exceeds the 126 MB L2" if (76 * n + 8 * stats["pairs_searched"]) > 126e6
                          else "working set fits L2; no flush between steps"},
         "gpu_launches": launches,
-        "e2e": {"value": n * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": n * world * e2e_steps / e2e_s if e2e_steps else None, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
@@ -294,6 +294,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dam_break_1M")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

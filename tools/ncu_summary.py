@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (read here, without a GPU) into a small CSV for profiles/: per captured launch the duration,
+DRAM bytes read/written, DRAM and SM throughput, L1/L2 hit rates, achieved occupancy, registers, grid, executed
+warp instructions.  Usage: python tools/ncu_summary.py gpurun_out/<tag>/prof.ncu-rep profiles/<name>.csv"""
+import csv
+import subprocess
+import sys
+
+WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
+        "smsp__cycles_active.avg", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem"]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = [hdr.index(w) for w in WANT if w in hdr]
+    with open(out, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow([hdr[i] for i in idx])
+        w.writerow([units[i] for i in idx])
+        for r in rows[2:]:
+            w.writerow([r[i][:60] if hdr[i] == "Kernel Name" else r[i] for i in idx])
+    print(f"{len(rows) - 2} launches -> {out}")
+
+
+if __name__ == "__main__":
+    main()
