@@ -220,9 +220,11 @@ class neighborhood_green(_Operator):
             keep = dict(sorted_key=torch.zeros(L.capacity, dtype=torch.int32, device=dev),
                         sorted_index=torch.zeros(L.capacity, dtype=torch.int32, device=dev),
                         cell_start=torch.zeros(n_cells, dtype=torch.int32, device=dev),
-                        cell_end=torch.zeros(n_cells, dtype=torch.int32, device=dev))
+                        cell_end=torch.zeros(n_cells, dtype=torch.int32, device=dev),
+                        pair_offsets=torch.zeros(L.capacity + 1, dtype=torch.int32, device=dev))
             dbg = _capi.SearchDebug(keep["sorted_key"].data_ptr(), keep["sorted_index"].data_ptr(),
                                     keep["cell_start"].data_ptr(), keep["cell_end"].data_ptr())
+            dbg.pair_offsets = keep["pair_offsets"].data_ptr()
         _check(self.ctx, self.lib.apbf_neighborhood_green_apply(
             self.ctx.handle, C.byref(fl), C.byref(rng), C.byref(nb), self.scale, _f3(self.min_pos), _f3(self.max_pos),
             self.res, C.byref(dbg) if dbg else None))
@@ -232,6 +234,7 @@ class neighborhood_green(_Operator):
             out = {k: v.cpu().numpy().view(np.uint32) for k, v in keep.items()}
             out["sorted_key"] = out["sorted_key"][:nh]
             out["sorted_index"] = out["sorted_index"][:nh]
+            out["pair_offsets"] = out["pair_offsets"][:L.length() + 1]
             return out
 
 

@@ -42,7 +42,7 @@ class Neighbors(C.Structure):
 
 
 class SearchDebug(C.Structure):
-    _fields_ = [("sorted_key", vp), ("sorted_index", vp), ("cell_start", vp), ("cell_end", vp), ("code", vp * 3)]
+    _fields_ = [("sorted_key", vp), ("sorted_index", vp), ("cell_start", vp), ("cell_end", vp), ("code", vp * 3), ("pair_offsets", vp)]
 
 
 class SimConfig(C.Structure):

@@ -17,10 +17,10 @@
 // named scratch slots (grown on demand, never shrunk: the steady state allocates nothing)
 enum apbf_scratch_slot {
 	SLOT_SORT_KEYS_A = 0, SLOT_SORT_KEYS_B, SLOT_SORT_VALS_A, SLOT_SORT_VALS_B, SLOT_SORT_HIST, SLOT_SORT_STATUS,
-	SLOT_SCAN_STATUS, SLOT_MISC_WORDS, SLOT_CELL_START, SLOT_CELL_END, SLOT_COUNTS, SLOT_OFFSETS, SLOT_SYMBITS,
+	SLOT_SCAN_STATUS, SLOT_MISC_WORDS, SLOT_CELL_START, SLOT_CELL_END, SLOT_COUNTS, SLOT_OFFSETS, SLOT_NB,
 	SLOT_INV_PERM, SLOT_TMP_KEYS, SLOT_TMP_VALS, SLOT_TMP_VALS2, SLOT_CODE0, SLOT_CODE1, SLOT_CODE2,
 	SLOT_P4, SLOT_L4, SLOT_G4, SLOT_DELTA, SLOT_PUSH, SLOT_RADIUS_ID, SLOT_KWFX, SLOT_KEEP_COUNTS, SLOT_KEEP_OFFSETS,
-	SLOT_PAIRS_TMP, SLOT_SYMBITS_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4, SLOT_KG, SLOT_KH, SLOT_Q4,
+	SLOT_PAIRS_TMP, SLOT_NB_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4, SLOT_KG, SLOT_KH, SLOT_Q4, SLOT_KEY_ID,
 	SLOT_COUNT
 };
 
@@ -70,7 +70,7 @@ struct apbf_ctx {
 	std::string   last_error;
 	apbf_scratch  scratch[SLOT_COUNT];
 	std::vector<apbf_pool_block> pool;
-	// provenance of the neighbour list structure built by the last search (offsets/symbits valid for this buffer)
+	// provenance of the neighbour list structure built by the last search (offsets/NB valid for this buffer)
 	const uint32_t* nbr_struct_pairs = nullptr;
 	uint32_t        nbr_struct_n_cap = 0;
 

@@ -31,9 +31,8 @@ struct sweep_args {
 	const float*    radius;        // hidden
 	const float*    kernel_width;  // per id
 	float*          boundariness;  // per id
-	const uint32_t* pairs;
+	const uint32_t* nbl;           // idN | (unmirrored << 31) per pair
 	const uint32_t* offsets;
-	const uint32_t* symbits;
 	uint32_t        pair_cap;
 	int4*           P4;   // {x, y, z, bits(1 / inverse mass)} per id
 	float4*         KG;   // {h, gradient c0, gradient c1, invRestDensity}
@@ -133,8 +132,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
 				const uint32_t beg = min(A.offsets[a], A.pair_cap), end = min(A.offsets[a + 1], A.pair_cap);
 				for (uint32_t e = beg + sub; e < end; e += 16) { // two pairs per lane in flight
 					const bool two = e + 8 < end;
-					const uint32_t b0 = A.pairs[2 * (size_t)e + 1];
-					const uint32_t b1 = two ? A.pairs[2 * (size_t)(e + 8) + 1] : b0;
+					const uint32_t b0 = A.nbl[e] & NB_ID_MASK;
+					const uint32_t b1 = two ? A.nbl[e + 8] & NB_ID_MASK : b0;
 					const int4 q0 = A.P4[b0];
 					const int4 q1 = A.P4[b1];
 #pragma unroll
@@ -258,10 +257,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_apply_delta(sweep_args A)
 				const bool push_a = has_asym && la.x < 0.0f;
 				const uint32_t beg = min(A.offsets[a], A.pair_cap), end = min(A.offsets[a + 1], A.pair_cap);
 				for (uint32_t e = beg + sub; e < end; e += 8) {
-					const uint32_t b = A.pairs[2 * (size_t)e + 1];
+					const uint32_t nbe = A.nbl[e];
+					const uint32_t b = nbe & NB_ID_MASK;
 					const int4 iq = A.P4[b];
 					const float4 lb = A.L4[b];
-					const bool mirrored = !has_asym || ((A.symbits[e >> 5] >> (e & 31u)) & 1u);
+					const bool mirrored = (nbe & NB_UNMIRRORED) == 0u;
 					const int dxi = iq.x - ip.x, dyi = iq.y - ip.y, dzi = iq.z - ip.z;
 					const float rx = (float)dxi * INV_R_POS, ry = (float)dyi * INV_R_POS, rz = (float)dzi * INV_R_POS;
 					const float r2 = dot3(rx, ry, rz, rx, ry, rz);
@@ -340,12 +340,9 @@ int fill_args(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors* nb, sweep_
 	A.radius = (const float*)p.radius.data;
 	A.kernel_width = (const float*)fluid->kernel_width.data;
 	A.boundariness = (float*)fluid->boundariness.data;
-	if (nb) {
-		A.pairs = nb->pairs;
-		A.pair_cap = nb->capacity;
-	}
+	if (nb) A.pair_cap = nb->capacity;
+	A.nbl = (const uint32_t*)ctx->scratch_get(SLOT_NB, 4);
 	A.offsets = (const uint32_t*)ctx->scratch_get(SLOT_OFFSETS, sizeof(uint32_t) * (size_t)(n_cap + 1));
-	A.symbits = (const uint32_t*)ctx->scratch_get(SLOT_SYMBITS, 4);
 	A.P4 = (int4*)ctx->scratch_get(SLOT_P4, sizeof(int4) * (size_t)n_cap);
 	A.KG = (float4*)ctx->scratch_get(SLOT_KG, sizeof(float4) * (size_t)n_cap);
 	A.KH = (float4*)ctx->scratch_get(SLOT_KH, sizeof(float4) * (size_t)n_cap);
@@ -356,7 +353,7 @@ int fill_args(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors* nb, sweep_
 	A.misc = ctx->misc();
 	A.s = ctx->settings;
 	A.D = (float)ctx->dims;
-	if (!A.offsets || !A.symbits || !A.P4 || !A.KG || !A.KH || !A.L4 || !A.E4 || !A.delta || !A.push || !A.misc)
+	if (!A.offsets || !A.nbl || !A.P4 || !A.KG || !A.KH || !A.L4 || !A.E4 || !A.delta || !A.push || !A.misc)
 		return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 	return APBF_OK;
 }

@@ -4,6 +4,7 @@
 
 namespace {
 
+template <int DIMS>
 __global__ void k_position_hash(const int32_t* __restrict__ pos4, uint32_t* __restrict__ out, const uint32_t* __restrict__ len,
                                 apbf_grid_params g)
 {
@@ -11,7 +12,7 @@ __global__ void k_position_hash(const int32_t* __restrict__ pos4, uint32_t* __re
 	for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
 		int4 p = ldg_int4(pos4, id);
 		float px = (float)p.x * INV_R_POS, py = (float)p.y * INV_R_POS, pz = (float)p.z * INV_R_POS;
-		out[id] = apbf_zhash(apbf_map_axis(px, g, 0), apbf_map_axis(py, g, 1), apbf_map_axis(pz, g, 2), g.res, g.dims);
+		out[id] = apbf_zhash<DIMS>(apbf_map_axis(px, g, 0), apbf_map_axis(py, g, 1), apbf_map_axis(pz, g, 2), g.res);
 	}
 }
 
@@ -158,7 +159,8 @@ int apbf_launch_position_hash(apbf_ctx* ctx, const int32_t* pos4, uint32_t* out,
                               const apbf_grid_params& g)
 {
 	if (cap == 0) return APBF_OK;
-	k_position_hash<<<apbf_grid(ctx, cap, 256), 256, 0, ctx->stream>>>(pos4, out, len, g);
+	if (g.dims == 3) k_position_hash<3><<<apbf_grid(ctx, cap, 256), 256, 0, ctx->stream>>>(pos4, out, len, g);
+	else k_position_hash<2><<<apbf_grid(ctx, cap, 256), 256, 0, ctx->stream>>>(pos4, out, len, g);
 	APBF_LAUNCHED(ctx);
 	return APBF_OK;
 }

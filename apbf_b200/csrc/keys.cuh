@@ -57,11 +57,15 @@ __device__ __forceinline__ unsigned long long spread3_21(unsigned long long v) /
 	return v;
 }
 
-// z-curve hash of calculate_position_hash.comp:29-36 / neighborhood_green.comp:40-47: only the low `res` bits per axis
-__device__ __forceinline__ uint32_t apbf_zhash(uint32_t gx, uint32_t gy, uint32_t gz, uint32_t res, int dims)
+// z-curve hash of calculate_position_hash.comp:29-36 / neighborhood_green.comp:40-47: only the low `res` bits per axis.
+// DIMS is a template parameter on purpose: with a run-time `dims` nvcc 12.9 (-O3, sm_100a) merges the tails of the
+// 3-D and the 2-D bit spread into one block in which "v | (v << s)" has become "v + (v << s)" -- valid for the 3-D
+// masks only -- and the 2-D hash of e.g. (0, 3) comes out as 2 instead of 10 (seen in the pair emit kernel, 2026-10).
+template <int DIMS>
+__device__ __forceinline__ uint32_t apbf_zhash(uint32_t gx, uint32_t gy, uint32_t gz, uint32_t res)
 {
 	const uint32_t m = (1u << res) - 1u;
-	if (dims == 3) return spread3_10(gx & m) | (spread3_10(gy & m) << 1) | (spread3_10(gz & m) << 2);
+	if (DIMS == 3) return spread3_10(gx & m) | (spread3_10(gy & m) << 1) | (spread3_10(gz & m) << 2);
 	return spread2_16(gx & m) | (spread2_16(gy & m) << 1);
 }
 

@@ -12,6 +12,7 @@
 #include "keys.cuh"
 #include "neighbors.cuh"
 #include "sort.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -93,92 +94,14 @@ __global__ void k_gather_ids(gather_table t, const uint32_t* __restrict__ perm, 
 }
 
 // ---- Green pair emit (neighborhood_green.comp:50-87) ----------------------------------------------------------------
-// One thread per particle.  FILL == false counts the accepted candidates, FILL == true writes them at the scanned offsets.
+// distance(pos, posN) = sqrt(dot(d, d)), d = pos - posN, unfused, left to right (oracle convention)
 __device__ __forceinline__ float dist_rn(float px, float py, float pz, float qx, float qy, float qz)
 {
-	// distance(pos, posN) = sqrt(dot(d, d)), d = pos - posN, unfused, left to right (oracle convention)
 	float dx = __fsub_rn(px, qx), dy = __fsub_rn(py, qy), dz = __fsub_rn(pz, qz);
 	float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 	return __fsqrt_rn(s);
 }
 
-struct sym_writer { // accumulates "mirrored" bits of one particle's segment and flushes whole words with atomicOr
-	uint32_t* bits;
-	uint32_t  word_idx, word;
-	__device__ __forceinline__ void begin(uint32_t* b, uint32_t first_bit) { bits = b; word_idx = first_bit >> 5; word = 0u; }
-	__device__ __forceinline__ void put(uint32_t bit_idx, bool v)
-	{
-		uint32_t w = bit_idx >> 5;
-		if (w != word_idx) { flush(); word_idx = w; }
-		if (v) word |= 1u << (bit_idx & 31u);
-	}
-	__device__ __forceinline__ void flush()
-	{
-		if (word) atomicOr(bits + word_idx, word);
-		word = 0u;
-	}
-};
-
-template <bool FILL>
-__global__ void __launch_bounds__(128)
-k_green_emit(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const float* __restrict__ range,
-             const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, const uint32_t* __restrict__ len,
-             apbf_grid_params g, float range_scale, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
-             uint32_t* __restrict__ pairs, uint32_t cap, uint32_t* __restrict__ symbits, uint32_t* misc)
-{
-	const uint32_t n = *len;
-	if (misc[MW_IDENTITY] != 0u) return; // k_green_emit_tiled handles identity index lists
-	const bool ident = false;
-	for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
-		const float r = range[id] * range_scale;
-		const uint32_t idx = ident ? id : index_list[id];
-		const int4 ip = ldg_int4(pos4, idx);
-		const float px = (float)ip.x * INV_R_POS, py = (float)ip.y * INV_R_POS, pz = (float)ip.z * INV_R_POS;
-		uint32_t gmin[3], gmax[3];
-		gmin[0] = apbf_map_axis(px - r, g, 0); gmax[0] = apbf_map_axis(px + r, g, 0);
-		gmin[1] = apbf_map_axis(py - r, g, 1); gmax[1] = apbf_map_axis(py + r, g, 1);
-		gmin[2] = apbf_map_axis(pz - r, g, 2); gmax[2] = apbf_map_axis(pz + r, g, 2);
-		if (g.dims < 3) { gmin[2] = 0u; gmax[2] = 0u; } // * uvec3(1, D > 1, D > 2), neighborhood_green.comp:36
-		uint32_t cnt = 0, out = 0, n_asym = 0;
-		sym_writer sw;
-		if (FILL) { out = offsets[id]; sw.begin(symbits, out); }
-		for (uint32_t cz = gmin[2];; cz++) {
-			for (uint32_t cy = gmin[1];; cy++) {
-				for (uint32_t cx = gmin[0];; cx++) {
-					const uint32_t h = apbf_zhash(cx, cy, cz, g.res, g.dims);
-					const uint32_t s = __ldg(cell_start + h), e = __ldg(cell_end + h);
-					for (uint32_t idN = s; idN < e; idN++) {
-						const uint32_t idxN = ident ? idN : index_list[idN];
-						const int4 iq = ldg_int4(pos4, idxN);
-						const float d = dist_rn(px, py, pz, (float)iq.x * INV_R_POS, (float)iq.y * INV_R_POS, (float)iq.z * INV_R_POS);
-						if (id == idN || d > r) continue;
-						if (FILL) {
-							const uint32_t o = out + cnt;
-							if (o < cap) {
-								*(uint2*)(pairs + 2 * (size_t)o) = make_uint2(id, idN);
-								const bool mirrored = !(d > range[idN] * range_scale); // (idN, id) is in the list too
-								sw.put(o, mirrored);
-								n_asym += mirrored ? 0u : 1u;
-							}
-						}
-						cnt++;
-					}
-					if (cx >= gmax[0]) break;
-				}
-				if (cy >= gmax[1]) break;
-			}
-			if (cz >= gmax[2]) break;
-		}
-		if (FILL) {
-			sw.flush();
-			if (n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
-		} else {
-			counts[id] = cnt;
-		}
-	}
-}
-
-// ---- Green pair emit, warp-tiled (the fast path when the index list is the identity) -----------------------------------
 // Q4[id] = {pos.x, pos.y, pos.z, T}: float position (vec3(ipos) / 2^18) and the acceptance threshold on the SQUARED
 // distance.  sqrt is monotone, so "distance(pos, posN) > range" (neighborhood_green.comp:83) is the same predicate as
 // "d2 > T" with T = the largest float whose correctly rounded square root is still <= range: no square root per
@@ -197,115 +120,188 @@ __device__ __forceinline__ float sqrt_threshold(float r)
 	return x;
 }
 
-__global__ void k_build_q4(const int32_t* __restrict__ pos4, const float* __restrict__ range, float range_scale,
-                           const uint32_t* __restrict__ len, float4* __restrict__ q4, const uint32_t* __restrict__ misc)
+// per id: packed float position + threshold, and the cell key of the particle behind the id
+__global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const uint32_t* __restrict__ hidden_key,
+                           const float* __restrict__ range, float range_scale, const uint32_t* __restrict__ len,
+                           float4* __restrict__ q4, uint32_t* __restrict__ key_id, const uint32_t* __restrict__ misc)
 {
-	if (misc[MW_IDENTITY] == 0u) return;
+	const bool ident = misc[MW_IDENTITY] != 0u;
 	const uint32_t n = *len;
 	for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
-		const int4 ip = ldg_int4(pos4, id);
+		const uint32_t idx = ident ? id : index_list[id];
+		const int4 ip = ldg_int4(pos4, idx);
 		q4[id] = make_float4((float)ip.x * INV_R_POS, (float)ip.y * INV_R_POS, (float)ip.z * INV_R_POS,
 		                     sqrt_threshold(range[id] * range_scale));
+		key_id[id] = hidden_key[idx];
 	}
 }
 
-__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v)
-{
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-	return v;
-}
-__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v)
-{
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-	return v;
-}
+// The pair emit works cell by cell.  All particles of one grid cell are contiguous ids (the lists were just sorted by
+// cell key) and their search boxes [gridMin, gridMax] nearly coincide, so a warp takes the particles of one cell as its
+// QUERIES (staged in shared memory), walks the union of their boxes in the reference's order (x fastest), flattens the
+// occupants of 32 cells at a time into a dense CANDIDATE stream -- one candidate per lane, loaded with one 16-byte
+// read -- and tests every query against the 32 candidates with one ballot.  Hits of one query are appended with the
+// ballot rank, so a query's pairs are written as contiguous runs and keep the reference's discovery order (a candidate
+// outside a query's own box cannot pass the distance test: the cell map is monotone in the position).
+// Work is proportional to the number of candidates, whatever the cell shape, occupancy or the Z-curve's jumps.
+// FILL == false counts the accepted candidates per id, FILL == true writes them at the scanned offsets: the public
+// (id, idN) pair list and the solver's internal list NB[e] = idN | (unmirrored << 31), where "mirrored" means that
+// (idN, id) is in the list as well (d <= range[idN]).
+constexpr int EMIT_WARPS = 8;
 
-// A warp owns 32 consecutive particles (a few neighbouring cells of the Z-curve).  It walks the union of their cell
-// boxes in the reference's order (x fastest); each cell's particles are contiguous in the sorted arrays, so they are
-// staged once per warp in shared memory by a coalesced 16-byte load and then broadcast to all lanes.  A lane only tests
-// the cells inside its own [gridMin, gridMax] box, which keeps every particle's pair order exactly the reference's.
-constexpr int TILED_WARPS = 4;
-template <bool FILL>
-__global__ void __launch_bounds__(TILED_WARPS * 32)
-k_green_emit_tiled(const float4* __restrict__ q4, const float* __restrict__ range, const uint32_t* __restrict__ cell_start,
-                   const uint32_t* __restrict__ cell_end, const uint32_t* __restrict__ len, apbf_grid_params g, float range_scale,
-                   uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ pairs, uint32_t cap,
-                   uint32_t* __restrict__ symbits, uint32_t* misc)
+template <bool FILL, int DIMS>
+__global__ void __launch_bounds__(EMIT_WARPS * 32)
+k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ key_id, const float* __restrict__ range,
+                   const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, const uint32_t* __restrict__ len,
+                   apbf_grid_params g, float range_scale, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                   uint32_t* __restrict__ pairs, uint32_t* __restrict__ nbl, uint32_t cap, uint32_t* misc, int cull)
 {
-	if (misc[MW_IDENTITY] == 0u) return; // the generic kernel handles index lists that are not the identity
-	__shared__ float4 s_slab[TILED_WARPS][32];
+	__shared__ float4 s_q[EMIT_WARPS][32];
 	const uint32_t n = *len;
 	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-	const uint32_t total_warps = gridDim.x * TILED_WARPS;
-	for (uint32_t tile = blockIdx.x * TILED_WARPS + w; (size_t)tile * 32 < n; tile += total_warps) {
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	const uint32_t axis_cap = 1u << g.res; // a box wider than the grid only revisits aliased cells
+	const uint32_t total_warps = gridDim.x * EMIT_WARPS;
+	uint32_t n_asym = 0;
+	for (uint32_t tile = blockIdx.x * EMIT_WARPS + w; (size_t)tile * 32 < n; tile += total_warps) {
 		const uint32_t id = tile * 32u + lane;
-		const bool valid = id < n;
-		float4 me = make_float4(0.f, 0.f, 0.f, -1.0f);
-		uint32_t gmin[3] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, gmax[3] = { 0u, 0u, 0u };
-		if (valid) {
-			me = q4[id];
-			const float r = range[id] * range_scale;
-			gmin[0] = apbf_map_axis(me.x - r, g, 0); gmax[0] = apbf_map_axis(me.x + r, g, 0);
-			gmin[1] = apbf_map_axis(me.y - r, g, 1); gmax[1] = apbf_map_axis(me.y + r, g, 1);
-			gmin[2] = apbf_map_axis(me.z - r, g, 2); gmax[2] = apbf_map_axis(me.z + r, g, 2);
-			if (g.dims < 3) { gmin[2] = 0u; gmax[2] = 0u; }
-			// the reference visits gridMin once even when gridMax < gridMin (its ++cell > gridMax wrap)
-			gmax[0] = max(gmax[0], gmin[0]); gmax[1] = max(gmax[1], gmin[1]); gmax[2] = max(gmax[2], gmin[2]);
-		}
-		uint32_t umin[3], umax[3];
+		const uint32_t key = id < n ? key_id[id] : 0xFFFFFFFFu;
+		uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+		if (lane == 0) prev = id > 0 ? key_id[id - 1] : ~key;
+		uint32_t heads = __ballot_sync(0xffffffffu, id < n && key != prev); // cells that start inside this tile
+		while (heads) {
+			const int hl = __ffs(heads) - 1;
+			heads &= heads - 1u;
+			const uint32_t cell_first = tile * 32u + (uint32_t)hl;
+			const uint32_t cell_last = __ldg(cell_end + __shfl_sync(0xffffffffu, key, hl));
+			for (uint32_t qb = cell_first; qb < cell_last; qb += 32) {
+				const uint32_t nq = min(32u, cell_last - qb);
+				const uint32_t q = qb + lane;
+				const bool valid = lane < nq;
+				float4 me = make_float4(0.f, 0.f, 0.f, -1.0f);
+				uint32_t gmin[3] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, gmax[3] = { 0u, 0u, 0u };
+				uint32_t qc[3] = { 0u, 0u, 0u }; // the query's own cell
+				float r_cull = 0.0f;
+				if (valid) {
+					me = q4[q];
+					const float r = range[q] * range_scale;
+					r_cull = r == r ? r : INFINITY; // a NaN range accepts every candidate
+					qc[0] = apbf_map_axis(me.x, g, 0); qc[1] = apbf_map_axis(me.y, g, 1); qc[2] = apbf_map_axis(me.z, g, 2);
+					gmin[0] = apbf_map_axis(me.x - r, g, 0); gmax[0] = apbf_map_axis(me.x + r, g, 0);
+					gmin[1] = apbf_map_axis(me.y - r, g, 1); gmax[1] = apbf_map_axis(me.y + r, g, 1);
+					gmin[2] = apbf_map_axis(me.z - r, g, 2); gmax[2] = apbf_map_axis(me.z + r, g, 2);
+					if (DIMS < 3) { gmin[2] = 0u; gmax[2] = 0u; } // * uvec3(1, D > 1, D > 2), neighborhood_green.comp:36
+					// the reference visits gridMin once even when gridMax < gridMin (its ++cell > gridMax wrap)
+					gmax[0] = max(gmax[0], gmin[0]); gmax[1] = max(gmax[1], gmin[1]); gmax[2] = max(gmax[2], gmin[2]);
+				}
+				uint32_t umin[3], ext[3];
 #pragma unroll
-		for (int d = 0; d < 3; d++) { umin[d] = warp_min_u32(gmin[d]); umax[d] = warp_max_u32(gmax[d]); }
-		uint32_t cnt = 0, out = 0, n_asym = 0;
-		sym_writer sw;
-		if (FILL && valid) { out = offsets[id]; sw.begin(symbits, out); }
-		for (uint32_t cz = umin[2]; cz <= umax[2]; cz++) {
-			const bool inz = cz >= gmin[2] && cz <= gmax[2];
-			for (uint32_t cy = umin[1]; cy <= umax[1]; cy++) {
-				const bool inzy = inz && cy >= gmin[1] && cy <= gmax[1];
-				for (uint32_t cx = umin[0]; cx <= umax[0]; cx++) {
-					const bool inbox = inzy && cx >= gmin[0] && cx <= gmax[0];
-					const uint32_t h = apbf_zhash(cx, cy, cz, g.res, g.dims);
-					const uint32_t s = __ldg(cell_start + h), e = __ldg(cell_end + h);
-					for (uint32_t c0 = s; c0 < e; c0 += 32) {
-						const uint32_t m = min(32u, e - c0);
-						if (lane < m) s_slab[w][lane] = q4[c0 + lane];
-						__syncwarp();
-						if (inbox) {
-							for (uint32_t j = 0; j < m; j++) {
-								const float4 q = s_slab[w][j];
-								const uint32_t idN = c0 + j;
-								const float dx = __fsub_rn(me.x, q.x), dy = __fsub_rn(me.y, q.y), dz = __fsub_rn(me.z, q.z);
-								const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-								if (id == idN || d2 > me.w) continue;
-								if (FILL) {
-									const uint32_t o = out + cnt;
-									if (o < cap) {
-										*(uint2*)(pairs + 2 * (size_t)o) = make_uint2(id, idN);
-										const bool mirrored = !(d2 > q.w); // (idN, id) is in the list too
-										sw.put(o, mirrored);
-										n_asym += mirrored ? 0u : 1u;
-									}
+				for (int d = 0; d < 3; d++) {
+					umin[d] = __reduce_min_sync(0xffffffffu, gmin[d]);
+					ext[d] = min(__reduce_max_sync(0xffffffffu, gmax[d]) - umin[d], axis_cap - 1u) + 1u;
+				}
+				// Cells farther from the queries' cell than the largest range cannot hold a hit: the gap between two cells is
+				// (|dc| - 1) cell widths per axis; 1.01 instead of 1 covers the rounding of the cell map (< 2e-4 cells).
+				// The gap is taken to the box [qlo, qhi] of the queries' cells (one cell whenever the particles lie inside
+				// the grid; particles outside it alias into the same key from different cells).
+				r_cull = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(r_cull, 0.0f))));
+				const float cull2 = cull ? r_cull * r_cull * 1.0001f : INFINITY;
+				float csz[3];
+				int qlo[3], qhi[3];
+#pragma unroll
+				for (int d = 0; d < 3; d++) {
+					qlo[d] = (int)min(__reduce_min_sync(0xffffffffu, valid ? qc[d] : 0xFFFFFFFFu), 0x7FFFFFFFu);
+					qhi[d] = (int)min(__reduce_max_sync(0xffffffffu, valid ? qc[d] : 0u), 0x7FFFFFFFu);
+					csz[d] = g.ext[d] / g.scale;
+				}
+				if (DIMS < 3) csz[2] = 0.0f; // z is not gridded in 2-D but the distance stays 3-D
+				__syncwarp();
+				s_q[w][lane] = me;
+				__syncwarp();
+				const uint32_t nxy = ext[0] * ext[1], ncell = nxy * ext[2];
+				const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)ext[0];
+				uint32_t my_off = (FILL && valid) ? offsets[q] : 0u, my_cnt = 0u;
+				for (uint32_t cbase = 0; cbase < ncell; cbase += 32) {
+					const uint32_t ci = cbase + lane;
+					uint32_t c_first = 0u, c_cnt = 0u;
+					if (ci < ncell) {
+						// ci = (cz * ny + cy) * nx + cx; float reciprocals + one correction step are exact for ci < 2^24
+						uint32_t cz, cy;
+						if (ncell <= (1u << 24)) {
+							cz = (uint32_t)((float)ci * inv_nxy);
+							if (cz * nxy > ci) cz--; else if ((cz + 1u) * nxy <= ci) cz++;
+						} else {
+							cz = ci / nxy;
+						}
+						const uint32_t rem = ci - cz * nxy;
+						if (ncell <= (1u << 24)) {
+							cy = (uint32_t)((float)rem * inv_nx);
+							if (cy * ext[0] > rem) cy--; else if ((cy + 1u) * ext[0] <= rem) cy++;
+						} else {
+							cy = rem / ext[0];
+						}
+						const uint32_t cx = rem - cy * ext[0];
+						const uint32_t ax = umin[0] + cx, ay = umin[1] + cy, az = umin[2] + cz;
+						const int ix = (int)min(ax, 0x7FFFFFFFu), iy = (int)min(ay, 0x7FFFFFFFu), iz = (int)min(az, 0x7FFFFFFFu);
+						const float gx = fmaxf((float)max(qlo[0] - ix, ix - qhi[0]) - 1.01f, 0.0f) * csz[0];
+						const float gy = fmaxf((float)max(qlo[1] - iy, iy - qhi[1]) - 1.01f, 0.0f) * csz[1];
+						const float gz = fmaxf((float)max(qlo[2] - iz, iz - qhi[2]) - 1.01f, 0.0f) * csz[2];
+						if (!(gx * gx + gy * gy + gz * gz > cull2)) {
+							const uint32_t h = apbf_zhash<DIMS>(ax, ay, az, g.res);
+							c_first = __ldg(cell_start + h);
+							c_cnt = __ldg(cell_end + h) - c_first;
+						}
+					}
+					uint32_t incl = c_cnt;
+#pragma unroll
+					for (int o = 1; o < 32; o <<= 1) {
+						const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+						if (lane >= (unsigned)o) incl += t;
+					}
+					const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+					const uint32_t c_base = c_first - (incl - c_cnt); // candidate t of this cell is id c_base + t
+					for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+						const uint32_t t = t0 + lane;
+						// the cell that holds candidate t: first lane whose inclusive count exceeds t
+						uint32_t pos = 0u;
+#pragma unroll
+						for (int step = 16; step > 0; step >>= 1) {
+							const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(pos + step - 1));
+							if (v <= t) pos += step;
+						}
+						const uint32_t cand = __shfl_sync(0xffffffffu, c_base, (int)(pos & 31u)) + t;
+						const bool cvalid = t < total;
+						float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+						if (cvalid) c4 = q4[cand];
+						for (uint32_t qi = 0; qi < nq; qi++) {
+							const float4 qv = s_q[w][qi];
+							const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
+							const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+							const bool hit = cvalid && !(d2 > qv.w) && cand != qb + qi;
+							const uint32_t b = __ballot_sync(0xffffffffu, hit);
+							if (b == 0u) continue;
+							if (FILL) {
+								const uint32_t o = __shfl_sync(0xffffffffu, my_off, (int)qi) + __popc(b & lt_mask);
+								if (hit && o < cap) {
+									const bool mirrored = !(d2 > c4.w);
+									*(uint2*)(pairs + 2 * (size_t)o) = make_uint2(qb + qi, cand);
+									nbl[o] = cand | (mirrored ? 0u : NB_UNMIRRORED);
+									n_asym += mirrored ? 0u : 1u;
 								}
-								cnt++;
+								if (lane == qi) my_off += __popc(b);
+							} else if (lane == qi) {
+								my_cnt += __popc(b);
 							}
 						}
-						__syncwarp();
 					}
-					if (cx == 0xFFFFFFFFu) break;
 				}
-				if (cy == 0xFFFFFFFFu) break;
+				if (!FILL && valid) counts[q] = my_cnt;
 			}
-			if (cz == 0xFFFFFFFFu) break;
 		}
-		if (FILL) {
-			if (valid) sw.flush();
-			n_asym = __reduce_add_sync(0xffffffffu, n_asym);
-			if (lane == 0 && n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
-		} else if (valid) {
-			counts[id] = cnt;
-		}
+	}
+	if (FILL) {
+		n_asym = __reduce_add_sync(0xffffffffu, n_asym);
+		if (lane == 0 && n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
 	}
 }
 
@@ -356,7 +352,7 @@ __global__ void __launch_bounds__(128)
 k_bsearch_emit(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const uint32_t* __restrict__ c0,
                const uint32_t* __restrict__ c1, const uint32_t* __restrict__ c2, const float* __restrict__ range,
                const uint32_t* __restrict__ len, float range_scale, uint32_t* __restrict__ counts,
-               const uint32_t* __restrict__ offsets, uint32_t* __restrict__ pairs, uint32_t cap, uint32_t* __restrict__ symbits,
+               const uint32_t* __restrict__ offsets, uint32_t* __restrict__ pairs, uint32_t cap, uint32_t* __restrict__ nbl,
                uint32_t* misc)
 {
 	const uint32_t n = *len;
@@ -389,8 +385,7 @@ k_bsearch_emit(const uint32_t* __restrict__ index_list, const int32_t* __restric
 		zs[1] = and96(center, zMask3);
 		const float px = (float)ip.x * INV_R_POS, py = (float)ip.y * INV_R_POS, pz = (float)ip.z * INV_R_POS;
 		uint32_t cnt = 0, out = 0, n_asym = 0;
-		sym_writer sw;
-		if (FILL) { out = offsets[id]; sw.begin(symbits, out); }
+		if (FILL) out = offsets[id];
 		for (int cz = 0; cz < 3; cz++) for (int cy = 0; cy < 3; cy++) for (int cx = 0; cx < 3; cx++) {
 			const u96 cellCode = or96(or96(xs[cx], ys[cy]), zs[cz]);
 			const u96 cellLast = or96(cellCode, mask);
@@ -405,7 +400,7 @@ k_bsearch_emit(const uint32_t* __restrict__ index_list, const int32_t* __restric
 						if (o < cap) {
 							*(uint2*)(pairs + 2 * (size_t)o) = make_uint2(id, idN);
 							const bool mirrored = d <= range[idN] * range_scale;
-							sw.put(o, mirrored);
+							nbl[o] = idN | (mirrored ? 0u : NB_UNMIRRORED);
 							n_asym += mirrored ? 0u : 1u;
 						}
 					}
@@ -414,7 +409,6 @@ k_bsearch_emit(const uint32_t* __restrict__ index_list, const int32_t* __restric
 			}
 		}
 		if (FILL) {
-			sw.flush();
 			if (n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
 		} else {
 			counts[id] = cnt;
@@ -508,10 +502,10 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 	uint32_t* ce = (uint32_t*)ctx->scratch_get(SLOT_CELL_END, sizeof(uint32_t) * (size_t)max_hash);
 	uint32_t* counts = (uint32_t*)ctx->scratch_get(SLOT_COUNTS, sizeof(uint32_t) * (size_t)(n_cap + 1));
 	uint32_t* offsets = (uint32_t*)ctx->scratch_get(SLOT_OFFSETS, sizeof(uint32_t) * (size_t)(n_cap + 1));
-	const size_t sym_words = ((size_t)nb->capacity + 31) / 32 + 1;
-	uint32_t* symbits = (uint32_t*)ctx->scratch_get(SLOT_SYMBITS, sizeof(uint32_t) * sym_words);
+	uint32_t* nbl = (uint32_t*)ctx->scratch_get(SLOT_NB, sizeof(uint32_t) * ((size_t)nb->capacity + 1));
 	float4* q4 = (float4*)ctx->scratch_get(SLOT_Q4, sizeof(float4) * (size_t)n_cap);
-	if (!keys || !skeys || !sidx || !cs || !ce || !counts || !offsets || !symbits || !misc || !q4)
+	uint32_t* key_id = (uint32_t*)ctx->scratch_get(SLOT_KEY_ID, sizeof(uint32_t) * (size_t)n_cap);
+	if (!keys || !skeys || !sidx || !cs || !ce || !counts || !offsets || !nbl || !misc || !q4 || !key_id)
 		return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 
 	// hash all hidden particles (neighborhood_green.cpp:50-52), sort by hash with the slot as payload (:53)
@@ -536,33 +530,32 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 	// pairs (:64-74): count, scan, fill
 	k_clear_search_words<<<1, 1, 0, st>>>(misc);
 	APBF_LAUNCHED(ctx);
-	// Two kernels per pass, selected on the device by the identity flag (the host never reads it): the warp-tiled one
-	// when the index list is the identity over the sorted particles, the generic one otherwise.
-	const unsigned grid = apbf_grid(ctx, n_cap, 128, 16);
-	const unsigned tgrid = apbf_grid(ctx, n_cap, TILED_WARPS * 32, 12);
+	const unsigned egrid = apbf_grid(ctx, n_cap, EMIT_WARPS * 32, 6);
+	static const int cull = getenv("APBF_NO_CULL") ? 0 : 1; // debugging aid: walk every cell of the union box
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_COUNT);
-		k_build_q4<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>(new_pos, new_range, range_scale, p.length, q4, misc);
+		k_build_q4<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>(new_index, new_pos, skeys, new_range, range_scale, p.length, q4, key_id, misc);
 		APBF_LAUNCHED(ctx);
-		k_green_emit_tiled<false><<<tgrid, TILED_WARPS * 32, 0, st>>>(q4, new_range, cs, ce, p.length, g, range_scale, counts, nullptr,
-		                                                              nullptr, 0u, nullptr, misc);
-		APBF_LAUNCHED(ctx);
-		k_green_emit<false><<<grid, 128, 0, st>>>(new_index, new_pos, new_range, cs, ce, p.length, g, range_scale, counts, nullptr,
-		                                          nullptr, 0u, nullptr, misc);
+		if (g.dims == 3)
+			k_green_emit_cells<false, 3><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, counts,
+			                                                               nullptr, nullptr, nullptr, 0u, misc, cull);
+		else
+			k_green_emit_cells<false, 2><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, counts,
+			                                                               nullptr, nullptr, nullptr, 0u, misc, cull);
 		APBF_LAUNCHED(ctx);
 	}
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_SCAN);
 		APBF_TRY(apbf_scan_u32(ctx, counts, offsets, p.length, n_cap, false, nb->length, nb->capacity, misc + MW_FLAGS, misc + MW_TOTAL_PAIRS));
-		APBF_CUDA(ctx, cudaMemsetAsync(symbits, 0, sizeof(uint32_t) * sym_words, st));
 	}
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
-		k_green_emit_tiled<true><<<tgrid, TILED_WARPS * 32, 0, st>>>(q4, new_range, cs, ce, p.length, g, range_scale, nullptr, offsets,
-		                                                             nb->pairs, nb->capacity, symbits, misc);
-		APBF_LAUNCHED(ctx);
-		k_green_emit<true><<<grid, 128, 0, st>>>(new_index, new_pos, new_range, cs, ce, p.length, g, range_scale, nullptr, offsets,
-		                                         nb->pairs, nb->capacity, symbits, misc);
+		if (g.dims == 3)
+			k_green_emit_cells<true, 3><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, nullptr,
+			                                                              offsets, nb->pairs, nbl, nb->capacity, misc, cull);
+		else
+			k_green_emit_cells<true, 2><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, nullptr,
+			                                                              offsets, nb->pairs, nbl, nb->capacity, misc, cull);
 		APBF_LAUNCHED(ctx);
 	}
 	ctx->nbr_struct_pairs = nb->pairs;
@@ -597,9 +590,8 @@ int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, cons
 	                   (uint32_t*)ctx->scratch_get(SLOT_CODE2, sizeof(uint32_t) * (size_t)nh_cap) };
 	uint32_t* counts = (uint32_t*)ctx->scratch_get(SLOT_COUNTS, sizeof(uint32_t) * (size_t)(n_cap + 1));
 	uint32_t* offsets = (uint32_t*)ctx->scratch_get(SLOT_OFFSETS, sizeof(uint32_t) * (size_t)(n_cap + 1));
-	const size_t sym_words = ((size_t)nb->capacity + 31) / 32 + 1;
-	uint32_t* symbits = (uint32_t*)ctx->scratch_get(SLOT_SYMBITS, sizeof(uint32_t) * sym_words);
-	if (!code || !scode || !idx_a || !idx_b || !c[0] || !c[1] || !c[2] || !counts || !offsets || !symbits || !misc)
+	uint32_t* nbl = (uint32_t*)ctx->scratch_get(SLOT_NB, sizeof(uint32_t) * ((size_t)nb->capacity + 1));
+	if (!code || !scode || !idx_a || !idx_b || !c[0] || !c[1] || !c[2] || !counts || !offsets || !nbl || !misc)
 		return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 
 	// three stable 32-bit sorts, least significant section first (neighborhood_binary_search.cpp:45-51)
@@ -625,9 +617,8 @@ int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, cons
 	                                            nullptr, nullptr, 0u, nullptr, misc);
 	APBF_LAUNCHED(ctx);
 	APBF_TRY(apbf_scan_u32(ctx, counts, offsets, p.length, n_cap, false, nb->length, nb->capacity, misc + MW_FLAGS, misc + MW_TOTAL_PAIRS));
-	APBF_CUDA(ctx, cudaMemsetAsync(symbits, 0, sizeof(uint32_t) * sym_words, st));
 	k_bsearch_emit<true><<<grid, 128, 0, st>>>(new_index, new_pos, c[0], c[1], c[2], new_range, p.length, range_scale, nullptr,
-	                                           offsets, nb->pairs, nb->capacity, symbits, misc);
+	                                           offsets, nb->pairs, nb->capacity, nbl, misc);
 	APBF_LAUNCHED(ctx);
 	ctx->nbr_struct_pairs = nb->pairs;
 	ctx->nbr_struct_n_cap = n_cap;

@@ -1,16 +1,17 @@
 // neighbors.cuh -- the grouped neighbour-list structure shared between the searches (neighbors.cu) and the sweeps
-// over it (solver.cu).
+// over it (solver.cu, incompress.cu).
 #pragma once
 #include "common.cuh"
 
-// The searches emit pairs grouped by id: pairs [offsets[id], offsets[id+1]) all have .x == id.  One bit per pair says
-// whether the mirrored pair (idN, id) is in the list as well; the sweeps gather through mirrored pairs and fall back to
-// integer atomics only for the unmirrored ones (variable kernel widths).  The structure lives in the context's scratch
-// memory and belongs to the pair buffer it was built for.
-struct apbf_nbr_struct {
-	const uint32_t* offsets; // [n + 1], unclamped running pair counts
-	uint32_t*       symbits; // [ceil(capacity / 32)]
-};
+// The searches emit pairs grouped by id: pairs [offsets[id], offsets[id+1]) all have .x == id.  Next to the public
+// (id, idN) list (the reference's pbd::neighbors layout) they write the solver's own 4-byte list
+//     NB[e] = idN | (unmirrored << 31)
+// where "mirrored" says that the pair (idN, id) is in the list as well; the sweeps gather through mirrored pairs and
+// fall back to integer atomics only for the unmirrored ones (variable kernel widths).  ids stay below 2^31 (the pair
+// counter is a u32).  The structure (offsets + NB) lives in the context's scratch memory and belongs to the
+// pair buffer it was built for.
+constexpr uint32_t NB_UNMIRRORED = 0x80000000u;
+constexpr uint32_t NB_ID_MASK = 0x7FFFFFFFu;
 
 static inline bool apbf_nbr_struct_valid(const apbf_ctx* ctx, const apbf_neighbors* nb)
 {

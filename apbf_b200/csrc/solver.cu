@@ -7,6 +7,7 @@
 #include "box.cuh"
 #include "neighbors.cuh"
 #include "sort.cuh"
+#include <utility>
 
 namespace {
 
@@ -40,14 +41,13 @@ struct kw_args {
 	const float*    target_radius; // per id
 	float*          kernel_width;  // per id (old on input)
 	uint32_t*       kwfx;          // per id
-	const uint32_t* pairs;
+	const uint32_t* nbl;           // idN | (unmirrored << 31) per pair
 	const uint32_t* offsets;
-	uint32_t*       symbits;
 	uint32_t        pair_cap;
 	uint32_t*       keep_counts;
 	const uint32_t* keep_offsets;
 	uint32_t*       out_pairs;
-	uint32_t*       out_symbits;
+	uint32_t*       out_nbl;
 	uint32_t*       misc;
 	int             base_on_target_radius;
 	float           speed;
@@ -100,12 +100,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_kw_sweep(kw_args A)
 			bool keep = false, mirrored = false, new_mirrored = false;
 			uint32_t b = 0;
 			if (e < end) {
-				b = A.pairs[2 * (size_t)e + 1];
+				const uint32_t nbe = A.nbl[e];
+				b = nbe & NB_ID_MASK;
 				const uint32_t idxN = ident ? b : A.index_list[b];
 				const int4 iq = __ldg((const int4*)A.pos4 + idxN);
 				const float rx = (float)(iq.x - ip.x) * INV_R_POS, ry = (float)(iq.y - ip.y) * INV_R_POS, rz = (float)(iq.z - ip.z) * INV_R_POS;
 				const float dist = sqrtf(dot3(rx, ry, rz, rx, ry, rz));
-				mirrored = (A.symbits[e >> 5] >> (e & 31u)) & 1u;
+				mirrored = (nbe & NB_UNMIRRORED) == 0u;
 				keep = dist <= cutoff_a; // kernel_width.comp:57
 				if (!COMPACT) {
 					if (mirrored) mx = max(mx, kw_influence(kw_original(A, b, idxN), dist)); // the pair (b, a) spreads b's width onto a
@@ -122,8 +123,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_kw_sweep(kw_args A)
 				if (keep) {
 					const uint32_t o = out + rank;
 					*(uint2*)(A.out_pairs + 2 * (size_t)o) = make_uint2(a, b);
-					if (new_mirrored) atomicOr(A.out_symbits + (o >> 5), 1u << (o & 31u));
-					else n_asym++;
+					A.out_nbl[o] = b | (new_mirrored ? 0u : NB_UNMIRRORED);
+					n_asym += new_mirrored ? 0u : 1u;
 				}
 				out += __popc(ballot);
 			}
@@ -157,6 +158,13 @@ __global__ void k_kw_finish(kw_args A)
 }
 
 __global__ void k_reset_asym(uint32_t* misc) { misc[MW_N_ASYM] = 0u; }
+
+// dst[0 .. *len) = src[0 .. *len), 8-byte elements (the kept pairs go back into the caller's list)
+__global__ void k_copy_pairs_len(const uint2* __restrict__ src, uint2* __restrict__ dst, const uint32_t* __restrict__ len)
+{
+	const uint32_t n = *len;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
 
 // ---- box collision (box_collision.comp:36-60) ------------------------------------------------------------------------------
 __global__ void k_box_collision(const uint32_t* __restrict__ index_list, int32_t* pos4, const float* __restrict__ radius,
@@ -208,7 +216,6 @@ int apbf_spread_kernel_width_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighb
 	const uint32_t n_cap = p.capacity;
 	if (n_cap == 0) return APBF_OK;
 	cudaStream_t st = ctx->stream;
-	const size_t sym_words = ((size_t)nb->capacity + 31) / 32 + 1;
 	kw_args A;
 	memset(&A, 0, sizeof A);
 	A.index_list = (const uint32_t*)p.index_list.data;
@@ -218,20 +225,20 @@ int apbf_spread_kernel_width_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighb
 	A.target_radius = (const float*)fluid->target_radius.data;
 	A.kernel_width = (float*)fluid->kernel_width.data;
 	A.kwfx = (uint32_t*)ctx->scratch_get(SLOT_KWFX, sizeof(uint32_t) * (size_t)n_cap);
-	A.pairs = nb->pairs;
 	A.pair_cap = nb->capacity;
 	uint32_t* offsets = (uint32_t*)ctx->scratch_get(SLOT_OFFSETS, sizeof(uint32_t) * (size_t)(n_cap + 1));
 	A.offsets = offsets;
-	A.symbits = (uint32_t*)ctx->scratch_get(SLOT_SYMBITS, sizeof(uint32_t) * sym_words);
+	uint32_t* nbl = (uint32_t*)ctx->scratch_get(SLOT_NB, sizeof(uint32_t) * ((size_t)nb->capacity + 1));
+	A.nbl = nbl;
 	A.keep_counts = (uint32_t*)ctx->scratch_get(SLOT_KEEP_COUNTS, sizeof(uint32_t) * (size_t)(n_cap + 1));
 	uint32_t* keep_offsets = (uint32_t*)ctx->scratch_get(SLOT_KEEP_OFFSETS, sizeof(uint32_t) * (size_t)(n_cap + 1));
 	A.keep_offsets = keep_offsets;
 	A.out_pairs = (uint32_t*)ctx->scratch_get(SLOT_PAIRS_TMP, sizeof(uint32_t) * 2 * (size_t)nb->capacity);
-	A.out_symbits = (uint32_t*)ctx->scratch_get(SLOT_SYMBITS_TMP, sizeof(uint32_t) * sym_words);
+	A.out_nbl = (uint32_t*)ctx->scratch_get(SLOT_NB_TMP, sizeof(uint32_t) * ((size_t)nb->capacity + 1));
 	A.misc = ctx->misc();
 	A.base_on_target_radius = ctx->settings.mBaseKernelWidthOnTargetRadius;
 	A.speed = ctx->settings.mKernelWidthAdaptionSpeed;
-	if (!A.kwfx || !offsets || !A.symbits || !A.keep_counts || !keep_offsets || !A.out_pairs || !A.out_symbits)
+	if (!A.kwfx || !offsets || !nbl || !A.keep_counts || !keep_offsets || !A.out_pairs || !A.out_nbl)
 		return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 	const unsigned egrid = apbf_grid(ctx, n_cap, 256);
 	const unsigned sgrid = apbf_grid(ctx, (size_t)n_cap * GROUP, SWEEP_THREADS, 8);
@@ -248,7 +255,6 @@ int apbf_spread_kernel_width_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighb
 	apbf_prof_scope ps_compact(ctx, PROF_KW_COMPACT);
 	// prune: scan the kept counts, compact into scratch, then the scratch list becomes the neighbour list
 	APBF_TRY(apbf_scan_u32(ctx, A.keep_counts, keep_offsets, p.length, n_cap, false, nb->length, nb->capacity, nullptr, A.misc + MW_KEPT_PAIRS));
-	APBF_CUDA(ctx, cudaMemsetAsync(A.out_symbits, 0, sizeof(uint32_t) * sym_words, st));
 	k_reset_asym<<<1, 1, 0, st>>>(A.misc);
 	APBF_LAUNCHED(ctx);
 	k_kw_sweep<true><<<sgrid, SWEEP_THREADS, 0, st>>>(A);
@@ -256,9 +262,12 @@ int apbf_spread_kernel_width_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighb
 	if (out_kw_fixed) APBF_CUDA(ctx, cudaMemcpyAsync(out_kw_fixed, A.kwfx, sizeof(uint32_t) * (size_t)n_cap, cudaMemcpyDeviceToDevice, st));
 	k_kw_finish<<<egrid, 256, 0, st>>>(A);
 	APBF_LAUNCHED(ctx);
-	APBF_CUDA(ctx, cudaMemcpyAsync(nb->pairs, A.out_pairs, sizeof(uint32_t) * 2 * (size_t)nb->capacity, cudaMemcpyDeviceToDevice, st));
-	APBF_CUDA(ctx, cudaMemcpyAsync(A.symbits, A.out_symbits, sizeof(uint32_t) * sym_words, cudaMemcpyDeviceToDevice, st));
-	APBF_CUDA(ctx, cudaMemcpyAsync(offsets, keep_offsets, sizeof(uint32_t) * (size_t)(n_cap + 1), cudaMemcpyDeviceToDevice, st));
+	// the pruned list replaces the neighbour list: pairs go back into the caller's buffer (only the kept ones are
+	// copied), the solver's own structure just swaps scratch buffers
+	k_copy_pairs_len<<<apbf_grid(ctx, nb->capacity, 256, 16), 256, 0, st>>>((const uint2*)A.out_pairs, (uint2*)nb->pairs, nb->length);
+	APBF_LAUNCHED(ctx);
+	std::swap(ctx->scratch[SLOT_NB], ctx->scratch[SLOT_NB_TMP]);
+	std::swap(ctx->scratch[SLOT_OFFSETS], ctx->scratch[SLOT_KEEP_OFFSETS]);
 	return APBF_OK;
 }
 

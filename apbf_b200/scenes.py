@@ -144,19 +144,25 @@ def dam_break(nx=100, ny=100, nz=100, r=1.0, jitter=0.05, seed=99, adaptive=True
 
 
 def waterdrop(side=160, r=1.0, jitter=0.05, seed=5, wall_gap=0.0):
-    """configs[2]: per-particle radius classes {r, 2^(1/3) r, 2^(2/3) r, 2r} by depth (emulates split/merge
-    output) -> variable kernel widths and neighbour-count skew."""
-    def radius_of(pos):
-        y = pos[:, 1]
-        t = (y - y.min()) / max(float(y.max() - y.min()), 1e-6)
-        cls = np.minimum((t * 4).astype(np.int32), 3)
-        return (np.float32(r) * np.power(np.float32(2.0), (3 - cls).astype(np.float32) / np.float32(3.0)))
-    half = side * r
-    origin = (-(side - 1) * r,) * 3
-    arrays = _lattice_state((side,) * 3, origin, r, jitter, seed, 3, radius_of)
+    """configs[2]: four radius classes {r, 2^(1/3) r, 2^(2/3) r, 2r} stacked by depth (emulates split/merge output,
+    SURVEY 8d-3): finest at the top, coarsest at the bottom, every class seeded on its own lattice of spacing 2 r_c so
+    that the rest density is right everywhere -> variable kernel widths, unmirrored pairs, neighbour-count skew.
+    `side` = number of finest-class particles that would fit along one axis."""
+    L = 2.0 * r * side
+    half = 0.5 * L
+    parts = []
+    for c in range(4):                      # c = 0: top slab (finest) ... c = 3: bottom slab (radius 2r)
+        rc = float(np.float32(r) * np.power(np.float32(2.0), np.float32(c) / np.float32(3.0)))
+        sp = 2.0 * rc
+        nxz = max(int(L / sp), 1)
+        ny = max(int((L / 4.0) / sp), 1)
+        y_top = half - c * (L / 4.0)
+        origin = (-0.5 * sp * (nxz - 1), y_top - rc - sp * (ny - 1), -0.5 * sp * (nxz - 1))
+        parts.append(_lattice_state((nxz, ny, nxz), origin, rc, jitter * rc / r if jitter else 0.0, seed + c, 3))
+    arrays = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    arrays["index_list"] = np.arange(arrays["position"].shape[0], dtype=np.uint32)
     lo = -(half + 12 * r); hi = half + 12 * r
     sc = Scene(name=f"waterdrop_{side}^3", dims=3, arrays=shuffle_state(arrays, seed), min_pos=(lo,) * 3, max_pos=(hi,) * 3,
                res_log2=_res_for(hi - lo, 8.0 * r), basic_pbf=False, solver_iterations=4, smallest_target_radius=r)
     sc.box_min, sc.box_max = pool_walls((-half - wall_gap,) * 3, (half + wall_gap,) * 3, r, 3)
     return sc
-

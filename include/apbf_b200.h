@@ -195,6 +195,7 @@ typedef struct apbf_search_debug {
 	uint32_t* cell_start;     /* [1 << (res*dims)] (Green)                                                        */
 	uint32_t* cell_end;
 	uint32_t* code[3];        /* [capacity] sorted 96-bit Morton code sections (binary search)                    */
+	uint32_t* pair_offsets;   /* [capacity + 1] pairs of id are [pair_offsets[id], pair_offsets[id + 1]) of the list */
 } apbf_search_debug;
 
 /* ---- operators --------------------------------------------------------------------------------------------- */
