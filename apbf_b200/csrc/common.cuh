@@ -42,6 +42,7 @@ enum apbf_misc_word {
 	MW_TOTAL_PAIRS = 2,  // unclamped pair count of the last search
 	MW_IDENTITY = 3,     // 1 if the index list is the identity over all hidden particles
 	MW_KEPT_PAIRS = 4,   // pair count after the last spread_kernel_width prune
+	MW_OCC_CELLS = 5,    // number of occupied grid cells seen by the last Green search
 	MW_TICKET0 = 8,      // tile tickets of the chained-scan kernels (8 words)
 	MW_SCAN_TOTAL = 16,
 	MW_WORDS = 64

@@ -123,7 +123,7 @@ __device__ __forceinline__ float sqrt_threshold(float r)
 // per id: packed float position + threshold, and the cell key of the particle behind the id
 __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const uint32_t* __restrict__ hidden_key,
                            const float* __restrict__ range, float range_scale, const uint32_t* __restrict__ len,
-                           float4* __restrict__ q4, uint32_t* __restrict__ key_id, const uint32_t* __restrict__ misc)
+                           float4* __restrict__ q4, uint32_t* __restrict__ key_id, uint32_t* __restrict__ misc)
 {
 	const bool ident = misc[MW_IDENTITY] != 0u;
 	const uint32_t n = *len;
@@ -132,18 +132,27 @@ __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_
 		const int4 ip = ldg_int4(pos4, idx);
 		q4[id] = make_float4((float)ip.x * INV_R_POS, (float)ip.y * INV_R_POS, (float)ip.z * INV_R_POS,
 		                     sqrt_threshold(range[id] * range_scale));
-		key_id[id] = hidden_key[idx];
+		const uint32_t key = hidden_key[idx];
+		key_id[id] = key;
+		// occupied cells = ids whose key differs from their predecessor's (the emit sizes its query blocks with it)
+		const bool head = id == 0u || hidden_key[ident ? id - 1u : index_list[id - 1u]] != key;
+		const uint32_t heads = __ballot_sync(__activemask(), head);
+		if (head && (heads & ((1u << lane_id()) - 1u)) == 0u) atomicAdd(misc + MW_OCC_CELLS, (uint32_t)__popc(heads));
 	}
 }
 
-// The pair emit works cell by cell.  All particles of one grid cell are contiguous ids (the lists were just sorted by
-// cell key) and their search boxes [gridMin, gridMax] nearly coincide, so a warp takes the particles of one cell as its
-// QUERIES (staged in shared memory), walks the union of their boxes in the reference's order (x fastest), flattens the
-// occupants of 32 cells at a time into a dense CANDIDATE stream -- one candidate per lane, loaded with one 16-byte
-// read -- and tests every query against the 32 candidates with one ballot.  Hits of one query are appended with the
-// ballot rank, so a query's pairs are written as contiguous runs and keep the reference's discovery order (a candidate
-// outside a query's own box cannot pass the distance test: the cell map is monotone in the position).
-// Work is proportional to the number of candidates, whatever the cell shape, occupancy or the Z-curve's jumps.
+// The pair emit works on groups of neighbouring cells.  The lists were just sorted by cell key, so the particles of a
+// cell -- and of an aligned 2x2x2 / 4x4x4 block of cells, which is a contiguous key range of the Z-curve -- are
+// consecutive ids with nearly the same search box [gridMin, gridMax].  A warp owns 32 consecutive ids (a tile) and
+// splits them into runs of equal block key; the run's particles are the QUERIES (staged in shared memory).  The warp
+// walks the union of their boxes in the reference's order (x fastest), skips the cells that are farther away than
+// the largest range, flattens the occupants of 32 cells at a time into a dense CANDIDATE stream -- one candidate per
+// lane, one 16-byte load each -- and tests every query against the 32 candidates with one ballot.  Hits of one query
+// are appended with the ballot rank, so a query's pairs are written as contiguous runs and keep the reference's
+// discovery order (a candidate outside a query's own box cannot pass the distance test: the cell map is monotone in
+// the position).  Work is proportional to the number of candidates, whatever the cell shape, occupancy or the
+// Z-curve's jumps.  The block size adapts to the occupancy (k_build_q4 counts the occupied cells): sparse grids
+// (a few particles per cell) group 8 or 64 cells so that a run still has a few dozen queries to amortise the walk.
 // FILL == false counts the accepted candidates per id, FILL == true writes them at the scanned offsets: the public
 // (id, idN) pair list and the solver's internal list NB[e] = idN | (unmirrored << 31), where "mirrored" means that
 // (idN, id) is in the list as well (d <= range[idN]).
@@ -162,142 +171,139 @@ k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ k
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	const uint32_t axis_cap = 1u << g.res; // a box wider than the grid only revisits aliased cells
 	const uint32_t total_warps = gridDim.x * EMIT_WARPS;
+	// query block: 1 cell, 2^D cells or 4^D cells, from the mean occupancy of the occupied cells
+	const uint32_t occupied = max(misc[MW_OCC_CELLS], 1u);
+	const uint32_t gshift = (n > 4u * occupied) ? 0u : ((2u * n > occupied) ? (uint32_t)DIMS : 2u * (uint32_t)DIMS);
+	float csz[3];
+#pragma unroll
+	for (int d = 0; d < 3; d++) csz[d] = g.ext[d] / g.scale;
+	if (DIMS < 3) csz[2] = 0.0f; // z is not gridded in 2-D but the distance stays 3-D
 	uint32_t n_asym = 0;
 	for (uint32_t tile = blockIdx.x * EMIT_WARPS + w; (size_t)tile * 32 < n; tile += total_warps) {
-		const uint32_t id = tile * 32u + lane;
-		const uint32_t key = id < n ? key_id[id] : 0xFFFFFFFFu;
-		uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-		if (lane == 0) prev = id > 0 ? key_id[id - 1] : ~key;
-		uint32_t heads = __ballot_sync(0xffffffffu, id < n && key != prev); // cells that start inside this tile
+		const uint32_t tile_first = tile * 32u;
+		const uint32_t id = tile_first + lane;
+		const bool in = id < n;
+		float4 me = make_float4(0.f, 0.f, 0.f, -1.0f);
+		uint32_t gmin[3] = { 0u, 0u, 0u }, gmax[3] = { 0u, 0u, 0u }, qc[3] = { 0u, 0u, 0u };
+		uint32_t gkey = 0xFFFFFFFFu;
+		float r_lane = 0.0f;
+		if (in) {
+			me = q4[id];
+			gkey = key_id[id] >> gshift;
+			const float r = range[id] * range_scale;
+			r_lane = r == r ? fmaxf(r, 0.0f) : INFINITY; // a NaN range accepts every candidate
+			qc[0] = apbf_map_axis(me.x, g, 0); qc[1] = apbf_map_axis(me.y, g, 1); qc[2] = apbf_map_axis(me.z, g, 2);
+			gmin[0] = apbf_map_axis(me.x - r, g, 0); gmax[0] = apbf_map_axis(me.x + r, g, 0);
+			gmin[1] = apbf_map_axis(me.y - r, g, 1); gmax[1] = apbf_map_axis(me.y + r, g, 1);
+			gmin[2] = apbf_map_axis(me.z - r, g, 2); gmax[2] = apbf_map_axis(me.z + r, g, 2);
+			if (DIMS < 3) { gmin[2] = 0u; gmax[2] = 0u; } // * uvec3(1, D > 1, D > 2), neighborhood_green.comp:36
+			// the reference visits gridMin once even when gridMax < gridMin (its ++cell > gridMax wrap)
+			gmax[0] = max(gmax[0], gmin[0]); gmax[1] = max(gmax[1], gmin[1]); gmax[2] = max(gmax[2], gmin[2]);
+		}
+		__syncwarp();
+		s_q[w][lane] = me;
+		__syncwarp();
+		const uint32_t gprev = __shfl_up_sync(0xffffffffu, gkey, 1);
+		uint32_t heads = __ballot_sync(0xffffffffu, in && (lane == 0u || gkey != gprev)); // runs of equal block key
+		const uint32_t n_in = min(32u, n - tile_first);
+		uint32_t my_off = (FILL && in) ? offsets[id] : 0u, my_cnt = 0u;
 		while (heads) {
-			const int hl = __ffs(heads) - 1;
+			const uint32_t r0 = (uint32_t)__ffs(heads) - 1u;
 			heads &= heads - 1u;
-			const uint32_t cell_first = tile * 32u + (uint32_t)hl;
-			const uint32_t cell_last = __ldg(cell_end + __shfl_sync(0xffffffffu, key, hl));
-			for (uint32_t qb = cell_first; qb < cell_last; qb += 32) {
-				const uint32_t nq = min(32u, cell_last - qb);
-				const uint32_t q = qb + lane;
-				const bool valid = lane < nq;
-				float4 me = make_float4(0.f, 0.f, 0.f, -1.0f);
-				uint32_t gmin[3] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, gmax[3] = { 0u, 0u, 0u };
-				uint32_t qc[3] = { 0u, 0u, 0u }; // the query's own cell
-				float r_cull = 0.0f;
-				if (valid) {
-					me = q4[q];
-					const float r = range[q] * range_scale;
-					r_cull = r == r ? r : INFINITY; // a NaN range accepts every candidate
-					qc[0] = apbf_map_axis(me.x, g, 0); qc[1] = apbf_map_axis(me.y, g, 1); qc[2] = apbf_map_axis(me.z, g, 2);
-					gmin[0] = apbf_map_axis(me.x - r, g, 0); gmax[0] = apbf_map_axis(me.x + r, g, 0);
-					gmin[1] = apbf_map_axis(me.y - r, g, 1); gmax[1] = apbf_map_axis(me.y + r, g, 1);
-					gmin[2] = apbf_map_axis(me.z - r, g, 2); gmax[2] = apbf_map_axis(me.z + r, g, 2);
-					if (DIMS < 3) { gmin[2] = 0u; gmax[2] = 0u; } // * uvec3(1, D > 1, D > 2), neighborhood_green.comp:36
-					// the reference visits gridMin once even when gridMax < gridMin (its ++cell > gridMax wrap)
-					gmax[0] = max(gmax[0], gmin[0]); gmax[1] = max(gmax[1], gmin[1]); gmax[2] = max(gmax[2], gmin[2]);
-				}
-				uint32_t umin[3], ext[3];
+			const uint32_t r1 = heads ? (uint32_t)__ffs(heads) - 1u : n_in;
+			const bool valid = lane >= r0 && lane < r1;
+			uint32_t umin[3], ext[3];
+			int qlo[3], qhi[3];
 #pragma unroll
-				for (int d = 0; d < 3; d++) {
-					umin[d] = __reduce_min_sync(0xffffffffu, gmin[d]);
-					ext[d] = min(__reduce_max_sync(0xffffffffu, gmax[d]) - umin[d], axis_cap - 1u) + 1u;
-				}
-				// Cells farther from the queries' cell than the largest range cannot hold a hit: the gap between two cells is
-				// (|dc| - 1) cell widths per axis; 1.01 instead of 1 covers the rounding of the cell map (< 2e-4 cells).
-				// The gap is taken to the box [qlo, qhi] of the queries' cells (one cell whenever the particles lie inside
-				// the grid; particles outside it alias into the same key from different cells).
-				r_cull = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(r_cull, 0.0f))));
-				const float cull2 = cull ? r_cull * r_cull * 1.0001f : INFINITY;
-				float csz[3];
-				int qlo[3], qhi[3];
-#pragma unroll
-				for (int d = 0; d < 3; d++) {
-					qlo[d] = (int)min(__reduce_min_sync(0xffffffffu, valid ? qc[d] : 0xFFFFFFFFu), 0x7FFFFFFFu);
-					qhi[d] = (int)min(__reduce_max_sync(0xffffffffu, valid ? qc[d] : 0u), 0x7FFFFFFFu);
-					csz[d] = g.ext[d] / g.scale;
-				}
-				if (DIMS < 3) csz[2] = 0.0f; // z is not gridded in 2-D but the distance stays 3-D
-				__syncwarp();
-				s_q[w][lane] = me;
-				__syncwarp();
-				const uint32_t nxy = ext[0] * ext[1], ncell = nxy * ext[2];
-				const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)ext[0];
-				uint32_t my_off = (FILL && valid) ? offsets[q] : 0u, my_cnt = 0u;
-				for (uint32_t cbase = 0; cbase < ncell; cbase += 32) {
-					const uint32_t ci = cbase + lane;
-					uint32_t c_first = 0u, c_cnt = 0u;
-					if (ci < ncell) {
-						// ci = (cz * ny + cy) * nx + cx; float reciprocals + one correction step are exact for ci < 2^24
-						uint32_t cz, cy;
-						if (ncell <= (1u << 24)) {
-							cz = (uint32_t)((float)ci * inv_nxy);
-							if (cz * nxy > ci) cz--; else if ((cz + 1u) * nxy <= ci) cz++;
-						} else {
-							cz = ci / nxy;
-						}
-						const uint32_t rem = ci - cz * nxy;
-						if (ncell <= (1u << 24)) {
-							cy = (uint32_t)((float)rem * inv_nx);
-							if (cy * ext[0] > rem) cy--; else if ((cy + 1u) * ext[0] <= rem) cy++;
-						} else {
-							cy = rem / ext[0];
-						}
-						const uint32_t cx = rem - cy * ext[0];
-						const uint32_t ax = umin[0] + cx, ay = umin[1] + cy, az = umin[2] + cz;
-						const int ix = (int)min(ax, 0x7FFFFFFFu), iy = (int)min(ay, 0x7FFFFFFFu), iz = (int)min(az, 0x7FFFFFFFu);
-						const float gx = fmaxf((float)max(qlo[0] - ix, ix - qhi[0]) - 1.01f, 0.0f) * csz[0];
-						const float gy = fmaxf((float)max(qlo[1] - iy, iy - qhi[1]) - 1.01f, 0.0f) * csz[1];
-						const float gz = fmaxf((float)max(qlo[2] - iz, iz - qhi[2]) - 1.01f, 0.0f) * csz[2];
-						if (!(gx * gx + gy * gy + gz * gz > cull2)) {
-							const uint32_t h = apbf_zhash<DIMS>(ax, ay, az, g.res);
-							c_first = __ldg(cell_start + h);
-							c_cnt = __ldg(cell_end + h) - c_first;
-						}
+			for (int d = 0; d < 3; d++) {
+				umin[d] = __reduce_min_sync(0xffffffffu, valid ? gmin[d] : 0xFFFFFFFFu);
+				ext[d] = min(__reduce_max_sync(0xffffffffu, valid ? gmax[d] : 0u) - umin[d], axis_cap - 1u) + 1u;
+				qlo[d] = (int)min(__reduce_min_sync(0xffffffffu, valid ? qc[d] : 0xFFFFFFFFu), 0x7FFFFFFFu);
+				qhi[d] = (int)min(__reduce_max_sync(0xffffffffu, valid ? qc[d] : 0u), 0x7FFFFFFFu);
+			}
+			// Cells farther from the queries' cells than the largest range cannot hold a hit: the gap between the box
+			// [qlo, qhi] of the queries' cells and a cell is (distance in cells - 1) cell widths per axis; 1.01 instead of 1
+			// covers the rounding of the cell map (< 2e-4 cells).
+			const float r_cull = __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(r_lane) : 0u));
+			const float cull2 = cull ? r_cull * r_cull * 1.0001f : INFINITY;
+			const uint32_t nxy = ext[0] * ext[1], ncell = nxy * ext[2];
+			const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)ext[0];
+			for (uint32_t cbase = 0; cbase < ncell; cbase += 32) {
+				const uint32_t ci = cbase + lane;
+				uint32_t c_first = 0u, c_cnt = 0u;
+				if (ci < ncell) {
+					// ci = (cz * ny + cy) * nx + cx; float reciprocals + one correction step are exact for ci < 2^24
+					uint32_t cz, cy;
+					if (ncell <= (1u << 24)) {
+						cz = (uint32_t)((float)ci * inv_nxy);
+						if (cz * nxy > ci) cz--; else if ((cz + 1u) * nxy <= ci) cz++;
+					} else {
+						cz = ci / nxy;
 					}
-					uint32_t incl = c_cnt;
-#pragma unroll
-					for (int o = 1; o < 32; o <<= 1) {
-						const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-						if (lane >= (unsigned)o) incl += t;
+					const uint32_t rem = ci - cz * nxy;
+					if (ncell <= (1u << 24)) {
+						cy = (uint32_t)((float)rem * inv_nx);
+						if (cy * ext[0] > rem) cy--; else if ((cy + 1u) * ext[0] <= rem) cy++;
+					} else {
+						cy = rem / ext[0];
 					}
-					const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-					const uint32_t c_base = c_first - (incl - c_cnt); // candidate t of this cell is id c_base + t
-					for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-						const uint32_t t = t0 + lane;
-						// the cell that holds candidate t: first lane whose inclusive count exceeds t
-						uint32_t pos = 0u;
+					const uint32_t cx = rem - cy * ext[0];
+					const uint32_t ax = umin[0] + cx, ay = umin[1] + cy, az = umin[2] + cz;
+					const int ix = (int)min(ax, 0x7FFFFFFFu), iy = (int)min(ay, 0x7FFFFFFFu), iz = (int)min(az, 0x7FFFFFFFu);
+					const float gx = fmaxf((float)max(qlo[0] - ix, ix - qhi[0]) - 1.01f, 0.0f) * csz[0];
+					const float gy = fmaxf((float)max(qlo[1] - iy, iy - qhi[1]) - 1.01f, 0.0f) * csz[1];
+					const float gz = fmaxf((float)max(qlo[2] - iz, iz - qhi[2]) - 1.01f, 0.0f) * csz[2];
+					if (!(gx * gx + gy * gy + gz * gz > cull2)) {
+						const uint32_t h = apbf_zhash<DIMS>(ax, ay, az, g.res);
+						c_first = __ldg(cell_start + h);
+						c_cnt = __ldg(cell_end + h) - c_first;
+					}
+				}
+				uint32_t incl = c_cnt;
 #pragma unroll
-						for (int step = 16; step > 0; step >>= 1) {
-							const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(pos + step - 1));
-							if (v <= t) pos += step;
-						}
-						const uint32_t cand = __shfl_sync(0xffffffffu, c_base, (int)(pos & 31u)) + t;
-						const bool cvalid = t < total;
-						float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-						if (cvalid) c4 = q4[cand];
-						for (uint32_t qi = 0; qi < nq; qi++) {
-							const float4 qv = s_q[w][qi];
-							const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
-							const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-							const bool hit = cvalid && !(d2 > qv.w) && cand != qb + qi;
-							const uint32_t b = __ballot_sync(0xffffffffu, hit);
-							if (b == 0u) continue;
-							if (FILL) {
-								const uint32_t o = __shfl_sync(0xffffffffu, my_off, (int)qi) + __popc(b & lt_mask);
-								if (hit && o < cap) {
-									const bool mirrored = !(d2 > c4.w);
-									*(uint2*)(pairs + 2 * (size_t)o) = make_uint2(qb + qi, cand);
-									nbl[o] = cand | (mirrored ? 0u : NB_UNMIRRORED);
-									n_asym += mirrored ? 0u : 1u;
-								}
-								if (lane == qi) my_off += __popc(b);
-							} else if (lane == qi) {
-								my_cnt += __popc(b);
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+					if (lane >= (unsigned)o) incl += t;
+				}
+				const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+				const uint32_t c_base = c_first - (incl - c_cnt); // candidate t of this cell is id c_base + t
+				for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+					const uint32_t t = t0 + lane;
+					// the cell that holds candidate t: first lane whose inclusive count exceeds t
+					uint32_t pos = 0u;
+#pragma unroll
+					for (int step = 16; step > 0; step >>= 1) {
+						const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(pos + step - 1));
+						if (v <= t) pos += step;
+					}
+					const uint32_t cand = __shfl_sync(0xffffffffu, c_base, (int)(pos & 31u)) + t;
+					const bool cvalid = t < total;
+					float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+					if (cvalid) c4 = q4[cand];
+					for (uint32_t qi = r0; qi < r1; qi++) {
+						const float4 qv = s_q[w][qi];
+						const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
+						const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+						const bool hit = cvalid && !(d2 > qv.w) && cand != tile_first + qi;
+						const uint32_t b = __ballot_sync(0xffffffffu, hit);
+						if (b == 0u) continue;
+						if (FILL) {
+							const uint32_t o = __shfl_sync(0xffffffffu, my_off, (int)qi) + __popc(b & lt_mask);
+							if (hit && o < cap) {
+								const bool mirrored = !(d2 > c4.w);
+								*(uint2*)(pairs + 2 * (size_t)o) = make_uint2(tile_first + qi, cand);
+								nbl[o] = cand | (mirrored ? 0u : NB_UNMIRRORED);
+								n_asym += mirrored ? 0u : 1u;
 							}
+							if (lane == qi) my_off += __popc(b);
+						} else if (lane == qi) {
+							my_cnt += __popc(b);
 						}
 					}
 				}
-				if (!FILL && valid) counts[q] = my_cnt;
 			}
 		}
+		if (!FILL && in) counts[id] = my_cnt;
 	}
 	if (FILL) {
 		n_asym = __reduce_add_sync(0xffffffffu, n_asym);
@@ -416,7 +422,10 @@ k_bsearch_emit(const uint32_t* __restrict__ index_list, const int32_t* __restric
 	}
 }
 
-__global__ void k_clear_search_words(uint32_t* misc) { misc[MW_N_ASYM] = 0u; misc[MW_TOTAL_PAIRS] = 0u; misc[MW_KEPT_PAIRS] = 0xFFFFFFFFu; }
+__global__ void k_clear_search_words(uint32_t* misc)
+{
+	misc[MW_N_ASYM] = 0u; misc[MW_TOTAL_PAIRS] = 0u; misc[MW_KEPT_PAIRS] = 0xFFFFFFFFu; misc[MW_OCC_CELLS] = 0u;
+}
 
 // shared front half of both searches: gather hidden arrays by sorted_index, rebuild the index list, gather per-id arrays
 int reorder_lists(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, const uint32_t* sorted_index)
@@ -566,6 +575,7 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 		if (dbg->sorted_index) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->sorted_index, sidx, sizeof(uint32_t) * (size_t)nh_cap, cudaMemcpyDeviceToDevice, st));
 		if (dbg->cell_start) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->cell_start, cs, sizeof(uint32_t) * (size_t)max_hash, cudaMemcpyDeviceToDevice, st));
 		if (dbg->cell_end) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->cell_end, ce, sizeof(uint32_t) * (size_t)max_hash, cudaMemcpyDeviceToDevice, st));
+		if (dbg->pair_offsets) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->pair_offsets, offsets, sizeof(uint32_t) * (size_t)(n_cap + 1), cudaMemcpyDeviceToDevice, st));
 	}
 	return APBF_OK;
 }
@@ -626,6 +636,7 @@ int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, cons
 		if (dbg->sorted_index) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->sorted_index, sidx, sizeof(uint32_t) * (size_t)nh_cap, cudaMemcpyDeviceToDevice, st));
 		for (int s = 0; s < 3; s++)
 			if (dbg->code[s]) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->code[s], c[s], sizeof(uint32_t) * (size_t)n_cap, cudaMemcpyDeviceToDevice, st));
+		if (dbg->pair_offsets) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->pair_offsets, offsets, sizeof(uint32_t) * (size_t)(n_cap + 1), cudaMemcpyDeviceToDevice, st));
 	}
 	return APBF_OK;
 }

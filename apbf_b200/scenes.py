@@ -163,6 +163,6 @@ def waterdrop(side=160, r=1.0, jitter=0.05, seed=5, wall_gap=0.0):
     arrays["index_list"] = np.arange(arrays["position"].shape[0], dtype=np.uint32)
     lo = -(half + 12 * r); hi = half + 12 * r
     sc = Scene(name=f"waterdrop_{side}^3", dims=3, arrays=shuffle_state(arrays, seed), min_pos=(lo,) * 3, max_pos=(hi,) * 3,
-               res_log2=_res_for(hi - lo, 8.0 * r), basic_pbf=False, solver_iterations=4, smallest_target_radius=r)
+               res_log2=_res_for(hi - lo, 6.0 * r), basic_pbf=False, solver_iterations=4, smallest_target_radius=r)
     sc.box_min, sc.box_max = pool_walls((-half - wall_gap,) * 3, (half + wall_gap,) * 3, r, 3)
     return sc

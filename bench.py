@@ -42,7 +42,7 @@ def make_scene(name):
     if name.startswith("uniform_"):  # configs[4]: uniform-block sweep, e.g. uniform_100 / 160 / 256
         return scenes.uniform_block(int(name.split("_")[1]), jitter=0.1, shuffle=True), dict(adaptive=False, pairs_per_particle=40)
     if name == "waterdrop_4M":      # configs[2]
-        return scenes.waterdrop(204), dict(adaptive=True, pairs_per_particle=220)
+        return scenes.waterdrop(204), dict(adaptive=True, pairs_per_particle=260)
     raise SystemExit(f"unknown workload {name}")
 
 
