@@ -20,6 +20,7 @@
 namespace {
 
 constexpr int SWEEP_THREADS = 256; // 8 warps = 256 particles per CTA tile
+constexpr int SWEEP_ILP = 4;       // pairs one lane has in flight: 8 lanes x 4 cover a typical 30-pair segment in one go
 #define R_INC APBF_INCOMPRESSIBILITY_DATA_RESOLUTION
 #define FULL 0xffffffffu
 
@@ -130,16 +131,17 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
 				hp.w = kg.x; hp.c0 = kh.x; hp.c1 = kh.y;
 				gp.w = kg.x; gp.c0 = kg.y; gp.c1 = kg.z;
 				const uint32_t beg = min(A.offsets[a], A.pair_cap), end = min(A.offsets[a + 1], A.pair_cap);
-				for (uint32_t e = beg + sub; e < end; e += 16) { // two pairs per lane in flight
-					const bool two = e + 8 < end;
-					const uint32_t b0 = A.nbl[e] & NB_ID_MASK;
-					const uint32_t b1 = two ? A.nbl[e + 8] & NB_ID_MASK : b0;
-					const int4 q0 = A.P4[b0];
-					const int4 q1 = A.P4[b1];
+				for (uint32_t e0 = beg + sub; e0 < end; e0 += 8 * SWEEP_ILP) { // SWEEP_ILP pairs per lane in flight
+					uint32_t bb[SWEEP_ILP];
+					int4 qq[SWEEP_ILP];
 #pragma unroll
-					for (int u = 0; u < 2; u++) {
-						if (u == 1 && !two) break;
-						const int4 iq = u ? q1 : q0;
+					for (int u = 0; u < SWEEP_ILP; u++) bb[u] = (e0 + 8 * u < end) ? A.nbl[e0 + 8 * u] & NB_ID_MASK : a;
+#pragma unroll
+					for (int u = 0; u < SWEEP_ILP; u++) qq[u] = A.P4[bb[u]];
+#pragma unroll
+					for (int u = 0; u < SWEEP_ILP; u++) {
+						if (e0 + 8 * u >= end) break;
+						const int4 iq = qq[u];
 						const float mN = __int_as_float(iq.w); // neighbour's mass = 1 / inverse mass
 						const int dxi = iq.x - ip.x, dyi = iq.y - ip.y, dzi = iq.z - ip.z; // int subtract first, incompressibility_1.comp:51
 						const float rx = (float)dxi * INV_R_POS, ry = (float)dyi * INV_R_POS, rz = (float)dzi * INV_R_POS;
@@ -252,43 +254,53 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_apply_delta(sweep_args A)
 			if (a < n) {
 				const int4 ip = A.P4[a];
 				const float4 la = A.L4[a];
-				float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f);
-				if (filter) e0 = A.E4[a];
+				float4 e0v = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (filter) e0v = A.E4[a];
 				const bool push_a = has_asym && la.x < 0.0f;
 				const uint32_t beg = min(A.offsets[a], A.pair_cap), end = min(A.offsets[a + 1], A.pair_cap);
-				for (uint32_t e = beg + sub; e < end; e += 8) {
-					const uint32_t nbe = A.nbl[e];
-					const uint32_t b = nbe & NB_ID_MASK;
-					const int4 iq = A.P4[b];
-					const float4 lb = A.L4[b];
-					const bool mirrored = (nbe & NB_UNMIRRORED) == 0u;
-					const int dxi = iq.x - ip.x, dyi = iq.y - ip.y, dzi = iq.z - ip.z;
-					const float rx = (float)dxi * INV_R_POS, ry = (float)dyi * INV_R_POS, rz = (float)dzi * INV_R_POS;
-					const float r2 = dot3(rx, ry, rz, rx, ry, rz);
-					if (filter) {
-						// filter_boundariness (incompressibility_3.comp:41-46): dot(emptyDirection, normalize(gradient)) > 0.6.
-						// Every kernel's gradient is a non-positive multiple of r, so normalize(gradient) = -r / |r| wherever
-						// the gradient is not zero: the test is dot(e0, r) < -0.6 |r|, evaluated without the square root.
-						bool nz = r2 >= 1.0e-8f;
-						// compact support: the gradient is zero outside h, and at |r| == h for all but the cone kernel
-						if (GK != 1) nz = nz && (GK == 3 ? !(sqrtf(r2) > la.y) : sqrtf(r2) < la.y);
-						const float d = dot3(e0.x, e0.y, e0.z, rx, ry, rz);
-						if (nz && d < 0.0f && d * d > 0.36f * r2) hit = 1;
-					}
-					if (mirrored) { // the pair (b, a): b shifts a with b's lambda and b's kernel width, diff = pos_a - pos_b
-						if (lb.x < 0.0f) {
-							kpar gp_b; gp_b.w = lb.y; gp_b.c0 = lb.z; gp_b.c1 = lb.w;
-							const vec3f g = kgrad_fast<GK>(gp_b, -rx, -ry, -rz, r2);
-							const float f = lb.x * R_POS;
-							sx += f2i(g.x * f); sy += f2i(g.y * f); sz += f2i(g.z * f);
+				for (uint32_t e0 = beg + sub; e0 < end; e0 += 8 * SWEEP_ILP) { // SWEEP_ILP pairs per lane in flight
+					uint32_t nn[SWEEP_ILP];
+					int4 qq[SWEEP_ILP];
+					float4 ll[SWEEP_ILP];
+#pragma unroll
+					for (int u = 0; u < SWEEP_ILP; u++) nn[u] = (e0 + 8 * u < end) ? A.nbl[e0 + 8 * u] : a;
+#pragma unroll
+					for (int u = 0; u < SWEEP_ILP; u++) { qq[u] = A.P4[nn[u] & NB_ID_MASK]; ll[u] = A.L4[nn[u] & NB_ID_MASK]; }
+#pragma unroll
+					for (int u = 0; u < SWEEP_ILP; u++) {
+						if (e0 + 8 * u >= end) break;
+						const uint32_t b = nn[u] & NB_ID_MASK;
+						const int4 iq = qq[u];
+						const float4 lb = ll[u];
+						const bool mirrored = (nn[u] & NB_UNMIRRORED) == 0u;
+						const int dxi = iq.x - ip.x, dyi = iq.y - ip.y, dzi = iq.z - ip.z;
+						const float rx = (float)dxi * INV_R_POS, ry = (float)dyi * INV_R_POS, rz = (float)dzi * INV_R_POS;
+						const float r2 = dot3(rx, ry, rz, rx, ry, rz);
+						if (filter) {
+							// filter_boundariness (incompressibility_3.comp:41-46): dot(emptyDirection, normalize(gradient)) > 0.6.
+							// Every kernel's gradient is a non-positive multiple of r, so normalize(gradient) = -r / |r| wherever
+							// the gradient is not zero: the test is dot(e0, r) < -0.6 |r|, evaluated without the square root.
+							bool nz = r2 >= 1.0e-8f;
+							// compact support: the gradient is zero outside h, and at |r| == h for all but the cone kernel
+							if (GK != 1) nz = nz && (GK == 3 ? !(sqrtf(r2) > la.y) : sqrtf(r2) < la.y);
+							const float d = dot3(e0v.x, e0v.y, e0v.z, rx, ry, rz);
+							if (nz && d < 0.0f && d * d > 0.36f * r2) hit = 1;
 						}
-					} else if (push_a) { // nobody gathers (a, b): push it like the reference does (:63-66)
-						kpar gp_a; gp_a.w = la.y; gp_a.c0 = la.z; gp_a.c1 = la.w;
-						const vec3f g = kgrad_fast<GK>(gp_a, rx, ry, rz, r2);
-						const float f = la.x * R_POS;
-						atomicAdd(&A.push[b].x, f2i(g.x * f));
-						atomicAdd(&A.push[b].y, f2i(g.y * f));
-						atomicAdd(&A.push[b].z, f2i(g.z * f));
+						if (mirrored) { // the pair (b, a): b shifts a with b's lambda and b's kernel width, diff = pos_a - pos_b
+							if (lb.x < 0.0f) {
+								kpar gp_b; gp_b.w = lb.y; gp_b.c0 = lb.z; gp_b.c1 = lb.w;
+								const vec3f g = kgrad_fast<GK>(gp_b, -rx, -ry, -rz, r2);
+								const float f = lb.x * R_POS;
+								sx += f2i(g.x * f); sy += f2i(g.y * f); sz += f2i(g.z * f);
+							}
+						} else if (push_a) { // nobody gathers (a, b): push it like the reference does (:63-66)
+							kpar gp_a; gp_a.w = la.y; gp_a.c0 = la.z; gp_a.c1 = la.w;
+							const vec3f g = kgrad_fast<GK>(gp_a, rx, ry, rz, r2);
+							const float f = la.x * R_POS;
+							atomicAdd(&A.push[b].x, f2i(g.x * f));
+							atomicAdd(&A.push[b].y, f2i(g.y * f));
+							atomicAdd(&A.push[b].z, f2i(g.z * f));
+						}
 					}
 				}
 			}
