@@ -84,6 +84,9 @@ SIGNATURES = {
     "apbf_scattered_write": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32]),
     "apbf_append_list": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]),
     "apbf_copy_with_differing_stride": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "apbf_find_value_changes": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32]),
+    "apbf_write_increasing_sequence": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32, C.c_uint32]),
+    "apbf_write_increasing_sequence_from_to": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32]),
     "apbf_apply_hidden_edit": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp]),
     "apbf_sort": (C.c_int, [vp, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32]),
     "apbf_prefix_sum": (C.c_int, [vp, vp, vp, C.c_uint32, vp]),

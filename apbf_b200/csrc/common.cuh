@@ -20,7 +20,7 @@ enum apbf_scratch_slot {
 	SLOT_SCAN_STATUS, SLOT_MISC_WORDS, SLOT_CELL_START, SLOT_CELL_END, SLOT_COUNTS, SLOT_OFFSETS, SLOT_NB,
 	SLOT_INV_PERM, SLOT_TMP_KEYS, SLOT_TMP_VALS, SLOT_TMP_VALS2, SLOT_CODE0, SLOT_CODE1, SLOT_CODE2,
 	SLOT_P4, SLOT_L4, SLOT_G4, SLOT_DELTA, SLOT_PUSH, SLOT_RADIUS_ID, SLOT_KWFX, SLOT_KEEP_COUNTS, SLOT_KEEP_OFFSETS,
-	SLOT_PAIRS_TMP, SLOT_NB_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4, SLOT_KG, SLOT_KH, SLOT_Q4, SLOT_KEY_ID,
+	SLOT_PAIRS_TMP, SLOT_NB_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4, SLOT_KG, SLOT_KH, SLOT_Q4, SLOT_KEY_ID, SLOT_EDIT_COUNTS, SLOT_EDIT_OFFSETS,
 	SLOT_COUNT
 };
 
@@ -43,6 +43,7 @@ enum apbf_misc_word {
 	MW_IDENTITY = 3,     // 1 if the index list is the identity over all hidden particles
 	MW_KEPT_PAIRS = 4,   // pair count after the last spread_kernel_width prune
 	MW_OCC_CELLS = 5,    // number of occupied grid cells seen by the last Green search
+	MW_SNAPSHOT = 6,     // scratch word of the list helpers
 	MW_TICKET0 = 8,      // tile tickets of the chained-scan kernels (8 words)
 	MW_SCAN_TOTAL = 16,
 	MW_WORDS = 64

@@ -122,6 +122,48 @@ __global__ void k_copy_strided(const uint32_t* __restrict__ src, uint32_t* __res
 	}
 }
 
+// find_value_changes.comp:16-30 (the id-1 read at id 0 is not replicated): `in` is a non-decreasing running count;
+// out[k] = first id whose value exceeds k, *out_len = last value
+__global__ void k_find_value_changes(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ in_len,
+                                     uint32_t* out_len)
+{
+	const uint32_t n = *in_len;
+	for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+		const uint32_t curr = in[id], prev = id > 0 ? in[id - 1] : 0u;
+		if (id == n - 1u) *out_len = curr;
+		if (curr != prev) out[prev] = id;
+	}
+}
+
+// write_increasing_sequence.comp:23-36: target[i] = *seq_min + i for i < L = min(capacity, seq_len, upper - *seq_min);
+// *new_seq_min = *seq_min + L, *new_target_len = L.  seq_min is read by every thread before lane 0 of block 0 may
+// overwrite it through an aliasing new_seq_min, hence the snapshot kernel in front.
+__global__ void k_increasing_sequence_words(const uint32_t* seq_min, uint32_t* new_seq_min, uint32_t* new_target_len,
+                                            uint32_t target_capacity, uint32_t upper, uint32_t seq_len, uint32_t* snapshot)
+{
+	const uint32_t m = *seq_min;
+	const uint32_t L = min(min(target_capacity, seq_len), upper - m);
+	*snapshot = m;
+	*new_seq_min = m + L;
+	*new_target_len = L;
+}
+__global__ void k_write_increasing_sequence_dev(uint32_t* __restrict__ target, uint32_t target_capacity, const uint32_t* snapshot,
+                                                uint32_t upper, uint32_t seq_len)
+{
+	const uint32_t m = *snapshot;
+	const uint32_t L = min(min(target_capacity, seq_len), upper - m);
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) target[i] = m + i;
+}
+
+// write_increasing_sequence_from_to.comp:19-31
+__global__ void k_write_from_to(uint32_t* __restrict__ out, uint32_t* out_len, const uint32_t* from, const uint32_t* to, uint32_t capacity)
+{
+	const uint32_t f = *from, t = *to;
+	const uint32_t n = min(t > f ? t - f : 0u, capacity);
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = f + i;
+}
+__global__ void k_write_from_to_len(uint32_t* out_len, const uint32_t* from, const uint32_t* to) { *out_len = *to - *from; }
+
 // ---- general apply_hidden_edit (sort based) --------------------------------------------------------------------------
 __global__ void k_hidden_edit_counts(const uint32_t* __restrict__ edit, const uint32_t* __restrict__ edit_len,
                                      const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
@@ -261,6 +303,50 @@ int apbf_append_list(apbf_ctx* ctx, void* target, const void* appending, const u
 	return APBF_OK;
 }
 
+int apbf_find_value_changes(apbf_ctx* ctx, const uint32_t* in, uint32_t* out_change, const uint32_t* in_len,
+                            uint32_t* out_change_len, uint32_t capacity)
+{
+	if (!ctx) return APBF_ERR_INVALID;
+	APBF_REQUIRE(ctx, in && out_change && in_len && out_change_len);
+	if (capacity == 0) return APBF_OK;
+	k_find_value_changes<<<apbf_grid(ctx, capacity, 256), 256, 0, ctx->stream>>>(in, out_change, in_len, out_change_len);
+	APBF_LAUNCHED(ctx);
+	return APBF_OK;
+}
+
+int apbf_write_increasing_sequence(apbf_ctx* ctx, uint32_t* target, uint32_t target_capacity, uint32_t* new_target_len,
+                                   const uint32_t* sequence_min_value, uint32_t* new_sequence_min_value,
+                                   uint32_t value_upper_bound, uint32_t sequence_length)
+{
+	if (!ctx) return APBF_ERR_INVALID;
+	APBF_REQUIRE(ctx, target && new_target_len && sequence_min_value && new_sequence_min_value);
+	uint32_t* snap = ctx->misc() + MW_SNAPSHOT;
+	k_increasing_sequence_words<<<1, 1, 0, ctx->stream>>>(sequence_min_value, new_sequence_min_value, new_target_len, target_capacity,
+	                                                      value_upper_bound, sequence_length, snap);
+	APBF_LAUNCHED(ctx);
+	const uint32_t most = target_capacity < sequence_length ? target_capacity : sequence_length;
+	if (most > 0) {
+		k_write_increasing_sequence_dev<<<apbf_grid(ctx, most, 256), 256, 0, ctx->stream>>>(target, target_capacity, snap, value_upper_bound,
+		                                                                                  sequence_length);
+		APBF_LAUNCHED(ctx);
+	}
+	return APBF_OK;
+}
+
+int apbf_write_increasing_sequence_from_to(apbf_ctx* ctx, uint32_t* out, uint32_t* out_len, const uint32_t* from, const uint32_t* to,
+                                           uint32_t capacity)
+{
+	if (!ctx) return APBF_ERR_INVALID;
+	APBF_REQUIRE(ctx, out && out_len && from && to && out_len != from && out_len != to);
+	if (capacity > 0) {
+		k_write_from_to<<<apbf_grid(ctx, capacity, 256), 256, 0, ctx->stream>>>(out, out_len, from, to, capacity);
+		APBF_LAUNCHED(ctx);
+	}
+	k_write_from_to_len<<<1, 1, 0, ctx->stream>>>(out_len, from, to);
+	APBF_LAUNCHED(ctx);
+	return APBF_OK;
+}
+
 int apbf_copy_with_differing_stride(apbf_ctx* ctx, const void* src, void* dst, const uint32_t* len, uint32_t capacity,
                                     uint32_t src_stride_bytes, uint32_t dst_stride_bytes)
 {
@@ -286,8 +372,8 @@ int apbf_apply_hidden_edit(apbf_ctx* ctx, const uint32_t* edit, const uint32_t* 
 	uint32_t* sv = (uint32_t*)ctx->scratch_get(SLOT_TMP_VALS, sizeof(uint32_t) * (size_t)(index_capacity + 1));
 	uint32_t* start = (uint32_t*)ctx->scratch_get(SLOT_HIDDEN_FLAGS, sizeof(uint32_t) * (size_t)(hidden_capacity + 1));
 	uint32_t* end = (uint32_t*)ctx->scratch_get(SLOT_HIDDEN_OFFS, sizeof(uint32_t) * (size_t)(hidden_capacity + 1));
-	uint32_t* counts = (uint32_t*)ctx->scratch_get(SLOT_COUNTS, sizeof(uint32_t) * (size_t)(edit_capacity + 2));
-	uint32_t* offsets = (uint32_t*)ctx->scratch_get(SLOT_OFFSETS, sizeof(uint32_t) * (size_t)(edit_capacity + 2));
+	uint32_t* counts = (uint32_t*)ctx->scratch_get(SLOT_EDIT_COUNTS, sizeof(uint32_t) * (size_t)(edit_capacity + 2));
+	uint32_t* offsets = (uint32_t*)ctx->scratch_get(SLOT_EDIT_OFFSETS, sizeof(uint32_t) * (size_t)(edit_capacity + 2));
 	if (!sk || !sv || !start || !end || !counts || !offsets) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 	int bits = 1;
 	while (bits < 32 && (hidden_capacity >> bits) != 0u) bits++;

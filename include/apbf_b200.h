@@ -117,6 +117,20 @@ int apbf_append_list(apbf_ctx* ctx, void* target, const void* appending, const u
 /* copy_with_differing_stride.comp:21-32 */
 int apbf_copy_with_differing_stride(apbf_ctx* ctx, const void* src, void* dst, const uint32_t* len, uint32_t capacity,
                                     uint32_t src_stride_bytes, uint32_t dst_stride_bytes);
+/* find_value_changes.comp:16-30 (indexed_list::delete_these, source/indexed_list.h:126-138): `in` is a running count;
+ * out_change[k] = first i with in[i] > k; *out_change_len = in[*in_len - 1] (untouched when *in_len == 0) */
+int apbf_find_value_changes(apbf_ctx* ctx, const uint32_t* in, uint32_t* out_change, const uint32_t* in_len,
+                            uint32_t* out_change_len, uint32_t capacity);
+/* write_increasing_sequence.comp:23-36 (shader_provider.cpp:198-219; indexed_list::increase_length, indexed_list.h:194-202):
+ * L = min(target_capacity, sequence_length, value_upper_bound - *sequence_min_value); target[i] = *sequence_min_value + i
+ * for i < L; *new_sequence_min_value = *sequence_min_value + L; *new_target_len = L.  The output words may alias the input. */
+int apbf_write_increasing_sequence(apbf_ctx* ctx, uint32_t* target, uint32_t target_capacity, uint32_t* new_target_len,
+                                   const uint32_t* sequence_min_value, uint32_t* new_sequence_min_value,
+                                   uint32_t value_upper_bound, uint32_t sequence_length);
+/* write_increasing_sequence_from_to.comp:19-31 (indexed_list::duplicate_these, indexed_list.h:141-152):
+ * out[i] = *from + i while *from + i < *to; *out_len = *to - *from */
+int apbf_write_increasing_sequence_from_to(apbf_ctx* ctx, uint32_t* out, uint32_t* out_len, const uint32_t* from, const uint32_t* to,
+                                           uint32_t capacity);
 /* indexed_list::apply_hidden_edit (source/indexed_list.h:289-308: atomic_swap.comp + generate_new_index_and_edit_list.comp)
  * followed by the index-list sort of indexed_list::sort (:276-286): for every new hidden slot h (ascending) and every
  * entry i of index_list with index_list[i] == edit[h], emit new_index = h and new_edit = i.  Result is ascending in

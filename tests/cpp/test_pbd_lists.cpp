@@ -1,0 +1,374 @@
+// test_pbd_lists.cpp -- the reference's own list / algorithm self tests (source/test.cpp:47-531: known-answer vectors and
+// properties) restated against include/apbf_pbd.hpp, plus one search + solve through the operator classes.
+// Built and run by tests/test_cpp_shim.py:   g++ -std=c++17 -Iinclude tests/cpp/test_pbd_lists.cpp -Lapbf_b200 -lapbf_b200
+// Needs a CUDA device (exit code 77 = no device: the product has no CPU path).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <random>
+#include <set>
+
+#include "apbf_pbd.hpp"
+
+using namespace pbd;
+
+static int g_failures = 0;
+
+template<class T>
+static gpu_list<sizeof(T)> to_gpu_list(const std::vector<T>& aData) // source/test.h:57-63
+{
+	gpu_list<sizeof(T)> result;
+	result.request_length(std::max<size_t>(aData.size(), 1)).set_length(aData.size());
+	if (!aData.empty()) algorithms::copy_bytes(aData.data(), result.write().buffer(), aData.size() * sizeof(T));
+	return result;
+}
+
+template<class T>
+static bool validate_list(const buffer& aBuffer, const std::vector<T>& aExpected, const char* aName)
+{
+	std::vector<T> got(aExpected.size());
+	if (!got.empty()) shader_provider::check(apbf_copy_bytes_to_host(shader_provider::context(), aBuffer.ptr, got.data(), got.size() * sizeof(T)));
+	const bool ok = got.empty() || std::memcmp(got.data(), aExpected.data(), got.size() * sizeof(T)) == 0;
+	if (!ok) { std::printf("FAILED: %s\n", aName); g_failures++; }
+	return ok;
+}
+
+static bool validate_length(const buffer& aLength, size_t aExpected, const char* aName)
+{
+	uint32_t l = 0;
+	shader_provider::check(apbf_copy_bytes_to_host(shader_provider::context(), aLength.ptr, &l, 4));
+	const bool ok = l == aExpected;
+	if (!ok) { std::printf("FAILED: %s: length %u, expected %zu\n", aName, l, aExpected); g_failures++; }
+	return ok;
+}
+
+struct f3 { float x, y, z; };
+
+static void gpu_list_tests()
+{
+	{ // test.cpp:47-58
+		std::vector<uint32_t> a{ 3u, 64u, 12683u, 4294967295u }, b{ 432587u, 0u, 5436u };
+		auto listA = to_gpu_list(a).request_length(a.size() + b.size());
+		auto listB = to_gpu_list(b);
+		listA += listB;
+		a.insert(a.end(), b.begin(), b.end());
+		validate_list(listA.buffer(), a, "gpu_list concatenation");
+		validate_length(listA.length(), a.size(), "gpu_list concatenation length");
+	}
+	{ // test.cpp:60-75
+		std::vector<f3> a{ { 0, 2, 61.5f }, { 13.65f, 4.65f, 234 } }, b{ { 1, 0, 2.5f } }, c{ { 8, 2, 1 }, { 2, 4, 9 } };
+		auto listA = to_gpu_list(a);
+		auto listB = to_gpu_list(b).request_length(a.size() + b.size() + c.size());
+		auto listC = to_gpu_list(c);
+		listB = listA + listB + listC;
+		a.insert(a.end(), b.begin(), b.end());
+		a.insert(a.end(), c.begin(), c.end());
+		validate_list(listB.buffer(), a, "gpu_list concatenation 2");
+	}
+	{ // test.cpp:77-89
+		std::vector<uint32_t> a{ 3u, 64u, 12683u, 4294967295u }, b;
+		auto listA = to_gpu_list(a).request_length(a.size() + 5);
+		auto listB = to_gpu_list(b).request_length(a.size() + 5);
+		listA += listB;
+		validate_length(listA.length(), 4, "gpu_list append empty");
+		validate_list(listA.buffer(), a, "gpu_list append empty content");
+	}
+	{ // test.cpp:91-105
+		std::vector<uint32_t> data{ 77u, 3u, 9999u, 4294967295u, 0u }, edit{ 1u, 3u, 1u, 4u }, expected{ 3u, 4294967295u, 3u, 0u };
+		auto list = to_gpu_list(data);
+		auto editList = to_gpu_list(edit);
+		list.apply_edit(editList, nullptr);
+		validate_length(list.length(), edit.size(), "gpu_list::apply_edit() length");
+		validate_list(list.buffer(), expected, "gpu_list::apply_edit()");
+	}
+	{ // lazy copy: a copy shares the storage until one side asks for write()
+		std::vector<uint32_t> data{ 1u, 2u, 3u };
+		auto a = to_gpu_list(data);
+		auto b = a;
+		if (a.buffer().ptr != b.buffer().ptr) { std::printf("FAILED: copy does not share storage\n"); g_failures++; }
+		const uint32_t nine = 9u;
+		algorithms::copy_bytes(&nine, b.write().buffer(), 4);
+		if (a.buffer().ptr == b.buffer().ptr) { std::printf("FAILED: write() did not make the copy unique\n"); g_failures++; }
+		validate_list(a.buffer(), data, "copy-on-write keeps the original");
+		validate_list(b.buffer(), std::vector<uint32_t>{ 9u, 2u, 3u }, "copy-on-write copy");
+	}
+}
+
+static void indexed_list_tests()
+{
+	{ // test.cpp:107-115
+		auto list = indexed_list<gpu_list<4>>(5).request_length(3);
+		list.increase_length(3);
+		validate_list(list.index_buffer(), std::vector<uint32_t>{ 0u, 1u, 2u }, "indexed_list::increase_length()");
+	}
+	{ // test.cpp:117-138
+		std::vector<uint32_t> edit{ 1u, 2u, 3u, 4u };
+		auto listA = indexed_list<gpu_list<4>>(5).request_length(5);
+		auto editList = to_gpu_list(edit);
+		listA.increase_length(2);
+		auto listB = listA;
+		listA.increase_length(3);
+		listA.hidden_list().apply_edit(editList, nullptr);
+		validate_length(listA.length(), 4, "apply_hidden_edit 1 length A");
+		validate_length(listB.length(), 1, "apply_hidden_edit 1 length B");
+		validate_list(listA.index_buffer(), std::vector<uint32_t>{ 0u, 1u, 2u, 3u }, "apply_hidden_edit 1 A");
+		validate_list(listB.index_buffer(), std::vector<uint32_t>{ 0u }, "apply_hidden_edit 1 B");
+	}
+	{ // test.cpp:140-162
+		std::vector<uint32_t> edit{ 0u, 1u, 3u, 4u }, bIdx{ 0u, 3u, 1u };
+		auto listA = indexed_list<gpu_list<12>>(5).request_length(5);
+		auto listB = indexed_list<gpu_list<12>>().request_length(bIdx.size()).set_length(bIdx.size());
+		auto editList = to_gpu_list(edit);
+		listB.share_hidden_data_from(listA);
+		listA.increase_length(5);
+		algorithms::copy_bytes(bIdx.data(), listB.write().index_buffer(), bIdx.size() * 4);
+		listA.hidden_list().apply_edit(editList, nullptr);
+		validate_length(listA.hidden_list().length(), 4, "apply_hidden_edit 2 hidden length");
+		validate_length(listA.length(), 4, "apply_hidden_edit 2 length A");
+		validate_length(listB.length(), 3, "apply_hidden_edit 2 length B");
+		validate_list(listA.index_buffer(), std::vector<uint32_t>{ 0u, 1u, 2u, 3u }, "apply_hidden_edit 2 A");
+		validate_list(listB.index_buffer(), std::vector<uint32_t>{ 0u, 1u, 2u }, "apply_hidden_edit 2 B");
+	}
+	{ // test.cpp:164-184 (duplication inside the edit)
+		std::vector<uint32_t> edit{ 2u, 1u, 2u, 4u, 1u }, bIdx{ 4u, 2u, 4u };
+		auto listA = indexed_list<gpu_list<12>>(5).request_length(5);
+		auto listB = indexed_list<gpu_list<12>>().request_length(5).set_length(bIdx.size());
+		auto editList = to_gpu_list(edit);
+		listB.share_hidden_data_from(listA);
+		listA.increase_length(5);
+		algorithms::copy_bytes(bIdx.data(), listB.write().index_buffer(), bIdx.size() * 4);
+		listA.hidden_list().apply_edit(editList, nullptr);
+		validate_length(listA.hidden_list().length(), 5, "apply_hidden_edit 3 hidden length");
+		validate_length(listA.length(), 5, "apply_hidden_edit 3 length A");
+		validate_length(listB.length(), 4, "apply_hidden_edit 3 length B");
+		validate_list(listA.index_buffer(), std::vector<uint32_t>{ 0u, 1u, 2u, 3u, 4u }, "apply_hidden_edit 3 A");
+		validate_list(listB.index_buffer(), std::vector<uint32_t>{ 0u, 2u, 3u, 3u }, "apply_hidden_edit 3 B");
+	}
+	{ // test.cpp:427-449
+		std::vector<uint32_t> hidden{ 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13 };
+		auto listA = indexed_list<gpu_list<4>>(13).request_length(13);
+		listA.increase_length(8);
+		auto listB = listA;
+		auto listC = listA;
+		listB.increase_length(3);
+		listC.increase_length(2);
+		algorithms::copy_bytes(hidden.data(), listA.hidden_list().write().buffer(), hidden.size() * 4);
+		listB.delete_these();
+		validate_length(listA.length(), 0, "delete_these() length A");
+		validate_length(listB.length(), 0, "delete_these() length B");
+		validate_length(listC.length(), 2, "delete_these() length C");
+		validate_length(listA.hidden_list().length(), 2, "delete_these() hidden length");
+		validate_list(listC.hidden_list().buffer(), std::vector<uint32_t>{ 12, 13 }, "delete_these()");
+	}
+	{ // test.cpp:451-465
+		auto listA = indexed_list<gpu_list<4>>(13).request_length(13);
+		listA.increase_length(8);
+		auto listB = listA;
+		listB.increase_length(5);
+		listB.delete_these();
+		validate_length(listA.length(), 0, "delete_these() 2 length A");
+		validate_length(listB.length(), 0, "delete_these() 2 length B");
+		validate_length(listA.hidden_list().length(), 0, "delete_these() 2 hidden length");
+	}
+	{ // test.cpp:467-485
+		std::vector<uint32_t> hidden{ 0, 1, 2, 3, 4, 5, 6, 7 };
+		auto listA = indexed_list<gpu_list<4>>(13).request_length(13);
+		listA.increase_length(8);
+		algorithms::copy_bytes(hidden.data(), listA.hidden_list().write().buffer(), hidden.size() * 4);
+		auto listB = listA;
+		listB.set_length(0);
+		listB.delete_these();
+		validate_length(listA.length(), 8, "delete_these() 3 length A");
+		validate_length(listB.length(), 0, "delete_these() 3 length B");
+		validate_length(listA.hidden_list().length(), 8, "delete_these() 3 hidden length");
+		validate_list(listA.hidden_list().buffer(), hidden, "delete_these() 3");
+		validate_list(listA.index_buffer(), hidden, "delete_these() 3 indices");
+	}
+	{ // test.cpp:487-513
+		std::vector<uint32_t> hidden{ 1, 2, 3, 4, 5, 6, 7, 8, 9, 10 };
+		auto listA = indexed_list<gpu_list<4>>(13).request_length(13);
+		listA.increase_length(3);
+		auto listB = listA;
+		auto listC = listB.increase_length(7);
+		algorithms::copy_bytes(hidden.data(), listA.hidden_list().write().buffer(), hidden.size() * 4);
+		listA.duplicate_these();
+		validate_length(listA.length(), 3, "duplicate_these() length A");
+		validate_length(listB.length(), 13, "duplicate_these() length B");
+		validate_length(listC.length(), 7, "duplicate_these() length C");
+		validate_length(listA.hidden_list().length(), 13, "duplicate_these() hidden length");
+		validate_list(listA.index_buffer(), std::vector<uint32_t>{ 0, 1, 2 }, "duplicate_these() A");
+		validate_list(listB.index_buffer(), std::vector<uint32_t>{ 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12 }, "duplicate_these() B");
+		validate_list(listC.index_buffer(), std::vector<uint32_t>{ 3, 4, 5, 6, 7, 8, 9 }, "duplicate_these() C");
+		validate_list(listC.hidden_list().buffer(), std::vector<uint32_t>{ 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 1, 2, 3 }, "duplicate_these() hidden");
+	}
+	{ // test.cpp:515-531
+		std::vector<uint32_t> hidden{ 10, 20, 30, 40, 50 };
+		auto listA = indexed_list<gpu_list<4>>(10).request_length(10);
+		auto listB = listA;
+		listB.increase_length(5);
+		algorithms::copy_bytes(hidden.data(), listA.hidden_list().write().buffer(), hidden.size() * 4);
+		listA.write().duplicate_these();
+		validate_length(listA.length(), 0, "duplicate_these() empty length A");
+		validate_length(listB.length(), 5, "duplicate_these() empty length B");
+		validate_length(listA.hidden_list().length(), 5, "duplicate_these() empty hidden length");
+		validate_list(listB.index_buffer(), std::vector<uint32_t>{ 0, 1, 2, 3, 4 }, "duplicate_these() empty B");
+		validate_list(listA.hidden_list().buffer(), hidden, "duplicate_these() empty hidden");
+	}
+}
+
+static void algorithm_tests()
+{
+	{ // test.cpp:186-197
+		std::vector<uint32_t> data{ 43u, 1u, 4567u, 0u, 1u, 0u, 84523487u }, expected{ 43u, 44u, 4611u, 4611u, 4612u, 4612u, 84528099u };
+		auto list = to_gpu_list(data);
+		auto helper = gpu_list<4>().request_length(algorithms::prefix_sum_calculate_needed_helper_list_length(data.size()));
+		algorithms::prefix_sum(list.write().buffer(), helper.write().buffer(), list.write().length(), data.size());
+		validate_list(list.buffer(), expected, "prefix sum");
+	}
+	{ // test.cpp:228-267 (property): 512*512 + 1000 values, inclusive running sum
+		std::mt19937 rng(0);
+		std::vector<uint32_t> data(512 * 512 + 1000), expected(data.size());
+		for (auto& v : data) v = rng() % 1000u;
+		std::partial_sum(data.begin(), data.end(), expected.begin());
+		auto list = to_gpu_list(data);
+		algorithms::prefix_sum(list.write().buffer(), buffer(), list.write().length(), data.size());
+		validate_list(list.buffer(), expected, "very long prefix sum");
+	}
+	auto sort_case = [](std::vector<uint32_t> keys, std::vector<uint32_t> expectedPayload, const char* name, size_t capacity = 0) {
+		std::vector<uint32_t> idx(keys.size());
+		std::iota(idx.begin(), idx.end(), 0u);
+		const size_t cap = std::max(capacity, keys.size());
+		auto values = to_gpu_list(keys).request_length(cap), second = to_gpu_list(idx).request_length(cap);
+		auto result = gpu_list<4>().request_length(cap), secondResult = gpu_list<4>().request_length(cap);
+		auto helper = gpu_list<4>().request_length(algorithms::sort_calculate_needed_helper_list_length(cap));
+		algorithms::sort(values.write().buffer(), second.write().buffer(), helper.write().buffer(), values.length(), cap, result.write().buffer(), secondResult.write().buffer());
+		std::vector<uint32_t> sortedKeys = keys;
+		std::stable_sort(sortedKeys.begin(), sortedKeys.end());
+		validate_list(result.buffer(), sortedKeys, name);
+		validate_list(secondResult.buffer(), expectedPayload, name);
+	};
+	sort_case({ 15u, 2u, 1234u, 2u, 0u, 4294967295u, 1u, 4294967294u }, { 4u, 6u, 1u, 3u, 0u, 2u, 7u, 5u }, "sort");                             // test.cpp:284-305
+	sort_case({ 15u, 2u, 3u, 2u, 0u, 14u, 1u, 14u }, { 4u, 6u, 1u, 3u, 2u, 5u, 7u, 0u }, "sort small values");                                     // test.cpp:343-364
+	sort_case({ 15u, 2u, 1234u, 2u, 0u, 4294967295u, 1u, 4294967294u }, { 4u, 6u, 1u, 3u, 0u, 2u, 7u, 5u }, "sort few values in long buffer", 600); // test.cpp:402-425
+	{ // test.cpp:307-341 (property): equals std::stable_sort with payload
+		std::mt19937 rng(0);
+		std::vector<uint32_t> keys(512 * 512 + 123), idx(keys.size());
+		for (auto& k : keys) k = rng();
+		std::iota(idx.begin(), idx.end(), 0u);
+		std::vector<uint32_t> order = idx;
+		std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+		auto values = to_gpu_list(keys), second = to_gpu_list(idx);
+		auto result = gpu_list<4>().request_length(keys.size()), secondResult = gpu_list<4>().request_length(keys.size());
+		algorithms::sort(values.write().buffer(), second.write().buffer(), buffer(), values.length(), keys.size(), result.write().buffer(), secondResult.write().buffer());
+		validate_list(secondResult.buffer(), order, "sort many values");
+	}
+	{ // gpu_list<4>::sort() drags the owner along (gpu_list.h:180-193)
+		std::vector<uint32_t> keys{ 5u, 1u, 4u, 1u, 0u };
+		auto list = to_gpu_list(keys);
+		list.sort();
+		validate_list(list.buffer(), std::vector<uint32_t>{ 0u, 1u, 1u, 4u, 5u }, "gpu_list<4>::sort()");
+	}
+}
+
+// One pool::update-like substep (source/pool.cpp:67-106) on a small jittered block through the operator classes; the pair
+// list is checked against a host brute force with the reference's acceptance test (neighborhood_brute_force.comp:31-50).
+static void operator_tests()
+{
+	const int side = 12;
+	const float r = 1.0f, R = 262144.0f;
+	const size_t n = size_t(side) * side * side;
+	std::mt19937 rng(7);
+	std::uniform_real_distribution<float> jit(-0.2f, 0.2f);
+	std::vector<int32_t> pos(n * 4, 0);
+	std::vector<float> vel(n * 4, 0.f), invMass(n, 1.0f / 8.0f), radius(n, r), kw(n, 4.0f * r), one(n, 1.0f);
+	std::vector<uint32_t> zeros(n, 0u), bdist(n, uint32_t(r * R));
+	for (size_t i = 0; i < n; i++) {
+		const int gx = int(i / (side * side)), gy = int(i / side) % side, gz = int(i % side);
+		const float p[3] = { -side + 1.0f + 2.0f * gx + jit(rng), -side + 1.0f + 2.0f * gy + jit(rng), -side + 1.0f + 2.0f * gz + jit(rng) };
+		for (int d = 0; d < 3; d++) pos[4 * i + d] = int32_t(p[d] * R);
+	}
+	particles prt(n);
+	prt.request_length(n);
+	fluid fl;
+	fl.request_length(n);
+	neighbors nb;
+	nb.request_length(n * 80);
+	using hp = hidden_particles_enum;
+	auto& hidden = prt.hidden_list();
+	fl.get<fluid_enum::particle>() = prt.increase_length(n);
+	fl.set_length(fl.get<fluid_enum::particle>().length());
+	algorithms::copy_bytes(pos.data(), hidden.get<hp::position>().write().buffer(), n * 16);
+	algorithms::copy_bytes(vel.data(), hidden.get<hp::velocity>().write().buffer(), n * 16);
+	algorithms::copy_bytes(invMass.data(), hidden.get<hp::inverse_mass>().write().buffer(), n * 4);
+	algorithms::copy_bytes(radius.data(), hidden.get<hp::radius>().write().buffer(), n * 4);
+	algorithms::copy_bytes(pos.data(), hidden.get<hp::pos_backup>().write().buffer(), n * 16);
+	algorithms::copy_bytes(zeros.data(), hidden.get<hp::transferring>().write().buffer(), n * 4);
+	algorithms::copy_bytes(kw.data(), fl.get<fluid_enum::kernel_width>().write().buffer(), n * 4);
+	algorithms::copy_bytes(radius.data(), fl.get<fluid_enum::target_radius>().write().buffer(), n * 4);
+	algorithms::copy_bytes(one.data(), fl.get<fluid_enum::boundariness>().write().buffer(), n * 4);
+	algorithms::copy_bytes(bdist.data(), fl.get<fluid_enum::boundary_distance>().write().buffer(), n * 4);
+
+	apbf_settings s;
+	apbf_default_settings(&s);
+	settings::update_apbf_settings_buffer(s, 3);
+	neighborhood_green search;
+	incompressibility solver;
+	const float lim = side + 4.0f;
+	search.set_data(&fl.get<fluid_enum::particle>(), &fl.get<fluid_enum::kernel_width>(), &nb).set_range_scale(1.0f).set_position_range(vec3(-lim), vec3(lim), 3u);
+	solver.set_data(&fl, &nb);
+	shader_provider::start_recording();
+	search.apply();
+	shader_provider::end_recording();
+
+	auto gotPos = fl.get<fluid_enum::particle>().hidden_list().get<hp::position>().read<int32_t>();
+	auto pairs = nb.read<uint32_t>();
+	validate_length(fl.length(), n, "search keeps the fluid length");
+	std::set<std::pair<uint32_t, uint32_t>> got;
+	for (size_t e = 0; e + 1 < pairs.size(); e += 2) got.insert({ pairs[e], pairs[e + 1] });
+	std::set<std::pair<uint32_t, uint32_t>> expected;
+	for (uint32_t a = 0; a < n; a++)
+		for (uint32_t b = 0; b < n; b++) {
+			if (a == b) continue;
+			const float dx = float(gotPos[4 * a]) / R - float(gotPos[4 * b]) / R, dy = float(gotPos[4 * a + 1]) / R - float(gotPos[4 * b + 1]) / R,
+			            dz = float(gotPos[4 * a + 2]) / R - float(gotPos[4 * b + 2]) / R;
+			const float d = std::sqrt((dx * dx + dy * dy) + dz * dz);
+			if (!(d > 4.0f * r)) expected.insert({ a, b });
+		}
+	if (got.size() * 2 != pairs.size()) { std::printf("FAILED: duplicate pairs\n"); g_failures++; }
+	if (got != expected) { std::printf("FAILED: neighbour set differs from brute force (%zu vs %zu)\n", got.size(), expected.size()); g_failures++; }
+	auto idx = fl.get<fluid_enum::particle>().index_read();
+	for (uint32_t i = 0; i < idx.size(); i++) if (idx[i] != i) { std::printf("FAILED: index list is not the identity after the search\n"); g_failures++; break; }
+	auto all = prt.index_read(); // the scene's own list shares the hidden particles and was re-mapped with them (pool.cpp:20)
+	if (all.size() != n) { std::printf("FAILED: the sharing list lost entries (%zu)\n", all.size()); g_failures++; }
+	for (uint32_t i = 0; i < all.size(); i++) if (all[i] != i) { std::printf("FAILED: the sharing list was not re-mapped\n"); g_failures++; break; }
+
+	shader_provider::start_recording();
+	for (int it = 0; it < 4; it++) solver.apply();
+	shader_provider::end_recording();
+	auto after = fl.get<fluid_enum::particle>().hidden_list().get<hp::position>().read<int32_t>();
+	long long moved = 0;
+	for (size_t i = 0; i < after.size(); i++) moved += std::llabs((long long)after[i] - gotPos[i]);
+	if (moved == 0) { std::printf("FAILED: the solver did not move any particle\n"); g_failures++; }
+}
+
+int main()
+{
+	apbf_ctx* ctx = nullptr;
+	const int rc = apbf_ctx_create(0, nullptr, &ctx);
+	if (rc == APBF_ERR_NO_DEVICE) { std::printf("no CUDA device: the product has no CPU path\n"); return 77; }
+	if (rc != APBF_OK) { std::printf("apbf_ctx_create failed: %d\n", rc); return 1; }
+	shader_provider::set_context(ctx);
+	try {
+		gpu_list_tests();
+		indexed_list_tests();
+		algorithm_tests();
+		operator_tests();
+	} catch (const std::exception& e) {
+		std::printf("EXCEPTION: %s\n", e.what());
+		g_failures++;
+	}
+	std::printf(g_failures ? "%d FAILED\n" : "all pbd list / algorithm / operator tests passed\n", g_failures);
+	return g_failures ? 1 : 0;
+}
