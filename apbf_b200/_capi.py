@@ -112,6 +112,19 @@ SIGNATURES = {
     "apbf_sim_neighbors": (C.c_int, [vp, C.POINTER(Neighbors)]),
     "apbf_sim_neighbor_count": (C.c_int, [vp, u32p]),
     "apbf_sim_stats": (C.c_int, [vp, u32p]),
+    "apbf_sim_mg_enable": (C.c_int, [vp, C.c_int, C.c_int, C.c_float]),
+    "apbf_sim_mg_brick": (C.c_int, [vp, C.c_int, u32p, u32p, u32p]),
+    "apbf_sim_mg_set_counts": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "apbf_sim_mg_route": (C.c_int, [vp, vp]),
+    "apbf_sim_mg_pack_state": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
+    "apbf_sim_mg_unpack_state": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, C.c_int]),
+    "apbf_sim_mg_copy_state": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "apbf_sim_mg_swap": (C.c_int, [vp]),
+    "apbf_sim_mg_halo_lists": (C.c_int, [vp, vp, C.c_uint32, vp]),
+    "apbf_sim_mg_pack": (C.c_int, [vp, C.c_int, vp, C.c_uint32, vp]),
+    "apbf_sim_mg_unpack": (C.c_int, [vp, C.c_int, vp, C.c_uint32, C.c_uint32, vp]),
+    "apbf_sim_mg_remap": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32]),
+    "apbf_sim_mg_phase": (C.c_int, [vp, C.c_int, C.c_int]),
     "apbf_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
     "apbf_host_free_pinned": (C.c_int, [vp]),
 }

@@ -20,7 +20,7 @@ enum apbf_scratch_slot {
 	SLOT_SCAN_STATUS, SLOT_MISC_WORDS, SLOT_CELL_START, SLOT_CELL_END, SLOT_COUNTS, SLOT_OFFSETS, SLOT_NB,
 	SLOT_INV_PERM, SLOT_TMP_KEYS, SLOT_TMP_VALS, SLOT_TMP_VALS2, SLOT_CODE0, SLOT_CODE1, SLOT_CODE2,
 	SLOT_P4, SLOT_L4, SLOT_G4, SLOT_DELTA, SLOT_PUSH, SLOT_RADIUS_ID, SLOT_KWFX, SLOT_KEEP_COUNTS, SLOT_KEEP_OFFSETS,
-	SLOT_PAIRS_TMP, SLOT_NB_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4, SLOT_KG, SLOT_KH, SLOT_Q4, SLOT_KEY_ID, SLOT_EDIT_COUNTS, SLOT_EDIT_OFFSETS,
+	SLOT_PAIRS_TMP, SLOT_NB_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4, SLOT_KG, SLOT_KH, SLOT_Q4, SLOT_KEY_ID, SLOT_EDIT_COUNTS, SLOT_EDIT_OFFSETS, SLOT_MG_INV,
 	SLOT_COUNT
 };
 
@@ -44,8 +44,10 @@ enum apbf_misc_word {
 	MW_KEPT_PAIRS = 4,   // pair count after the last spread_kernel_width prune
 	MW_OCC_CELLS = 5,    // number of occupied grid cells seen by the last Green search
 	MW_SNAPSHOT = 6,     // scratch word of the list helpers
+	MW_N_OWNED = 7,      // multi-GPU: ids >= this are ghost particles (0xFFFFFFFF: none)
 	MW_TICKET0 = 8,      // tile tickets of the chained-scan kernels (8 words)
 	MW_SCAN_TOTAL = 16,
+	MW_GID_BASE = 17,    // multi-GPU: global id of local id 0 (box_collision hashes the id)
 	MW_WORDS = 64
 };
 
@@ -75,6 +77,8 @@ struct apbf_ctx {
 	// provenance of the neighbour list structure built by the last search (offsets/NB valid for this buffer)
 	const uint32_t* nbr_struct_pairs = nullptr;
 	uint32_t        nbr_struct_n_cap = 0;
+	// multi-GPU slabs: ghost particles sort into a second key space and are searched through a second cell table
+	bool            mg_enabled = false;
 
 	void* scratch_get(int slot, size_t bytes);
 	uint32_t* misc() { return (uint32_t*)scratch_get(SLOT_MISC_WORDS, MW_WORDS * sizeof(uint32_t)); }

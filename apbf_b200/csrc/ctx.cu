@@ -63,7 +63,11 @@ void* apbf_ctx::scratch_get(int slot, size_t bytes)
 		return nullptr;
 	}
 	s.bytes = want;
-	if (slot == SLOT_MISC_WORDS) cudaMemset(s.ptr, 0, want);
+	if (slot == SLOT_MISC_WORDS) {
+		cudaMemset(s.ptr, 0, want);
+		const uint32_t none = 0xFFFFFFFFu;
+		cudaMemcpy((uint32_t*)s.ptr + MW_N_OWNED, &none, 4, cudaMemcpyHostToDevice);
+	}
 	return s.ptr;
 }
 

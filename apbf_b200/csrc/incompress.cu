@@ -91,7 +91,9 @@ __global__ void k_begin_iteration(sweep_args A)
 	const uint32_t n = *A.len;
 	const bool ident = A.misc[MW_IDENTITY] != 0u;
 	const bool has_asym = A.misc[MW_N_ASYM] != 0u;
-	for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+	const uint32_t n_own = min(n, A.misc[MW_N_OWNED]); // ghosts: their packed records arrive by halo exchange
+	const uint32_t gid_base = A.misc[MW_GID_BASE];
+	for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_own; a += gridDim.x * blockDim.x) {
 		const uint32_t idx = ident ? a : A.index_list[a];
 		int4 p = *((const int4*)A.pos4 + idx);
 		if (COMMIT) {
@@ -101,7 +103,7 @@ __global__ void k_begin_iteration(sweep_args A)
 		}
 		if (BOX) { // box_collision.comp:36-60
 			float px = (float)p.x * INV_R_POS, py = (float)p.y * INV_R_POS, pz = (float)p.z * INV_R_POS;
-			box_push(px, py, pz, a, A.radius[idx], A.bmin, A.bmax, A.n_boxes);
+			box_push(px, py, pz, a + gid_base, A.radius[idx], A.bmin, A.bmax, A.n_boxes);
 			p.x = f2i(px * R_POS); p.y = f2i(py * R_POS); p.z = f2i(pz * R_POS);
 		}
 		if (COMMIT || BOX) *((int4*)A.pos4 + idx) = p;
@@ -113,7 +115,7 @@ __global__ void k_begin_iteration(sweep_args A)
 template <int HK, int GK, bool COM>
 __global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
 {
-	const uint32_t n = *A.len;
+	const uint32_t n = min(*A.len, A.misc[MW_N_OWNED]); // owned particles only; a ghost's lambda arrives by halo exchange
 	const bool has_asym = A.misc[MW_N_ASYM] != 0u;
 	const unsigned lane = threadIdx.x & 31u, sub = lane & 7u, grp = lane >> 3;
 	const uint32_t warps_per_grid = gridDim.x * (SWEEP_THREADS / 32);
@@ -240,6 +242,7 @@ template <int GK>
 __global__ void __launch_bounds__(SWEEP_THREADS) k_apply_delta(sweep_args A)
 {
 	const uint32_t n = *A.len;
+	const uint32_t n_own = min(n, A.misc[MW_N_OWNED]); // a ghost's segment holds only unmirrored pairs onto owned particles: push part only
 	const bool filter = A.s.mBoundarinessCalculationMethod == 2;
 	const bool has_asym = A.misc[MW_N_ASYM] != 0u;
 	const unsigned lane = threadIdx.x & 31u, sub = lane & 7u, grp = lane >> 3;
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_apply_delta(sweep_args A)
 			t = __shfl_sync(FULL, hit, src); if (mine) my_hit = t;
 		}
 		const uint32_t a = base + lane;
-		if (a >= n) continue;
+		if (a >= n_own) continue;
 		int4 d = A.delta[a]; // the particle's own shift from T1
 		d.x += my_sx; d.y += my_sy; d.z += my_sz;
 		A.delta[a] = d;
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_apply_delta(sweep_args A)
 // position += delta (+ pushes); xyz only, w is the caller's
 __global__ void k_commit_delta(sweep_args A)
 {
-	const uint32_t n = *A.len;
+	const uint32_t n = min(*A.len, A.misc[MW_N_OWNED]);
 	const bool ident = A.misc[MW_IDENTITY] != 0u;
 	const bool has_asym = A.misc[MW_N_ASYM] != 0u;
 	for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
@@ -443,7 +446,8 @@ int apbf_solver_iteration(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors
 	A.out_incomp = out_incomp;
 	cudaStream_t st = ctx->stream;
 	const unsigned egrid = apbf_grid(ctx, n_cap, 256);
-	{
+	const bool run_all = (flags & (ITER_RUN_BEGIN | ITER_RUN_T1 | ITER_RUN_T2)) == 0;
+	if (run_all || (flags & ITER_RUN_BEGIN)) {
 		apbf_prof_scope ps(ctx, (flags & ITER_BEGIN_BOX) ? PROF_BOX : PROF_COMMIT);
 		const bool c = flags & ITER_BEGIN_COMMIT, b = flags & ITER_BEGIN_BOX;
 		if (c && b) k_begin_iteration<true, true><<<egrid, 256, 0, st>>>(A);
@@ -453,7 +457,7 @@ int apbf_solver_iteration(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors
 		APBF_LAUNCHED(ctx);
 	}
 	const unsigned grid = apbf_grid(ctx, n_cap, SWEEP_THREADS, 8);
-	{
+	if (run_all || (flags & ITER_RUN_T1)) {
 		apbf_prof_scope ps(ctx, PROF_DENSITY_LAMBDA);
 		switch (A.s.mHeightKernelId) {
 			case 0: APBF_TRY(launch_density_lambda<0>(ctx, A, grid)); break;
@@ -464,7 +468,7 @@ int apbf_solver_iteration(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors
 			default: return apbf_fail(ctx, APBF_ERR_INVALID, "height kernel id", __FILE__, __LINE__);
 		}
 	}
-	{
+	if (run_all || (flags & ITER_RUN_T2)) {
 		apbf_prof_scope ps(ctx, PROF_APPLY_DELTA);
 		switch (A.s.mGradientKernelId) {
 			case 0: k_apply_delta<0><<<grid, SWEEP_THREADS, 0, st>>>(A); break;

@@ -6,13 +6,14 @@ namespace {
 
 template <int DIMS>
 __global__ void k_position_hash(const int32_t* __restrict__ pos4, uint32_t* __restrict__ out, const uint32_t* __restrict__ len,
-                                apbf_grid_params g)
+                                apbf_grid_params g, const uint32_t* __restrict__ misc, uint32_t ghost_bit)
 {
 	const uint32_t n = *len;
+	const uint32_t n_owned = ghost_bit ? misc[MW_N_OWNED] : 0xFFFFFFFFu;
 	for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
 		int4 p = ldg_int4(pos4, id);
 		float px = (float)p.x * INV_R_POS, py = (float)p.y * INV_R_POS, pz = (float)p.z * INV_R_POS;
-		out[id] = apbf_zhash<DIMS>(apbf_map_axis(px, g, 0), apbf_map_axis(py, g, 1), apbf_map_axis(pz, g, 2), g.res);
+		out[id] = apbf_zhash<DIMS>(apbf_map_axis(px, g, 0), apbf_map_axis(py, g, 1), apbf_map_axis(pz, g, 2), g.res) | (id >= n_owned ? ghost_bit : 0u);
 	}
 }
 
@@ -198,11 +199,11 @@ __global__ void k_hidden_edit_emit(const uint32_t* __restrict__ edit, const uint
 
 // ---- internal launchers ---------------------------------------------------------------------------------------------
 int apbf_launch_position_hash(apbf_ctx* ctx, const int32_t* pos4, uint32_t* out, const uint32_t* len, uint32_t cap,
-                              const apbf_grid_params& g)
+                              const apbf_grid_params& g, uint32_t ghost_bit)
 {
 	if (cap == 0) return APBF_OK;
-	if (g.dims == 3) k_position_hash<3><<<apbf_grid(ctx, cap, 256), 256, 0, ctx->stream>>>(pos4, out, len, g);
-	else k_position_hash<2><<<apbf_grid(ctx, cap, 256), 256, 0, ctx->stream>>>(pos4, out, len, g);
+	if (g.dims == 3) k_position_hash<3><<<apbf_grid(ctx, cap, 256), 256, 0, ctx->stream>>>(pos4, out, len, g, ctx->misc(), ghost_bit);
+	else k_position_hash<2><<<apbf_grid(ctx, cap, 256), 256, 0, ctx->stream>>>(pos4, out, len, g, ctx->misc(), ghost_bit);
 	APBF_LAUNCHED(ctx);
 	return APBF_OK;
 }

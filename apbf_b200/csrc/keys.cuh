@@ -12,8 +12,9 @@ struct apbf_grid_params {
 };
 
 int apbf_make_grid_params(apbf_ctx* ctx, const float mn[3], const float mx[3], uint32_t res, apbf_grid_params* g);
+// ghost_bit != 0: ids >= misc[MW_N_OWNED] get this bit added to their key (they sort behind all owned particles)
 int apbf_launch_position_hash(apbf_ctx* ctx, const int32_t* pos4, uint32_t* out, const uint32_t* len, uint32_t cap,
-                              const apbf_grid_params& g);
+                              const apbf_grid_params& g, uint32_t ghost_bit = 0u);
 int apbf_launch_position_code(apbf_ctx* ctx, const uint32_t* index_list, const int32_t* pos4, uint32_t* out,
                               const uint32_t* len, uint32_t cap, uint32_t section);
 int apbf_launch_find_value_ranges(apbf_ctx* ctx, const uint32_t* index_list, const uint32_t* values, uint32_t* range_start,

@@ -163,10 +163,16 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32)
 k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ key_id, const float* __restrict__ range,
                    const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, const uint32_t* __restrict__ len,
                    apbf_grid_params g, float range_scale, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
-                   uint32_t* __restrict__ pairs, uint32_t* __restrict__ nbl, uint32_t cap, uint32_t* misc, int cull)
+                   uint32_t* __restrict__ pairs, uint32_t* __restrict__ nbl, uint32_t cap, uint32_t* misc, int cull, uint32_t table_cells,
+                   uint32_t layers)
 {
+	// Multi-GPU slabs (layers == 2): ids >= n_owned are ghosts.  Their keys carry one extra bit, so they form a second cell
+	// table behind the first (offset table_cells) and every cell is walked in both.  A ghost is a query too, but only for
+	// the pairs nobody else provides: unmirrored pairs onto owned particles (the scatter part of the sweeps).
 	__shared__ float4 s_q[EMIT_WARPS][32];
 	const uint32_t n = *len;
+	const uint32_t n_owned = misc[MW_N_OWNED];
+	const uint32_t key_mask = table_cells - 1u; // table_cells is a power of two
 	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	const uint32_t axis_cap = 1u << g.res; // a box wider than the grid only revisits aliased cells
@@ -189,7 +195,7 @@ k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ k
 		float r_lane = 0.0f;
 		if (in) {
 			me = q4[id];
-			gkey = key_id[id] >> gshift;
+			gkey = key_id[id] >> gshift; // includes the ghost bit: owned and ghost particles never share a run
 			const float r = range[id] * range_scale;
 			r_lane = r == r ? fmaxf(r, 0.0f) : INFINITY; // a NaN range accepts every candidate
 			qc[0] = apbf_map_axis(me.x, g, 0); qc[1] = apbf_map_axis(me.y, g, 1); qc[2] = apbf_map_axis(me.z, g, 2);
@@ -228,10 +234,13 @@ k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ k
 			const float cull2 = cull ? r_cull * r_cull * 1.0001f : INFINITY;
 			const uint32_t nxy = ext[0] * ext[1], ncell = nxy * ext[2];
 			const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)ext[0];
-			for (uint32_t cbase = 0; cbase < ncell; cbase += 32) {
-				const uint32_t ci = cbase + lane;
+			const bool ghost_run = tile_first + r0 >= n_owned;
+			for (uint32_t cbase = 0; cbase < ncell * layers; cbase += 32) {
+				uint32_t ci = cbase + lane;
 				uint32_t c_first = 0u, c_cnt = 0u;
-				if (ci < ncell) {
+				if (ci < ncell * layers) {
+					const uint32_t table_off = ci >= ncell ? table_cells : 0u;
+					if (ci >= ncell) ci -= ncell;
 					// ci = (cz * ny + cy) * nx + cx; float reciprocals + one correction step are exact for ci < 2^24
 					uint32_t cz, cy;
 					if (ncell <= (1u << 24)) {
@@ -254,7 +263,7 @@ k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ k
 					const float gy = fmaxf((float)max(qlo[1] - iy, iy - qhi[1]) - 1.01f, 0.0f) * csz[1];
 					const float gz = fmaxf((float)max(qlo[2] - iz, iz - qhi[2]) - 1.01f, 0.0f) * csz[2];
 					if (!(gx * gx + gy * gy + gz * gz > cull2)) {
-						const uint32_t h = apbf_zhash<DIMS>(ax, ay, az, g.res);
+						const uint32_t h = (apbf_zhash<DIMS>(ax, ay, az, g.res) & key_mask) + table_off;
 						c_first = __ldg(cell_start + h);
 						c_cnt = __ldg(cell_end + h) - c_first;
 					}
@@ -284,7 +293,8 @@ k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ k
 						const float4 qv = s_q[w][qi];
 						const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
 						const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-						const bool hit = cvalid && !(d2 > qv.w) && cand != tile_first + qi;
+						bool hit = cvalid && !(d2 > qv.w) && cand != tile_first + qi;
+						if (ghost_run) hit = hit && cand < n_owned && d2 > c4.w;
 						const uint32_t b = __ballot_sync(0xffffffffu, hit);
 						if (b == 0u) continue;
 						if (FILL) {
@@ -507,8 +517,10 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 	uint32_t* keys = (uint32_t*)ctx->scratch_get(SLOT_SORT_KEYS_A, sizeof(uint32_t) * (size_t)nh_cap);
 	uint32_t* skeys = (uint32_t*)ctx->scratch_get(SLOT_TMP_KEYS, sizeof(uint32_t) * (size_t)nh_cap);
 	uint32_t* sidx = (uint32_t*)ctx->scratch_get(SLOT_TMP_VALS, sizeof(uint32_t) * (size_t)nh_cap);
-	uint32_t* cs = (uint32_t*)ctx->scratch_get(SLOT_CELL_START, sizeof(uint32_t) * (size_t)max_hash);
-	uint32_t* ce = (uint32_t*)ctx->scratch_get(SLOT_CELL_END, sizeof(uint32_t) * (size_t)max_hash);
+	const uint32_t layers = ctx->mg_enabled ? 2u : 1u; // ghosts: second key space / cell table
+	APBF_REQUIRE(ctx, layers == 1u || max_hash <= (1u << 30));
+	uint32_t* cs = (uint32_t*)ctx->scratch_get(SLOT_CELL_START, sizeof(uint32_t) * (size_t)max_hash * layers);
+	uint32_t* ce = (uint32_t*)ctx->scratch_get(SLOT_CELL_END, sizeof(uint32_t) * (size_t)max_hash * layers);
 	uint32_t* counts = (uint32_t*)ctx->scratch_get(SLOT_COUNTS, sizeof(uint32_t) * (size_t)(n_cap + 1));
 	uint32_t* offsets = (uint32_t*)ctx->scratch_get(SLOT_OFFSETS, sizeof(uint32_t) * (size_t)(n_cap + 1));
 	uint32_t* nbl = (uint32_t*)ctx->scratch_get(SLOT_NB, sizeof(uint32_t) * ((size_t)nb->capacity + 1));
@@ -520,7 +532,7 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 	// hash all hidden particles (neighborhood_green.cpp:50-52), sort by hash with the slot as payload (:53)
 	{
 		apbf_prof_scope ps(ctx, PROF_HASH_SORT);
-		APBF_TRY(apbf_launch_position_hash(ctx, (const int32_t*)p.position.data, keys, p.hidden_length, nh_cap, g));
+		APBF_TRY(apbf_launch_position_hash(ctx, (const int32_t*)p.position.data, keys, p.hidden_length, nh_cap, g, layers == 2u ? max_hash : 0u));
 		APBF_TRY(apbf_radix_sort_pairs(ctx, keys, nullptr, skeys, sidx, p.hidden_length, nh_cap, apbf_reference_sort_bits(max_hash)));
 	}
 	// permute hidden arrays, index list and per-id arrays (:54-56)
@@ -534,7 +546,7 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 	// cell ranges (:58-63)
 	{
 		apbf_prof_scope ps(ctx, PROF_CELL_RANGES);
-		APBF_TRY(apbf_launch_find_value_ranges(ctx, new_index, skeys, cs, ce, p.length, n_cap, max_hash));
+		APBF_TRY(apbf_launch_find_value_ranges(ctx, new_index, skeys, cs, ce, p.length, n_cap, max_hash * layers));
 	}
 	// pairs (:64-74): count, scan, fill
 	k_clear_search_words<<<1, 1, 0, st>>>(misc);
@@ -547,10 +559,10 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 		APBF_LAUNCHED(ctx);
 		if (g.dims == 3)
 			k_green_emit_cells<false, 3><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, counts,
-			                                                               nullptr, nullptr, nullptr, 0u, misc, cull);
+			                                                               nullptr, nullptr, nullptr, 0u, misc, cull, max_hash, layers);
 		else
 			k_green_emit_cells<false, 2><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, counts,
-			                                                               nullptr, nullptr, nullptr, 0u, misc, cull);
+			                                                               nullptr, nullptr, nullptr, 0u, misc, cull, max_hash, layers);
 		APBF_LAUNCHED(ctx);
 	}
 	{
@@ -561,10 +573,10 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
 		if (g.dims == 3)
 			k_green_emit_cells<true, 3><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, nullptr,
-			                                                              offsets, nb->pairs, nbl, nb->capacity, misc, cull);
+			                                                              offsets, nb->pairs, nbl, nb->capacity, misc, cull, max_hash, layers);
 		else
 			k_green_emit_cells<true, 2><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, nullptr,
-			                                                              offsets, nb->pairs, nbl, nb->capacity, misc, cull);
+			                                                              offsets, nb->pairs, nbl, nb->capacity, misc, cull, max_hash, layers);
 		APBF_LAUNCHED(ctx);
 	}
 	ctx->nbr_struct_pairs = nb->pairs;

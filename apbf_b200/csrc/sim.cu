@@ -4,15 +4,7 @@
 #include "common.cuh"
 #include "solver.cuh"
 
-struct apbf_sim {
-	apbf_ctx*       ctx;
-	apbf_sim_config cfg;
-	apbf_fluid      fluid;
-	apbf_neighbors  nb;
-	float*          boxes;    // [2 * n_boxes * 4]
-	float           last_dt;  // velocity_handling::mLastDeltaTime (velocity_handling.h:18)
-	std::vector<void*> owned;
-};
+#include "sim.cuh"
 
 namespace {
 
@@ -31,7 +23,11 @@ void swap_array(apbf_array* a)
 	void* t = a->data; a->data = a->reorder_out; a->reorder_out = t;
 }
 
-void swap_after_search(apbf_sim* sim)
+__global__ void k_set_lengths(uint32_t* a, uint32_t* b, uint32_t n) { *a = n; *b = n; }
+
+} // namespace
+
+void apbf_sim_swap_buffers(apbf_sim* sim)
 {
 	apbf_fluid& f = sim->fluid;
 	apbf_array* all[] = { &f.particle.index_list, &f.particle.position, &f.particle.velocity, &f.particle.inverse_mass,
@@ -39,10 +35,6 @@ void swap_after_search(apbf_sim* sim)
 	                      &f.kernel_width, &f.boundariness, &f.boundary_distance };
 	for (apbf_array* a : all) swap_array(a);
 }
-
-__global__ void k_set_lengths(uint32_t* a, uint32_t* b, uint32_t n) { *a = n; *b = n; }
-
-} // namespace
 
 extern "C" {
 
@@ -180,7 +172,7 @@ int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
 			APBF_TRY(apbf_neighborhood_binary_search_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, nullptr));
 		else
 			APBF_TRY(apbf_neighborhood_green_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, nullptr));
-		swap_after_search(sim);
+		apbf_sim_swap_buffers(sim);
 		if (adaptive) APBF_TRY(apbf_spread_kernel_width_apply(ctx, &sim->fluid, &sim->nb, nullptr)); // pool.cpp:87-89
 		// pool.cpp:92-95: solverIterations x (box_collision, incompressibility).  Same results as calling the two
 		// operators in turn; the per-particle constants are computed once (kernel widths are fixed from here on) and

@@ -1,0 +1,25 @@
+// sim.cuh -- the whole-scene object shared by sim.cu (single GPU) and mgpu.cu (slab partition across GPUs)
+#pragma once
+#include "common.cuh"
+
+struct apbf_mg_state {
+	bool     enabled = false;
+	int      rank = 0, world = 1;
+	uint32_t lo[8][3], hi[8][3];   // brick of every rank in cell coordinates, inclusive
+	uint32_t halo[3];              // halo width in cells per axis
+	uint32_t n_owned = 0, n_total = 0;
+};
+
+struct apbf_sim {
+	apbf_ctx*       ctx;
+	apbf_sim_config cfg;
+	apbf_fluid      fluid;
+	apbf_neighbors  nb;
+	float*          boxes;    // [2 * n_boxes * 4]
+	float           last_dt;  // velocity_handling::mLastDeltaTime (velocity_handling.h:18)
+	std::vector<void*> owned;
+	apbf_mg_state   mg;
+};
+
+// data <-> reorder_out of every list (after a search or a re-partition)
+void apbf_sim_swap_buffers(apbf_sim* sim);

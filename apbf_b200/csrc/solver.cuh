@@ -5,7 +5,9 @@
 enum apbf_iter_flags {
 	ITER_BEGIN_COMMIT = 1, // add the previous iteration's pending position deltas first
 	ITER_BEGIN_BOX = 2,    // box_collision fused into the prologue (pool.cpp:93)
-	ITER_END_COMMIT = 4    // add this iteration's deltas to the positions before returning
+	ITER_END_COMMIT = 4,   // add this iteration's deltas to the positions before returning
+	// multi-GPU: run only part of the iteration (halo exchanges happen in between); none of the three set = all of them
+	ITER_RUN_BEGIN = 8, ITER_RUN_T1 = 16, ITER_RUN_T2 = 32
 };
 
 // per-particle constants that only depend on kernel width / radius / inverse mass (exact double-precision pow);

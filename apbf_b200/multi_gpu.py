@@ -1,0 +1,256 @@
+"""One scene across the GPUs of a node: host side of the slab (brick) protocol (device side: csrc/mgpu.cu).
+
+One process per GPU.  `SlabDomain.substep()` is pool::update (source/pool.cpp:67-106) cut where data of other ranks is
+needed:
+
+    integrate owned                          (velocity_handling)
+    ROUTE    particles that left the brick change owner: full 80-byte state, new order
+             [arrivals from lower ranks | stayers | arrivals from higher ranks] == the order the single-GPU sort sees
+    HALO     owned particles inside another rank's brick grown by the halo width go there as ghosts (32 bytes each)
+    search   over owned + ghosts; send lists and ghost slots follow the sort permutation
+    spread_kernel_width, then KW exchange    (owners' new widths overwrite the ghosts')
+    per iteration: prologue (commit, box collision, pack) -> P4 exchange -> density/lambda sweep -> LAMBDA exchange
+                   -> apply sweep
+    final commit
+
+Two host synchronisations per substep (the message sizes of ROUTE and HALO); the four per-iteration exchanges reuse the
+send lists, their sizes are known, and they are stream-ordered.  All accumulators on the path are integers, hence the
+N-rank result equals the 1-rank result bit for bit.
+
+The class is backend-agnostic on purpose: `CudaRankBackend` drives the C-ABI (`apbf_sim_mg_*`), and the CPU tests plug in a
+numpy/oracle backend over gloo to check this host logic without a GPU (tests/test_multi_rank_gloo.py).  torch.distributed is
+plumbing only.
+"""
+import ctypes as C
+
+import numpy as np
+
+HALO, KW, P4, LAMBDA = 0, 1, 2, 3
+WORDS = {HALO: 8, KW: 1, P4: 4, LAMBDA: 1}
+STATE_WORDS = 20
+
+
+class TorchComm:
+    """send/recv of int32 word buffers between ranks through torch.distributed (nccl: device tensors, gloo: CPU tensors)"""
+
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.device = device if device is not None else torch.device("cpu")
+        self.bytes_sent = 0
+        self.messages = 0
+
+    def all_gather_counts(self, counts):
+        """counts: list[world] of ints on this rank -> matrix m[src][dst]"""
+        t = self.torch.tensor([int(c) for c in counts], dtype=self.torch.int64, device=self.device)
+        if self.world == 1:
+            return [t.tolist()]
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [o.tolist() for o in out]
+
+    def exchange(self, send, recv_counts, words):
+        """send: {rank: int32 tensor [count, words]}, recv_counts: {rank: count} -> {rank: int32 tensor [count, words]}"""
+        torch, dist = self.torch, self.dist
+        recv = {r: torch.empty((int(c), words), dtype=torch.int32, device=self.device) for r, c in recv_counts.items() if c}
+        ops = []
+        for r in sorted(set(send) | set(recv)):
+            if r in send and send[r].numel():
+                ops.append(dist.P2POp(dist.isend, send[r].contiguous(), r))
+                self.bytes_sent += send[r].numel() * 4
+                self.messages += 1
+            if r in recv:
+                ops.append(dist.P2POp(dist.irecv, recv[r], r))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return recv
+
+
+class SlabDomain:
+    def __init__(self, backend, comm, adaptive, solver_iterations, integrate=True):
+        self.b, self.comm = backend, comm
+        self.rank, self.world = comm.rank, comm.world
+        self.adaptive, self.iters, self.integrate = bool(adaptive), int(solver_iterations), bool(integrate)
+        self.n_own = backend.n_owned()
+        self.gid_base = 0
+        self.stats = dict(migrated=0, ghosts=0)
+
+    # ---- one exchange of `what` for the current send lists / ghost slots ------------------------------------------------------
+    def _refresh_ghosts(self, what):
+        if self.world == 1:
+            return
+        send = {r: self.b.pack(what, r) for r in range(self.world) if r != self.rank and self.send_counts[r]}
+        recv = self.comm.exchange(send, self.ghost_counts, WORDS[what])
+        off = 0
+        for r in range(self.world):
+            c = self.ghost_counts.get(r, 0)
+            if c:
+                self.b.unpack(what, off, c, recv[r])
+            off += c
+
+    def substep(self):
+        b, me, W = self.b, self.rank, self.world
+        b.set_counts(self.n_own, self.n_own, self.gid_base)          # ghosts of the last substep are dropped
+        if self.integrate:
+            b.integrate()
+        if W > 1:
+            # ---- ROUTE ---------------------------------------------------------------------------------------------------
+            counts = b.route()                                        # host sync 1
+            m = self.comm.all_gather_counts(counts)
+            first = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+            send = {r: b.pack_state(int(first[r]), int(counts[r])) for r in range(W) if r != me and counts[r]}
+            recv = self.comm.exchange(send, {r: m[r][me] for r in range(W) if r != me}, STATE_WORDS)
+            b.assemble(int(first[me]), int(counts[me]), [(r, recv[r]) for r in sorted(recv)], me)
+            owned = [sum(m[src][dst] for src in range(W)) for dst in range(W)]
+            self.stats["migrated"] = int(sum(counts) - counts[me])
+            self.n_own, self.gid_base = int(owned[me]), int(sum(owned[:me]))
+            b.set_counts(self.n_own, self.n_own, self.gid_base)
+            # ---- HALO ----------------------------------------------------------------------------------------------------
+            hc = b.halo_lists()                                       # host sync 2
+            mh = self.comm.all_gather_counts(hc)
+            self.send_counts = [int(c) for c in hc]
+            self.ghost_counts = {r: int(mh[r][me]) for r in range(W) if r != me and mh[r][me]}
+            n_ghost = sum(self.ghost_counts.values())
+            b.set_counts(self.n_own, self.n_own + n_ghost, self.gid_base)
+            b.begin_ghosts(n_ghost)
+            self._refresh_ghosts(HALO)
+            self.stats["ghosts"] = n_ghost
+        b.search()
+        if W > 1:
+            b.remap_after_search(self.send_counts, sum(self.ghost_counts.values()))
+        if self.adaptive:
+            b.spread()
+            self._refresh_ghosts(KW)
+        b.prepare()
+        for it in range(self.iters):
+            b.iter_begin(it)
+            self._refresh_ghosts(P4)
+            b.density_lambda()
+            self._refresh_ghosts(LAMBDA)
+            b.apply_delta()
+        b.final_commit()
+        b.set_counts(self.n_own, self.n_own, self.gid_base)
+
+
+class CudaRankBackend:
+    """The device steps of the protocol through the C-ABI (apbf_sim_mg_*); staging buffers are torch device tensors."""
+
+    def __init__(self, sim, n_owned, world, rank, halo_range, ghost_capacity):
+        import torch
+        from . import _check
+        self.torch, self._check = torch, _check
+        self.sim, self.lib, self.ctx = sim, sim.lib, sim.ctx
+        self.world, self.rank = world, rank
+        self._n_owned = int(n_owned)
+        dev = torch.device("cuda", sim.ctx.device)
+        self.dev = dev
+        self.cap_per_dest = int(ghost_capacity)
+        self.counts_dev = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.send_ids = torch.zeros((world, self.cap_per_dest), dtype=torch.int32, device=dev)
+        self.ghost_ids = torch.zeros(max(self.cap_per_dest * max(world - 1, 1), 1), dtype=torch.int32, device=dev)
+        self.send_counts = [0] * world
+        self.ghost_first = 0
+        self._ck(self.lib.apbf_sim_mg_enable(sim.handle, rank, world, C.c_float(halo_range)))
+
+    def _ck(self, rc):
+        self._check(self.ctx, rc)
+
+    def n_owned(self):
+        return self._n_owned
+
+    def set_counts(self, n_owned, n_total, gid_base):
+        self._n_owned = n_owned
+        self._ck(self.lib.apbf_sim_mg_set_counts(self.sim.handle, n_owned, n_total, gid_base))
+
+    def _phase(self, p, it=0):
+        self._ck(self.lib.apbf_sim_mg_phase(self.sim.handle, p, it))
+
+    def integrate(self): self._phase(0)
+    def search(self): self._phase(1)
+    def spread(self): self._phase(2)
+    def prepare(self): self._phase(3)
+    def iter_begin(self, it): self._phase(4, it)
+    def density_lambda(self): self._phase(5)
+    def apply_delta(self): self._phase(6)
+    def final_commit(self): self._phase(7)
+
+    def route(self):
+        self._ck(self.lib.apbf_sim_mg_route(self.sim.handle, self.counts_dev.data_ptr()))
+        return self.counts_dev[: self.world].tolist()                # synchronises
+
+    def pack_state(self, first, count):
+        out = self.torch.empty((count, STATE_WORDS), dtype=self.torch.int32, device=self.dev)
+        self._ck(self.lib.apbf_sim_mg_pack_state(self.sim.handle, first, count, out.data_ptr()))
+        return out
+
+    def assemble(self, stay_first, stay_count, arrivals, me):
+        off = 0
+        placed_stayers = False
+        for r, buf in arrivals + [(None, None)]:
+            if not placed_stayers and (r is None or r > me):
+                self._ck(self.lib.apbf_sim_mg_copy_state(self.sim.handle, stay_first, off, stay_count))
+                off += stay_count
+                placed_stayers = True
+            if r is not None:
+                self._ck(self.lib.apbf_sim_mg_unpack_state(self.sim.handle, off, buf.shape[0], buf.data_ptr(), 1))
+                off += buf.shape[0]
+        self._ck(self.lib.apbf_sim_mg_swap(self.sim.handle))
+
+    def halo_lists(self):
+        self._ck(self.lib.apbf_sim_mg_halo_lists(self.sim.handle, self.send_ids.data_ptr(), self.cap_per_dest, self.counts_dev.data_ptr()))
+        c = self.counts_dev[: self.world].tolist()                    # synchronises
+        if max(c) > self.cap_per_dest:
+            raise RuntimeError(f"halo send list overflow: {max(c)} > capacity {self.cap_per_dest}")
+        self.send_counts = c
+        return c
+
+    def begin_ghosts(self, n_ghost):
+        if n_ghost > self.ghost_ids.numel():
+            raise RuntimeError(f"ghost capacity exceeded: {n_ghost} > {self.ghost_ids.numel()}")
+        self.ghost_first = self._n_owned
+        self.ghosts_sorted = False
+
+    def pack(self, what, dest):
+        n = self.send_counts[dest]
+        out = self.torch.empty((n, WORDS[what]), dtype=self.torch.int32, device=self.dev)
+        self._ck(self.lib.apbf_sim_mg_pack(self.sim.handle, what, self.send_ids[dest].data_ptr(), n, out.data_ptr()))
+        return out
+
+    def unpack(self, what, ghost_offset, count, buf):
+        ids = self.ghost_ids.data_ptr() + 4 * ghost_offset
+        self._ck(self.lib.apbf_sim_mg_unpack(self.sim.handle, what, ids, self.ghost_first + ghost_offset, count, buf.data_ptr()))
+
+    def remap_after_search(self, send_counts, n_ghost):
+        for r in range(self.world):
+            if r != self.rank and send_counts[r]:
+                self._ck(self.lib.apbf_sim_mg_remap(self.sim.handle, self.send_ids[r].data_ptr(), send_counts[r], 0xFFFFFFFF))
+        self._ck(self.lib.apbf_sim_mg_remap(self.sim.handle, self.ghost_ids.data_ptr(), n_ghost, self.ghost_first))
+
+
+def brick_of_rank(sim, rank):
+    lo, hi, halo = (C.c_uint32 * 3)(), (C.c_uint32 * 3)(), (C.c_uint32 * 3)()
+    sim.lib.apbf_sim_mg_brick(sim.handle, rank, lo, hi, halo)
+    return list(lo), list(hi), list(halo)
+
+
+def owner_rank_of_positions(position, min_pos, max_pos, res_log2, dims, world):
+    """Host-side initial distribution: rank of every particle = top log2(world) bits of its cell key (same float arithmetic
+    as calculate_position_hash.comp:23-36)."""
+    f32 = np.float32
+    lw = int(np.log2(world))
+    if lw == 0:
+        return np.zeros(len(position), np.int64)
+    mn, mx = np.asarray(min_pos, f32), np.asarray(max_pos, f32)
+    p = position[:, :3].astype(f32) * f32(1.0 / 262144.0)
+    cell = ((p - mn) / (mx - mn) * f32(1 << res_log2))
+    cell = np.clip(cell, 0, None).astype(np.uint32) & np.uint32((1 << res_log2) - 1)
+    rank = np.zeros(len(position), np.int64)
+    for b in range(lw):
+        level, axis = b // dims, dims - 1 - (b % dims)
+        bit = (cell[:, axis] >> np.uint32(res_log2 - 1 - level)) & 1
+        rank = (rank << 1) | bit.astype(np.int64)
+    return rank

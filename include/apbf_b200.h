@@ -294,6 +294,33 @@ int  apbf_sim_neighbor_count(apbf_sim* sim, uint32_t* out_count);
  * out[0] particles, out[1] pairs found by the search (unclamped), out[2] pairs after the spread_kernel_width prune
  * (== out[1] when it did not run), out[3] pairs without a mirrored pair */
 int  apbf_sim_stats(apbf_sim* sim, uint32_t out[4]);
+/* ---- one scene across the GPUs of a node: slab (brick) partition with ghost particles -------------------------------------
+ * No reference counterpart (the reference is single-device); device side of the protocol described in
+ * apbf_b200/csrc/mgpu.cu.  One apbf_sim per rank; the host moves the staging buffers between ranks (NCCL send/recv).
+ * rank = top log2(world) bits of the particle's cell key (world in {1, 2, 4, 8}); halo_range = upper bound of
+ * range_scale * kernel width over the whole scene. */
+int  apbf_sim_mg_enable(apbf_sim* sim, int rank, int world, float halo_range);
+int  apbf_sim_mg_brick(apbf_sim* sim, int rank, uint32_t out_lo[3], uint32_t out_hi[3], uint32_t out_halo[3]);
+/* list lengths = n_total (owned + ghosts), ids >= n_owned are ghosts, global id of local id 0 (box_collision hashes the id) */
+int  apbf_sim_mg_set_counts(apbf_sim* sim, uint32_t n_owned, uint32_t n_total, uint32_t gid_base);
+/* re-partition: group the owned particles by destination rank (stable), counts_dev[8] = group sizes */
+int  apbf_sim_mg_route(apbf_sim* sim, uint32_t* counts_dev);
+/* 80-byte records of every list of a particle, for the particles that change owner */
+int  apbf_sim_mg_pack_state(apbf_sim* sim, uint32_t first, uint32_t count, void* out_dev);
+int  apbf_sim_mg_unpack_state(apbf_sim* sim, uint32_t first, uint32_t count, const void* in_dev, int into_other);
+int  apbf_sim_mg_copy_state(apbf_sim* sim, uint32_t src_first, uint32_t dst_first, uint32_t count); /* current -> other buffers */
+int  apbf_sim_mg_swap(apbf_sim* sim);
+/* send lists: ids_dev[world][cap_per_dest] = owned ids inside rank r's brick grown by the halo; counts_dev[8] */
+int  apbf_sim_mg_halo_lists(apbf_sim* sim, uint32_t* ids_dev, uint32_t cap_per_dest, uint32_t* counts_dev);
+/* what: 0 halo record (32 B), 1 kernel width (4 B), 2 packed solver position (16 B), 3 lambda (4 B) */
+int  apbf_sim_mg_pack(apbf_sim* sim, int what, const uint32_t* ids_dev, uint32_t count, void* out_dev);
+int  apbf_sim_mg_unpack(apbf_sim* sim, int what, const uint32_t* ids_dev, uint32_t first, uint32_t count, const void* in_dev);
+/* after the search: slots before the sort -> ids after it (first != 0xFFFFFFFF: ids_dev[k] = first + k beforehand) */
+int  apbf_sim_mg_remap(apbf_sim* sim, uint32_t* ids_dev, uint32_t count, uint32_t first);
+/* phase: 0 integrate, 1 search, 2 spread_kernel_width, 3 solver constants, 4 iteration prologue, 5 density/lambda sweep,
+ * 6 apply sweep, 7 final commit (pool.cpp:67-106 cut where the halo exchanges happen) */
+int  apbf_sim_mg_phase(apbf_sim* sim, int phase, int iteration);
+
 /* pinned host memory helpers for callers without a CUDA runtime of their own */
 int  apbf_host_alloc_pinned(size_t bytes, void** out_host_ptr);
 int  apbf_host_free_pinned(void* host_ptr);

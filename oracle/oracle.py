@@ -261,3 +261,27 @@ def substep(st, s, *, dims, basic_pbf, solver_iterations, min_pos, max_pos, res_
     cst = st.c()
     n = lib().orc_substep(C.byref(cst), C.byref(s), C.byref(p), _p(pairs), C.c_uint32(cap))
     return pairs[:n]
+
+
+# ---- the four incompressibility passes one by one (incompressibility.cpp:39-42), for callers that step between them ----
+def incompressibility_passes_012(st, s, dims, pairs):
+    """Passes 0, 1, 2 on `st` (positions get the particles' own shift, incompressibility_2.comp:106-109).
+    Returns (incomp [n,8] u32, grad4 [P,4] f32, lambda [n] f32) for pass 3."""
+    pairs = np.ascontiguousarray(pairs, np.uint32)
+    n, npairs = st.n, len(pairs)
+    incomp = np.zeros((max(n, 1), 8), np.uint32)
+    lam = np.zeros(max(n, 1), np.float32)
+    grad4 = np.zeros((max(npairs, 1), 4), np.float32)
+    com4 = np.zeros((max(n, 1), 4), np.int32)
+    cst = st.c()
+    L = lib()
+    L.orc_incompressibility_0(C.byref(cst), C.byref(s), dims, _p(incomp))
+    L.orc_incompressibility_1(C.byref(cst), C.byref(s), dims, _p(pairs), C.c_uint32(npairs), _p(incomp), _p(com4), _p(grad4))
+    L.orc_incompressibility_2(C.byref(cst), C.byref(s), dims, _p(incomp), _p(com4), _p(lam))
+    return incomp, grad4, lam
+
+
+def incompressibility_pass_3(st, s, dims, pairs, incomp, grad4, lam):
+    pairs = np.ascontiguousarray(pairs, np.uint32)
+    cst = st.c()
+    lib().orc_incompressibility_3(C.byref(cst), C.byref(s), dims, _p(pairs), C.c_uint32(len(pairs)), _p(grad4), _p(lam), _p(incomp))
