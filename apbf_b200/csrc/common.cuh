@@ -79,6 +79,9 @@ struct apbf_ctx {
 	uint32_t        nbr_struct_n_cap = 0;
 	// multi-GPU slabs: ghost particles sort into a second key space and are searched through a second cell table
 	bool            mg_enabled = false;
+	// a following spread_kernel_width prunes pairs, which can turn a mirrored pair into an unmirrored one: ghosts then
+	// keep ALL their pairs onto owned particles until the prune has decided
+	bool            mg_ghost_all_pairs = false;
 
 	void* scratch_get(int slot, size_t bytes);
 	uint32_t* misc() { return (uint32_t*)scratch_get(SLOT_MISC_WORDS, MW_WORDS * sizeof(uint32_t)); }

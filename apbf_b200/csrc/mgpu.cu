@@ -467,6 +467,7 @@ int apbf_sim_mg_phase(apbf_sim* sim, int phase, int iteration)
 			sim->last_dt = c.dt;
 			return APBF_OK;
 		case 1: {
+			ctx->mg_ghost_all_pairs = !c.basic_pbf && !s.mBaseKernelWidthOnBoundaryDistance; // spread_kernel_width will prune
 			APBF_TRY(apbf_neighborhood_green_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, unit_scale ? 1.0f : 1.5f, c.min_pos, c.max_pos, c.res_log2, nullptr));
 			apbf_sim_swap_buffers(sim);
 			// old slot -> new id, for the send lists and the ghost slots (the search's sorted_index is still in scratch)

@@ -235,10 +235,11 @@ k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ k
 			const uint32_t nxy = ext[0] * ext[1], ncell = nxy * ext[2];
 			const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)ext[0];
 			const bool ghost_run = tile_first + r0 >= n_owned;
-			for (uint32_t cbase = 0; cbase < ncell * layers; cbase += 32) {
+			const uint32_t n_layers = layers > 1u ? 2u : 1u; // layers == 3: two tables + ghosts keep their mirrored pairs too
+			for (uint32_t cbase = 0; cbase < ncell * n_layers; cbase += 32) {
 				uint32_t ci = cbase + lane;
 				uint32_t c_first = 0u, c_cnt = 0u;
-				if (ci < ncell * layers) {
+				if (ci < ncell * n_layers) {
 					const uint32_t table_off = ci >= ncell ? table_cells : 0u;
 					if (ci >= ncell) ci -= ncell;
 					// ci = (cz * ny + cy) * nx + cx; float reciprocals + one correction step are exact for ci < 2^24
@@ -294,7 +295,7 @@ k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ k
 						const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
 						const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 						bool hit = cvalid && !(d2 > qv.w) && cand != tile_first + qi;
-						if (ghost_run) hit = hit && cand < n_owned && d2 > c4.w;
+						if (ghost_run) hit = hit && cand < n_owned && (layers == 3u || d2 > c4.w);
 						const uint32_t b = __ballot_sync(0xffffffffu, hit);
 						if (b == 0u) continue;
 						if (FILL) {
@@ -518,6 +519,7 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 	uint32_t* skeys = (uint32_t*)ctx->scratch_get(SLOT_TMP_KEYS, sizeof(uint32_t) * (size_t)nh_cap);
 	uint32_t* sidx = (uint32_t*)ctx->scratch_get(SLOT_TMP_VALS, sizeof(uint32_t) * (size_t)nh_cap);
 	const uint32_t layers = ctx->mg_enabled ? 2u : 1u; // ghosts: second key space / cell table
+	const uint32_t emit_mode = ctx->mg_enabled && ctx->mg_ghost_all_pairs ? 3u : layers;
 	APBF_REQUIRE(ctx, layers == 1u || max_hash <= (1u << 30));
 	uint32_t* cs = (uint32_t*)ctx->scratch_get(SLOT_CELL_START, sizeof(uint32_t) * (size_t)max_hash * layers);
 	uint32_t* ce = (uint32_t*)ctx->scratch_get(SLOT_CELL_END, sizeof(uint32_t) * (size_t)max_hash * layers);
@@ -559,10 +561,10 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 		APBF_LAUNCHED(ctx);
 		if (g.dims == 3)
 			k_green_emit_cells<false, 3><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, counts,
-			                                                               nullptr, nullptr, nullptr, 0u, misc, cull, max_hash, layers);
+			                                                               nullptr, nullptr, nullptr, 0u, misc, cull, max_hash, emit_mode);
 		else
 			k_green_emit_cells<false, 2><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, counts,
-			                                                               nullptr, nullptr, nullptr, 0u, misc, cull, max_hash, layers);
+			                                                               nullptr, nullptr, nullptr, 0u, misc, cull, max_hash, emit_mode);
 		APBF_LAUNCHED(ctx);
 	}
 	{
@@ -573,10 +575,10 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
 		if (g.dims == 3)
 			k_green_emit_cells<true, 3><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, nullptr,
-			                                                              offsets, nb->pairs, nbl, nb->capacity, misc, cull, max_hash, layers);
+			                                                              offsets, nb->pairs, nbl, nb->capacity, misc, cull, max_hash, emit_mode);
 		else
 			k_green_emit_cells<true, 2><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, nullptr,
-			                                                              offsets, nb->pairs, nbl, nb->capacity, misc, cull, max_hash, layers);
+			                                                              offsets, nb->pairs, nbl, nb->capacity, misc, cull, max_hash, emit_mode);
 		APBF_LAUNCHED(ctx);
 	}
 	ctx->nbr_struct_pairs = nb->pairs;

@@ -83,6 +83,7 @@ template <bool COMPACT>
 __global__ void __launch_bounds__(SWEEP_THREADS) k_kw_sweep(kw_args A)
 {
 	const uint32_t n = *A.len;
+	const uint32_t n_owned = A.misc[MW_N_OWNED]; // multi-GPU: a ghost keeps only the pairs that end up unmirrored (its scatter part)
 	const bool ident = A.misc[MW_IDENTITY] != 0u;
 	const unsigned sub = threadIdx.x & (GROUP - 1);
 	const unsigned group_shift = (threadIdx.x & 31u) & ~(GROUP - 1u);
@@ -111,9 +112,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_kw_sweep(kw_args A)
 				if (!COMPACT) {
 					if (mirrored) mx = max(mx, kw_influence(kw_original(A, b, idxN), dist)); // the pair (b, a) spreads b's width onto a
 					else atomicMax(A.kwfx + b, kw_influence(orig_a, dist));                   // (a, b) has no mirror: spread directly (:53)
-				} else if (keep) {
-					new_mirrored = mirrored && dist <= glsl_max(kw_original(A, b, idxN), A.kernel_width[b]);
 				}
+				if (keep) new_mirrored = mirrored && dist <= glsl_max(kw_original(A, b, idxN), A.kernel_width[b]);
+				if (a >= n_owned) keep = keep && !new_mirrored;
 			}
 			if (!COMPACT) {
 				kept += keep ? 1u : 0u;

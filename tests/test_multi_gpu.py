@@ -1,0 +1,83 @@
+"""N-rank CUDA run (one process per GPU, NCCL) against the 1-rank CUDA run: the slab protocol must not change a bit.
+Needs >= 2 GPUs (skipped otherwise); the host logic itself is covered on CPU by tests/test_multi_rank_gloo.py."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _scene(adaptive, side):
+    from apbf_b200 import scenes
+    sc = scenes.waterdrop(side, jitter=0.1, wall_gap=6.0) if adaptive else scenes.uniform_block(side, jitter=0.2, shuffle=True, wall_gap=0.0)
+    sc.arrays["position"][:, 3] = np.arange(sc.n, dtype=np.int32)
+    sc.arrays["pos_backup"][:, :3] -= np.array([6000000, 7200000, 9000000], np.int32)  # velocity_handling starts with mLastDeltaTime = 1 (velocity_handling.h:18)
+    return sc
+
+
+def _worker(rank, world, port, adaptive, side, steps, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import apbf_b200
+    from apbf_b200 import multi_gpu
+    sc = _scene(adaptive, side)
+    owner = multi_gpu.owner_rank_of_positions(sc.arrays["position"], sc.min_pos, sc.max_pos, sc.res_log2, sc.dims, world)
+    mine = {k: np.ascontiguousarray(v[owner == rank]) for k, v in sc.arrays.items()}
+    n_own = len(mine["position"])
+    mine["index_list"] = np.arange(n_own, dtype=np.uint32)
+    ctx = apbf_b200.Context(device=rank, dims=sc.dims)
+    ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if adaptive else 1, mSmallestTargetRadius=sc.smallest_target_radius)
+    cap = sc.n                      # room for every particle plus ghosts on one rank
+    sim = apbf_b200.Sim(ctx, sc, capacity=cap, neighbor_capacity=cap * (700 if adaptive else 80), integrate=True, basic_pbf=not adaptive)
+    sim.upload(mine, n=n_own)
+    halo_range = float(sc.arrays["kernel_width"].max()) * (1.5 if adaptive else 1.0) * 1.05
+    backend = multi_gpu.CudaRankBackend(sim, n_own, world, rank, halo_range, ghost_capacity=cap)
+    dom = multi_gpu.SlabDomain(backend, multi_gpu.TorchComm(torch.device("cuda", rank)), adaptive=adaptive, solver_iterations=4, integrate=True)
+    migrated = 0
+    for _ in range(steps):
+        dom.substep()
+        migrated += dom.stats["migrated"]
+    out = apbf_b200.empty_host_arrays(cap)
+    n = sim.download(out)
+    assert n == dom.n_own, (n, dom.n_own)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), migrated=migrated, ghosts=dom.stats["ghosts"], flags=ctx.device_flags(),
+             **{k: v[:n] for k, v in out.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("adaptive,side", [(False, 24), (True, 20)])
+def test_n_rank_equals_one_rank(tmp_path, adaptive, side):
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+    import apbf_b200
+    world = 4 if torch.cuda.device_count() >= 4 else 2
+    steps = 3
+    port = 29500 + (os.getpid() % 1000) + int(adaptive)
+    mp.spawn(_worker, args=(world, port, adaptive, side, steps, str(tmp_path)), nprocs=world, join=True)
+    sc = _scene(adaptive, side)
+    ctx = apbf_b200.Context(dims=sc.dims)
+    ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if adaptive else 1, mSmallestTargetRadius=sc.smallest_target_radius)
+    sim = apbf_b200.Sim(ctx, sc, neighbor_capacity=sc.n * (700 if adaptive else 80), integrate=True, basic_pbf=not adaptive)
+    sim.upload(sc.arrays)
+    sim.substep(steps)
+    exp = apbf_b200.empty_host_arrays(sc.n)
+    assert sim.download(exp) == sc.n
+    parts = [np.load(os.path.join(str(tmp_path), f"rank{r}.npz")) for r in range(world)]
+    assert all(int(p["flags"]) == 0 for p in parts)
+    pos = np.concatenate([p["position"] for p in parts])
+    assert len(pos) == sc.n and len(set(pos[:, 3].tolist())) == sc.n
+    assert sum(int(p["migrated"]) for p in parts) > 0 and all(int(p["ghosts"]) > 0 for p in parts)
+    got, ref = np.argsort(pos[:, 3]), np.argsort(exp["position"][:, 3])
+    for k in ("position", "velocity", "kernel_width", "boundariness"):
+        a = np.concatenate([p[k] for p in parts])[got]
+        assert np.array_equal(a, exp[k][ref]), k      # same kernels, integer accumulators: bit for bit, walls included (global ids)
