@@ -238,6 +238,23 @@ class neighborhood_green(_Operator):
             return out
 
 
+class neighborhood_green_spread(neighborhood_green):
+    """neighborhood_green::apply() + spread_kernel_width::apply() in one pass (source/pool.cpp:83-89); not a class of the
+    reference: what the whole-scene substep runs for adaptive kernel widths (apbf_neighborhood_green_spread_apply)."""
+
+    def apply(self, debug=False):
+        torch = _torch()
+        L = self.lists
+        fl, nb = L.fluid(), L.neighbors()
+        kwfx = torch.zeros(L.capacity, dtype=torch.int32, device=L.words.device) if debug else None
+        _check(self.ctx, self.lib.apbf_neighborhood_green_spread_apply(
+            self.ctx.handle, C.byref(fl), C.byref(nb), self.scale, _f3(self.min_pos), _f3(self.max_pos), self.res, None,
+            kwfx.data_ptr() if debug else None))
+        L.swap()
+        if debug:
+            return kwfx[:L.length()].cpu().numpy().view(np.uint32)
+
+
 class neighborhood_binary_search(_Operator):
     """pbd::neighborhood_binary_search (source/neighborhood_binary_search.h:8-21)"""
 

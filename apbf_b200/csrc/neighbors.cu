@@ -121,9 +121,20 @@ __device__ __forceinline__ float sqrt_threshold(float r)
 }
 
 // per id: packed float position + threshold, and the cell key of the particle behind the id
+// fused spread_kernel_width only (i4 != nullptr): integer position + original kernel width (kernel_width_init.comp:28-34)
+// and the prune cutoff max(original, old kernel width) (kernel_width.comp:57)
+struct build_kw_args {
+	const float* radius;        // hidden
+	const float* target_radius; // per id
+	const float* kernel_width;  // per id, before the update
+	int          base_on_target_radius;
+	int4*        i4;
+	float*       cutoff; // threshold on the squared integer distance equivalent to dist <= max(original, old kernel width)
+};
+
 __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const uint32_t* __restrict__ hidden_key,
                            const float* __restrict__ range, float range_scale, const uint32_t* __restrict__ len,
-                           float4* __restrict__ q4, uint32_t* __restrict__ key_id, uint32_t* __restrict__ misc)
+                           float4* __restrict__ q4, uint32_t* __restrict__ key_id, uint32_t* __restrict__ misc, const build_kw_args K)
 {
 	const bool ident = misc[MW_IDENTITY] != 0u;
 	const uint32_t n = *len;
@@ -132,6 +143,14 @@ __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_
 		const int4 ip = ldg_int4(pos4, idx);
 		q4[id] = make_float4((float)ip.x * INV_R_POS, (float)ip.y * INV_R_POS, (float)ip.z * INV_R_POS,
 		                     sqrt_threshold(range[id] * range_scale));
+		if (K.i4) {
+			const float orig = glsl_max(K.radius[idx], K.base_on_target_radius ? K.target_radius[id] : 0.0f) * APBF_KERNEL_SCALE;
+			K.i4[id] = make_int4(ip.x, ip.y, ip.z, __float_as_int(orig));
+			// dist <= cutoff (kernel_width.comp:57) with dist = sqrt(d2) is d2 <= sqrt_threshold(cutoff); d2 = D2 * 2^-36 exactly,
+			// D2 the same sum over the unscaled integer differences (powers of two commute with the roundings)
+			const float cut = glsl_max(orig, K.kernel_width[id]);
+			K.cutoff[id] = cut == cut ? sqrt_threshold(cut) * 68719476736.0f : -1.0f; // dist <= NaN keeps nothing
+		}
 		const uint32_t key = hidden_key[idx];
 		key_id[id] = key;
 		// occupied cells = ids whose key differs from their predecessor's (the emit sizes its query blocks with it)
@@ -143,49 +162,90 @@ __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_
 
 // The pair emit works on groups of neighbouring cells.  The lists were just sorted by cell key, so the particles of a
 // cell -- and of an aligned 2x2x2 / 4x4x4 block of cells, which is a contiguous key range of the Z-curve -- are
-// consecutive ids with nearly the same search box [gridMin, gridMax].  A warp owns 32 consecutive ids (a tile) and
-// splits them into runs of equal block key; the run's particles are the QUERIES (staged in shared memory).  The warp
-// walks the union of their boxes in the reference's order (x fastest), skips the cells that are farther away than
-// the largest range, flattens the occupants of 32 cells at a time into a dense CANDIDATE stream -- one candidate per
-// lane, one 16-byte load each -- and tests every query against the 32 candidates with one ballot.  Hits of one query
-// are appended with the ballot rank, so a query's pairs are written as contiguous runs and keep the reference's
-// discovery order (a candidate outside a query's own box cannot pass the distance test: the cell map is monotone in
-// the position).  Work is proportional to the number of candidates, whatever the cell shape, occupancy or the
-// Z-curve's jumps.  The block size adapts to the occupancy (k_build_q4 counts the occupied cells): sparse grids
-// (a few particles per cell) group 8 or 64 cells so that a run still has a few dozen queries to amortise the walk.
+// consecutive ids with nearly the same search box [gridMin, gridMax].  A warp owns 32 consecutive ids (a tile, handed
+// out by a ticket) and splits them into runs of equal block key; the run's particles are the QUERIES (staged in shared
+// memory).  The warp walks the union of their boxes in the reference's order (x fastest), skips the cells that are
+// farther away than the largest range and flattens the occupants of 32 cells at a time into a dense CANDIDATE stream.
+// Every batch of 32 candidates is handled in two phases:
+//   phase 1, lane = candidate: one 16-byte load per lane, then every query is tested against the 32 candidates
+//            (8 unfused flops + compare) and the ballot of the result goes to shared memory -- no branch, no counting;
+//   phase 2, lane = query: each query takes its ballot, drops the invalid lanes and itself, and either counts the bits
+//            or walks them in ascending order and appends the pairs behind its own offset.
+// Ascending bit order inside a batch and batches in walk order keep the reference's discovery order (a candidate outside
+// a query's own box cannot pass the distance test: the cell map is monotone in the position).  Work is proportional to
+// the number of candidates, whatever the cell shape, occupancy or the Z-curve's jumps.  The block size adapts to the
+// occupancy (k_build_q4 counts the occupied cells): sparse grids group 8 or 64 cells so that a run still has a few
+// dozen queries to amortise the walk.
 // FILL == false counts the accepted candidates per id, FILL == true writes them at the scanned offsets: the public
 // (id, idN) pair list and the solver's internal list NB[e] = idN | (unmirrored << 31), where "mirrored" means that
 // (idN, id) is in the list as well (d <= range[idN]).
+// VARIANT: EMIT_PLAIN; EMIT_MG (multi-GPU slabs, ghost particles behind n_owned); EMIT_FUSED = neighborhood_green followed
+// by spread_kernel_width in one go (pool.cpp:83-89): the width spread (kernel_width.comp:49-53) is GATHERED by the target
+// -- a query a collects max(orig_b * influence) over every candidate b whose own range reaches a, which are exactly the
+// pairs (b, a) of the unpruned list -- so there is no atomicMax, and only the pairs that survive the prune
+// (kernel_width.comp:57) are ever counted and written.
 constexpr int EMIT_WARPS = 8;
+constexpr int EMIT_PLAIN = 0, EMIT_MG = 1, EMIT_FUSED = 2;
 
-template <bool FILL, int DIMS>
+struct emit_args {
+	const float4*   q4;
+	const uint32_t* key_id;
+	const float*    range;
+	const uint32_t* cell_start;
+	const uint32_t* cell_end;
+	const uint32_t* len;
+	apbf_grid_params g;
+	float           range_scale;
+	uint32_t*       counts;
+	const uint32_t* offsets;
+	uint32_t*       pairs;
+	uint32_t*       nbl;
+	uint32_t        cap;
+	uint32_t*       misc;
+	uint32_t*       ticket;
+	int             cull;
+	uint32_t        table_cells;
+	uint32_t        layers;
+	// EMIT_FUSED
+	const int4*     i4;      // {ipos.xyz, bits(original kernel width)} per id
+	const float*    cutoff;  // prune threshold (kernel_width.comp:57) on the squared distance in integer units, per id
+	uint32_t*       kwfx;
+};
+
+template <bool FILL, int VARIANT, int DIMS>
 __global__ void __launch_bounds__(EMIT_WARPS * 32)
-k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ key_id, const float* __restrict__ range,
-                   const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, const uint32_t* __restrict__ len,
-                   apbf_grid_params g, float range_scale, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
-                   uint32_t* __restrict__ pairs, uint32_t* __restrict__ nbl, uint32_t cap, uint32_t* misc, int cull, uint32_t table_cells,
-                   uint32_t layers)
+k_green_emit(const emit_args A)
 {
-	// Multi-GPU slabs (layers == 2): ids >= n_owned are ghosts.  Their keys carry one extra bit, so they form a second cell
+	constexpr bool FUSED = VARIANT == EMIT_FUSED, MG = VARIANT == EMIT_MG;
+	constexpr bool NEED_M = FILL || FUSED || MG; // the reverse test d <= range[idN]
+	// Multi-GPU slabs (layers >= 2): ids >= n_owned are ghosts.  Their keys carry one extra bit, so they form a second cell
 	// table behind the first (offset table_cells) and every cell is walked in both.  A ghost is a query too, but only for
 	// the pairs nobody else provides: unmirrored pairs onto owned particles (the scatter part of the sweeps).
 	__shared__ float4 s_q[EMIT_WARPS][32];
-	const uint32_t n = *len;
-	const uint32_t n_owned = misc[MW_N_OWNED];
-	const uint32_t key_mask = table_cells - 1u; // table_cells is a power of two
+	__shared__ uint2 s_fm[EMIT_WARPS][32]; // per query: ballots of d <= range[id] (.x) and d <= range[idN] (.y)
+	__shared__ uint32_t s_cand[EMIT_WARPS][32], s_self[EMIT_WARPS][32];
+	__shared__ int4 s_ci[FUSED ? EMIT_WARPS : 1][32];
+	__shared__ float s_ccut[FUSED ? EMIT_WARPS : 1][32];
+	const apbf_grid_params& g = A.g;
+	const uint32_t n = *A.len;
+	const uint32_t n_owned = MG ? A.misc[MW_N_OWNED] : 0xFFFFFFFFu;
+	const uint32_t layers = MG ? A.layers : 1u;
+	const uint32_t key_mask = A.table_cells - 1u; // table_cells is a power of two
 	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-	const uint32_t lt_mask = (1u << lane) - 1u;
 	const uint32_t axis_cap = 1u << g.res; // a box wider than the grid only revisits aliased cells
-	const uint32_t total_warps = gridDim.x * EMIT_WARPS;
 	// query block: 1 cell, 2^D cells or 4^D cells, from the mean occupancy of the occupied cells
-	const uint32_t occupied = max(misc[MW_OCC_CELLS], 1u);
+	const uint32_t occupied = max(A.misc[MW_OCC_CELLS], 1u);
 	const uint32_t gshift = (n > 4u * occupied) ? 0u : ((2u * n > occupied) ? (uint32_t)DIMS : 2u * (uint32_t)DIMS);
 	float csz[3];
 #pragma unroll
 	for (int d = 0; d < 3; d++) csz[d] = g.ext[d] / g.scale;
 	if (DIMS < 3) csz[2] = 0.0f; // z is not gridded in 2-D but the distance stays 3-D
-	uint32_t n_asym = 0;
-	for (uint32_t tile = blockIdx.x * EMIT_WARPS + w; (size_t)tile * 32 < n; tile += total_warps) {
+	uint32_t n_asym = 0, n_searched = 0;
+	for (;;) {
+		uint32_t tile = 0;
+		if (lane == 0) tile = atomicAdd(A.ticket, 1u);
+		tile = __shfl_sync(0xffffffffu, tile, 0);
+		if ((size_t)tile * 32 >= n) break;
 		const uint32_t tile_first = tile * 32u;
 		const uint32_t id = tile_first + lane;
 		const bool in = id < n;
@@ -193,10 +253,12 @@ k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ k
 		uint32_t gmin[3] = { 0u, 0u, 0u }, gmax[3] = { 0u, 0u, 0u }, qc[3] = { 0u, 0u, 0u };
 		uint32_t gkey = 0xFFFFFFFFu;
 		float r_lane = 0.0f;
+		int4 ip = make_int4(0, 0, 0, 0);
+		float cutoff_a = 0.0f;
 		if (in) {
-			me = q4[id];
-			gkey = key_id[id] >> gshift; // includes the ghost bit: owned and ghost particles never share a run
-			const float r = range[id] * range_scale;
+			me = A.q4[id];
+			gkey = A.key_id[id] >> gshift; // includes the ghost bit: owned and ghost particles never share a run
+			const float r = A.range[id] * A.range_scale;
 			r_lane = r == r ? fmaxf(r, 0.0f) : INFINITY; // a NaN range accepts every candidate
 			qc[0] = apbf_map_axis(me.x, g, 0); qc[1] = apbf_map_axis(me.y, g, 1); qc[2] = apbf_map_axis(me.z, g, 2);
 			gmin[0] = apbf_map_axis(me.x - r, g, 0); gmax[0] = apbf_map_axis(me.x + r, g, 0);
@@ -205,6 +267,7 @@ k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ k
 			if (DIMS < 3) { gmin[2] = 0u; gmax[2] = 0u; } // * uvec3(1, D > 1, D > 2), neighborhood_green.comp:36
 			// the reference visits gridMin once even when gridMax < gridMin (its ++cell > gridMax wrap)
 			gmax[0] = max(gmax[0], gmin[0]); gmax[1] = max(gmax[1], gmin[1]); gmax[2] = max(gmax[2], gmin[2]);
+			if (FUSED) { ip = __ldg(A.i4 + id); cutoff_a = A.cutoff[id]; }
 		}
 		__syncwarp();
 		s_q[w][lane] = me;
@@ -212,7 +275,10 @@ k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ k
 		const uint32_t gprev = __shfl_up_sync(0xffffffffu, gkey, 1);
 		uint32_t heads = __ballot_sync(0xffffffffu, in && (lane == 0u || gkey != gprev)); // runs of equal block key
 		const uint32_t n_in = min(32u, n - tile_first);
-		uint32_t my_off = (FILL && in) ? offsets[id] : 0u, my_cnt = 0u;
+		uint32_t my_off = (FILL && in) ? A.offsets[id] : 0u, my_cnt = 0u;
+		// kernel_width_init.comp:35; everything a neighbour spreads is at most ITS initial value, so a candidate is only
+		// looked at when that exceeds what the query already has
+		uint32_t my_mx = FUSED ? f2u(__int_as_float(ip.w) * APBF_KERNEL_WIDTH_RESOLUTION) : 0u;
 		while (heads) {
 			const uint32_t r0 = (uint32_t)__ffs(heads) - 1u;
 			heads &= heads - 1u;
@@ -231,16 +297,16 @@ k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ k
 			// [qlo, qhi] of the queries' cells and a cell is (distance in cells - 1) cell widths per axis; 1.01 instead of 1
 			// covers the rounding of the cell map (< 2e-4 cells).
 			const float r_cull = __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(r_lane) : 0u));
-			const float cull2 = cull ? r_cull * r_cull * 1.0001f : INFINITY;
+			const float cull2 = A.cull ? r_cull * r_cull * 1.0001f : INFINITY;
 			const uint32_t nxy = ext[0] * ext[1], ncell = nxy * ext[2];
 			const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)ext[0];
-			const bool ghost_run = tile_first + r0 >= n_owned;
+			const bool ghost_run = MG && tile_first + r0 >= n_owned;
 			const uint32_t n_layers = layers > 1u ? 2u : 1u; // layers == 3: two tables + ghosts keep their mirrored pairs too
 			for (uint32_t cbase = 0; cbase < ncell * n_layers; cbase += 32) {
 				uint32_t ci = cbase + lane;
 				uint32_t c_first = 0u, c_cnt = 0u;
 				if (ci < ncell * n_layers) {
-					const uint32_t table_off = ci >= ncell ? table_cells : 0u;
+					const uint32_t table_off = ci >= ncell ? A.table_cells : 0u;
 					if (ci >= ncell) ci -= ncell;
 					// ci = (cz * ny + cy) * nx + cx; float reciprocals + one correction step are exact for ci < 2^24
 					uint32_t cz, cy;
@@ -265,8 +331,8 @@ k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ k
 					const float gz = fmaxf((float)max(qlo[2] - iz, iz - qhi[2]) - 1.01f, 0.0f) * csz[2];
 					if (!(gx * gx + gy * gy + gz * gz > cull2)) {
 						const uint32_t h = (apbf_zhash<DIMS>(ax, ay, az, g.res) & key_mask) + table_off;
-						c_first = __ldg(cell_start + h);
-						c_cnt = __ldg(cell_end + h) - c_first;
+						c_first = __ldg(A.cell_start + h);
+						c_cnt = __ldg(A.cell_end + h) - c_first;
 					}
 				}
 				uint32_t incl = c_cnt;
@@ -288,37 +354,120 @@ k_green_emit_cells(const float4* __restrict__ q4, const uint32_t* __restrict__ k
 					}
 					const uint32_t cand = __shfl_sync(0xffffffffu, c_base, (int)(pos & 31u)) + t;
 					const bool cvalid = t < total;
+					const uint32_t valid_mask = total - t0 >= 32u ? 0xFFFFFFFFu : (1u << (total - t0)) - 1u;
 					float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-					if (cvalid) c4 = q4[cand];
-					for (uint32_t qi = r0; qi < r1; qi++) {
-						const float4 qv = s_q[w][qi];
-						const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
-						const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-						bool hit = cvalid && !(d2 > qv.w) && cand != tile_first + qi;
-						if (ghost_run) hit = hit && cand < n_owned && (layers == 3u || d2 > c4.w);
-						const uint32_t b = __ballot_sync(0xffffffffu, hit);
-						if (b == 0u) continue;
-						if (FILL) {
-							const uint32_t o = __shfl_sync(0xffffffffu, my_off, (int)qi) + __popc(b & lt_mask);
-							if (hit && o < cap) {
-								const bool mirrored = !(d2 > c4.w);
-								*(uint2*)(pairs + 2 * (size_t)o) = make_uint2(tile_first + qi, cand);
-								nbl[o] = cand | (mirrored ? 0u : NB_UNMIRRORED);
-								n_asym += mirrored ? 0u : 1u;
-							}
-							if (lane == qi) my_off += __popc(b);
-						} else if (lane == qi) {
-							my_cnt += __popc(b);
+					if (cvalid) c4 = A.q4[cand];
+					// ---- phase 1: lane = candidate ----------------------------------------------------------------------
+					s_cand[w][lane] = cand;
+					s_self[w][lane] = 0u;
+					bool spread = false; // fused count pass: can a candidate of this batch raise the width of a query of this run?
+					if (FUSED) {
+						const int4 ci4 = cvalid ? __ldg(A.i4 + cand) : make_int4(0, 0, 0, 0);
+						s_ci[w][lane] = ci4;
+						if (FILL) s_ccut[w][lane] = cvalid ? A.cutoff[cand] : 0.0f;
+						else {
+							const uint32_t c_init = cvalid ? f2u(__int_as_float(ci4.w) * APBF_KERNEL_WIDTH_RESOLUTION) : 0u;
+							spread = __reduce_max_sync(0xffffffffu, c_init) > __reduce_min_sync(0xffffffffu, valid ? my_mx : 0xFFFFFFFFu);
 						}
 					}
+					__syncwarp();
+					const uint32_t sq = cand - tile_first; // this candidate is query sq of the tile: id != idN, :83
+					if (cvalid && sq < 32u) s_self[w][sq] = 1u << lane;
+					if (NEED_M && (FILL || !FUSED || spread)) {
+#pragma unroll 4
+						for (uint32_t qi = r0; qi < r1; qi++) {
+							const float4 qv = s_q[w][qi];
+							const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
+							const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+							const uint32_t fb = __ballot_sync(0xffffffffu, !(d2 > qv.w));
+							const uint32_t mb = __ballot_sync(0xffffffffu, !(d2 > c4.w));
+							if (lane == 0u) s_fm[w][qi] = make_uint2(fb, mb);
+						}
+					} else {
+#pragma unroll 4
+						for (uint32_t qi = r0; qi < r1; qi++) {
+							const float4 qv = s_q[w][qi];
+							const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
+							const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+							const uint32_t fb = __ballot_sync(0xffffffffu, !(d2 > qv.w));
+							if (lane == 0u) s_fm[w][qi] = make_uint2(fb, 0u);
+						}
+					}
+					const uint32_t owned_mask = MG ? __ballot_sync(0xffffffffu, cand < n_owned) : 0xFFFFFFFFu;
+					__syncwarp();
+					// ---- phase 2: lane = query --------------------------------------------------------------------------
+					if (valid) {
+						const uint32_t live = valid_mask & ~s_self[w][lane];
+						const uint2 fm = s_fm[w][lane];
+						uint32_t fb = fm.x & live;
+						const uint32_t mb = fm.y & live;
+						if (MG && ghost_run) {
+							fb &= owned_mask;
+							if (layers != 3u) fb &= ~mb;
+						}
+						if (!FUSED) {
+							if (!FILL) {
+								my_cnt += __popc(fb);
+							} else {
+								while (fb) {
+									const uint32_t j = (uint32_t)__ffs(fb) - 1u;
+									fb &= fb - 1u;
+									if (my_off < A.cap) {
+										const uint32_t c = s_cand[w][j];
+										const bool mirrored = (mb >> j) & 1u;
+										*(uint2*)(A.pairs + 2 * (size_t)my_off) = make_uint2(id, c);
+										A.nbl[my_off] = c | (mirrored ? 0u : NB_UNMIRRORED);
+										n_asym += mirrored ? 0u : 1u;
+									}
+									my_off++;
+								}
+							}
+						} else {
+							if (!FILL) n_searched += __popc(fb);
+							uint32_t bits = FILL ? fb : (fb | mb);
+							while (bits) {
+								const uint32_t j = (uint32_t)__ffs(bits) - 1u;
+								bits &= bits - 1u;
+								const int4 cq = s_ci[w][j];
+								// kernel_width.comp:36-38: integer subtract first, then to float; D2 = dist^2 * 2^36
+								const float ux = (float)(cq.x - ip.x), uy = (float)(cq.y - ip.y), uz = (float)(cq.z - ip.z);
+								const float D2 = dot3(ux, uy, uz, ux, uy, uz);
+								const bool keep = ((fb >> j) & 1u) && D2 <= cutoff_a; // :57
+								if (!FILL) {
+									my_cnt += keep ? 1u : 0u;
+									// the pair (idN, id) of the unpruned list spreads idN's width onto id (:49-53)
+									if (((mb >> j) & 1u) && f2u(__int_as_float(cq.w) * APBF_KERNEL_WIDTH_RESOLUTION) > my_mx) {
+										const float rx = ux * INV_R_POS, ry = uy * INV_R_POS, rz = uz * INV_R_POS;
+										my_mx = max(my_mx, apbf_kw_influence(__int_as_float(cq.w), sqrtf(dot3(rx, ry, rz, rx, ry, rz))));
+									}
+								} else if (keep) {
+									if (my_off < A.cap) {
+										const uint32_t c = s_cand[w][j];
+										const bool mirrored = ((mb >> j) & 1u) && D2 <= s_ccut[w][j]; // (idN, id) survives the prune as well
+										*(uint2*)(A.pairs + 2 * (size_t)my_off) = make_uint2(id, c);
+										A.nbl[my_off] = c | (mirrored ? 0u : NB_UNMIRRORED);
+										n_asym += mirrored ? 0u : 1u;
+									}
+									my_off++;
+								}
+							}
+						}
+					}
+					__syncwarp();
 				}
 			}
 		}
-		if (!FILL && in) counts[id] = my_cnt;
+		if (!FILL && in) {
+			A.counts[id] = my_cnt;
+			if (FUSED) A.kwfx[id] = my_mx; // kernel_width_init.comp:35 + the atomicMax of kernel_width.comp:53, gathered
+		}
 	}
 	if (FILL) {
 		n_asym = __reduce_add_sync(0xffffffffu, n_asym);
-		if (lane == 0 && n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
+		if (lane == 0 && n_asym) atomicAdd(A.misc + MW_N_ASYM, n_asym);
+	} else if (FUSED) {
+		n_searched = __reduce_add_sync(0xffffffffu, n_searched);
+		if (lane == 0 && n_searched) atomicAdd(A.misc + MW_TOTAL_PAIRS, n_searched);
 	}
 }
 
@@ -436,6 +585,7 @@ k_bsearch_emit(const uint32_t* __restrict__ index_list, const int32_t* __restric
 __global__ void k_clear_search_words(uint32_t* misc)
 {
 	misc[MW_N_ASYM] = 0u; misc[MW_TOTAL_PAIRS] = 0u; misc[MW_KEPT_PAIRS] = 0xFFFFFFFFu; misc[MW_OCC_CELLS] = 0u;
+	misc[MW_EMIT_TICKET0] = 0u; misc[MW_EMIT_TICKET1] = 0u;
 }
 
 // shared front half of both searches: gather hidden arrays by sorted_index, rebuild the index list, gather per-id arrays
@@ -495,13 +645,26 @@ int reorder_lists(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, con
 	return APBF_OK;
 }
 
-} // namespace
+template <bool FILL, int VARIANT>
+void launch_emit(int dims, unsigned grid, cudaStream_t st, const emit_args& A)
+{
+	if (dims == 3) k_green_emit<FILL, VARIANT, 3><<<grid, EMIT_WARPS * 32, 0, st>>>(A);
+	else k_green_emit<FILL, VARIANT, 2><<<grid, EMIT_WARPS * 32, 0, st>>>(A);
+}
 
-extern "C" {
+template <bool FILL>
+void launch_emit(int variant, int dims, unsigned grid, cudaStream_t st, const emit_args& A)
+{
+	if (variant == EMIT_FUSED) launch_emit<FILL, EMIT_FUSED>(dims, grid, st, A);
+	else if (variant == EMIT_MG) launch_emit<FILL, EMIT_MG>(dims, grid, st, A);
+	else launch_emit<FILL, EMIT_PLAIN>(dims, grid, st, A);
+}
 
-int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb,
-                                  float range_scale, const float min_pos[3], const float max_pos[3], uint32_t res_log2,
-                                  const apbf_search_debug* dbg)
+// neighborhood_green::apply (neighborhood_green.cpp:27-77); fuse_kw: followed by spread_kernel_width::apply
+// (spread_kernel_width.cpp:12-26) on the same lists, with range == fluid->kernel_width as in pool.cpp:83-89
+int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb, float range_scale,
+                 const float min_pos[3], const float max_pos[3], uint32_t res_log2, const apbf_search_debug* dbg, bool fuse_kw,
+                 uint32_t* out_kw_fixed)
 {
 	if (!ctx) return APBF_ERR_INVALID;
 	APBF_REQUIRE(ctx, fluid && range && nb && min_pos && max_pos);
@@ -510,6 +673,7 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 	cudaStream_t st = ctx->stream;
 	const uint32_t nh_cap = p.hidden_capacity, n_cap = p.capacity;
 	if (nh_cap == 0 || n_cap == 0) { APBF_CUDA(ctx, cudaMemsetAsync(nb->length, 0, 4, st)); return APBF_OK; }
+	if (fuse_kw) APBF_REQUIRE(ctx, p.radius.data && fluid->target_radius.data && fluid->kernel_width.data);
 	apbf_grid_params g;
 	APBF_TRY(apbf_make_grid_params(ctx, min_pos, max_pos, res_log2, &g));
 	const uint32_t max_hash = 1u << (res_log2 * (uint32_t)ctx->dims); // neighborhood_green.cpp:31
@@ -530,6 +694,15 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 	uint32_t* key_id = (uint32_t*)ctx->scratch_get(SLOT_KEY_ID, sizeof(uint32_t) * (size_t)n_cap);
 	if (!keys || !skeys || !sidx || !cs || !ce || !counts || !offsets || !nbl || !misc || !q4 || !key_id)
 		return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+	build_kw_args K;
+	memset(&K, 0, sizeof K);
+	uint32_t* kwfx = nullptr;
+	if (fuse_kw) {
+		K.i4 = (int4*)ctx->scratch_get(SLOT_I4, sizeof(int4) * (size_t)n_cap);
+		K.cutoff = (float*)ctx->scratch_get(SLOT_CUTOFF, sizeof(float) * (size_t)n_cap);
+		kwfx = (uint32_t*)ctx->scratch_get(SLOT_KWFX, sizeof(uint32_t) * (size_t)n_cap);
+		if (!K.i4 || !K.cutoff || !kwfx) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+	}
 
 	// hash all hidden particles (neighborhood_green.cpp:50-52), sort by hash with the slot as payload (:53)
 	{
@@ -545,6 +718,12 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 	const uint32_t* new_index = (const uint32_t*)p.index_list.reorder_out;
 	const int32_t* new_pos = (const int32_t*)p.position.reorder_out;
 	const float* new_range = (const float*)range->reorder_out;
+	if (fuse_kw) {
+		K.radius = (const float*)p.radius.reorder_out;
+		K.target_radius = (const float*)fluid->target_radius.reorder_out;
+		K.kernel_width = (const float*)fluid->kernel_width.reorder_out;
+		K.base_on_target_radius = ctx->settings.mBaseKernelWidthOnTargetRadius;
+	}
 	// cell ranges (:58-63)
 	{
 		apbf_prof_scope ps(ctx, PROF_CELL_RANGES);
@@ -555,30 +734,30 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 	APBF_LAUNCHED(ctx);
 	const unsigned egrid = apbf_grid(ctx, n_cap, EMIT_WARPS * 32, 6);
 	static const int cull = getenv("APBF_NO_CULL") ? 0 : 1; // debugging aid: walk every cell of the union box
+	const int variant = fuse_kw ? EMIT_FUSED : (ctx->mg_enabled ? EMIT_MG : EMIT_PLAIN);
+	emit_args A;
+	memset(&A, 0, sizeof A);
+	A.q4 = q4; A.key_id = key_id; A.range = new_range; A.cell_start = cs; A.cell_end = ce; A.len = p.length; A.g = g;
+	A.range_scale = range_scale; A.counts = counts; A.offsets = offsets; A.pairs = nb->pairs; A.nbl = nbl; A.cap = nb->capacity;
+	A.misc = misc; A.cull = cull; A.table_cells = max_hash; A.layers = emit_mode; A.i4 = K.i4; A.cutoff = K.cutoff; A.kwfx = kwfx;
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_COUNT);
-		k_build_q4<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>(new_index, new_pos, skeys, new_range, range_scale, p.length, q4, key_id, misc);
+		k_build_q4<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>(new_index, new_pos, skeys, new_range, range_scale, p.length, q4, key_id, misc, K);
 		APBF_LAUNCHED(ctx);
-		if (g.dims == 3)
-			k_green_emit_cells<false, 3><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, counts,
-			                                                               nullptr, nullptr, nullptr, 0u, misc, cull, max_hash, emit_mode);
-		else
-			k_green_emit_cells<false, 2><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, counts,
-			                                                               nullptr, nullptr, nullptr, 0u, misc, cull, max_hash, emit_mode);
+		A.ticket = misc + MW_EMIT_TICKET0;
+		launch_emit<false>(variant, g.dims, egrid, st, A);
 		APBF_LAUNCHED(ctx);
 	}
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_SCAN);
-		APBF_TRY(apbf_scan_u32(ctx, counts, offsets, p.length, n_cap, false, nb->length, nb->capacity, misc + MW_FLAGS, misc + MW_TOTAL_PAIRS));
+		// fused: the counts are those of the pruned list; the size of the unpruned one is summed up by the count pass
+		APBF_TRY(apbf_scan_u32(ctx, counts, offsets, p.length, n_cap, false, nb->length, nb->capacity, misc + MW_FLAGS,
+		                       misc + (fuse_kw ? MW_KEPT_PAIRS : MW_TOTAL_PAIRS)));
 	}
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
-		if (g.dims == 3)
-			k_green_emit_cells<true, 3><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, nullptr,
-			                                                              offsets, nb->pairs, nbl, nb->capacity, misc, cull, max_hash, emit_mode);
-		else
-			k_green_emit_cells<true, 2><<<egrid, EMIT_WARPS * 32, 0, st>>>(q4, key_id, new_range, cs, ce, p.length, g, range_scale, nullptr,
-			                                                              offsets, nb->pairs, nbl, nb->capacity, misc, cull, max_hash, emit_mode);
+		A.ticket = misc + MW_EMIT_TICKET1;
+		launch_emit<true>(variant, g.dims, egrid, st, A);
 		APBF_LAUNCHED(ctx);
 	}
 	ctx->nbr_struct_pairs = nb->pairs;
@@ -591,7 +770,36 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 		if (dbg->cell_end) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->cell_end, ce, sizeof(uint32_t) * (size_t)max_hash, cudaMemcpyDeviceToDevice, st));
 		if (dbg->pair_offsets) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->pair_offsets, offsets, sizeof(uint32_t) * (size_t)(n_cap + 1), cudaMemcpyDeviceToDevice, st));
 	}
+	if (fuse_kw) {
+		// The reordered lists are still in reorder_out (the caller swaps after the search): the width update works on them.
+		apbf_fluid sorted = *fluid;
+		sorted.kernel_width.data = fluid->kernel_width.reorder_out;
+		apbf_prof_scope ps(ctx, PROF_KW_MISC);
+		APBF_TRY(apbf_kw_finish(ctx, &sorted, out_kw_fixed));
+	}
 	return APBF_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb,
+                                  float range_scale, const float min_pos[3], const float max_pos[3], uint32_t res_log2,
+                                  const apbf_search_debug* dbg)
+{
+	return green_search(ctx, fluid, range, nb, range_scale, min_pos, max_pos, res_log2, dbg, false, nullptr);
+}
+
+int apbf_neighborhood_green_spread_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighbors* nb, float range_scale,
+                                         const float min_pos[3], const float max_pos[3], uint32_t res_log2,
+                                         const apbf_search_debug* dbg, uint32_t* out_kw_fixed)
+{
+	if (!ctx) return APBF_ERR_INVALID;
+	APBF_REQUIRE(ctx, fluid);
+	if (ctx->mg_enabled) // slabs: ghosts take part in the prune; the two operators run one after the other
+		return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, "fused search + spread is single-GPU only", __FILE__, __LINE__);
+	return green_search(ctx, fluid, &fluid->kernel_width, nb, range_scale, min_pos, max_pos, res_log2, dbg, true, out_kw_fixed);
 }
 
 int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb,

@@ -17,3 +17,16 @@ static inline bool apbf_nbr_struct_valid(const apbf_ctx* ctx, const apbf_neighbo
 {
 	return nb && nb->pairs && ctx->nbr_struct_pairs == nb->pairs;
 }
+
+#ifdef __CUDACC__
+// kernel_width.comp:49-52: what a particle with original kernel width `orig` spreads onto a neighbour at distance `dist`
+__device__ __forceinline__ uint32_t apbf_kw_influence(float orig, float dist)
+{
+	const float distanceFromKernel = dist - orig;
+	const float influence = glsl_max(0.0f, 1.0f - glsl_max(0.0f, distanceFromKernel / (orig * APBF_KERNEL_WIDTH_PROPAGATION_FACTOR)));
+	return f2u(orig * influence * APBF_KERNEL_WIDTH_RESOLUTION);
+}
+#endif
+
+// uint_to_float_but_gradual over the fixed-point widths in SLOT_KWFX (solver.cu; tail of spread_kernel_width::apply)
+int apbf_kw_finish(apbf_ctx* ctx, apbf_fluid* fluid, uint32_t* out_kw_fixed);

@@ -5,6 +5,7 @@
 #include "solver.cuh"
 
 #include "sim.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -48,6 +49,7 @@ int apbf_sim_create(apbf_ctx* ctx, const apbf_sim_config* cfg, apbf_sim** out_si
 	sim->ctx = ctx;
 	sim->cfg = *cfg;
 	sim->last_dt = 1.0f;
+	sim->no_fuse = getenv("APBF_NO_FUSE") != nullptr; // debugging aid: search and spread_kernel_width as two operators
 	sim->boxes = nullptr;
 	memset(&sim->fluid, 0, sizeof sim->fluid);
 	memset(&sim->nb, 0, sizeof sim->nb);
@@ -168,12 +170,16 @@ int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
 			sim->last_dt = c.dt;
 		}
 		const float scale = unit_scale ? 1.0f : 1.5f;
+		// pool.cpp:83-89.  Green search followed by spread_kernel_width runs as one fused pass (same lists, pair for pair)
+		const bool fused = adaptive && !c.use_binary_search && !ctx->mg_enabled && !sim->no_fuse;
 		if (c.use_binary_search)                                                      // pool.cpp:83-84
 			APBF_TRY(apbf_neighborhood_binary_search_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, nullptr));
+		else if (fused)
+			APBF_TRY(apbf_neighborhood_green_spread_apply(ctx, &sim->fluid, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, nullptr, nullptr));
 		else
 			APBF_TRY(apbf_neighborhood_green_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, nullptr));
 		apbf_sim_swap_buffers(sim);
-		if (adaptive) APBF_TRY(apbf_spread_kernel_width_apply(ctx, &sim->fluid, &sim->nb, nullptr)); // pool.cpp:87-89
+		if (adaptive && !fused) APBF_TRY(apbf_spread_kernel_width_apply(ctx, &sim->fluid, &sim->nb, nullptr)); // pool.cpp:87-89
 		// pool.cpp:92-95: solverIterations x (box_collision, incompressibility).  Same results as calling the two
 		// operators in turn; the per-particle constants are computed once (kernel widths are fixed from here on) and
 		// box collision + the previous iteration's position update ride in the next iteration's prologue.

@@ -17,6 +17,7 @@ struct apbf_sim {
 	apbf_neighbors  nb;
 	float*          boxes;    // [2 * n_boxes * 4]
 	float           last_dt;  // velocity_handling::mLastDeltaTime (velocity_handling.h:18)
+	bool            no_fuse;
 	std::vector<void*> owned;
 	apbf_mg_state   mg;
 };

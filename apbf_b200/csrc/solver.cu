@@ -70,12 +70,7 @@ __global__ void k_kw_init(kw_args A)
 	}
 }
 
-__device__ __forceinline__ uint32_t kw_influence(float orig, float dist) // kernel_width.comp:49-52
-{
-	const float distanceFromKernel = dist - orig;
-	const float influence = glsl_max(0.0f, 1.0f - glsl_max(0.0f, distanceFromKernel / (orig * APBF_KERNEL_WIDTH_PROPAGATION_FACTOR)));
-	return f2u(orig * influence * R_KW);
-}
+__device__ __forceinline__ uint32_t kw_influence(float orig, float dist) { return apbf_kw_influence(orig, dist); }
 
 // COMPACT == false: atomicMax spread (gathered through mirrored pairs) + number of pairs to keep per particle
 // COMPACT == true : write the kept pairs at the scanned offsets with their new mirrored bits
@@ -203,6 +198,22 @@ __global__ void k_velocity_handling(const uint32_t* __restrict__ index_list, int
 }
 
 } // namespace
+
+int apbf_kw_finish(apbf_ctx* ctx, apbf_fluid* fluid, uint32_t* out_kw_fixed)
+{
+	const uint32_t n_cap = fluid->particle.capacity;
+	kw_args A;
+	memset(&A, 0, sizeof A);
+	A.len = fluid->particle.length;
+	A.kernel_width = (float*)fluid->kernel_width.data;
+	A.kwfx = (uint32_t*)ctx->scratch_get(SLOT_KWFX, sizeof(uint32_t) * (size_t)n_cap);
+	A.speed = ctx->settings.mKernelWidthAdaptionSpeed;
+	if (!A.kwfx) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+	if (out_kw_fixed) APBF_CUDA(ctx, cudaMemcpyAsync(out_kw_fixed, A.kwfx, sizeof(uint32_t) * (size_t)n_cap, cudaMemcpyDeviceToDevice, ctx->stream));
+	k_kw_finish<<<apbf_grid(ctx, n_cap, 256), 256, 0, ctx->stream>>>(A);
+	APBF_LAUNCHED(ctx);
+	return APBF_OK;
+}
 
 extern "C" {
 

@@ -221,6 +221,15 @@ typedef struct apbf_search_debug {
 int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* neighbors,
                                   float range_scale, const float min_pos[3], const float max_pos[3], uint32_t res_log2,
                                   const apbf_search_debug* debug);
+/* neighborhood_green::apply() immediately followed by spread_kernel_width::apply() on the same lists, i.e. source/pool.cpp:83-89
+ * (`range` = fluid->kernel_width), in one pass: the width spread (kernel_width.comp:49-53) is gathered while the
+ * candidates are tested and only the pairs that survive the prune (kernel_width.comp:57) are written.  Same kernel widths
+ * and the same neighbour list, pair for pair and in the same order, as the two calls one after the other -- except that
+ * `neighbors->capacity` only has to hold the pruned list (the reference clamps the unpruned one, neighbor_add.glsl:23-24).
+ * out_kw_fixed (optional, device, [capacity]): the fixed-point widths after the atomicMax spread.  Single GPU only. */
+int apbf_neighborhood_green_spread_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighbors* neighbors, float range_scale,
+                                         const float min_pos[3], const float max_pos[3], uint32_t res_log2,
+                                         const apbf_search_debug* debug, uint32_t* out_kw_fixed);
 /* pbd::neighborhood_binary_search::set_data(...).set_range_scale(s).apply() (source/neighborhood_binary_search.cpp:22-75) */
 int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range,
                                           apbf_neighbors* neighbors, float range_scale, const apbf_search_debug* debug);

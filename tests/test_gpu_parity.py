@@ -342,6 +342,42 @@ def test_spread_kernel_width_matches_oracle(gpu, orc):
     _check_incompressibility(ga, ea, L.read("position"), st.position, before)
 
 
+@pytest.mark.parametrize("base_on_target_radius,dims", [(0, 3), (1, 3), (0, 2)])
+def test_fused_search_spread_matches_two_operators(gpu, orc, base_on_target_radius, dims):
+    """apbf_neighborhood_green_spread_apply (what the whole-scene substep runs, pool.cpp:83-89 in one pass) against the
+    oracle's neighborhood_green + spread_kernel_width: fixed-point widths, kept pairs in order, new widths -- bit exact --
+    and the solver's mirrored bits of the pruned list (through one incompressibility pass)."""
+    if dims == 3:
+        sc = scenes.waterdrop(22, jitter=0.1)
+    else:
+        sc = scenes.uniform_block(40, jitter=0.2, dims=2, shuffle=True)
+        rng = np.random.default_rng(3)                       # variable widths in 2-D as well
+        sc.arrays["kernel_width"] = (sc.arrays["kernel_width"] * rng.choice([1.0, 1.3, 1.7], sc.n)).astype(np.float32)
+    sc.arrays["target_radius"] = (sc.arrays["target_radius"] * np.random.default_rng(5).choice([1.0, 1.5], sc.n)).astype(np.float32)
+    s = orc.default_settings()
+    s.mBaseKernelWidthOnBoundaryDistance = 0
+    s.mBaseKernelWidthOnTargetRadius = base_on_target_radius
+    cap = sc.n * 700
+    st = oracle_state(orc, sc)
+    epairs = orc.green_apply(st, s, sc.dims, 1.5, sc.min_pos, sc.max_pos, sc.res_log2, cap)
+    ekept, ekw = orc.spread_kernel_width_apply(st, s, epairs)
+    assert 0 < len(ekept) < len(epairs)
+    ctx = gpu.Context(dims=sc.dims)
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=len(ekept) + 7)   # only the pruned list has to fit
+    gkw = gpu.neighborhood_green_spread(ctx).set_data(L).set_range_scale(1.5).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply(debug=True)
+    assert ctx.device_flags() == 0
+    assert np.array_equal(gkw, ekw)
+    assert np.array_equal(L.read_pairs(), ekept)
+    assert np.array_equal(L.read("kernel_width"), st.kernel_width)
+    for k in ("position", "radius", "target_radius", "index_list"):
+        assert np.array_equal(L.read(k), getattr(st, k)), k
+    before = st.position.copy()
+    ea = orc.incompressibility_apply(st, s, sc.dims, ekept, want_aux=True)
+    ga = gpu.incompressibility(ctx).set_data(L).apply(debug=True)
+    _check_incompressibility(ga, ea, L.read("position"), st.position, before)
+
+
 def test_box_collision_matches_oracle(gpu, orc):
     sc = scenes.uniform_block(16, jitter=0.3, shuffle=True)
     st = oracle_state(orc, sc)
