@@ -130,6 +130,7 @@ struct build_kw_args {
 	int          base_on_target_radius;
 	int4*        i4;
 	float*       cutoff; // threshold on the squared integer distance equivalent to dist <= max(original, old kernel width)
+	float4*      qb4;    // {K, C * ihw, ihw, original width}: the prune decided on the float-form distance (see k_green_stream)
 };
 
 __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const uint32_t* __restrict__ hidden_key,
@@ -150,6 +151,23 @@ __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_
 			// D2 the same sum over the unscaled integer differences (powers of two commute with the roundings)
 			const float cut = glsl_max(orig, K.kernel_width[id]);
 			K.cutoff[id] = cut == cut ? sqrt_threshold(cut) * 68719476736.0f : -1.0f; // dist <= NaN keeps nothing
+			// The prune compares the distance of the INTEGER difference (kernel_width.comp:36-38), the search the distance
+			// of the float positions (neighborhood_green.comp:83).  Both approximate the same squared distance s; with
+			// |p| the largest coordinate of the particle and c the cutoff, |d2_float - d2_int| <= 2^-22 (1.73 c (|p| + c)
+			// + 2 c^2) for s near c^2 (conversion of the coordinates to float: 2^-24 |p| each; subtraction and the two
+			// dot products: a few 2^-24 s).  hw is four times that: a pair with d2_float <= C - hw is kept for sure, one
+			// with d2_float > C + hw is dropped for sure, and only the band in between needs the integer form.
+			const float T = sqrt_threshold(range[id] * range_scale);
+			float4 qb = make_float4(T, 10.0f, 0.0f, orig); // no prune, never ambiguous (cutoff >= 1e15 or +inf)
+			if (!(cut == cut) || cut < 0.0f) qb.x = -1.0f; // keeps nothing
+			else if (cut < 1.0e15f) {
+				const float pm = fmaxf(fmaxf(fabsf((float)ip.x), fabsf((float)ip.y)), fabsf((float)ip.z)) * INV_R_POS;
+				const float C = sqrt_threshold(cut);
+				const float hw = fmaxf(2.3841858e-7f * cut * (7.0f * (pm + cut) + 8.0f * cut), 1.0e-20f);
+				const float ihw = 1.0f / hw;
+				qb = make_float4(glsl_min(T, C - hw), C * ihw, ihw, orig);
+			}
+			K.qb4[id] = qb;
 		}
 		const uint32_t key = hidden_key[idx];
 		key_id[id] = key;
@@ -210,6 +228,13 @@ struct emit_args {
 	const int4*     i4;      // {ipos.xyz, bits(original kernel width)} per id
 	const float*    cutoff;  // prune threshold (kernel_width.comp:57) on the squared distance in integer units, per id
 	uint32_t*       kwfx;
+	// one-pass emit (k_green_stream + k_regroup)
+	const float4*   qb4;
+	uint32_t*       stream;
+	uint32_t        stream_blocks;
+	uint32_t*       tile_first;
+	uint32_t*       tile_total;
+	int             fallback; // two-pass fill kernel: run only if the hit stream overflowed
 };
 
 template <bool FILL, int VARIANT, int DIMS>
@@ -226,6 +251,7 @@ k_green_emit(const emit_args A)
 	__shared__ uint32_t s_cand[EMIT_WARPS][32], s_self[EMIT_WARPS][32];
 	__shared__ int4 s_ci[FUSED ? EMIT_WARPS : 1][32];
 	__shared__ float s_ccut[FUSED ? EMIT_WARPS : 1][32];
+	if (A.fallback && A.misc[MW_STREAM_OVERFLOW] == 0u) return;
 	const apbf_grid_params& g = A.g;
 	const uint32_t n = *A.len;
 	const uint32_t n_owned = MG ? A.misc[MW_N_OWNED] : 0xFFFFFFFFu;
@@ -471,6 +497,342 @@ k_green_emit(const emit_args A)
 	}
 }
 
+// ---- one-pass pair emit: hit stream + regroup ---------------------------------------------------------------------------
+// k_green_emit tests every (query, candidate) twice: once to count, once to fill.  k_green_stream tests once.  Same tiles,
+// runs, cell walk and candidate batches, but:
+//   * lane = candidate all the way: the lane keeps one bit per query of the run (colK: pair kept, colM: the mirrored pair
+//     is kept as well) -- 8 unfused flops, two compares and two predicated ORs per query, no ballots, no shared-memory
+//     traffic besides the broadcast load of the query;
+//   * the hits of a batch go, candidate after candidate, into the tile's HIT STREAM: {idN | unmirrored << 31, query lane},
+//     5 bytes per pair, in 256-entry blocks taken from a global allocator and chained per tile; a shared-memory counter
+//     per query yields counts[id];
+//   * after the scan of the counts, k_regroup (one warp per tile) walks the tile's chain once and moves every entry to
+//     offsets[id] + rank, rank = number of earlier entries of the same query (match_any within 32 entries + a running
+//     base per query): the list comes out grouped by id, and within an id in discovery order, exactly like the two-pass
+//     emit -- for 5 + 5 bytes of extra traffic per pair instead of a second round of distance tests.
+// Fused spread_kernel_width (EMIT_FUSED): the prune (kernel_width.comp:57) is decided on the float-form squared distance
+// with the conservative threshold K = min(T, C - hw) built by k_build_q4; a batch in which any pair falls into the
+// ambiguity band |d2 - C| <= hw of the query or of the candidate (about one batch in 300) is redone with the integer form.
+// The width spread (kernel_width.comp:49-53) only matters where a candidate starts wider than a query of the run
+// currently is; those batches take a second, exact loop.
+// If the stream runs out of blocks -- which needs more pairs than the pair list can hold -- MW_STREAM_OVERFLOW is set,
+// k_regroup does nothing and the fill pass of the two-pass emit writes the clamped list from the same counts.
+constexpr uint32_t SB_ENTRIES = 256u, SB_HEADER = 32u, SB_WORDS = SB_HEADER + SB_ENTRIES + SB_ENTRIES / 4u; // 1408 bytes
+constexpr uint32_t SB_NONE = 0xFFFFFFFFu;
+
+template <int VARIANT, int DIMS, bool STATS>
+__global__ void __launch_bounds__(EMIT_WARPS * 32)
+k_green_stream(const emit_args A)
+{
+	constexpr bool FUSED = VARIANT == EMIT_FUSED, MG = VARIANT == EMIT_MG;
+	__shared__ float4 s_q[EMIT_WARPS][32];                    // {x, y, z, K}: K = T (plain) or min(T, C - hw) (fused)
+	__shared__ float2 s_amb[FUSED ? EMIT_WARPS : 1][32];      // {C * ihw, ihw} of the query's ambiguity band
+	__shared__ float s_T[(FUSED || STATS) ? EMIT_WARPS : 1][32]; // threshold of the range test alone
+	__shared__ uint32_t s_cnt[EMIT_WARPS][32];
+	const apbf_grid_params& g = A.g;
+	const uint32_t n = *A.len;
+	const uint32_t n_owned = MG ? A.misc[MW_N_OWNED] : 0xFFFFFFFFu;
+	const uint32_t layers = MG ? A.layers : 1u;
+	const uint32_t key_mask = A.table_cells - 1u;
+	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+	const uint32_t axis_cap = 1u << g.res;
+	const uint32_t occupied = max(A.misc[MW_OCC_CELLS], 1u);
+	const uint32_t gshift = (n > 4u * occupied) ? 0u : ((2u * n > occupied) ? (uint32_t)DIMS : 2u * (uint32_t)DIMS);
+	float csz[3];
+#pragma unroll
+	for (int d = 0; d < 3; d++) csz[d] = g.ext[d] / g.scale;
+	if (DIMS < 3) csz[2] = 0.0f;
+	uint32_t n_searched = 0;
+	for (;;) {
+		uint32_t tile = 0;
+		if (lane == 0) tile = atomicAdd(A.ticket, 1u);
+		tile = __shfl_sync(0xffffffffu, tile, 0);
+		if ((size_t)tile * 32 >= n) break;
+		const uint32_t tile_first = tile * 32u;
+		const uint32_t id = tile_first + lane;
+		const bool in = id < n;
+		float4 me = make_float4(0.f, 0.f, 0.f, -1.0f);
+		float4 qb = make_float4(-1.0f, 10.0f, 0.0f, 0.0f);
+		uint32_t gmin[3] = { 0u, 0u, 0u }, gmax[3] = { 0u, 0u, 0u }, qc[3] = { 0u, 0u, 0u };
+		uint32_t gkey = 0xFFFFFFFFu;
+		float r_lane = 0.0f;
+		if (in) {
+			me = A.q4[id];
+			gkey = A.key_id[id] >> gshift;
+			const float r = A.range[id] * A.range_scale;
+			r_lane = r == r ? fmaxf(r, 0.0f) : INFINITY;
+			qc[0] = apbf_map_axis(me.x, g, 0); qc[1] = apbf_map_axis(me.y, g, 1); qc[2] = apbf_map_axis(me.z, g, 2);
+			gmin[0] = apbf_map_axis(me.x - r, g, 0); gmax[0] = apbf_map_axis(me.x + r, g, 0);
+			gmin[1] = apbf_map_axis(me.y - r, g, 1); gmax[1] = apbf_map_axis(me.y + r, g, 1);
+			gmin[2] = apbf_map_axis(me.z - r, g, 2); gmax[2] = apbf_map_axis(me.z + r, g, 2);
+			if (DIMS < 3) { gmin[2] = 0u; gmax[2] = 0u; }
+			gmax[0] = max(gmax[0], gmin[0]); gmax[1] = max(gmax[1], gmin[1]); gmax[2] = max(gmax[2], gmin[2]);
+			if (FUSED) qb = A.qb4[id];
+		}
+		__syncwarp();
+		s_q[w][lane] = make_float4(me.x, me.y, me.z, FUSED ? qb.x : me.w);
+		if (FUSED) s_amb[w][lane] = make_float2(qb.y, qb.z);
+		if (FUSED || STATS) s_T[w][lane] = me.w;
+		s_cnt[w][lane] = 0u;
+		__syncwarp();
+		const uint32_t gprev = __shfl_up_sync(0xffffffffu, gkey, 1);
+		uint32_t heads = __ballot_sync(0xffffffffu, in && (lane == 0u || gkey != gprev));
+		const uint32_t n_in = min(32u, n - tile_first);
+		uint32_t my_mx = FUSED ? f2u(qb.w * APBF_KERNEL_WIDTH_RESOLUTION) : 0u; // kernel_width_init.comp:35
+		uint32_t tile_pos = 0u, n_alloc = 0u, last_blk = SB_NONE; // the tile's stream: entries so far, blocks so far, newest block
+		while (heads) {
+			const uint32_t r0 = (uint32_t)__ffs(heads) - 1u;
+			heads &= heads - 1u;
+			const uint32_t r1 = heads ? (uint32_t)__ffs(heads) - 1u : n_in;
+			const bool valid = lane >= r0 && lane < r1;
+			uint32_t umin[3], ext[3];
+			int qlo[3], qhi[3];
+#pragma unroll
+			for (int d = 0; d < 3; d++) {
+				umin[d] = __reduce_min_sync(0xffffffffu, valid ? gmin[d] : 0xFFFFFFFFu);
+				ext[d] = min(__reduce_max_sync(0xffffffffu, valid ? gmax[d] : 0u) - umin[d], axis_cap - 1u) + 1u;
+				qlo[d] = (int)min(__reduce_min_sync(0xffffffffu, valid ? qc[d] : 0xFFFFFFFFu), 0x7FFFFFFFu);
+				qhi[d] = (int)min(__reduce_max_sync(0xffffffffu, valid ? qc[d] : 0u), 0x7FFFFFFFu);
+			}
+			const float r_cull = __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(r_lane) : 0u));
+			const float cull2 = A.cull ? r_cull * r_cull * 1.0001f : INFINITY;
+			const uint32_t nxy = ext[0] * ext[1], ncell = nxy * ext[2];
+			const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)ext[0];
+			const bool ghost_run = MG && tile_first + r0 >= n_owned;
+			const uint32_t n_layers = layers > 1u ? 2u : 1u;
+			for (uint32_t cbase = 0; cbase < ncell * n_layers; cbase += 32) {
+				uint32_t ci = cbase + lane;
+				uint32_t c_first = 0u, c_cnt = 0u;
+				if (ci < ncell * n_layers) {
+					const uint32_t table_off = ci >= ncell ? A.table_cells : 0u;
+					if (ci >= ncell) ci -= ncell;
+					uint32_t cz, cy;
+					if (ncell <= (1u << 24)) {
+						cz = (uint32_t)((float)ci * inv_nxy);
+						if (cz * nxy > ci) cz--; else if ((cz + 1u) * nxy <= ci) cz++;
+					} else {
+						cz = ci / nxy;
+					}
+					const uint32_t rem = ci - cz * nxy;
+					if (ncell <= (1u << 24)) {
+						cy = (uint32_t)((float)rem * inv_nx);
+						if (cy * ext[0] > rem) cy--; else if ((cy + 1u) * ext[0] <= rem) cy++;
+					} else {
+						cy = rem / ext[0];
+					}
+					const uint32_t cx = rem - cy * ext[0];
+					const uint32_t ax = umin[0] + cx, ay = umin[1] + cy, az = umin[2] + cz;
+					const int ix = (int)min(ax, 0x7FFFFFFFu), iy = (int)min(ay, 0x7FFFFFFFu), iz = (int)min(az, 0x7FFFFFFFu);
+					const float gx = fmaxf((float)max(qlo[0] - ix, ix - qhi[0]) - 1.01f, 0.0f) * csz[0];
+					const float gy = fmaxf((float)max(qlo[1] - iy, iy - qhi[1]) - 1.01f, 0.0f) * csz[1];
+					const float gz = fmaxf((float)max(qlo[2] - iz, iz - qhi[2]) - 1.01f, 0.0f) * csz[2];
+					if (!(gx * gx + gy * gy + gz * gz > cull2)) {
+						const uint32_t h = (apbf_zhash<DIMS>(ax, ay, az, g.res) & key_mask) + table_off;
+						c_first = __ldg(A.cell_start + h);
+						c_cnt = __ldg(A.cell_end + h) - c_first;
+					}
+				}
+				uint32_t incl = c_cnt;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+					if (lane >= (unsigned)o) incl += t;
+				}
+				const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+				const uint32_t c_base = c_first - (incl - c_cnt);
+				for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+					const uint32_t t = t0 + lane;
+					uint32_t pos = 0u;
+#pragma unroll
+					for (int step = 16; step > 0; step >>= 1) {
+						const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(pos + step - 1));
+						if (v <= t) pos += step;
+					}
+					const uint32_t cand = __shfl_sync(0xffffffffu, c_base, (int)(pos & 31u)) + t;
+					const bool cvalid = t < total;
+					float4 c4 = make_float4(0.f, 0.f, 0.f, -1.0f);
+					float4 cb = make_float4(-1.0f, 10.0f, 0.0f, 0.0f);
+					if (cvalid) {
+						c4 = A.q4[cand];
+						if (FUSED) cb = A.qb4[cand];
+					}
+					const float Kb = FUSED ? cb.x : c4.w;
+					bool spread = false; // can a candidate of this batch raise the width of a query of this run?
+					if (FUSED)
+						spread = __reduce_max_sync(0xffffffffu, f2u(cb.w * APBF_KERNEL_WIDTH_RESOLUTION)) >
+						         __reduce_min_sync(0xffffffffu, valid ? my_mx : 0xFFFFFFFFu);
+					// ---- the tests: one bit per query of the run ----------------------------------------------------------
+					uint32_t colK = 0u, colM = 0u, colS = 0u;
+					float ambmin = 4.0f;
+#pragma unroll 4
+					for (uint32_t qi = r0; qi < r1; qi++) {
+						const float4 qv = s_q[w][qi];
+						const uint32_t bit = 1u << qi;
+						const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
+						const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+						const bool pk = !(d2 > qv.w);
+						const bool pm = pk && !(d2 > Kb);
+						colK |= pk ? bit : 0u;
+						colM |= pm ? bit : 0u;
+						if (FUSED) {
+							const float2 ab = s_amb[w][qi];
+							ambmin = fminf(ambmin, fminf(fabsf(__fmaf_rn(d2, ab.y, -ab.x)), fabsf(__fmaf_rn(d2, cb.z, -cb.y))));
+						}
+						if (STATS && FUSED) colS |= !(d2 > s_T[w][qi]) ? bit : 0u;
+					}
+					const uint32_t sq = cand - tile_first; // this candidate is query sq of the tile: id != idN, neighborhood_green.comp:83
+					const uint32_t live = cvalid ? ~(sq < 32u ? 1u << sq : 0u) : 0u;
+					if (FUSED && __any_sync(0xffffffffu, cvalid && ambmin <= 1.0f)) {
+						// a pair of this batch sits in an ambiguity band: the whole batch again, prune on the integer form
+						const int4 ci4 = cvalid ? __ldg(A.i4 + cand) : make_int4(0, 0, 0, 0);
+						const float cutb = cvalid ? A.cutoff[cand] : -1.0f;
+						colK = 0u; colM = 0u;
+						for (uint32_t qi = r0; qi < r1; qi++) {
+							const float4 qv = s_q[w][qi];
+							const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
+							const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+							const int4 ia = __ldg(A.i4 + tile_first + qi);
+							// kernel_width.comp:36-38: integer subtract first, then to float; D2 = dist^2 * 2^36
+							const float ux = (float)(ci4.x - ia.x), uy = (float)(ci4.y - ia.y), uz = (float)(ci4.z - ia.z);
+							const float D2 = dot3(ux, uy, uz, ux, uy, uz);
+							const bool keep = !(d2 > s_T[w][qi]) && D2 <= A.cutoff[tile_first + qi]; // :57
+							const bool mir = keep && !(d2 > c4.w) && D2 <= cutb;                     // (idN, id) survives as well
+							colK |= keep ? 1u << qi : 0u;
+							colM |= mir ? 1u << qi : 0u;
+						}
+					}
+					colK &= live; colM &= live;
+					if (STATS) n_searched += __popc((FUSED ? colS : colK) & live);
+					if (FUSED && spread) {
+						// the pair (idN, id) of the unpruned list spreads idN's width onto id (kernel_width.comp:49-53), gathered
+						const int4 ci4 = cvalid ? __ldg(A.i4 + cand) : make_int4(0, 0, 0, 0);
+						for (uint32_t qi = r0; qi < r1; qi++) {
+							const float4 qv = s_q[w][qi];
+							const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
+							const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+							uint32_t val = 0u;
+							if (((live >> qi) & 1u) && !(d2 > c4.w)) {
+								const int4 ia = __ldg(A.i4 + tile_first + qi);
+								const float ux = (float)(ci4.x - ia.x), uy = (float)(ci4.y - ia.y), uz = (float)(ci4.z - ia.z);
+								const float rx = ux * INV_R_POS, ry = uy * INV_R_POS, rz = uz * INV_R_POS;
+								val = apbf_kw_influence(cb.w, sqrtf(dot3(rx, ry, rz, rx, ry, rz)));
+							}
+							val = __reduce_max_sync(0xffffffffu, val);
+							if (lane == qi) my_mx = max(my_mx, val);
+						}
+					}
+					if (MG && ghost_run) {
+						// a ghost is a query only for the pairs nobody else provides: unmirrored pairs onto owned particles
+						if (cand >= n_owned) colK = 0u;
+						if (layers != 3u) colK &= ~colM;
+					}
+					// ---- append the batch's hits to the tile's stream, candidate after candidate ------------------------------
+					const uint32_t c = (uint32_t)__popc(colK);
+					uint32_t inc = c;
+#pragma unroll
+					for (int o = 1; o < 32; o <<= 1) {
+						const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+						if (lane >= (unsigned)o) inc += v;
+					}
+					const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+					if (tot) {
+						const uint32_t n_before = n_alloc, need = ((tile_pos + tot - 1u) >> 8) + 1u;
+						uint32_t base = 0u;
+						if (need > n_before) {
+							const uint32_t grp = need - n_before;
+							if (lane == 0) base = atomicAdd(A.misc + MW_STREAM_CURSOR, grp);
+							base = __shfl_sync(0xffffffffu, base, 0);
+							if (lane == 0) {
+								if (n_before == 0u) A.tile_first[tile] = base;
+								else if (last_blk < A.stream_blocks) A.stream[(size_t)last_blk * SB_WORDS] = base;
+								if (base + grp > A.stream_blocks || base + grp < base) A.misc[MW_STREAM_OVERFLOW] = 1u;
+							}
+							for (uint32_t i = lane; i + 1u < grp; i += 32u)
+								if (base + i < A.stream_blocks) A.stream[(size_t)(base + i) * SB_WORDS] = base + i + 1u;
+						}
+						uint32_t m = colK, tp = tile_pos + (inc - c);
+						while (m) {
+							const uint32_t q = (uint32_t)__ffs(m) - 1u;
+							m &= m - 1u;
+							const uint32_t o = tp >> 8;
+							const uint32_t blk = o < n_before ? last_blk : base + (o - n_before);
+							if (blk < A.stream_blocks) {
+								uint32_t* B = A.stream + (size_t)blk * SB_WORDS + SB_HEADER;
+								B[tp & 255u] = cand | (((colM >> q) & 1u) ? 0u : NB_UNMIRRORED);
+								((uint8_t*)(B + SB_ENTRIES))[tp & 255u] = (uint8_t)q;
+							}
+							atomicAdd(&s_cnt[w][q], 1u);
+							tp++;
+						}
+						if (need > n_before) { last_blk = base + (need - n_before) - 1u; n_alloc = need; }
+						tile_pos += tot;
+					}
+					__syncwarp();
+				}
+			}
+		}
+		__syncwarp();
+		if (in) {
+			A.counts[id] = s_cnt[w][lane];
+			if (FUSED) A.kwfx[id] = my_mx; // kernel_width_init.comp:35 + the atomicMax of kernel_width.comp:53, gathered
+		}
+		if (lane == 0) {
+			A.tile_total[tile] = tile_pos;
+			if (n_alloc == 0u) A.tile_first[tile] = SB_NONE;
+		}
+	}
+	if (STATS) {
+		n_searched = __reduce_add_sync(0xffffffffu, n_searched);
+		if (lane == 0 && n_searched) atomicAdd(A.misc + MW_TOTAL_PAIRS, n_searched);
+	}
+}
+
+// second half of the one-pass emit: entries of a tile's stream -> offsets[id] + rank
+__global__ void __launch_bounds__(256)
+k_regroup(const uint32_t* __restrict__ stream, const uint32_t* __restrict__ tile_first, const uint32_t* __restrict__ tile_total,
+          const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ len, uint32_t* __restrict__ pairs,
+          uint32_t* __restrict__ nbl, uint32_t cap, uint32_t* misc)
+{
+	if (misc[MW_STREAM_OVERFLOW] != 0u) return;
+	__shared__ uint32_t s_base[8][32];
+	const uint32_t n = *len;
+	const uint32_t n_tiles = (n + 31u) >> 5;
+	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+	const uint32_t lt = (1u << lane) - 1u;
+	uint32_t n_asym = 0u;
+	for (uint32_t tile = blockIdx.x * 8u + w; tile < n_tiles; tile += gridDim.x * 8u) {
+		const uint32_t id0 = tile * 32u;
+		__syncwarp();
+		s_base[w][lane] = id0 + lane < n ? offsets[id0 + lane] : 0u;
+		__syncwarp();
+		const uint32_t total = tile_total[tile];
+		uint32_t blk = tile_first[tile];
+		for (uint32_t t0 = 0; t0 < total; t0 += 32u) {
+			if (t0 != 0u && (t0 & (SB_ENTRIES - 1u)) == 0u) blk = stream[(size_t)blk * SB_WORDS];
+			const uint32_t* B = stream + (size_t)blk * SB_WORDS + SB_HEADER;
+			const uint32_t t = t0 + lane;
+			const bool ok = t < total;
+			const uint32_t word = ok ? B[t & 255u] : 0u;
+			const uint32_t q = ok ? (uint32_t)((const uint8_t*)(B + SB_ENTRIES))[t & 255u] : 32u + lane;
+			const uint32_t peers = __match_any_sync(0xffffffffu, q);
+			const uint32_t rank = (uint32_t)__popc(peers & lt);
+			if (ok) {
+				const uint32_t o = s_base[w][q] + rank;
+				if (o < cap) {
+					*(uint2*)(pairs + 2 * (size_t)o) = make_uint2(id0 + q, word & NB_ID_MASK);
+					nbl[o] = word;
+					n_asym += word >> 31;
+				}
+			}
+			__syncwarp();
+			if (ok && rank == 0u) s_base[w][q] += (uint32_t)__popc(peers);
+			__syncwarp();
+		}
+	}
+	n_asym = __reduce_add_sync(0xffffffffu, n_asym);
+	if (lane == 0 && n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
+}
+
 // ---- binary-search pair emit (neighborhood_binary_search.comp:166-276) ----------------------------------------------
 struct u96 { uint32_t v[3]; };
 __device__ __forceinline__ u96 mk96(uint32_t a, uint32_t b, uint32_t c) { u96 r; r.v[0] = a; r.v[1] = b; r.v[2] = c; return r; }
@@ -585,7 +947,7 @@ k_bsearch_emit(const uint32_t* __restrict__ index_list, const int32_t* __restric
 __global__ void k_clear_search_words(uint32_t* misc)
 {
 	misc[MW_N_ASYM] = 0u; misc[MW_TOTAL_PAIRS] = 0u; misc[MW_KEPT_PAIRS] = 0xFFFFFFFFu; misc[MW_OCC_CELLS] = 0u;
-	misc[MW_EMIT_TICKET0] = 0u; misc[MW_EMIT_TICKET1] = 0u;
+	misc[MW_EMIT_TICKET0] = 0u; misc[MW_EMIT_TICKET1] = 0u; misc[MW_STREAM_CURSOR] = 0u; misc[MW_STREAM_OVERFLOW] = 0u;
 }
 
 // shared front half of both searches: gather hidden arrays by sorted_index, rebuild the index list, gather per-id arrays
@@ -660,6 +1022,19 @@ void launch_emit(int variant, int dims, unsigned grid, cudaStream_t st, const em
 	else launch_emit<FILL, EMIT_PLAIN>(dims, grid, st, A);
 }
 
+template <int VARIANT, bool STATS>
+void launch_stream(int dims, unsigned grid, cudaStream_t st, const emit_args& A)
+{
+	if (dims == 3) k_green_stream<VARIANT, 3, STATS><<<grid, EMIT_WARPS * 32, 0, st>>>(A);
+	else k_green_stream<VARIANT, 2, STATS><<<grid, EMIT_WARPS * 32, 0, st>>>(A);
+}
+void launch_stream(int variant, int dims, unsigned grid, cudaStream_t st, const emit_args& A)
+{
+	if (variant == EMIT_FUSED) launch_stream<EMIT_FUSED, true>(dims, grid, st, A);
+	else if (variant == EMIT_MG) launch_stream<EMIT_MG, false>(dims, grid, st, A);
+	else launch_stream<EMIT_PLAIN, false>(dims, grid, st, A);
+}
+
 // neighborhood_green::apply (neighborhood_green.cpp:27-77); fuse_kw: followed by spread_kernel_width::apply
 // (spread_kernel_width.cpp:12-26) on the same lists, with range == fluid->kernel_width as in pool.cpp:83-89
 int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb, float range_scale,
@@ -700,9 +1075,18 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 	if (fuse_kw) {
 		K.i4 = (int4*)ctx->scratch_get(SLOT_I4, sizeof(int4) * (size_t)n_cap);
 		K.cutoff = (float*)ctx->scratch_get(SLOT_CUTOFF, sizeof(float) * (size_t)n_cap);
+		K.qb4 = (float4*)ctx->scratch_get(SLOT_QB4, sizeof(float4) * (size_t)n_cap);
 		kwfx = (uint32_t*)ctx->scratch_get(SLOT_KWFX, sizeof(uint32_t) * (size_t)n_cap);
-		if (!K.i4 || !K.cutoff || !kwfx) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+		if (!K.i4 || !K.cutoff || !K.qb4 || !kwfx) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 	}
+	// hit stream of the one-pass emit: every tile ends with a partly filled block, hence capacity / 256 + tiles blocks hold
+	// any list that fits the pair buffer
+	const uint32_t n_tiles_cap = n_cap / 32u + 1u;
+	const uint32_t stream_blocks = nb->capacity / SB_ENTRIES + n_tiles_cap + 1u;
+	uint32_t* stream = (uint32_t*)ctx->scratch_get(SLOT_STREAM, sizeof(uint32_t) * (size_t)stream_blocks * SB_WORDS);
+	uint32_t* tile_first = (uint32_t*)ctx->scratch_get(SLOT_TILE_FIRST, sizeof(uint32_t) * (size_t)n_tiles_cap);
+	uint32_t* tile_total = (uint32_t*)ctx->scratch_get(SLOT_TILE_TOTAL, sizeof(uint32_t) * (size_t)n_tiles_cap);
+	if (!stream || !tile_first || !tile_total) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 
 	// hash all hidden particles (neighborhood_green.cpp:50-52), sort by hash with the slot as payload (:53)
 	{
@@ -740,12 +1124,15 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 	A.q4 = q4; A.key_id = key_id; A.range = new_range; A.cell_start = cs; A.cell_end = ce; A.len = p.length; A.g = g;
 	A.range_scale = range_scale; A.counts = counts; A.offsets = offsets; A.pairs = nb->pairs; A.nbl = nbl; A.cap = nb->capacity;
 	A.misc = misc; A.cull = cull; A.table_cells = max_hash; A.layers = emit_mode; A.i4 = K.i4; A.cutoff = K.cutoff; A.kwfx = kwfx;
+	A.qb4 = K.qb4; A.stream = stream; A.stream_blocks = stream_blocks; A.tile_first = tile_first; A.tile_total = tile_total;
+	static const int two_pass = getenv("APBF_TWO_PASS_EMIT") ? 1 : 0; // debugging aid: the count/fill emit instead of stream/regroup
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_COUNT);
 		k_build_q4<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>(new_index, new_pos, skeys, new_range, range_scale, p.length, q4, key_id, misc, K);
 		APBF_LAUNCHED(ctx);
 		A.ticket = misc + MW_EMIT_TICKET0;
-		launch_emit<false>(variant, g.dims, egrid, st, A);
+		if (two_pass) launch_emit<false>(variant, g.dims, egrid, st, A);
+		else launch_stream(variant, g.dims, egrid, st, A);
 		APBF_LAUNCHED(ctx);
 	}
 	{
@@ -756,7 +1143,13 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 	}
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
+		if (!two_pass) {
+			k_regroup<<<apbf_grid(ctx, n_tiles_cap, 8, 8), 256, 0, st>>>(stream, tile_first, tile_total, offsets, p.length, nb->pairs, nbl,
+			                                                            nb->capacity, misc);
+			APBF_LAUNCHED(ctx);
+		}
 		A.ticket = misc + MW_EMIT_TICKET1;
+		A.fallback = two_pass ? 0 : 1; // leaves at once unless the stream overflowed
 		launch_emit<true>(variant, g.dims, egrid, st, A);
 		APBF_LAUNCHED(ctx);
 	}
