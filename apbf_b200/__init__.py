@@ -83,6 +83,10 @@ class Context:
     def launch_count(self):
         return int(self.lib.apbf_ctx_launch_count(self.handle))
 
+    def set_search_stats(self, enable=True):
+        """fused search + spread: also count the pairs of the (never materialised) unpruned list"""
+        _check(self, self.lib.apbf_ctx_set_search_stats(self.handle, int(enable)))
+
     def profile(self, enable=True):
         _check(self, self.lib.apbf_ctx_profile(self.handle, int(enable)))
 

@@ -161,6 +161,12 @@ int apbf_ctx_set_dimensions(apbf_ctx* ctx, int dims)
 }
 
 uint64_t apbf_ctx_launch_count(apbf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int apbf_ctx_set_search_stats(apbf_ctx* ctx, int enable)
+{
+	if (!ctx) return APBF_ERR_INVALID;
+	ctx->search_stats = enable != 0;
+	return APBF_OK;
+}
 
 int apbf_ctx_profile(apbf_ctx* ctx, int enable)
 {

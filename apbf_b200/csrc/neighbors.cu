@@ -13,6 +13,7 @@
 #include "neighbors.cuh"
 #include "sort.cuh"
 #include <stdlib.h>
+#include <algorithm>
 
 namespace {
 
@@ -130,7 +131,7 @@ struct build_kw_args {
 	int          base_on_target_radius;
 	int4*        i4;
 	float*       cutoff; // threshold on the squared integer distance equivalent to dist <= max(original, old kernel width)
-	float4*      qb4;    // {K, C * ihw, ihw, original width}: the prune decided on the float-form distance (see k_green_stream)
+	float4*      qb4;    // {K, U, -, original width}: the prune decided on the float-form distance (see k_green_stream)
 };
 
 __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const uint32_t* __restrict__ hidden_key,
@@ -155,17 +156,17 @@ __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_
 			// of the float positions (neighborhood_green.comp:83).  Both approximate the same squared distance s; with
 			// |p| the largest coordinate of the particle and c the cutoff, |d2_float - d2_int| <= 2^-22 (1.73 c (|p| + c)
 			// + 2 c^2) for s near c^2 (conversion of the coordinates to float: 2^-24 |p| each; subtraction and the two
-			// dot products: a few 2^-24 s).  hw is four times that: a pair with d2_float <= C - hw is kept for sure, one
-			// with d2_float > C + hw is dropped for sure, and only the band in between needs the integer form.
+			// dot products: a few 2^-24 s).  hw is four times that: a pair with d2_float <= K = C - hw is kept for sure, one
+			// with d2_float > U = C + hw is dropped for sure, and only the band in between needs the integer form.
 			const float T = sqrt_threshold(range[id] * range_scale);
-			float4 qb = make_float4(T, 10.0f, 0.0f, orig); // no prune, never ambiguous (cutoff >= 1e15 or +inf)
-			if (!(cut == cut) || cut < 0.0f) qb.x = -1.0f; // keeps nothing
+			float4 qb = make_float4(T, T, 0.0f, orig); // no prune, never ambiguous (cutoff >= 1e15 or +inf)
+			if (!(cut == cut) || cut < 0.0f) qb.x = qb.y = -1.0f; // keeps nothing
 			else if (cut < 1.0e15f) {
 				const float pm = fmaxf(fmaxf(fabsf((float)ip.x), fabsf((float)ip.y)), fabsf((float)ip.z)) * INV_R_POS;
 				const float C = sqrt_threshold(cut);
 				const float hw = fmaxf(2.3841858e-7f * cut * (7.0f * (pm + cut) + 8.0f * cut), 1.0e-20f);
-				const float ihw = 1.0f / hw;
-				qb = make_float4(glsl_min(T, C - hw), C * ihw, ihw, orig);
+				qb.x = glsl_min(T, C - hw); // kept for sure
+				qb.y = glsl_min(T, C + hw); // kept at most
 			}
 			K.qb4[id] = qb;
 		}
@@ -232,8 +233,6 @@ struct emit_args {
 	const float4*   qb4;
 	uint32_t*       stream;
 	uint32_t        stream_blocks;
-	uint32_t*       tile_first;
-	uint32_t*       tile_total;
 	int             fallback; // two-pass fill kernel: run only if the hit stream overflowed
 };
 
@@ -498,37 +497,62 @@ k_green_emit(const emit_args A)
 }
 
 // ---- one-pass pair emit: hit stream + regroup ---------------------------------------------------------------------------
-// k_green_emit tests every (query, candidate) twice: once to count, once to fill.  k_green_stream tests once.  Same tiles,
-// runs, cell walk and candidate batches, but:
-//   * lane = candidate all the way: the lane keeps one bit per query of the run (colK: pair kept, colM: the mirrored pair
-//     is kept as well) -- 8 unfused flops, two compares and two predicated ORs per query, no ballots, no shared-memory
-//     traffic besides the broadcast load of the query;
-//   * the hits of a batch go, candidate after candidate, into the tile's HIT STREAM: {idN | unmirrored << 31, query lane},
-//     5 bytes per pair, in 256-entry blocks taken from a global allocator and chained per tile; a shared-memory counter
-//     per query yields counts[id];
-//   * after the scan of the counts, k_regroup (one warp per tile) walks the tile's chain once and moves every entry to
-//     offsets[id] + rank, rank = number of earlier entries of the same query (match_any within 32 entries + a running
-//     base per query): the list comes out grouped by id, and within an id in discovery order, exactly like the two-pass
-//     emit -- for 5 + 5 bytes of extra traffic per pair instead of a second round of distance tests.
+// k_green_emit tests every (query, candidate) twice: once to count, once to fill.  k_green_stream tests once.
+//   * QUERIES: a warp takes a window of 32 ids by ticket and handles every block of cells whose first particle lies in
+//     the window -- the whole block, in chunks of up to 32 particles, also where it extends past the window.  A block is
+//     an aligned group of 2^s cells (a contiguous key range of the Z-curve, an axis-aligned box), s chosen on the device
+//     so that a block holds about 32 particles.  All queries of a chunk share one candidate walk.
+//   * CANDIDATES: the cells of the union of the queries' boxes, x fastest as in the reference; a cell is skipped when the
+//     gap between its bounds and the bounding box of the queries' POSITIONS exceeds the largest range (cell 0 of an axis
+//     also holds what lies below the grid, hence its lower bound is -inf).  32 occupancies at a time become a dense
+//     candidate stream (warp scan + shuffle search), one candidate per lane.
+//   * TESTS, lane = candidate: one bit per query of the chunk (colK: pair kept, colM: the mirrored pair is kept too):
+//     a broadcast shared-memory load, 8 unfused flops, two compares and two predicated ORs per query.
+//   * the kept bits are transposed (32 x 32 bit matrix, five shuffle stages) so that lane = query again; every query
+//     appends its hits {idN | unmirrored << 31, lane << 27 | rank} to the chunk's HIT STREAM: 128-entry blocks taken from
+//     a global allocator, header = {first id of the chunk, entries}.  rank = how many pairs the query had before, so
+//     counts[id] falls out of the same registers.
+//   * after the scan of the counts, k_regroup moves every entry to offsets[id] + rank -- no order, no chains, one thread
+//     per entry.  The list comes out grouped by id, within an id in discovery order, exactly like the two-pass emit,
+//     for 8 + 8 bytes of extra traffic per pair instead of a second round of distance tests.
 // Fused spread_kernel_width (EMIT_FUSED): the prune (kernel_width.comp:57) is decided on the float-form squared distance
-// with the conservative threshold K = min(T, C - hw) built by k_build_q4; a batch in which any pair falls into the
-// ambiguity band |d2 - C| <= hw of the query or of the candidate (about one batch in 300) is redone with the integer form.
-// The width spread (kernel_width.comp:49-53) only matters where a candidate starts wider than a query of the run
+// with the thresholds K = min(T, C - hw) ("kept for sure") and U = min(T, C + hw) ("kept at most") built by k_build_q4;
+// a batch in which the two disagree for the query's or the candidate's prune is redone with the integer form.
+// The width spread (kernel_width.comp:49-53) only matters where a candidate starts wider than a query of the chunk
 // currently is; those batches take a second, exact loop.
 // If the stream runs out of blocks -- which needs more pairs than the pair list can hold -- MW_STREAM_OVERFLOW is set,
 // k_regroup does nothing and the fill pass of the two-pass emit writes the clamped list from the same counts.
-constexpr uint32_t SB_ENTRIES = 256u, SB_HEADER = 32u, SB_WORDS = SB_HEADER + SB_ENTRIES + SB_ENTRIES / 4u; // 1408 bytes
-constexpr uint32_t SB_NONE = 0xFFFFFFFFu;
+constexpr uint32_t SB_SHIFT = 7u, SB_ENTRIES = 1u << SB_SHIFT, SB_HEADER = 8u, SB_WORDS = SB_HEADER + 2u * SB_ENTRIES; // 1056 bytes
+constexpr uint32_t SB_RANK_BITS = 27u, SB_RANK_MASK = (1u << SB_RANK_BITS) - 1u;
+
+__device__ __forceinline__ uint32_t fkey(float f) // order-preserving float -> uint
+{
+	const uint32_t u = __float_as_uint(f);
+	return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) { return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu)); }
+
+// bit j of lane i  ->  bit i of lane j
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, unsigned lane)
+{
+#pragma unroll
+	for (int s = 16; s > 0; s >>= 1) {
+		const uint32_t m = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+		const uint32_t t = __shfl_xor_sync(0xffffffffu, x, s);
+		x = (lane & (unsigned)s) ? ((x & ~m) | ((t >> s) & m)) : ((x & m) | ((t << s) & ~m));
+	}
+	return x;
+}
 
 template <int VARIANT, int DIMS, bool STATS>
-__global__ void __launch_bounds__(EMIT_WARPS * 32)
+__global__ void __launch_bounds__(EMIT_WARPS * 32, 3)
 k_green_stream(const emit_args A)
 {
 	constexpr bool FUSED = VARIANT == EMIT_FUSED, MG = VARIANT == EMIT_MG;
-	__shared__ float4 s_q[EMIT_WARPS][32];                    // {x, y, z, K}: K = T (plain) or min(T, C - hw) (fused)
-	__shared__ float2 s_amb[FUSED ? EMIT_WARPS : 1][32];      // {C * ihw, ihw} of the query's ambiguity band
-	__shared__ float s_T[(FUSED || STATS) ? EMIT_WARPS : 1][32]; // threshold of the range test alone
-	__shared__ uint32_t s_cnt[EMIT_WARPS][32];
+	__shared__ float4 s_q[EMIT_WARPS][32];                       // {x, y, z, K}: K = T (plain) or min(T, C - hw) (fused)
+	__shared__ float s_u[FUSED ? EMIT_WARPS : 1][32];            // U = min(T, C + hw)
+	__shared__ float s_T[FUSED ? EMIT_WARPS : 1][32];            // threshold of the range test alone
+	__shared__ uint32_t s_cand[EMIT_WARPS][32], s_colM[EMIT_WARPS][32];
 	const apbf_grid_params& g = A.g;
 	const uint32_t n = *A.len;
 	const uint32_t n_owned = MG ? A.misc[MW_N_OWNED] : 0xFFFFFFFFu;
@@ -536,249 +560,272 @@ k_green_stream(const emit_args A)
 	const uint32_t key_mask = A.table_cells - 1u;
 	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 	const uint32_t axis_cap = 1u << g.res;
+	// block = 2^gshift cells with about 32 particles, from the mean occupancy of the occupied cells
 	const uint32_t occupied = max(A.misc[MW_OCC_CELLS], 1u);
-	const uint32_t gshift = (n > 4u * occupied) ? 0u : ((2u * n > occupied) ? (uint32_t)DIMS : 2u * (uint32_t)DIMS);
-	float csz[3];
+	const uint32_t per32 = (uint32_t)min((32ull * occupied) / max(n, 1u), 64ull);
+	const uint32_t gshift = min(per32 > 1u ? 31u - (uint32_t)__clz((int)per32) : 0u, g.res * (uint32_t)DIMS);
+	float csz[3], eps[3];
 #pragma unroll
-	for (int d = 0; d < 3; d++) csz[d] = g.ext[d] / g.scale;
-	if (DIMS < 3) csz[2] = 0.0f;
+	for (int d = 0; d < 3; d++) {
+		csz[d] = g.ext[d] / g.scale;
+		eps[d] = 1.0e-3f * csz[d] + 1.0e-5f * (fabsf(g.mn[d]) + fabsf(g.ext[d])); // rounding of the cell map, generously
+	}
 	uint32_t n_searched = 0;
 	for (;;) {
-		uint32_t tile = 0;
-		if (lane == 0) tile = atomicAdd(A.ticket, 1u);
-		tile = __shfl_sync(0xffffffffu, tile, 0);
-		if ((size_t)tile * 32 >= n) break;
-		const uint32_t tile_first = tile * 32u;
-		const uint32_t id = tile_first + lane;
-		const bool in = id < n;
-		float4 me = make_float4(0.f, 0.f, 0.f, -1.0f);
-		float4 qb = make_float4(-1.0f, 10.0f, 0.0f, 0.0f);
-		uint32_t gmin[3] = { 0u, 0u, 0u }, gmax[3] = { 0u, 0u, 0u }, qc[3] = { 0u, 0u, 0u };
-		uint32_t gkey = 0xFFFFFFFFu;
-		float r_lane = 0.0f;
-		if (in) {
-			me = A.q4[id];
-			gkey = A.key_id[id] >> gshift;
-			const float r = A.range[id] * A.range_scale;
-			r_lane = r == r ? fmaxf(r, 0.0f) : INFINITY;
-			qc[0] = apbf_map_axis(me.x, g, 0); qc[1] = apbf_map_axis(me.y, g, 1); qc[2] = apbf_map_axis(me.z, g, 2);
-			gmin[0] = apbf_map_axis(me.x - r, g, 0); gmax[0] = apbf_map_axis(me.x + r, g, 0);
-			gmin[1] = apbf_map_axis(me.y - r, g, 1); gmax[1] = apbf_map_axis(me.y + r, g, 1);
-			gmin[2] = apbf_map_axis(me.z - r, g, 2); gmax[2] = apbf_map_axis(me.z + r, g, 2);
-			if (DIMS < 3) { gmin[2] = 0u; gmax[2] = 0u; }
-			gmax[0] = max(gmax[0], gmin[0]); gmax[1] = max(gmax[1], gmin[1]); gmax[2] = max(gmax[2], gmin[2]);
-			if (FUSED) qb = A.qb4[id];
+		uint32_t win = 0;
+		if (lane == 0) win = atomicAdd(A.ticket, 1u);
+		win = __shfl_sync(0xffffffffu, win, 0);
+		if ((size_t)win * 32 >= n) break;
+		const uint32_t win_first = win * 32u;
+		uint32_t wkey = 0xFFFFFFFFu;
+		bool head = false;
+		if (win_first + lane < n) {
+			wkey = A.key_id[win_first + lane] >> gshift; // includes the ghost bit: owned and ghost particles never share a block
+			head = win_first + lane == 0u || (A.key_id[win_first + lane - 1u] >> gshift) != wkey;
 		}
-		__syncwarp();
-		s_q[w][lane] = make_float4(me.x, me.y, me.z, FUSED ? qb.x : me.w);
-		if (FUSED) s_amb[w][lane] = make_float2(qb.y, qb.z);
-		if (FUSED || STATS) s_T[w][lane] = me.w;
-		s_cnt[w][lane] = 0u;
-		__syncwarp();
-		const uint32_t gprev = __shfl_up_sync(0xffffffffu, gkey, 1);
-		uint32_t heads = __ballot_sync(0xffffffffu, in && (lane == 0u || gkey != gprev));
-		const uint32_t n_in = min(32u, n - tile_first);
-		uint32_t my_mx = FUSED ? f2u(qb.w * APBF_KERNEL_WIDTH_RESOLUTION) : 0u; // kernel_width_init.comp:35
-		uint32_t tile_pos = 0u, n_alloc = 0u, last_blk = SB_NONE; // the tile's stream: entries so far, blocks so far, newest block
+		uint32_t heads = __ballot_sync(0xffffffffu, head);
 		while (heads) {
-			const uint32_t r0 = (uint32_t)__ffs(heads) - 1u;
+			const uint32_t hl = (uint32_t)__ffs(heads) - 1u;
 			heads &= heads - 1u;
-			const uint32_t r1 = heads ? (uint32_t)__ffs(heads) - 1u : n_in;
-			const bool valid = lane >= r0 && lane < r1;
-			uint32_t umin[3], ext[3];
-			int qlo[3], qhi[3];
-#pragma unroll
-			for (int d = 0; d < 3; d++) {
-				umin[d] = __reduce_min_sync(0xffffffffu, valid ? gmin[d] : 0xFFFFFFFFu);
-				ext[d] = min(__reduce_max_sync(0xffffffffu, valid ? gmax[d] : 0u) - umin[d], axis_cap - 1u) + 1u;
-				qlo[d] = (int)min(__reduce_min_sync(0xffffffffu, valid ? qc[d] : 0xFFFFFFFFu), 0x7FFFFFFFu);
-				qhi[d] = (int)min(__reduce_max_sync(0xffffffffu, valid ? qc[d] : 0u), 0x7FFFFFFFu);
+			const uint32_t blk_first = win_first + hl;
+			const uint32_t bkey = __shfl_sync(0xffffffffu, wkey, (int)hl);
+			uint32_t blk_len = 1u; // particles of the block: up to the next change of the block key
+			for (uint32_t b = blk_first + 1u;; b += 32u) {
+				const uint32_t i = b + lane;
+				const bool same = i < n && (A.key_id[i] >> gshift) == bkey;
+				const uint32_t diff = __ballot_sync(0xffffffffu, !same);
+				if (diff) { blk_len += (uint32_t)__ffs(diff) - 1u; break; }
+				blk_len += 32u;
 			}
-			const float r_cull = __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(r_lane) : 0u));
-			const float cull2 = A.cull ? r_cull * r_cull * 1.0001f : INFINITY;
-			const uint32_t nxy = ext[0] * ext[1], ncell = nxy * ext[2];
-			const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)ext[0];
-			const bool ghost_run = MG && tile_first + r0 >= n_owned;
-			const uint32_t n_layers = layers > 1u ? 2u : 1u;
-			for (uint32_t cbase = 0; cbase < ncell * n_layers; cbase += 32) {
-				uint32_t ci = cbase + lane;
-				uint32_t c_first = 0u, c_cnt = 0u;
-				if (ci < ncell * n_layers) {
-					const uint32_t table_off = ci >= ncell ? A.table_cells : 0u;
-					if (ci >= ncell) ci -= ncell;
-					uint32_t cz, cy;
-					if (ncell <= (1u << 24)) {
-						cz = (uint32_t)((float)ci * inv_nxy);
-						if (cz * nxy > ci) cz--; else if ((cz + 1u) * nxy <= ci) cz++;
-					} else {
-						cz = ci / nxy;
-					}
-					const uint32_t rem = ci - cz * nxy;
-					if (ncell <= (1u << 24)) {
-						cy = (uint32_t)((float)rem * inv_nx);
-						if (cy * ext[0] > rem) cy--; else if ((cy + 1u) * ext[0] <= rem) cy++;
-					} else {
-						cy = rem / ext[0];
-					}
-					const uint32_t cx = rem - cy * ext[0];
-					const uint32_t ax = umin[0] + cx, ay = umin[1] + cy, az = umin[2] + cz;
-					const int ix = (int)min(ax, 0x7FFFFFFFu), iy = (int)min(ay, 0x7FFFFFFFu), iz = (int)min(az, 0x7FFFFFFFu);
-					const float gx = fmaxf((float)max(qlo[0] - ix, ix - qhi[0]) - 1.01f, 0.0f) * csz[0];
-					const float gy = fmaxf((float)max(qlo[1] - iy, iy - qhi[1]) - 1.01f, 0.0f) * csz[1];
-					const float gz = fmaxf((float)max(qlo[2] - iz, iz - qhi[2]) - 1.01f, 0.0f) * csz[2];
-					if (!(gx * gx + gy * gy + gz * gz > cull2)) {
-						const uint32_t h = (apbf_zhash<DIMS>(ax, ay, az, g.res) & key_mask) + table_off;
-						c_first = __ldg(A.cell_start + h);
-						c_cnt = __ldg(A.cell_end + h) - c_first;
-					}
+			for (uint32_t c0 = 0; c0 < blk_len; c0 += 32u) {
+				// ---- one chunk: queries first .. first + cnt, lane = query ----------------------------------------------------
+				const uint32_t first = blk_first + c0, cnt = min(32u, blk_len - c0);
+				const uint32_t id = first + lane;
+				const bool valid = lane < cnt;
+				float4 me = make_float4(0.f, 0.f, 0.f, -1.0f);
+				float4 qb = make_float4(-1.0f, -1.0f, 0.0f, 0.0f);
+				uint32_t gmin[3] = { 0u, 0u, 0u }, gmax[3] = { 0u, 0u, 0u };
+				float r_lane = 0.0f;
+				if (valid) {
+					me = A.q4[id];
+					const float r = A.range[id] * A.range_scale;
+					r_lane = r == r ? fmaxf(r, 0.0f) : INFINITY; // a NaN range accepts every candidate
+					gmin[0] = apbf_map_axis(me.x - r, g, 0); gmax[0] = apbf_map_axis(me.x + r, g, 0);
+					gmin[1] = apbf_map_axis(me.y - r, g, 1); gmax[1] = apbf_map_axis(me.y + r, g, 1);
+					gmin[2] = apbf_map_axis(me.z - r, g, 2); gmax[2] = apbf_map_axis(me.z + r, g, 2);
+					if (DIMS < 3) { gmin[2] = 0u; gmax[2] = 0u; } // * uvec3(1, D > 1, D > 2), neighborhood_green.comp:36
+					// the reference visits gridMin once even when gridMax < gridMin (its ++cell > gridMax wrap)
+					gmax[0] = max(gmax[0], gmin[0]); gmax[1] = max(gmax[1], gmin[1]); gmax[2] = max(gmax[2], gmin[2]);
+					if (FUSED) qb = A.qb4[id];
 				}
-				uint32_t incl = c_cnt;
+				__syncwarp();
+				s_q[w][lane] = make_float4(me.x, me.y, me.z, FUSED ? qb.x : me.w);
+				if (FUSED) { s_u[w][lane] = qb.y; s_T[w][lane] = me.w; }
+				__syncwarp();
+				uint32_t my_mx = FUSED ? f2u(qb.w * APBF_KERNEL_WIDTH_RESOLUTION) : 0u; // kernel_width_init.comp:35
+				uint32_t my_cnt = 0u;
+				uint32_t tile_pos = 0u, n_alloc = 0u, last_blk = 0xFFFFFFFFu; // the chunk's stream: entries, blocks, newest block
+				uint32_t umin[3], ext[3];
+				float qlo[3], qhi[3]; // bounding box of the queries' positions
 #pragma unroll
-				for (int o = 1; o < 32; o <<= 1) {
-					const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-					if (lane >= (unsigned)o) incl += t;
+				for (int d = 0; d < 3; d++) {
+					umin[d] = __reduce_min_sync(0xffffffffu, valid ? gmin[d] : 0xFFFFFFFFu);
+					ext[d] = min(__reduce_max_sync(0xffffffffu, valid ? gmax[d] : 0u) - umin[d], axis_cap - 1u) + 1u;
+					const float p = d == 0 ? me.x : (d == 1 ? me.y : me.z);
+					qlo[d] = fkey_inv(__reduce_min_sync(0xffffffffu, valid ? fkey(p) : 0xFFFFFFFFu));
+					qhi[d] = fkey_inv(__reduce_max_sync(0xffffffffu, valid ? fkey(p) : 0u));
 				}
-				const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-				const uint32_t c_base = c_first - (incl - c_cnt);
-				for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-					const uint32_t t = t0 + lane;
-					uint32_t pos = 0u;
+				const float r_cull = __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(r_lane) : 0u));
+				const float cull2 = A.cull ? r_cull * r_cull * 1.0001f : INFINITY;
+				const uint32_t nxy = ext[0] * ext[1], ncell = nxy * ext[2];
+				const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)ext[0];
+				const bool ghost_run = MG && first >= n_owned;
+				const uint32_t n_layers = layers > 1u ? 2u : 1u;
+				for (uint32_t cbase = 0; cbase < ncell * n_layers; cbase += 32) {
+					uint32_t ci = cbase + lane;
+					uint32_t c_first = 0u, c_cnt = 0u;
+					if (ci < ncell * n_layers) {
+						const uint32_t table_off = ci >= ncell ? A.table_cells : 0u;
+						if (ci >= ncell) ci -= ncell;
+						// ci = (cz * ny + cy) * nx + cx; float reciprocals + one correction step are exact for ci < 2^24
+						uint32_t cz, cy;
+						if (ncell <= (1u << 24)) {
+							cz = (uint32_t)((float)ci * inv_nxy);
+							if (cz * nxy > ci) cz--; else if ((cz + 1u) * nxy <= ci) cz++;
+						} else {
+							cz = ci / nxy;
+						}
+						const uint32_t rem = ci - cz * nxy;
+						if (ncell <= (1u << 24)) {
+							cy = (uint32_t)((float)rem * inv_nx);
+							if (cy * ext[0] > rem) cy--; else if ((cy + 1u) * ext[0] <= rem) cy++;
+						} else {
+							cy = rem / ext[0];
+						}
+						const uint32_t cx = rem - cy * ext[0];
+						const uint32_t a[3] = { umin[0] + cx, umin[1] + cy, umin[2] + cz };
+						float gap2 = 0.0f;
 #pragma unroll
-					for (int step = 16; step > 0; step >>= 1) {
-						const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(pos + step - 1));
-						if (v <= t) pos += step;
-					}
-					const uint32_t cand = __shfl_sync(0xffffffffu, c_base, (int)(pos & 31u)) + t;
-					const bool cvalid = t < total;
-					float4 c4 = make_float4(0.f, 0.f, 0.f, -1.0f);
-					float4 cb = make_float4(-1.0f, 10.0f, 0.0f, 0.0f);
-					if (cvalid) {
-						c4 = A.q4[cand];
-						if (FUSED) cb = A.qb4[cand];
-					}
-					const float Kb = FUSED ? cb.x : c4.w;
-					bool spread = false; // can a candidate of this batch raise the width of a query of this run?
-					if (FUSED)
-						spread = __reduce_max_sync(0xffffffffu, f2u(cb.w * APBF_KERNEL_WIDTH_RESOLUTION)) >
-						         __reduce_min_sync(0xffffffffu, valid ? my_mx : 0xFFFFFFFFu);
-					// ---- the tests: one bit per query of the run ----------------------------------------------------------
-					uint32_t colK = 0u, colM = 0u, colS = 0u;
-					float ambmin = 4.0f;
-#pragma unroll 4
-					for (uint32_t qi = r0; qi < r1; qi++) {
-						const float4 qv = s_q[w][qi];
-						const uint32_t bit = 1u << qi;
-						const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
-						const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-						const bool pk = !(d2 > qv.w);
-						const bool pm = pk && !(d2 > Kb);
-						colK |= pk ? bit : 0u;
-						colM |= pm ? bit : 0u;
-						if (FUSED) {
-							const float2 ab = s_amb[w][qi];
-							ambmin = fminf(ambmin, fminf(fabsf(__fmaf_rn(d2, ab.y, -ab.x)), fabsf(__fmaf_rn(d2, cb.z, -cb.y))));
+						for (int d = 0; d < DIMS; d++) {
+							const float lo = a[d] == 0u ? -INFINITY : g.mn[d] + (float)a[d] * csz[d];
+							const float hi = g.mn[d] + ((float)a[d] + 1.0f) * csz[d];
+							const float gp = fmaxf(fmaxf(lo - qhi[d], qlo[d] - hi) - eps[d], 0.0f);
+							gap2 += gp * gp;
 						}
-						if (STATS && FUSED) colS |= !(d2 > s_T[w][qi]) ? bit : 0u;
-					}
-					const uint32_t sq = cand - tile_first; // this candidate is query sq of the tile: id != idN, neighborhood_green.comp:83
-					const uint32_t live = cvalid ? ~(sq < 32u ? 1u << sq : 0u) : 0u;
-					if (FUSED && __any_sync(0xffffffffu, cvalid && ambmin <= 1.0f)) {
-						// a pair of this batch sits in an ambiguity band: the whole batch again, prune on the integer form
-						const int4 ci4 = cvalid ? __ldg(A.i4 + cand) : make_int4(0, 0, 0, 0);
-						const float cutb = cvalid ? A.cutoff[cand] : -1.0f;
-						colK = 0u; colM = 0u;
-						for (uint32_t qi = r0; qi < r1; qi++) {
-							const float4 qv = s_q[w][qi];
-							const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
-							const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-							const int4 ia = __ldg(A.i4 + tile_first + qi);
-							// kernel_width.comp:36-38: integer subtract first, then to float; D2 = dist^2 * 2^36
-							const float ux = (float)(ci4.x - ia.x), uy = (float)(ci4.y - ia.y), uz = (float)(ci4.z - ia.z);
-							const float D2 = dot3(ux, uy, uz, ux, uy, uz);
-							const bool keep = !(d2 > s_T[w][qi]) && D2 <= A.cutoff[tile_first + qi]; // :57
-							const bool mir = keep && !(d2 > c4.w) && D2 <= cutb;                     // (idN, id) survives as well
-							colK |= keep ? 1u << qi : 0u;
-							colM |= mir ? 1u << qi : 0u;
+						if (!(gap2 > cull2)) {
+							const uint32_t h = (apbf_zhash<DIMS>(a[0], a[1], a[2], g.res) & key_mask) + table_off;
+							c_first = __ldg(A.cell_start + h);
+							c_cnt = __ldg(A.cell_end + h) - c_first;
 						}
 					}
-					colK &= live; colM &= live;
-					if (STATS) n_searched += __popc((FUSED ? colS : colK) & live);
-					if (FUSED && spread) {
-						// the pair (idN, id) of the unpruned list spreads idN's width onto id (kernel_width.comp:49-53), gathered
-						const int4 ci4 = cvalid ? __ldg(A.i4 + cand) : make_int4(0, 0, 0, 0);
-						for (uint32_t qi = r0; qi < r1; qi++) {
-							const float4 qv = s_q[w][qi];
-							const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
-							const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-							uint32_t val = 0u;
-							if (((live >> qi) & 1u) && !(d2 > c4.w)) {
-								const int4 ia = __ldg(A.i4 + tile_first + qi);
-								const float ux = (float)(ci4.x - ia.x), uy = (float)(ci4.y - ia.y), uz = (float)(ci4.z - ia.z);
-								const float rx = ux * INV_R_POS, ry = uy * INV_R_POS, rz = uz * INV_R_POS;
-								val = apbf_kw_influence(cb.w, sqrtf(dot3(rx, ry, rz, rx, ry, rz)));
-							}
-							val = __reduce_max_sync(0xffffffffu, val);
-							if (lane == qi) my_mx = max(my_mx, val);
-						}
-					}
-					if (MG && ghost_run) {
-						// a ghost is a query only for the pairs nobody else provides: unmirrored pairs onto owned particles
-						if (cand >= n_owned) colK = 0u;
-						if (layers != 3u) colK &= ~colM;
-					}
-					// ---- append the batch's hits to the tile's stream, candidate after candidate ------------------------------
-					const uint32_t c = (uint32_t)__popc(colK);
-					uint32_t inc = c;
+					uint32_t incl = c_cnt;
 #pragma unroll
 					for (int o = 1; o < 32; o <<= 1) {
-						const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-						if (lane >= (unsigned)o) inc += v;
+						const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+						if (lane >= (unsigned)o) incl += t;
 					}
-					const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
-					if (tot) {
-						const uint32_t n_before = n_alloc, need = ((tile_pos + tot - 1u) >> 8) + 1u;
-						uint32_t base = 0u;
-						if (need > n_before) {
-							const uint32_t grp = need - n_before;
-							if (lane == 0) base = atomicAdd(A.misc + MW_STREAM_CURSOR, grp);
-							base = __shfl_sync(0xffffffffu, base, 0);
-							if (lane == 0) {
-								if (n_before == 0u) A.tile_first[tile] = base;
-								else if (last_blk < A.stream_blocks) A.stream[(size_t)last_blk * SB_WORDS] = base;
-								if (base + grp > A.stream_blocks || base + grp < base) A.misc[MW_STREAM_OVERFLOW] = 1u;
-							}
-							for (uint32_t i = lane; i + 1u < grp; i += 32u)
-								if (base + i < A.stream_blocks) A.stream[(size_t)(base + i) * SB_WORDS] = base + i + 1u;
+					const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+					const uint32_t c_base = c_first - (incl - c_cnt); // candidate t of this cell is id c_base + t
+					for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+						const uint32_t t = t0 + lane;
+						// the cell that holds candidate t: first lane whose inclusive count exceeds t
+						uint32_t pos = 0u;
+#pragma unroll
+						for (int step = 16; step > 0; step >>= 1) {
+							const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(pos + step - 1));
+							if (v <= t) pos += step;
 						}
-						uint32_t m = colK, tp = tile_pos + (inc - c);
-						while (m) {
-							const uint32_t q = (uint32_t)__ffs(m) - 1u;
-							m &= m - 1u;
-							const uint32_t o = tp >> 8;
-							const uint32_t blk = o < n_before ? last_blk : base + (o - n_before);
-							if (blk < A.stream_blocks) {
-								uint32_t* B = A.stream + (size_t)blk * SB_WORDS + SB_HEADER;
-								B[tp & 255u] = cand | (((colM >> q) & 1u) ? 0u : NB_UNMIRRORED);
-								((uint8_t*)(B + SB_ENTRIES))[tp & 255u] = (uint8_t)q;
-							}
-							atomicAdd(&s_cnt[w][q], 1u);
-							tp++;
+						const uint32_t cand = __shfl_sync(0xffffffffu, c_base, (int)(pos & 31u)) + t;
+						const bool cvalid = t < total;
+						float4 c4 = make_float4(0.f, 0.f, 0.f, -1.0f);
+						float4 cb = make_float4(-1.0f, -1.0f, 0.0f, 0.0f);
+						if (cvalid) {
+							c4 = A.q4[cand];
+							if (FUSED) cb = A.qb4[cand];
 						}
-						if (need > n_before) { last_blk = base + (need - n_before) - 1u; n_alloc = need; }
-						tile_pos += tot;
+						const float Kb = FUSED ? cb.x : c4.w;
+						bool spread = false; // can a candidate of this batch raise the width of a query of this chunk?
+						if (FUSED)
+							spread = __reduce_max_sync(0xffffffffu, f2u(cb.w * APBF_KERNEL_WIDTH_RESOLUTION)) >
+							         __reduce_min_sync(0xffffffffu, valid ? my_mx : 0xFFFFFFFFu);
+						// ---- the tests, lane = candidate: one bit per query of the chunk ------------------------------------------
+						uint32_t colK = 0u, colM = 0u, colU = 0u, colMu = 0u, colS = 0u;
+#pragma unroll 4
+						for (uint32_t qi = 0; qi < cnt; qi++) {
+							const float4 qv = s_q[w][qi];
+							const uint32_t bit = 1u << qi;
+							const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
+							const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+							const bool pk = !(d2 > qv.w);
+							colK |= pk ? bit : 0u;
+							colM |= (pk && !(d2 > Kb)) ? bit : 0u;
+							if (FUSED) {
+								const bool pu = !(d2 > s_u[w][qi]);
+								colU |= pu ? bit : 0u;
+								colMu |= (pu && !(d2 > cb.y)) ? bit : 0u;
+								if (STATS) colS |= !(d2 > s_T[w][qi]) ? bit : 0u;
+							}
+						}
+						const uint32_t sq = cand - first; // this candidate is query sq of the chunk: id != idN, neighborhood_green.comp:83
+						const uint32_t live = cvalid ? ~(sq < 32u ? 1u << sq : 0u) : 0u;
+						if (FUSED && __any_sync(0xffffffffu, (((colU ^ colK) | (colMu ^ colM)) & live) != 0u)) {
+							// a pair of this batch sits in an ambiguity band: the whole batch again, prune on the integer form
+							const int4 ci4 = cvalid ? __ldg(A.i4 + cand) : make_int4(0, 0, 0, 0);
+							const float cutb = cvalid ? A.cutoff[cand] : -1.0f;
+							colK = 0u; colM = 0u;
+							for (uint32_t qi = 0; qi < cnt; qi++) {
+								const float4 qv = s_q[w][qi];
+								const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
+								const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+								const int4 ia = __ldg(A.i4 + first + qi);
+								// kernel_width.comp:36-38: integer subtract first, then to float; D2 = dist^2 * 2^36
+								const float ux = (float)(ci4.x - ia.x), uy = (float)(ci4.y - ia.y), uz = (float)(ci4.z - ia.z);
+								const float D2 = dot3(ux, uy, uz, ux, uy, uz);
+								const bool keep = !(d2 > s_T[w][qi]) && D2 <= A.cutoff[first + qi]; // :57
+								const bool mir = keep && !(d2 > c4.w) && D2 <= cutb;                 // (idN, id) survives as well
+								colK |= keep ? 1u << qi : 0u;
+								colM |= mir ? 1u << qi : 0u;
+							}
+						}
+						colK &= live; colM &= live;
+						if (STATS) n_searched += __popc((FUSED ? colS : colK) & live);
+						if (FUSED && spread) {
+							// the pair (idN, id) of the unpruned list spreads idN's width onto id (kernel_width.comp:49-53), gathered
+							const int4 ci4 = cvalid ? __ldg(A.i4 + cand) : make_int4(0, 0, 0, 0);
+							for (uint32_t qi = 0; qi < cnt; qi++) {
+								const float4 qv = s_q[w][qi];
+								const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
+								const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+								uint32_t val = 0u;
+								if (((live >> qi) & 1u) && !(d2 > c4.w)) {
+									const int4 ia = __ldg(A.i4 + first + qi);
+									const float ux = (float)(ci4.x - ia.x), uy = (float)(ci4.y - ia.y), uz = (float)(ci4.z - ia.z);
+									const float rx = ux * INV_R_POS, ry = uy * INV_R_POS, rz = uz * INV_R_POS;
+									val = apbf_kw_influence(cb.w, sqrtf(dot3(rx, ry, rz, rx, ry, rz)));
+								}
+								val = __reduce_max_sync(0xffffffffu, val);
+								if (lane == qi) my_mx = max(my_mx, val);
+							}
+						}
+						if (MG && ghost_run) {
+							// a ghost is a query only for the pairs nobody else provides: unmirrored pairs onto owned particles
+							if (cand >= n_owned) colK = 0u;
+							if (layers != 3u) colK &= ~colM;
+						}
+						// ---- lane = query again: append the hits to the chunk's stream ---------------------------------------------
+						if (__any_sync(0xffffffffu, colK != 0u)) {
+							s_cand[w][lane] = cand;
+							s_colM[w][lane] = colM;
+							const uint32_t rowK = transpose32(colK, lane); // bit j: candidate j of the batch
+							const uint32_t c = (uint32_t)__popc(rowK);
+							uint32_t inc = c;
+#pragma unroll
+							for (int o = 1; o < 32; o <<= 1) {
+								const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+								if (lane >= (unsigned)o) inc += v;
+							}
+							const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+							const uint32_t n_before = n_alloc, need = ((tile_pos + tot - 1u) >> SB_SHIFT) + 1u;
+							uint32_t base = 0u;
+							if (need > n_before) {
+								const uint32_t grp = need - n_before;
+								if (lane == 0) {
+									base = atomicAdd(A.misc + MW_STREAM_CURSOR, grp);
+									if (base + grp > A.stream_blocks || base + grp < base) A.misc[MW_STREAM_OVERFLOW] = 1u;
+								}
+								base = __shfl_sync(0xffffffffu, base, 0);
+								for (uint32_t i = lane; i < grp; i += 32u)
+									if (base + i < A.stream_blocks) *(uint2*)(A.stream + (size_t)(base + i) * SB_WORDS) = make_uint2(first, SB_ENTRIES);
+							}
+							if (my_cnt + c > SB_RANK_MASK) A.misc[MW_STREAM_OVERFLOW] = 1u; // the rank field is full: two-pass fill
+							__syncwarp();
+							uint32_t m = rowK, tp = tile_pos + (inc - c), rk = (lane << SB_RANK_BITS) | (my_cnt & SB_RANK_MASK);
+							while (m) {
+								const uint32_t j = (uint32_t)__ffs(m) - 1u;
+								m &= m - 1u;
+								const uint32_t o = tp >> SB_SHIFT;
+								const uint32_t blk = o < n_before ? last_blk : base + (o - n_before);
+								if (blk < A.stream_blocks) {
+									uint32_t* B = A.stream + (size_t)blk * SB_WORDS + SB_HEADER;
+									B[tp & (SB_ENTRIES - 1u)] = s_cand[w][j] | (((s_colM[w][j] >> lane) & 1u) ? 0u : NB_UNMIRRORED);
+									B[SB_ENTRIES + (tp & (SB_ENTRIES - 1u))] = rk;
+								}
+								tp++; rk++;
+							}
+							my_cnt += c;
+							if (need > n_before) { last_blk = base + (need - n_before) - 1u; n_alloc = need; }
+							tile_pos += tot;
+							__syncwarp();
+						}
 					}
-					__syncwarp();
 				}
+				if (valid) {
+					A.counts[id] = my_cnt;
+					if (FUSED) A.kwfx[id] = my_mx; // kernel_width_init.comp:35 + the atomicMax of kernel_width.comp:53, gathered
+				}
+				if (lane == 0 && n_alloc != 0u && last_blk < A.stream_blocks)
+					A.stream[(size_t)last_blk * SB_WORDS + 1u] = tile_pos - SB_ENTRIES * (n_alloc - 1u); // entries of the last block
 			}
-		}
-		__syncwarp();
-		if (in) {
-			A.counts[id] = s_cnt[w][lane];
-			if (FUSED) A.kwfx[id] = my_mx; // kernel_width_init.comp:35 + the atomicMax of kernel_width.comp:53, gathered
-		}
-		if (lane == 0) {
-			A.tile_total[tile] = tile_pos;
-			if (n_alloc == 0u) A.tile_first[tile] = SB_NONE;
 		}
 	}
 	if (STATS) {
@@ -787,50 +834,49 @@ k_green_stream(const emit_args A)
 	}
 }
 
-// second half of the one-pass emit: entries of a tile's stream -> offsets[id] + rank
-__global__ void __launch_bounds__(256)
-k_regroup(const uint32_t* __restrict__ stream, const uint32_t* __restrict__ tile_first, const uint32_t* __restrict__ tile_total,
-          const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ len, uint32_t* __restrict__ pairs,
-          uint32_t* __restrict__ nbl, uint32_t cap, uint32_t* misc)
+// second half of the one-pass emit: every entry of the hit stream -> offsets[id] + rank
+__global__ void __launch_bounds__(SB_ENTRIES)
+k_regroup(const uint32_t* __restrict__ stream, uint32_t stream_blocks, const uint32_t* __restrict__ offsets,
+          uint32_t* __restrict__ pairs, uint32_t* __restrict__ nbl, uint32_t cap, uint32_t* misc)
 {
 	if (misc[MW_STREAM_OVERFLOW] != 0u) return;
-	__shared__ uint32_t s_base[8][32];
-	const uint32_t n = *len;
-	const uint32_t n_tiles = (n + 31u) >> 5;
-	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-	const uint32_t lt = (1u << lane) - 1u;
+	const uint32_t used = min(misc[MW_STREAM_CURSOR], stream_blocks);
 	uint32_t n_asym = 0u;
-	for (uint32_t tile = blockIdx.x * 8u + w; tile < n_tiles; tile += gridDim.x * 8u) {
-		const uint32_t id0 = tile * 32u;
-		__syncwarp();
-		s_base[w][lane] = id0 + lane < n ? offsets[id0 + lane] : 0u;
-		__syncwarp();
-		const uint32_t total = tile_total[tile];
-		uint32_t blk = tile_first[tile];
-		for (uint32_t t0 = 0; t0 < total; t0 += 32u) {
-			if (t0 != 0u && (t0 & (SB_ENTRIES - 1u)) == 0u) blk = stream[(size_t)blk * SB_WORDS];
-			const uint32_t* B = stream + (size_t)blk * SB_WORDS + SB_HEADER;
-			const uint32_t t = t0 + lane;
-			const bool ok = t < total;
-			const uint32_t word = ok ? B[t & 255u] : 0u;
-			const uint32_t q = ok ? (uint32_t)((const uint8_t*)(B + SB_ENTRIES))[t & 255u] : 32u + lane;
-			const uint32_t peers = __match_any_sync(0xffffffffu, q);
-			const uint32_t rank = (uint32_t)__popc(peers & lt);
-			if (ok) {
-				const uint32_t o = s_base[w][q] + rank;
-				if (o < cap) {
-					*(uint2*)(pairs + 2 * (size_t)o) = make_uint2(id0 + q, word & NB_ID_MASK);
-					nbl[o] = word;
-					n_asym += word >> 31;
-				}
+	constexpr int U = 4; // blocks in flight per thread: the chain header -> entry -> offset -> store is pure latency
+	for (uint32_t blk0 = blockIdx.x; blk0 < used; blk0 += U * gridDim.x) {
+		uint2 hdr[U];
+		uint32_t word[U], rk[U];
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const uint32_t blk = blk0 + u * gridDim.x;
+			hdr[u] = make_uint2(0u, 0u);
+			if (blk < used) {
+				const uint32_t* B = stream + (size_t)blk * SB_WORDS;
+				hdr[u] = *(const uint2*)B;
+				word[u] = B[SB_HEADER + threadIdx.x];
+				rk[u] = B[SB_HEADER + SB_ENTRIES + threadIdx.x];
 			}
-			__syncwarp();
-			if (ok && rank == 0u) s_base[w][q] += (uint32_t)__popc(peers);
-			__syncwarp();
+		}
+		uint32_t o[U], id[U];
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			o[u] = 0xFFFFFFFFu;
+			if (threadIdx.x < hdr[u].y) {
+				id[u] = hdr[u].x + (rk[u] >> SB_RANK_BITS);
+				o[u] = offsets[id[u]] + (rk[u] & SB_RANK_MASK);
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			if (threadIdx.x < hdr[u].y && o[u] < cap) {
+				*(uint2*)(pairs + 2 * (size_t)o[u]) = make_uint2(id[u], word[u] & NB_ID_MASK);
+				nbl[o[u]] = word[u];
+				n_asym += word[u] >> 31;
+			}
 		}
 	}
 	n_asym = __reduce_add_sync(0xffffffffu, n_asym);
-	if (lane == 0 && n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
+	if ((threadIdx.x & 31u) == 0u && n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
 }
 
 // ---- binary-search pair emit (neighborhood_binary_search.comp:166-276) ----------------------------------------------
@@ -1028,9 +1074,10 @@ void launch_stream(int dims, unsigned grid, cudaStream_t st, const emit_args& A)
 	if (dims == 3) k_green_stream<VARIANT, 3, STATS><<<grid, EMIT_WARPS * 32, 0, st>>>(A);
 	else k_green_stream<VARIANT, 2, STATS><<<grid, EMIT_WARPS * 32, 0, st>>>(A);
 }
-void launch_stream(int variant, int dims, unsigned grid, cudaStream_t st, const emit_args& A)
+void launch_stream(int variant, bool stats, int dims, unsigned grid, cudaStream_t st, const emit_args& A)
 {
-	if (variant == EMIT_FUSED) launch_stream<EMIT_FUSED, true>(dims, grid, st, A);
+	if (variant == EMIT_FUSED && stats) launch_stream<EMIT_FUSED, true>(dims, grid, st, A);
+	else if (variant == EMIT_FUSED) launch_stream<EMIT_FUSED, false>(dims, grid, st, A);
 	else if (variant == EMIT_MG) launch_stream<EMIT_MG, false>(dims, grid, st, A);
 	else launch_stream<EMIT_PLAIN, false>(dims, grid, st, A);
 }
@@ -1079,14 +1126,12 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 		kwfx = (uint32_t*)ctx->scratch_get(SLOT_KWFX, sizeof(uint32_t) * (size_t)n_cap);
 		if (!K.i4 || !K.cutoff || !K.qb4 || !kwfx) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 	}
-	// hit stream of the one-pass emit: every tile ends with a partly filled block, hence capacity / 256 + tiles blocks hold
-	// any list that fits the pair buffer
-	const uint32_t n_tiles_cap = n_cap / 32u + 1u;
-	const uint32_t stream_blocks = nb->capacity / SB_ENTRIES + n_tiles_cap + 1u;
+	// hit stream of the one-pass emit: every chunk of queries ends with a partly filled block, and there is at most one
+	// chunk per particle, hence capacity / 128 + particles blocks would hold any list that fits the pair buffer; the usual
+	// demand is pairs / 128 + particles / 20, and capacity / 128 + particles / 8 is what is reserved
+	const uint32_t stream_blocks = (uint32_t)std::min<size_t>((size_t)nb->capacity / SB_ENTRIES + (size_t)n_cap / 8u + 1024u, 0x7FFFFFFFu);
 	uint32_t* stream = (uint32_t*)ctx->scratch_get(SLOT_STREAM, sizeof(uint32_t) * (size_t)stream_blocks * SB_WORDS);
-	uint32_t* tile_first = (uint32_t*)ctx->scratch_get(SLOT_TILE_FIRST, sizeof(uint32_t) * (size_t)n_tiles_cap);
-	uint32_t* tile_total = (uint32_t*)ctx->scratch_get(SLOT_TILE_TOTAL, sizeof(uint32_t) * (size_t)n_tiles_cap);
-	if (!stream || !tile_first || !tile_total) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+	if (!stream) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 
 	// hash all hidden particles (neighborhood_green.cpp:50-52), sort by hash with the slot as payload (:53)
 	{
@@ -1124,7 +1169,7 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 	A.q4 = q4; A.key_id = key_id; A.range = new_range; A.cell_start = cs; A.cell_end = ce; A.len = p.length; A.g = g;
 	A.range_scale = range_scale; A.counts = counts; A.offsets = offsets; A.pairs = nb->pairs; A.nbl = nbl; A.cap = nb->capacity;
 	A.misc = misc; A.cull = cull; A.table_cells = max_hash; A.layers = emit_mode; A.i4 = K.i4; A.cutoff = K.cutoff; A.kwfx = kwfx;
-	A.qb4 = K.qb4; A.stream = stream; A.stream_blocks = stream_blocks; A.tile_first = tile_first; A.tile_total = tile_total;
+	A.qb4 = K.qb4; A.stream = stream; A.stream_blocks = stream_blocks;
 	static const int two_pass = getenv("APBF_TWO_PASS_EMIT") ? 1 : 0; // debugging aid: the count/fill emit instead of stream/regroup
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_COUNT);
@@ -1132,7 +1177,7 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 		APBF_LAUNCHED(ctx);
 		A.ticket = misc + MW_EMIT_TICKET0;
 		if (two_pass) launch_emit<false>(variant, g.dims, egrid, st, A);
-		else launch_stream(variant, g.dims, egrid, st, A);
+		else launch_stream(variant, ctx->search_stats, g.dims, egrid, st, A);
 		APBF_LAUNCHED(ctx);
 	}
 	{
@@ -1144,8 +1189,7 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
 		if (!two_pass) {
-			k_regroup<<<apbf_grid(ctx, n_tiles_cap, 8, 8), 256, 0, st>>>(stream, tile_first, tile_total, offsets, p.length, nb->pairs, nbl,
-			                                                            nb->capacity, misc);
+			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, nb->pairs, nbl, nb->capacity, misc);
 			APBF_LAUNCHED(ctx);
 		}
 		A.ticket = misc + MW_EMIT_TICKET1;

@@ -206,6 +206,12 @@ def run_gpu(args, rank, world, local_rank):
     launches = ctx.launch_count - launches0
     prof = ctx.profile_read()
     stats = sim.stats()
+    if meta["adaptive"]:
+        # the fused search never builds the unpruned list; one more (untimed) substep counts what it would have held
+        ctx.set_search_stats(True)
+        sim.substep(1)
+        stats = dict(stats, pairs_searched=sim.stats()["pairs_searched"])
+        ctx.set_search_stats(False)
     clocks = sampler.stop() if sampler else None
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)

@@ -82,6 +82,10 @@ int  apbf_ctx_set_settings(apbf_ctx* ctx, const apbf_settings* s);
 int  apbf_ctx_set_dimensions(apbf_ctx* ctx, int dims);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t apbf_ctx_launch_count(apbf_ctx* ctx);
+/* apbf_neighborhood_green_spread_apply never materialises the unpruned pair list of neighborhood_green; with this switch
+ * on (default off) it still counts how many pairs that list would have held (apbf_sim_stats: pairs searched), at the
+ * price of one more compare per distance test. */
+int  apbf_ctx_set_search_stats(apbf_ctx* ctx, int enable);
 /* Per-pass device timing with CUDA events on the context stream (replaces measurements::record_timing_interval_*,
  * source/measurements.cpp:27-62).  apbf_ctx_profile(ctx, 1) clears and starts, (ctx, 0) stops; apbf_ctx_profile_read
  * returns the accumulated milliseconds and span count of category 0 .. n-1 (APBF_ERR_INVALID past the last one) and
