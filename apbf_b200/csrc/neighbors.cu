@@ -131,6 +131,7 @@ struct build_kw_args {
 	int          base_on_target_radius;
 	int4*        i4;
 	float*       cutoff; // threshold on the squared integer distance equivalent to dist <= max(original, old kernel width)
+	float        pmax;   // largest |coordinate| of the search grid
 	float4*      qb4;    // {K, U, -, original width}: the prune decided on the float-form distance (see k_green_stream)
 };
 
@@ -162,7 +163,8 @@ __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_
 			float4 qb = make_float4(T, T, 0.0f, orig); // no prune, never ambiguous (cutoff >= 1e15 or +inf)
 			if (!(cut == cut) || cut < 0.0f) qb.x = qb.y = -1.0f; // keeps nothing
 			else if (cut < 1.0e15f) {
-				const float pm = fmaxf(fmaxf(fabsf((float)ip.x), fabsf((float)ip.y)), fabsf((float)ip.z)) * INV_R_POS;
+				// |p|: at least the largest coordinate of the grid, so that particles of equal cutoff share K and U
+				const float pm = fmaxf(fmaxf(fmaxf(fabsf((float)ip.x), fabsf((float)ip.y)), fabsf((float)ip.z)) * INV_R_POS, K.pmax);
 				const float C = sqrt_threshold(cut);
 				const float hw = fmaxf(2.3841858e-7f * cut * (7.0f * (pm + cut) + 8.0f * cut), 1.0e-20f);
 				qb.x = glsl_min(T, C - hw); // kept for sure
@@ -544,6 +546,50 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, unsigned lane)
 	return x;
 }
 
+// The distance tests of one candidate (this lane) against the queries of a chunk: one bit per query.  The flops go to the
+// fma pipe, compares and bit ORs to the alu pipe, each good for one warp instruction every other cycle: the loop is
+// written so that a query costs 8 + (2 | 4 | 8) of them -- compare into a predicate, predicated OR (the compiler's own
+// rendering of "mask |= p ? bit : 0" spends a SEL per mask on top).
+//   MODE 0: colK                      (all thresholds of the batch equal: the mirrored test is the same test)
+//   MODE 1: colK, colM                (plain search, per-particle ranges)
+//   MODE 2: colK, colU                (fused prune, all thresholds equal)
+//   MODE 3: colK, colM, colU, colMu   (fused prune, per-particle thresholds)
+// "d2 > K" is false for a NaN distance, i.e. NaN is accepted, like !(distance > range) in neighborhood_green.comp:83.
+template <int MODE>
+__device__ __forceinline__ void chunk_tests(const float4* __restrict__ sq, const float* __restrict__ su, uint32_t cnt, const float4 c4,
+                                            float Kb, float Ub, uint32_t& colK, uint32_t& colM, uint32_t& colU, uint32_t& colMu)
+{
+	uint32_t bit = 1u;
+#pragma unroll 4
+	for (uint32_t qi = 0; qi < cnt; qi++) {
+		const float4 qv = sq[qi];
+		const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
+		const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+		if (MODE == 0) {
+			asm("{\n\t.reg .pred pk;\n\tsetp.gt.f32 pk, %1, %2;\n\t@!pk or.b32 %0, %0, %3;\n\t}"
+			    : "+r"(colK) : "f"(d2), "f"(qv.w), "r"(bit));
+		} else if (MODE == 1) {
+			asm("{\n\t.reg .pred pk, pm;\n\tsetp.gt.f32 pk, %2, %3;\n\tsetp.gt.or.f32 pm, %2, %4, pk;\n\t"
+			    "@!pk or.b32 %0, %0, %5;\n\t@!pm or.b32 %1, %1, %5;\n\t}"
+			    : "+r"(colK), "+r"(colM) : "f"(d2), "f"(qv.w), "f"(Kb), "r"(bit));
+		} else if (MODE == 2) {
+			const float ua = su[qi];
+			asm("{\n\t.reg .pred pk, pu;\n\tsetp.gt.f32 pk, %2, %3;\n\tsetp.gt.f32 pu, %2, %4;\n\t"
+			    "@!pk or.b32 %0, %0, %5;\n\t@!pu or.b32 %1, %1, %5;\n\t}"
+			    : "+r"(colK), "+r"(colU) : "f"(d2), "f"(qv.w), "f"(ua), "r"(bit));
+		} else {
+			const float ua = su[qi];
+			asm("{\n\t.reg .pred pk, pm, pu, pn;\n\tsetp.gt.f32 pk, %4, %5;\n\tsetp.gt.or.f32 pm, %4, %6, pk;\n\t"
+			    "setp.gt.f32 pu, %4, %7;\n\tsetp.gt.or.f32 pn, %4, %8, pu;\n\t"
+			    "@!pk or.b32 %0, %0, %9;\n\t@!pm or.b32 %1, %1, %9;\n\t@!pu or.b32 %2, %2, %9;\n\t@!pn or.b32 %3, %3, %9;\n\t}"
+			    : "+r"(colK), "+r"(colM), "+r"(colU), "+r"(colMu) : "f"(d2), "f"(qv.w), "f"(Kb), "f"(ua), "f"(Ub), "r"(bit));
+		}
+		bit += bit;
+	}
+	if (MODE == 0) colM = colK;
+	if (MODE == 2) { colM = colK; colMu = colU; }
+}
+
 template <int VARIANT, int DIMS, bool STATS>
 __global__ void __launch_bounds__(EMIT_WARPS * 32, 3)
 k_green_stream(const emit_args A)
@@ -624,6 +670,10 @@ k_green_stream(const emit_args A)
 				__syncwarp();
 				uint32_t my_mx = FUSED ? f2u(qb.w * APBF_KERNEL_WIDTH_RESOLUTION) : 0u; // kernel_width_init.comp:35
 				uint32_t my_cnt = 0u;
+				// do all queries of the chunk share their thresholds?  (then, for a batch of candidates that share them too,
+				// "the mirrored pair is kept" is the same test as "the pair is kept")
+				const float qK = __shfl_sync(0xffffffffu, FUSED ? qb.x : me.w, 0), qU = __shfl_sync(0xffffffffu, qb.y, 0);
+				const bool q_uniform = __all_sync(0xffffffffu, !valid || ((FUSED ? qb.x : me.w) == qK && (!FUSED || qb.y == qU)));
 				uint32_t tile_pos = 0u, n_alloc = 0u, last_blk = 0xFFFFFFFFu; // the chunk's stream: entries, blocks, newest block
 				uint32_t umin[3], ext[3];
 				float qlo[3], qhi[3]; // bounding box of the queries' positions
@@ -710,20 +760,31 @@ k_green_stream(const emit_args A)
 							         __reduce_min_sync(0xffffffffu, valid ? my_mx : 0xFFFFFFFFu);
 						// ---- the tests, lane = candidate: one bit per query of the chunk ------------------------------------------
 						uint32_t colK = 0u, colM = 0u, colU = 0u, colMu = 0u, colS = 0u;
-#pragma unroll 4
-						for (uint32_t qi = 0; qi < cnt; qi++) {
-							const float4 qv = s_q[w][qi];
-							const uint32_t bit = 1u << qi;
-							const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
-							const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-							const bool pk = !(d2 > qv.w);
-							colK |= pk ? bit : 0u;
-							colM |= (pk && !(d2 > Kb)) ? bit : 0u;
+						if (STATS) { // counting run: the plain loop with the range test of the unpruned list on top
+							for (uint32_t qi = 0; qi < cnt; qi++) {
+								const float4 qv = s_q[w][qi];
+								const uint32_t bit = 1u << qi;
+								const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
+								const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+								const bool pk = !(d2 > qv.w);
+								colK |= pk ? bit : 0u;
+								colM |= (pk && !(d2 > Kb)) ? bit : 0u;
+								if (FUSED) {
+									const bool pu = !(d2 > s_u[w][qi]);
+									colU |= pu ? bit : 0u;
+									colMu |= (pu && !(d2 > cb.y)) ? bit : 0u;
+									colS |= !(d2 > s_T[w][qi]) ? bit : 0u;
+								}
+							}
+						} else {
+							// all thresholds of the chunk and of the batch equal: the mirrored test is the query's own test
+							const bool uni = q_uniform && __all_sync(0xffffffffu, !cvalid || (Kb == qK && (!FUSED || cb.y == qU)));
 							if (FUSED) {
-								const bool pu = !(d2 > s_u[w][qi]);
-								colU |= pu ? bit : 0u;
-								colMu |= (pu && !(d2 > cb.y)) ? bit : 0u;
-								if (STATS) colS |= !(d2 > s_T[w][qi]) ? bit : 0u;
+								if (uni) chunk_tests<2>(s_q[w], s_u[w], cnt, c4, Kb, cb.y, colK, colM, colU, colMu);
+								else chunk_tests<3>(s_q[w], s_u[w], cnt, c4, Kb, cb.y, colK, colM, colU, colMu);
+							} else {
+								if (uni) chunk_tests<0>(s_q[w], nullptr, cnt, c4, Kb, 0.0f, colK, colM, colU, colMu);
+								else chunk_tests<1>(s_q[w], nullptr, cnt, c4, Kb, 0.0f, colK, colM, colU, colMu);
 							}
 						}
 						const uint32_t sq = cand - first; // this candidate is query sq of the chunk: id != idN, neighborhood_green.comp:83
@@ -1152,6 +1213,8 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 		K.target_radius = (const float*)fluid->target_radius.reorder_out;
 		K.kernel_width = (const float*)fluid->kernel_width.reorder_out;
 		K.base_on_target_radius = ctx->settings.mBaseKernelWidthOnTargetRadius;
+		K.pmax = 0.0f;
+		for (int d = 0; d < 3; d++) K.pmax = std::max(K.pmax, std::max(fabsf(min_pos[d]), fabsf(max_pos[d])));
 	}
 	// cell ranges (:58-63)
 	{
