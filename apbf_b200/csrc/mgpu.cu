@@ -467,8 +467,13 @@ int apbf_sim_mg_phase(apbf_sim* sim, int phase, int iteration)
 			sim->last_dt = c.dt;
 			return APBF_OK;
 		case 1: {
-			ctx->mg_ghost_all_pairs = !c.basic_pbf && !s.mBaseKernelWidthOnBoundaryDistance; // spread_kernel_width will prune
-			APBF_TRY(apbf_neighborhood_green_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, unit_scale ? 1.0f : 1.5f, c.min_pos, c.max_pos, c.res_log2, nullptr));
+			const bool adaptive = !c.basic_pbf && !s.mBaseKernelWidthOnBoundaryDistance; // spread_kernel_width will prune
+			sim->mg_fused = adaptive && !sim->no_fuse;
+			ctx->mg_ghost_all_pairs = adaptive && !sim->mg_fused;
+			if (sim->mg_fused) // search + spread_kernel_width in one pass (pool.cpp:83-89), ghosts included
+				APBF_TRY(apbf_neighborhood_green_spread_apply(ctx, &sim->fluid, &sim->nb, 1.5f, c.min_pos, c.max_pos, c.res_log2, nullptr, nullptr));
+			else
+				APBF_TRY(apbf_neighborhood_green_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, unit_scale ? 1.0f : 1.5f, c.min_pos, c.max_pos, c.res_log2, nullptr));
 			apbf_sim_swap_buffers(sim);
 			// old slot -> new id, for the send lists and the ghost slots (the search's sorted_index is still in scratch)
 			const uint32_t cap = c.particle_capacity;
@@ -479,7 +484,7 @@ int apbf_sim_mg_phase(apbf_sim* sim, int phase, int iteration)
 			APBF_LAUNCHED(ctx);
 			return APBF_OK;
 		}
-		case 2: return apbf_spread_kernel_width_apply(ctx, &sim->fluid, &sim->nb, nullptr);
+		case 2: return sim->mg_fused ? APBF_OK : apbf_spread_kernel_width_apply(ctx, &sim->fluid, &sim->nb, nullptr);
 		case 3: return apbf_solver_prepare(ctx, &sim->fluid);
 		case 4: return apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_BEGIN | ITER_BEGIN_BOX | (iteration > 0 ? ITER_BEGIN_COMMIT : 0), bmin, bmax, c.n_boxes, nullptr, nullptr);
 		case 5: return apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_T1, bmin, bmax, c.n_boxes, nullptr, nullptr);

@@ -206,7 +206,7 @@ __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_
 // pairs (b, a) of the unpruned list -- so there is no atomicMax, and only the pairs that survive the prune
 // (kernel_width.comp:57) are ever counted and written.
 constexpr int EMIT_WARPS = 8;
-constexpr int EMIT_PLAIN = 0, EMIT_MG = 1, EMIT_FUSED = 2;
+constexpr int EMIT_PLAIN = 0, EMIT_MG = 1, EMIT_FUSED = 2, EMIT_FUSED_MG = 3; // k_green_stream: bit 0 = slabs, bit 1 = fused prune
 
 struct emit_args {
 	const float4*   q4;
@@ -594,7 +594,7 @@ template <int VARIANT, int DIMS, bool STATS>
 __global__ void __launch_bounds__(EMIT_WARPS * 32, 3)
 k_green_stream(const emit_args A)
 {
-	constexpr bool FUSED = VARIANT == EMIT_FUSED, MG = VARIANT == EMIT_MG;
+	constexpr bool FUSED = (VARIANT & EMIT_FUSED) != 0, MG = (VARIANT & EMIT_MG) != 0;
 	__shared__ float4 s_q[EMIT_WARPS][32];                       // {x, y, z, K}: K = T (plain) or min(T, C - hw) (fused)
 	__shared__ float s_u[FUSED ? EMIT_WARPS : 1][32];            // U = min(T, C + hw)
 	__shared__ float s_T[FUSED ? EMIT_WARPS : 1][32];            // threshold of the range test alone
@@ -830,8 +830,10 @@ k_green_stream(const emit_args A)
 						}
 						if (MG && ghost_run) {
 							// a ghost is a query only for the pairs nobody else provides: unmirrored pairs onto owned particles
+							// (fused: colM is the mirrored bit AFTER the prune, so this is final; otherwise a following spread_kernel_width
+							// can still turn mirrored pairs into unmirrored ones and layers == 3 keeps them all)
 							if (cand >= n_owned) colK = 0u;
-							if (layers != 3u) colK &= ~colM;
+							if (FUSED || layers != 3u) colK &= ~colM;
 						}
 						// ---- lane = query again: append the hits to the chunk's stream ---------------------------------------------
 						if (__any_sync(0xffffffffu, colK != 0u)) {
@@ -900,7 +902,10 @@ __global__ void __launch_bounds__(SB_ENTRIES)
 k_regroup(const uint32_t* __restrict__ stream, uint32_t stream_blocks, const uint32_t* __restrict__ offsets,
           uint32_t* __restrict__ pairs, uint32_t* __restrict__ nbl, uint32_t cap, uint32_t* misc)
 {
-	if (misc[MW_STREAM_OVERFLOW] != 0u) return;
+	if (misc[MW_STREAM_OVERFLOW] != 0u) {
+		if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(misc + MW_FLAGS, 1u); // only happens when the pair list overflows
+		return;
+	}
 	const uint32_t used = min(misc[MW_STREAM_CURSOR], stream_blocks);
 	uint32_t n_asym = 0u;
 	constexpr int U = 4; // blocks in flight per thread: the chain header -> entry -> offset -> store is pure latency
@@ -1139,6 +1144,8 @@ void launch_stream(int variant, bool stats, int dims, unsigned grid, cudaStream_
 {
 	if (variant == EMIT_FUSED && stats) launch_stream<EMIT_FUSED, true>(dims, grid, st, A);
 	else if (variant == EMIT_FUSED) launch_stream<EMIT_FUSED, false>(dims, grid, st, A);
+	else if (variant == EMIT_FUSED_MG && stats) launch_stream<EMIT_FUSED_MG, true>(dims, grid, st, A);
+	else if (variant == EMIT_FUSED_MG) launch_stream<EMIT_FUSED_MG, false>(dims, grid, st, A);
 	else if (variant == EMIT_MG) launch_stream<EMIT_MG, false>(dims, grid, st, A);
 	else launch_stream<EMIT_PLAIN, false>(dims, grid, st, A);
 }
@@ -1166,7 +1173,7 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 	uint32_t* skeys = (uint32_t*)ctx->scratch_get(SLOT_TMP_KEYS, sizeof(uint32_t) * (size_t)nh_cap);
 	uint32_t* sidx = (uint32_t*)ctx->scratch_get(SLOT_TMP_VALS, sizeof(uint32_t) * (size_t)nh_cap);
 	const uint32_t layers = ctx->mg_enabled ? 2u : 1u; // ghosts: second key space / cell table
-	const uint32_t emit_mode = ctx->mg_enabled && ctx->mg_ghost_all_pairs ? 3u : layers;
+	const uint32_t emit_mode = ctx->mg_enabled && ctx->mg_ghost_all_pairs && !fuse_kw ? 3u : layers;
 	APBF_REQUIRE(ctx, layers == 1u || max_hash <= (1u << 30));
 	uint32_t* cs = (uint32_t*)ctx->scratch_get(SLOT_CELL_START, sizeof(uint32_t) * (size_t)max_hash * layers);
 	uint32_t* ce = (uint32_t*)ctx->scratch_get(SLOT_CELL_END, sizeof(uint32_t) * (size_t)max_hash * layers);
@@ -1226,7 +1233,7 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 	APBF_LAUNCHED(ctx);
 	const unsigned egrid = apbf_grid(ctx, n_cap, EMIT_WARPS * 32, 6);
 	static const int cull = getenv("APBF_NO_CULL") ? 0 : 1; // debugging aid: walk every cell of the union box
-	const int variant = fuse_kw ? EMIT_FUSED : (ctx->mg_enabled ? EMIT_MG : EMIT_PLAIN);
+	const int variant = (fuse_kw ? EMIT_FUSED : 0) | (ctx->mg_enabled ? EMIT_MG : 0);
 	emit_args A;
 	memset(&A, 0, sizeof A);
 	A.q4 = q4; A.key_id = key_id; A.range = new_range; A.cell_start = cs; A.cell_end = ce; A.len = p.length; A.g = g;
@@ -1255,10 +1262,12 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, nb->pairs, nbl, nb->capacity, misc);
 			APBF_LAUNCHED(ctx);
 		}
-		A.ticket = misc + MW_EMIT_TICKET1;
-		A.fallback = two_pass ? 0 : 1; // leaves at once unless the stream overflowed
-		launch_emit<true>(variant, g.dims, egrid, st, A);
-		APBF_LAUNCHED(ctx);
+		if (variant != EMIT_FUSED_MG) { // (fused + slabs has no two-pass form: an overflow there only raises the sticky flag)
+			A.ticket = misc + MW_EMIT_TICKET1;
+			A.fallback = two_pass ? 0 : 1; // leaves at once unless the stream overflowed
+			launch_emit<true>(variant, g.dims, egrid, st, A);
+			APBF_LAUNCHED(ctx);
+		}
 	}
 	ctx->nbr_struct_pairs = nb->pairs;
 	ctx->nbr_struct_n_cap = n_cap;
@@ -1297,8 +1306,6 @@ int apbf_neighborhood_green_spread_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_
 {
 	if (!ctx) return APBF_ERR_INVALID;
 	APBF_REQUIRE(ctx, fluid);
-	if (ctx->mg_enabled) // slabs: ghosts take part in the prune; the two operators run one after the other
-		return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, "fused search + spread is single-GPU only", __FILE__, __LINE__);
 	return green_search(ctx, fluid, &fluid->kernel_width, nb, range_scale, min_pos, max_pos, res_log2, dbg, true, out_kw_fixed);
 }
 

@@ -18,6 +18,7 @@ struct apbf_sim {
 	float*          boxes;    // [2 * n_boxes * 4]
 	float           last_dt;  // velocity_handling::mLastDeltaTime (velocity_handling.h:18)
 	bool            no_fuse;
+	bool            mg_fused = false; // slabs: the last search ran fused with spread_kernel_width
 	std::vector<void*> owned;
 	apbf_mg_state   mg;
 };

@@ -126,18 +126,31 @@ def shuffle_state(arrays, seed=7):
     return out
 
 
-def dam_break(nx=100, ny=100, nz=100, r=1.0, jitter=0.05, seed=99, adaptive=True):
-    """configs[1]: a block occupying one third of a pool floor (walls per pool.cpp:30-40), adaptive widths."""
+def dam_break(nx=100, ny=100, nz=100, r=1.0, jitter=0.05, seed=99, adaptive=True, blocks=1, center_y=False, res_log2=None):
+    """configs[1]: a block occupying one third of a pool floor (walls per pool.cpp:30-40), adaptive widths.
+    Multi-GPU variants (bench.py --gpus N; bricks = halves of the grid along z, then y, then x): `blocks=2` puts a second,
+    mirrored block at the far end of the pool (the pool is twice as long, the blocks still cover a third of the floor) so
+    that the x halves hold the same number of particles; `center_y` makes the grid's y range symmetric about the block."""
     ext = np.array([nx, ny, nz], np.float32) * 2 * r
     pool_min = np.array([0, 0, 0], np.float32)
-    pool_max = np.array([3 * ext[0], 1.5 * ext[1], ext[2]], np.float32)
+    pool_max = np.array([3 * blocks * ext[0], 1.5 * ext[1], ext[2]], np.float32)
     arrays = _lattice_state((nx, ny, nz), pool_min + r, r, jitter, seed)
+    if blocks == 2:
+        far = _lattice_state((nx, ny, nz), (pool_max[0] - ext[0] + r, r, r), r, jitter, seed + 1)
+        arrays = {k: np.concatenate([arrays[k], far[k]]) for k in arrays}
+        arrays["index_list"] = np.arange(arrays["position"].shape[0], dtype=np.uint32)
     margin = 6.0 * r + 4.0
-    lo = tuple(float(v - margin) for v in pool_min)
-    hi = tuple(float(v + margin) for v in pool_max)
-    # per-axis grid bounds (cells need not be cubes); resolution so that the widest cell is about 0.75 x search range
-    sc = Scene(name=f"dam_break_{nx}x{ny}x{nz}", dims=3, arrays=shuffle_state(arrays, seed),
-               min_pos=lo, max_pos=hi, res_log2=_res_for(max(h - l for l, h in zip(lo, hi)), 4.5 * r),
+    lo = [float(v - margin) for v in pool_min]
+    hi = [float(v + margin) for v in pool_max]
+    if center_y:
+        cy = 0.5 * float(ext[1])
+        half = max(cy - lo[1], hi[1] - cy)
+        lo[1], hi[1] = cy - half, cy + half
+    if res_log2 is None:
+        # per-axis grid bounds (cells need not be cubes); resolution so that the widest cell is about 0.75 x search range
+        res_log2 = _res_for(max(h - l for l, h in zip(lo, hi)), 4.5 * r)
+    sc = Scene(name=f"dam_break_{nx}x{ny}x{nz}" + ("x2" if blocks == 2 else ""), dims=3, arrays=shuffle_state(arrays, seed),
+               min_pos=tuple(lo), max_pos=tuple(hi), res_log2=res_log2,
                basic_pbf=not adaptive, solver_iterations=4, smallest_target_radius=r)
     sc.box_min, sc.box_max = pool_walls(pool_min, pool_max, r, 3)
     return sc

@@ -29,8 +29,16 @@ METRIC = "particle-substeps/sec (search + 4-iter PBF solve)"
 UNIT = "particle-substeps/s"
 
 
-def make_scene(name):
+# one scene across N GPUs (weak scaling, 10^6 particles per GPU): the bricks are the halves of the search grid along z, then y,
+# then x (apbf_b200/multi_gpu.py), so the dam-break grows along those axes and stays symmetric about the cutting planes
+SLAB_DAM_BREAK = {2: dict(nx=100, ny=100, nz=200), 4: dict(nx=100, ny=200, nz=200, center_y=True, res_log2=8),
+                  8: dict(nx=100, ny=200, nz=200, blocks=2, center_y=True)}
+
+
+def make_scene(name, world=1):
     """BASELINE.json configs -> synthetic scenes (apbf_b200/scenes.py)"""
+    if name == "dam_break_1M" and world in SLAB_DAM_BREAK:
+        return scenes.dam_break(adaptive=True, **SLAB_DAM_BREAK[world]), dict(adaptive=True, pairs_per_particle=150, slab=True)
     if name == "dam_break_1M":      # configs[1]: pool scene dam-break, 1M particles, adaptive kernel width
         return scenes.dam_break(100, 100, 100, adaptive=True), dict(adaptive=True, pairs_per_particle=150)
     if name == "dam_break_64k":     # bounded sample of the same workload for the CPU arm
@@ -163,33 +171,59 @@ def run_gpu(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    sc, meta = make_scene(args.workload)
-    n = sc.n
+    sc, meta = make_scene(args.workload, 1 if args.replicas else world)
+    slab = world > 1 and bool(meta.get("slab"))
     ctx = apbf_b200.Context(device=local_rank, dims=sc.dims)
     ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if meta["adaptive"] else 1, mSmallestTargetRadius=sc.smallest_target_radius)
-    cap = n * meta["pairs_per_particle"]
-    sim = apbf_b200.Sim(ctx, sc, neighbor_capacity=cap, integrate=True, basic_pbf=not meta["adaptive"])
+    if slab:
+        # this rank's brick of the scene: the particles whose cell key starts with the rank's bits
+        from apbf_b200 import multi_gpu
+        owner = multi_gpu.owner_rank_of_positions(sc.arrays["position"], sc.min_pos, sc.max_pos, sc.res_log2, sc.dims, world)
+        arrays = {k: np.ascontiguousarray(v[owner == rank]) for k, v in sc.arrays.items()}
+        n = len(arrays["position"])
+        arrays["index_list"] = np.arange(n, dtype=np.uint32)
+        n_total = sc.n
+        del owner
+        ghost_cap = 400_000
+        capacity = int(n * 1.25) + ghost_cap
+    else:
+        arrays, n, n_total, capacity = sc.arrays, sc.n, sc.n * world, sc.n
+    cap = capacity * meta["pairs_per_particle"]
+    sim = apbf_b200.Sim(ctx, sc, capacity=capacity, neighbor_capacity=cap, integrate=True, basic_pbf=not meta["adaptive"])
 
     # host copies of the lists in pinned memory (the e2e leg streams them in every step)
     host = {}
     for name, dt, w in apbf_b200.FIELDS:
-        a = np.ascontiguousarray(sc.arrays[name], dtype=dt).reshape(-1, w)
+        a = np.ascontiguousarray(arrays[name], dtype=dt).reshape(-1, w)
         t = torch.from_numpy(a.view(np.int32) if dt == np.uint32 else a).pin_memory()
         host[name] = t
-    out_pos = torch.zeros((n, 4), dtype=torch.int32).pin_memory()
-    out_kw = torch.zeros((n,), dtype=torch.float32).pin_memory()
+    out_pos = torch.zeros((capacity, 4), dtype=torch.int32).pin_memory()
+    out_kw = torch.zeros((capacity,), dtype=torch.float32).pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in host.values())
-    d2h = out_pos.numel() * 4 + out_kw.numel() * 4
+    d2h = n * 16 + n * 4
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    sim.upload(host, n=n)
+    dom = None
+    if slab:
+        halo_range = float(sc.arrays["kernel_width"].max()) * (1.5 if meta["adaptive"] else 1.0) * 1.05
+        backend = multi_gpu.CudaRankBackend(sim, n, world, rank, halo_range, ghost_capacity=ghost_cap)
+        comm = multi_gpu.TorchComm(torch.device("cuda", local_rank))
+        dom = multi_gpu.SlabDomain(backend, comm, adaptive=meta["adaptive"], solver_iterations=sc.solver_iterations, integrate=True)
+
+    def step():
+        if dom is not None:
+            dom.substep()
+        else:
+            sim.substep(1)
+
     # ---- device-resident throughput ----------------------------------------------------------------------------------
-    sim.upload(host)
     for _ in range(args.warmup):
-        sim.substep(1)
+        step()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ctx.launch_count
@@ -198,7 +232,7 @@ def run_gpu(args, rank, world, local_rank):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        sim.substep(1)
+        step()
     e1.record()
     barrier()
     ctx.profile(False)
@@ -206,10 +240,11 @@ def run_gpu(args, rank, world, local_rank):
     launches = ctx.launch_count - launches0
     prof = ctx.profile_read()
     stats = sim.stats()
+    slab_stats = dict(dom.stats, halo_bytes=comm.bytes_sent, messages=comm.messages) if dom is not None else None
     if meta["adaptive"]:
         # the fused search never builds the unpruned list; one more (untimed) substep counts what it would have held
         ctx.set_search_stats(True)
-        sim.substep(1)
+        step()
         stats = dict(stats, pairs_searched=sim.stats()["pairs_searched"])
         ctx.set_search_stats(False)
     clocks = sampler.stop() if sampler else None
@@ -219,15 +254,21 @@ def run_gpu(args, rank, world, local_rank):
         ms = float(t.item())
 
     # ---- end to end: host buffers in, host buffers out, every step ---------------------------------------------------
+    def e2e_step():
+        sim.upload(host, n=n)
+        if dom is not None:
+            dom.n_own, dom.gid_base = n, 0     # the uploaded brick is the initial one again
+            backend.set_counts(n, n, 0)
+        step()
+        sim.download({"position": out_pos, "kernel_width": out_kw})   # synchronises
+
     e2e_steps = 0 if args.no_e2e else max(3, min(args.steps, 20))
     for _ in range(2 if e2e_steps else 0):
-        sim.upload(host); sim.substep(1); sim.download({"position": out_pos, "kernel_width": out_kw})
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        sim.upload(host)
-        sim.substep(1)
-        sim.download({"position": out_pos, "kernel_width": out_kw})   # synchronises
+        e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -259,7 +300,7 @@ def run_gpu(args, rank, world, local_rank):
                   **({"gbs": round(per_launch[k] / (v[0] / v[1] * 1e-3) / 1e9, 1)} if k in per_launch else {})}
               for k, v in timed.items()}
 
-    value = n * world * args.steps / (ms * 1e-3)
+    value = n_total * args.steps / (ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -267,11 +308,14 @@ def run_gpu(args, rank, world, local_rank):
         "config": {"workload": args.workload, "scene": sc.name, "particles_per_gpu": n, "adaptive_kernel_width": meta["adaptive"],
                    "solver_iterations": sc.solver_iterations, "search": "green", "res_log2": sc.res_log2,
                    "pairs_searched": stats["pairs_searched"], "pairs_kept": stats["pairs_kept"],
-                   "pairs_unmirrored": stats["pairs_unmirrored"], "multi_gpu": "independent replicas" if world > 1 else "single",
+                   "pairs_unmirrored": stats["pairs_unmirrored"],
+                   "multi_gpu": "single" if world == 1 else ("one scene in bricks (top key bits), halo exchange over NCCL send/recv" if slab
+                                                             else "independent replicas"),
+                   **({"particles_total": n_total, "slab": slab_stats} if slab else {}),
                    "l2": "working set (lists + pair list) exceeds the 126 MB L2" if (76 * n + 8 * stats["pairs_searched"]) > 126e6
                          else "working set fits L2; no flush between steps"},
         "gpu_launches": launches,
-        "e2e": {"value": n * world * e2e_steps / e2e_s if e2e_steps else None, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": n_total * e2e_steps / e2e_s if e2e_steps else None, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
@@ -303,6 +347,7 @@ def main():
     ap.add_argument("--workload", default="dam_break_1M")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: N independent copies of the 1-GPU scene instead of one scene in bricks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
