@@ -22,6 +22,7 @@ numpy/oracle backend over gloo to check this host logic without a GPU (tests/tes
 plumbing only.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -42,6 +43,8 @@ class TorchComm:
         self.device = device if device is not None else torch.device("cpu")
         self.bytes_sent = 0
         self.messages = 0
+        # APBF_MG_FLAT=1: one all_to_all per exchange instead of a send/recv pair per neighbour (measured slower at 2 GPUs)
+        self.use_all_to_all = dist.is_initialized() and dist.get_backend() == "nccl" and bool(os.environ.get("APBF_MG_FLAT"))
 
     def all_gather_counts(self, counts):
         """counts: list[world] of ints on this rank -> matrix m[src][dst]"""
@@ -51,6 +54,16 @@ class TorchComm:
         out = [self.torch.zeros_like(t) for _ in range(self.world)]
         self.dist.all_gather(out, t)
         return [o.tolist() for o in out]
+
+    def all_to_all(self, buf, send_counts, recv_counts, words):
+        """one collective instead of a send/recv pair per neighbour: buf [sum(send_counts), words] ordered by destination ->
+        [sum(recv_counts), words] ordered by source"""
+        torch, dist = self.torch, self.dist
+        out = torch.empty((int(sum(recv_counts)), words), dtype=torch.int32, device=self.device)
+        dist.all_to_all_single(out, buf, [int(c) for c in recv_counts], [int(c) for c in send_counts])
+        self.bytes_sent += buf.numel() * 4
+        self.messages += sum(1 for c in send_counts if c)
+        return out
 
     def exchange(self, send, recv_counts, words):
         """send: {rank: int32 tensor [count, words]}, recv_counts: {rank: count} -> {rank: int32 tensor [count, words]}"""
@@ -78,10 +91,24 @@ class SlabDomain:
         self.n_own = backend.n_owned()
         self.gid_base = 0
         self.stats = dict(migrated=0, ghosts=0)
+        self.timing = {} if os.environ.get("APBF_MG_TIMING") and hasattr(backend, "torch") else None
+        # device backends pack every destination in one go and exchange with a single all_to_all (NCCL); the CPU test
+        # backend keeps the pairwise send/recv form (gloo)
+        self.flat = hasattr(backend, "pack_all") and getattr(comm, "use_all_to_all", False)
+        if self.flat:
+            backend.flat_only = True
 
     # ---- one exchange of `what` for the current send lists / ghost slots ------------------------------------------------------
     def _refresh_ghosts(self, what):
         if self.world == 1:
+            return
+        if self.flat:
+            # all destinations packed by one kernel, one all_to_all, all ghosts unpacked by one kernel
+            n_ghost = sum(self.ghost_counts.values())
+            if self.comm.world > 1:
+                recv = self.comm.all_to_all(self.b.pack_all(what), [0 if r == self.rank else self.send_counts[r] for r in range(self.world)],
+                                            [self.ghost_counts.get(r, 0) for r in range(self.world)], WORDS[what])
+                self.b.unpack(what, 0, n_ghost, recv)
             return
         send = {r: self.b.pack(what, r) for r in range(self.world) if r != self.rank and self.send_counts[r]}
         recv = self.comm.exchange(send, self.ghost_counts, WORDS[what])
@@ -92,15 +119,32 @@ class SlabDomain:
                 self.b.unpack(what, off, c, recv[r])
             off += c
 
+    def _mark(self, name):
+        """APBF_MG_TIMING=1: synchronised wall time per section of the substep (diagnostics, serialises the pipeline)"""
+        if self.timing is None:
+            return
+        import time
+        self.b.torch.cuda.synchronize()
+        now = time.perf_counter()
+        self.timing[name] = self.timing.get(name, 0.0) + (now - self._t_last)
+        self._t_last = now
+
     def substep(self):
         b, me, W = self.b, self.rank, self.world
+        if self.timing is not None:
+            import time
+            b.torch.cuda.synchronize()
+            self._t_last = time.perf_counter()
         b.set_counts(self.n_own, self.n_own, self.gid_base)          # ghosts of the last substep are dropped
         if self.integrate:
             b.integrate()
+        self._mark("integrate")
         if W > 1:
             # ---- ROUTE ---------------------------------------------------------------------------------------------------
             counts = b.route()                                        # host sync 1
+            self._mark("route")
             m = self.comm.all_gather_counts(counts)
+            self._mark("route_counts")
             first = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
             send = {r: b.pack_state(int(first[r]), int(counts[r])) for r in range(W) if r != me and counts[r]}
             recv = self.comm.exchange(send, {r: m[r][me] for r in range(W) if r != me}, STATE_WORDS)
@@ -109,9 +153,12 @@ class SlabDomain:
             self.stats["migrated"] = int(sum(counts) - counts[me])
             self.n_own, self.gid_base = int(owned[me]), int(sum(owned[:me]))
             b.set_counts(self.n_own, self.n_own, self.gid_base)
+            self._mark("route_exchange")
             # ---- HALO ----------------------------------------------------------------------------------------------------
             hc = b.halo_lists()                                       # host sync 2
+            self._mark("halo_lists")
             mh = self.comm.all_gather_counts(hc)
+            self._mark("halo_counts")
             self.send_counts = [int(c) for c in hc]
             self.ghost_counts = {r: int(mh[r][me]) for r in range(W) if r != me and mh[r][me]}
             n_ghost = sum(self.ghost_counts.values())
@@ -119,21 +166,30 @@ class SlabDomain:
             b.begin_ghosts(n_ghost)
             self._refresh_ghosts(HALO)
             self.stats["ghosts"] = n_ghost
+            self._mark("halo_exchange")
         b.search()
+        self._mark("search")
         if W > 1:
             b.remap_after_search(self.send_counts, sum(self.ghost_counts.values()))
         if self.adaptive:
             b.spread()
             self._refresh_ghosts(KW)
+        self._mark("remap_kw")
         b.prepare()
         for it in range(self.iters):
             b.iter_begin(it)
+            self._mark("iter_begin")
             self._refresh_ghosts(P4)
+            self._mark("x_p4")
             b.density_lambda()
+            self._mark("density_lambda")
             self._refresh_ghosts(LAMBDA)
+            self._mark("x_lambda")
             b.apply_delta()
+            self._mark("apply_delta")
         b.final_commit()
         b.set_counts(self.n_own, self.n_own, self.gid_base)
+        self._mark("final")
 
 
 class CudaRankBackend:
@@ -153,6 +209,8 @@ class CudaRankBackend:
         self.send_ids = torch.zeros((world, self.cap_per_dest), dtype=torch.int32, device=dev)
         self.ghost_ids = torch.zeros(max(self.cap_per_dest * max(world - 1, 1), 1), dtype=torch.int32, device=dev)
         self.send_counts = [0] * world
+        self.send_flat = None
+        self.flat_only = False   # set by SlabDomain when every exchange goes through pack_all
         self.ghost_first = 0
         self._ck(self.lib.apbf_sim_mg_enable(sim.handle, rank, world, C.c_float(halo_range)))
 
@@ -206,6 +264,7 @@ class CudaRankBackend:
         if max(c) > self.cap_per_dest:
             raise RuntimeError(f"halo send list overflow: {max(c)} > capacity {self.cap_per_dest}")
         self.send_counts = c
+        self.send_flat = None
         return c
 
     def begin_ghosts(self, n_ghost):
@@ -220,14 +279,34 @@ class CudaRankBackend:
         self._ck(self.lib.apbf_sim_mg_pack(self.sim.handle, what, self.send_ids[dest].data_ptr(), n, out.data_ptr()))
         return out
 
+    def _flat_ids(self):
+        if self.send_flat is None:   # send lists of all destinations, destination after destination
+            parts = [self.send_ids[r, : self.send_counts[r]] for r in range(self.world) if r != self.rank and self.send_counts[r]]
+            self.send_flat = self.torch.cat(parts) if parts else self.torch.zeros(0, dtype=self.torch.int32, device=self.dev)
+        return self.send_flat
+
+    def pack_all(self, what):
+        ids = self._flat_ids()
+        n = ids.numel()
+        out = self.torch.empty((n, WORDS[what]), dtype=self.torch.int32, device=self.dev)
+        if n:
+            self._ck(self.lib.apbf_sim_mg_pack(self.sim.handle, what, ids.data_ptr(), n, out.data_ptr()))
+        return out
+
     def unpack(self, what, ghost_offset, count, buf):
         ids = self.ghost_ids.data_ptr() + 4 * ghost_offset
         self._ck(self.lib.apbf_sim_mg_unpack(self.sim.handle, what, ids, self.ghost_first + ghost_offset, count, buf.data_ptr()))
 
     def remap_after_search(self, send_counts, n_ghost):
-        for r in range(self.world):
-            if r != self.rank and send_counts[r]:
-                self._ck(self.lib.apbf_sim_mg_remap(self.sim.handle, self.send_ids[r].data_ptr(), send_counts[r], 0xFFFFFFFF))
+        if self.flat_only:      # one remap over the concatenated send lists
+            ids = self._flat_ids()
+            if ids.numel():
+                self._ck(self.lib.apbf_sim_mg_remap(self.sim.handle, ids.data_ptr(), ids.numel(), 0xFFFFFFFF))
+        else:
+            self.send_flat = None
+            for r in range(self.world):
+                if r != self.rank and send_counts[r]:
+                    self._ck(self.lib.apbf_sim_mg_remap(self.sim.handle, self.send_ids[r].data_ptr(), send_counts[r], 0xFFFFFFFF))
         self._ck(self.lib.apbf_sim_mg_remap(self.sim.handle, self.ghost_ids.data_ptr(), n_ghost, self.ghost_first))
 
 

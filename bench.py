@@ -66,8 +66,10 @@ def algorithmic_bytes(n, p_searched, p_kept, cells, bits, iters, adaptive):
         "hash_sort": 16 * n + 4 * n + 16 * n * passes,
         "reorder": 152 * n,
         "cell_ranges": 4 * n + 8 * cells,
-        "emit_count": 16 * n + 4 * n + 8 * cells,
-        "emit_fill": 16 * n + 4 * n + 8 * cells + 8 * p_searched,
+        # adaptive: search and spread_kernel_width run fused (one pass of tests, only the kept pairs are written, first as
+        # 8-byte stream entries and then as the grouped list); fixed widths: the same with kept == searched
+        "emit_count": 16 * n + 4 * n + 8 * cells + 8 * p_kept,
+        "emit_fill": 8 * p_kept + 8 * p_kept,
         "kw_spread": 8 * p_searched + 12 * n,
         "kw_compact": 8 * p_searched + 8 * p_kept,
         "box_collision": 36 * n,
@@ -241,6 +243,10 @@ def run_gpu(args, rank, world, local_rank):
     prof = ctx.profile_read()
     stats = sim.stats()
     slab_stats = dict(dom.stats, halo_bytes=comm.bytes_sent, messages=comm.messages) if dom is not None else None
+    if dom is not None and dom.timing is not None and rank == 0:
+        tot = sum(dom.timing.values())
+        sys.stderr.write("slab sections (ms/substep, serialised): " + ", ".join(
+            f"{k} {v / (args.steps + args.warmup) * 1e3:.3f}" for k, v in dom.timing.items()) + f" | total {tot / (args.steps + args.warmup) * 1e3:.3f}\n")
     if meta["adaptive"]:
         # the fused search never builds the unpruned list; one more (untimed) substep counts what it would have held
         ctx.set_search_stats(True)
