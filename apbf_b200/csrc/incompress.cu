@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
 
 // ---- T2 -------------------------------------------------------------------------------------------------------------------------
 template <int GK>
-__global__ void __launch_bounds__(SWEEP_THREADS) k_apply_delta(sweep_args A)
+__global__ void __launch_bounds__(SWEEP_THREADS, 4) k_apply_delta(sweep_args A)
 {
 	const uint32_t n = *A.len;
 	const uint32_t n_own = min(n, A.misc[MW_N_OWNED]); // a ghost's segment holds only unmirrored pairs onto owned particles: push part only
@@ -456,7 +456,9 @@ int apbf_solver_iteration(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors
 		else k_begin_iteration<false, false><<<egrid, 256, 0, st>>>(A);
 		APBF_LAUNCHED(ctx);
 	}
-	const unsigned grid = apbf_grid(ctx, n_cap, SWEEP_THREADS, 8);
+	// one 256-particle tile per CTA up to 64 CTAs per SM: the hardware scheduler evens out the segments' lengths (a grid of
+	// exactly-resident CTAs with a static tile stride left a third of the warp slots idle at the tail)
+	const unsigned grid = apbf_grid(ctx, n_cap, SWEEP_THREADS, 64);
 	if (run_all || (flags & ITER_RUN_T1)) {
 		apbf_prof_scope ps(ctx, PROF_DENSITY_LAMBDA);
 		switch (A.s.mHeightKernelId) {

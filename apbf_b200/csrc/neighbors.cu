@@ -643,9 +643,11 @@ k_green_stream(const emit_args A)
 				if (diff) { blk_len += (uint32_t)__ffs(diff) - 1u; break; }
 				blk_len += 32u;
 			}
-			for (uint32_t c0 = 0; c0 < blk_len; c0 += 32u) {
+			// chunks of equal size: 40 particles are 20 + 20, not 32 + 8 (a chunk costs a candidate walk whatever its size)
+			const uint32_t n_chunks = (blk_len + 31u) >> 5, chunk_len = (blk_len + n_chunks - 1u) / n_chunks;
+			for (uint32_t c0 = 0; c0 < blk_len; c0 += chunk_len) {
 				// ---- one chunk: queries first .. first + cnt, lane = query ----------------------------------------------------
-				const uint32_t first = blk_first + c0, cnt = min(32u, blk_len - c0);
+				const uint32_t first = blk_first + c0, cnt = min(chunk_len, blk_len - c0);
 				const uint32_t id = first + lane;
 				const bool valid = lane < cnt;
 				float4 me = make_float4(0.f, 0.f, 0.f, -1.0f);
