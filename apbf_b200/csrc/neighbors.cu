@@ -591,7 +591,7 @@ __device__ __forceinline__ void chunk_tests(const float4* __restrict__ sq, const
 }
 
 template <int VARIANT, int DIMS, bool STATS>
-__global__ void __launch_bounds__(EMIT_WARPS * 32, 3)
+__global__ void __launch_bounds__(EMIT_WARPS * 32, 4)
 k_green_stream(const emit_args A)
 {
 	constexpr bool FUSED = (VARIANT & EMIT_FUSED) != 0, MG = (VARIANT & EMIT_MG) != 0;
@@ -1233,7 +1233,7 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 	// pairs (:64-74): count, scan, fill
 	k_clear_search_words<<<1, 1, 0, st>>>(misc);
 	APBF_LAUNCHED(ctx);
-	const unsigned egrid = apbf_grid(ctx, n_cap, EMIT_WARPS * 32, 6);
+	const unsigned egrid = apbf_grid(ctx, n_cap, EMIT_WARPS * 32, 4);
 	static const int cull = getenv("APBF_NO_CULL") ? 0 : 1; // debugging aid: walk every cell of the union box
 	const int variant = (fuse_kw ? EMIT_FUSED : 0) | (ctx->mg_enabled ? EMIT_MG : 0);
 	emit_args A;
