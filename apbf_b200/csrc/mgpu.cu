@@ -14,6 +14,7 @@
 // owners' lambdas refresh them before the apply sweep.  A ghost's own pair list only holds the unmirrored pairs onto owned
 // particles (the scatter part of the sweeps); everything else about a ghost comes from its owner.
 #include "keys.cuh"
+#include "neighbors.cuh"
 #include "sim.cuh"
 #include "solver.cuh"
 #include "sort.cuh"
@@ -293,12 +294,14 @@ int apbf_sim_mg_route(apbf_sim* sim, uint32_t* counts_dev)
 	APBF_LAUNCHED(ctx);
 	APBF_TRY(apbf_radix_sort_pairs(ctx, dest, nullptr, sdest, perm, len, cap, lw > 0 ? lw : 1));
 	apbf_fluid& f = sim->fluid;
-	struct { apbf_array* a; uint32_t stride; } arrays[] = {
-		{ &f.particle.position, 16 }, { &f.particle.velocity, 16 }, { &f.particle.pos_backup, 16 }, { &f.particle.inverse_mass, 4 },
-		{ &f.particle.radius, 4 }, { &f.particle.transferring, 4 }, { &f.target_radius, 4 }, { &f.kernel_width, 4 },
-		{ &f.boundariness, 4 }, { &f.boundary_distance, 4 },
-	};
-	for (auto& it : arrays) APBF_TRY(apbf_launch_gather(ctx, it.a->data, it.a->reorder_out, perm, len, cap, it.stride));
+	apbf_reorder_table t; // every list of the scene in one pass (16-byte loads), like the search's own reorder
+	memset(&t, 0, sizeof t);
+	apbf_array* a16[3] = { &f.particle.position, &f.particle.velocity, &f.particle.pos_backup };
+	apbf_array* a4[7] = { &f.particle.inverse_mass, &f.particle.radius, &f.particle.transferring, &f.target_radius, &f.kernel_width,
+	                      &f.boundariness, &f.boundary_distance };
+	for (auto a : a16) { t.src16[t.n16] = (const int4*)a->data; t.dst16[t.n16] = (int4*)a->reorder_out; t.n16++; }
+	for (auto a : a4) { t.src4[t.n4] = (const uint32_t*)a->data; t.dst4[t.n4] = (uint32_t*)a->reorder_out; t.n4++; }
+	APBF_TRY(apbf_launch_reorder(ctx, t, perm, len, cap));
 	APBF_TRY(apbf_write_sequence(ctx, (uint32_t*)f.particle.index_list.reorder_out, len, cap, 0u, 1u, 1u));
 	apbf_sim_swap_buffers(sim);
 	return APBF_OK;

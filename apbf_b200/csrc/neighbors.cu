@@ -18,13 +18,7 @@
 namespace {
 
 // ---- fused reorder of all hidden arrays -------------------------------------------------------------------------------
-struct reorder_table {
-	int          n16, n4;
-	const int4*  src16[4];
-	int4*        dst16[4];
-	const uint32_t* src4[8];
-	uint32_t*    dst4[8];
-};
+using reorder_table = apbf_reorder_table;
 
 __global__ void __launch_bounds__(256) k_reorder(reorder_table t, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ len)
 {
@@ -43,6 +37,17 @@ __global__ void __launch_bounds__(256) k_reorder(reorder_table t, const uint32_t
 		for (int a = 0; a < 8; a++) if (a < t.n4) t.dst4[a][i] = v4[a];
 	}
 }
+
+} // namespace
+
+int apbf_launch_reorder(apbf_ctx* ctx, const apbf_reorder_table& t, const uint32_t* perm, const uint32_t* len, uint32_t cap)
+{
+	k_reorder<<<apbf_grid(ctx, cap, 256), 256, 0, ctx->stream>>>(t, perm, len);
+	APBF_LAUNCHED(ctx);
+	return APBF_OK;
+}
+
+namespace {
 
 // ---- index list after the hidden permutation (indexed_list.h:289-308 + :276-286 for a permutation edit) ------------------
 __global__ void k_mark_members(const uint32_t* __restrict__ index_list, const uint32_t* __restrict__ len, uint32_t* __restrict__ mark)

@@ -30,3 +30,13 @@ __device__ __forceinline__ uint32_t apbf_kw_influence(float orig, float dist)
 
 // uint_to_float_but_gradual over the fixed-point widths in SLOT_KWFX (solver.cu; tail of spread_kernel_width::apply)
 int apbf_kw_finish(apbf_ctx* ctx, apbf_fluid* fluid, uint32_t* out_kw_fixed);
+
+// one gather of up to four 16-byte and eight 4-byte arrays through the same permutation: dst[i] = src[perm[i]], i < *len
+struct apbf_reorder_table {
+	int          n16, n4;
+	const int4*  src16[4];
+	int4*        dst16[4];
+	const uint32_t* src4[8];
+	uint32_t*    dst4[8];
+};
+int apbf_launch_reorder(apbf_ctx* ctx, const apbf_reorder_table& t, const uint32_t* perm, const uint32_t* len, uint32_t cap);

@@ -43,16 +43,25 @@ class TorchComm:
         self.device = device if device is not None else torch.device("cpu")
         self.bytes_sent = 0
         self.messages = 0
-        # APBF_MG_FLAT=1: one all_to_all per exchange instead of a send/recv pair per neighbour (measured slower at 2 GPUs)
-        self.use_all_to_all = dist.is_initialized() and dist.get_backend() == "nccl" and bool(os.environ.get("APBF_MG_FLAT"))
+        # one all_to_all per exchange instead of a send/recv pair per neighbour: 6 % faster at 4 GPUs, no gain with a single
+        # neighbour (APBF_MG_FLAT=0/1 overrides)
+        flat = os.environ.get("APBF_MG_FLAT")
+        self.use_all_to_all = dist.is_initialized() and dist.get_backend() == "nccl" and (self.world > 2 if flat is None else flat == "1")
 
     def all_gather_counts(self, counts):
-        """counts: list[world] of ints on this rank -> matrix m[src][dst]"""
-        t = self.torch.tensor([int(c) for c in counts], dtype=self.torch.int64, device=self.device)
+        """counts: list[world] of ints, or a device tensor of them (no host round trip before the collective)
+        -> matrix m[src][dst] on the host; the one read-back synchronises"""
+        torch = self.torch
+        if not torch.is_tensor(counts):
+            counts = torch.tensor([int(c) for c in counts], dtype=torch.int32, device=self.device)
         if self.world == 1:
-            return [t.tolist()]
-        out = [self.torch.zeros_like(t) for _ in range(self.world)]
-        self.dist.all_gather(out, t)
+            return [counts.tolist()]
+        if counts.is_cuda:
+            out = torch.empty(self.world * counts.numel(), dtype=counts.dtype, device=counts.device)
+            self.dist.all_gather_into_tensor(out, counts.contiguous())
+            return out.view(self.world, -1).tolist()
+        out = [torch.zeros_like(counts) for _ in range(self.world)]
+        self.dist.all_gather(out, counts)
         return [o.tolist() for o in out]
 
     def all_to_all(self, buf, send_counts, recv_counts, words):
@@ -141,9 +150,10 @@ class SlabDomain:
         self._mark("integrate")
         if W > 1:
             # ---- ROUTE ---------------------------------------------------------------------------------------------------
-            counts = b.route()                                        # host sync 1
+            raw = b.route()                                           # (device counts: no read-back before the collective)
             self._mark("route")
-            m = self.comm.all_gather_counts(counts)
+            m = self.comm.all_gather_counts(raw)                      # host sync 1
+            counts = [int(c) for c in m[me]]
             self._mark("route_counts")
             first = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
             send = {r: b.pack_state(int(first[r]), int(counts[r])) for r in range(W) if r != me and counts[r]}
@@ -155,11 +165,13 @@ class SlabDomain:
             b.set_counts(self.n_own, self.n_own, self.gid_base)
             self._mark("route_exchange")
             # ---- HALO ----------------------------------------------------------------------------------------------------
-            hc = b.halo_lists()                                       # host sync 2
+            raw = b.halo_lists()
             self._mark("halo_lists")
-            mh = self.comm.all_gather_counts(hc)
+            mh = self.comm.all_gather_counts(raw)                     # host sync 2
             self._mark("halo_counts")
-            self.send_counts = [int(c) for c in hc]
+            self.send_counts = [int(c) for c in mh[me]]
+            if hasattr(b, "set_send_counts"):
+                b.set_send_counts(self.send_counts)
             self.ghost_counts = {r: int(mh[r][me]) for r in range(W) if r != me and mh[r][me]}
             n_ghost = sum(self.ghost_counts.values())
             b.set_counts(self.n_own, self.n_own + n_ghost, self.gid_base)
@@ -206,6 +218,7 @@ class CudaRankBackend:
         self.dev = dev
         self.cap_per_dest = int(ghost_capacity)
         self.counts_dev = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.halo_counts_dev = torch.zeros(8, dtype=torch.int32, device=dev)
         self.send_ids = torch.zeros((world, self.cap_per_dest), dtype=torch.int32, device=dev)
         self.ghost_ids = torch.zeros(max(self.cap_per_dest * max(world - 1, 1), 1), dtype=torch.int32, device=dev)
         self.send_counts = [0] * world
@@ -238,7 +251,7 @@ class CudaRankBackend:
 
     def route(self):
         self._ck(self.lib.apbf_sim_mg_route(self.sim.handle, self.counts_dev.data_ptr()))
-        return self.counts_dev[: self.world].tolist()                # synchronises
+        return self.counts_dev[: self.world]                         # stays on the device until the counts are all-gathered
 
     def pack_state(self, first, count):
         out = self.torch.empty((count, STATE_WORDS), dtype=self.torch.int32, device=self.dev)
@@ -259,13 +272,14 @@ class CudaRankBackend:
         self._ck(self.lib.apbf_sim_mg_swap(self.sim.handle))
 
     def halo_lists(self):
-        self._ck(self.lib.apbf_sim_mg_halo_lists(self.sim.handle, self.send_ids.data_ptr(), self.cap_per_dest, self.counts_dev.data_ptr()))
-        c = self.counts_dev[: self.world].tolist()                    # synchronises
+        self._ck(self.lib.apbf_sim_mg_halo_lists(self.sim.handle, self.send_ids.data_ptr(), self.cap_per_dest, self.halo_counts_dev.data_ptr()))
+        return self.halo_counts_dev[: self.world]
+
+    def set_send_counts(self, c):
         if max(c) > self.cap_per_dest:
             raise RuntimeError(f"halo send list overflow: {max(c)} > capacity {self.cap_per_dest}")
-        self.send_counts = c
+        self.send_counts = list(c)
         self.send_flat = None
-        return c
 
     def begin_ghosts(self, n_ghost):
         if n_ghost > self.ghost_ids.numel():
