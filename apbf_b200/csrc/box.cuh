@@ -20,6 +20,14 @@ __device__ __forceinline__ void box_push(float& px, float& py, float& pz, uint32
                                          const float4* __restrict__ bmax, uint32_t n_boxes)
 {
 	for (uint32_t i = 0; i < n_boxes; i++) {
+		{
+			// A push needs the particle strictly inside the box grown by radius + jitter on every axis, and the jitter is
+			// 0.05 * hash with hash in [0, 1).  Outside the box grown by radius + 0.06 nothing can happen: skip the two
+			// position hashes (most particles are nowhere near a wall).  0.01 covers the roundings many times over.
+			const float4 lo = __ldg(bmin + i), hi = __ldg(bmax + i);
+			const float m = radius + 0.06f;
+			if (px < lo.x - m || py < lo.y - m || pz < lo.z - m || px > hi.x + m || py > hi.y + m || pz > hi.z + m) continue;
+		}
 		const vec3f h0 = hash31((float)id * px - py - pz);
 		const vec3f h1 = hash31((float)id * py + px + pz);
 		const float4 lo = __ldg(bmin + i), hi = __ldg(bmax + i);

@@ -298,10 +298,17 @@ def run_gpu(args, rank, world, local_rank):
     bits = 4 * -(-(sc.res_log2 * sc.dims + 1) // 4)
     per_launch, substep_bytes = algorithmic_bytes(n, stats["pairs_searched"], stats["pairs_kept"], cells, bits,
                                                  sc.solver_iterations, meta["adaptive"])
+    traffic, traffic_src = None, None
+    try:   # per-launch DRAM bytes of the passes from the committed ncu --set full capture of this workload (tools/ncu_traffic.py)
+        tj = json.load(open(os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")))
+    except (OSError, ValueError):
+        tj = None
     timed = {k: v for k, v in prof.items() if v[1] > 0}
     top = max((k for k in timed if k in per_launch), key=lambda k: timed[k][0])
     top_ms = timed[top][0] / timed[top][1]
     achieved = per_launch[top] / (top_ms * 1e-3) / 1e9
+    if tj and world == 1 and top in tj.get("passes", {}):
+        traffic, traffic_src = tj["passes"][top]["dram_bytes_per_launch"], tj["source"]
     passes = {k: {"ms_per_launch": round(v[0] / v[1], 4), "launches": v[1], "share": round(v[0] / ms, 4),
                   **({"gbs": round(per_launch[k] / (v[0] / v[1] * 1e-3) / 1e9, 1)} if k in per_launch else {})}
               for k, v in timed.items()}
@@ -324,7 +331,7 @@ def run_gpu(args, rank, world, local_rank):
         "e2e": {"value": n_total * e2e_steps / e2e_s if e2e_steps else None, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                      "algorithmic_bytes_per_launch": per_launch[top], "ms_per_launch": top_ms,
                      "substep": {"algorithmic_bytes": substep_bytes, "achieved": substep_bytes / (ms / args.steps * 1e-3) / 1e9,
                                  "frac": substep_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}},

@@ -30,7 +30,7 @@ tail -2 "$OUT/ncu_launches.log"
 
 echo "== ncu --set full on the sweeps and the emit"
 timeout 1200 ncu --set full --clock-control none --import-source on \
-    -k regex:'k_density_lambda|k_apply_delta|k_green_emit|k_regroup|k_onesweep|k_reorder' -s 36 -c 16 \
+    -k regex:'k_density_lambda|k_apply_delta|k_green_stream|k_regroup|k_onesweep|k_reorder|k_begin_iteration' -s 45 -c 18 \
     -o "$OUT/prof" -f python bench.py --gpus 1 --steps 1 --warmup 3 --workload "$WL" --no-cpu-baseline --no-e2e > "$OUT/ncu_full.log" 2>&1
 tail -2 "$OUT/ncu_full.log"
 ls -la "$OUT"
