@@ -83,6 +83,10 @@ class Context:
     def launch_count(self):
         return int(self.lib.apbf_ctx_launch_count(self.handle))
 
+    def set_stream_blocks(self, max_blocks=0):
+        """testing aid: cap the hit stream of the pair emit (0 = automatic); an exhausted stream falls back to the two-pass fill"""
+        _check(self, self.lib.apbf_ctx_set_stream_blocks(self.handle, int(max_blocks)))
+
     def set_search_stats(self, enable=True):
         """fused search + spread: also count the pairs of the (never materialised) unpruned list"""
         _check(self, self.lib.apbf_ctx_set_search_stats(self.handle, int(enable)))

@@ -86,6 +86,7 @@ struct apbf_ctx {
 	// a following spread_kernel_width prunes pairs, which can turn a mirrored pair into an unmirrored one: ghosts then
 	// keep ALL their pairs onto owned particles until the prune has decided
 	bool            mg_ghost_all_pairs = false;
+	uint32_t        stream_blocks_cap = 0; // testing aid: upper bound on the hit stream's blocks (0 = automatic)
 	bool            search_stats = false; // fused search + spread: count the pairs of the unpruned list as well
 
 	void* scratch_get(int slot, size_t bytes);

@@ -161,6 +161,12 @@ int apbf_ctx_set_dimensions(apbf_ctx* ctx, int dims)
 }
 
 uint64_t apbf_ctx_launch_count(apbf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int apbf_ctx_set_stream_blocks(apbf_ctx* ctx, uint32_t max_blocks)
+{
+	if (!ctx) return APBF_ERR_INVALID;
+	ctx->stream_blocks_cap = max_blocks;
+	return APBF_OK;
+}
 int apbf_ctx_set_search_stats(apbf_ctx* ctx, int enable)
 {
 	if (!ctx) return APBF_ERR_INVALID;

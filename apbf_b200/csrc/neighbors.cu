@@ -907,10 +907,11 @@ k_green_stream(const emit_args A)
 // second half of the one-pass emit: every entry of the hit stream -> offsets[id] + rank
 __global__ void __launch_bounds__(SB_ENTRIES)
 k_regroup(const uint32_t* __restrict__ stream, uint32_t stream_blocks, const uint32_t* __restrict__ offsets,
-          uint32_t* __restrict__ pairs, uint32_t* __restrict__ nbl, uint32_t cap, uint32_t* misc)
+          uint32_t* __restrict__ pairs, uint32_t* __restrict__ nbl, uint32_t cap, uint32_t* misc, int no_fallback)
 {
 	if (misc[MW_STREAM_OVERFLOW] != 0u) {
-		if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(misc + MW_FLAGS, 1u); // only happens when the pair list overflows
+		// (fused + slabs has no two-pass fill behind it: raise the sticky overflow flag; needs more pairs than the list holds)
+		if (no_fallback && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(misc + MW_FLAGS, 1u);
 		return;
 	}
 	const uint32_t used = min(misc[MW_STREAM_CURSOR], stream_blocks);
@@ -1204,7 +1205,8 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 	// hit stream of the one-pass emit: every chunk of queries ends with a partly filled block, and there is at most one
 	// chunk per particle, hence capacity / 128 + particles blocks would hold any list that fits the pair buffer; the usual
 	// demand is pairs / 128 + particles / 20, and capacity / 128 + particles / 8 is what is reserved
-	const uint32_t stream_blocks = (uint32_t)std::min<size_t>((size_t)nb->capacity / SB_ENTRIES + (size_t)n_cap / 8u + 1024u, 0x7FFFFFFFu);
+	uint32_t stream_blocks = (uint32_t)std::min<size_t>((size_t)nb->capacity / SB_ENTRIES + (size_t)n_cap / 8u + 1024u, 0x7FFFFFFFu);
+	if (ctx->stream_blocks_cap) stream_blocks = std::min(stream_blocks, std::max(ctx->stream_blocks_cap, 1u));
 	uint32_t* stream = (uint32_t*)ctx->scratch_get(SLOT_STREAM, sizeof(uint32_t) * (size_t)stream_blocks * SB_WORDS);
 	if (!stream) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 
@@ -1266,7 +1268,8 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
 		if (!two_pass) {
-			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, nb->pairs, nbl, nb->capacity, misc);
+			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, nb->pairs, nbl, nb->capacity, misc,
+			                                                    variant == EMIT_FUSED_MG ? 1 : 0);
 			APBF_LAUNCHED(ctx);
 		}
 		if (variant != EMIT_FUSED_MG) { // (fused + slabs has no two-pass form: an overflow there only raises the sticky flag)

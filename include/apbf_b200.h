@@ -86,6 +86,9 @@ uint64_t apbf_ctx_launch_count(apbf_ctx* ctx);
  * on (default off) it still counts how many pairs that list would have held (apbf_sim_stats: pairs searched), at the
  * price of one more compare per distance test. */
 int  apbf_ctx_set_search_stats(apbf_ctx* ctx, int enable);
+/* Testing aid: cap the number of 128-entry blocks of the pair emit's hit stream (0 = sized from the list capacities).  A
+ * stream that runs out of blocks makes the search fall back to its two-pass fill; results do not change. */
+int  apbf_ctx_set_stream_blocks(apbf_ctx* ctx, uint32_t max_blocks);
 /* Per-pass device timing with CUDA events on the context stream (replaces measurements::record_timing_interval_*,
  * source/measurements.cpp:27-62).  apbf_ctx_profile(ctx, 1) clears and starts, (ctx, 0) stops; apbf_ctx_profile_read
  * returns the accumulated milliseconds and span count of category 0 .. n-1 (APBF_ERR_INVALID past the last one) and

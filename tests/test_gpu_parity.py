@@ -378,6 +378,82 @@ def test_fused_search_spread_matches_two_operators(gpu, orc, base_on_target_radi
     _check_incompressibility(ga, ea, L.read("position"), st.position, before)
 
 
+@pytest.mark.parametrize("fused", [False, True])
+def test_stream_overflow_falls_back_to_two_pass_fill(gpu, orc, fused):
+    """The one-pass emit writes its hits into a block stream (csrc/neighbors.cu: k_green_stream / k_regroup); when the stream
+    runs out of blocks the fill pass of the two-pass emit takes over.  Same pairs either way, bit for bit."""
+    sc = scenes.waterdrop(16, jitter=0.1) if fused else scenes.uniform_block(20, jitter=0.2, shuffle=True)
+    s = orc.default_settings()
+    s.mBaseKernelWidthOnBoundaryDistance = 0 if fused else 1
+    cap = sc.n * 700
+    st = oracle_state(orc, sc)
+    scale = 1.5 if fused else 1.0
+    epairs = orc.green_apply(st, s, sc.dims, scale, sc.min_pos, sc.max_pos, sc.res_log2, cap)
+    if fused:
+        epairs, ekw = orc.spread_kernel_width_apply(st, s, epairs)
+    ctx = gpu.Context(dims=sc.dims)
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    ctx.set_stream_blocks(40)                                # 5120 entries: far too few
+    L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=cap)
+    op = gpu.neighborhood_green_spread(ctx) if fused else gpu.neighborhood_green(ctx)
+    op.set_data(L).set_range_scale(scale).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply()
+    assert len(epairs) > 5120 and ctx.device_flags() == 0
+    assert np.array_equal(L.read_pairs(), epairs)
+    if fused:
+        assert np.array_equal(L.read("kernel_width"), st.kernel_width)
+    ctx.set_stream_blocks(0)
+
+
+def test_search_crowded_cell_and_coincident_particles(gpu, orc):
+    """hundreds of particles in one cell (blocks longer than a chunk of 32 queries), many of them at the same position
+    (distance 0, id != idN still holds), ranges from 0 to several cells"""
+    rng = np.random.default_rng(17)
+    sc = scenes.uniform_block(8, jitter=0.0, res_log2=4)   # 16 cells per axis: no search box is wider than the grid (DESIGN.md 4)
+    n = sc.n
+    pos = sc.arrays["position"]
+    pos[: n // 2, :3] = pos[0, :3]                                            # 256 coincident particles
+    pos[n // 2: 3 * n // 4, :3] = pos[0, :3] + rng.integers(-40000, 40000, (n // 4, 3)).astype(np.int32)
+    sc.arrays["pos_backup"][:] = pos
+    sc.arrays["kernel_width"] = (sc.arrays["kernel_width"] * rng.choice([0.0, 0.3, 1.0, 2.5], n)).astype(np.float32)
+    s = orc.default_settings()
+    cap = n * n
+    st = oracle_state(orc, sc)
+    epairs = orc.green_apply(st, s, 3, 1.0, sc.min_pos, sc.max_pos, sc.res_log2, cap)
+    ctx = gpu.Context()
+    L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=cap)
+    gpu.neighborhood_green(ctx).set_data(L).set_range_scale(1.0).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply()
+    assert ctx.device_flags() == 0 and len(epairs) > 50000
+    assert np.array_equal(L.read_pairs(), epairs)
+
+
+def test_fused_prune_on_the_ambiguity_band(gpu, orc):
+    """Pairs whose distance sits right at the prune cutoff max(original width, old width) (kernel_width.comp:57): the fused
+    emit decides them on the integer-difference form like the reference, not on the float positions it searches with.
+    Lattice at spacing 2 with widths 4: the neighbours at distance exactly 4 are all on the cutoff; far from the origin the two
+    distance forms round differently."""
+    sc = scenes.uniform_block(14, jitter=0.0)
+    shift = np.array([37 * 262144 + 12345, -53 * 262144 - 777, 61 * 262144 + 4242], np.int32)
+    sc.arrays["position"][:, :3] += shift
+    sc.arrays["pos_backup"][:, :3] += shift
+    sc.arrays["position"][::3, :3] += np.random.default_rng(23).integers(-2, 3, (len(sc.arrays["position"][::3]), 3)).astype(np.int32)
+    off = np.array([37.0, -53.0, 61.0], np.float32)
+    sc.min_pos = tuple(float(v) for v in (np.asarray(sc.min_pos, np.float32) + off - 1.0))
+    sc.max_pos = tuple(float(v) for v in (np.asarray(sc.max_pos, np.float32) + off + 1.0))
+    s = orc.default_settings()
+    s.mBaseKernelWidthOnBoundaryDistance = 0
+    cap = sc.n * 200
+    st = oracle_state(orc, sc)
+    epairs = orc.green_apply(st, s, 3, 1.5, sc.min_pos, sc.max_pos, sc.res_log2, cap)
+    ekept, ekw = orc.spread_kernel_width_apply(st, s, epairs)
+    assert 0 < len(ekept) < len(epairs)
+    ctx = gpu.Context()
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=cap)
+    gkw = gpu.neighborhood_green_spread(ctx).set_data(L).set_range_scale(1.5).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply(debug=True)
+    assert np.array_equal(gkw, ekw)
+    assert np.array_equal(L.read_pairs(), ekept)
+
+
 def test_box_collision_matches_oracle(gpu, orc):
     sc = scenes.uniform_block(16, jitter=0.3, shuffle=True)
     st = oracle_state(orc, sc)

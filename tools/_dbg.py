@@ -1,31 +1,36 @@
-import sys, os, numpy as np
-sys.path.insert(0, '.')
+"""debugging aid (GPU box): the crowded-cell search case, missing / extra pairs against the oracle"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import apbf_b200 as gpu
 from apbf_b200 import scenes
 from oracle import oracle as orc
-orc.build()
-sc = scenes.uniform_block(96, jitter=0.2, dims=2, shuffle=True)
-print(sc.min_pos, sc.max_pos, sc.res_log2, sc.n)
-s = orc.default_settings(); cap = sc.n*80
-st = orc.State(**{k: v.copy() for k, v in sc.arrays.items()})
-ep = orc.green_apply(st, s, 2, 1.0, sc.min_pos, sc.max_pos, sc.res_log2, cap)
-ctx = gpu.Context(dims=2)
+from test_gpu_parity import oracle_state
+
+rng = np.random.default_rng(17)
+sc = scenes.uniform_block(8, jitter=0.0, res_log2=4)
+n = sc.n
+pos = sc.arrays["position"]
+pos[: n // 2, :3] = pos[0, :3]
+pos[n // 2: 3 * n // 4, :3] = pos[0, :3] + rng.integers(-40000, 40000, (n // 4, 3)).astype(np.int32)
+sc.arrays["pos_backup"][:] = pos
+sc.arrays["kernel_width"] = (sc.arrays["kernel_width"] * rng.choice([0.0, 0.3, 1.0, 2.5], n)).astype(np.float32)
+s = orc.default_settings()
+cap = n * n
+st = oracle_state(orc, sc)
+ep = orc.green_apply(st, s, 3, 1.0, sc.min_pos, sc.max_pos, sc.res_log2, cap)
+ctx = gpu.Context()
 L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=cap)
-_ = gpu.neighborhood_green(ctx).set_data(L).set_range_scale(1.0).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply(debug=True)
-aux = _
-p = L.read_pairs()
-print(len(p), len(ep))
-ce = np.bincount(ep[:,0], minlength=sc.n); cg = np.bincount(p[:,0], minlength=sc.n)
-off = aux["pair_offsets"]; cc = np.diff(off.astype(np.int64))
-print("count-pass counts vs oracle: mismatches", int((cc != ce).sum()), "total", off[-1], "first bad", np.nonzero(cc != ce)[0][:10], cc[np.nonzero(cc != ce)[0][:10]], ce[np.nonzero(cc != ce)[0][:10]])
-bad = np.nonzero(ce != cg)[0]
-print("bad ids", len(bad), bad[:20], ce[bad[:20]], cg[bad[:20]])
-pos = L.read("position")
-print(pos[bad[:10]] / 262144.0)
-pf = pos[:, :3] / 262144.0
-for a in bad[:3]:
-    e = ep[ep[:,0]==a][:,1]; g_ = p[p[:,0]==a][:,1]
-    print("id", a, "exp", e, "got", g_)
-    for b in sorted(set(g_.tolist()) ^ set(e.tolist())):
-        print("   diff b", b, "dist", np.linalg.norm(pf[a]-pf[b]), "pos", pf[b])
-kw = L.read("kernel_width"); print("kw", kw[:5], kw.min(), kw.max())
+gpu.neighborhood_green(ctx).set_data(L).set_range_scale(1.0).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply()
+gp = L.read_pairs()
+print("res", sc.res_log2, "min", sc.min_pos, "max", sc.max_pos, "oracle", len(ep), "gpu", len(gp))
+es = set(map(tuple, ep.tolist())); gs = set(map(tuple, gp.tolist()))
+miss = sorted(es - gs); extra = sorted(gs - es)
+print("missing", len(miss), "extra", len(extra))
+p = st.position[:, :3].astype(np.float64) / 262144.0
+for a, b in miss[:20]:
+    d = np.linalg.norm(p[a] - p[b])
+    print("miss", a, b, "kw_a", st.kernel_width[a], "kw_b", st.kernel_width[b], "d", d, "pa", p[a], "pb", p[b])
+for a, b in extra[:10]:
+    print("extra", a, b)
