@@ -86,6 +86,9 @@ struct apbf_ctx {
 	// a following spread_kernel_width prunes pairs, which can turn a mirrored pair into an unmirrored one: ghosts then
 	// keep ALL their pairs onto owned particles until the prune has decided
 	bool            mg_ghost_all_pairs = false;
+	// whole-scene path (apbf_sim_*): nothing reads the public (id, idN) list between the search and the sweeps, which use the
+	// 4-byte NB list; the green search then skips the 8-byte stores (the list length is still set)
+	bool            skip_public_pairs = false;
 	uint32_t        stream_blocks_cap = 0; // testing aid: upper bound on the hit stream's blocks (0 = automatic)
 	bool            search_stats = false; // fused search + spread: count the pairs of the unpruned list as well
 

@@ -943,7 +943,7 @@ k_regroup(const uint32_t* __restrict__ stream, uint32_t stream_blocks, const uin
 #pragma unroll
 		for (int u = 0; u < U; u++) {
 			if (threadIdx.x < hdr[u].y && o[u] < cap) {
-				*(uint2*)(pairs + 2 * (size_t)o[u]) = make_uint2(id[u], word[u] & NB_ID_MASK);
+				if (pairs) *(uint2*)(pairs + 2 * (size_t)o[u]) = make_uint2(id[u], word[u] & NB_ID_MASK);
 				nbl[o[u]] = word[u];
 				n_asym += word[u] >> 31;
 			}
@@ -1268,7 +1268,7 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
 		if (!two_pass) {
-			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, nb->pairs, nbl, nb->capacity, misc,
+			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, ctx->skip_public_pairs ? nullptr : nb->pairs, nbl, nb->capacity, misc,
 			                                                    variant == EMIT_FUSED_MG ? 1 : 0);
 			APBF_LAUNCHED(ctx);
 		}

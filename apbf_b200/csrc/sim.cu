@@ -172,12 +172,14 @@ int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
 		const float scale = unit_scale ? 1.0f : 1.5f;
 		// pool.cpp:83-89.  Green search followed by spread_kernel_width runs as one fused pass (same lists, pair for pair)
 		const bool fused = adaptive && !c.use_binary_search && !ctx->mg_enabled && !sim->no_fuse;
+		ctx->skip_public_pairs = !c.use_binary_search && (fused || !adaptive); // the sweeps read NB; a separate spread rewrites the pairs
 		if (c.use_binary_search)                                                      // pool.cpp:83-84
 			APBF_TRY(apbf_neighborhood_binary_search_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, nullptr));
 		else if (fused)
 			APBF_TRY(apbf_neighborhood_green_spread_apply(ctx, &sim->fluid, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, nullptr, nullptr));
 		else
 			APBF_TRY(apbf_neighborhood_green_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, nullptr));
+		ctx->skip_public_pairs = false;
 		apbf_sim_swap_buffers(sim);
 		if (adaptive && !fused) APBF_TRY(apbf_spread_kernel_width_apply(ctx, &sim->fluid, &sim->nb, nullptr)); // pool.cpp:87-89
 		// pool.cpp:92-95: solverIterations x (box_collision, incompressibility).  Same results as calling the two

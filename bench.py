@@ -69,7 +69,7 @@ def algorithmic_bytes(n, p_searched, p_kept, cells, bits, iters, adaptive):
         # adaptive: search and spread_kernel_width run fused (one pass of tests, only the kept pairs are written, first as
         # 8-byte stream entries and then as the grouped list); fixed widths: the same with kept == searched
         "emit_count": 16 * n + 4 * n + 8 * cells + 8 * p_kept,
-        "emit_fill": 8 * p_kept + 8 * p_kept,
+        "emit_fill": 8 * p_kept + 4 * p_kept,     # stream entries in, 4-byte NB list out (the whole-scene path keeps no 8-byte list)
         "kw_spread": 8 * p_searched + 12 * n,
         "kw_compact": 8 * p_searched + 8 * p_kept,
         "box_collision": 36 * n,
