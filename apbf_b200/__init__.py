@@ -336,6 +336,31 @@ class spread_kernel_width(_Operator):
             return kwfx[:L.length()].cpu().numpy().view(np.uint32)
 
 
+class update_transfers(_Operator):
+    """pbd::update_transfers (source/update_transfers.h) with merge and split off: boundary-distance flood-fill step, nearest
+    neighbour, target radius, boundary-distance decay, boundariness threshold (find_split_and_merge_1/2/3.comp)"""
+
+    def set_data(self, lists, transfers=None):
+        self.lists = lists
+        return self
+
+    def apply(self, debug=False):
+        torch = _torch()
+        L = self.lists
+        fl, nb = L.fluid(), L.neighbors()
+        nearest = torch.zeros(L.capacity, dtype=torch.int32, device=L.words.device) if debug else None
+        _check(self.ctx, self.lib.apbf_update_transfers_apply(self.ctx.handle, C.byref(fl), C.byref(nb),
+                                                              nearest.data_ptr() if debug else None))
+        if debug:
+            return nearest[:L.length()].cpu().numpy().view(np.uint32)
+
+
+def kernel_width_from_boundary_distance(ctx, lists):
+    """pool.cpp:77-80: shader_provider::uint_to_float_with_indexed_lower_bound on boundary_distance -> kernel_width"""
+    fl = lists.fluid()
+    _check(ctx, ctx.lib.apbf_kernel_width_from_boundary_distance(ctx.handle, C.byref(fl)))
+
+
 class box_collision(_Operator):
     """pbd::box_collision (source/box_collision.h:8-18)"""
 
@@ -401,7 +426,7 @@ class Sim:
     upload()/download() move the lists between host memory and the device (the end-to-end path)."""
 
     def __init__(self, ctx, scene, capacity=None, neighbor_capacity=None, use_binary_search=False, integrate=False,
-                 dt=1.0 / 60.0, accel=(0.0, -10.0, 0.0), solver_iterations=None, basic_pbf=None):
+                 dt=1.0 / 60.0, accel=(0.0, -10.0, 0.0), solver_iterations=None, basic_pbf=None, update_transfers=False):
         self.ctx, self.lib = ctx, ctx.lib
         self.capacity = int(capacity or scene.n)
         self.neighbor_capacity = int(neighbor_capacity or 40 * self.capacity)
@@ -413,6 +438,7 @@ class Sim:
         cfg.use_binary_search, cfg.integrate, cfg.dt = int(use_binary_search), int(integrate), dt
         cfg.accel, cfg.min_pos, cfg.max_pos = _f3(accel), _f3(scene.min_pos), _f3(scene.max_pos)
         cfg.res_log2 = scene.res_log2
+        cfg.update_transfers = int(update_transfers)
         bmin = np.ascontiguousarray(scene.box_min, np.float32).reshape(-1, 4)
         bmax = np.ascontiguousarray(scene.box_max, np.float32).reshape(-1, 4)
         cfg.n_boxes = bmin.shape[0]

@@ -50,7 +50,7 @@ class SimConfig(C.Structure):
                 ("basic_pbf", C.c_int), ("solver_iterations", C.c_int), ("use_binary_search", C.c_int),
                 ("integrate", C.c_int), ("dt", C.c_float), ("accel", C.c_float * 3), ("min_pos", C.c_float * 3),
                 ("max_pos", C.c_float * 3), ("res_log2", C.c_uint32), ("n_boxes", C.c_uint32), ("box_min4_host", vp),
-                ("box_max4_host", vp)]
+                ("box_max4_host", vp), ("update_transfers", C.c_int)]
 
 
 class HostState(C.Structure):
@@ -105,6 +105,8 @@ SIGNATURES = {
                                                         C.c_float, C.POINTER(SearchDebug)]),
     "apbf_incompressibility_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), vp, vp]),
     "apbf_spread_kernel_width_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), vp]),
+    "apbf_update_transfers_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), vp]),
+    "apbf_kernel_width_from_boundary_distance": (C.c_int, [vp, C.POINTER(Fluid)]),
     "apbf_box_collision_apply": (C.c_int, [vp, C.POINTER(Particles), vp, vp, C.c_uint32]),
     "apbf_velocity_handling_apply": (C.c_int, [vp, C.POINTER(Particles), C.c_float, C.c_float, f32p]),
     "apbf_sim_create": (C.c_int, [vp, C.POINTER(SimConfig), C.POINTER(vp)]),

@@ -20,7 +20,7 @@ enum apbf_scratch_slot {
 	SLOT_SCAN_STATUS, SLOT_MISC_WORDS, SLOT_CELL_START, SLOT_CELL_END, SLOT_COUNTS, SLOT_OFFSETS, SLOT_NB,
 	SLOT_INV_PERM, SLOT_TMP_KEYS, SLOT_TMP_VALS, SLOT_TMP_VALS2, SLOT_CODE0, SLOT_CODE1, SLOT_CODE2,
 	SLOT_P4, SLOT_L4, SLOT_G4, SLOT_DELTA, SLOT_PUSH, SLOT_RADIUS_ID, SLOT_KWFX, SLOT_KEEP_COUNTS, SLOT_KEEP_OFFSETS,
-	SLOT_PAIRS_TMP, SLOT_NB_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4, SLOT_KG, SLOT_KH, SLOT_Q4, SLOT_KEY_ID, SLOT_EDIT_COUNTS, SLOT_EDIT_OFFSETS, SLOT_MG_INV, SLOT_I4, SLOT_CUTOFF, SLOT_QB4, SLOT_STREAM, SLOT_TILE_FIRST, SLOT_TILE_TOTAL,
+	SLOT_PAIRS_TMP, SLOT_NB_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4, SLOT_KG, SLOT_KH, SLOT_Q4, SLOT_KEY_ID, SLOT_EDIT_COUNTS, SLOT_EDIT_OFFSETS, SLOT_MG_INV, SLOT_I4, SLOT_CUTOFF, SLOT_QB4, SLOT_STREAM, SLOT_TILE_FIRST, SLOT_TILE_TOTAL, SLOT_OLD_BOUNDARY_DIST,
 	SLOT_COUNT
 };
 
@@ -58,7 +58,7 @@ enum apbf_misc_word {
 // per-kernel-category device timing (CUDA events on the context stream), off by default
 enum apbf_prof_cat {
 	PROF_HASH_SORT = 0, PROF_REORDER, PROF_CELL_RANGES, PROF_EMIT_COUNT, PROF_EMIT_SCAN, PROF_EMIT_FILL, PROF_KW_SPREAD,
-	PROF_KW_COMPACT, PROF_KW_MISC, PROF_BOX, PROF_DENSITY_LAMBDA, PROF_APPLY_DELTA, PROF_COMMIT, PROF_VELOCITY, PROF_SOLVER_PREPARE, PROF_COUNT
+	PROF_KW_COMPACT, PROF_KW_MISC, PROF_BOX, PROF_DENSITY_LAMBDA, PROF_APPLY_DELTA, PROF_COMMIT, PROF_VELOCITY, PROF_SOLVER_PREPARE, PROF_UPDATE_TRANSFERS, PROF_COUNT
 };
 struct apbf_prof_span { int cat; cudaEvent_t beg, end; };
 

@@ -187,7 +187,7 @@ int apbf_ctx_profile(apbf_ctx* ctx, int enable)
 
 static const char* const k_prof_names[PROF_COUNT] = {
 	"hash_sort", "reorder", "cell_ranges", "emit_count", "emit_scan", "emit_fill", "kw_spread", "kw_compact", "kw_misc",
-	"box_collision", "density_lambda", "apply_delta", "commit", "velocity", "solver_prepare"
+	"box_collision", "density_lambda", "apply_delta", "commit", "velocity", "solver_prepare", "update_transfers"
 };
 
 int apbf_ctx_profile_read(apbf_ctx* ctx, int category, const char** out_name, double* out_ms, uint64_t* out_calls)

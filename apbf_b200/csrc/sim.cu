@@ -169,6 +169,8 @@ int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
 			APBF_TRY(apbf_velocity_handling_apply(ctx, &sim->fluid.particle, c.dt, sim->last_dt, c.accel));
 			sim->last_dt = c.dt;
 		}
+		if (c.update_transfers && !c.basic_pbf && s.mBaseKernelWidthOnBoundaryDistance)  // pool.cpp:77-80
+			APBF_TRY(apbf_kernel_width_from_boundary_distance(ctx, &sim->fluid));
 		const float scale = unit_scale ? 1.0f : 1.5f;
 		// pool.cpp:83-89.  Green search followed by spread_kernel_width runs as one fused pass (same lists, pair for pair)
 		const bool fused = adaptive && !c.use_binary_search && !ctx->mg_enabled && !sim->no_fuse;
@@ -191,6 +193,8 @@ int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
 			APBF_TRY(apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, flags, sim->boxes,
 			                               sim->boxes ? sim->boxes + 4 * (size_t)c.n_boxes : nullptr, c.n_boxes, nullptr, nullptr));
 		}
+		if (c.update_transfers && !c.basic_pbf)                                       // pool.cpp:99-102
+			APBF_TRY(apbf_update_transfers_apply(ctx, &sim->fluid, &sim->nb, nullptr));
 	}
 	return APBF_OK;
 }

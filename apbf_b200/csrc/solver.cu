@@ -153,6 +153,97 @@ __global__ void k_kw_finish(kw_args A)
 	}
 }
 
+// ---- update_transfers (merge and split off): find_split_and_merge_1/2/3.comp as one gather over the grouped list -----------
+// The reference scatters with atomicMin over the pair list (one thread per pair) and picks the nearest neighbour in a second
+// pass over all pairs (every pair at the minimum distance writes; which one stays is a race).  Here GROUP lanes walk the
+// particle's own segment: both minima are plain reductions, and among several pairs at the minimum distance the last one in
+// list order wins (what a sequential run of the reference's second pass leaves behind).
+struct ut_args {
+	const uint32_t* index_list;
+	const uint32_t* len;
+	const int32_t*  pos4;
+	const float*    radius;            // hidden
+	const uint32_t* old_boundary_dist; // per id: copy taken before the pass (update_transfers.cpp:32)
+	uint32_t*       boundary_dist;     // per id
+	float*          target_radius;     // per id
+	float*          boundariness;      // per id
+	uint32_t*       nearest;           // per id, optional
+	const uint32_t* nbl;
+	const uint32_t* offsets;
+	uint32_t        pair_cap;
+	const uint32_t* misc;
+	apbf_settings   s;
+};
+
+__global__ void __launch_bounds__(SWEEP_THREADS) k_update_transfers(ut_args A)
+{
+	const uint32_t n = *A.len;
+	const bool ident = A.misc[MW_IDENTITY] != 0u;
+	const unsigned sub = threadIdx.x & (GROUP - 1);
+	const uint32_t gm = group_mask();
+	const uint32_t groups_per_grid = gridDim.x * (SWEEP_THREADS / GROUP);
+	for (uint32_t a = blockIdx.x * (SWEEP_THREADS / GROUP) + threadIdx.x / GROUP; a < n; a += groups_per_grid) {
+		const uint32_t idx = ident ? a : A.index_list[a];
+		const int4 ip = __ldg((const int4*)A.pos4 + idx);
+		uint32_t bd = 0xFFFFFFFFu;                      // write_sequence(..., max, 0), update_transfers.cpp:39
+		unsigned long long best = 0xFFFFFFFFFFFFFFFFull; // (distance, ~pair index): smallest distance, then the latest pair
+		const uint32_t beg = min(A.offsets[a], A.pair_cap), end = min(A.offsets[a + 1], A.pair_cap);
+		for (uint32_t e = beg + sub; e < end; e += GROUP) {
+			const uint32_t b = A.nbl[e] & NB_ID_MASK;
+			const uint32_t idxN = ident ? b : A.index_list[b];
+			const int4 iq = __ldg((const int4*)A.pos4 + idxN);
+			// uint(length(posN - pos)): integer difference, length in float (find_split_and_merge_1.comp:30-31)
+			const float fx = (float)(iq.x - ip.x), fy = (float)(iq.y - ip.y), fz = (float)(iq.z - ip.z);
+			const uint32_t dist = f2u(sqrtf(dot3(fx, fy, fz, fx, fy, fz)));
+			bd = min(bd, A.old_boundary_dist[b] + dist); // uint arithmetic wraps like the shader's (:33)
+			best = min(best, ((unsigned long long)dist << 32) | (unsigned long long)(0xFFFFFFFFu - e));
+		}
+#pragma unroll
+		for (int o = GROUP / 2; o > 0; o >>= 1) {
+			bd = min(bd, __shfl_xor_sync(gm, bd, o, GROUP));
+			best = min(best, __shfl_xor_sync(gm, best, o, GROUP));
+		}
+		if (sub != 0) continue;
+		if (A.nearest) A.nearest[a] = beg < end ? A.nbl[0xFFFFFFFFu - (uint32_t)best] & NB_ID_MASK : 0xFFFFFFFFu;
+		// find_split_and_merge_3.comp:55-84
+		const float radius = A.radius[idx];
+		const float boundaryDistance = (float)bd / R_POS;
+		float targetRadius;
+		if (A.s.mUpdateTargetRadius) {
+			if (A.s.mBaseKernelWidthOnBoundaryDistance) {
+				targetRadius = (A.s.mTargetRadiusScaleFactor / (APBF_KERNEL_SCALE + APBF_KERNEL_SCALE * A.s.mTargetRadiusScaleFactor)) * boundaryDistance;
+				targetRadius = glsl_max(targetRadius, A.s.mSmallestTargetRadius);
+			} else {
+				targetRadius = A.s.mSmallestTargetRadius + glsl_max(0.0f, (boundaryDistance - A.s.mTargetRadiusOffset) * A.s.mTargetRadiusScaleFactor);
+			}
+			A.target_radius[a] = targetRadius;
+		}
+		const float boundariness = A.boundariness[a] >= 1.0f ? 1.0f : 0.0f;
+		// mix(boundaryDistance, radius, boundariness): boundary distance "decay" (:79)
+		A.boundary_dist[a] = f2u((boundaryDistance * (1.0f - boundariness) + radius * boundariness) * R_POS);
+		A.boundariness[a] = boundariness;
+	}
+}
+
+// pool.cpp:77-80 -> uint_to_float_with_indexed_lower_bound.comp:32-44
+__global__ void k_kw_from_boundary_distance(const uint32_t* __restrict__ index_list, const uint32_t* __restrict__ len,
+                                            const uint32_t* __restrict__ boundary_dist, const float* __restrict__ radius,
+                                            float* __restrict__ kernel_width, float factor, float lower_bound_factor, float speed)
+{
+	const uint32_t n = *len;
+	for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+		const uint32_t idx = index_list[id]; // (runs before the search: no cached knowledge about the index list)
+		const float newValue = (float)boundary_dist[id] * factor;
+		const float lowerBound = radius[idx] * lower_bound_factor;
+		const float oldValue = kernel_width[id];
+		const float d = newValue - oldValue;
+		const float dir = d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f);
+		const float result = oldValue * (1.0f + speed * dir);
+		const bool reached = (oldValue < newValue) != (result < newValue);
+		kernel_width[id] = glsl_max(reached ? newValue : result, lowerBound);
+	}
+}
+
 __global__ void k_reset_asym(uint32_t* misc) { misc[MW_N_ASYM] = 0u; }
 
 // dst[0 .. *len) = src[0 .. *len), 8-byte elements (the kept pairs go back into the caller's list)
@@ -280,6 +371,60 @@ int apbf_spread_kernel_width_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighb
 	APBF_LAUNCHED(ctx);
 	std::swap(ctx->scratch[SLOT_NB], ctx->scratch[SLOT_NB_TMP]);
 	std::swap(ctx->scratch[SLOT_OFFSETS], ctx->scratch[SLOT_KEEP_OFFSETS]);
+	return APBF_OK;
+}
+
+int apbf_update_transfers_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors* nb, uint32_t* out_nearest_neighbor)
+{
+	if (!ctx) return APBF_ERR_INVALID;
+	APBF_REQUIRE(ctx, fluid && nb);
+	apbf_particles& p = fluid->particle;
+	APBF_REQUIRE(ctx, p.index_list.data && p.length && p.position.data && p.radius.data && fluid->boundary_distance.data &&
+	                      fluid->target_radius.data && fluid->boundariness.data);
+	if (!apbf_nbr_struct_valid(ctx, nb))
+		return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, "neighbour list was not produced by this context's search", __FILE__, __LINE__);
+	const uint32_t n_cap = p.capacity;
+	if (n_cap == 0) return APBF_OK;
+	cudaStream_t st = ctx->stream;
+	apbf_prof_scope ps(ctx, PROF_UPDATE_TRANSFERS);
+	ut_args A;
+	memset(&A, 0, sizeof A);
+	uint32_t* old_bd = (uint32_t*)ctx->scratch_get(SLOT_OLD_BOUNDARY_DIST, sizeof(uint32_t) * (size_t)n_cap);
+	A.offsets = (const uint32_t*)ctx->scratch_get(SLOT_OFFSETS, sizeof(uint32_t) * (size_t)(n_cap + 1));
+	A.nbl = (const uint32_t*)ctx->scratch_get(SLOT_NB, sizeof(uint32_t) * ((size_t)nb->capacity + 1));
+	if (!old_bd || !A.offsets || !A.nbl) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+	// auto oldBoundaryDistanceList = boundaryDistanceList (update_transfers.cpp:32)
+	APBF_CUDA(ctx, cudaMemcpyAsync(old_bd, fluid->boundary_distance.data, sizeof(uint32_t) * (size_t)n_cap, cudaMemcpyDeviceToDevice, st));
+	A.index_list = (const uint32_t*)p.index_list.data;
+	A.len = p.length;
+	A.pos4 = (const int32_t*)p.position.data;
+	A.radius = (const float*)p.radius.data;
+	A.old_boundary_dist = old_bd;
+	A.boundary_dist = (uint32_t*)fluid->boundary_distance.data;
+	A.target_radius = (float*)fluid->target_radius.data;
+	A.boundariness = (float*)fluid->boundariness.data;
+	A.nearest = out_nearest_neighbor;
+	A.pair_cap = nb->capacity;
+	A.misc = ctx->misc();
+	A.s = ctx->settings;
+	k_update_transfers<<<apbf_grid(ctx, (size_t)n_cap * GROUP, SWEEP_THREADS, 64), SWEEP_THREADS, 0, st>>>(A);
+	APBF_LAUNCHED(ctx);
+	return APBF_OK;
+}
+
+int apbf_kernel_width_from_boundary_distance(apbf_ctx* ctx, apbf_fluid* fluid)
+{
+	if (!ctx) return APBF_ERR_INVALID;
+	APBF_REQUIRE(ctx, fluid);
+	apbf_particles& p = fluid->particle;
+	APBF_REQUIRE(ctx, p.index_list.data && p.length && p.radius.data && fluid->boundary_distance.data && fluid->kernel_width.data);
+	if (p.capacity == 0) return APBF_OK;
+	apbf_prof_scope ps(ctx, PROF_KW_MISC);
+	k_kw_from_boundary_distance<<<apbf_grid(ctx, p.capacity, 256), 256, 0, ctx->stream>>>(
+	    (const uint32_t*)p.index_list.data, p.length, (const uint32_t*)fluid->boundary_distance.data, (const float*)p.radius.data,
+	    (float*)fluid->kernel_width.data, ctx->settings.mTargetRadiusScaleFactor / APBF_POS_RESOLUTION, APBF_KERNEL_SCALE,
+	    ctx->settings.mKernelWidthAdaptionSpeed);
+	APBF_LAUNCHED(ctx);
 	return APBF_OK;
 }
 

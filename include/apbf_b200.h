@@ -248,6 +248,16 @@ int apbf_incompressibility_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_ne
 /* pbd::spread_kernel_width::set_data(fluid, neighbors).apply() (source/spread_kernel_width.cpp:12-26); the pruned pair
  * list replaces the content of `neighbors`.  Optional output kw_fixed[capacity] (the atomicMax target). */
 int apbf_spread_kernel_width_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighbors* neighbors, uint32_t* out_kw_fixed);
+/* pbd::update_transfers::set_data(fluid, neighbors, transfers).apply() (source/update_transfers.cpp:14-54) with
+ * settings::merge and settings::split off: one step of the boundary-distance flood fill and the nearest
+ * neighbour (find_split_and_merge_1/2.comp), target radius, boundary-distance decay and boundariness threshold
+ * (find_split_and_merge_3.comp:55-84).  The merge / split bookkeeping (:88-121) is not performed, whatever mMerge / mSplit
+ * say.  Optional output nearest_neighbor[capacity] (0xFFFFFFFF for a particle without pairs; among several pairs at the
+ * minimum distance the last one of the list -- the reference leaves that to a race). */
+int apbf_update_transfers_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors* neighbors, uint32_t* out_nearest_neighbor);
+/* pool.cpp:77-80: shader_provider::uint_to_float_with_indexed_lower_bound(boundary_distance -> kernel_width, factor
+ * targetRadiusScaleFactor / POS_RESOLUTION, lower bound radius * KERNEL_SCALE, step kernelWidthAdaptionSpeed) */
+int apbf_kernel_width_from_boundary_distance(apbf_ctx* ctx, apbf_fluid* fluid);
 /* pbd::box_collision::set_data(particles, boxMin, boxMax).apply() (source/box_collision.cpp:12-24); boxes are vec4
  * device arrays, n_boxes host-known (user_controlled_boxes owns them, <= 64) */
 int apbf_box_collision_apply(apbf_ctx* ctx, apbf_particles* particles, const float* box_min4, const float* box_max4,
@@ -273,6 +283,8 @@ typedef struct apbf_sim_config {
 	uint32_t n_boxes;
 	const float* box_min4_host;    /* vec4 [n_boxes] */
 	const float* box_max4_host;
+	int      update_transfers;     /* pool.cpp:77-80 and :99-102: kernel width from the boundary distance before the search (default
+	                                  adaptive mode) and update_transfers::apply after the solver (merge and split stay off) */
 } apbf_sim_config;
 
 /* host-side view of the scene's lists (the reference's list schema, plain host arrays) */

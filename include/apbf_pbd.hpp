@@ -713,6 +713,30 @@ namespace pbd
 		neighbors* mNeighbors = nullptr;
 	};
 
+	/// The transfers list of the reference (list_definitions.h: hidden_transfers source / target / time_left) only matters
+	/// with settings::merge or settings::split on, which is outside this library's scope; the pointer is kept for the signature.
+	struct transfers;
+
+	/// pbd::update_transfers (source/update_transfers.h, update_transfers.cpp:14-54) with merge and split off
+	class update_transfers
+	{
+	public:
+		update_transfers& set_data(fluid* aFluid, neighbors* aNeighbors, transfers* aTransfers = nullptr) { mFluid = aFluid; mNeighbors = aNeighbors; mTransfers = aTransfers; return *this; }
+		void apply()
+		{
+			if (!mFluid || !mNeighbors) throw std::runtime_error("update_transfers: set_data() has not been called");
+			if (mFluid->empty()) return;
+			apbf_fluid f;
+			detail::fill_fluid_in_place(*mFluid, f);
+			apbf_neighbors nb = detail::neighbors_view(*mNeighbors);
+			shader_provider::check(apbf_update_transfers_apply(shader_provider::context(), &f, &nb, nullptr));
+		}
+	private:
+		fluid* mFluid = nullptr;
+		neighbors* mNeighbors = nullptr;
+		transfers* mTransfers = nullptr;
+	};
+
 	class box_collision
 	{
 	public:

@@ -840,6 +840,82 @@ uint32_t orc_spread_kernel_width_apply(orc_state* st, const orc_settings* s, uin
 }
 
 /* ---------------------------------------------------------------------------------- */
+/* update_transfers::apply with settings::merge and settings::split off               */
+/* (update_transfers.cpp:14-54) and the kernel width of the default adaptive mode     */
+/* (pool.cpp:77-80)                                                                   */
+/* ---------------------------------------------------------------------------------- */
+static inline uint32_t pair_dist_units(const orc_state* st, uint32_t n0, uint32_t n1)
+{ /* find_split_and_merge_1.comp:25-31 / _2.comp:27-33: uint(length(posN - pos)), integer difference, length in float */
+	uint32_t idx = st->index_list[n0], idxN = st->index_list[n1];
+	const int32_t* pos = &st->position[4 * idx];
+	const int32_t* posN = &st->position[4 * idxN];
+	float diff[3] = { (float)(posN[0] - pos[0]), (float)(posN[1] - pos[1]), (float)(posN[2] - pos[2]) };
+	return f2u(length3(diff));
+}
+
+void orc_update_transfers_apply(orc_state* st, const orc_settings* s, const uint32_t* pairs, uint32_t n_pairs,
+                                uint32_t* out_nearest)
+{
+	uint32_t n = st->n;
+	uint32_t* old_bd = (uint32_t*)malloc(sizeof(uint32_t) * (n ? n : 1));
+	uint32_t* min_nd = (uint32_t*)malloc(sizeof(uint32_t) * (n ? n : 1));
+	uint32_t* nearest = out_nearest ? out_nearest : (uint32_t*)malloc(sizeof(uint32_t) * (n ? n : 1));
+	memcpy(old_bd, st->boundary_distance, sizeof(uint32_t) * n);      /* oldBoundaryDistanceList, update_transfers.cpp:32 */
+	for (uint32_t id = 0; id < n; id++) {                             /* write_sequence(..., max, 0), :39 and :46 */
+		st->boundary_distance[id] = 0xFFFFFFFFu;
+		min_nd[id] = 0xFFFFFFFFu;
+		nearest[id] = 0xFFFFFFFFu;                                    /* not initialised by the reference */
+	}
+	for (uint32_t e = 0; e < n_pairs; e++) {                          /* find_split_and_merge_1.comp:21-34 */
+		uint32_t n0 = pairs[2 * e], n1 = pairs[2 * e + 1];
+		uint32_t dist = pair_dist_units(st, n0, n1);
+		uint32_t v = old_bd[n1] + dist;                               /* uint arithmetic: wraps like the shader */
+		if (v < st->boundary_distance[n0]) st->boundary_distance[n0] = v;
+		if (dist < min_nd[n0]) min_nd[n0] = dist;
+	}
+	for (uint32_t e = 0; e < n_pairs; e++) {                          /* find_split_and_merge_2.comp:21-37 */
+		uint32_t n0 = pairs[2 * e], n1 = pairs[2 * e + 1];
+		/* every pair at the minimum distance writes; in list order the last one stays */
+		if (pair_dist_units(st, n0, n1) == min_nd[n0]) nearest[n0] = n1;
+	}
+	for (uint32_t id = 0; id < n; id++) {                             /* find_split_and_merge_3.comp:55-84 */
+		uint32_t idx = st->index_list[id];
+		float radius = st->radius[idx];
+		float boundaryDistance = (float)st->boundary_distance[id] / R_POS;
+		float boundariness = st->boundariness[id];
+		float targetRadius;
+		if (s->mUpdateTargetRadius) {
+			if (s->mBaseKernelWidthOnBoundaryDistance) {
+				targetRadius = (s->mTargetRadiusScaleFactor / (ORC_KERNEL_SCALE + ORC_KERNEL_SCALE * s->mTargetRadiusScaleFactor)) * boundaryDistance;
+				targetRadius = fmaxf_(targetRadius, s->mSmallestTargetRadius);
+			} else {
+				targetRadius = s->mSmallestTargetRadius + fmaxf_(0.0f, (boundaryDistance - s->mTargetRadiusOffset) * s->mTargetRadiusScaleFactor);
+			}
+			st->target_radius[id] = targetRadius;
+		}
+		boundariness = boundariness >= 1.0f ? 1.0f : 0.0f;
+		/* mix(x, y, a) = x * (1 - a) + y * a */
+		st->boundary_distance[id] = f2u((boundaryDistance * (1.0f - boundariness) + radius * boundariness) * R_POS);
+		st->boundariness[id] = boundariness;
+		/* :88-121 merge / split bookkeeping: both switches are off in this scope */
+	}
+	free(old_bd); free(min_nd);
+	if (!out_nearest) free(nearest);
+}
+
+void orc_kernel_width_from_boundary_distance(orc_state* st, const orc_settings* s)
+{ /* pool.cpp:77-80 -> uint_to_float_with_indexed_lower_bound.comp:32-44 */
+	const float factor = s->mTargetRadiusScaleFactor / R_POS, lowerBoundFactor = ORC_KERNEL_SCALE;
+	for (uint32_t id = 0; id < st->n; id++) {
+		uint32_t idx = st->index_list[id];
+		float value = (float)st->boundary_distance[id] * factor;
+		float lowerBound = st->radius[idx] * lowerBoundFactor;
+		value = move_towards_rel(st->kernel_width[id], value, s->mKernelWidthAdaptionSpeed);
+		st->kernel_width[id] = fmaxf_(value, lowerBound);
+	}
+}
+
+/* ---------------------------------------------------------------------------------- */
 /* box collision                                                                      */
 /* ---------------------------------------------------------------------------------- */
 static inline void hash31(float p, float o[3]) /* box_collision.comp:20-25 */
@@ -922,11 +998,13 @@ void orc_velocity_handling(orc_state* st, float dt, const float accel[3])
 }
 
 /* ---------------------------------------------------------------------------------- */
-/* one substep, pool.cpp:67-106 (without split/merge and update_transfers)            */
+/* one substep, pool.cpp:67-106 (without split/merge; update_transfers on request)     */
 /* ---------------------------------------------------------------------------------- */
 uint32_t orc_substep(orc_state* st, const orc_settings* s, const orc_substep_params* p, uint32_t* pairs, uint32_t cap)
 {
 	if (p->integrate) orc_velocity_handling(st, p->dt, p->accel);                        /* pool.cpp:71 */
+	if (p->update_transfers && !p->basic_pbf && s->mBaseKernelWidthOnBoundaryDistance)
+		orc_kernel_width_from_boundary_distance(st, s);                                  /* pool.cpp:77-80 */
 	int adaptive = !p->basic_pbf && !s->mBaseKernelWidthOnBoundaryDistance;
 	float scale = (p->basic_pbf || s->mBaseKernelWidthOnBoundaryDistance) ? 1.0f : 1.5f; /* pool.cpp:83 */
 	uint32_t np;
@@ -937,5 +1015,6 @@ uint32_t orc_substep(orc_state* st, const orc_settings* s, const orc_substep_par
 		if (st->n > 0) orc_box_collision(st, p->box_min4, p->box_max4, p->n_boxes);
 		orc_incompressibility_apply(st, s, p->dims, pairs, np, NULL, NULL);
 	}
+	if (p->update_transfers && !p->basic_pbf) orc_update_transfers_apply(st, s, pairs, np, NULL); /* pool.cpp:99-102 */
 	return np;
 }

@@ -175,6 +175,13 @@ uint32_t orc_spread_kernel_width_apply(orc_state* st, const orc_settings* s, uin
                                        uint32_t* out_kw_fixed /* optional [n] */);
 
 /* ---- box collision (box_collision.comp:36-60) ------------------------------------- */
+/* update_transfers::apply with settings::merge / settings::split off (update_transfers.cpp:14-54):
+ * find_split_and_merge_1/2/3.comp.  out_nearest: optional [n], 0xFFFFFFFF where a particle has no pair. */
+void orc_update_transfers_apply(orc_state* st, const orc_settings* s, const uint32_t* pairs, uint32_t n_pairs,
+                                uint32_t* out_nearest);
+/* pool.cpp:77-80: uint_to_float_with_indexed_lower_bound.comp, boundary distance -> kernel width */
+void orc_kernel_width_from_boundary_distance(orc_state* st, const orc_settings* s);
+
 void orc_box_collision(orc_state* st, const float* box_min4, const float* box_max4, uint32_t n_boxes);
 
 /* ---- velocity handling (velocity_handling.cpp:15-31) ------------------------------ */
@@ -194,6 +201,7 @@ typedef struct orc_substep_params {
 	uint32_t n_boxes;
 	const float* box_min4;
 	const float* box_max4;
+	int      update_transfers;   /* pool.cpp:77-80 and :99-102 (merge and split stay off) */
 } orc_substep_params;
 /* returns the number of pairs left in `pairs` after the substep */
 uint32_t orc_substep(orc_state* st, const orc_settings* s, const orc_substep_params* p,

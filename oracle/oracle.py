@@ -43,7 +43,8 @@ class _SubstepParams(C.Structure):
     _fields_ = [("dims", C.c_int), ("basic_pbf", C.c_int), ("solver_iterations", C.c_int),
                 ("use_binary_search", C.c_int), ("integrate", C.c_int), ("dt", C.c_float),
                 ("accel", C.c_float * 3), ("min_pos", C.c_float * 3), ("max_pos", C.c_float * 3),
-                ("res_log2", C.c_uint32), ("n_boxes", C.c_uint32), ("box_min4", C.c_void_p), ("box_max4", C.c_void_p)]
+                ("res_log2", C.c_uint32), ("n_boxes", C.c_uint32), ("box_min4", C.c_void_p), ("box_max4", C.c_void_p),
+                ("update_transfers", C.c_int)]
 
 
 _lib = None
@@ -234,6 +235,21 @@ def spread_kernel_width_apply(st, s, pairs):
     return pairs[:n], kwfx
 
 
+def update_transfers_apply(st, s, pairs):
+    """update_transfers::apply with merge and split off (update_transfers.cpp:14-54); returns the nearest-neighbour ids"""
+    pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+    nearest = np.zeros(st.n, np.uint32)
+    cst = st.c()
+    lib().orc_update_transfers_apply(C.byref(cst), C.byref(s), _p(pairs), C.c_uint32(len(pairs)), _p(nearest))
+    return nearest
+
+
+def kernel_width_from_boundary_distance(st, s):
+    """pool.cpp:77-80 (uint_to_float_with_indexed_lower_bound.comp)"""
+    cst = st.c()
+    lib().orc_kernel_width_from_boundary_distance(C.byref(cst), C.byref(s))
+
+
 def box_collision(st, box_min4, box_max4):
     box_min4 = np.ascontiguousarray(box_min4, np.float32).reshape(-1, 4)
     box_max4 = np.ascontiguousarray(box_max4, np.float32).reshape(-1, 4)
@@ -247,7 +263,7 @@ def velocity_handling(st, dt, accel):
 
 
 def substep(st, s, *, dims, basic_pbf, solver_iterations, min_pos, max_pos, res_log2, box_min4, box_max4, cap,
-            use_binary_search=False, integrate=False, dt=1.0 / 60.0, accel=(0.0, -10.0, 0.0)):
+            use_binary_search=False, integrate=False, dt=1.0 / 60.0, accel=(0.0, -10.0, 0.0), update_transfers=False):
     """One substep in pool::update order (pool.cpp:67-106). Returns the final pair list."""
     box_min4 = np.ascontiguousarray(box_min4, np.float32).reshape(-1, 4)
     box_max4 = np.ascontiguousarray(box_max4, np.float32).reshape(-1, 4)
@@ -257,6 +273,7 @@ def substep(st, s, *, dims, basic_pbf, solver_iterations, min_pos, max_pos, res_
     p.accel, p.min_pos, p.max_pos = _f3(accel), _f3(min_pos), _f3(max_pos)
     p.res_log2, p.n_boxes = res_log2, box_min4.shape[0]
     p.box_min4, p.box_max4 = box_min4.ctypes.data, box_max4.ctypes.data
+    p.update_transfers = int(update_transfers)
     pairs = np.zeros((cap, 2), np.uint32)
     cst = st.c()
     n = lib().orc_substep(C.byref(cst), C.byref(s), C.byref(p), _p(pairs), C.c_uint32(cap))

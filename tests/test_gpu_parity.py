@@ -454,6 +454,93 @@ def test_fused_prune_on_the_ambiguity_band(gpu, orc):
     assert np.array_equal(L.read_pairs(), ekept)
 
 
+# ---- update_transfers (merge and split off) -------------------------------------------------------------------
+@pytest.mark.parametrize("on_boundary_distance,update_target_radius", [(1, 1), (0, 1), (1, 0)])
+def test_update_transfers_matches_oracle(gpu, orc, on_boundary_distance, update_target_radius):
+    """find_split_and_merge_1/2/3.comp as one gather over the grouped list: boundary distance (flood-fill step + decay), nearest
+    neighbour, target radius and thresholded boundariness -- all bit exact (integer minima; the float part is a handful of
+    unfused elementwise operations)"""
+    sc = scenes.waterdrop(16, jitter=0.1)
+    rng = np.random.default_rng(31)
+    sc.arrays["boundariness"] = rng.choice([0.0, 0.4, 1.0, 1.0], sc.n).astype(np.float32)
+    sc.arrays["boundary_distance"] = (sc.arrays["boundary_distance"] * rng.uniform(1.0, 6.0, sc.n)).astype(np.uint32)
+    sc.arrays["boundary_distance"][:: 17] = 0xFFFFFFFF                     # an isolated particle of the previous substep: the sum wraps
+    s = orc.default_settings()
+    s.mBaseKernelWidthOnBoundaryDistance = on_boundary_distance
+    s.mUpdateTargetRadius = update_target_radius
+    s.mTargetRadiusOffset, s.mTargetRadiusScaleFactor = 2.0, 2.5            # a small scene: let the target radius leave its floor
+    cap = sc.n * 300
+    st = oracle_state(orc, sc)
+    epairs = orc.green_apply(st, s, 3, 1.0, sc.min_pos, sc.max_pos, sc.res_log2, cap)
+    ctx = gpu.Context()
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=cap)
+    gpu.neighborhood_green(ctx).set_data(L).set_range_scale(1.0).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply()
+    assert np.array_equal(L.read_pairs(), epairs)
+    enearest = orc.update_transfers_apply(st, s, epairs)
+    gnearest = gpu.update_transfers(ctx).set_data(L).apply(debug=True)
+    assert np.array_equal(gnearest, enearest)
+    for k in ("boundary_distance", "target_radius", "boundariness", "kernel_width", "position"):
+        assert np.array_equal(L.read(k), getattr(st, k)), k
+    assert len(np.unique(st.boundary_distance)) > 50 and (update_target_radius == 0 or len(np.unique(st.target_radius)) > 1)
+    # pool.cpp:77-80 on the new boundary distances, twice (the second step starts from the moved widths)
+    for _ in range(2):
+        orc.kernel_width_from_boundary_distance(st, s)
+        gpu.kernel_width_from_boundary_distance(ctx, L)
+    assert np.array_equal(L.read("kernel_width"), st.kernel_width)
+
+
+def test_update_transfers_without_pairs(gpu, orc):
+    """particles without a single pair: the boundary distance stays at the fill value and saturates in the decay"""
+    sc = scenes.uniform_block(4, jitter=0.0)
+    sc.arrays["kernel_width"][:] = 0.5                                      # range below the lattice spacing: no pairs at all
+    sc.arrays["boundariness"][::2] = 0.0                                    # no decay: uint(2^32) saturates
+    s = orc.default_settings()
+    st = oracle_state(orc, sc)
+    epairs = orc.green_apply(st, s, 3, 1.0, sc.min_pos, sc.max_pos, sc.res_log2, 1024)
+    assert len(epairs) == 0
+    ctx = gpu.Context()
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=1024)
+    gpu.neighborhood_green(ctx).set_data(L).set_range_scale(1.0).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply()
+    enearest = orc.update_transfers_apply(st, s, epairs)
+    gnearest = gpu.update_transfers(ctx).set_data(L).apply(debug=True)
+    assert np.array_equal(gnearest, enearest) and np.all(gnearest == 0xFFFFFFFF)
+    for k in ("boundary_distance", "target_radius", "boundariness"):
+        assert np.array_equal(L.read(k), getattr(st, k)), k
+
+
+def test_substeps_default_adaptive_mode_match_oracle(gpu, orc):
+    """the reference's default mode (baseKernelWidthOnBoundaryDistance, pool.cpp:77-80 + update_transfers after the solver,
+    :99-102) through apbf_sim_*: kernel widths follow the boundary distance that update_transfers floods inwards"""
+    sc = scenes.waterdrop(16, jitter=0.1, wall_gap=3.0)
+    s = orc.default_settings()
+    s.mBaseKernelWidthOnBoundaryDistance = 1
+    cap = sc.n * 700
+    sc.arrays["position"][:, 3] = np.arange(sc.n, dtype=np.int32)
+    st = oracle_state(orc, sc)
+    ctx = gpu.Context(dims=3)
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    sim = gpu.Sim(ctx, sc, neighbor_capacity=cap, integrate=True, basic_pbf=False, update_transfers=True)
+    sim.upload(sc.arrays)
+    for step in range(3):
+        orc.substep(st, s, dims=3, basic_pbf=False, solver_iterations=4, min_pos=sc.min_pos, max_pos=sc.max_pos, res_log2=sc.res_log2,
+                    box_min4=sc.box_min, box_max4=sc.box_max, cap=cap, integrate=True, update_transfers=True)
+        sim.substep(1)
+    from apbf_b200 import empty_host_arrays
+    out = empty_host_arrays(sc.n)
+    assert sim.download(out) == sc.n
+    got_order, exp_order = np.argsort(out["position"][:, 3]), np.argsort(st.position[:, 3])
+    d = np.abs(out["position"][got_order, :3].astype(np.int64) - st.position[exp_order, :3])
+    assert np.percentile(d, 99) <= 32 and d.max() <= 256, (np.percentile(d, 99), d.max())
+    # boundary distances are integer sums of truncated distances: a unit of position difference moves them by a unit or two
+    bd = np.abs(out["boundary_distance"][got_order].astype(np.int64) - st.boundary_distance[exp_order].astype(np.int64))
+    assert np.percentile(bd, 99) <= 64, np.percentile(bd, 99)
+    assert np.allclose(out["target_radius"][got_order], st.target_radius[exp_order], rtol=1e-4, atol=1e-4)
+    assert np.allclose(out["kernel_width"][got_order], st.kernel_width[exp_order], rtol=1e-4)
+    assert len(np.unique(st.boundary_distance)) > 50
+
+
 def test_box_collision_matches_oracle(gpu, orc):
     sc = scenes.uniform_block(16, jitter=0.3, shuffle=True)
     st = oracle_state(orc, sc)
