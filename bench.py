@@ -41,6 +41,11 @@ def make_scene(name, world=1):
         return scenes.dam_break(adaptive=True, **SLAB_DAM_BREAK[world]), dict(adaptive=True, pairs_per_particle=150, slab=True)
     if name == "dam_break_1M":      # configs[1]: pool scene dam-break, 1M particles, adaptive kernel width
         return scenes.dam_break(100, 100, 100, adaptive=True), dict(adaptive=True, pairs_per_particle=150)
+    if name == "dam_break_1M_default_mode":   # the reference's default adaptive mode: kernel width from the boundary distance
+        # (pool.cpp:77-80) + update_transfers after the solver (pool.cpp:99-102, merge and split off); no spread_kernel_width
+        return scenes.dam_break(100, 100, 100, adaptive=True), dict(adaptive=False, basic_pbf=False, update_transfers=True, pairs_per_particle=60)
+    if name == "dam_break_64k_default_mode":
+        return scenes.dam_break(40, 40, 40, adaptive=True), dict(adaptive=False, basic_pbf=False, update_transfers=True, pairs_per_particle=60)
     if name == "dam_break_64k":     # bounded sample of the same workload for the CPU arm
         return scenes.dam_break(40, 40, 40, adaptive=True), dict(adaptive=True, pairs_per_particle=150)
     if name == "uniform_64":        # configs[0]: uniform 64^3 block, fixed kernel width (jittered lattice)
@@ -75,6 +80,7 @@ def algorithmic_bytes(n, p_searched, p_kept, cells, bits, iters, adaptive):
         "box_collision": 36 * n,
         "density_lambda": 8 * p_kept + 56 * n,
         "apply_delta": 8 * p_kept + 40 * n,
+        "update_transfers": 8 * p_kept + 48 * n,   # pairs + per particle: position, radius, old/new boundary distance, target radius, boundariness
     }
     substep = (196 + 16 * passes) * n + 16 * cells + 8 * p_searched + iters * (16 * p_kept + 132 * n)
     if adaptive:
@@ -129,8 +135,9 @@ def time_oracle(sample_name, steps, warmup, threads):
     orc.set_threads(threads)
     st = orc.State(**{k: v.copy() for k, v in sc.arrays.items()})
     cap = sc.n * meta["pairs_per_particle"]
-    kw = dict(dims=sc.dims, basic_pbf=not meta["adaptive"], solver_iterations=sc.solver_iterations, min_pos=sc.min_pos,
-              max_pos=sc.max_pos, res_log2=sc.res_log2, box_min4=sc.box_min, box_max4=sc.box_max, cap=cap, integrate=True)
+    kw = dict(dims=sc.dims, basic_pbf=meta.get("basic_pbf", not meta["adaptive"]), solver_iterations=sc.solver_iterations, min_pos=sc.min_pos,
+              max_pos=sc.max_pos, res_log2=sc.res_log2, box_min4=sc.box_min, box_max4=sc.box_max, cap=cap, integrate=True,
+              update_transfers=bool(meta.get("update_transfers")))
     for _ in range(warmup):
         orc.substep(st, s, **kw)
     t0 = time.perf_counter()
@@ -146,7 +153,8 @@ def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = {"dam_break_1M": "dam_break_64k", "uniform_64": "uniform_32"}.get(args.workload, args.workload)
+    sample = {"dam_break_1M": "dam_break_64k", "uniform_64": "uniform_32",
+              "dam_break_1M_default_mode": "dam_break_64k_default_mode"}.get(args.workload, args.workload)
     steps = max(1, min(args.steps, 150))     # ~0.4 s per step of the 64k-particle sample on 16 threads
     warm = min(args.warmup, 3)
     value, sec_per_step, sc = time_oracle(sample, steps, warm, threads)
@@ -191,7 +199,8 @@ def run_gpu(args, rank, world, local_rank):
     else:
         arrays, n, n_total, capacity = sc.arrays, sc.n, sc.n * world, sc.n
     cap = capacity * meta["pairs_per_particle"]
-    sim = apbf_b200.Sim(ctx, sc, capacity=capacity, neighbor_capacity=cap, integrate=True, basic_pbf=not meta["adaptive"])
+    sim = apbf_b200.Sim(ctx, sc, capacity=capacity, neighbor_capacity=cap, integrate=True, basic_pbf=meta.get("basic_pbf", not meta["adaptive"]),
+                        update_transfers=bool(meta.get("update_transfers")))
 
     # host copies of the lists in pinned memory (the e2e leg streams them in every step)
     host = {}
@@ -339,7 +348,7 @@ def run_gpu(args, rank, world, local_rank):
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        sample = {"dam_break_1M": "dam_break_64k", "uniform_64": "uniform_32"}.get(args.workload, args.workload)
+        sample = {"dam_break_1M": "dam_break_64k", "uniform_64": "uniform_32", "dam_break_1M_default_mode": "dam_break_64k_default_mode"}.get(args.workload, args.workload)
         threads = os.cpu_count() or 1
         cpu_steps = 30                           # bounded sample: 10-30 s of CPU work
         v, sec, ssc = time_oracle(sample, cpu_steps, 1, threads)
