@@ -361,6 +361,47 @@ def kernel_width_from_boundary_distance(ctx, lists):
     _check(ctx, ctx.lib.apbf_kernel_width_from_boundary_distance(ctx.handle, C.byref(fl)))
 
 
+def _fmt_g(x):
+    """a float the way `std::ostream << float` prints it by default: printf("%g"), six significant digits"""
+    return "%g" % float(np.float32(x))
+
+
+def save_particle_info(lists, folder="particle_data"):
+    """pbd::save_particle_info::set_data(fluid, neighbors, transfers).apply() on device lists (reads them back first)"""
+    return write_particle_info(lists.read_all(), lists.read_pairs(), folder)
+
+
+def write_particle_info(a, pairs, folder="particle_data"):
+    """pbd::save_particle_info::apply() (source/save_particle_info.cpp:21-130): the reference's on-disk particle dump -- six
+    ';'-separated text files and data.csv, sorted by the distance to (0, 10, -60).  Host-side only: lets a run of this library
+    be diffed against a run of the reference.  `a`: the lists as host arrays (FIELDS), `pairs`: [P, 2].
+    Returns the folder."""
+    import os
+    f32 = np.float32
+    idx = np.asarray(a["index_list"]).astype(np.int64)
+    n = len(idx)
+    pos = (np.asarray(a["position"])[idx, :3].astype(f32) / f32(262144.0)).astype(f32)
+    pairs = np.asarray(pairs).reshape(-1, 2)
+    nbr_count = np.bincount(pairs[:, 0].astype(np.int64), minlength=n)[:n] if len(pairs) else np.zeros(n, np.int64)
+    bdr = (np.asarray(a["boundary_distance"]).astype(f32) / f32(262144.0)).astype(f32)
+    d = pos - np.array([0.0, 10.0, -60.0], f32)                      # centerPos, :49
+    center = np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(f32) + d[:, 2] * d[:, 2]).astype(f32)
+    radius, inv_mass = np.asarray(a["radius"])[idx], np.asarray(a["inverse_mass"])[idx]
+    os.makedirs(folder, exist_ok=True)
+    for name, v, ints in (("centerDist.txt", center, False), ("radius.txt", radius, False), ("neighborCount.txt", nbr_count, True),
+                          ("kernelWidth.txt", a["kernel_width"], False), ("targetRadius.txt", a["target_radius"], False),
+                          ("boundaryDistance.txt", bdr, False)):
+        with open(os.path.join(folder, name), "w") as f:
+            f.write("".join((str(int(x)) if ints else _fmt_g(x)) + ";" for x in v))
+    order = np.argsort(center, kind="stable")                        # std::sort: the order of equal distances is unspecified
+    with open(os.path.join(folder, "data.csv"), "w") as f:
+        f.write("center distance,boundary distance,kernel width,neighbor count,radius,target radius,inverse mass,x,y,z\n")
+        for k in order:
+            f.write(",".join([_fmt_g(center[k]), _fmt_g(bdr[k]), _fmt_g(a["kernel_width"][k]), str(int(nbr_count[k])), _fmt_g(radius[k]),
+                              _fmt_g(a["target_radius"][k]), _fmt_g(inv_mass[k]), _fmt_g(pos[k, 0]), _fmt_g(pos[k, 1]), _fmt_g(pos[k, 2])]) + "\n")
+    return folder
+
+
 class box_collision(_Operator):
     """pbd::box_collision (source/box_collision.h:8-18)"""
 

@@ -22,6 +22,9 @@
 
 #include <algorithm>
 #include <cassert>
+#include <cmath>
+#include <filesystem>
+#include <fstream>
 #include <cstdint>
 #include <cstring>
 #include <limits>
@@ -735,6 +738,67 @@ namespace pbd
 		fluid* mFluid = nullptr;
 		neighbors* mNeighbors = nullptr;
 		transfers* mTransfers = nullptr;
+	};
+
+	/// pbd::save_particle_info::apply() (source/save_particle_info.cpp:21-130): the reference's on-disk particle dump --
+	/// six ';'-separated text files and data.csv (sorted by the distance to (0, 10, -60)) in PARTICLE_INFO_FOLDER_NAME
+	/// ("particle_data", cpu_gpu_shared_config.h:21), floats in the default ostream format.  Host-side only; lets a run of
+	/// this library be diffed against a run of the reference.  save_as_svg is rendering and not provided.
+	class save_particle_info
+	{
+	public:
+		save_particle_info& set_data(fluid* aFluid, neighbors* aNeighbors, transfers* aTransfers = nullptr) { mFluid = aFluid; mNeighbors = aNeighbors; (void)aTransfers; return *this; }
+		save_particle_info& set_folder(const std::string& aFolder) { mFolder = aFolder; return *this; } // default: the reference's
+		void apply()
+		{
+			if (!mFluid || !mNeighbors) throw std::runtime_error("save_particle_info: set_data() has not been called");
+			using hp = hidden_particles_enum;
+			auto& parts = mFluid->get<fluid_enum::particle>();
+			auto indices = parts.index_read();
+			auto positions = parts.hidden_list().template get<hp::position>().template read<int32_t>();   // ivec4 per particle
+			auto radii = parts.hidden_list().template get<hp::radius>().template read<float>();
+			auto invMasses = parts.hidden_list().template get<hp::inverse_mass>().template read<float>();
+			auto kernelWidth = mFluid->get<fluid_enum::kernel_width>().template read<float>();
+			auto targetRadius = mFluid->get<fluid_enum::target_radius>().template read<float>();
+			auto boundaryDist = mFluid->get<fluid_enum::boundary_distance>().template read<uint32_t>();
+			auto nbrPairs = mNeighbors->template read<uint32_t>();                                         // uvec2 per pair
+			const size_t n = indices.size();
+			std::vector<unsigned int> nbrCount(n, 0u), sortedIdx(n);
+			std::vector<float> radius(n), inverseMass(n), centerDist(n), bdrDist(n), px(n), py(n), pz(n);
+			for (size_t e = 0; e + 1 < nbrPairs.size(); e += 2) nbrCount[nbrPairs[e]]++;
+			for (size_t i = 0; i < n; i++) {
+				const uint32_t id = indices[i];
+				px[i] = static_cast<float>(positions[4 * id]) / APBF_POS_RESOLUTION;
+				py[i] = static_cast<float>(positions[4 * id + 1]) / APBF_POS_RESOLUTION;
+				pz[i] = static_cast<float>(positions[4 * id + 2]) / APBF_POS_RESOLUTION;
+				bdrDist[i] = boundaryDist[i] / APBF_POS_RESOLUTION;
+				const float dx = px[i] - 0.0f, dy = py[i] - 10.0f, dz = pz[i] - (-60.0f);              // centerPos, :49
+				centerDist[i] = std::sqrt(dx * dx + dy * dy + dz * dz);
+				radius[i] = radii[id];
+				inverseMass[i] = invMasses[id];
+				sortedIdx[i] = static_cast<unsigned int>(i);
+			}
+			std::filesystem::create_directories(mFolder);
+			auto dump = [&](const char* name, const auto& v) { std::ofstream f(mFolder + "/" + name); for (auto& x : v) f << x << ";"; };
+			dump("centerDist.txt", centerDist);
+			dump("radius.txt", radius);
+			dump("neighborCount.txt", nbrCount);
+			dump("kernelWidth.txt", kernelWidth);
+			dump("targetRadius.txt", targetRadius);
+			dump("boundaryDistance.txt", bdrDist);
+			std::sort(sortedIdx.begin(), sortedIdx.end(), [&](unsigned int a, unsigned int b) { return centerDist[a] < centerDist[b]; });
+			std::ofstream f(mFolder + "/data.csv");
+			f << "center distance,boundary distance,kernel width,neighbor count,radius,target radius,inverse mass,x,y,z" << std::endl;
+			for (size_t i = 0; i < n; i++) {
+				const unsigned int k = sortedIdx[i];
+				f << centerDist[k] << "," << bdrDist[k] << "," << kernelWidth[k] << "," << nbrCount[k] << "," << radius[k] << ","
+				  << targetRadius[k] << "," << inverseMass[k] << "," << px[k] << "," << py[k] << "," << pz[k] << std::endl;
+			}
+		}
+	private:
+		fluid* mFluid = nullptr;
+		neighbors* mNeighbors = nullptr;
+		std::string mFolder = "particle_data";
 	};
 
 	class box_collision
