@@ -117,6 +117,43 @@ def test_three_particle_neighbours(orc):
     assert _pairs_by_position(st, b) == expected
 
 
+def test_update_transfers_hand_derived(orc):
+    """find_split_and_merge_1/2/3.comp by hand on the three particles of test.cpp:560-563 with the pair set
+    {(0,1),(0,2),(1,0),(2,0),(2,1)}: unit distance = 262144 fixed-point units, sqrt(2) -> uint(370727.6) = 370727."""
+    R, S2 = 262144, 370727
+    st = orc.State(**_three_particles())
+    st.boundary_distance[:] = [1000, 2000, 3000]
+    st.boundariness[:] = [1.0, 0.25, 0.0]
+    st.radius[:] = [1.0, 1.0, 0.5]
+    s = orc.default_settings()
+    s.mBaseKernelWidthOnBoundaryDistance = 0
+    s.mUpdateTargetRadius = 1
+    s.mSmallestTargetRadius, s.mTargetRadiusOffset, s.mTargetRadiusScaleFactor = 1.0, 0.5, 2.0
+    pairs = np.array([[0, 1], [0, 2], [1, 0], [2, 0], [2, 1]], np.uint32)
+    nearest = orc.update_transfers_apply(st, s, pairs)
+    # pass 1: bd[n0] = min over pairs of old_bd[n1] + dist
+    bd = [min(2000 + R, 3000 + R), 1000 + R, min(1000 + R, 2000 + S2)]
+    # pass 2: nearest neighbour = the pair at the minimum distance; particle 0 has two at distance R -> the last one of the list
+    assert nearest.tolist() == [2, 0, 0]
+    # pass 3: target radius = smallest + max(0, (bd / 2^18 - offset) * factor); decay mix(bd, radius, boundariness >= 1)
+    f32 = np.float32
+    exp_tr = [f32(1.0) + max(f32(0.0), (f32(b) / f32(R) - f32(0.5)) * f32(2.0)) for b in bd]
+    assert np.array_equal(st.target_radius, np.array(exp_tr, f32))
+    assert st.boundariness.tolist() == [1.0, 0.0, 0.0]
+    assert st.boundary_distance.tolist() == [R, bd[1], bd[2]]          # particle 0 is on the boundary: its distance falls back to its radius
+    # pool.cpp:77-80 with factor 2 / 2^18, lower bound 4 * radius, step 1 %: particles 0 and 1 (width 1, value ~2) step to 1.01 and
+    # are lifted to the lower bound 4; particle 2 (width 2, value 2.0076 within one step) reaches the value, above its bound 2
+    orc.kernel_width_from_boundary_distance(st, s)
+    assert np.array_equal(st.kernel_width, np.array([4.0, 4.0, f32(bd[2]) * (f32(2.0) / f32(R))], f32))
+    st.radius[:] = 0.1
+    st.kernel_width[:] = [1.0, 3.0, 1.0]
+    orc.kernel_width_from_boundary_distance(st, s)
+    v = [f32(b) * (f32(2.0) / f32(R)) for b in st.boundary_distance]      # 2, ~2.0076, ~2.0076
+    exp = [f32(1.0) * (f32(1.0) + s.mKernelWidthAdaptionSpeed), f32(3.0) * (f32(1.0) - f32(s.mKernelWidthAdaptionSpeed)),
+           f32(1.0) * (f32(1.0) + s.mKernelWidthAdaptionSpeed)]
+    assert np.array_equal(st.kernel_width, np.array(exp, f32)) and all(e < x for e, x in zip(exp[::2], v[::2]))
+
+
 @pytest.mark.parametrize("dims", [2, 3])
 def test_searches_agree_with_brute_force(orc, dims):
     sc = scenes.uniform_block(10 if dims == 3 else 40, jitter=0.3, dims=dims, shuffle=True)
