@@ -191,6 +191,14 @@ class ParticleLists:
     def read_all(self):
         return {name: self.read(name) for name, _, _ in FIELDS}
 
+    def write(self, name, values):
+        """overwrite the first len(values) entries of one list from a host array (tests)"""
+        torch = _torch()
+        _, dt, w = next(f for f in FIELDS if f[0] == name)
+        a = np.ascontiguousarray(values, dtype=dt).reshape(-1, w)
+        t = torch.from_numpy(a.view(np.int32) if dt == np.uint32 else a).to(self.words.device)
+        self.buf[name][0][: a.shape[0]].view(-1, w).copy_(t)
+
     def read_pairs(self):
         return self.pairs[:self.pair_count()].cpu().numpy().view(np.uint32)
 

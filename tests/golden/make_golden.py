@@ -62,6 +62,14 @@ def scene_case(name, sc, scale, adaptive, hk=1, gk=1, method=2):
         kept, kwfx = orc.spread_kernel_width_apply(st, s, pairs)
         out.update(kept_pairs=kept, kw_fixed=kwfx, kernel_width=st.kernel_width.copy())
         pairs = kept
+    # update_transfers (merge / split off) and the kernel width of the default adaptive mode, on a copy of the searched state:
+    # the incompressibility outputs below stay what they were before these two were added
+    st2 = st.copy()
+    nearest = orc.update_transfers_apply(st2, s, pairs)
+    out.update(ut_nearest=nearest, ut_boundary_distance=st2.boundary_distance.copy(), ut_target_radius=st2.target_radius.copy(),
+               ut_boundariness=st2.boundariness.copy())
+    orc.kernel_width_from_boundary_distance(st2, s)
+    out.update(ut_kernel_width=st2.kernel_width.copy())
     a = orc.incompressibility_apply(st, s, sc.dims, pairs, want_aux=True)
     out.update(density=a["density"], grad_sum=a["grad_sum"], sq_grad_sum=a["sq_grad_sum"], lam=a["lam"], position_after=st.position.copy(),
                boundariness=st.boundariness.copy())

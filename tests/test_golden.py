@@ -79,6 +79,12 @@ def test_oracle_reproduces_frozen_outputs(orc, name):
     if meta["adaptive"]:
         pairs, kwfx = orc.spread_kernel_width_apply(st, s, pairs)
         assert np.array_equal(pairs, g["kept_pairs"]) and np.array_equal(kwfx, g["kw_fixed"]) and np.array_equal(st.kernel_width, g["kernel_width"])
+    st2 = st.copy()                                   # update_transfers + pool.cpp:77-80 on the searched state
+    assert np.array_equal(orc.update_transfers_apply(st2, s, pairs), g["ut_nearest"])
+    for k in ("boundary_distance", "target_radius", "boundariness"):
+        assert np.array_equal(getattr(st2, k), g["ut_" + k]), k
+    orc.kernel_width_from_boundary_distance(st2, s)
+    assert np.array_equal(st2.kernel_width, g["ut_kernel_width"])
     a = orc.incompressibility_apply(st, s, sc.dims, pairs, want_aux=True)
     for k in ("density", "grad_sum", "sq_grad_sum", "lam"):
         assert np.array_equal(a[k], g[k]), k
@@ -177,6 +183,16 @@ def test_cuda_matches_frozen_outputs(gpu, orc, name):
         kwfx = gpu.spread_kernel_width(ctx).set_data(L).apply(debug=True)
         assert np.array_equal(kwfx, g["kw_fixed"]) and np.array_equal(L.read_pairs(), g["kept_pairs"])
         assert np.array_equal(L.read("kernel_width"), g["kernel_width"])
+    # update_transfers on the searched state: integer minima and a few unfused float operations -> bit exact.  It rewrites
+    # boundary distance, target radius and boundariness only; none of them enters the quantities compared below.
+    nearest = gpu.update_transfers(ctx).set_data(L).apply(debug=True)
+    assert np.array_equal(nearest, g["ut_nearest"])
+    for k in ("boundary_distance", "target_radius", "boundariness"):
+        assert np.array_equal(L.read(k), g["ut_" + k]), k
+    kw_before = L.read("kernel_width").copy()
+    gpu.kernel_width_from_boundary_distance(ctx, L)
+    assert np.array_equal(L.read("kernel_width"), g["ut_kernel_width"])
+    L.write("kernel_width", kw_before)                # the solver below runs with the widths the fixture was made with
     a = gpu.incompressibility(ctx).set_data(L).apply(debug=True)
     # integer accumulators in units of 2^-18: CUDA's expf/powf differ from glibc's in the last bit, which the float -> fixed
     # truncation turns into at most one unit per pair; tolerance 1 unit + 1e-5 relative (north_star)
