@@ -20,7 +20,7 @@ enum apbf_scratch_slot {
 	SLOT_SCAN_STATUS, SLOT_MISC_WORDS, SLOT_CELL_START, SLOT_CELL_END, SLOT_COUNTS, SLOT_OFFSETS, SLOT_NB,
 	SLOT_INV_PERM, SLOT_TMP_KEYS, SLOT_TMP_VALS, SLOT_TMP_VALS2, SLOT_CODE0, SLOT_CODE1, SLOT_CODE2,
 	SLOT_P4, SLOT_L4, SLOT_G4, SLOT_DELTA, SLOT_PUSH, SLOT_RADIUS_ID, SLOT_KWFX, SLOT_KEEP_COUNTS, SLOT_KEEP_OFFSETS,
-	SLOT_PAIRS_TMP, SLOT_NB_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4, SLOT_KG, SLOT_KH, SLOT_Q4, SLOT_KEY_ID, SLOT_EDIT_COUNTS, SLOT_EDIT_OFFSETS, SLOT_MG_INV, SLOT_I4, SLOT_CUTOFF, SLOT_QB4, SLOT_STREAM, SLOT_TILE_FIRST, SLOT_TILE_TOTAL, SLOT_OLD_BOUNDARY_DIST,
+	SLOT_PAIRS_TMP, SLOT_NB_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4, SLOT_KG, SLOT_KH, SLOT_Q4, SLOT_KEY_ID, SLOT_EDIT_COUNTS, SLOT_EDIT_OFFSETS, SLOT_MG_INV, SLOT_I4, SLOT_CUTOFF, SLOT_QB4, SLOT_STREAM, SLOT_TILE_FIRST, SLOT_TILE_TOTAL, SLOT_OLD_BOUNDARY_DIST, SLOT_CELL_MAXW,
 	SLOT_COUNT
 };
 
@@ -51,6 +51,7 @@ enum apbf_misc_word {
 	MW_EMIT_TICKET0 = 18, // tile tickets of the pair emit (count pass, fill pass)
 	MW_EMIT_TICKET1 = 19,
 	MW_STREAM_CURSOR = 20,   // block allocator of the pair emit's hit stream
+	MW_MAX_INIT = 22,        // fused search + spread: largest initial kernel width (fixed point) over all particles
 	MW_STREAM_OVERFLOW = 21, // the hit stream ran out of blocks (only when the pair list overflows): the two-pass fill takes over
 	MW_WORDS = 64
 };

@@ -137,6 +137,7 @@ struct build_kw_args {
 	int4*        i4;
 	float*       cutoff; // threshold on the squared integer distance equivalent to dist <= max(original, old kernel width)
 	float        pmax;   // largest |coordinate| of the search grid
+	uint32_t*    cell_maxw; // per cell: largest original width (fixed point) of its particles -- can this cell spread onto a query?
 	float4*      qb4;    // {K, U, -, original width}: the prune decided on the float-form distance (see k_green_stream)
 };
 
@@ -146,6 +147,7 @@ __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_
 {
 	const bool ident = misc[MW_IDENTITY] != 0u;
 	const uint32_t n = *len;
+	uint32_t max_init = 0u; // fused: the largest initial width (kernel_width_init.comp:35) this thread has seen
 	for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
 		const uint32_t idx = ident ? id : index_list[id];
 		const int4 ip = ldg_int4(pos4, idx);
@@ -176,6 +178,8 @@ __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_
 				qb.y = glsl_min(T, C + hw); // kept at most
 			}
 			K.qb4[id] = qb;
+			atomicMax(K.cell_maxw + hidden_key[idx], f2u(orig * APBF_KERNEL_WIDTH_RESOLUTION)); // (keys of ghosts index the second table)
+			max_init = max(max_init, f2u(orig * APBF_KERNEL_WIDTH_RESOLUTION));
 		}
 		const uint32_t key = hidden_key[idx];
 		key_id[id] = key;
@@ -183,6 +187,11 @@ __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_
 		const bool head = id == 0u || hidden_key[ident ? id - 1u : index_list[id - 1u]] != key;
 		const uint32_t heads = __ballot_sync(__activemask(), head);
 		if (head && (heads & ((1u << lane_id()) - 1u)) == 0u) atomicAdd(misc + MW_OCC_CELLS, (uint32_t)__popc(heads));
+	}
+	if (K.i4) {
+		const uint32_t m = __activemask();
+		max_init = __reduce_max_sync(m, max_init);
+		if ((m & ((1u << lane_id()) - 1u)) == 0u && max_init) atomicMax(misc + MW_MAX_INIT, max_init);
 	}
 }
 
@@ -238,6 +247,7 @@ struct emit_args {
 	uint32_t*       kwfx;
 	// one-pass emit (k_green_stream + k_regroup)
 	const float4*   qb4;
+	const uint32_t* cell_maxw; // fused: per cell, the largest initial width (kernel_width_init.comp:35) of its particles
 	uint32_t*       stream;
 	uint32_t        stream_blocks;
 	int             fallback; // two-pass fill kernel: run only if the hit stream overflowed
@@ -658,11 +668,20 @@ k_green_stream(const emit_args A)
 				float4 me = make_float4(0.f, 0.f, 0.f, -1.0f);
 				float4 qb = make_float4(-1.0f, -1.0f, 0.0f, 0.0f);
 				uint32_t gmin[3] = { 0u, 0u, 0u }, gmax[3] = { 0u, 0u, 0u };
-				float r_lane = 0.0f;
+				float r_lane = 0.0f, r = 0.0f;
 				if (valid) {
 					me = A.q4[id];
-					const float r = A.range[id] * A.range_scale;
+					r = A.range[id] * A.range_scale;
 					r_lane = r == r ? fmaxf(r, 0.0f) : INFINITY; // a NaN range accepts every candidate
+					if (FUSED) qb = A.qb4[id];
+				}
+				// Fused prune, nobody in the whole list starts wider than any query of this chunk is: nothing beyond the prune
+				// cutoff matters (see keep2 below), so the boxes shrink from the search range to the cutoff sqrt(U).
+				if (FUSED && !STATS && A.cull) {
+					const uint32_t mx0 = __reduce_min_sync(0xffffffffu, valid ? f2u(qb.w * APBF_KERNEL_WIDTH_RESOLUTION) : 0xFFFFFFFFu);
+					if (A.misc[MW_MAX_INIT] <= mx0 && r == r) r = fminf(r, sqrtf(fmaxf(qb.y, 0.0f)) * 1.0001f);
+				}
+				if (valid) {
 					gmin[0] = apbf_map_axis(me.x - r, g, 0); gmax[0] = apbf_map_axis(me.x + r, g, 0);
 					gmin[1] = apbf_map_axis(me.y - r, g, 1); gmax[1] = apbf_map_axis(me.y + r, g, 1);
 					gmin[2] = apbf_map_axis(me.z - r, g, 2); gmax[2] = apbf_map_axis(me.z + r, g, 2);
@@ -694,6 +713,18 @@ k_green_stream(const emit_args A)
 				}
 				const float r_cull = __uint_as_float(__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(r_lane) : 0u));
 				const float cull2 = A.cull ? r_cull * r_cull * 1.0001f : INFINITY;
+				// Fused prune: a pair farther than the largest cutoff of the chunk (U, "kept at most", squared) is searched only
+				// to spread the candidate's width onto the query (kernel_width.comp:49-53), which needs a candidate that starts
+				// wider than the query is.  Cells beyond the cutoff whose widest particle cannot do that for any query of the chunk
+				// are skipped: in a region of equal widths the walk shrinks from the search range (1.5 widths) to the cutoff.
+				// (Not when the pairs of the unpruned list are being counted.)
+				float keep2 = cull2;
+				uint32_t min_mx0 = 0u;
+				if (FUSED && !STATS && A.cull) {
+					const float u_max = fkey_inv(__reduce_max_sync(0xffffffffu, valid ? fkey(qb.y) : 0u));
+					keep2 = fminf(cull2, fmaxf(u_max, 0.0f) * 1.0001f);
+					min_mx0 = __reduce_min_sync(0xffffffffu, valid ? my_mx : 0xFFFFFFFFu);
+				}
 				const uint32_t nxy = ext[0] * ext[1], ncell = nxy * ext[2];
 				const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)ext[0];
 				const bool ghost_run = MG && first >= n_owned;
@@ -731,8 +762,10 @@ k_green_stream(const emit_args A)
 						}
 						if (!(gap2 > cull2)) {
 							const uint32_t h = (apbf_zhash<DIMS>(a[0], a[1], a[2], g.res) & key_mask) + table_off;
-							c_first = __ldg(A.cell_start + h);
-							c_cnt = __ldg(A.cell_end + h) - c_first;
+							if (!FUSED || STATS || !(gap2 > keep2) || __ldg(A.cell_maxw + h) > min_mx0) {
+								c_first = __ldg(A.cell_start + h);
+								c_cnt = __ldg(A.cell_end + h) - c_first;
+							}
 						}
 					}
 					uint32_t incl = c_cnt;
@@ -1067,7 +1100,7 @@ k_bsearch_emit(const uint32_t* __restrict__ index_list, const int32_t* __restric
 __global__ void k_clear_search_words(uint32_t* misc)
 {
 	misc[MW_N_ASYM] = 0u; misc[MW_TOTAL_PAIRS] = 0u; misc[MW_KEPT_PAIRS] = 0xFFFFFFFFu; misc[MW_OCC_CELLS] = 0u;
-	misc[MW_EMIT_TICKET0] = 0u; misc[MW_EMIT_TICKET1] = 0u; misc[MW_STREAM_CURSOR] = 0u; misc[MW_STREAM_OVERFLOW] = 0u;
+	misc[MW_EMIT_TICKET0] = 0u; misc[MW_EMIT_TICKET1] = 0u; misc[MW_STREAM_CURSOR] = 0u; misc[MW_STREAM_OVERFLOW] = 0u; misc[MW_MAX_INIT] = 0u;
 }
 
 // shared front half of both searches: gather hidden arrays by sorted_index, rebuild the index list, gather per-id arrays
@@ -1199,6 +1232,8 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 		K.i4 = (int4*)ctx->scratch_get(SLOT_I4, sizeof(int4) * (size_t)n_cap);
 		K.cutoff = (float*)ctx->scratch_get(SLOT_CUTOFF, sizeof(float) * (size_t)n_cap);
 		K.qb4 = (float4*)ctx->scratch_get(SLOT_QB4, sizeof(float4) * (size_t)n_cap);
+		K.cell_maxw = (uint32_t*)ctx->scratch_get(SLOT_CELL_MAXW, sizeof(uint32_t) * (size_t)max_hash * layers);
+		if (!K.cell_maxw) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 		kwfx = (uint32_t*)ctx->scratch_get(SLOT_KWFX, sizeof(uint32_t) * (size_t)n_cap);
 		if (!K.i4 || !K.cutoff || !K.qb4 || !kwfx) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 	}
@@ -1248,10 +1283,11 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 	A.q4 = q4; A.key_id = key_id; A.range = new_range; A.cell_start = cs; A.cell_end = ce; A.len = p.length; A.g = g;
 	A.range_scale = range_scale; A.counts = counts; A.offsets = offsets; A.pairs = nb->pairs; A.nbl = nbl; A.cap = nb->capacity;
 	A.misc = misc; A.cull = cull; A.table_cells = max_hash; A.layers = emit_mode; A.i4 = K.i4; A.cutoff = K.cutoff; A.kwfx = kwfx;
-	A.qb4 = K.qb4; A.stream = stream; A.stream_blocks = stream_blocks;
+	A.qb4 = K.qb4; A.cell_maxw = K.cell_maxw; A.stream = stream; A.stream_blocks = stream_blocks;
 	static const int two_pass = getenv("APBF_TWO_PASS_EMIT") ? 1 : 0; // debugging aid: the count/fill emit instead of stream/regroup
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_COUNT);
+		if (fuse_kw) APBF_CUDA(ctx, cudaMemsetAsync(K.cell_maxw, 0, sizeof(uint32_t) * (size_t)max_hash * layers, st));
 		k_build_q4<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>(new_index, new_pos, skeys, new_range, range_scale, p.length, q4, key_id, misc, K);
 		APBF_LAUNCHED(ctx);
 		A.ticket = misc + MW_EMIT_TICKET0;
