@@ -131,6 +131,9 @@ SIGNATURES = {
     "apbf_sim_mg_unpack": (C.c_int, [vp, C.c_int, vp, C.c_uint32, C.c_uint32, vp]),
     "apbf_sim_mg_remap": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32]),
     "apbf_sim_mg_phase": (C.c_int, [vp, C.c_int, C.c_int]),
+    "apbf_mg_nccl_unique_id": (C.c_int, [vp]),
+    "apbf_sim_mg_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+    "apbf_sim_mg_solve": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int]),
     "apbf_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
     "apbf_host_free_pinned": (C.c_int, [vp]),
 }

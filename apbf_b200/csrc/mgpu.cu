@@ -18,6 +18,7 @@
 #include "sim.cuh"
 #include "solver.cuh"
 #include "sort.cuh"
+#include <dlfcn.h>
 
 namespace {
 
@@ -497,6 +498,146 @@ int apbf_sim_mg_phase(apbf_sim* sim, int phase, int iteration)
 		case 7: return apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_BEGIN | ITER_BEGIN_COMMIT, nullptr, nullptr, 0u, nullptr, nullptr);
 	}
 	return apbf_fail(ctx, APBF_ERR_INVALID, "phase", __FILE__, __LINE__);
+}
+
+} // extern "C"
+
+// ---- the library's own NCCL communicator ---------------------------------------------------------------------------------------
+// Driving every exchange from the host language costs a pack call, a torch collective (with two stream hops) and an unpack
+// call per exchange, ten times per substep.  With its own communicator the library runs pack -> ncclSend/ncclRecv -> unpack
+// on the context's stream, and the solver loop of a substep is ONE call (apbf_sim_mg_solve).  NCCL is bound at run time
+// (dlopen of the libnccl.so.2 the process already uses): the shared library itself does not link against it.
+namespace {
+struct nccl_uid { char internal[128]; };
+typedef void* nccl_comm;
+struct nccl_api {
+	void* so = nullptr;
+	int (*GetUniqueId)(nccl_uid*) = nullptr;
+	int (*CommInitRank)(nccl_comm*, int, nccl_uid, int) = nullptr;
+	int (*CommDestroy)(nccl_comm) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+	int (*Send)(const void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+	int (*Recv)(void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int NCCL_INT32 = 2; // ncclInt32 (nccl.h: ncclInt8 0, ncclUint8 1, ncclInt32 2)
+
+nccl_api* nccl()
+{
+	static nccl_api api;
+	static bool tried = false;
+	if (!tried) {
+		tried = true;
+		void* so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if (!so) so = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+		if (so) {
+			api.GetUniqueId = (int (*)(nccl_uid*))dlsym(so, "ncclGetUniqueId");
+			api.CommInitRank = (int (*)(nccl_comm*, int, nccl_uid, int))dlsym(so, "ncclCommInitRank");
+			api.CommDestroy = (int (*)(nccl_comm))dlsym(so, "ncclCommDestroy");
+			api.GroupStart = (int (*)())dlsym(so, "ncclGroupStart");
+			api.GroupEnd = (int (*)())dlsym(so, "ncclGroupEnd");
+			api.Send = (int (*)(const void*, size_t, int, int, nccl_comm, cudaStream_t))dlsym(so, "ncclSend");
+			api.Recv = (int (*)(void*, size_t, int, int, nccl_comm, cudaStream_t))dlsym(so, "ncclRecv");
+			api.GetErrorString = (const char* (*)(int))dlsym(so, "ncclGetErrorString");
+			if (api.GetUniqueId && api.CommInitRank && api.GroupStart && api.GroupEnd && api.Send && api.Recv) api.so = so;
+		}
+	}
+	return api.so ? &api : nullptr;
+}
+
+#define APBF_NCCL(ctx, expr)                                                                                            \
+	do {                                                                                                                \
+		int r__ = (expr);                                                                                               \
+		if (r__ != 0) return apbf_fail(ctx, APBF_ERR_CUDA, nccl()->GetErrorString ? nccl()->GetErrorString(r__) : "nccl", __FILE__, __LINE__); \
+	} while (0)
+
+struct mg_lists {
+	const uint32_t* send_ids;    // concatenated send lists, destination after destination
+	const uint32_t* ghost_ids;   // ghost slots, source after source
+	uint32_t send_counts[8], ghost_counts[8];
+	uint32_t n_send, n_ghost;
+};
+
+// one halo exchange of `what` (1 kernel width, 2 packed position, 3 lambda) on the context's stream
+int mg_exchange(apbf_sim* sim, const mg_lists& L, int what)
+{
+	apbf_ctx* ctx = sim->ctx;
+	nccl_api* N = nccl();
+	if (!N || !sim->nccl_comm) return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, "apbf_sim_mg_comm_init has not been called", __FILE__, __LINE__);
+	const uint32_t words = what == 2 ? 4u : 1u;
+	uint32_t* stage_s = (uint32_t*)ctx->scratch_get(SLOT_MG_SEND, sizeof(uint32_t) * 4 * (size_t)(L.n_send ? L.n_send : 1));
+	uint32_t* stage_r = (uint32_t*)ctx->scratch_get(SLOT_MG_RECV, sizeof(uint32_t) * 4 * (size_t)(L.n_ghost ? L.n_ghost : 1));
+	if (!stage_s || !stage_r) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+	APBF_TRY(apbf_sim_mg_pack(sim, what, L.send_ids, L.n_send, stage_s));
+	APBF_NCCL(ctx, N->GroupStart());
+	size_t so = 0, ro = 0;
+	for (int r = 0; r < sim->mg.world; r++) {
+		if (r == sim->mg.rank) continue;
+		if (L.send_counts[r]) APBF_NCCL(ctx, N->Send(stage_s + so * words, (size_t)L.send_counts[r] * words, NCCL_INT32, r, sim->nccl_comm, ctx->stream));
+		if (L.ghost_counts[r]) APBF_NCCL(ctx, N->Recv(stage_r + ro * words, (size_t)L.ghost_counts[r] * words, NCCL_INT32, r, sim->nccl_comm, ctx->stream));
+		so += L.send_counts[r]; ro += L.ghost_counts[r];
+	}
+	APBF_NCCL(ctx, N->GroupEnd());
+	APBF_TRY(apbf_sim_mg_unpack(sim, what, L.ghost_ids, 0u, L.n_ghost, stage_r));
+	return APBF_OK;
+}
+} // namespace
+
+extern "C" {
+
+int apbf_mg_nccl_unique_id(void* out_id128)
+{
+	nccl_api* N = nccl();
+	if (!N || !out_id128) return APBF_ERR_UNSUPPORTED;
+	nccl_uid id;
+	if (N->GetUniqueId(&id) != 0) return APBF_ERR_CUDA;
+	memcpy(out_id128, &id, sizeof id);
+	return APBF_OK;
+}
+
+int apbf_sim_mg_comm_init(apbf_sim* sim, const void* id128, int rank, int world)
+{
+	if (!sim || !id128) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	nccl_api* N = nccl();
+	if (!N) return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, "libnccl.so.2 not found", __FILE__, __LINE__);
+	APBF_REQUIRE(ctx, sim->mg.enabled && rank == sim->mg.rank && world == sim->mg.world && !sim->nccl_comm);
+	APBF_CUDA(ctx, cudaSetDevice(ctx->device));
+	nccl_uid id;
+	memcpy(&id, id128, sizeof id);
+	APBF_NCCL(ctx, N->CommInitRank(&sim->nccl_comm, world, id, rank));
+	return APBF_OK;
+}
+
+// spread_kernel_width's new widths to the ghosts (if adaptive), solver constants, then `iterations` x (prologue, packed positions
+// to the ghosts, density/lambda sweep, lambdas to the ghosts, apply sweep) and the final commit: phases 3-7 of apbf_sim_mg_phase
+// with the exchanges in between, in one call.  send_ids: the send lists of all destinations, concatenated; counts per rank.
+int apbf_sim_mg_solve(apbf_sim* sim, const uint32_t* send_ids_dev, const uint32_t* send_counts, const uint32_t* ghost_ids_dev,
+                      const uint32_t* ghost_counts, int exchange_kernel_width, int iterations)
+{
+	if (!sim || !send_counts || !ghost_counts) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	APBF_REQUIRE(ctx, sim->mg.enabled && sim->mg.world <= 8);
+	mg_lists L;
+	memset(&L, 0, sizeof L);
+	L.send_ids = send_ids_dev; L.ghost_ids = ghost_ids_dev;
+	for (int r = 0; r < sim->mg.world; r++) {
+		L.send_counts[r] = r == sim->mg.rank ? 0u : send_counts[r];
+		L.ghost_counts[r] = r == sim->mg.rank ? 0u : ghost_counts[r];
+		L.n_send += L.send_counts[r]; L.n_ghost += L.ghost_counts[r];
+	}
+	APBF_REQUIRE(ctx, (L.n_send == 0 || send_ids_dev) && (L.n_ghost == 0 || ghost_ids_dev));
+	if (exchange_kernel_width) APBF_TRY(mg_exchange(sim, L, 1));
+	APBF_TRY(apbf_sim_mg_phase(sim, 3, 0));
+	for (int it = 0; it < iterations; it++) {
+		APBF_TRY(apbf_sim_mg_phase(sim, 4, it));
+		APBF_TRY(mg_exchange(sim, L, 2));
+		APBF_TRY(apbf_sim_mg_phase(sim, 5, it));
+		APBF_TRY(mg_exchange(sim, L, 3));
+		APBF_TRY(apbf_sim_mg_phase(sim, 6, it));
+	}
+	return apbf_sim_mg_phase(sim, 7, 0);
 }
 
 } // extern "C"

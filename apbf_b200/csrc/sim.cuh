@@ -19,6 +19,7 @@ struct apbf_sim {
 	float           last_dt;  // velocity_handling::mLastDeltaTime (velocity_handling.h:18)
 	bool            no_fuse;
 	bool            mg_fused = false; // slabs: the last search ran fused with spread_kernel_width
+	void*           nccl_comm = nullptr; // slabs: the library's own communicator (apbf_sim_mg_comm_init)
 	std::vector<void*> owned;
 	apbf_mg_state   mg;
 };

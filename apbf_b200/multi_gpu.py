@@ -106,6 +106,9 @@ class SlabDomain:
         self.flat = hasattr(backend, "pack_all") and getattr(comm, "use_all_to_all", False)
         if self.flat:
             backend.flat_only = True
+        if self.world > 1 and hasattr(backend, "init_comm") and getattr(comm, "device", None) is not None and comm.device.type == "cuda" \
+                and not os.environ.get("APBF_MG_PY_LOOP"):
+            backend.init_comm(comm)       # solver loop and its exchanges inside the library (NCCL on the context's stream)
 
     # ---- one exchange of `what` for the current send lists / ghost slots ------------------------------------------------------
     def _refresh_ghosts(self, what):
@@ -185,6 +188,14 @@ class SlabDomain:
             b.remap_after_search(self.send_counts, sum(self.ghost_counts.values()))
         if self.adaptive:
             b.spread()
+        if W > 1 and getattr(b, "has_comm", False):
+            # the library's own communicator: widths to the ghosts, constants, the whole solver loop with its exchanges and the
+            # final commit in one call on the context's stream
+            b.solve(self.send_counts, self.ghost_counts, self.adaptive, self.iters)
+            b.set_counts(self.n_own, self.n_own, self.gid_base)
+            self._mark("solve")
+            return
+        if self.adaptive:
             self._refresh_ghosts(KW)
         self._mark("remap_kw")
         b.prepare()
@@ -224,6 +235,7 @@ class CudaRankBackend:
         self.send_counts = [0] * world
         self.send_flat = None
         self.flat_only = False   # set by SlabDomain when every exchange goes through pack_all
+        self.has_comm = False
         self.ghost_first = 0
         self._ck(self.lib.apbf_sim_mg_enable(sim.handle, rank, world, C.c_float(halo_range)))
 
@@ -306,6 +318,26 @@ class CudaRankBackend:
         if n:
             self._ck(self.lib.apbf_sim_mg_pack(self.sim.handle, what, ids.data_ptr(), n, out.data_ptr()))
         return out
+
+    def init_comm(self, comm):
+        """the library's own NCCL communicator: rank 0 makes the id, torch.distributed carries its 128 bytes"""
+        torch = self.torch
+        buf = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            self._ck(self.lib.apbf_mg_nccl_unique_id(buf.data_ptr()))
+        t = buf.to(self.dev)
+        comm.dist.broadcast(t, 0)
+        buf = t.cpu()
+        self._ck(self.lib.apbf_sim_mg_comm_init(self.sim.handle, buf.data_ptr(), self.rank, self.world))
+        self.has_comm = True
+        self.flat_only = True
+
+    def solve(self, send_counts, ghost_counts, adaptive, iterations):
+        ids = self._flat_ids()
+        sc = (C.c_uint32 * self.world)(*[0 if r == self.rank else int(send_counts[r]) for r in range(self.world)])
+        gc = (C.c_uint32 * self.world)(*[int(ghost_counts.get(r, 0)) for r in range(self.world)])
+        self._ck(self.lib.apbf_sim_mg_solve(self.sim.handle, ids.data_ptr() if ids.numel() else None, sc, self.ghost_ids.data_ptr(), gc,
+                                            int(bool(adaptive)), int(iterations)))
 
     def unpack(self, what, ghost_offset, count, buf):
         ids = self.ghost_ids.data_ptr() + 4 * ghost_offset

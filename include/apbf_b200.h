@@ -348,6 +348,16 @@ int  apbf_sim_mg_remap(apbf_sim* sim, uint32_t* ids_dev, uint32_t count, uint32_
 /* phase: 0 integrate, 1 search, 2 spread_kernel_width, 3 solver constants, 4 iteration prologue, 5 density/lambda sweep,
  * 6 apply sweep, 7 final commit (pool.cpp:67-106 cut where the halo exchanges happen) */
 int  apbf_sim_mg_phase(apbf_sim* sim, int phase, int iteration);
+/* The library's own NCCL communicator for the halo exchanges (libnccl.so.2 is bound at run time with dlopen; nothing links
+ * against it).  Rank 0 creates the id, the caller distributes its 128 bytes, every rank of the node calls comm_init. */
+int  apbf_mg_nccl_unique_id(void* out_id128);
+int  apbf_sim_mg_comm_init(apbf_sim* sim, const void* id128, int rank, int world);
+/* Phases 3-7 of one substep with the exchanges between them in one call, everything on the context's stream:
+ * [kernel widths to the ghosts] -> solver constants -> iterations x (prologue, packed positions to the ghosts, density /
+ * lambda sweep, lambdas to the ghosts, apply sweep) -> final commit.  send_ids_dev: the send lists of all destinations,
+ * destination after destination; ghost_ids_dev: the ghost slots, source after source; counts: host arrays [world]. */
+int  apbf_sim_mg_solve(apbf_sim* sim, const uint32_t* send_ids_dev, const uint32_t* send_counts, const uint32_t* ghost_ids_dev,
+                       const uint32_t* ghost_counts, int exchange_kernel_width, int iterations);
 
 /* pinned host memory helpers for callers without a CUDA runtime of their own */
 int  apbf_host_alloc_pinned(size_t bytes, void** out_host_ptr);
