@@ -233,12 +233,12 @@ def run_gpu(args, rank, world, local_rank):
             sim.substep(1)
 
     # ---- device-resident throughput ----------------------------------------------------------------------------------
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # nvidia-smi needs ~0.2 s to deliver its first sample: start it
+    for _ in range(args.warmup):                                # with the warm-up so that it is sampling during the timed steps
         step()
     barrier()
     if dom is not None and dom.timing is not None:
         dom.timing.clear()          # APBF_MG_TIMING: sections of the timed steps only
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ctx.launch_count
     ctx.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
