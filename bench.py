@@ -166,7 +166,7 @@ def run_reference(args, rank):
                          "sample": f"{sample}: {sc.n} particles, {steps} substep(s) of the {args.workload} workload"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit_line(line)
 
 
 # ---- GPU arm -----------------------------------------------------------------------------------------------------------
@@ -357,12 +357,27 @@ def run_gpu(args, rank, world, local_rank):
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{sample}: {ssc.n} particles, {cpu_steps} substeps of the {args.workload} workload "
                                           f"({sec * cpu_steps:.1f} s of CPU work)"}
-    print(json.dumps(line), flush=True)
+    _emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit_line(line):
+    """the ONE JSON line goes to the process's original stdout (see main(): fd 1 is pointed at stderr while the bench runs,
+    because libraries print there -- NCCL's version banner for one)"""
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    os.write(fd, data)
+
+
+_REAL_STDOUT = None
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
