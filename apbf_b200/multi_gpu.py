@@ -107,8 +107,11 @@ class SlabDomain:
         if self.flat:
             backend.flat_only = True
         if self.world > 1 and hasattr(backend, "init_comm") and getattr(comm, "device", None) is not None and comm.device.type == "cuda" \
-                and not os.environ.get("APBF_MG_PY_LOOP"):
-            backend.init_comm(comm)       # solver loop and its exchanges inside the library (NCCL on the context's stream)
+                and os.environ.get("APBF_MG_C_LOOP"):
+            # APBF_MG_C_LOOP=1: solver loop and its exchanges inside the library (own NCCL communicator, grouped send/recv on the
+            # context's stream, one call per substep).  Measured: no gain at 2 ranks, 4 % slower than one torch all_to_all per
+            # exchange at 4 ranks -- the exchanges are bound by NCCL's latency, not by the host calls around them.  Off by default.
+            backend.init_comm(comm)
 
     # ---- one exchange of `what` for the current send lists / ghost slots ------------------------------------------------------
     def _refresh_ghosts(self, what):
