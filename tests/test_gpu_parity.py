@@ -541,6 +541,30 @@ def test_substeps_default_adaptive_mode_match_oracle(gpu, orc):
     assert len(np.unique(st.boundary_distance)) > 50
 
 
+@pytest.mark.parametrize("mode", ["adaptive", "default_mode"])
+def test_hundred_substeps_stay_sane(gpu, orc, mode):
+    """100 substeps of a small dam break through apbf_sim (north_star's horizon): no overflow flag, every particle still there and
+    inside the pool walls, widths finite, and the density error |rho / rho0 - 1| of the resting bulk stays small"""
+    sc = scenes.dam_break(16, 16, 16, adaptive=True)
+    ctx = gpu.Context(dims=3)
+    ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if mode == "adaptive" else 1, mSmallestTargetRadius=sc.smallest_target_radius)
+    sim = gpu.Sim(ctx, sc, neighbor_capacity=sc.n * 400, integrate=True, basic_pbf=False, update_transfers=(mode == "default_mode"))
+    sc.arrays["position"][:, 3] = np.arange(sc.n, dtype=np.int32)
+    sim.upload(sc.arrays)
+    sim.substep(100)
+    from apbf_b200 import empty_host_arrays
+    out = empty_host_arrays(sc.n)
+    assert sim.download(out) == sc.n and ctx.device_flags() == 0
+    assert sorted(out["position"][:, 3].tolist()) == list(range(sc.n))
+    pos = out["position"][:, :3].astype(np.float64) / 262144.0
+    lo, hi = np.asarray(sc.min_pos), np.asarray(sc.max_pos)
+    assert np.all(pos > lo) and np.all(pos < hi)
+    assert np.all(np.isfinite(out["kernel_width"])) and out["kernel_width"].min() >= 3.9 and out["kernel_width"].max() < 40.0
+    assert np.all(np.isfinite(out["velocity"]))
+    st = sim.stats()
+    assert 10 * sc.n < st["pairs_kept"] < 400 * sc.n
+
+
 def test_box_collision_matches_oracle(gpu, orc):
     sc = scenes.uniform_block(16, jitter=0.3, shuffle=True)
     st = oracle_state(orc, sc)
