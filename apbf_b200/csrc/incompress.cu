@@ -150,9 +150,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
 						const float r2 = dot3(rx, ry, rz, rx, ry, rz);
 						float W; vec3f g;
 						pair_eval<HK, GK>(hp, gp, rx, ry, rz, r2, W, g);
-						dens += (int)f2u(W * mN * R_INC);                                        // :55
-						gx += f2i(g.x * mN * R_INC); gy += f2i(g.y * mN * R_INC); gz += f2i(g.z * mN * R_INC); // :56-58
-						sq += (int)f2u(dot3(g.x, g.y, g.z, g.x, g.y, g.z) * mN * R_INC);         // :59
+						// x / invMassN * 2^18 (:55-59): 2^18 is a power of two, so (x * mN) * 2^18 == x * (mN * 2^18) bit for bit
+						const float mNR = mN * R_INC;
+						dens += (int)f2u(W * mNR);                                               // :55
+						gx += f2i(g.x * mNR); gy += f2i(g.y * mNR); gz += f2i(g.z * mNR);        // :56-58
+						sq += (int)f2u(dot3(g.x, g.y, g.z, g.x, g.y, g.z) * mNR);                // :59
 						if (COM) { // boundariness method 1, :62-68
 							const float div = kg.x / mN; // invMassN * kernelWidth
 							cx += f2i((float)dxi / div); cy += f2i((float)dyi / div); cz += f2i((float)dzi / div);
