@@ -302,6 +302,22 @@ class neighborhood_binary_search(_Operator):
             return {k: v.cpu().numpy().view(np.uint32)[:n] for k, v in keep.items()}
 
 
+class neighborhood_binary_search_spread(neighborhood_binary_search):
+    """neighborhood_binary_search::apply() + spread_kernel_width::apply() in one pass (pool.cpp:83-89 with NEIGHBORHOOD_TYPE 3);
+    not a class of the reference: what the whole-scene substep runs for adaptive widths with the binary search"""
+
+    def apply(self, debug=False):
+        torch = _torch()
+        L = self.lists
+        fl, nb = L.fluid(), L.neighbors()
+        kwfx = torch.zeros(L.capacity, dtype=torch.int32, device=L.words.device) if debug else None
+        _check(self.ctx, self.lib.apbf_neighborhood_binary_search_spread_apply(
+            self.ctx.handle, C.byref(fl), C.byref(nb), self.scale, None, kwfx.data_ptr() if debug else None))
+        L.swap()
+        if debug:
+            return kwfx[:L.length()].cpu().numpy().view(np.uint32)
+
+
 class incompressibility(_Operator):
     """pbd::incompressibility (source/incompressibility.h:8-18)"""
 

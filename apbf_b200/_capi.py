@@ -101,6 +101,7 @@ SIGNATURES = {
                                                 f32p, f32p, C.c_uint32, C.POINTER(SearchDebug)]),
     "apbf_neighborhood_green_spread_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), C.c_float, f32p, f32p,
                                                        C.c_uint32, C.POINTER(SearchDebug), vp]),
+    "apbf_neighborhood_binary_search_spread_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), C.c_float, vp, vp]),
     "apbf_neighborhood_binary_search_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Array), C.POINTER(Neighbors),
                                                         C.c_float, C.POINTER(SearchDebug)]),
     "apbf_incompressibility_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), vp, vp]),

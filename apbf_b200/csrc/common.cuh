@@ -51,6 +51,7 @@ enum apbf_misc_word {
 	MW_EMIT_TICKET0 = 18, // tile tickets of the pair emit (count pass, fill pass)
 	MW_EMIT_TICKET1 = 19,
 	MW_STREAM_CURSOR = 20,   // block allocator of the pair emit's hit stream
+	MW_PMAX = 23,            // binary search fused with the spread: largest |coordinate| of the list (float bits)
 	MW_MAX_INIT = 22,        // fused search + spread: largest initial kernel width (fixed point) over all particles
 	MW_STREAM_OVERFLOW = 21, // the hit stream ran out of blocks (only when the pair list overflows): the two-pass fill takes over
 	MW_WORDS = 64

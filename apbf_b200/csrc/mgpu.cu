@@ -474,7 +474,7 @@ int apbf_sim_mg_phase(apbf_sim* sim, int phase, int iteration)
 			const bool adaptive = !c.basic_pbf && !s.mBaseKernelWidthOnBoundaryDistance; // spread_kernel_width will prune
 			sim->mg_fused = adaptive && !sim->no_fuse;
 			ctx->mg_ghost_all_pairs = adaptive && !sim->mg_fused;
-			ctx->skip_public_pairs = sim->mg_fused || !adaptive;
+			ctx->skip_public_pairs = true; // (the sweeps and a separate spread work on NB + offsets)
 			if (sim->mg_fused) // search + spread_kernel_width in one pass (pool.cpp:83-89), ghosts included
 				APBF_TRY(apbf_neighborhood_green_spread_apply(ctx, &sim->fluid, &sim->nb, 1.5f, c.min_pos, c.max_pos, c.res_log2, nullptr, nullptr));
 			else

@@ -141,6 +141,28 @@ struct build_kw_args {
 	float4*      qb4;    // {K, U, -, original width}: the prune decided on the float-form distance (see k_green_stream)
 };
 
+// Fused search + spread_kernel_width: the per-id record {K, U, -, original width} of the prune (kernel_width.comp:57).
+// The prune compares the distance of the INTEGER difference (kernel_width.comp:36-38), the search the distance of the float
+// positions (neighborhood_green.comp:83).  Both approximate the same squared distance s; with |p| the largest coordinate of
+// the particle and c the cutoff, |d2_float - d2_int| <= 2^-22 (1.73 c (|p| + c) + 2 c^2) for s near c^2 (conversion of the
+// coordinates to float: 2^-24 |p| each; subtraction and the two dot products: a few 2^-24 s).  hw is four times that: a pair
+// with d2_float <= K = C - hw is kept for sure, one with d2_float > U = C + hw is dropped for sure, and only the band in
+// between needs the integer form.  T: threshold of the range test; pmax: largest |coordinate| of the search grid (so that
+// particles of equal cutoff share K and U).
+__device__ __forceinline__ float4 prune_record(float T, float cut, float orig, int4 ip, float pmax)
+{
+	float4 qb = make_float4(T, T, 0.0f, orig); // no prune, never ambiguous (cutoff >= 1e15 or +inf)
+	if (!(cut == cut) || cut < 0.0f) qb.x = qb.y = -1.0f; // keeps nothing
+	else if (cut < 1.0e15f) {
+		const float pm = fmaxf(fmaxf(fmaxf(fabsf((float)ip.x), fabsf((float)ip.y)), fabsf((float)ip.z)) * INV_R_POS, pmax);
+		const float C = sqrt_threshold(cut);
+		const float hw = fmaxf(2.3841858e-7f * cut * (7.0f * (pm + cut) + 8.0f * cut), 1.0e-20f);
+		qb.x = glsl_min(T, C - hw); // kept for sure
+		qb.y = glsl_min(T, C + hw); // kept at most
+	}
+	return qb;
+}
+
 __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const uint32_t* __restrict__ hidden_key,
                            const float* __restrict__ range, float range_scale, const uint32_t* __restrict__ len,
                            float4* __restrict__ q4, uint32_t* __restrict__ key_id, uint32_t* __restrict__ misc, const build_kw_args K)
@@ -160,23 +182,7 @@ __global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_
 			// D2 the same sum over the unscaled integer differences (powers of two commute with the roundings)
 			const float cut = glsl_max(orig, K.kernel_width[id]);
 			K.cutoff[id] = cut == cut ? sqrt_threshold(cut) * 68719476736.0f : -1.0f; // dist <= NaN keeps nothing
-			// The prune compares the distance of the INTEGER difference (kernel_width.comp:36-38), the search the distance
-			// of the float positions (neighborhood_green.comp:83).  Both approximate the same squared distance s; with
-			// |p| the largest coordinate of the particle and c the cutoff, |d2_float - d2_int| <= 2^-22 (1.73 c (|p| + c)
-			// + 2 c^2) for s near c^2 (conversion of the coordinates to float: 2^-24 |p| each; subtraction and the two
-			// dot products: a few 2^-24 s).  hw is four times that: a pair with d2_float <= K = C - hw is kept for sure, one
-			// with d2_float > U = C + hw is dropped for sure, and only the band in between needs the integer form.
-			const float T = sqrt_threshold(range[id] * range_scale);
-			float4 qb = make_float4(T, T, 0.0f, orig); // no prune, never ambiguous (cutoff >= 1e15 or +inf)
-			if (!(cut == cut) || cut < 0.0f) qb.x = qb.y = -1.0f; // keeps nothing
-			else if (cut < 1.0e15f) {
-				// |p|: at least the largest coordinate of the grid, so that particles of equal cutoff share K and U
-				const float pm = fmaxf(fmaxf(fmaxf(fabsf((float)ip.x), fabsf((float)ip.y)), fabsf((float)ip.z)) * INV_R_POS, K.pmax);
-				const float C = sqrt_threshold(cut);
-				const float hw = fmaxf(2.3841858e-7f * cut * (7.0f * (pm + cut) + 8.0f * cut), 1.0e-20f);
-				qb.x = glsl_min(T, C - hw); // kept for sure
-				qb.y = glsl_min(T, C + hw); // kept at most
-			}
+			const float4 qb = prune_record(sqrt_threshold(range[id] * range_scale), cut, orig, ip, K.pmax);
 			K.qb4[id] = qb;
 			atomicMax(K.cell_maxw + hidden_key[idx], f2u(orig * APBF_KERNEL_WIDTH_RESOLUTION)); // (keys of ghosts index the second table)
 			max_init = max(max_init, f2u(orig * APBF_KERNEL_WIDTH_RESOLUTION));
@@ -251,6 +257,10 @@ struct emit_args {
 	uint32_t*       stream;
 	uint32_t        stream_blocks;
 	int             fallback; // two-pass fill kernel: run only if the hit stream overflowed
+	// binary search (SEARCH == 1): sorted 96-bit codes per id, raw positions
+	const uint32_t *c0, *c1, *c2;
+	const int32_t*  pos4;
+	const uint32_t* index_list;
 };
 
 template <bool FILL, int VARIANT, int DIMS>
@@ -513,6 +523,141 @@ k_green_emit(const emit_args A)
 	}
 }
 
+// ---- 96-bit Morton code helpers of the binary search (neighborhood_binary_search.comp:166-276) ---------------------------
+struct u96 { uint32_t v[3]; };
+__device__ __forceinline__ u96 mk96(uint32_t a, uint32_t b, uint32_t c) { u96 r; r.v[0] = a; r.v[1] = b; r.v[2] = c; return r; }
+__device__ __forceinline__ u96 plus96(u96 a, u96 b)
+{
+	u96 r = mk96(a.v[0] + b.v[0], a.v[1] + b.v[1], a.v[2] + b.v[2]);
+	bool y = r.v[0] < a.v[0];
+	bool z = r.v[1] < a.v[1] || (y && r.v[1] == 0xFFFFFFFFu);
+	r.v[1] += y ? 1u : 0u; r.v[2] += z ? 1u : 0u;
+	return r;
+}
+__device__ __forceinline__ u96 minus96(u96 a, u96 b)
+{
+	bool y = a.v[0] < b.v[0];
+	bool z = a.v[1] < b.v[1] || (y && a.v[1] == b.v[1]);
+	return mk96(a.v[0] - b.v[0], a.v[1] - b.v[1] - (y ? 1u : 0u), a.v[2] - b.v[2] - (z ? 1u : 0u));
+}
+__device__ __forceinline__ u96 shl96_small(u96 a, uint32_t s) // s in {1, 2}
+{
+	return mk96(a.v[0] << s, (a.v[1] << s) | (a.v[0] >> (32u - s)), (a.v[2] << s) | (a.v[1] >> (32u - s)));
+}
+__device__ __forceinline__ bool greater96(u96 a, u96 b)
+{
+	if (a.v[2] != b.v[2]) return a.v[2] > b.v[2];
+	if (a.v[1] != b.v[1]) return a.v[1] > b.v[1];
+	return a.v[0] > b.v[0];
+}
+__device__ __forceinline__ u96 and96(u96 a, u96 b) { return mk96(a.v[0] & b.v[0], a.v[1] & b.v[1], a.v[2] & b.v[2]); }
+__device__ __forceinline__ u96 or96(u96 a, u96 b) { return mk96(a.v[0] | b.v[0], a.v[1] | b.v[1], a.v[2] | b.v[2]); }
+__device__ __forceinline__ u96 not96(u96 a) { return mk96(~a.v[0], ~a.v[1], ~a.v[2]); }
+
+__device__ __forceinline__ uint32_t lower_bound96(const uint32_t* __restrict__ c0, const uint32_t* __restrict__ c1,
+                                                  const uint32_t* __restrict__ c2, uint32_t n, u96 code)
+{
+	uint32_t lo = 0u, hi = n;
+	while (lo < hi) {
+		uint32_t mid = lo + ((hi - lo) >> 1);
+		if (greater96(code, mk96(__ldg(c0 + mid), __ldg(c1 + mid), __ldg(c2 + mid)))) lo = mid + 1u; else hi = mid;
+	}
+	return lo;
+}
+
+__device__ __forceinline__ uint32_t upper_bound96(const uint32_t* __restrict__ c0, const uint32_t* __restrict__ c1,
+                                                  const uint32_t* __restrict__ c2, uint32_t n, u96 code)
+{ // first index whose code is greater than `code`
+	uint32_t lo = 0u, hi = n;
+	while (lo < hi) {
+		uint32_t mid = lo + ((hi - lo) >> 1);
+		if (greater96(mk96(__ldg(c0 + mid), __ldg(c1 + mid), __ldg(c2 + mid)), code)) hi = mid; else lo = mid + 1u;
+	}
+	return lo;
+}
+// the cell of a particle in the binary search: level = 3 * ceil(log2(range * 2^18)) low bits masked off its Morton code (:183-190)
+struct bs_cell { u96 center, mask; };
+__device__ __forceinline__ bs_cell bs_cell_of(int4 ip, float r)
+{
+	u96 code;
+	apbf_encode96(ip.x, ip.y, ip.z, code.v);
+	const uint32_t digits = f2u(ceilf(log2f(r * R_POS))) * 3u;
+	bs_cell c;
+	c.mask.v[0] = (digits < 32u ? 1u << digits : 0u) - 1u;
+	c.mask.v[1] = (digits < 64u ? 1u << (max(digits, 32u) - 32u) : 0u) - 1u;
+	c.mask.v[2] = (digits < 96u ? 1u << (max(digits, 64u) - 64u) : 0u) - 1u;
+	c.center = mk96(code.v[0] - (code.v[0] & c.mask.v[0]), code.v[1] - (code.v[1] & c.mask.v[1]), code.v[2] - (code.v[2] & c.mask.v[2]));
+	return c;
+}
+// cell (cx, cy, cz) in {0, 1, 2}^3 around the centre: dilated-integer +-1 per axis (:196-220)
+__device__ __forceinline__ u96 bs_neighbor_cell(const bs_cell& c, int cx, int cy, int cz)
+{
+	const u96 xMask3 = mk96(011111111111u, 022222222222u, 04444444444u);
+	const u96 yMask3 = mk96(022222222222u, 04444444444u, 011111111111u);
+	const u96 zMask3 = mk96(04444444444u, 011111111111u, 022222222222u);
+	const u96 step = plus96(c.mask, mk96(1u, 0u, 0u));
+	u96 x = and96(c.center, xMask3), y = and96(c.center, yMask3), z = and96(c.center, zMask3);
+	if (cx == 0) x = and96(minus96(and96(c.center, xMask3), step), xMask3);
+	if (cx == 2) x = and96(plus96(or96(c.center, not96(xMask3)), step), xMask3);
+	if (cy == 0) y = and96(minus96(and96(c.center, yMask3), shl96_small(step, 1u)), yMask3);
+	if (cy == 2) y = and96(plus96(or96(c.center, not96(yMask3)), shl96_small(step, 1u)), yMask3);
+	if (cz == 0) z = and96(minus96(and96(c.center, zMask3), shl96_small(step, 2u)), zMask3);
+	if (cz == 2) z = and96(plus96(or96(c.center, not96(zMask3)), shl96_small(step, 2u)), zMask3);
+	return or96(or96(x, y), z);
+}
+
+// largest |coordinate| over the list (float bits; non-negative floats order like unsigned integers)
+__global__ void k_max_abs_coord(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const uint32_t* __restrict__ len,
+                                uint32_t* __restrict__ misc)
+{
+	const bool ident = misc[MW_IDENTITY] != 0u;
+	const uint32_t n = *len;
+	float m = 0.0f;
+	for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+		const int4 ip = ldg_int4(pos4, ident ? id : index_list[id]);
+		m = fmaxf(m, fmaxf(fmaxf(fabsf((float)ip.x), fabsf((float)ip.y)), fabsf((float)ip.z)) * INV_R_POS);
+	}
+	const uint32_t am = __activemask();
+	const uint32_t mx = __reduce_max_sync(am, __float_as_uint(m));
+	if ((am & ((1u << lane_id()) - 1u)) == 0u) atomicMax(misc + MW_PMAX, mx);
+}
+
+// binary search, per id: packed float position + threshold of "d <= range" (a NaN range rejects everything here), and a flag
+// where the particle's cell (level and centre) differs from its predecessor's: the stream emit takes runs of equal cells as
+// its chunks of queries
+__global__ void k_build_bq(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const float* __restrict__ range,
+                           float range_scale, const uint32_t* __restrict__ len, float4* __restrict__ q4, uint32_t* __restrict__ head,
+                           const uint32_t* __restrict__ misc, const build_kw_args K)
+{
+	const bool ident = misc[MW_IDENTITY] != 0u;
+	const uint32_t n = *len;
+	for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+		const uint32_t idx = ident ? id : index_list[id];
+		const int4 ip = ldg_int4(pos4, idx);
+		const float r = range[id] * range_scale;
+		const float T = r == r ? sqrt_threshold(r) : -1.0f;
+		q4[id] = make_float4((float)ip.x * INV_R_POS, (float)ip.y * INV_R_POS, (float)ip.z * INV_R_POS, T);
+		if (K.i4) { // fused with spread_kernel_width (see k_build_q4)
+			const float orig = glsl_max(K.radius[idx], K.base_on_target_radius ? K.target_radius[id] : 0.0f) * APBF_KERNEL_SCALE;
+			K.i4[id] = make_int4(ip.x, ip.y, ip.z, __float_as_int(orig));
+			const float cut = glsl_max(orig, K.kernel_width[id]);
+			K.cutoff[id] = cut == cut ? sqrt_threshold(cut) * 68719476736.0f : -1.0f;
+			// |p| of the band: the list's largest coordinate rounded up to a power of two (the same for everybody, and stable
+			// from substep to substep, so that particles of equal cutoff share K and U)
+			const float pm = exp2f(ceilf(log2f(fmaxf(__uint_as_float(misc[MW_PMAX]), 1.0f))));
+			K.qb4[id] = prune_record(T, cut, orig, ip, pm);
+		}
+		uint32_t h = 1u;
+		if (id > 0u) {
+			const bs_cell a = bs_cell_of(ip, r);
+			const bs_cell b = bs_cell_of(ldg_int4(pos4, ident ? id - 1u : index_list[id - 1u]), range[id - 1u] * range_scale);
+			h = (a.center.v[0] != b.center.v[0] || a.center.v[1] != b.center.v[1] || a.center.v[2] != b.center.v[2] ||
+			     a.mask.v[0] != b.mask.v[0] || a.mask.v[1] != b.mask.v[1] || a.mask.v[2] != b.mask.v[2]) ? 1u : 0u;
+		}
+		head[id] = h;
+	}
+}
+
 // ---- one-pass pair emit: hit stream + regroup ---------------------------------------------------------------------------
 // k_green_emit tests every (query, candidate) twice: once to count, once to fill.  k_green_stream tests once.
 //   * QUERIES: a warp takes a window of 32 ids by ticket and handles every block of cells whose first particle lies in
@@ -605,7 +750,9 @@ __device__ __forceinline__ void chunk_tests(const float4* __restrict__ sq, const
 	if (MODE == 2) { colM = colK; colMu = colU; }
 }
 
-template <int VARIANT, int DIMS, bool STATS>
+// SEARCH: 0 = uniform grid (neighborhood_green), 1 = 96-bit Morton code with per-particle power-of-two cells
+// (neighborhood_binary_search): key_id holds run numbers of equal cells, a chunk's candidates are the 27 key ranges around it
+template <int VARIANT, int DIMS, bool STATS, int SEARCH = 0>
 __global__ void __launch_bounds__(EMIT_WARPS * 32, 4)
 k_green_stream(const emit_args A)
 {
@@ -624,7 +771,7 @@ k_green_stream(const emit_args A)
 	// block = 2^gshift cells with about 32 particles, from the mean occupancy of the occupied cells
 	const uint32_t occupied = max(A.misc[MW_OCC_CELLS], 1u);
 	const uint32_t per32 = (uint32_t)min((32ull * occupied) / max(n, 1u), 64ull);
-	const uint32_t gshift = min(per32 > 1u ? 31u - (uint32_t)__clz((int)per32) : 0u, g.res * (uint32_t)DIMS);
+	const uint32_t gshift = SEARCH == 1 ? 0u : min(per32 > 1u ? 31u - (uint32_t)__clz((int)per32) : 0u, g.res * (uint32_t)DIMS);
 	float csz[3], eps[3];
 #pragma unroll
 	for (int d = 0; d < 3; d++) {
@@ -681,7 +828,7 @@ k_green_stream(const emit_args A)
 					const uint32_t mx0 = __reduce_min_sync(0xffffffffu, valid ? f2u(qb.w * APBF_KERNEL_WIDTH_RESOLUTION) : 0xFFFFFFFFu);
 					if (A.misc[MW_MAX_INIT] <= mx0 && r == r) r = fminf(r, sqrtf(fmaxf(qb.y, 0.0f)) * 1.0001f);
 				}
-				if (valid) {
+				if (valid && SEARCH == 0) {
 					gmin[0] = apbf_map_axis(me.x - r, g, 0); gmax[0] = apbf_map_axis(me.x + r, g, 0);
 					gmin[1] = apbf_map_axis(me.y - r, g, 1); gmax[1] = apbf_map_axis(me.y + r, g, 1);
 					gmin[2] = apbf_map_axis(me.z - r, g, 2); gmax[2] = apbf_map_axis(me.z + r, g, 2);
@@ -725,14 +872,26 @@ k_green_stream(const emit_args A)
 					keep2 = fminf(cull2, fmaxf(u_max, 0.0f) * 1.0001f);
 					min_mx0 = __reduce_min_sync(0xffffffffu, valid ? my_mx : 0xFFFFFFFFu);
 				}
-				const uint32_t nxy = ext[0] * ext[1], ncell = nxy * ext[2];
+				const uint32_t nxy = ext[0] * ext[1], ncell = SEARCH == 1 ? 27u : nxy * ext[2];
 				const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)ext[0];
 				const bool ghost_run = MG && first >= n_owned;
 				const uint32_t n_layers = layers > 1u ? 2u : 1u;
+				uint32_t bs_first = 0u, bs_cnt = 0u;
+				if (SEARCH == 1 && lane < 27u) {
+					// the 27 cells around the chunk's cell, in the reference's loop order (z outer, x inner), as ranges of the
+					// sorted codes: [first code >= cell, first code > cell | mask)
+					const bool ident = A.misc[MW_IDENTITY] != 0u;
+					const bs_cell c = bs_cell_of(ldg_int4(A.pos4, ident ? first : A.index_list[first]), A.range[first] * A.range_scale);
+					const u96 cell = bs_neighbor_cell(c, (int)(lane % 3u), (int)((lane / 3u) % 3u), (int)(lane / 9u));
+					bs_first = lower_bound96(A.c0, A.c1, A.c2, n, cell);
+					bs_cnt = upper_bound96(A.c0, A.c1, A.c2, n, or96(cell, c.mask)) - bs_first;
+				}
 				for (uint32_t cbase = 0; cbase < ncell * n_layers; cbase += 32) {
 					uint32_t ci = cbase + lane;
 					uint32_t c_first = 0u, c_cnt = 0u;
-					if (ci < ncell * n_layers) {
+					if (SEARCH == 1) {
+						c_first = bs_first; c_cnt = bs_cnt;
+					} else if (ci < ncell * n_layers) {
 						const uint32_t table_off = ci >= ncell ? A.table_cells : 0u;
 						if (ci >= ncell) ci -= ncell;
 						// ci = (cz * ny + cy) * nx + cx; float reciprocals + one correction step are exact for ci < 2^24
@@ -986,56 +1145,16 @@ k_regroup(const uint32_t* __restrict__ stream, uint32_t stream_blocks, const uin
 	if ((threadIdx.x & 31u) == 0u && n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
 }
 
-// ---- binary-search pair emit (neighborhood_binary_search.comp:166-276) ----------------------------------------------
-struct u96 { uint32_t v[3]; };
-__device__ __forceinline__ u96 mk96(uint32_t a, uint32_t b, uint32_t c) { u96 r; r.v[0] = a; r.v[1] = b; r.v[2] = c; return r; }
-__device__ __forceinline__ u96 plus96(u96 a, u96 b)
-{
-	u96 r = mk96(a.v[0] + b.v[0], a.v[1] + b.v[1], a.v[2] + b.v[2]);
-	bool y = r.v[0] < a.v[0];
-	bool z = r.v[1] < a.v[1] || (y && r.v[1] == 0xFFFFFFFFu);
-	r.v[1] += y ? 1u : 0u; r.v[2] += z ? 1u : 0u;
-	return r;
-}
-__device__ __forceinline__ u96 minus96(u96 a, u96 b)
-{
-	bool y = a.v[0] < b.v[0];
-	bool z = a.v[1] < b.v[1] || (y && a.v[1] == b.v[1]);
-	return mk96(a.v[0] - b.v[0], a.v[1] - b.v[1] - (y ? 1u : 0u), a.v[2] - b.v[2] - (z ? 1u : 0u));
-}
-__device__ __forceinline__ u96 shl96_small(u96 a, uint32_t s) // s in {1, 2}
-{
-	return mk96(a.v[0] << s, (a.v[1] << s) | (a.v[0] >> (32u - s)), (a.v[2] << s) | (a.v[1] >> (32u - s)));
-}
-__device__ __forceinline__ bool greater96(u96 a, u96 b)
-{
-	if (a.v[2] != b.v[2]) return a.v[2] > b.v[2];
-	if (a.v[1] != b.v[1]) return a.v[1] > b.v[1];
-	return a.v[0] > b.v[0];
-}
-__device__ __forceinline__ u96 and96(u96 a, u96 b) { return mk96(a.v[0] & b.v[0], a.v[1] & b.v[1], a.v[2] & b.v[2]); }
-__device__ __forceinline__ u96 or96(u96 a, u96 b) { return mk96(a.v[0] | b.v[0], a.v[1] | b.v[1], a.v[2] | b.v[2]); }
-__device__ __forceinline__ u96 not96(u96 a) { return mk96(~a.v[0], ~a.v[1], ~a.v[2]); }
-
-__device__ __forceinline__ uint32_t lower_bound96(const uint32_t* __restrict__ c0, const uint32_t* __restrict__ c1,
-                                                  const uint32_t* __restrict__ c2, uint32_t n, u96 code)
-{
-	uint32_t lo = 0u, hi = n;
-	while (lo < hi) {
-		uint32_t mid = lo + ((hi - lo) >> 1);
-		if (greater96(code, mk96(__ldg(c0 + mid), __ldg(c1 + mid), __ldg(c2 + mid)))) lo = mid + 1u; else hi = mid;
-	}
-	return lo;
-}
-
+// ---- binary-search pair emit, two-pass form (overflow fallback of the stream form) ----------------------------------------
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_bsearch_emit(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const uint32_t* __restrict__ c0,
                const uint32_t* __restrict__ c1, const uint32_t* __restrict__ c2, const float* __restrict__ range,
                const uint32_t* __restrict__ len, float range_scale, uint32_t* __restrict__ counts,
                const uint32_t* __restrict__ offsets, uint32_t* __restrict__ pairs, uint32_t cap, uint32_t* __restrict__ nbl,
-               uint32_t* misc)
+               uint32_t* misc, int fallback)
 {
+	if (fallback && misc[MW_STREAM_OVERFLOW] == 0u) return; // only if the hit stream of the one-pass emit overflowed
 	const uint32_t n = *len;
 	const bool ident = misc[MW_IDENTITY] != 0u;
 	const u96 xMask3 = mk96(011111111111u, 022222222222u, 04444444444u);
@@ -1100,7 +1219,7 @@ k_bsearch_emit(const uint32_t* __restrict__ index_list, const int32_t* __restric
 __global__ void k_clear_search_words(uint32_t* misc)
 {
 	misc[MW_N_ASYM] = 0u; misc[MW_TOTAL_PAIRS] = 0u; misc[MW_KEPT_PAIRS] = 0xFFFFFFFFu; misc[MW_OCC_CELLS] = 0u;
-	misc[MW_EMIT_TICKET0] = 0u; misc[MW_EMIT_TICKET1] = 0u; misc[MW_STREAM_CURSOR] = 0u; misc[MW_STREAM_OVERFLOW] = 0u; misc[MW_MAX_INIT] = 0u;
+	misc[MW_EMIT_TICKET0] = 0u; misc[MW_EMIT_TICKET1] = 0u; misc[MW_STREAM_CURSOR] = 0u; misc[MW_STREAM_OVERFLOW] = 0u; misc[MW_MAX_INIT] = 0u; misc[MW_PMAX] = 0u;
 }
 
 // shared front half of both searches: gather hidden arrays by sorted_index, rebuild the index list, gather per-id arrays
@@ -1355,16 +1474,23 @@ int apbf_neighborhood_green_spread_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_
 	return green_search(ctx, fluid, &fluid->kernel_width, nb, range_scale, min_pos, max_pos, res_log2, dbg, true, out_kw_fixed);
 }
 
-int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb,
-                                          float range_scale, const apbf_search_debug* dbg)
+} // extern "C"
+
+namespace {
+// neighborhood_binary_search::apply (neighborhood_binary_search.cpp:22-75); fuse_kw: followed by spread_kernel_width::apply on
+// the same lists with range == fluid->kernel_width (pool.cpp:83-89 with NEIGHBORHOOD_TYPE 3)
+int binary_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb, float range_scale,
+                  const apbf_search_debug* dbg, bool fuse_kw, uint32_t* out_kw_fixed)
 {
 	if (!ctx) return APBF_ERR_INVALID;
 	APBF_REQUIRE(ctx, fluid && range && nb);
 	APBF_REQUIRE(ctx, nb->pairs && nb->length && fluid->particle.length && fluid->particle.hidden_length);
+	APBF_REQUIRE(ctx, !ctx->mg_enabled); // slabs partition by the grid key of the Green search
 	apbf_particles& p = fluid->particle;
 	cudaStream_t st = ctx->stream;
 	const uint32_t nh_cap = p.hidden_capacity, n_cap = p.capacity;
 	if (nh_cap == 0 || n_cap == 0) { APBF_CUDA(ctx, cudaMemsetAsync(nb->length, 0, 4, st)); return APBF_OK; }
+	if (fuse_kw) APBF_REQUIRE(ctx, p.radius.data && fluid->target_radius.data && fluid->kernel_width.data);
 	uint32_t* misc = ctx->misc();
 	uint32_t* code = (uint32_t*)ctx->scratch_get(SLOT_SORT_KEYS_A, sizeof(uint32_t) * (size_t)nh_cap);
 	uint32_t* scode = (uint32_t*)ctx->scratch_get(SLOT_TMP_KEYS, sizeof(uint32_t) * (size_t)nh_cap);
@@ -1382,14 +1508,20 @@ int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, cons
 	// three stable 32-bit sorts, least significant section first (neighborhood_binary_search.cpp:45-51)
 	const uint32_t* cur = nullptr; // nullptr == identity payload
 	uint32_t* ping[2] = { idx_a, idx_b };
-	for (uint32_t sec = 0; sec < 3u; sec++) {
-		APBF_TRY(apbf_launch_position_code(ctx, cur, (const int32_t*)p.position.data, code, p.hidden_length, nh_cap, sec));
-		uint32_t* dst = ping[sec & 1u];
-		APBF_TRY(apbf_radix_sort_pairs(ctx, code, cur, scode, dst, p.hidden_length, nh_cap, 32));
-		cur = dst;
+	{
+		apbf_prof_scope ps(ctx, PROF_HASH_SORT);
+		for (uint32_t sec = 0; sec < 3u; sec++) {
+			APBF_TRY(apbf_launch_position_code(ctx, cur, (const int32_t*)p.position.data, code, p.hidden_length, nh_cap, sec));
+			uint32_t* dst = ping[sec & 1u];
+			APBF_TRY(apbf_radix_sort_pairs(ctx, code, cur, scode, dst, p.hidden_length, nh_cap, 32));
+			cur = dst;
+		}
 	}
 	const uint32_t* sidx = cur;
-	APBF_TRY(reorder_lists(ctx, fluid, range, sidx)); // :53-54
+	{
+		apbf_prof_scope ps(ctx, PROF_REORDER);
+		APBF_TRY(reorder_lists(ctx, fluid, range, sidx)); // :53-54
+	}
 	const uint32_t* new_index = (const uint32_t*)p.index_list.reorder_out;
 	const int32_t* new_pos = (const int32_t*)p.position.reorder_out;
 	const float* new_range = (const float*)range->reorder_out;
@@ -1398,13 +1530,77 @@ int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, cons
 	k_clear_search_words<<<1, 1, 0, st>>>(misc);
 	APBF_LAUNCHED(ctx);
 	const unsigned grid = apbf_grid(ctx, n_cap, 128, 16);
-	k_bsearch_emit<false><<<grid, 128, 0, st>>>(new_index, new_pos, c[0], c[1], c[2], new_range, p.length, range_scale, counts,
-	                                            nullptr, nullptr, 0u, nullptr, misc);
-	APBF_LAUNCHED(ctx);
-	APBF_TRY(apbf_scan_u32(ctx, counts, offsets, p.length, n_cap, false, nb->length, nb->capacity, misc + MW_FLAGS, misc + MW_TOTAL_PAIRS));
-	k_bsearch_emit<true><<<grid, 128, 0, st>>>(new_index, new_pos, c[0], c[1], c[2], new_range, p.length, range_scale, nullptr,
-	                                           offsets, nb->pairs, nb->capacity, nbl, misc);
-	APBF_LAUNCHED(ctx);
+	static const int two_pass_env = getenv("APBF_TWO_PASS_EMIT") ? 1 : 0; // debugging aid: per-thread count/fill instead of stream/regroup
+	const int two_pass = two_pass_env && !fuse_kw;
+	build_kw_args K;
+	memset(&K, 0, sizeof K);
+	uint32_t* kwfx = nullptr;
+	if (fuse_kw) {
+		K.i4 = (int4*)ctx->scratch_get(SLOT_I4, sizeof(int4) * (size_t)n_cap);
+		K.cutoff = (float*)ctx->scratch_get(SLOT_CUTOFF, sizeof(float) * (size_t)n_cap);
+		K.qb4 = (float4*)ctx->scratch_get(SLOT_QB4, sizeof(float4) * (size_t)n_cap);
+		kwfx = (uint32_t*)ctx->scratch_get(SLOT_KWFX, sizeof(uint32_t) * (size_t)n_cap);
+		if (!K.i4 || !K.cutoff || !K.qb4 || !kwfx) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+		K.radius = (const float*)p.radius.reorder_out;
+		K.target_radius = (const float*)fluid->target_radius.reorder_out;
+		K.kernel_width = (const float*)fluid->kernel_width.reorder_out;
+		K.base_on_target_radius = ctx->settings.mBaseKernelWidthOnTargetRadius;
+	}
+	// one-pass emit (see k_green_stream): chunks of queries = runs of equal cells, candidates = the 27 code ranges around the cell
+	float4* q4 = (float4*)ctx->scratch_get(SLOT_Q4, sizeof(float4) * (size_t)n_cap);
+	uint32_t* key_id = (uint32_t*)ctx->scratch_get(SLOT_KEY_ID, sizeof(uint32_t) * (size_t)n_cap);
+	uint32_t* head = (uint32_t*)ctx->scratch_get(SLOT_KEEP_COUNTS, sizeof(uint32_t) * (size_t)(n_cap + 1));
+	uint32_t stream_blocks = (uint32_t)std::min<size_t>((size_t)nb->capacity / SB_ENTRIES + (size_t)n_cap / 8u + 1024u, 0x7FFFFFFFu);
+	if (ctx->stream_blocks_cap) stream_blocks = std::min(stream_blocks, std::max(ctx->stream_blocks_cap, 1u));
+	uint32_t* stream = (uint32_t*)ctx->scratch_get(SLOT_STREAM, sizeof(uint32_t) * (size_t)stream_blocks * SB_WORDS);
+	if (!q4 || !key_id || !head || !stream) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+	{
+		apbf_prof_scope ps(ctx, PROF_EMIT_COUNT);
+		if (two_pass) {
+			k_bsearch_emit<false><<<grid, 128, 0, st>>>(new_index, new_pos, c[0], c[1], c[2], new_range, p.length, range_scale, counts,
+			                                            nullptr, nullptr, 0u, nullptr, misc, 0);
+			APBF_LAUNCHED(ctx);
+		} else {
+			if (fuse_kw) {
+				k_max_abs_coord<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>(new_index, new_pos, p.length, misc);
+				APBF_LAUNCHED(ctx);
+			}
+			k_build_bq<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>(new_index, new_pos, new_range, range_scale, p.length, q4, head, misc, K);
+			APBF_LAUNCHED(ctx);
+			APBF_TRY(apbf_scan_u32(ctx, head, key_id, p.length, n_cap, true, nullptr, 0xFFFFFFFFu, nullptr, nullptr));
+			emit_args A;
+			memset(&A, 0, sizeof A);
+			A.q4 = q4; A.key_id = key_id; A.range = new_range; A.len = p.length; A.range_scale = range_scale; A.counts = counts;
+			A.offsets = offsets; A.pairs = nb->pairs; A.nbl = nbl; A.cap = nb->capacity; A.misc = misc; A.table_cells = 1u; A.layers = 1u;
+			A.g.ext[0] = A.g.ext[1] = A.g.ext[2] = 1.0f; A.g.scale = 1.0f; A.g.res = 1u; A.g.dims = 3; // (no grid in this search)
+			A.stream = stream; A.stream_blocks = stream_blocks; A.ticket = misc + MW_EMIT_TICKET0;
+			A.c0 = c[0]; A.c1 = c[1]; A.c2 = c[2]; A.pos4 = new_pos; A.index_list = new_index;
+			A.i4 = K.i4; A.cutoff = K.cutoff; A.qb4 = K.qb4; A.kwfx = kwfx;
+			const unsigned sgrid = apbf_grid(ctx, n_cap, EMIT_WARPS * 32, 4);
+			if (!fuse_kw) k_green_stream<EMIT_PLAIN, 3, false, 1><<<sgrid, EMIT_WARPS * 32, 0, st>>>(A);
+			else if (ctx->search_stats) k_green_stream<EMIT_FUSED, 3, true, 1><<<sgrid, EMIT_WARPS * 32, 0, st>>>(A);
+			else k_green_stream<EMIT_FUSED, 3, false, 1><<<sgrid, EMIT_WARPS * 32, 0, st>>>(A);
+			APBF_LAUNCHED(ctx);
+		}
+	}
+	{
+		apbf_prof_scope ps(ctx, PROF_EMIT_SCAN);
+		APBF_TRY(apbf_scan_u32(ctx, counts, offsets, p.length, n_cap, false, nb->length, nb->capacity, misc + MW_FLAGS,
+		                       misc + (fuse_kw ? MW_KEPT_PAIRS : MW_TOTAL_PAIRS)));
+	}
+	{
+		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
+		if (!two_pass) {
+			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, ctx->skip_public_pairs ? nullptr : nb->pairs, nbl,
+			                                                    nb->capacity, misc, fuse_kw ? 1 : 0);
+			APBF_LAUNCHED(ctx);
+		}
+		if (!fuse_kw) { // (the fused form has no two-pass fill behind it: a stream overflow raises the sticky flag)
+			k_bsearch_emit<true><<<grid, 128, 0, st>>>(new_index, new_pos, c[0], c[1], c[2], new_range, p.length, range_scale, nullptr,
+			                                           offsets, nb->pairs, nb->capacity, nbl, misc, two_pass ? 0 : 1);
+			APBF_LAUNCHED(ctx);
+		}
+	}
 	ctx->nbr_struct_pairs = nb->pairs;
 	ctx->nbr_struct_n_cap = n_cap;
 	if (dbg) {
@@ -1413,7 +1609,30 @@ int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, cons
 			if (dbg->code[s]) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->code[s], c[s], sizeof(uint32_t) * (size_t)n_cap, cudaMemcpyDeviceToDevice, st));
 		if (dbg->pair_offsets) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->pair_offsets, offsets, sizeof(uint32_t) * (size_t)(n_cap + 1), cudaMemcpyDeviceToDevice, st));
 	}
+	if (fuse_kw) { // the reordered lists are still in reorder_out (the caller swaps after the search)
+		apbf_fluid sorted = *fluid;
+		sorted.kernel_width.data = fluid->kernel_width.reorder_out;
+		apbf_prof_scope ps(ctx, PROF_KW_MISC);
+		APBF_TRY(apbf_kw_finish(ctx, &sorted, out_kw_fixed));
+	}
 	return APBF_OK;
+}
+} // namespace
+
+extern "C" {
+
+int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb,
+                                          float range_scale, const apbf_search_debug* dbg)
+{
+	return binary_search(ctx, fluid, range, nb, range_scale, dbg, false, nullptr);
+}
+
+int apbf_neighborhood_binary_search_spread_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighbors* nb, float range_scale,
+                                                 const apbf_search_debug* dbg, uint32_t* out_kw_fixed)
+{
+	if (!ctx) return APBF_ERR_INVALID;
+	APBF_REQUIRE(ctx, fluid);
+	return binary_search(ctx, fluid, &fluid->kernel_width, nb, range_scale, dbg, true, out_kw_fixed);
 }
 
 } // extern "C"

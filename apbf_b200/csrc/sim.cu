@@ -173,9 +173,11 @@ int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
 			APBF_TRY(apbf_kernel_width_from_boundary_distance(ctx, &sim->fluid));
 		const float scale = unit_scale ? 1.0f : 1.5f;
 		// pool.cpp:83-89.  Green search followed by spread_kernel_width runs as one fused pass (same lists, pair for pair)
-		const bool fused = adaptive && !c.use_binary_search && !ctx->mg_enabled && !sim->no_fuse;
-		ctx->skip_public_pairs = !c.use_binary_search && (fused || !adaptive); // the sweeps read NB; a separate spread rewrites the pairs
-		if (c.use_binary_search)                                                      // pool.cpp:83-84
+		const bool fused = adaptive && !ctx->mg_enabled && !sim->no_fuse;
+		ctx->skip_public_pairs = true; // nothing reads the (id, idN) list: the sweeps and a separate spread work on NB + offsets
+		if (c.use_binary_search && fused)
+			APBF_TRY(apbf_neighborhood_binary_search_spread_apply(ctx, &sim->fluid, &sim->nb, scale, nullptr, nullptr));
+		else if (c.use_binary_search)                                                 // pool.cpp:83-84
 			APBF_TRY(apbf_neighborhood_binary_search_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, nullptr));
 		else if (fused)
 			APBF_TRY(apbf_neighborhood_green_spread_apply(ctx, &sim->fluid, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, nullptr, nullptr));

@@ -200,7 +200,7 @@ def run_gpu(args, rank, world, local_rank):
         arrays, n, n_total, capacity = sc.arrays, sc.n, sc.n * world, sc.n
     cap = capacity * meta["pairs_per_particle"]
     sim = apbf_b200.Sim(ctx, sc, capacity=capacity, neighbor_capacity=cap, integrate=True, basic_pbf=meta.get("basic_pbf", not meta["adaptive"]),
-                        update_transfers=bool(meta.get("update_transfers")))
+                        update_transfers=bool(meta.get("update_transfers")), use_binary_search=(args.search == "binary"))
 
     # host copies of the lists in pinned memory (the e2e leg streams them in every step)
     host = {}
@@ -330,7 +330,7 @@ def run_gpu(args, rank, world, local_rank):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32+i32", "data": "synthetic",
         "config": {"workload": args.workload, "scene": sc.name, "particles_per_gpu": n, "adaptive_kernel_width": meta["adaptive"],
-                   "solver_iterations": sc.solver_iterations, "search": "green", "res_log2": sc.res_log2,
+                   "solver_iterations": sc.solver_iterations, "search": args.search, "res_log2": sc.res_log2,
                    "pairs_searched": stats["pairs_searched"], "pairs_kept": stats["pairs_kept"],
                    "pairs_unmirrored": stats["pairs_unmirrored"],
                    "multi_gpu": "single" if world == 1 else ("one scene in bricks (top key bits), halo exchange over NCCL send/recv" if slab
@@ -386,6 +386,8 @@ def main():
     ap.add_argument("--workload", default="dam_break_1M")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--search", default="green", choices=["green", "binary"],
+                    help="neighborhood_green (default, pool.cpp NEIGHBORHOOD_TYPE 1) or neighborhood_binary_search (type 3; 1 GPU only)")
     ap.add_argument("--replicas", action="store_true", help="N > 1: N independent copies of the 1-GPU scene instead of one scene in bricks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

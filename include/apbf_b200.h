@@ -237,6 +237,11 @@ int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_a
 int apbf_neighborhood_green_spread_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighbors* neighbors, float range_scale,
                                          const float min_pos[3], const float max_pos[3], uint32_t res_log2,
                                          const apbf_search_debug* debug, uint32_t* out_kw_fixed);
+/* The same fusion for the binary search (NEIGHBORHOOD_TYPE 3): neighborhood_binary_search::apply() followed by
+ * spread_kernel_width::apply() on the same lists with range = kernel_width (pool.cpp:83-89).  Same lists afterwards, pair for
+ * pair, as calling the two entry points in turn. */
+int apbf_neighborhood_binary_search_spread_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighbors* neighbors, float range_scale,
+                                                 const apbf_search_debug* debug, uint32_t* out_kw_fixed);
 /* pbd::neighborhood_binary_search::set_data(...).set_range_scale(s).apply() (source/neighborhood_binary_search.cpp:22-75) */
 int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range,
                                           apbf_neighbors* neighbors, float range_scale, const apbf_search_debug* debug);

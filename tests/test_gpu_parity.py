@@ -378,6 +378,36 @@ def test_fused_search_spread_matches_two_operators(gpu, orc, base_on_target_radi
     _check_incompressibility(ga, ea, L.read("position"), st.position, before)
 
 
+@pytest.mark.parametrize("base_on_target_radius", [0, 1])
+def test_fused_binary_search_spread_matches_two_operators(gpu, orc, base_on_target_radius):
+    """apbf_neighborhood_binary_search_spread_apply against the oracle's neighborhood_binary_search + spread_kernel_width: widths,
+    kept pairs in order, new kernel widths -- bit exact"""
+    sc = scenes.waterdrop(22, jitter=0.1)
+    sc.arrays["target_radius"] = (sc.arrays["target_radius"] * np.random.default_rng(5).choice([1.0, 1.5], sc.n)).astype(np.float32)
+    s = orc.default_settings()
+    s.mBaseKernelWidthOnBoundaryDistance = 0
+    s.mBaseKernelWidthOnTargetRadius = base_on_target_radius
+    cap = sc.n * 700
+    st = oracle_state(orc, sc)
+    epairs = orc.binary_search_apply(st, s, 1.5, cap)
+    ekept, ekw = orc.spread_kernel_width_apply(st, s, epairs)
+    assert 0 < len(ekept) < len(epairs)
+    ctx = gpu.Context(dims=3)
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=len(ekept) + 7)
+    gkw = gpu.neighborhood_binary_search_spread(ctx).set_data(L).set_range_scale(1.5).apply(debug=True)
+    assert ctx.device_flags() == 0
+    assert np.array_equal(gkw, ekw)
+    assert np.array_equal(L.read_pairs(), ekept)
+    assert np.array_equal(L.read("kernel_width"), st.kernel_width)
+    for k in ("position", "radius", "target_radius", "index_list"):
+        assert np.array_equal(L.read(k), getattr(st, k)), k
+    before = st.position.copy()
+    ea = orc.incompressibility_apply(st, s, 3, ekept, want_aux=True)
+    ga = gpu.incompressibility(ctx).set_data(L).apply(debug=True)
+    _check_incompressibility(ga, ea, L.read("position"), st.position, before)
+
+
 @pytest.mark.parametrize("fused", [False, True])
 def test_stream_overflow_falls_back_to_two_pass_fill(gpu, orc, fused):
     """The one-pass emit writes its hits into a block stream (csrc/neighbors.cu: k_green_stream / k_regroup); when the stream
