@@ -1145,6 +1145,20 @@ k_regroup(const uint32_t* __restrict__ stream, uint32_t stream_blocks, const uin
 	if ((threadIdx.x & 31u) == 0u && n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
 }
 
+// the public (id, idN) list from the grouped 4-byte list: 8 lanes per particle walk its segment, coalesced on both sides
+// (writing the 8-byte pairs from the regroup scatters them over partially filled sectors and costs three times as much)
+__global__ void __launch_bounds__(256)
+k_expand_pairs(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ nbl, const uint32_t* __restrict__ len,
+               uint32_t* __restrict__ pairs, uint32_t cap)
+{
+	const uint32_t n = *len;
+	const unsigned sub = threadIdx.x & 7u;
+	for (uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; a < n; a += (gridDim.x * blockDim.x) >> 3) {
+		const uint32_t beg = min(offsets[a], cap), end = min(offsets[a + 1], cap);
+		for (uint32_t e = beg + sub; e < end; e += 8u) *(uint2*)(pairs + 2 * (size_t)e) = make_uint2(a, nbl[e] & NB_ID_MASK);
+	}
+}
+
 // ---- binary-search pair emit, two-pass form (overflow fallback of the stream form) ----------------------------------------
 template <bool FILL>
 __global__ void __launch_bounds__(128)
@@ -1423,9 +1437,13 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
 		if (!two_pass) {
-			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, ctx->skip_public_pairs ? nullptr : nb->pairs, nbl, nb->capacity, misc,
+			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, nullptr, nbl, nb->capacity, misc,
 			                                                    variant == EMIT_FUSED_MG ? 1 : 0);
 			APBF_LAUNCHED(ctx);
+			if (!ctx->skip_public_pairs) {
+				k_expand_pairs<<<apbf_grid(ctx, (size_t)n_cap * 8, 256, 32), 256, 0, st>>>(offsets, nbl, p.length, nb->pairs, nb->capacity);
+				APBF_LAUNCHED(ctx);
+			}
 		}
 		if (variant != EMIT_FUSED_MG) { // (fused + slabs has no two-pass form: an overflow there only raises the sticky flag)
 			A.ticket = misc + MW_EMIT_TICKET1;
@@ -1591,9 +1609,12 @@ int binary_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apb
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
 		if (!two_pass) {
-			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, ctx->skip_public_pairs ? nullptr : nb->pairs, nbl,
-			                                                    nb->capacity, misc, fuse_kw ? 1 : 0);
+			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, nullptr, nbl, nb->capacity, misc, fuse_kw ? 1 : 0);
 			APBF_LAUNCHED(ctx);
+			if (!ctx->skip_public_pairs) {
+				k_expand_pairs<<<apbf_grid(ctx, (size_t)n_cap * 8, 256, 32), 256, 0, st>>>(offsets, nbl, p.length, nb->pairs, nb->capacity);
+				APBF_LAUNCHED(ctx);
+			}
 		}
 		if (!fuse_kw) { // (the fused form has no two-pass fill behind it: a stream overflow raises the sticky flag)
 			k_bsearch_emit<true><<<grid, 128, 0, st>>>(new_index, new_pos, c[0], c[1], c[2], new_range, p.length, range_scale, nullptr,
