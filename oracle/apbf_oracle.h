@@ -15,6 +15,8 @@
  *   uint_to_float_but_gradual.comp, box_collision.comp, copy_scattered_read.comp,
  *   radix_sort_*.comp / prefix_sum_*.comp (semantics: stable, inclusive),
  *   infer_velocity.comp / apply_acceleration.comp / apply_velocity.comp,
+ *   find_split_and_merge_1/2/3.comp (merge and split off),
+ *   uint_to_float_with_indexed_lower_bound.comp, source/update_transfers.cpp:14-54,
  *   source/algorithms.cpp, neighborhood_green.cpp, neighborhood_binary_search.cpp,
  *   incompressibility.cpp, spread_kernel_width.cpp, box_collision.cpp,
  *   velocity_handling.cpp, pool.cpp:67-106.
@@ -24,7 +26,7 @@
  *     vectors (source/test.cpp:91-105,186-197,269-282,284-305,343-364,402-425)
  *     and the Z-curve vectors of the dead sortByPositions test (test.cpp:623).
  *   - neighbour search, position hash/code, incompressibility, kernel width,
- *     box collision: PARITY UNPINNED -- the reference has no enabled test for
+ *     box collision, update_transfers: PARITY UNPINNED -- the reference has no enabled test for
  *     them (test.cpp:533-583 return true) and its GLSL cannot be compiled or
  *     run in this image (no glslang, no Vulkan).  Cross-checked only by the
  *     brute-force search and hand-derived micro cases.
