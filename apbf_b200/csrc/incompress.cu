@@ -240,13 +240,17 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
 }
 
 // ---- T2 -------------------------------------------------------------------------------------------------------------------------
-template <int GK>
+// ASYM: the list holds unmirrored pairs (variable kernel widths), which push with integer atomics like the reference.  Both
+// forms are launched and the one that does not match the list's state returns at once: the host does not know the state
+// without a read-back, and the form without the push path needs fewer registers.
+template <int GK, bool ASYM>
 __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_apply_delta(sweep_args A)
 {
+	if ((A.misc[MW_N_ASYM] != 0u) != ASYM) return;
 	const uint32_t n = *A.len;
 	const uint32_t n_own = min(n, A.misc[MW_N_OWNED]); // a ghost's segment holds only unmirrored pairs onto owned particles: push part only
 	const bool filter = A.s.mBoundarinessCalculationMethod == 2;
-	const bool has_asym = A.misc[MW_N_ASYM] != 0u;
+	constexpr bool has_asym = ASYM;
 	const unsigned lane = threadIdx.x & 31u, sub = lane & 7u, grp = lane >> 3;
 	const uint32_t warps_per_grid = gridDim.x * (SWEEP_THREADS / 32);
 	for (uint32_t tile = blockIdx.x * (SWEEP_THREADS / 32) + (threadIdx.x >> 5); (size_t)tile * 32 < n; tile += warps_per_grid) {
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_apply_delta(sweep_args A)
 						const uint32_t b = nn[u] & NB_ID_MASK;
 						const int4 iq = qq[u];
 						const float4 lb = ll[u];
-						const bool mirrored = (nn[u] & NB_UNMIRRORED) == 0u;
+						const bool mirrored = !ASYM || (nn[u] & NB_UNMIRRORED) == 0u; // (no unmirrored pair in the list: nothing to test)
 						const int dxi = iq.x - ip.x, dyi = iq.y - ip.y, dzi = iq.z - ip.z;
 						const float rx = (float)dxi * INV_R_POS, ry = (float)dyi * INV_R_POS, rz = (float)dzi * INV_R_POS;
 						const float r2 = dot3(rx, ry, rz, rx, ry, rz);
@@ -475,11 +479,11 @@ int apbf_solver_iteration(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors
 	if (run_all || (flags & ITER_RUN_T2)) {
 		apbf_prof_scope ps(ctx, PROF_APPLY_DELTA);
 		switch (A.s.mGradientKernelId) {
-			case 0: k_apply_delta<0><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
-			case 1: k_apply_delta<1><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
-			case 2: k_apply_delta<2><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
-			case 3: k_apply_delta<3><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
-			case 4: k_apply_delta<4><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+			case 0: k_apply_delta<0, false><<<grid, SWEEP_THREADS, 0, st>>>(A); k_apply_delta<0, true><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+			case 1: k_apply_delta<1, false><<<grid, SWEEP_THREADS, 0, st>>>(A); k_apply_delta<1, true><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+			case 2: k_apply_delta<2, false><<<grid, SWEEP_THREADS, 0, st>>>(A); k_apply_delta<2, true><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+			case 3: k_apply_delta<3, false><<<grid, SWEEP_THREADS, 0, st>>>(A); k_apply_delta<3, true><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+			case 4: k_apply_delta<4, false><<<grid, SWEEP_THREADS, 0, st>>>(A); k_apply_delta<4, true><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
 		}
 		APBF_LAUNCHED(ctx);
 	}
