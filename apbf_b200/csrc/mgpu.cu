@@ -123,28 +123,30 @@ __global__ void k_halo_lists(const int32_t* __restrict__ pos4, uint32_t n_owned,
 
 struct halo_lists {
 	const int4* pos;
-	const uint32_t *inv_mass, *radius, *kernel_width, *target_radius;
+	const uint32_t *inv_mass, *radius, *kernel_width, *target_radius, *boundary_distance;
 };
 struct halo_lists_out {
 	int4* pos;
-	uint32_t *inv_mass, *radius, *kernel_width, *target_radius, *index_list;
+	uint32_t *inv_mass, *radius, *kernel_width, *target_radius, *boundary_distance, *index_list;
 };
 
 __global__ void k_pack_halo(halo_lists L, const uint32_t* __restrict__ ids, uint32_t count, int4* __restrict__ out)
 {
 	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
 		const uint32_t id = ids[k];
-		out[2 * (size_t)k] = L.pos[id];
-		out[2 * (size_t)k + 1] = make_int4((int)L.inv_mass[id], (int)L.radius[id], (int)L.kernel_width[id], (int)L.target_radius[id]);
+		out[3 * (size_t)k] = L.pos[id];
+		out[3 * (size_t)k + 1] = make_int4((int)L.inv_mass[id], (int)L.radius[id], (int)L.kernel_width[id], (int)L.target_radius[id]);
+		out[3 * (size_t)k + 2] = make_int4((int)L.boundary_distance[id], 0, 0, 0); // (update_transfers floods it across the bricks)
 	}
 }
 __global__ void k_unpack_halo(halo_lists_out L, uint32_t first, uint32_t count, const int4* __restrict__ in)
 {
 	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
 		const uint32_t id = first + k;
-		L.pos[id] = in[2 * (size_t)k];
-		const int4 a = in[2 * (size_t)k + 1];
+		L.pos[id] = in[3 * (size_t)k];
+		const int4 a = in[3 * (size_t)k + 1];
 		L.inv_mass[id] = (uint32_t)a.x; L.radius[id] = (uint32_t)a.y; L.kernel_width[id] = (uint32_t)a.z; L.target_radius[id] = (uint32_t)a.w;
+		L.boundary_distance[id] = (uint32_t)in[3 * (size_t)k + 2].x;
 		L.index_list[id] = id;
 	}
 }
@@ -376,8 +378,8 @@ int apbf_sim_mg_halo_lists(apbf_sim* sim, uint32_t* ids_dev, uint32_t cap_per_de
 	return APBF_OK;
 }
 
-// what: 0 halo record (32 B: position, inverse mass, radius, kernel width, target radius), 1 kernel width (4 B),
-//       2 packed position of the solver (16 B), 3 lambda (4 B)
+// what: 0 halo record (48 B: position, inverse mass, radius, kernel width, target radius, boundary distance), 1 kernel width
+//       (4 B), 2 packed position of the solver (16 B), 3 lambda (4 B), 4 committed position (16 B)
 int apbf_sim_mg_pack(apbf_sim* sim, int what, const uint32_t* ids_dev, uint32_t count, void* out)
 {
 	if (!sim) return APBF_ERR_INVALID;
@@ -390,7 +392,7 @@ int apbf_sim_mg_pack(apbf_sim* sim, int what, const uint32_t* ids_dev, uint32_t 
 	cudaStream_t st = ctx->stream;
 	if (what == 0) {
 		halo_lists L{ (const int4*)f.particle.position.data, (const uint32_t*)f.particle.inverse_mass.data, (const uint32_t*)f.particle.radius.data,
-		              (const uint32_t*)f.kernel_width.data, (const uint32_t*)f.target_radius.data };
+		              (const uint32_t*)f.kernel_width.data, (const uint32_t*)f.target_radius.data, (const uint32_t*)f.boundary_distance.data };
 		k_pack_halo<<<grid, 256, 0, st>>>(L, ids_dev, count, (int4*)out);
 	} else if (what == 1) {
 		k_pack_u32<<<grid, 256, 0, st>>>((const uint32_t*)f.kernel_width.data, 1u, ids_dev, count, (uint32_t*)out);
@@ -398,6 +400,8 @@ int apbf_sim_mg_pack(apbf_sim* sim, int what, const uint32_t* ids_dev, uint32_t 
 		k_pack_16<<<grid, 256, 0, st>>>((const int4*)ctx->scratch_get(SLOT_P4, sizeof(int4) * (size_t)cap), ids_dev, count, (int4*)out);
 	} else if (what == 3) {
 		k_pack_u32<<<grid, 256, 0, st>>>((const uint32_t*)ctx->scratch_get(SLOT_L4, sizeof(float4) * (size_t)cap), 4u, ids_dev, count, (uint32_t*)out);
+	} else if (what == 4) { // committed positions (update_transfers measures distances after the solver)
+		k_pack_16<<<grid, 256, 0, st>>>((const int4*)f.particle.position.data, ids_dev, count, (int4*)out);
 	} else {
 		return apbf_fail(ctx, APBF_ERR_INVALID, "what", __FILE__, __LINE__);
 	}
@@ -419,7 +423,8 @@ int apbf_sim_mg_unpack(apbf_sim* sim, int what, const uint32_t* ids_dev, uint32_
 	if (what == 0) {
 		APBF_REQUIRE(ctx, (size_t)first + count <= cap);
 		halo_lists_out L{ (int4*)f.particle.position.data, (uint32_t*)f.particle.inverse_mass.data, (uint32_t*)f.particle.radius.data,
-		                  (uint32_t*)f.kernel_width.data, (uint32_t*)f.target_radius.data, (uint32_t*)f.particle.index_list.data };
+		                  (uint32_t*)f.kernel_width.data, (uint32_t*)f.target_radius.data, (uint32_t*)f.boundary_distance.data,
+		                  (uint32_t*)f.particle.index_list.data };
 		k_unpack_halo<<<grid, 256, 0, st>>>(L, first, count, (const int4*)in);
 	} else if (what == 1) {
 		k_unpack_u32<<<grid, 256, 0, st>>>((uint32_t*)f.kernel_width.data, ids_dev, count, (const uint32_t*)in);
@@ -428,6 +433,8 @@ int apbf_sim_mg_unpack(apbf_sim* sim, int what, const uint32_t* ids_dev, uint32_
 	} else if (what == 3) {
 		k_unpack_lambda<<<grid, 256, 0, st>>>((float4*)ctx->scratch_get(SLOT_L4, sizeof(float4) * (size_t)cap),
 		                                      (const float4*)ctx->scratch_get(SLOT_KG, sizeof(float4) * (size_t)cap), ids_dev, count, (const float*)in);
+	} else if (what == 4) {
+		k_unpack_16<<<grid, 256, 0, st>>>((int4*)f.particle.position.data, ids_dev, count, (const int4*)in);
 	} else {
 		return apbf_fail(ctx, APBF_ERR_INVALID, "what", __FILE__, __LINE__);
 	}
@@ -454,7 +461,8 @@ int apbf_sim_mg_remap(apbf_sim* sim, uint32_t* ids_dev, uint32_t count, uint32_t
 }
 
 // phase: 0 integrate, 1 search, 2 spread_kernel_width, 3 solver constants, 4 iteration prologue (commit of the previous
-// iteration, box collision, pack), 5 density/lambda sweep, 6 apply sweep, 7 final commit
+// iteration, box collision, pack), 5 density/lambda sweep, 6 apply sweep, 7 final commit, 8 kernel width from the boundary
+// distance, 9 update_transfers
 int apbf_sim_mg_phase(apbf_sim* sim, int phase, int iteration)
 {
 	if (!sim) return APBF_ERR_INVALID;
@@ -496,6 +504,8 @@ int apbf_sim_mg_phase(apbf_sim* sim, int phase, int iteration)
 		case 5: return apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_T1, bmin, bmax, c.n_boxes, nullptr, nullptr);
 		case 6: return apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_T2, bmin, bmax, c.n_boxes, nullptr, nullptr);
 		case 7: return apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_BEGIN | ITER_BEGIN_COMMIT, nullptr, nullptr, 0u, nullptr, nullptr);
+		case 8: return apbf_kernel_width_from_boundary_distance(ctx, &sim->fluid); // pool.cpp:77-80 (owned particles; call before ROUTE)
+		case 9: return apbf_update_transfers_apply(ctx, &sim->fluid, &sim->nb, nullptr); // pool.cpp:99-102, after the ghosts' positions came in
 	}
 	return apbf_fail(ctx, APBF_ERR_INVALID, "phase", __FILE__, __LINE__);
 }

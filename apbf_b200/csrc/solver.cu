@@ -177,7 +177,7 @@ struct ut_args {
 
 __global__ void __launch_bounds__(SWEEP_THREADS) k_update_transfers(ut_args A)
 {
-	const uint32_t n = *A.len;
+	const uint32_t n = min(*A.len, A.misc[MW_N_OWNED]); // slabs: a ghost's values come from its owner (its own list is incomplete)
 	const bool ident = A.misc[MW_IDENTITY] != 0u;
 	const unsigned sub = threadIdx.x & (GROUP - 1);
 	const uint32_t gm = group_mask();

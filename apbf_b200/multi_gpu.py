@@ -26,8 +26,8 @@ import os
 
 import numpy as np
 
-HALO, KW, P4, LAMBDA = 0, 1, 2, 3
-WORDS = {HALO: 8, KW: 1, P4: 4, LAMBDA: 1}
+HALO, KW, P4, LAMBDA, POS = 0, 1, 2, 3, 4
+WORDS = {HALO: 12, KW: 1, P4: 4, LAMBDA: 1, POS: 4}
 STATE_WORDS = 20
 
 
@@ -93,10 +93,14 @@ class TorchComm:
 
 
 class SlabDomain:
-    def __init__(self, backend, comm, adaptive, solver_iterations, integrate=True):
+    def __init__(self, backend, comm, adaptive, solver_iterations, integrate=True, update_transfers=False, width_from_boundary_distance=False):
         self.b, self.comm = backend, comm
         self.rank, self.world = comm.rank, comm.world
         self.adaptive, self.iters, self.integrate = bool(adaptive), int(solver_iterations), bool(integrate)
+        # the reference's default adaptive mode (pool.cpp:77-80 and :99-102): kernel width from the boundary distance before the
+        # search, update_transfers after the solver (its flood fill crosses the bricks: the halo record carries the ghosts' old
+        # boundary distances, and their committed positions follow the solver)
+        self.update_transfers, self.width_from_bd = bool(update_transfers), bool(width_from_boundary_distance)
         self.n_own = backend.n_owned()
         self.gid_base = 0
         self.stats = dict(migrated=0, ghosts=0)
@@ -153,6 +157,8 @@ class SlabDomain:
         b.set_counts(self.n_own, self.n_own, self.gid_base)          # ghosts of the last substep are dropped
         if self.integrate:
             b.integrate()
+        if self.width_from_bd:
+            b.kernel_width_from_boundary_distance()
         self._mark("integrate")
         if W > 1:
             # ---- ROUTE ---------------------------------------------------------------------------------------------------
@@ -195,7 +201,7 @@ class SlabDomain:
             # the library's own communicator: widths to the ghosts, constants, the whole solver loop with its exchanges and the
             # final commit in one call on the context's stream
             b.solve(self.send_counts, self.ghost_counts, self.adaptive, self.iters)
-            b.set_counts(self.n_own, self.n_own, self.gid_base)
+            self._finish()
             self._mark("solve")
             return
         if self.adaptive:
@@ -214,8 +220,14 @@ class SlabDomain:
             b.apply_delta()
             self._mark("apply_delta")
         b.final_commit()
-        b.set_counts(self.n_own, self.n_own, self.gid_base)
+        self._finish()
         self._mark("final")
+
+    def _finish(self):
+        if self.update_transfers:
+            self._refresh_ghosts(POS)                       # distances are taken after the solver
+            self.b.update_transfers()
+        self.b.set_counts(self.n_own, self.n_own, self.gid_base)
 
 
 class CudaRankBackend:
@@ -263,6 +275,8 @@ class CudaRankBackend:
     def density_lambda(self): self._phase(5)
     def apply_delta(self): self._phase(6)
     def final_commit(self): self._phase(7)
+    def kernel_width_from_boundary_distance(self): self._phase(8)
+    def update_transfers(self): self._phase(9)
 
     def route(self):
         self._ck(self.lib.apbf_sim_mg_route(self.sim.handle, self.counts_dev.data_ptr()))

@@ -8,7 +8,7 @@ the CUDA path only keeps a ghost's unmirrored pairs -- the exchanged quantities 
 import numpy as np
 import torch
 
-from apbf_b200.multi_gpu import HALO, KW, LAMBDA, P4
+from apbf_b200.multi_gpu import HALO, KW, LAMBDA, P4, POS
 from oracle import oracle as orc
 
 FIELDS = [f[0] for f in orc.State.FIELDS if f[0] != "index_list"]
@@ -131,9 +131,10 @@ class OracleRankBackend:
         ids = self.send_ids[dest]
         if what == HALO:
             cols = [self.a["position"][ids].view(np.int32)] + [self.a[k][ids].reshape(-1, 1).view(np.int32) for k in ("inverse_mass", "radius", "kernel_width", "target_radius")]
+            cols += [self.a["boundary_distance"][ids].reshape(-1, 1).view(np.int32), np.zeros((len(ids), 3), np.int32)]
         elif what == KW:
             cols = [self.a["kernel_width"][ids].reshape(-1, 1).view(np.int32)]
-        elif what == P4:
+        elif what in (P4, POS):
             cols = [self.a["position"][ids].view(np.int32)]
         else:
             cols = [self.lam[ids].reshape(-1, 1).view(np.int32)]
@@ -146,9 +147,10 @@ class OracleRankBackend:
             self.a["position"][ids] = w[:, :4]
             for i, k in enumerate(("inverse_mass", "radius", "kernel_width", "target_radius")):
                 self.a[k][ids] = w[:, 4 + i].copy().view(np.float32)
+            self.a["boundary_distance"][ids] = w[:, 8].copy().view(np.uint32)
         elif what == KW:
             self.a["kernel_width"][ids] = w[:, 0].copy().view(np.float32)
-        elif what == P4:
+        elif what in (P4, POS):
             self.a["position"][ids] = w
         else:
             self.lam[ids] = w[:, 0].copy().view(np.float32)
@@ -196,6 +198,23 @@ class OracleRankBackend:
         order = np.concatenate([np.nonzero(self.owned_mask)[0], np.nonzero(~self.owned_mask)[0]])
         for k in FIELDS:
             self.a[k] = self.a[k][order].copy()
+        inv = np.zeros(self.n_tot, np.int64)
+        inv[order] = np.arange(self.n_tot)
+        self.pairs = inv[self.pairs.astype(np.int64)].astype(np.uint32)        # the pair list follows (update_transfers reads it)
+        for r in self.send_ids:
+            self.send_ids[r] = inv[self.send_ids[r]]
+        self.ghost_ids = inv[self.ghost_ids]
+
+    def kernel_width_from_boundary_distance(self):
+        st = self._state(self.n_own)
+        orc.kernel_width_from_boundary_distance(st, self.s)
+        self._store(st, self.n_own)
+
+    def update_transfers(self):
+        st = self._state(self.n_tot)
+        order = np.argsort(self.pairs[:, 0], kind="stable")                    # grouped by id again, discovery order inside
+        orc.update_transfers_apply(st, self.s, self.pairs[order])
+        self._store(st, self.n_tot)
 
     def owned_arrays(self):
         return {k: self.a[k][: self.n_own] for k in FIELDS}

@@ -17,7 +17,7 @@ def _scene(adaptive, side):
     return sc
 
 
-def _worker(rank, world, port, adaptive, side, steps, out_dir):
+def _worker(rank, world, port, adaptive, side, steps, out_dir, default_mode=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     import torch
@@ -26,7 +26,7 @@ def _worker(rank, world, port, adaptive, side, steps, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import apbf_b200
     from apbf_b200 import multi_gpu
-    sc = _scene(adaptive, side)
+    sc = _scene(adaptive or default_mode, side)
     owner = multi_gpu.owner_rank_of_positions(sc.arrays["position"], sc.min_pos, sc.max_pos, sc.res_log2, sc.dims, world)
     mine = {k: np.ascontiguousarray(v[owner == rank]) for k, v in sc.arrays.items()}
     n_own = len(mine["position"])
@@ -34,11 +34,13 @@ def _worker(rank, world, port, adaptive, side, steps, out_dir):
     ctx = apbf_b200.Context(device=rank, dims=sc.dims)
     ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if adaptive else 1, mSmallestTargetRadius=sc.smallest_target_radius)
     cap = sc.n                      # room for every particle plus ghosts on one rank
-    sim = apbf_b200.Sim(ctx, sc, capacity=cap, neighbor_capacity=cap * (700 if adaptive else 80), integrate=True, basic_pbf=not adaptive)
+    sim = apbf_b200.Sim(ctx, sc, capacity=cap, neighbor_capacity=cap * (700 if adaptive or default_mode else 80), integrate=True,
+                        basic_pbf=not (adaptive or default_mode))
     sim.upload(mine, n=n_own)
     halo_range = float(sc.arrays["kernel_width"].max()) * (1.5 if adaptive else 1.0) * 1.05
     backend = multi_gpu.CudaRankBackend(sim, n_own, world, rank, halo_range, ghost_capacity=cap)
-    dom = multi_gpu.SlabDomain(backend, multi_gpu.TorchComm(torch.device("cuda", rank)), adaptive=adaptive, solver_iterations=4, integrate=True)
+    dom = multi_gpu.SlabDomain(backend, multi_gpu.TorchComm(torch.device("cuda", rank)), adaptive=adaptive, solver_iterations=4, integrate=True,
+                               update_transfers=default_mode, width_from_boundary_distance=default_mode)
     migrated = 0
     for _ in range(steps):
         dom.substep()
@@ -53,8 +55,8 @@ def _worker(rank, world, port, adaptive, side, steps, out_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("adaptive,side", [(False, 24), (True, 20)])
-def test_n_rank_equals_one_rank(tmp_path, adaptive, side):
+@pytest.mark.parametrize("adaptive,side,default_mode", [(False, 24, False), (True, 20, False), (False, 20, True)])
+def test_n_rank_equals_one_rank(tmp_path, adaptive, side, default_mode):
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -62,12 +64,13 @@ def test_n_rank_equals_one_rank(tmp_path, adaptive, side):
     import apbf_b200
     world = 4 if torch.cuda.device_count() >= 4 else 2
     steps = 3
-    port = 29500 + (os.getpid() % 1000) + int(adaptive)
-    mp.spawn(_worker, args=(world, port, adaptive, side, steps, str(tmp_path)), nprocs=world, join=True)
-    sc = _scene(adaptive, side)
+    port = 29500 + (os.getpid() % 1000) + int(adaptive) + 2 * int(default_mode)
+    mp.spawn(_worker, args=(world, port, adaptive, side, steps, str(tmp_path), default_mode), nprocs=world, join=True)
+    sc = _scene(adaptive or default_mode, side)
     ctx = apbf_b200.Context(dims=sc.dims)
     ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if adaptive else 1, mSmallestTargetRadius=sc.smallest_target_radius)
-    sim = apbf_b200.Sim(ctx, sc, neighbor_capacity=sc.n * (700 if adaptive else 80), integrate=True, basic_pbf=not adaptive)
+    sim = apbf_b200.Sim(ctx, sc, neighbor_capacity=sc.n * (700 if adaptive or default_mode else 80), integrate=True,
+                        basic_pbf=not (adaptive or default_mode), update_transfers=default_mode)
     sim.upload(sc.arrays)
     sim.substep(steps)
     exp = apbf_b200.empty_host_arrays(sc.n)
@@ -78,6 +81,6 @@ def test_n_rank_equals_one_rank(tmp_path, adaptive, side):
     assert len(pos) == sc.n and len(set(pos[:, 3].tolist())) == sc.n
     assert sum(int(p["migrated"]) for p in parts) > 0 and all(int(p["ghosts"]) > 0 for p in parts)
     got, ref = np.argsort(pos[:, 3]), np.argsort(exp["position"][:, 3])
-    for k in ("position", "velocity", "kernel_width", "boundariness"):
+    for k in ("position", "velocity", "kernel_width", "boundariness") + (("boundary_distance", "target_radius") if default_mode else ()):
         a = np.concatenate([p[k] for p in parts])[got]
         assert np.array_equal(a, exp[k][ref]), k      # same kernels, integer accumulators: bit for bit, walls included (global ids)

@@ -32,7 +32,7 @@ def _settings(orc, sc, adaptive):
     return s
 
 
-def _worker(rank, world, port, adaptive, steps, out_dir):
+def _worker(rank, world, port, adaptive, steps, out_dir, default_mode=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -41,13 +41,14 @@ def _worker(rank, world, port, adaptive, steps, out_dir):
     from oracle import oracle as orc
     from mg_oracle_backend import OracleRankBackend
     orc.set_threads(1)
-    sc = _scene(adaptive)
+    sc = _scene(adaptive or default_mode)
     s = _settings(orc, sc, adaptive)
     owner = multi_gpu.owner_rank_of_positions(sc.arrays["position"], sc.min_pos, sc.max_pos, sc.res_log2, sc.dims, world)
     mine = {k: v[owner == rank] for k, v in sc.arrays.items() if k != "index_list"}
     halo_range = float(sc.arrays["kernel_width"].max()) * (1.5 if adaptive else 1.0) * 1.05
     backend = OracleRankBackend(mine, sc, s, rank, world, halo_range, adaptive, cap_pairs=sc.n * 700)
-    dom = multi_gpu.SlabDomain(backend, multi_gpu.TorchComm(), adaptive=adaptive, solver_iterations=4, integrate=True)
+    dom = multi_gpu.SlabDomain(backend, multi_gpu.TorchComm(), adaptive=adaptive, solver_iterations=4, integrate=True,
+                               update_transfers=default_mode, width_from_boundary_distance=default_mode)
     migrated = 0
     for _ in range(steps):
         dom.substep()
@@ -58,19 +59,22 @@ def _worker(rank, world, port, adaptive, steps, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,adaptive", [(2, False), (2, True), (4, False)])
-def test_slab_protocol_equals_single_rank(orc, tmp_path, world, adaptive):
+@pytest.mark.parametrize("world,adaptive,default_mode", [(2, False, False), (2, True, False), (4, False, False), (2, False, True)])
+def test_slab_protocol_equals_single_rank(orc, tmp_path, world, adaptive, default_mode):
+    """default_mode: the reference's default adaptive mode -- kernel width from the boundary distance before the search and
+    update_transfers after the solver (its flood fill crosses the bricks)"""
     steps = 3
-    port = 29000 + (os.getpid() % 2000) + world * 3 + int(adaptive)
-    mp.spawn(_worker, args=(world, port, adaptive, steps, str(tmp_path)), nprocs=world, join=True)
+    port = 29000 + (os.getpid() % 2000) + world * 3 + int(adaptive) + 7 * int(default_mode)
+    mp.spawn(_worker, args=(world, port, adaptive, steps, str(tmp_path), default_mode), nprocs=world, join=True)
     # single rank: the plain oracle substep
-    sc = _scene(adaptive)
+    sc = _scene(adaptive or default_mode)
     s = _settings(orc, sc, adaptive)
     orc.set_threads(1)
     st = orc.State(**{k: v.copy() for k, v in sc.arrays.items()})
     for _ in range(steps):
-        orc.substep(st, s, dims=sc.dims, basic_pbf=not adaptive, solver_iterations=4, min_pos=sc.min_pos, max_pos=sc.max_pos,
-                    res_log2=sc.res_log2, box_min4=sc.box_min, box_max4=sc.box_max, cap=sc.n * 700, integrate=True)
+        orc.substep(st, s, dims=sc.dims, basic_pbf=not (adaptive or default_mode), solver_iterations=4, min_pos=sc.min_pos, max_pos=sc.max_pos,
+                    res_log2=sc.res_log2, box_min4=sc.box_min, box_max4=sc.box_max, cap=sc.n * 700, integrate=True,
+                    update_transfers=default_mode)
     parts = [np.load(os.path.join(str(tmp_path), f"rank{r}.npz")) for r in range(world)]
     pos = np.concatenate([p["position"] for p in parts])
     kw = np.concatenate([p["kernel_width"] for p in parts])
@@ -82,3 +86,8 @@ def test_slab_protocol_equals_single_rank(orc, tmp_path, world, adaptive):
     assert np.array_equal(pos[got], st.position[exp])                           # bit for bit
     assert np.array_equal(kw[got], st.kernel_width[exp])
     assert np.array_equal(vel[got], st.velocity[exp])
+    if default_mode:
+        for k in ("boundary_distance", "target_radius", "boundariness"):
+            a = np.concatenate([p[k] for p in parts])
+            assert np.array_equal(a[got], getattr(st, k)[exp]), k
+        assert len(np.unique(st.boundary_distance)) > 50
