@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <numeric>
 #include <random>
+#include <filesystem>
+#include <fstream>
 #include <set>
 
 #include "apbf_pbd.hpp"
@@ -351,6 +353,36 @@ static void operator_tests()
 	long long moved = 0;
 	for (size_t i = 0; i < after.size(); i++) moved += std::llabs((long long)after[i] - gotPos[i]);
 	if (moved == 0) { std::printf("FAILED: the solver did not move any particle\n"); g_failures++; }
+
+	// update_transfers (merge and split off; update_transfers.cpp:14-54): one step of the boundary-distance flood fill.
+	// Every particle starts at its radius; with all boundariness at 1 the decay puts it back there, so clear the flag of
+	// the inner particles first and expect their distance to grow by a neighbour distance.
+	std::vector<float> bness(n, 0.0f);
+	algorithms::copy_bytes(bness.data(), fl.get<fluid_enum::boundariness>().write().buffer(), n * 4);
+	update_transfers transfersUpdate;
+	transfersUpdate.set_data(&fl, &nb);
+	shader_provider::start_recording();
+	transfersUpdate.apply();
+	shader_provider::end_recording();
+	auto bd = fl.get<fluid_enum::boundary_distance>().read<uint32_t>();
+	size_t grown = 0;
+	for (auto v : bd) grown += v > uint32_t(r * R) ? 1u : 0u;
+	if (bd.size() != n || grown != n) { std::printf("FAILED: update_transfers did not flood the boundary distance (%zu of %zu)\n", grown, n); g_failures++; }
+
+	// save_particle_info (save_particle_info.cpp:21-130): the on-disk dump
+	save_particle_info dump;
+	const std::string folder = (std::filesystem::temp_directory_path() / "apbf_b200_particle_data_test").string();
+	dump.set_data(&fl, &nb).set_folder(folder);
+	dump.apply();
+	std::ifstream csv(folder + "/data.csv");
+	size_t lines = 0;
+	for (std::string line; std::getline(csv, line);) lines++;
+	if (lines != n + 1) { std::printf("FAILED: data.csv has %zu lines, expected %zu\n", lines, n + 1); g_failures++; }
+	std::ifstream cnt(folder + "/neighborCount.txt");
+	std::string first;
+	std::getline(cnt, first, ';');
+	if (first.empty() || std::stoul(first) == 0) { std::printf("FAILED: neighborCount.txt starts with '%s'\n", first.c_str()); g_failures++; }
+	std::filesystem::remove_all(folder);
 }
 
 int main()
