@@ -14,7 +14,8 @@ from . import _capi
 from ._capi import Settings
 
 __all__ = ["Context", "ParticleLists", "neighborhood_green", "neighborhood_binary_search", "incompressibility",
-           "spread_kernel_width", "box_collision", "velocity_handling", "algorithms", "Sim", "Settings"]
+           "spread_kernel_width", "box_collision", "velocity_handling", "algorithms", "Sim", "Settings", "TransferList",
+           "update_transfers", "particle_transfer"]
 
 _HIDDEN = (("position", np.int32, 4), ("velocity", np.float32, 4), ("inverse_mass", np.float32, 1),
            ("radius", np.float32, 1), ("pos_backup", np.int32, 4), ("transferring", np.uint32, 1))
@@ -203,6 +204,44 @@ class ParticleLists:
         return self.pairs[:self.pair_count()].cpu().numpy().view(np.uint32)
 
 
+class TransferList:
+    """pbd::transfers (source/list_definitions.h:16-18): rows (source, target, time_left) in device memory; source and target
+    index the hidden particle list.  Two buffers per list, like ParticleLists."""
+
+    def __init__(self, ctx, capacity, source=(), target=(), time_left=()):
+        torch = _torch()
+        self.ctx, self.capacity = ctx, int(capacity)
+        dev = torch.device("cuda", ctx.device)
+        self.buf = {k: [torch.zeros(self.capacity, dtype=dt, device=dev), torch.zeros(self.capacity, dtype=dt, device=dev)]
+                    for k, dt in (("source", torch.int32), ("target", torch.int32), ("time_left", torch.float32))}
+        n = len(source)
+        if n:
+            self.buf["source"][0][:n] = torch.from_numpy(np.asarray(source, np.uint32).view(np.int32)).to(dev)
+            self.buf["target"][0][:n] = torch.from_numpy(np.asarray(target, np.uint32).view(np.int32)).to(dev)
+            self.buf["time_left"][0][:n] = torch.from_numpy(np.asarray(time_left, np.float32)).to(dev)
+        self.word = torch.tensor([n], dtype=torch.int32, device=dev)
+
+    def c(self):
+        t = _capi.Transfers()
+        for k in ("source", "target", "time_left"):
+            a, b = self.buf[k]
+            setattr(t, k, _capi.Array(a.data_ptr(), b.data_ptr()))
+        t.length, t.capacity = self.word.data_ptr(), self.capacity
+        return t
+
+    def swap(self):
+        for v in self.buf.values():
+            v.reverse()
+
+    def length(self):
+        return int(self.word.item())
+
+    def rows(self):
+        n = self.length()
+        return (self.buf["source"][0][:n].cpu().numpy().view(np.uint32), self.buf["target"][0][:n].cpu().numpy().view(np.uint32),
+                self.buf["time_left"][0][:n].cpu().numpy())
+
+
 class _Operator:
     def __init__(self, ctx):
         self.ctx = ctx
@@ -361,11 +400,17 @@ class spread_kernel_width(_Operator):
 
 
 class update_transfers(_Operator):
-    """pbd::update_transfers (source/update_transfers.h) with merge and split off: boundary-distance flood-fill step, nearest
-    neighbour, target radius, boundary-distance decay, boundariness threshold (find_split_and_merge_1/2/3.comp)"""
+    """pbd::update_transfers (source/update_transfers.h, update_transfers.cpp:14-70): boundary-distance flood-fill step, nearest
+    neighbour, target radius, boundary-distance decay, boundariness threshold (find_split_and_merge_1/2/3.comp); with a transfer
+    list also the merge / split decisions and the start of the splits, as mMerge / mSplit of the context's settings say"""
 
     def set_data(self, lists, transfers=None):
-        self.lists = lists
+        self.lists, self.transfers = lists, transfers
+        return self
+
+    def set_split_duration(self, split_duration):
+        """settings::splitDuration (a host-side setting of the reference, update_transfers.cpp:63)"""
+        self.split_duration = float(split_duration)
         return self
 
     def apply(self, debug=False):
@@ -373,10 +418,31 @@ class update_transfers(_Operator):
         L = self.lists
         fl, nb = L.fluid(), L.neighbors()
         nearest = torch.zeros(L.capacity, dtype=torch.int32, device=L.words.device) if debug else None
-        _check(self.ctx, self.lib.apbf_update_transfers_apply(self.ctx.handle, C.byref(fl), C.byref(nb),
-                                                              nearest.data_ptr() if debug else None))
+        n = L.length()
+        if self.transfers is None:
+            _check(self.ctx, self.lib.apbf_update_transfers_apply(self.ctx.handle, C.byref(fl), C.byref(nb),
+                                                                  nearest.data_ptr() if debug else None))
+        else:
+            tr = self.transfers.c()
+            _check(self.ctx, self.lib.apbf_update_transfers_split_merge_apply(
+                self.ctx.handle, C.byref(fl), C.byref(nb), C.byref(tr), getattr(self, "split_duration", 0.0),
+                nearest.data_ptr() if debug else None))
         if debug:
-            return nearest[:L.length()].cpu().numpy().view(np.uint32)
+            return nearest[:n].cpu().numpy().view(np.uint32)
+
+
+class particle_transfer(_Operator):
+    """pbd::particle_transfer (source/particle_transfer.h, particle_transfer.cpp:10-28)"""
+
+    def set_data(self, lists, transfers):
+        self.lists, self.transfers = lists, transfers
+        return self
+
+    def apply(self, delta_time):
+        fl, tr = self.lists.fluid(), self.transfers.c()
+        _check(self.ctx, self.lib.apbf_particle_transfer_apply(self.ctx.handle, C.byref(fl), C.byref(tr), float(delta_time)))
+        self.lists.swap()
+        self.transfers.swap()
 
 
 def kernel_width_from_boundary_distance(ctx, lists):
@@ -491,7 +557,8 @@ class Sim:
     upload()/download() move the lists between host memory and the device (the end-to-end path)."""
 
     def __init__(self, ctx, scene, capacity=None, neighbor_capacity=None, use_binary_search=False, integrate=False,
-                 dt=1.0 / 60.0, accel=(0.0, -10.0, 0.0), solver_iterations=None, basic_pbf=None, update_transfers=False):
+                 dt=1.0 / 60.0, accel=(0.0, -10.0, 0.0), solver_iterations=None, basic_pbf=None, update_transfers=False,
+                 transfers=False, transfer_capacity=0, split_duration=0.0):
         self.ctx, self.lib = ctx, ctx.lib
         self.capacity = int(capacity or scene.n)
         self.neighbor_capacity = int(neighbor_capacity or 40 * self.capacity)
@@ -504,6 +571,8 @@ class Sim:
         cfg.accel, cfg.min_pos, cfg.max_pos = _f3(accel), _f3(scene.min_pos), _f3(scene.max_pos)
         cfg.res_log2 = scene.res_log2
         cfg.update_transfers = int(update_transfers)
+        cfg.transfers, cfg.transfer_capacity, cfg.split_duration = int(transfers), int(transfer_capacity), float(split_duration)
+        self.transfer_capacity = int(transfer_capacity or self.capacity) if transfers else 0
         bmin = np.ascontiguousarray(scene.box_min, np.float32).reshape(-1, 4)
         bmax = np.ascontiguousarray(scene.box_max, np.float32).reshape(-1, 4)
         cfg.n_boxes = bmin.shape[0]
@@ -541,6 +610,13 @@ class Sim:
         w = (C.c_uint32 * 4)()
         _check(self.ctx, self.lib.apbf_sim_stats(self.handle, w))
         return dict(n=w[0], pairs_searched=w[1], pairs_kept=w[2], pairs_unmirrored=w[3])
+
+    def download_transfers(self):
+        """(source, target, time_left) rows of the scene's transfer list (synchronises)"""
+        src, tgt = np.zeros(self.transfer_capacity, np.uint32), np.zeros(self.transfer_capacity, np.uint32)
+        ttl, n = np.zeros(self.transfer_capacity, np.float32), C.c_uint32()
+        _check(self.ctx, self.lib.apbf_sim_download_transfers(self.handle, C.byref(n), src.ctypes.data, tgt.ctypes.data, ttl.ctypes.data))
+        return src[:n.value], tgt[:n.value], ttl[:n.value]
 
     def neighbor_count(self):
         c = C.c_uint32()

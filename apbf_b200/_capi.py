@@ -50,7 +50,12 @@ class SimConfig(C.Structure):
                 ("basic_pbf", C.c_int), ("solver_iterations", C.c_int), ("use_binary_search", C.c_int),
                 ("integrate", C.c_int), ("dt", C.c_float), ("accel", C.c_float * 3), ("min_pos", C.c_float * 3),
                 ("max_pos", C.c_float * 3), ("res_log2", C.c_uint32), ("n_boxes", C.c_uint32), ("box_min4_host", vp),
-                ("box_max4_host", vp), ("update_transfers", C.c_int)]
+                ("box_max4_host", vp), ("update_transfers", C.c_int), ("transfers", C.c_int),
+                ("transfer_capacity", C.c_uint32), ("split_duration", C.c_float)]
+
+
+class Transfers(C.Structure):
+    _fields_ = [("source", Array), ("target", Array), ("time_left", Array), ("length", vp), ("capacity", C.c_uint32)]
 
 
 class HostState(C.Structure):
@@ -107,6 +112,9 @@ SIGNATURES = {
     "apbf_incompressibility_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), vp, vp]),
     "apbf_spread_kernel_width_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), vp]),
     "apbf_update_transfers_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), vp]),
+    "apbf_update_transfers_split_merge_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), C.POINTER(Transfers), C.c_float, vp]),
+    "apbf_particle_transfer_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Transfers), C.c_float]),
+    "apbf_transfers_follow_reorder": (C.c_int, [vp, C.POINTER(Transfers), vp, vp, C.c_uint32]),
     "apbf_kernel_width_from_boundary_distance": (C.c_int, [vp, C.POINTER(Fluid)]),
     "apbf_box_collision_apply": (C.c_int, [vp, C.POINTER(Particles), vp, vp, C.c_uint32]),
     "apbf_velocity_handling_apply": (C.c_int, [vp, C.POINTER(Particles), C.c_float, C.c_float, f32p]),
@@ -118,6 +126,8 @@ SIGNATURES = {
     "apbf_sim_fluid": (C.c_int, [vp, C.POINTER(Fluid)]),
     "apbf_sim_neighbors": (C.c_int, [vp, C.POINTER(Neighbors)]),
     "apbf_sim_neighbor_count": (C.c_int, [vp, u32p]),
+    "apbf_sim_transfers": (C.c_int, [vp, C.POINTER(Transfers)]),
+    "apbf_sim_download_transfers": (C.c_int, [vp, u32p, vp, vp, vp]),
     "apbf_sim_stats": (C.c_int, [vp, u32p]),
     "apbf_sim_mg_enable": (C.c_int, [vp, C.c_int, C.c_int, C.c_float]),
     "apbf_sim_mg_brick": (C.c_int, [vp, C.c_int, u32p, u32p, u32p]),

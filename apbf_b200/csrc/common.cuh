@@ -21,6 +21,9 @@ enum apbf_scratch_slot {
 	SLOT_INV_PERM, SLOT_TMP_KEYS, SLOT_TMP_VALS, SLOT_TMP_VALS2, SLOT_CODE0, SLOT_CODE1, SLOT_CODE2,
 	SLOT_P4, SLOT_L4, SLOT_G4, SLOT_DELTA, SLOT_PUSH, SLOT_RADIUS_ID, SLOT_KWFX, SLOT_KEEP_COUNTS, SLOT_KEEP_OFFSETS,
 	SLOT_PAIRS_TMP, SLOT_NB_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4, SLOT_KG, SLOT_KH, SLOT_Q4, SLOT_KEY_ID, SLOT_EDIT_COUNTS, SLOT_EDIT_OFFSETS, SLOT_MG_INV, SLOT_I4, SLOT_CUTOFF, SLOT_QB4, SLOT_STREAM, SLOT_TILE_FIRST, SLOT_TILE_TOTAL, SLOT_OLD_BOUNDARY_DIST, SLOT_CELL_MAXW, SLOT_MG_SEND, SLOT_MG_RECV,
+	SLOT_TM_NEAREST, SLOT_TM_FLAGS, SLOT_TM_OFFS, SLOT_TM_SRC, SLOT_TM_TGT, SLOT_TM_CID, SLOT_TM_CSRC, SLOT_TM_CTGT, SLOT_TM_STATE, SLOT_TM_RANK,
+	SLOT_TM_OWNER, SLOT_TM_WORDS, SLOT_TM_KEEP_H, SLOT_TM_OFFS_H, SLOT_TM_PERM_H, SLOT_TM_KEEP_I, SLOT_TM_OFFS_I, SLOT_TM_PERM_I, SLOT_TM_KEEP_R,
+	SLOT_TM_OFFS_R, SLOT_TM_PERM_R,
 	SLOT_COUNT
 };
 

@@ -92,6 +92,18 @@ int apbf_sim_create(apbf_ctx* ctx, const apbf_sim_config* cfg, apbf_sim** out_si
 			cudaStreamSynchronize(ctx->stream); // the host box arrays need not outlive this call
 		}
 	}
+	if (!rc && cfg->transfers) {
+		const size_t tc = cfg->transfer_capacity ? cfg->transfer_capacity : cfg->particle_capacity;
+		sim->cfg.transfer_capacity = (uint32_t)tc;
+		sim->tr.capacity = (uint32_t)tc;
+		sim->tr.length = (uint32_t*)words + 3;
+		rc = rc ? rc : alloc_array(sim, &sim->tr.source, 4 * tc);
+		rc = rc ? rc : alloc_array(sim, &sim->tr.target, 4 * tc);
+		rc = rc ? rc : alloc_array(sim, &sim->tr.time_left, 4 * tc);
+		void* si = nullptr;
+		if (!rc && cudaMalloc(&si, 4 * (n ? n : 4)) != cudaSuccess) rc = APBF_ERR_OOM;
+		if (!rc) { sim->owned.push_back(si); sim->sorted_index = (uint32_t*)si; }
+	}
 	sim->cfg.box_min4_host = sim->cfg.box_max4_host = nullptr;
 	if (rc) { apbf_sim_destroy(sim); return apbf_fail(ctx, rc, "sim allocation failed", __FILE__, __LINE__); }
 	*out_sim = sim;
@@ -164,10 +176,21 @@ int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
 	const apbf_settings& s = ctx->settings;
 	const bool unit_scale = c.basic_pbf || s.mBaseKernelWidthOnBoundaryDistance;     // pool.cpp:83
 	const bool adaptive = !c.basic_pbf && !s.mBaseKernelWidthOnBoundaryDistance;     // pool.cpp:87
+	const bool transfers = c.transfers && !c.basic_pbf && (s.mMerge || s.mSplit);    // pool.cpp:73, :99
+	if (transfers && ctx->mg_enabled) return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, "merge / split is not available on slabs", __FILE__, __LINE__);
+	apbf_search_debug follow;
+	memset(&follow, 0, sizeof follow);
+	follow.sorted_index = sim->sorted_index;
+	const apbf_search_debug* dbg = transfers ? &follow : nullptr;
 	for (uint32_t step = 0; step < n_substeps; step++) {
 		if (c.integrate) {                                                            // pool.cpp:71
 			APBF_TRY(apbf_velocity_handling_apply(ctx, &sim->fluid.particle, c.dt, sim->last_dt, c.accel));
 			sim->last_dt = c.dt;
+		}
+		if (transfers) {                                                              // pool.cpp:73-75
+			APBF_TRY(apbf_particle_transfer_apply(ctx, &sim->fluid, &sim->tr, c.dt));
+			apbf_sim_swap_buffers(sim);
+			for (apbf_array* a : { &sim->tr.source, &sim->tr.target, &sim->tr.time_left }) swap_array(a);
 		}
 		if (c.update_transfers && !c.basic_pbf && s.mBaseKernelWidthOnBoundaryDistance)  // pool.cpp:77-80
 			APBF_TRY(apbf_kernel_width_from_boundary_distance(ctx, &sim->fluid));
@@ -176,15 +199,17 @@ int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
 		const bool fused = adaptive && !ctx->mg_enabled && !sim->no_fuse;
 		ctx->skip_public_pairs = true; // nothing reads the (id, idN) list: the sweeps and a separate spread work on NB + offsets
 		if (c.use_binary_search && fused)
-			APBF_TRY(apbf_neighborhood_binary_search_spread_apply(ctx, &sim->fluid, &sim->nb, scale, nullptr, nullptr));
+			APBF_TRY(apbf_neighborhood_binary_search_spread_apply(ctx, &sim->fluid, &sim->nb, scale, dbg, nullptr));
 		else if (c.use_binary_search)                                                 // pool.cpp:83-84
-			APBF_TRY(apbf_neighborhood_binary_search_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, nullptr));
+			APBF_TRY(apbf_neighborhood_binary_search_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, dbg));
 		else if (fused)
-			APBF_TRY(apbf_neighborhood_green_spread_apply(ctx, &sim->fluid, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, nullptr, nullptr));
+			APBF_TRY(apbf_neighborhood_green_spread_apply(ctx, &sim->fluid, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, dbg, nullptr));
 		else
-			APBF_TRY(apbf_neighborhood_green_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, nullptr));
+			APBF_TRY(apbf_neighborhood_green_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, dbg));
 		ctx->skip_public_pairs = false;
 		apbf_sim_swap_buffers(sim);
+		if (transfers) // the transfers' source / target lists share the hidden particle data (pool.cpp:18-19)
+			APBF_TRY(apbf_transfers_follow_reorder(ctx, &sim->tr, sim->sorted_index, sim->fluid.particle.hidden_length, c.particle_capacity));
 		if (adaptive && !fused) APBF_TRY(apbf_spread_kernel_width_apply(ctx, &sim->fluid, &sim->nb, nullptr)); // pool.cpp:87-89
 		// pool.cpp:92-95: solverIterations x (box_collision, incompressibility).  Same results as calling the two
 		// operators in turn; the per-particle constants are computed once (kernel widths are fixed from here on) and
@@ -195,7 +220,9 @@ int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
 			APBF_TRY(apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, flags, sim->boxes,
 			                               sim->boxes ? sim->boxes + 4 * (size_t)c.n_boxes : nullptr, c.n_boxes, nullptr, nullptr));
 		}
-		if (c.update_transfers && !c.basic_pbf)                                       // pool.cpp:99-102
+		if (transfers)                                                                // pool.cpp:99-102
+			APBF_TRY(apbf_update_transfers_split_merge_apply(ctx, &sim->fluid, &sim->nb, &sim->tr, c.split_duration, nullptr));
+		else if (c.update_transfers && !c.basic_pbf)
 			APBF_TRY(apbf_update_transfers_apply(ctx, &sim->fluid, &sim->nb, nullptr));
 	}
 	return APBF_OK;
@@ -226,6 +253,32 @@ int apbf_sim_stats(apbf_sim* sim, uint32_t out[4])
 	out[1] = words[MW_TOTAL_PAIRS];
 	out[2] = words[MW_KEPT_PAIRS] == 0xFFFFFFFFu ? words[MW_TOTAL_PAIRS] : words[MW_KEPT_PAIRS];
 	out[3] = words[MW_N_ASYM];
+	return APBF_OK;
+}
+
+int apbf_sim_transfers(apbf_sim* sim, apbf_transfers* out)
+{
+	if (!sim || !out) return APBF_ERR_INVALID;
+	APBF_REQUIRE(sim->ctx, sim->cfg.transfers);
+	*out = sim->tr;
+	return APBF_OK;
+}
+
+int apbf_sim_download_transfers(apbf_sim* sim, uint32_t* out_n, uint32_t* source_host, uint32_t* target_host, float* time_left_host)
+{
+	if (!sim || !out_n) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	APBF_REQUIRE(ctx, sim->cfg.transfers);
+	cudaStream_t st = ctx->stream;
+	uint32_t n = 0;
+	APBF_CUDA(ctx, cudaMemcpyAsync(&n, sim->tr.length, 4, cudaMemcpyDeviceToHost, st));
+	APBF_CUDA(ctx, cudaStreamSynchronize(st));
+	if (n > sim->tr.capacity) n = sim->tr.capacity;
+	*out_n = n;
+	struct { void* dst; const void* src; } items[] = { { source_host, sim->tr.source.data }, { target_host, sim->tr.target.data }, { time_left_host, sim->tr.time_left.data } };
+	for (auto& it : items)
+		if (it.dst && n) APBF_CUDA(ctx, cudaMemcpyAsync(it.dst, it.src, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+	APBF_CUDA(ctx, cudaStreamSynchronize(st));
 	return APBF_OK;
 }
 

@@ -22,6 +22,8 @@ struct apbf_sim {
 	void*           nccl_comm = nullptr; // slabs: the library's own communicator (apbf_sim_mg_comm_init)
 	std::vector<void*> owned;
 	apbf_mg_state   mg;
+	apbf_transfers  tr = {};             // cfg.transfers: the transfer list (pool.cpp:8)
+	uint32_t*       sorted_index = nullptr; // cfg.transfers: the search's permutation of the hidden list, for the transfers to follow
 };
 
 // data <-> reorder_out of every list (after a search or a re-partition)

@@ -260,6 +260,34 @@ int apbf_spread_kernel_width_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighb
  * say.  Optional output nearest_neighbor[capacity] (0xFFFFFFFF for a particle without pairs; among several pairs at the
  * minimum distance the last one of the list -- the reference leaves that to a race). */
 int apbf_update_transfers_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors* neighbors, uint32_t* out_nearest_neighbor);
+/* pbd::transfers = indexed_list<hidden_transfers> (source/list_definitions.h:16-18): rows (source, target, time_left); source and
+ * target are indices into the hidden particle list (they share its data, pool.cpp:18-19); time_left > 0 is a merge, <= 0 a split
+ * (particle_transfer.comp:35-37).  Like the particle arrays every list has a second buffer for the list edits. */
+typedef struct apbf_transfers {
+	apbf_array source;      /* u32 [capacity] */
+	apbf_array target;      /* u32 */
+	apbf_array time_left;   /* f32 */
+	uint32_t*  length;      /* device word */
+	uint32_t   capacity;    /* MAX_TRANSFERS */
+} apbf_transfers;
+/* pbd::update_transfers::set_data(fluid, neighbors, transfers).apply() in full (source/update_transfers.cpp:14-70): what
+ * apbf_update_transfers_apply does, then the merge / split decisions of find_split_and_merge_3.comp:86-121 as mMerge / mSplit
+ * say, remove_impossible_splits.comp, duplicate_these (indexed_list.h:141-152), initialize_split_particles.comp and the three
+ * appends to the transfer lists.  Works in place on the `data` buffers; the list lengths grow by the number of splits.  The
+ * reference resolves conflicting candidates and orders its output lists by atomics (a race); this call returns the result of
+ * running the invocations in ascending id order, with copies appended in that order.  A particle without pairs never merges. */
+int apbf_update_transfers_split_merge_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors* neighbors, apbf_transfers* transfers,
+                                            float split_duration, uint32_t* out_nearest_neighbor);
+/* pbd::particle_transfer::set_data(fluid, transfers).apply(dt) (source/particle_transfer.cpp:10-28, particle_transfer.comp:30-84)
+ * including deleteTransferList.delete_these() and deleteParticleList.delete_these() (indexed_list.h:126-138): finished splits
+ * leave the transfer list, the sources of finished merges leave the hidden particle list, and every list that shares it follows.
+ * Like a search, the call writes the edited lists of `fluid` AND `transfers` into their reorder_out buffers (surviving entries
+ * keep their order); afterwards the caller uses reorder_out as the lists' buffers. */
+int apbf_particle_transfer_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_transfers* transfers, float dt);
+/* The searches permute the hidden particle list; the transfers' source / target lists share it and follow through
+ * indexed_list::apply_hidden_edit (source/indexed_list.h:289-308).  sorted_index[new slot] = old slot (apbf_search_debug). */
+int apbf_transfers_follow_reorder(apbf_ctx* ctx, apbf_transfers* transfers, const uint32_t* sorted_index, const uint32_t* hidden_length,
+                                  uint32_t hidden_capacity);
 /* pool.cpp:77-80: shader_provider::uint_to_float_with_indexed_lower_bound(boundary_distance -> kernel_width, factor
  * targetRadiusScaleFactor / POS_RESOLUTION, lower bound radius * KERNEL_SCALE, step kernelWidthAdaptionSpeed) */
 int apbf_kernel_width_from_boundary_distance(apbf_ctx* ctx, apbf_fluid* fluid);
@@ -289,7 +317,12 @@ typedef struct apbf_sim_config {
 	const float* box_min4_host;    /* vec4 [n_boxes] */
 	const float* box_max4_host;
 	int      update_transfers;     /* pool.cpp:77-80 and :99-102: kernel width from the boundary distance before the search (default
-	                                  adaptive mode) and update_transfers::apply after the solver (merge and split stay off) */
+	                                  adaptive mode) and update_transfers::apply after the solver */
+	int      transfers;            /* pool.cpp:73-75 and :99-102 with settings::merge / settings::split: particle_transfer::apply after
+	                                  velocity_handling and the full update_transfers::apply after the solver (as mMerge / mSplit of the
+	                                  context's settings say); particle_capacity is the room for the copies */
+	uint32_t transfer_capacity;    /* MAX_TRANSFERS (0: particle_capacity) */
+	float    split_duration;       /* settings::splitDuration */
 } apbf_sim_config;
 
 /* host-side view of the scene's lists (the reference's list schema, plain host arrays) */
@@ -323,6 +356,10 @@ int  apbf_sim_fluid(apbf_sim* sim, apbf_fluid* out_fluid);
 int  apbf_sim_neighbors(apbf_sim* sim, apbf_neighbors* out_neighbors);
 /* pair count of the last search (device -> host read, synchronises) */
 int  apbf_sim_neighbor_count(apbf_sim* sim, uint32_t* out_count);
+/* the transfer list of a scene created with cfg.transfers: device view, and a synchronising read-back into host arrays of
+ * transfer_capacity entries (any of them may be NULL) */
+int  apbf_sim_transfers(apbf_sim* sim, apbf_transfers* out_transfers);
+int  apbf_sim_download_transfers(apbf_sim* sim, uint32_t* out_n, uint32_t* source_host, uint32_t* target_host, float* time_left_host);
 /* counters of the last substep (device -> host read, synchronises):
  * out[0] particles, out[1] pairs found by the search (unclamped), out[2] pairs after the spread_kernel_width prune
  * (== out[1] when it did not run), out[3] pairs without a mirrored pair */

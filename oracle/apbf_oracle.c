@@ -903,6 +903,205 @@ void orc_update_transfers_apply(orc_state* st, const orc_settings* s, const uint
 	if (!out_nearest) free(nearest);
 }
 
+/* ---------------------------------------------------------------------------------- */
+/* update_transfers::apply with merge and split as the settings say                   */
+/* (update_transfers.cpp:14-70) and particle_transfer::apply (particle_transfer.cpp)   */
+/*                                                                                    */
+/* Serialisation.  The reference decides merges and splits with atomicExchange /      */
+/* atomicAdd across threads (find_split_and_merge_3.comp:95-120), so which of two     */
+/* conflicting candidates wins and the order of the output lists are races.  The      */
+/* restatement runs the invocations in ascending id order -- one of the orders the    */
+/* reference may take; list edits (delete_these / duplicate_these, indexed_list.h:    */
+/* 126-152) keep the surviving entries in their order and append copies at the end.   */
+/* A particle without any pair has no nearest neighbour (the reference reads an       */
+/* uninitialised list entry there): it never merges.                                  */
+/* `1 / 0` in initialize_split_particles.comp:30 is an INTEGER constant expression;   */
+/* glslang folds an integer division by zero to 0x7FFFFFFF, so the inverse mass of a  */
+/* fresh duplicate is float(0x7FFFFFFF) = 2^31 (assumption, named in DESIGN.md).      */
+/* pow(2.0, 1.0 / DIMENSIONS) * 0.99 (find_split_and_merge_3.comp:88) is folded by    */
+/* the compiler in double precision and rounded to float once.                        */
+/* ---------------------------------------------------------------------------------- */
+static void find_split_and_merge_3_decide(orc_state* st, const orc_settings* s, int D, const uint32_t* nearest,
+                                          orc_transfers* t, uint32_t* split_ids, uint32_t* n_split, uint32_t max_split)
+{ /* find_split_and_merge_3.comp:86-121, invocations in ascending id order */
+	const float splitFactor = (float)(pow(2.0, 1.0 / (double)D) * 0.99);
+	uint32_t n0 = st->n;
+	*n_split = 0;
+	for (uint32_t id = 0; id < n0; id++) {
+		uint32_t idx = st->index_list[id];
+		float radius = st->radius[idx];
+		float targetRadius = st->target_radius[id];
+		int split = s->mSplit && (targetRadius * splitFactor <= radius);
+		int merge = 0, nnLarger = 0;
+		uint32_t nnIdx = 0;
+		if (s->mMerge && nearest[id] != 0xFFFFFFFFu) {
+			nnIdx = st->index_list[nearest[id]];
+			const int32_t* pos = &st->position[4 * idx];
+			const int32_t* posN = &st->position[4 * nnIdx];
+			float diff[3] = { (float)(posN[0] - pos[0]), (float)(posN[1] - pos[1]), (float)(posN[2] - pos[2]) };
+			float nnDist = length3(diff) / R_POS;
+			float nnRadius = st->radius[nnIdx];
+			nnLarger = nnRadius > radius || (nnRadius == radius && nnIdx > idx);
+			merge = nnDist < radius && powf(radius, (float)D) + powf(nnRadius, (float)D) <= powf(targetRadius, (float)D);
+		}
+		if (!merge && !split) continue;
+		uint32_t sourceIdx = (merge && nnLarger) ? nnIdx : idx;
+		uint32_t targetIdx = (merge && nnLarger) ? idx : nnIdx;
+		if (st->transferring[sourceIdx] == 1u) continue;          /* atomicExchange(..., 1) == 1 */
+		st->transferring[sourceIdx] = 1u;
+		if (merge) {
+			if (st->transferring[targetIdx] == 1u) { st->transferring[sourceIdx] = 0u; continue; }
+			st->transferring[targetIdx] = 1u;
+			if (t->n >= t->cap) {                                  /* :104-109 */
+				t->n = t->cap;
+				st->transferring[sourceIdx] = 0u;
+				st->transferring[targetIdx] = 0u;
+				continue;
+			}
+			t->source[t->n] = sourceIdx;
+			t->target[t->n] = targetIdx;
+			t->time_left[t->n] = fmaxf_(0.0001f, s->mMergeDuration);
+			t->n++;
+		} else {
+			if (*n_split >= max_split) { *n_split = max_split; st->transferring[sourceIdx] = 0u; continue; }
+			split_ids[(*n_split)++] = id;                          /* outSplit[sIdx] = idx: kept as the id, the idx follows */
+		}
+	}
+}
+
+void orc_update_transfers_full(orc_state* st, uint32_t hidden_cap, uint32_t id_cap, const orc_settings* s, int D,
+                               const uint32_t* pairs, uint32_t n_pairs, orc_transfers* t, float split_duration,
+                               uint32_t* out_nearest)
+{
+	uint32_t n0 = st->n;
+	uint32_t* nearest = out_nearest ? out_nearest : (uint32_t*)malloc(sizeof(uint32_t) * (n0 ? n0 : 1));
+	uint32_t* split_ids = (uint32_t*)malloc(sizeof(uint32_t) * (n0 ? n0 : 1));
+	uint32_t n_split = 0;
+	orc_update_transfers_apply(st, s, pairs, n_pairs, nearest);              /* update_transfers.cpp:36-48 */
+	if (s->mMerge || s->mSplit)
+		find_split_and_merge_3_decide(st, s, D, nearest, t, split_ids, &n_split, id_cap); /* :48, mMaxSplitLength = requested_length() */
+	if (s->mSplit) {                                                        /* update_transfers.cpp:60-70 */
+		/* remove_impossible_splits.comp:33-43 */
+		uint32_t newLen = n_split;
+		if (t->cap - t->n < newLen) newLen = t->cap - t->n;
+		if (hidden_cap - st->n_hidden < newLen) newLen = hidden_cap - st->n_hidden;
+		for (uint32_t k = newLen; k < n_split; k++) st->transferring[st->index_list[split_ids[k]]] = 0u;
+		n_split = newLen;
+		for (uint32_t k = 0; k < n_split; k++) {
+			uint32_t id = split_ids[k], idx = st->index_list[id];
+			uint32_t h = st->n_hidden + k, nid = st->n + k;
+			/* duplicate_these (indexed_list.h:141-152): the copy goes to the end of the hidden list, and every list that
+			 * shares the hidden data gains an entry for it -- the fluid's per-id values are copied as well */
+			memcpy(&st->position[4 * h], &st->position[4 * idx], 16);
+			memcpy(&st->velocity[4 * h], &st->velocity[4 * idx], 16);
+			memcpy(&st->pos_backup[4 * h], &st->pos_backup[4 * idx], 16);
+			st->inverse_mass[h] = st->inverse_mass[idx];
+			st->radius[h] = st->radius[idx];
+			st->transferring[h] = st->transferring[idx];
+			if (nid < id_cap) {
+				st->index_list[nid] = h;
+				st->target_radius[nid] = st->target_radius[id];
+				st->kernel_width[nid] = st->kernel_width[id];
+				st->boundariness[nid] = st->boundariness[id];
+				st->boundary_distance[nid] = st->boundary_distance[id];
+			}
+			/* initialize_split_particles.comp:24-31 */
+			st->position[4 * h] += f2i(st->radius[h] * R_POS * 0.1f);
+			st->radius[h] = 0.0f;
+			st->inverse_mass[h] = 2147483648.0f;                            /* float(1 / 0), see the header of this section */
+			/* transferSourceList += splitList etc., update_transfers.cpp:66-68 */
+			t->source[t->n + k] = idx;
+			t->target[t->n + k] = h;
+			t->time_left[t->n + k] = -split_duration;                       /* write_sequence_float(-splitDuration, 0) */
+		}
+		t->n += n_split;
+		st->n_hidden += n_split;
+		st->n = st->n + n_split < id_cap ? st->n + n_split : id_cap;
+	}
+	free(split_ids);
+	if (!out_nearest) free(nearest);
+}
+
+void orc_particle_transfer_apply(orc_state* st, orc_transfers* t, int D, float dt)
+{ /* particle_transfer.cpp:10-28 + particle_transfer.comp:30-84 */
+	uint32_t nh = st->n_hidden;
+	uint8_t* del_h = (uint8_t*)calloc(nh ? nh : 1, 1);
+	uint8_t* del_row = (uint8_t*)calloc(t->n ? t->n : 1, 1);
+	const float invD = (float)(1.0 / (double)D);
+	for (uint32_t id = 0; id < t->n; id++) {
+		float ttl_and_type = t->time_left[id];
+		float ttl = fmaxf_(dt, fabsf(ttl_and_type));
+		int merge = ttl_and_type > 0.0f;
+		uint32_t idS = t->source[id], idT = t->target[id];
+		float radiusS = st->radius[idS], radiusT = st->radius[idT];
+		float invMassS = st->inverse_mass[idS], invMassT = st->inverse_mass[idT];
+		float volS = powf(radiusS, (float)D), volT = powf(radiusT, (float)D);
+		float factorS = merge ? fminf_(1.0f, dt / ttl) : dt * (volS - volT) / (2.0f * ttl * volS);
+		float transfVol = factorS * volS;
+		float normFactor = 1.0f / (invMassS + factorS * invMassT);
+		st->inverse_mass[idS] = invMassS / (1.0f - factorS);
+		st->inverse_mass[idT] = invMassS * invMassT * normFactor;
+		st->radius[idS] = powf(volS - transfVol, invD);
+		st->radius[idT] = powf(volT + transfVol, invD);
+		t->time_left[id] = (ttl - dt) * (merge ? 1.0f : -1.0f);
+		if (ttl == dt) {
+			if (merge) del_h[idS] = 1; else del_row[id] = 1;
+			st->transferring[idS] = 0u;
+			st->transferring[idT] = 0u;
+		}
+	}
+	/* deleteTransferList.delete_these(), then deleteParticleList.delete_these() (particle_transfer.cpp:26-27): the hidden
+	 * particle list is compacted; every list sharing it (the fluid's index list with its per-id values, the transfers' source
+	 * and target lists with the rows they belong to) loses the entries that pointed at a deleted particle */
+	uint32_t* map = (uint32_t*)malloc(sizeof(uint32_t) * (nh ? nh : 1));
+	uint32_t w = 0;
+	for (uint32_t h = 0; h < nh; h++) {
+		map[h] = w;
+		if (del_h[h]) continue;
+		if (w != h) {
+			memcpy(&st->position[4 * w], &st->position[4 * h], 16);
+			memcpy(&st->velocity[4 * w], &st->velocity[4 * h], 16);
+			memcpy(&st->pos_backup[4 * w], &st->pos_backup[4 * h], 16);
+			st->inverse_mass[w] = st->inverse_mass[h];
+			st->radius[w] = st->radius[h];
+			st->transferring[w] = st->transferring[h];
+		}
+		w++;
+	}
+	st->n_hidden = w;
+	w = 0;
+	for (uint32_t id = 0; id < st->n; id++) {
+		uint32_t idx = st->index_list[id];
+		if (del_h[idx]) continue;
+		st->index_list[w] = map[idx];
+		st->target_radius[w] = st->target_radius[id];
+		st->kernel_width[w] = st->kernel_width[id];
+		st->boundariness[w] = st->boundariness[id];
+		st->boundary_distance[w] = st->boundary_distance[id];
+		w++;
+	}
+	st->n = w;
+	w = 0;
+	for (uint32_t id = 0; id < t->n; id++) {
+		if (del_row[id] || del_h[t->source[id]]) continue;
+		t->source[w] = map[t->source[id]];
+		t->target[w] = map[t->target[id]];
+		t->time_left[w] = t->time_left[id];
+		w++;
+	}
+	t->n = w;
+	free(del_h); free(del_row); free(map);
+}
+
+void orc_transfers_follow_reorder(orc_transfers* t, const uint32_t* sorted_index, uint32_t n_hidden)
+{ /* the search permutes the hidden list (hidden'[h] = hidden[sorted_index[h]]); the transfers' source and target lists
+     share that hidden data and are re-pointed by indexed_list::apply_hidden_edit (indexed_list.h:289-308) */
+	uint32_t* inv = (uint32_t*)malloc(sizeof(uint32_t) * (n_hidden ? n_hidden : 1));
+	for (uint32_t h = 0; h < n_hidden; h++) inv[sorted_index[h]] = h;
+	for (uint32_t r = 0; r < t->n; r++) { t->source[r] = inv[t->source[r]]; t->target[r] = inv[t->target[r]]; }
+	free(inv);
+}
+
 void orc_kernel_width_from_boundary_distance(orc_state* st, const orc_settings* s)
 { /* pool.cpp:77-80 -> uint_to_float_with_indexed_lower_bound.comp:32-44 */
 	const float factor = s->mTargetRadiusScaleFactor / R_POS, lowerBoundFactor = ORC_KERNEL_SCALE;
@@ -998,23 +1197,29 @@ void orc_velocity_handling(orc_state* st, float dt, const float accel[3])
 }
 
 /* ---------------------------------------------------------------------------------- */
-/* one substep, pool.cpp:67-106 (without split/merge; update_transfers on request)     */
+/* one substep, pool.cpp:67-106                                                       */
 /* ---------------------------------------------------------------------------------- */
 uint32_t orc_substep(orc_state* st, const orc_settings* s, const orc_substep_params* p, uint32_t* pairs, uint32_t cap)
 {
+	const int transfers = p->transfers != NULL && !p->basic_pbf && (s->mMerge || s->mSplit);
 	if (p->integrate) orc_velocity_handling(st, p->dt, p->accel);                        /* pool.cpp:71 */
+	if (transfers) orc_particle_transfer_apply(st, p->transfers, p->dims, p->dt);        /* pool.cpp:73-75 */
 	if (p->update_transfers && !p->basic_pbf && s->mBaseKernelWidthOnBoundaryDistance)
 		orc_kernel_width_from_boundary_distance(st, s);                                  /* pool.cpp:77-80 */
 	int adaptive = !p->basic_pbf && !s->mBaseKernelWidthOnBoundaryDistance;
 	float scale = (p->basic_pbf || s->mBaseKernelWidthOnBoundaryDistance) ? 1.0f : 1.5f; /* pool.cpp:83 */
 	uint32_t np;
-	if (p->use_binary_search) np = orc_neighborhood_binary_search_apply(st, s, scale, pairs, cap, NULL, NULL, NULL, NULL);
-	else np = orc_neighborhood_green_apply(st, s, p->dims, scale, p->min_pos, p->max_pos, p->res_log2, pairs, cap, NULL, NULL, NULL, NULL);
+	uint32_t* sidx = transfers ? (uint32_t*)malloc(sizeof(uint32_t) * (st->n_hidden ? st->n_hidden : 1)) : NULL;
+	if (p->use_binary_search) np = orc_neighborhood_binary_search_apply(st, s, scale, pairs, cap, NULL, NULL, NULL, sidx);
+	else np = orc_neighborhood_green_apply(st, s, p->dims, scale, p->min_pos, p->max_pos, p->res_log2, pairs, cap, NULL, sidx, NULL, NULL);
+	if (transfers) { orc_transfers_follow_reorder(p->transfers, sidx, st->n_hidden); free(sidx); }
 	if (adaptive) np = orc_spread_kernel_width_apply(st, s, pairs, np, NULL);            /* pool.cpp:87-89 */
 	for (int i = 0; i < p->solver_iterations; i++) {                                     /* pool.cpp:92-95 */
 		if (st->n > 0) orc_box_collision(st, p->box_min4, p->box_max4, p->n_boxes);
 		orc_incompressibility_apply(st, s, p->dims, pairs, np, NULL, NULL);
 	}
-	if (p->update_transfers && !p->basic_pbf) orc_update_transfers_apply(st, s, pairs, np, NULL); /* pool.cpp:99-102 */
+	if (transfers)                                                                       /* pool.cpp:99-102 */
+		orc_update_transfers_full(st, p->hidden_cap, p->hidden_cap, s, p->dims, pairs, np, p->transfers, p->split_duration, NULL);
+	else if (p->update_transfers && !p->basic_pbf) orc_update_transfers_apply(st, s, pairs, np, NULL);
 	return np;
 }

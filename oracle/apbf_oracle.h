@@ -184,6 +184,23 @@ void orc_update_transfers_apply(orc_state* st, const orc_settings* s, const uint
 /* pool.cpp:77-80: uint_to_float_with_indexed_lower_bound.comp, boundary distance -> kernel width */
 void orc_kernel_width_from_boundary_distance(orc_state* st, const orc_settings* s);
 
+/* list_definitions.h:16-18: hidden_transfers (source and target index the hidden particle list) */
+typedef struct orc_transfers {
+	uint32_t  n, cap;
+	uint32_t* source;    /* [cap] hidden particle index */
+	uint32_t* target;    /* [cap] */
+	float*    time_left; /* [cap] > 0 merge, <= 0 split (particle_transfer.comp:35-37) */
+} orc_transfers;
+/* update_transfers::apply (update_transfers.cpp:14-70) with merge / split as `s` says, invocations in ascending id order.
+ * The arrays of `st` must have room for hidden_cap hidden entries and id_cap ids; st->n, st->n_hidden and t->n are updated. */
+void orc_update_transfers_full(orc_state* st, uint32_t hidden_cap, uint32_t id_cap, const orc_settings* s, int dims,
+                               const uint32_t* pairs, uint32_t n_pairs, orc_transfers* t, float split_duration,
+                               uint32_t* out_nearest);
+/* particle_transfer::apply(dt) (particle_transfer.cpp:10-28, particle_transfer.comp:30-84) incl. both delete_these() */
+void orc_particle_transfer_apply(orc_state* st, orc_transfers* t, int dims, float dt);
+/* the transfers' source / target follow a permutation of the hidden list (sorted_index[new] = old) */
+void orc_transfers_follow_reorder(orc_transfers* t, const uint32_t* sorted_index, uint32_t n_hidden);
+
 void orc_box_collision(orc_state* st, const float* box_min4, const float* box_max4, uint32_t n_boxes);
 
 /* ---- velocity handling (velocity_handling.cpp:15-31) ------------------------------ */
@@ -203,7 +220,10 @@ typedef struct orc_substep_params {
 	uint32_t n_boxes;
 	const float* box_min4;
 	const float* box_max4;
-	int      update_transfers;   /* pool.cpp:77-80 and :99-102 (merge and split stay off) */
+	int      update_transfers;   /* pool.cpp:77-80 and :99-102 */
+	orc_transfers* transfers;    /* non-NULL with mMerge / mSplit: particle_transfer (pool.cpp:73-75) and the full update_transfers */
+	uint32_t hidden_cap;         /* room in the arrays of the state (hidden entries and ids) */
+	float    split_duration;     /* settings::splitDuration */
 } orc_substep_params;
 /* returns the number of pairs left in `pairs` after the substep */
 uint32_t orc_substep(orc_state* st, const orc_settings* s, const orc_substep_params* p,

@@ -44,7 +44,13 @@ class _SubstepParams(C.Structure):
                 ("use_binary_search", C.c_int), ("integrate", C.c_int), ("dt", C.c_float),
                 ("accel", C.c_float * 3), ("min_pos", C.c_float * 3), ("max_pos", C.c_float * 3),
                 ("res_log2", C.c_uint32), ("n_boxes", C.c_uint32), ("box_min4", C.c_void_p), ("box_max4", C.c_void_p),
-                ("update_transfers", C.c_int)]
+                ("update_transfers", C.c_int), ("transfers", C.c_void_p), ("hidden_cap", C.c_uint32),
+                ("split_duration", C.c_float)]
+
+
+class _Transfers(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("cap", C.c_uint32), ("source", C.c_void_p), ("target", C.c_void_p),
+                ("time_left", C.c_void_p)]
 
 
 _lib = None
@@ -109,6 +115,46 @@ class State:
         for name, _, _ in self.FIELDS:
             setattr(st, name, getattr(self, name).ctypes.data)
         return st
+
+
+class Transfers:
+    """hidden_transfers (list_definitions.h:16-18): rows (source idx, target idx, time left), fixed capacity"""
+
+    def __init__(self, cap, source=(), target=(), time_left=()):
+        self.cap = int(cap)
+        self.source = np.zeros(self.cap, np.uint32)
+        self.target = np.zeros(self.cap, np.uint32)
+        self.time_left = np.zeros(self.cap, np.float32)
+        self.n = len(source)
+        self.source[:self.n], self.target[:self.n], self.time_left[:self.n] = source, target, time_left
+
+    def copy(self):
+        return Transfers(self.cap, self.source[:self.n], self.target[:self.n], self.time_left[:self.n])
+
+    def c(self):
+        t = _Transfers()
+        t.n, t.cap = self.n, self.cap
+        t.source, t.target, t.time_left = self.source.ctypes.data, self.target.ctypes.data, self.time_left.ctypes.data
+        return t
+
+    def rows(self):
+        return self.source[:self.n].copy(), self.target[:self.n].copy(), self.time_left[:self.n].copy()
+
+
+def _with_room(st, cap):
+    """the lists of `st` in arrays with room for `cap` entries (split appends particles)"""
+    for name, dt, w in State.FIELDS:
+        a = getattr(st, name)
+        big = np.zeros((cap, w) if w > 1 else (cap,), dt)
+        big[:a.shape[0]] = a
+        setattr(st, name, big)
+
+
+def _trim(st, cst):
+    hidden = ("position", "velocity", "inverse_mass", "radius", "pos_backup", "transferring")
+    for name, _, _ in State.FIELDS:
+        setattr(st, name, getattr(st, name)[:cst.n_hidden if name in hidden else cst.n].copy())
+    st.n, st.n_hidden = int(cst.n), int(cst.n_hidden)
 
 
 # ---- thin wrappers --------------------------------------------------------------------
@@ -244,6 +290,28 @@ def update_transfers_apply(st, s, pairs):
     return nearest
 
 
+def update_transfers_full(st, s, dims, pairs, transfers, hidden_cap, split_duration=0.0):
+    """update_transfers::apply (update_transfers.cpp:14-70) with merge / split as the settings say; `st` and `transfers`
+    are updated in place (the lists may grow up to hidden_cap).  Returns the nearest-neighbour ids."""
+    pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+    nearest = np.zeros(max(st.n, 1), np.uint32)
+    _with_room(st, hidden_cap)
+    cst, ct = st.c(), transfers.c()
+    lib().orc_update_transfers_full(C.byref(cst), C.c_uint32(hidden_cap), C.c_uint32(hidden_cap), C.byref(s), dims, _p(pairs),
+                                    C.c_uint32(len(pairs)), C.byref(ct), C.c_float(split_duration), _p(nearest))
+    _trim(st, cst)
+    transfers.n = int(ct.n)
+    return nearest
+
+
+def particle_transfer_apply(st, transfers, dims, dt):
+    """particle_transfer::apply(dt) (particle_transfer.cpp:10-28)"""
+    cst, ct = st.c(), transfers.c()
+    lib().orc_particle_transfer_apply(C.byref(cst), C.byref(ct), dims, C.c_float(dt))
+    _trim(st, cst)
+    transfers.n = int(ct.n)
+
+
 def kernel_width_from_boundary_distance(st, s):
     """pool.cpp:77-80 (uint_to_float_with_indexed_lower_bound.comp)"""
     cst = st.c()
@@ -263,7 +331,8 @@ def velocity_handling(st, dt, accel):
 
 
 def substep(st, s, *, dims, basic_pbf, solver_iterations, min_pos, max_pos, res_log2, box_min4, box_max4, cap,
-            use_binary_search=False, integrate=False, dt=1.0 / 60.0, accel=(0.0, -10.0, 0.0), update_transfers=False):
+            use_binary_search=False, integrate=False, dt=1.0 / 60.0, accel=(0.0, -10.0, 0.0), update_transfers=False,
+            transfers=None, hidden_cap=None, split_duration=0.0):
     """One substep in pool::update order (pool.cpp:67-106). Returns the final pair list."""
     box_min4 = np.ascontiguousarray(box_min4, np.float32).reshape(-1, 4)
     box_max4 = np.ascontiguousarray(box_max4, np.float32).reshape(-1, 4)
@@ -275,8 +344,17 @@ def substep(st, s, *, dims, basic_pbf, solver_iterations, min_pos, max_pos, res_
     p.box_min4, p.box_max4 = box_min4.ctypes.data, box_max4.ctypes.data
     p.update_transfers = int(update_transfers)
     pairs = np.zeros((cap, 2), np.uint32)
+    ct = None
+    if transfers is not None:                       # settings::merge / split: the lists may grow up to hidden_cap
+        hidden_cap = int(hidden_cap or st.n_hidden)
+        _with_room(st, hidden_cap)
+        ct = transfers.c()
+        p.transfers, p.hidden_cap, p.split_duration = C.addressof(ct), hidden_cap, split_duration
     cst = st.c()
     n = lib().orc_substep(C.byref(cst), C.byref(s), C.byref(p), _p(pairs), C.c_uint32(cap))
+    if transfers is not None:
+        _trim(st, cst)
+        transfers.n = int(ct.n)
     return pairs[:n]
 
 

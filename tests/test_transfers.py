@@ -1,0 +1,288 @@
+"""Split / merge proper: update_transfers::apply with settings::merge / settings::split
+(source/update_transfers.cpp:14-70) and particle_transfer::apply (source/particle_transfer.cpp:10-28).
+
+CPU leg: known answers derived by hand from the shaders (find_split_and_merge_3.comp:86-121, remove_impossible_splits.comp,
+initialize_split_particles.comp, particle_transfer.comp:30-84) pin the oracle's restatement -- the reference has no test for
+this path (parity unpinned by the reference, pinned by these hand-derived cases).
+GPU leg: the CUDA path through the C-ABI against the oracle, bit for bit (lists, lengths, transfer rows).
+"""
+import numpy as np
+import pytest
+
+from apbf_b200 import scenes
+from conftest import oracle_state
+
+R = 262144.0
+DT = np.float32(1.0 / 60.0)
+
+
+def _state(orc, pos, radius, target_radius, transferring=None):
+    n = len(pos)
+    position = np.zeros((n, 4), np.int32)
+    position[:, :3] = np.trunc(np.asarray(pos, np.float32) * np.float32(R)).astype(np.int32)
+    radius = np.asarray(radius, np.float32)
+    return orc.State(index_list=np.arange(n, dtype=np.uint32), position=position, velocity=np.zeros((n, 4), np.float32),
+                     inverse_mass=(1.0 / (2.0 * radius) ** 3).astype(np.float32), radius=radius, pos_backup=position.copy(),
+                     transferring=np.zeros(n, np.uint32) if transferring is None else np.asarray(transferring, np.uint32),
+                     target_radius=np.asarray(target_radius, np.float32), kernel_width=4.0 * radius,
+                     boundariness=np.ones(n, np.float32), boundary_distance=(radius * R).astype(np.uint32))
+
+
+def _settings(orc, merge, split, merge_duration=2.0 / 60.0):
+    s = orc.default_settings()
+    s.mMerge, s.mSplit, s.mUpdateTargetRadius, s.mMergeDuration = merge, split, 0, merge_duration
+    return s
+
+
+def _all_pairs(n):
+    return np.array([(a, b) for a in range(n) for b in range(n) if a != b], np.uint32).reshape(-1, 2)
+
+
+# ---- CPU: hand-derived known answers ------------------------------------------------------------------------------------------
+def test_merge_known_answer(orc):
+    """two equal particles 0.5 apart, target radius 2: 1 + 1 <= 8 -> merge; equal radii: the higher hidden index is the source
+    (find_split_and_merge_3.comp:66,95-96).  Two steps of 1/60 with mergeDuration 2/60: half the mass moves, then the rest."""
+    st = _state(orc, [(0, 0, 0), (0.5, 0, 0)], [1, 1], [2, 2])
+    s, T = _settings(orc, 1, 0), orc.Transfers(4)
+    nearest = orc.update_transfers_full(st, s, 3, _all_pairs(2), T, hidden_cap=4)
+    assert nearest.tolist() == [1, 0]
+    src, tgt, ttl = T.rows()
+    assert (src.tolist(), tgt.tolist()) == ([1], [0]) and ttl[0] == np.float32(2.0 / 60.0)
+    assert st.transferring.tolist() == [1, 1] and st.n == 2
+    orc.particle_transfer_apply(st, T, 3, DT)
+    assert st.n == 2 and T.n == 1
+    assert st.inverse_mass.tolist() == [np.float32(0.125 * 0.125) * (np.float32(1.0) / np.float32(0.125 + 0.5 * 0.125)), 0.25]
+    assert np.allclose(1.0 / st.inverse_mass, [12.0, 4.0], rtol=1e-6)                  # 8 + 4 and 8 - 4
+    assert np.allclose(st.radius, [1.5 ** (1 / 3), 0.5 ** (1 / 3)], rtol=1e-6)
+    assert T.rows()[2][0] == np.float32(2.0 / 60.0) - DT
+    orc.particle_transfer_apply(st, T, 3, DT)                                          # ttl == dt: the source is deleted
+    assert st.n == 1 and st.n_hidden == 1 and T.n == 0
+    assert np.allclose(1.0 / st.inverse_mass, [16.0], rtol=1e-6) and np.allclose(st.radius, [2.0 ** (1 / 3)], rtol=1e-6)
+    assert st.transferring.tolist() == [0] and st.index_list.tolist() == [0]
+
+
+def test_split_known_answer(orc):
+    """radius 2 against a target radius of 1: 1 * 2^(1/3) * 0.99 <= 2 -> split.  The copy sits 0.1 radius along x with radius 0
+    and inverse mass float(1 / 0) = 2^31; with splitDuration 0 one particle_transfer step halves the volume."""
+    st = _state(orc, [(3, 0, 0)], [2], [1])
+    s, T = _settings(orc, 0, 1), orc.Transfers(4)
+    st.kernel_width[:] = 9.0
+    orc.update_transfers_full(st, s, 3, np.zeros((0, 2), np.uint32), T, hidden_cap=4, split_duration=0.0)
+    assert st.n == 2 and st.n_hidden == 2 and st.index_list.tolist() == [0, 1]
+    assert st.position[:, 0].tolist() == [3 * 262144, 3 * 262144 + 52428]
+    assert st.radius.tolist() == [2.0, 0.0] and st.inverse_mass.tolist() == [1.0 / 64.0, 2147483648.0]
+    assert st.kernel_width.tolist() == [9.0, 9.0] and st.transferring.tolist() == [1, 1]
+    src, tgt, ttl = T.rows()
+    assert (src.tolist(), tgt.tolist()) == ([0], [1]) and ttl[0] == 0.0 and np.signbit(ttl[0])
+    orc.particle_transfer_apply(st, T, 3, DT)
+    assert T.n == 0 and st.n == 2 and st.transferring.tolist() == [0, 0]
+    assert st.inverse_mass.tolist() == [1.0 / 32.0, 1.0 / 32.0]
+    assert np.allclose(st.radius, [4.0 ** (1 / 3)] * 2, rtol=1e-6)
+
+
+def test_conflicting_merges_resolve_in_id_order(orc):
+    """three particles in a row, each wants its nearest neighbour: id 0 takes (1 -> 0); ids 1 and 2 find particle 1 taken and
+    release their source again (find_split_and_merge_3.comp:98-102)"""
+    st = _state(orc, [(0, 0, 0), (0.5, 0, 0), (0.9, 0, 0)], [1, 1, 1], [2, 2, 2])
+    s, T = _settings(orc, 1, 0), orc.Transfers(4)
+    nearest = orc.update_transfers_full(st, s, 3, _all_pairs(3), T, hidden_cap=4)
+    assert nearest.tolist() == [1, 2, 1]
+    assert [a.tolist() for a in T.rows()[:2]] == [[1], [0]] and st.transferring.tolist() == [1, 1, 0]
+
+
+def test_full_transfer_list_releases_the_particles(orc):
+    """no room in the transfer list: the merge is dropped and both particles are free again (:104-109), so that the split of a
+    later id still happens; no room in the hidden list: the split is removed again (remove_impossible_splits.comp:33-43)"""
+    st = _state(orc, [(0, 0, 0), (0.5, 0, 0), (0.9, 0, 0)], [1, 1, 2.6], [2, 2, 2])
+    s, T = _settings(orc, 1, 1), orc.Transfers(1, [7], [8], [0.5])                     # one row, already taken
+    orc.update_transfers_full(st, s, 3, _all_pairs(3), T, hidden_cap=4)
+    assert T.n == 1 and st.n == 3 and st.transferring.tolist() == [0, 0, 0]           # merge dropped; the split has no row either
+    T = orc.Transfers(2, [7], [8], [0.5])
+    st = _state(orc, [(0, 0, 0), (0.5, 0, 0), (0.9, 0, 0)], [1, 1, 2.6], [2, 2, 2])
+    orc.update_transfers_full(st, s, 3, _all_pairs(3), T, hidden_cap=4)                # id 0 merges (1 -> 0); id 2 splits but has no row left
+    assert [a.tolist() for a in T.rows()[:2]] == [[7, 1], [8, 0]] and st.n == 3 and st.transferring.tolist() == [1, 1, 0]
+    T = orc.Transfers(3, [7], [8], [0.5])
+    st = _state(orc, [(0, 0, 0), (0.5, 0, 0), (0.9, 0, 0)], [1, 1, 2.6], [2, 2, 2])
+    orc.update_transfers_full(st, s, 3, _all_pairs(3), T, hidden_cap=3)                # a row, but no room for the copy
+    assert T.n == 2 and st.n == 3 and st.transferring.tolist() == [1, 1, 0]
+    st = _state(orc, [(0, 0, 0), (0.5, 0, 0), (0.9, 0, 0)], [1, 1, 2.6], [2, 2, 2])
+    T = orc.Transfers(3, [7], [8], [0.5])
+    orc.update_transfers_full(st, s, 3, _all_pairs(3), T, hidden_cap=4, split_duration=0.25)
+    assert [a.tolist() for a in T.rows()] == [[7, 1, 2], [8, 0, 3], [0.5, np.float32(2.0 / 60.0), -0.25]]
+    assert st.n == 4 and st.transferring.tolist() == [1, 1, 1, 1]
+
+
+def test_transfers_follow_the_search_and_mass_is_conserved(orc):
+    """substeps with merge and split on (pool.cpp:67-106): the transfer rows follow the search's permutation, every flagged
+    particle is in exactly one row, the hidden and the index list stay in step, mass is conserved"""
+    sc = scenes.waterdrop(12, jitter=0.1, wall_gap=3.0)
+    s = orc.default_settings()
+    s.mMerge, s.mSplit, s.mBaseKernelWidthOnBoundaryDistance = 1, 1, 0
+    s.mTargetRadiusOffset, s.mTargetRadiusScaleFactor, s.mMergeDuration = 2.0, 0.25, 0.05
+    st = oracle_state(orc, sc)
+    st.radius[::7] *= 1.9                                                              # some particles far above their target radius: splits
+    st.inverse_mass[::7] = 1.0 / (2.0 * st.radius[::7]) ** 3
+    cap = 2 * sc.n
+    T = orc.Transfers(cap)
+    mass0 = (1.0 / st.inverse_mass.astype(np.float64)).sum()
+    seen_rows, n_min, n_max = 0, st.n, st.n
+    for _ in range(14):
+        orc.substep(st, s, dims=3, basic_pbf=False, solver_iterations=2, min_pos=sc.min_pos, max_pos=sc.max_pos, res_log2=sc.res_log2,
+                    box_min4=sc.box_min, box_max4=sc.box_max, cap=sc.n * 600, integrate=True, update_transfers=True, transfers=T,
+                    hidden_cap=cap, split_duration=0.0)
+        src, tgt, _ = T.rows()
+        seen_rows += T.n
+        n_min, n_max = min(n_min, st.n), max(n_max, st.n)
+        assert st.n == st.n_hidden and sorted(st.index_list.tolist()) == list(range(st.n))
+        members = np.concatenate([src, tgt])
+        assert len(np.unique(members)) == len(members) and (len(members) == 0 or members.max() < st.n_hidden)
+        assert sorted(np.flatnonzero(st.transferring).tolist()) == sorted(members.tolist())
+        m = (1.0 / st.inverse_mass.astype(np.float64))
+        assert abs(m[np.isfinite(m)].sum() / mass0 - 1.0) < 1e-5
+    assert seen_rows > 0 and n_max > sc.n and n_min <= n_max
+
+
+# ---- GPU: the CUDA path against the oracle ------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import apbf_b200
+    return apbf_b200
+
+
+def _searched(gpu, orc, s, capacity_factor=2.0, side=14, seed=11):
+    """the same searched state on both sides, radii / target radii / flags drawn so that merges, splits and conflicts all occur"""
+    sc = scenes.waterdrop(side, jitter=0.1)
+    cap = sc.n * 300
+    st = oracle_state(orc, sc)
+    epairs = orc.green_apply(st, s, 3, 1.0, sc.min_pos, sc.max_pos, sc.res_log2, cap)
+    ctx = gpu.Context()
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    pcap = int(sc.n * capacity_factor)
+    L = gpu.ParticleLists(ctx, sc.arrays, capacity=pcap, neighbor_capacity=cap)
+    gpu.neighborhood_green(ctx).set_data(L).set_range_scale(1.0).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply()
+    assert np.array_equal(L.read_pairs(), epairs) and np.array_equal(st.index_list, np.arange(sc.n))
+    rng = np.random.default_rng(seed)
+    radius = rng.uniform(0.8, 3.2, sc.n).astype(np.float32)
+    radius[rng.random(sc.n) < 0.3] = np.float32(1.5)                                   # ties: equal radii decide by the hidden index
+    inv_mass = (1.0 / (2.0 * radius) ** 3).astype(np.float32)
+    target = rng.uniform(0.7, 4.5, sc.n).astype(np.float32)
+    flags = (rng.random(sc.n) < 0.1).astype(np.uint32)
+    for name, v in (("radius", radius), ("inverse_mass", inv_mass), ("target_radius", target), ("transferring", flags)):
+        getattr(st, name)[:] = v
+        L.write(name, v)
+    return sc, st, epairs, ctx, L, pcap
+
+
+def _same_lists(L, st, T, TL):
+    assert L.length() == st.n and int(L.words[1].item()) == st.n_hidden
+    got = L.read_all()
+    for k, _, _ in type(st).FIELDS:
+        assert np.array_equal(got[k].view(np.uint32), getattr(st, k).view(np.uint32)), k
+    for a, b in zip(TL.rows(), T.rows()):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("merge,split,t_cap,cap_factor,split_duration", [
+    (1, 1, 0, 2.0, 0.0), (1, 0, 0, 2.0, 0.0), (0, 1, 0, 2.0, 0.5), (1, 1, 40, 2.0, 0.0), (1, 1, 0, 1.02, 0.25), (1, 1, 3, 1.0, 0.0)])
+def test_update_transfers_split_merge_matches_oracle(gpu, orc, merge, split, t_cap, cap_factor, split_duration):
+    """the merge / split decisions in ascending id order, rows, copies and the lengths: bit exact, also with a transfer list that
+    fills up (later merges release their particles, later splits take them) and a hidden list without room for every copy"""
+    s = _settings(orc, merge, split, merge_duration=2.0 / 60.0)
+    sc, st, epairs, ctx, L, pcap = _searched(gpu, orc, s, cap_factor)
+    t_cap = t_cap or pcap
+    pre = ([sc.n + 5, sc.n + 6], [sc.n + 7, sc.n + 8], [0.25, -0.5])                  # rows already there stay where they are
+    T, TL = orc.Transfers(t_cap, *pre), gpu.TransferList(ctx, t_cap, *pre)
+    enearest = orc.update_transfers_full(st, s, 3, epairs, T, hidden_cap=pcap, split_duration=split_duration)
+    gnearest = gpu.update_transfers(ctx).set_data(L, TL).set_split_duration(split_duration).apply(debug=True)
+    assert np.array_equal(gnearest, enearest)
+    _same_lists(L, st, T, TL)
+    if t_cap == pcap and cap_factor == 2.0:
+        src, tgt, ttl = T.rows()
+        assert (not merge or np.count_nonzero(ttl[2:] > 0) > 20) and (not split or st.n > sc.n + 20)
+
+
+@pytest.mark.gpu
+def test_particle_transfer_matches_oracle(gpu, orc):
+    """particle_transfer.comp row by row, then both delete_these(): three steps over merges that take two steps and splits that
+    finish at once -- masses, radii, flags, the compacted lists and the re-pointed transfer rows, bit exact"""
+    s = _settings(orc, 1, 1, merge_duration=2.0 / 60.0)
+    sc, st, epairs, ctx, L, pcap = _searched(gpu, orc, s)
+    T, TL = orc.Transfers(pcap), gpu.TransferList(ctx, pcap)
+    orc.update_transfers_full(st, s, 3, epairs, T, hidden_cap=pcap, split_duration=0.0)
+    gpu.update_transfers(ctx).set_data(L, TL).apply()
+    _same_lists(L, st, T, TL)
+    n_before, rows_before = st.n, T.n
+    op = gpu.particle_transfer(ctx).set_data(L, TL)
+    for step in range(3):
+        orc.particle_transfer_apply(st, T, 3, float(DT))
+        op.apply(float(DT))
+        _same_lists(L, st, T, TL)
+    assert st.n < n_before and T.n == 0 and rows_before > 40 and not st.transferring.any()
+
+
+@pytest.mark.gpu
+def test_transfers_follow_reorder_matches_oracle(gpu, orc):
+    """a search permutes the hidden list: source / target of the rows are re-pointed (indexed_list::apply_hidden_edit)"""
+    import torch
+    s = _settings(orc, 1, 1)
+    sc, st, epairs, ctx, L, pcap = _searched(gpu, orc, s)
+    rng = np.random.default_rng(3)
+    members = rng.permutation(sc.n)[:200].astype(np.uint32)
+    T = orc.Transfers(pcap, members[:100], members[100:], rng.uniform(-1, 1, 100).astype(np.float32))
+    TL = gpu.TransferList(ctx, pcap, *T.rows())
+    perm = rng.permutation(sc.n).astype(np.uint32)                                     # sorted_index[new] = old
+    inv = np.empty_like(perm); inv[perm] = np.arange(sc.n, dtype=np.uint32)
+    t, sidx = TL.c(), torch.from_numpy(perm.view(np.int32)).cuda()
+    import ctypes as C
+    rc = ctx.lib.apbf_transfers_follow_reorder(ctx.handle, C.byref(t), sidx.data_ptr(), L.words.data_ptr() + 4, L.capacity)
+    assert rc == 0
+    src, tgt, ttl = TL.rows()
+    assert np.array_equal(src, inv[members[:100]]) and np.array_equal(tgt, inv[members[100:]]) and np.array_equal(ttl, T.rows()[2])
+
+
+@pytest.mark.gpu
+def test_sim_with_merge_and_split(gpu, orc):
+    """pool::update with settings::merge / split through apbf_sim (particle_transfer after velocity_handling, the full
+    update_transfers after the solver): the lists stay consistent, mass is conserved, particles are created and deleted, and
+    the run tracks the oracle's (the decisions are thresholds on floating-point values: counts may differ by a few)"""
+    sc = scenes.waterdrop(12, jitter=0.1, wall_gap=3.0)
+    s = orc.default_settings()
+    s.mMerge, s.mSplit, s.mBaseKernelWidthOnBoundaryDistance = 1, 1, 0
+    s.mTargetRadiusOffset, s.mTargetRadiusScaleFactor, s.mMergeDuration = 2.0, 0.25, 0.05
+    sc.arrays["radius"][::7] *= 1.9
+    sc.arrays["inverse_mass"][::7] = 1.0 / (2.0 * sc.arrays["radius"][::7]) ** 3
+    st = oracle_state(orc, sc)
+    cap = 2 * sc.n
+    T = orc.Transfers(cap)
+    ctx = gpu.Context(dims=3)
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    sim = gpu.Sim(ctx, sc, capacity=cap, neighbor_capacity=sc.n * 600, integrate=True, basic_pbf=False, solver_iterations=2,
+                  update_transfers=True, transfers=True, split_duration=0.0)
+    sim.upload(sc.arrays)
+    mass0 = (1.0 / sc.arrays["inverse_mass"].astype(np.float64)).sum()
+    from apbf_b200 import empty_host_arrays
+    seen_rows, n_max = 0, sc.n
+    for step in range(14):
+        orc.substep(st, s, dims=3, basic_pbf=False, solver_iterations=2, min_pos=sc.min_pos, max_pos=sc.max_pos, res_log2=sc.res_log2,
+                    box_min4=sc.box_min, box_max4=sc.box_max, cap=sc.n * 600, integrate=True, update_transfers=True, transfers=T,
+                    hidden_cap=cap, split_duration=0.0)
+        sim.substep(1)
+        out = empty_host_arrays(cap)
+        n = sim.download(out)
+        src, tgt, ttl = sim.download_transfers()
+        seen_rows += len(src)
+        n_max = max(n_max, n)
+        assert ctx.device_flags() == 0 and sorted(out["index_list"][:n].tolist()) == list(range(n))
+        members = np.concatenate([src, tgt])
+        assert len(np.unique(members)) == len(members) and (len(members) == 0 or members.max() < n)
+        assert sorted(np.flatnonzero(out["transferring"][:n]).tolist()) == sorted(members.tolist())
+        m = 1.0 / out["inverse_mass"][:n].astype(np.float64)
+        assert abs(m[np.isfinite(m)].sum() / mass0 - 1.0) < 1e-5
+        assert abs(n - st.n) <= max(4, st.n // 50) and abs(len(src) - T.n) <= max(4, T.n // 10), (step, n, st.n, len(src), T.n)
+        if step == 0:                                                                  # first substep: same state in, same decisions out
+            assert n == st.n and len(src) == T.n
+    assert seen_rows > 0 and n_max > sc.n
