@@ -440,7 +440,7 @@ class particle_transfer(_Operator):
 
     def apply(self, delta_time):
         fl, tr = self.lists.fluid(), self.transfers.c()
-        _check(self.ctx, self.lib.apbf_particle_transfer_apply(self.ctx.handle, C.byref(fl), C.byref(tr), float(delta_time)))
+        _check(self.ctx, self.lib.apbf_particle_transfer_apply(self.ctx.handle, C.byref(fl), C.byref(tr), float(delta_time), None))
         self.lists.swap()
         self.transfers.swap()
 

@@ -113,7 +113,7 @@ SIGNATURES = {
     "apbf_spread_kernel_width_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), vp]),
     "apbf_update_transfers_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), vp]),
     "apbf_update_transfers_split_merge_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), C.POINTER(Transfers), C.c_float, vp]),
-    "apbf_particle_transfer_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Transfers), C.c_float]),
+    "apbf_particle_transfer_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Transfers), C.c_float, vp]),
     "apbf_transfers_follow_reorder": (C.c_int, [vp, C.POINTER(Transfers), vp, vp, C.c_uint32]),
     "apbf_kernel_width_from_boundary_distance": (C.c_int, [vp, C.POINTER(Fluid)]),
     "apbf_box_collision_apply": (C.c_int, [vp, C.POINTER(Particles), vp, vp, C.c_uint32]),

@@ -139,6 +139,7 @@ int apbf_sim_upload(apbf_sim* sim, const apbf_host_state* h)
 		if (it.src && n) APBF_CUDA(ctx, cudaMemcpyAsync(it.dst, it.src, it.stride * n, cudaMemcpyHostToDevice, st));
 	k_set_lengths<<<1, 1, 0, st>>>(f.particle.length, f.particle.hidden_length, (uint32_t)n);
 	APBF_LAUNCHED(ctx);
+	if (sim->tr.length) APBF_CUDA(ctx, cudaMemsetAsync(sim->tr.length, 0, 4, st)); // a fresh scene has no transfers under way
 	if (!h->index_list) APBF_TRY(apbf_write_sequence(ctx, (uint32_t*)f.particle.index_list.data, f.particle.length, sim->cfg.particle_capacity, 0u, 1u, 1u));
 	return APBF_OK;
 }
@@ -188,7 +189,7 @@ int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
 			sim->last_dt = c.dt;
 		}
 		if (transfers) {                                                              // pool.cpp:73-75
-			APBF_TRY(apbf_particle_transfer_apply(ctx, &sim->fluid, &sim->tr, c.dt));
+			APBF_TRY(apbf_particle_transfer_apply(ctx, &sim->fluid, &sim->tr, c.dt, nullptr));
 			apbf_sim_swap_buffers(sim);
 			for (apbf_array* a : { &sim->tr.source, &sim->tr.target, &sim->tr.time_left }) swap_array(a);
 		}

@@ -470,7 +470,7 @@ int apbf_update_transfers_split_merge_apply(apbf_ctx* ctx, apbf_fluid* fluid, co
 	return APBF_OK;
 }
 
-int apbf_particle_transfer_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_transfers* transfers, float dt)
+int apbf_particle_transfer_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_transfers* transfers, float dt, uint32_t* out_hidden_edit)
 {
 	if (!ctx) return APBF_ERR_INVALID;
 	APBF_REQUIRE(ctx, fluid && transfers_valid(transfers));
@@ -551,6 +551,7 @@ int apbf_particle_transfer_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_transfer
 	memset(&t, 0, sizeof t);
 	t.src4[0] = (const uint32_t*)transfers->time_left.data; t.dst4[0] = (uint32_t*)transfers->time_left.reorder_out; t.n4 = 1;
 	APBF_TRY(apbf_launch_reorder(ctx, t, perm_r, words + TW_NEW_ROWS, t_cap));
+	if (out_hidden_edit) APBF_CUDA(ctx, cudaMemcpyAsync(out_hidden_edit, perm_h, w * nh_cap, cudaMemcpyDeviceToDevice, st));
 	k_pt_lengths<<<1, 1, 0, st>>>(words, p.hidden_length, p.length, transfers->length);
 	APBF_LAUNCHED(ctx);
 	return APBF_OK;

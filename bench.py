@@ -44,6 +44,13 @@ def make_scene(name, world=1):
     if name == "dam_break_1M_default_mode":   # the reference's default adaptive mode: kernel width from the boundary distance
         # (pool.cpp:77-80) + update_transfers after the solver (pool.cpp:99-102, merge and split off); no spread_kernel_width
         return scenes.dam_break(100, 100, 100, adaptive=True), dict(adaptive=False, basic_pbf=False, update_transfers=True, pairs_per_particle=60)
+    if name == "dam_break_1M_split_merge":   # the default mode with settings::merge / settings::split on (pool.cpp:73-75, :99-102;
+        # SURVEY 8f row 3): particle_transfer after velocity_handling, merge / split decisions after the solver; room for 25 % copies
+        return scenes.dam_break(100, 100, 100, adaptive=True), dict(adaptive=False, basic_pbf=False, update_transfers=True, transfers=True,
+                                                                    pairs_per_particle=60, capacity_factor=1.25)
+    if name == "dam_break_64k_split_merge":
+        return scenes.dam_break(40, 40, 40, adaptive=True), dict(adaptive=False, basic_pbf=False, update_transfers=True, transfers=True,
+                                                                 pairs_per_particle=60, capacity_factor=1.25)
     if name == "dam_break_64k_default_mode":
         return scenes.dam_break(40, 40, 40, adaptive=True), dict(adaptive=False, basic_pbf=False, update_transfers=True, pairs_per_particle=60)
     if name == "dam_break_64k":     # bounded sample of the same workload for the CPU arm
@@ -132,12 +139,16 @@ def time_oracle(sample_name, steps, warmup, threads):
     s = orc.default_settings()
     s.mBaseKernelWidthOnBoundaryDistance = 0 if meta["adaptive"] else 1
     s.mSmallestTargetRadius = sc.smallest_target_radius
+    s.mMerge = s.mSplit = 1 if meta.get("transfers") else 0
     orc.set_threads(threads)
     st = orc.State(**{k: v.copy() for k, v in sc.arrays.items()})
     cap = sc.n * meta["pairs_per_particle"]
     kw = dict(dims=sc.dims, basic_pbf=meta.get("basic_pbf", not meta["adaptive"]), solver_iterations=sc.solver_iterations, min_pos=sc.min_pos,
               max_pos=sc.max_pos, res_log2=sc.res_log2, box_min4=sc.box_min, box_max4=sc.box_max, cap=cap, integrate=True,
               update_transfers=bool(meta.get("update_transfers")))
+    if meta.get("transfers"):
+        hidden_cap = int(sc.n * meta.get("capacity_factor", 1.0))
+        kw.update(transfers=orc.Transfers(hidden_cap), hidden_cap=hidden_cap, split_duration=0.0)
     for _ in range(warmup):
         orc.substep(st, s, **kw)
     t0 = time.perf_counter()
@@ -154,7 +165,8 @@ def run_reference(args, rank):
         return
     threads = os.cpu_count() or 1
     sample = {"dam_break_1M": "dam_break_64k", "uniform_64": "uniform_32",
-              "dam_break_1M_default_mode": "dam_break_64k_default_mode"}.get(args.workload, args.workload)
+              "dam_break_1M_default_mode": "dam_break_64k_default_mode",
+              "dam_break_1M_split_merge": "dam_break_64k_split_merge"}.get(args.workload, args.workload)
     steps = max(1, min(args.steps, 150))     # ~0.4 s per step of the 64k-particle sample on 16 threads
     warm = min(args.warmup, 3)
     value, sec_per_step, sc = time_oracle(sample, steps, warm, threads)
@@ -184,7 +196,8 @@ def run_gpu(args, rank, world, local_rank):
     sc, meta = make_scene(args.workload, 1 if args.replicas else world)
     slab = world > 1 and bool(meta.get("slab"))
     ctx = apbf_b200.Context(device=local_rank, dims=sc.dims)
-    ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if meta["adaptive"] else 1, mSmallestTargetRadius=sc.smallest_target_radius)
+    ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if meta["adaptive"] else 1, mSmallestTargetRadius=sc.smallest_target_radius,
+                     mMerge=1 if meta.get("transfers") else 0, mSplit=1 if meta.get("transfers") else 0)
     if slab:
         # this rank's brick of the scene: the particles whose cell key starts with the rank's bits
         from apbf_b200 import multi_gpu
@@ -197,10 +210,11 @@ def run_gpu(args, rank, world, local_rank):
         ghost_cap = 400_000
         capacity = int(n * 1.25) + ghost_cap
     else:
-        arrays, n, n_total, capacity = sc.arrays, sc.n, sc.n * world, sc.n
+        arrays, n, n_total, capacity = sc.arrays, sc.n, sc.n * world, int(sc.n * meta.get("capacity_factor", 1.0))
     cap = capacity * meta["pairs_per_particle"]
     sim = apbf_b200.Sim(ctx, sc, capacity=capacity, neighbor_capacity=cap, integrate=True, basic_pbf=meta.get("basic_pbf", not meta["adaptive"]),
-                        update_transfers=bool(meta.get("update_transfers")), use_binary_search=(args.search == "binary"))
+                        update_transfers=bool(meta.get("update_transfers")), use_binary_search=(args.search == "binary"),
+                        transfers=bool(meta.get("transfers")))
 
     # host copies of the lists in pinned memory (the e2e leg streams them in every step)
     host = {}
@@ -350,7 +364,8 @@ def run_gpu(args, rank, world, local_rank):
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        sample = {"dam_break_1M": "dam_break_64k", "uniform_64": "uniform_32", "dam_break_1M_default_mode": "dam_break_64k_default_mode"}.get(args.workload, args.workload)
+        sample = {"dam_break_1M": "dam_break_64k", "uniform_64": "uniform_32", "dam_break_1M_default_mode": "dam_break_64k_default_mode",
+              "dam_break_1M_split_merge": "dam_break_64k_split_merge"}.get(args.workload, args.workload)
         threads = os.cpu_count() or 1
         cpu_steps = 30                           # bounded sample: 10-30 s of CPU work
         v, sec, ssc = time_oracle(sample, cpu_steps, 1, threads)

@@ -282,8 +282,10 @@ int apbf_update_transfers_split_merge_apply(apbf_ctx* ctx, apbf_fluid* fluid, co
  * including deleteTransferList.delete_these() and deleteParticleList.delete_these() (indexed_list.h:126-138): finished splits
  * leave the transfer list, the sources of finished merges leave the hidden particle list, and every list that shares it follows.
  * Like a search, the call writes the edited lists of `fluid` AND `transfers` into their reorder_out buffers (surviving entries
- * keep their order); afterwards the caller uses reorder_out as the lists' buffers. */
-int apbf_particle_transfer_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_transfers* transfers, float dt);
+ * keep their order); afterwards the caller uses reorder_out as the lists' buffers.  out_hidden_edit (optional, device,
+ * [hidden_capacity]): new hidden slot -> old hidden slot for the first *hidden_length entries afterwards -- the edit list that
+ * other lists sharing the hidden particles follow (indexed_list::apply_hidden_edit). */
+int apbf_particle_transfer_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_transfers* transfers, float dt, uint32_t* out_hidden_edit);
 /* The searches permute the hidden particle list; the transfers' source / target lists share it and follow through
  * indexed_list::apply_hidden_edit (source/indexed_list.h:289-308).  sorted_index[new slot] = old slot (apbf_search_debug). */
 int apbf_transfers_follow_reorder(apbf_ctx* ctx, apbf_transfers* transfers, const uint32_t* sorted_index, const uint32_t* hidden_length,

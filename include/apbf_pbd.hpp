@@ -175,7 +175,7 @@ namespace pbd
 		}
 		gpu_list& set_length(const pbd::buffer& aLength)
 		{
-			if (write().mData) algorithms::copy_bytes(aLength, mData->mLength, 4);
+			if (write().mData && mData->mLength.ptr != aLength.ptr) algorithms::copy_bytes(aLength, mData->mLength, 4);
 			return *this;
 		}
 		gpu_list& request_length(size_t aLength) { mRequestedLength = aLength; return *this; }
@@ -467,6 +467,14 @@ namespace pbd
 		/// the other indexed_lists sharing the hidden data (they need the generic re-map when the hidden list is permuted)
 		std::vector<indexed_list*> sharers() { std::vector<indexed_list*> v; for (auto* o : mHiddenData->mOwners) if (o != this) v.push_back(o); return v; }
 		void apply_hidden_edit_public(gpu_list<4>& aEditList) { apply_hidden_edit(aEditList); }
+		/// a list of ALL hidden entries (the scene's mParticles, pool.cpp:7) after copies were appended to the hidden list: 0 .. length-1
+		void follow_hidden_growth()
+		{
+			mIndexList.write();
+			mIndexList.set_length(mHiddenData->mData.length());
+			shader_provider::write_sequence(mIndexList.buffer(), mIndexList.length(), 0u, 1u);
+			mSorted = true;
+		}
 
 	private:
 		class hidden_data : public list_interface<gpu_list<4>>
@@ -513,11 +521,15 @@ namespace pbd
 	enum class fluid_enum { particle, target_radius, kernel_width, boundariness, boundary_distance };
 	using fluid = uninterleaved_list<fluid_enum, particles, gpu_list<4>, gpu_list<4>, gpu_list<4>, gpu_list<4>>;
 	using neighbors = gpu_list<8>;
+	enum class hidden_transfers_enum { source, target, time_left };
+	using hidden_transfers = uninterleaved_list<hidden_transfers_enum, particles, particles, gpu_list<4>>;
+	using transfers = indexed_list<hidden_transfers>;
 
 	/// runtime settings (source/settings.h static globals -> the context's apbf_settings + DIMENSIONS)
 	class settings
 	{
 	public:
+		static inline float splitDuration = 0.0f; // settings.cpp:23 (host-side: update_transfers.cpp:63)
 		static void update_apbf_settings_buffer(const apbf_settings& aSettings, int aDimensions)
 		{
 			shader_provider::check(apbf_ctx_set_settings(shader_provider::context(), &aSettings));
@@ -716,11 +728,22 @@ namespace pbd
 		neighbors* mNeighbors = nullptr;
 	};
 
-	/// The transfers list of the reference (list_definitions.h: hidden_transfers source / target / time_left) only matters
-	/// with settings::merge or settings::split on, which is outside this library's scope; the pointer is kept for the signature.
-	struct transfers;
+	namespace detail
+	{
+		/// the reference's transfer lists (list_definitions.h:16-18) as the C-ABI's view; source and target are index lists into the
+		/// hidden particle data (pool.cpp:18-19)
+		inline void check_transfers(transfers& t)
+		{
+			using ht = hidden_transfers_enum;
+			auto& h = t.hidden_list();
+			if (h.get<ht::source>().index_list().requested_length() == 0 || h.get<ht::target>().index_list().requested_length() == 0 || h.get<ht::time_left>().requested_length() == 0)
+				throw std::runtime_error("transfers: the hidden list has no requested length (construct with transfers(MAX_TRANSFERS))");
+		}
+	}
 
-	/// pbd::update_transfers (source/update_transfers.h, update_transfers.cpp:14-54) with merge and split off
+	/// pbd::update_transfers (source/update_transfers.h, update_transfers.cpp:14-70).  Without a transfers list (or with
+	/// mMerge and mSplit off) only the first part runs (boundary-distance flood fill, nearest neighbour, target radius); with one,
+	/// merges are entered and splits are started as the context's settings say (conflicts resolved in ascending id order).
 	class update_transfers
 	{
 	public:
@@ -732,11 +755,109 @@ namespace pbd
 			apbf_fluid f;
 			detail::fill_fluid_in_place(*mFluid, f);
 			apbf_neighbors nb = detail::neighbors_view(*mNeighbors);
-			shader_provider::check(apbf_update_transfers_apply(shader_provider::context(), &f, &nb, nullptr));
+			if (!mTransfers) {
+				shader_provider::check(apbf_update_transfers_apply(shader_provider::context(), &f, &nb, nullptr));
+				return;
+			}
+			using ht = hidden_transfers_enum;
+			using hp = hidden_particles_enum;
+			detail::check_transfers(*mTransfers);
+			auto& rows = mTransfers->hidden_list();
+			auto& source = rows.get<ht::source>();
+			auto& target = rows.get<ht::target>();
+			auto& timeLeft = rows.get<ht::time_left>();
+			apbf_transfers t;
+			std::memset(&t, 0, sizeof t);
+			t.source = detail::in_place(source.index_list());
+			t.target = detail::in_place(target.index_list());
+			t.time_left = detail::in_place(timeLeft);
+			t.length = source.length().as<uint32_t>();
+			t.capacity = std::min(source.index_list().capacity(), std::min(target.index_list().capacity(), timeLeft.capacity()));
+			shader_provider::check(apbf_update_transfers_split_merge_apply(shader_provider::context(), &f, &nb, &t, settings::splitDuration, nullptr));
+			// every member list carries its own length word: the new lengths reach the siblings like in update_transfers.cpp:54
+			auto& particleList = mFluid->get<fluid_enum::particle>();
+			auto& hidden = particleList.hidden_list();
+			hidden.set_length(hidden.get<hp::position>().length());
+			mFluid->set_length(particleList.length());
+			rows.set_length(source.length());
+			for (auto* other : particleList.sharers())   // the scene's own list of all particles gains the copies as well
+				if (other != &source && other != &target && other->owner() == nullptr && other->index_list().capacity() > 0) other->follow_hidden_growth();
 		}
 	private:
 		fluid* mFluid = nullptr;
 		neighbors* mNeighbors = nullptr;
+		transfers* mTransfers = nullptr;
+	};
+
+	/// pbd::particle_transfer (source/particle_transfer.h, particle_transfer.cpp:10-28): one time step of every transfer under way;
+	/// finished splits leave the transfer list, the sources of finished merges leave the particle lists (surviving entries keep
+	/// their order)
+	class particle_transfer
+	{
+	public:
+		particle_transfer& set_data(fluid* aFluid, transfers* aTransfers) { mFluid = aFluid; mTransfers = aTransfers; return *this; }
+		void apply(float aDeltaTime)
+		{
+			if (!mFluid || !mTransfers) throw std::runtime_error("particle_transfer: set_data() has not been called");
+			using ht = hidden_transfers_enum;
+			using hp = hidden_particles_enum;
+			auto& particleList = mFluid->get<fluid_enum::particle>();
+			auto& hidden = particleList.hidden_list();
+			if (hidden.empty() || particleList.empty()) return;
+			detail::check_transfers(*mTransfers);
+			auto& rows = mTransfers->hidden_list();
+			auto& source = rows.get<ht::source>();
+			auto& target = rows.get<ht::target>();
+			auto& timeLeft = rows.get<ht::time_left>();
+			source.index_list().write(); target.index_list().write(); timeLeft.write();
+			// other lists sharing the hidden particles follow through the generic path with the edit the call reports
+			std::vector<particles*> others;
+			for (auto* o : particleList.sharers()) if (o != &source && o != &target) others.push_back(o);
+			gpu_list<4> hiddenEdit;
+			uint32_t* editOut = nullptr;
+			if (!others.empty()) {
+				hiddenEdit.request_length(hidden.get<hp::position>().capacity());
+				hiddenEdit.set_length(0);
+				editOut = hiddenEdit.write().buffer().as<uint32_t>();
+			}
+			detail::reorder_scope scope;
+			apbf_fluid f;
+			std::memset(&f, 0, sizeof f);
+			apbf_particles& p = f.particle;
+			p.capacity = particleList.index_list().capacity();
+			p.hidden_capacity = hidden.get<hp::position>().capacity();
+			p.index_list = scope.rewrite(particleList.index_list());
+			p.position = scope.rewrite(hidden.get<hp::position>());
+			p.velocity = scope.rewrite(hidden.get<hp::velocity>());
+			p.inverse_mass = scope.rewrite(hidden.get<hp::inverse_mass>());
+			p.radius = scope.rewrite(hidden.get<hp::radius>());
+			p.pos_backup = scope.rewrite(hidden.get<hp::pos_backup>());
+			p.transferring = scope.rewrite(hidden.get<hp::transferring>());
+			f.target_radius = scope.rewrite(mFluid->get<fluid_enum::target_radius>());
+			f.kernel_width = scope.rewrite(mFluid->get<fluid_enum::kernel_width>());
+			f.boundariness = scope.rewrite(mFluid->get<fluid_enum::boundariness>());
+			f.boundary_distance = scope.rewrite(mFluid->get<fluid_enum::boundary_distance>());
+			// the new storages start with a copy of the old length words; the call reads them and leaves the new lengths there
+			p.length = particleList.length().as<uint32_t>();
+			p.hidden_length = hidden.get<hp::position>().length().as<uint32_t>();
+			apbf_transfers t;
+			std::memset(&t, 0, sizeof t);
+			t.source = scope.rewrite(source.index_list());
+			t.target = scope.rewrite(target.index_list());
+			t.time_left = scope.rewrite(timeLeft);
+			t.length = source.length().as<uint32_t>();
+			t.capacity = std::min(source.index_list().capacity(), std::min(target.index_list().capacity(), timeLeft.capacity()));
+			shader_provider::check(apbf_particle_transfer_apply(shader_provider::context(), &f, &t, aDeltaTime, editOut));
+			hidden.set_length(hidden.get<hp::position>().length());
+			mFluid->set_length(particleList.length());
+			rows.set_length(source.length());
+			if (!others.empty()) {
+				hiddenEdit.set_length(hidden.get<hp::position>().length());
+				for (auto* o : others) o->apply_hidden_edit_public(hiddenEdit);
+			}
+		}
+	private:
+		fluid* mFluid = nullptr;
 		transfers* mTransfers = nullptr;
 	};
 

@@ -385,6 +385,115 @@ static void operator_tests()
 	std::filesystem::remove_all(folder);
 }
 
+// update_transfers with a transfers list + particle_transfer (update_transfers.cpp:14-70, particle_transfer.cpp:10-28):
+// a lattice whose target radius asks every second particle to split and lets close pairs merge; checks the list bookkeeping
+// (lengths of all member lists, flags == members of the rows, the scene's own list follows) and that mass is conserved.
+static void transfer_tests()
+{
+	const int side = 8;
+	const float r = 1.0f, R = 262144.0f;
+	const size_t n = size_t(side) * side * side, cap = 2 * n;
+	std::mt19937 rng(11);
+	std::uniform_real_distribution<float> jit(-0.45f, 0.45f);
+	std::vector<int32_t> pos(n * 4, 0);
+	std::vector<float> vel(n * 4, 0.f), invMass(n), radius(n), kw(n, 4.0f * r), one(n, 1.0f), target(n);
+	std::vector<uint32_t> zeros(n, 0u), bdist(n, uint32_t(r * R));
+	for (size_t i = 0; i < n; i++) {
+		const int gx = int(i / (side * side)), gy = int(i / side) % side, gz = int(i % side);
+		const float p[3] = { -side + 1.0f + 2.0f * gx + jit(rng), -side + 1.0f + 2.0f * gy + jit(rng), -side + 1.0f + 2.0f * gz + jit(rng) };
+		for (int d = 0; d < 3; d++) pos[4 * i + d] = int32_t(p[d] * R);
+		radius[i] = (i % 2) ? 2.0f : 1.6f;                 // odd: far above the target radius -> split; even: may merge with a close neighbour
+		target[i] = (i % 2) ? 1.0f : 2.6f;
+		invMass[i] = 1.0f / (8.0f * radius[i] * radius[i] * radius[i]);
+	}
+	particles prt(cap);
+	prt.request_length(cap);
+	fluid fl;
+	fl.request_length(cap);
+	neighbors nb;
+	nb.request_length(n * 80);
+	transfers tr(cap);
+	using hp = hidden_particles_enum;
+	using ht = hidden_transfers_enum;
+	tr.hidden_list().get<ht::source>().share_hidden_data_from(prt);   // pool.cpp:18-19
+	tr.hidden_list().get<ht::target>().share_hidden_data_from(prt);
+	tr.hidden_list().get<ht::source>().request_length(cap);
+	tr.hidden_list().get<ht::target>().request_length(cap);
+	tr.hidden_list().set_length(0);
+	auto& hidden = prt.hidden_list();
+	fl.get<fluid_enum::particle>() = prt.increase_length(n);
+	fl.set_length(fl.get<fluid_enum::particle>().length());
+	algorithms::copy_bytes(pos.data(), hidden.get<hp::position>().write().buffer(), n * 16);
+	algorithms::copy_bytes(vel.data(), hidden.get<hp::velocity>().write().buffer(), n * 16);
+	algorithms::copy_bytes(invMass.data(), hidden.get<hp::inverse_mass>().write().buffer(), n * 4);
+	algorithms::copy_bytes(radius.data(), hidden.get<hp::radius>().write().buffer(), n * 4);
+	algorithms::copy_bytes(pos.data(), hidden.get<hp::pos_backup>().write().buffer(), n * 16);
+	algorithms::copy_bytes(zeros.data(), hidden.get<hp::transferring>().write().buffer(), n * 4);
+	algorithms::copy_bytes(kw.data(), fl.get<fluid_enum::kernel_width>().write().buffer(), n * 4);
+	algorithms::copy_bytes(target.data(), fl.get<fluid_enum::target_radius>().write().buffer(), n * 4);
+	algorithms::copy_bytes(one.data(), fl.get<fluid_enum::boundariness>().write().buffer(), n * 4);
+	algorithms::copy_bytes(bdist.data(), fl.get<fluid_enum::boundary_distance>().write().buffer(), n * 4);
+
+	apbf_settings s;
+	apbf_default_settings(&s);
+	s.mMerge = 1; s.mSplit = 1; s.mUpdateTargetRadius = 0; s.mMergeDuration = 2.0f / 60.0f;
+	settings::update_apbf_settings_buffer(s, 3);
+	settings::splitDuration = 0.0f;
+	const float lim = side + 4.0f, dt = 1.0f / 60.0f;
+	neighborhood_green search;
+	search.set_data(&fl.get<fluid_enum::particle>(), &fl.get<fluid_enum::kernel_width>(), &nb).set_range_scale(1.0f).set_position_range(vec3(-lim), vec3(lim), 3u);
+	update_transfers update;
+	update.set_data(&fl, &nb, &tr);
+	particle_transfer transfer;
+	transfer.set_data(&fl, &tr);
+
+	auto total_mass = [&]() { double m = 0; for (float im : hidden.get<hp::inverse_mass>().read<float>()) if (im < 1.0e6f) m += 1.0 / double(im); return m; };
+	auto consistent = [&](const char* aWhen) {
+		auto src = tr.hidden_list().get<ht::source>().index_read(), tgt = tr.hidden_list().get<ht::target>().index_read();
+		auto ttl = tr.hidden_list().get<ht::time_left>().read<float>();
+		auto flags = hidden.get<hp::transferring>().read<uint32_t>();
+		auto idx = fl.get<fluid_enum::particle>().index_read();
+		auto all = prt.index_read();
+		auto kwNow = fl.get<fluid_enum::kernel_width>().read<float>();
+		auto velNow = hidden.get<hp::velocity>().read<float>();
+		bool ok = src.size() == tgt.size() && src.size() == ttl.size() && idx.size() == flags.size() && all.size() == flags.size() && kwNow.size() == idx.size() && velNow.size() == 4 * flags.size();
+		std::set<uint32_t> members;
+		for (auto v : src) ok = ok && v < flags.size() && members.insert(v).second;
+		for (auto v : tgt) ok = ok && v < flags.size() && members.insert(v).second;
+		size_t flagged = 0;
+		for (size_t i = 0; i < flags.size(); i++) { flagged += flags[i]; ok = ok && ((flags[i] == 1u) == (members.count(uint32_t(i)) == 1)); }
+		for (uint32_t i = 0; i < idx.size(); i++) ok = ok && idx[i] == i && all[i] == i;
+		if (!ok) { std::printf("FAILED: transfer lists inconsistent %s (%zu rows, %zu flagged, %zu / %zu / %zu particles)\n", aWhen, src.size(), flagged, flags.size(), idx.size(), all.size()); g_failures++; }
+		return std::make_pair(flags.size(), src.size());
+	};
+
+	shader_provider::start_recording();
+	search.apply();
+	shader_provider::end_recording();
+	const double mass0 = total_mass();
+	shader_provider::start_recording();
+	update.apply();
+	shader_provider::end_recording();
+	auto [n1, rows1] = consistent("after update_transfers");
+	if (n1 <= n || n1 > cap || rows1 < n1 - n) { std::printf("FAILED: update_transfers started no split (%zu particles, %zu rows)\n", n1, rows1); g_failures++; }
+	const bool merges = rows1 > n1 - n;
+	shader_provider::start_recording();
+	transfer.apply(dt);                                   // splits finish at once (splitDuration 0), merges are half way
+	shader_provider::end_recording();
+	auto [n2, rows2] = consistent("after the first particle_transfer");
+	if (n2 != n1 || rows2 != rows1 - (n1 - n)) { std::printf("FAILED: finished splits did not leave the transfer list (%zu rows of %zu)\n", rows2, rows1); g_failures++; }
+	if (std::fabs(total_mass() / mass0 - 1.0) > 1e-5) { std::printf("FAILED: mass not conserved by the splits (%g)\n", total_mass() / mass0); g_failures++; }
+	shader_provider::start_recording();
+	search.apply();                                       // the rows follow the search's permutation of the hidden list
+	transfer.apply(dt);                                   // merges finish: their sources leave every list
+	shader_provider::end_recording();
+	auto [n3, rows3] = consistent("after the second particle_transfer");
+	if (rows3 != 0 || n3 != n2 - rows2) { std::printf("FAILED: finished merges did not delete their sources (%zu particles, %zu rows; %zu merges)\n", n3, rows3, rows2); g_failures++; }
+	if (std::fabs(total_mass() / mass0 - 1.0) > 1e-5) { std::printf("FAILED: mass not conserved by the merges (%g)\n", total_mass() / mass0); g_failures++; }
+	if (!merges) std::printf("note: the transfer test scene produced no merge\n");
+	validate_length(fl.length(), n3, "fluid length after the merges");
+}
+
 int main()
 {
 	apbf_ctx* ctx = nullptr;
@@ -397,6 +506,7 @@ int main()
 		indexed_list_tests();
 		algorithm_tests();
 		operator_tests();
+		transfer_tests();
 	} catch (const std::exception& e) {
 		std::printf("EXCEPTION: %s\n", e.what());
 		g_failures++;
