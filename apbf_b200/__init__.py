@@ -88,6 +88,10 @@ class Context:
         """testing aid: cap the hit stream of the pair emit (0 = automatic); an exhausted stream falls back to the two-pass fill"""
         _check(self, self.lib.apbf_ctx_set_stream_blocks(self.handle, int(max_blocks)))
 
+    def set_match_grid_min(self, min_candidates):
+        """tuning / testing aid: merge / split matching runs its first rounds grid-wide from this many candidates on"""
+        _check(self, self.lib.apbf_ctx_set_match_grid_min(self.handle, int(min_candidates)))
+
     def set_search_stats(self, enable=True):
         """fused search + spread: also count the pairs of the (never materialised) unpruned list"""
         _check(self, self.lib.apbf_ctx_set_search_stats(self.handle, int(enable)))

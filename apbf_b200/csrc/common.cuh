@@ -95,6 +95,7 @@ struct apbf_ctx {
 	// 4-byte NB list; the green search then skips the 8-byte stores (the list length is still set)
 	bool            skip_public_pairs = false;
 	uint32_t        stream_blocks_cap = 0; // testing aid: upper bound on the hit stream's blocks (0 = automatic)
+	uint32_t        match_grid_min = 16384; // merge / split matching: grid-wide rounds from this many candidates on
 	bool            search_stats = false; // fused search + spread: count the pairs of the unpruned list as well
 
 	void* scratch_get(int slot, size_t bytes);

@@ -167,6 +167,12 @@ int apbf_ctx_set_stream_blocks(apbf_ctx* ctx, uint32_t max_blocks)
 	ctx->stream_blocks_cap = max_blocks;
 	return APBF_OK;
 }
+int apbf_ctx_set_match_grid_min(apbf_ctx* ctx, uint32_t min_candidates)
+{
+	if (!ctx) return APBF_ERR_INVALID;
+	ctx->match_grid_min = min_candidates;
+	return APBF_OK;
+}
 int apbf_ctx_set_search_stats(apbf_ctx* ctx, int enable)
 {
 	if (!ctx) return APBF_ERR_INVALID;

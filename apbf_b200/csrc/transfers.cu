@@ -10,7 +10,8 @@
 //   compaction   candidates in id order (scan)
 //   matching     "lowest id wins": a candidate is accepted once it is the lowest live candidate on each of its particles;
 //                candidates on a taken particle die; repeat until nobody is live.  This is the greedy matching in id order.
-//                One CTA (rounds are separated by __syncthreads()); the work is proportional to the number of candidates.
+//                With many candidates the first rounds run grid-wide (three launches per round), the rest in one CTA
+//                (rounds separated by __syncthreads()); the work is proportional to the number of candidates.
 //   ranks        accepted merges / splits get their row in id order; a full transfer list rejects the later merges, which
 //                frees their particles for later splits (find_split_and_merge_3.comp:104-109)
 //   emit         rows, duplicates (appended to the hidden list, the index list and the per-id lists) in parallel
@@ -129,14 +130,48 @@ struct match_args {
 	int             split_on;     // settings::split (update_transfers.cpp:60)
 };
 
+__global__ void __launch_bounds__(256) k_tm_init(uint32_t* __restrict__ state, const uint32_t* __restrict__ words)
+{
+	const uint32_t M = words[TW_M];
+	for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) state[j] = 0u;
+}
+
+// One round of the matching spread over the whole grid (the three phases are three launches: the kernel boundary is the
+// barrier).  Only worth its launches when there are many candidates -- e.g. the substep in which the flood fill lifts the
+// target radius of the whole interior at once; below `grid_min` candidates the kernels return at once and k_tm_match does all
+// the rounds in one CTA.  After GRID_ROUNDS rounds the live set has shrunk geometrically and k_tm_match finishes the rest.
+template <int PHASE>
+__global__ void __launch_bounds__(256) k_tm_round(match_args A, uint32_t grid_min)
+{
+	const uint32_t M = A.words[TW_M];
+	if (M < grid_min) return;
+	for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
+		if (A.state[j] != 0u) continue;
+		const uint32_t cs = A.c_src[j], src = cs & IDX_MASK, tgt = A.c_tgt[j];
+		if (PHASE == 0) {
+			if (A.transferring[src] == 1u || ((cs & KIND_MERGE) && A.transferring[tgt] == 1u)) { A.state[j] = 2u; continue; }
+			A.owner[src] = NONE;
+			if (cs & KIND_MERGE) A.owner[tgt] = NONE;
+		} else if (PHASE == 1) {
+			atomicMin(&A.owner[src], j);
+			if (cs & KIND_MERGE) atomicMin(&A.owner[tgt], j);
+		} else {
+			if (A.owner[src] == j && (!(cs & KIND_MERGE) || A.owner[tgt] == j)) {
+				A.state[j] = 1u;
+				A.transferring[src] = 1u;
+				if (cs & KIND_MERGE) A.transferring[tgt] = 1u;
+			}
+		}
+	}
+}
+
 __global__ void __launch_bounds__(MATCH_THREADS) k_tm_match(match_args A)
 {
 	__shared__ uint32_t s_warp[MATCH_THREADS / 32];
 	__shared__ uint32_t s_live, s_jstar;
 	const uint32_t M = A.words[TW_M];
 	const uint32_t tid = threadIdx.x;
-	for (uint32_t j = tid; j < M; j += MATCH_THREADS) A.state[j] = 0u;
-	__syncthreads();
+	// (the states were cleared by k_tm_init; grid-wide rounds may have decided part of the candidates already)
 	// ---- greedy matching in id order: rounds of "lowest live candidate on each of its particles wins" ----
 	for (;;) {
 		if (tid == 0) s_live = 0u;
@@ -447,6 +482,18 @@ int apbf_update_transfers_split_merge_apply(apbf_ctx* ctx, apbf_fluid* fluid, co
 	M.c_src = c_src; M.c_tgt = c_tgt; M.state = state; M.rank = rank; M.owner = owner;
 	M.transferring = (uint32_t*)p.transferring.data; M.words = words; M.t_len = transfers->length; M.t_cap = transfers->capacity;
 	M.hidden_len = p.hidden_length; M.hidden_cap = nh_cap; M.split_on = s.mSplit;
+	k_tm_init<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>(state, words);
+	APBF_LAUNCHED(ctx);
+	constexpr int GRID_ROUNDS = 8;
+	const unsigned rgrid = apbf_grid(ctx, n_cap, 256, 4);
+	for (int r = 0; r < GRID_ROUNDS; r++) {
+		k_tm_round<0><<<rgrid, 256, 0, st>>>(M, ctx->match_grid_min);
+		APBF_LAUNCHED(ctx);
+		k_tm_round<1><<<rgrid, 256, 0, st>>>(M, ctx->match_grid_min);
+		APBF_LAUNCHED(ctx);
+		k_tm_round<2><<<rgrid, 256, 0, st>>>(M, ctx->match_grid_min);
+		APBF_LAUNCHED(ctx);
+	}
 	k_tm_match<<<1, MATCH_THREADS, 0, st>>>(M);
 	APBF_LAUNCHED(ctx);
 

@@ -89,6 +89,9 @@ int  apbf_ctx_set_search_stats(apbf_ctx* ctx, int enable);
 /* Testing aid: cap the number of 128-entry blocks of the pair emit's hit stream (0 = sized from the list capacities).  A
  * stream that runs out of blocks makes the search fall back to its two-pass fill; results do not change. */
 int  apbf_ctx_set_stream_blocks(apbf_ctx* ctx, uint32_t max_blocks);
+/* Tuning / testing aid: the merge / split matching of apbf_update_transfers_split_merge_apply runs its first rounds grid-wide
+ * when there are at least this many candidates (default 16384; 0 = always, 0xFFFFFFFF = never).  Results do not change. */
+int  apbf_ctx_set_match_grid_min(apbf_ctx* ctx, uint32_t min_candidates);
 /* Per-pass device timing with CUDA events on the context stream (replaces measurements::record_timing_interval_*,
  * source/measurements.cpp:27-62).  apbf_ctx_profile(ctx, 1) clears and starts, (ctx, 0) stops; apbf_ctx_profile_read
  * returns the accumulated milliseconds and span count of category 0 .. n-1 (APBF_ERR_INVALID past the last one) and

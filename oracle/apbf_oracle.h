@@ -15,8 +15,11 @@
  *   uint_to_float_but_gradual.comp, box_collision.comp, copy_scattered_read.comp,
  *   radix_sort_*.comp / prefix_sum_*.comp (semantics: stable, inclusive),
  *   infer_velocity.comp / apply_acceleration.comp / apply_velocity.comp,
- *   find_split_and_merge_1/2/3.comp (merge and split off),
- *   uint_to_float_with_indexed_lower_bound.comp, source/update_transfers.cpp:14-54,
+ *   find_split_and_merge_1/2/3.comp, remove_impossible_splits.comp,
+ *   initialize_split_particles.comp, particle_transfer.comp,
+ *   uint_to_float_with_indexed_lower_bound.comp, source/update_transfers.cpp:14-70,
+ *   source/particle_transfer.cpp:10-28, indexed_list.h:126-152 (delete_these /
+ *   duplicate_these: stable order, copies at the end),
  *   source/algorithms.cpp, neighborhood_green.cpp, neighborhood_binary_search.cpp,
  *   incompressibility.cpp, spread_kernel_width.cpp, box_collision.cpp,
  *   velocity_handling.cpp, pool.cpp:67-106.
@@ -26,10 +29,14 @@
  *     vectors (source/test.cpp:91-105,186-197,269-282,284-305,343-364,402-425)
  *     and the Z-curve vectors of the dead sortByPositions test (test.cpp:623).
  *   - neighbour search, position hash/code, incompressibility, kernel width,
- *     box collision, update_transfers: PARITY UNPINNED -- the reference has no enabled test for
+ *     box collision, update_transfers, particle_transfer (merge / split): PARITY
+ *     UNPINNED by the reference -- it has no enabled test for
  *     them (test.cpp:533-583 return true) and its GLSL cannot be compiled or
  *     run in this image (no glslang, no Vulkan).  Cross-checked only by the
- *     brute-force search and hand-derived micro cases.
+ *     brute-force search and hand-derived micro cases (tests/test_oracle_kats.py,
+ *     tests/test_transfers.py).  Merge / split decisions are a race in the
+ *     reference (atomicExchange); the restatement runs the invocations in
+ *     ascending id order.
  *
  * Floating-point conventions fixed here (GLSL leaves them to the driver):
  *   IEEE binary32, round-to-nearest-even, no FMA contraction (build with

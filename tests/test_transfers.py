@@ -186,13 +186,17 @@ def _same_lists(L, st, T, TL):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("grid_min", [None, 0])
 @pytest.mark.parametrize("merge,split,t_cap,cap_factor,split_duration", [
     (1, 1, 0, 2.0, 0.0), (1, 0, 0, 2.0, 0.0), (0, 1, 0, 2.0, 0.5), (1, 1, 40, 2.0, 0.0), (1, 1, 0, 1.02, 0.25), (1, 1, 3, 1.0, 0.0)])
-def test_update_transfers_split_merge_matches_oracle(gpu, orc, merge, split, t_cap, cap_factor, split_duration):
+def test_update_transfers_split_merge_matches_oracle(gpu, orc, merge, split, t_cap, cap_factor, split_duration, grid_min):
     """the merge / split decisions in ascending id order, rows, copies and the lengths: bit exact, also with a transfer list that
-    fills up (later merges release their particles, later splits take them) and a hidden list without room for every copy"""
+    fills up (later merges release their particles, later splits take them) and a hidden list without room for every copy;
+    with the matching rounds in one CTA (few candidates) and grid-wide (grid_min 0)"""
     s = _settings(orc, merge, split, merge_duration=2.0 / 60.0)
     sc, st, epairs, ctx, L, pcap = _searched(gpu, orc, s, cap_factor)
+    if grid_min is not None:
+        ctx.set_match_grid_min(grid_min)       # the first matching rounds grid-wide, whatever the number of candidates
     t_cap = t_cap or pcap
     pre = ([sc.n + 5, sc.n + 6], [sc.n + 7, sc.n + 8], [0.25, -0.5])                  # rows already there stay where they are
     T, TL = orc.Transfers(t_cap, *pre), gpu.TransferList(ctx, t_cap, *pre)
@@ -203,6 +207,33 @@ def test_update_transfers_split_merge_matches_oracle(gpu, orc, merge, split, t_c
     if t_cap == pcap and cap_factor == 2.0:
         src, tgt, ttl = T.rows()
         assert (not merge or np.count_nonzero(ttl[2:] > 0) > 20) and (not split or st.n > sc.n + 20)
+
+
+@pytest.mark.gpu
+def test_every_particle_a_candidate(gpu, orc):
+    """the substep in which the whole interior becomes a candidate at once: a jitter-free lattice (every nearest-neighbour
+    distance ties, the last pair of the list wins: long chains of conflicts in ascending id order), 46 656 merge candidates --
+    grid-wide rounds first, the rest in one CTA; rows and flags bit exact"""
+    sc = scenes.uniform_block(36, jitter=0.0, shuffle=True)
+    s = _settings(orc, 1, 1)
+    cap = sc.n * 40
+    st = oracle_state(orc, sc)
+    epairs = orc.green_apply(st, s, 3, 1.0, sc.min_pos, sc.max_pos, sc.res_log2, cap)
+    ctx = gpu.Context()
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    L = gpu.ParticleLists(ctx, sc.arrays, capacity=2 * sc.n, neighbor_capacity=cap)
+    gpu.neighborhood_green(ctx).set_data(L).set_range_scale(1.0).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply()
+    assert np.array_equal(L.read_pairs(), epairs)
+    radius = np.full(sc.n, 2.5, np.float32)                                            # neighbours at 2.0 are "close", 2 * 2.5^3 <= 3.2^3
+    target = np.full(sc.n, 3.2, np.float32)
+    for name, v in (("radius", radius), ("target_radius", target)):
+        getattr(st, name)[:] = v
+        L.write(name, v)
+    T, TL = orc.Transfers(2 * sc.n), gpu.TransferList(ctx, 2 * sc.n)
+    orc.update_transfers_full(st, s, 3, epairs, T, hidden_cap=2 * sc.n)
+    gpu.update_transfers(ctx).set_data(L, TL).apply()
+    _same_lists(L, st, T, TL)
+    assert T.n > sc.n // 4 and int(st.transferring.sum()) == 2 * T.n
 
 
 @pytest.mark.gpu
