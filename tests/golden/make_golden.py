@@ -77,7 +77,49 @@ def scene_case(name, sc, scale, adaptive, hk=1, gk=1, method=2):
     return {k: sha(v) for k, v in out.items()}
 
 
+def transfers_case(name="transfers14"):
+    """split / merge proper (update_transfers.cpp:14-70, particle_transfer.cpp:10-28): a searched waterdrop(14) with radii, target
+    radii and transferring flags drawn so that merges, splits and conflicts all occur; frozen after update_transfers and after
+    each of two particle_transfer steps (merges take two steps, splits finish at once)."""
+    sc = scenes.waterdrop(14, jitter=0.1)
+    s = orc.default_settings()
+    s.mMerge, s.mSplit, s.mUpdateTargetRadius, s.mMergeDuration = 1, 1, 0, 2.0 / 60.0
+    orc.set_threads(1)
+    st = orc.State(**{k: v.copy() for k, v in sc.arrays.items()})
+    pairs = orc.green_apply(st, s, 3, 1.0, sc.min_pos, sc.max_pos, sc.res_log2, sc.n * 300)
+    rng = np.random.default_rng(11)
+    radius = rng.uniform(0.8, 3.2, sc.n).astype(np.float32)
+    radius[rng.random(sc.n) < 0.3] = np.float32(1.5)
+    inputs = dict(radius=radius, inverse_mass=(1.0 / (2.0 * radius) ** 3).astype(np.float32),
+                  target_radius=rng.uniform(0.7, 4.5, sc.n).astype(np.float32), transferring=(rng.random(sc.n) < 0.1).astype(np.uint32))
+    for k, v in inputs.items():
+        getattr(st, k)[:] = v
+    out = {"in_" + k: v for k, v in inputs.items()}
+    cap = 2 * sc.n
+    T = orc.Transfers(cap)
+
+    def freeze(tag):
+        for k, _, _ in orc.State.FIELDS:
+            out[f"{tag}_{k}"] = getattr(st, k).copy()
+        out[f"{tag}_rows_source"], out[f"{tag}_rows_target"], out[f"{tag}_rows_time_left"] = T.rows()
+
+    out["nearest"] = orc.update_transfers_full(st, s, 3, pairs, T, hidden_cap=cap, split_duration=0.0)
+    freeze("u")
+    for step in (1, 2):
+        orc.particle_transfer_apply(st, T, 3, float(np.float32(1.0 / 60.0)))
+        freeze(f"p{step}")
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    return dict(n=sc.n, capacity=cap, sha256={k: sha(v) for k, v in out.items()})
+
+
 def main():
+    if sys.argv[1:] == ["transfers"]:           # only the split / merge fixture (the others stay byte for byte what they are)
+        index = json.load(open(os.path.join(HERE, "index.json")))
+        index["transfers14"] = transfers_case()
+        with open(os.path.join(HERE, "index.json"), "w") as f:
+            json.dump(index, f, indent=1)
+        print("wrote transfers14.npz")
+        return
     index = {"kats": "kats.json", "scenes": {}}
     with open(os.path.join(HERE, "kats.json"), "w") as f:
         json.dump(KATS, f, indent=1)
@@ -89,6 +131,7 @@ def main():
     }
     for name, (sc, scale, adaptive, hk, gk, method) in cases.items():
         index["scenes"][name] = dict(scale=scale, adaptive=adaptive, kernels=[hk, gk], method=method, n=sc.n, sha256=scene_case(name, sc, scale, adaptive, hk, gk, method))
+    index["transfers14"] = transfers_case()
     with open(os.path.join(HERE, "index.json"), "w") as f:
         json.dump(index, f, indent=1)
     print("wrote", ", ".join(sorted(os.listdir(HERE))))

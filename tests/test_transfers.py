@@ -142,6 +142,56 @@ def test_transfers_follow_the_search_and_mass_is_conserved(orc):
     assert seen_rows > 0 and n_max > sc.n and n_min <= n_max
 
 
+# ---- frozen oracle outputs (tests/golden/transfers14.npz, generator tests/golden/make_golden.py) ------------------------------
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "transfers14.npz"))
+
+
+def _golden_same(g, tag, fields, rows):
+    for k, v in fields.items():
+        assert np.array_equal(np.asarray(v).view(np.uint32), g[f"{tag}_{k}"].view(np.uint32)), (tag, k)
+    for k, v in zip(("source", "target", "time_left"), rows):
+        assert np.array_equal(np.asarray(v).view(np.uint32), g[f"{tag}_rows_{k}"].view(np.uint32)), (tag, "rows", k)
+
+
+def test_oracle_reproduces_the_frozen_transfers(orc):
+    g = _golden()
+    sc = scenes.waterdrop(14, jitter=0.1)
+    s = _settings(orc, 1, 1)
+    st = oracle_state(orc, sc)
+    pairs = orc.green_apply(st, s, 3, 1.0, sc.min_pos, sc.max_pos, sc.res_log2, sc.n * 300)
+    for k in ("radius", "inverse_mass", "target_radius", "transferring"):
+        getattr(st, k)[:] = g["in_" + k]
+    T = orc.Transfers(2 * sc.n)
+    assert np.array_equal(orc.update_transfers_full(st, s, 3, pairs, T, hidden_cap=2 * sc.n), g["nearest"])
+    _golden_same(g, "u", {k: getattr(st, k) for k, _, _ in orc.State.FIELDS}, T.rows())
+    for tag in ("p1", "p2"):
+        orc.particle_transfer_apply(st, T, 3, float(DT))
+        _golden_same(g, tag, {k: getattr(st, k) for k, _, _ in orc.State.FIELDS}, T.rows())
+    assert len(g["u_rows_source"]) > 100 and len(g["p2_rows_source"]) == 0 and len(g["p2_radius"]) < len(g["u_radius"])
+
+
+@pytest.mark.gpu
+def test_cuda_path_reproduces_the_frozen_transfers(gpu, orc):
+    g = _golden()
+    sc = scenes.waterdrop(14, jitter=0.1)
+    s = _settings(orc, 1, 1)
+    ctx = gpu.Context()
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    L = gpu.ParticleLists(ctx, sc.arrays, capacity=2 * sc.n, neighbor_capacity=sc.n * 300)
+    gpu.neighborhood_green(ctx).set_data(L).set_range_scale(1.0).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply()
+    for k in ("radius", "inverse_mass", "target_radius", "transferring"):
+        L.write(k, g["in_" + k])
+    TL = gpu.TransferList(ctx, 2 * sc.n)
+    assert np.array_equal(gpu.update_transfers(ctx).set_data(L, TL).apply(debug=True), g["nearest"])
+    _golden_same(g, "u", L.read_all(), TL.rows())
+    op = gpu.particle_transfer(ctx).set_data(L, TL)
+    for tag in ("p1", "p2"):
+        op.apply(float(DT))
+        _golden_same(g, tag, L.read_all(), TL.rows())
+
+
 # ---- GPU: the CUDA path against the oracle ------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def gpu():
