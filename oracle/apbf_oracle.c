@@ -921,6 +921,11 @@ void orc_update_transfers_apply(orc_state* st, const orc_settings* s, const uint
 /* pow(2.0, 1.0 / DIMENSIONS) * 0.99 (find_split_and_merge_3.comp:88) is folded by    */
 /* the compiler in double precision and rounded to float once.                        */
 /* ---------------------------------------------------------------------------------- */
+/* pow() of the merge / split passes: evaluated in double and rounded to float once (what the CUDA path's pow_rn does).
+ * GLSL leaves pow to the driver; glibc's powf is within 0.52 ulp but not always correctly rounded, so "powf on both sides"
+ * is not a reproducible convention for x^2, x^(1/2) -- this one is (double rounding is harmless at 53 -> 24 bits here). */
+static inline float pow_rn(float x, float y) { return (float)pow((double)x, (double)y); }
+
 static void find_split_and_merge_3_decide(orc_state* st, const orc_settings* s, int D, const uint32_t* nearest,
                                           orc_transfers* t, uint32_t* split_ids, uint32_t* n_split, uint32_t max_split)
 { /* find_split_and_merge_3.comp:86-121, invocations in ascending id order */
@@ -942,7 +947,7 @@ static void find_split_and_merge_3_decide(orc_state* st, const orc_settings* s, 
 			float nnDist = length3(diff) / R_POS;
 			float nnRadius = st->radius[nnIdx];
 			nnLarger = nnRadius > radius || (nnRadius == radius && nnIdx > idx);
-			merge = nnDist < radius && powf(radius, (float)D) + powf(nnRadius, (float)D) <= powf(targetRadius, (float)D);
+			merge = nnDist < radius && pow_rn(radius, (float)D) + pow_rn(nnRadius, (float)D) <= pow_rn(targetRadius, (float)D);
 		}
 		if (!merge && !split) continue;
 		uint32_t sourceIdx = (merge && nnLarger) ? nnIdx : idx;
@@ -1035,14 +1040,14 @@ void orc_particle_transfer_apply(orc_state* st, orc_transfers* t, int D, float d
 		uint32_t idS = t->source[id], idT = t->target[id];
 		float radiusS = st->radius[idS], radiusT = st->radius[idT];
 		float invMassS = st->inverse_mass[idS], invMassT = st->inverse_mass[idT];
-		float volS = powf(radiusS, (float)D), volT = powf(radiusT, (float)D);
+		float volS = pow_rn(radiusS, (float)D), volT = pow_rn(radiusT, (float)D);
 		float factorS = merge ? fminf_(1.0f, dt / ttl) : dt * (volS - volT) / (2.0f * ttl * volS);
 		float transfVol = factorS * volS;
 		float normFactor = 1.0f / (invMassS + factorS * invMassT);
 		st->inverse_mass[idS] = invMassS / (1.0f - factorS);
 		st->inverse_mass[idT] = invMassS * invMassT * normFactor;
-		st->radius[idS] = powf(volS - transfVol, invD);
-		st->radius[idT] = powf(volT + transfVol, invD);
+		st->radius[idS] = pow_rn(volS - transfVol, invD);
+		st->radius[idT] = pow_rn(volT + transfVol, invD);
 		t->time_left[id] = (ttl - dt) * (merge ? 1.0f : -1.0f);
 		if (ttl == dt) {
 			if (merge) del_h[idS] = 1; else del_row[id] = 1;

@@ -40,7 +40,8 @@
  *
  * Floating-point conventions fixed here (GLSL leaves them to the driver):
  *   IEEE binary32, round-to-nearest-even, no FMA contraction (build with
- *   -ffp-contract=off), sqrtf and '/' correctly rounded, glibc powf/expf/log2f;
+ *   -ffp-contract=off), sqrtf and '/' correctly rounded, glibc powf/expf/log2f
+ *   (the merge / split passes: pow in double, rounded to float once);
  *   dot(a,b) = (a.x*b.x + a.y*b.y) + a.z*b.z; length(v) = sqrtf(dot(v,v));
  *   normalize(v) = v / length(v) (component-wise division); distance(a,b) =
  *   length(a-b); float->int/uint conversions truncate toward zero, uint() of a

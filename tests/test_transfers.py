@@ -259,6 +259,53 @@ def test_update_transfers_split_merge_matches_oracle(gpu, orc, merge, split, t_c
         assert (not merge or np.count_nonzero(ttl[2:] > 0) > 20) and (not split or st.n > sc.n + 20)
 
 
+def _two_d(orc):
+    """DIMENSIONS 2 (the reference's compiled default, cpu_gpu_shared_config.h:2): inverse mass 1/(2r)^2, pow(r, 2), pow(v, 1/2)"""
+    sc = scenes.uniform_block(40, jitter=0.3, dims=2, shuffle=True)
+    s = _settings(orc, 1, 1)
+    st = oracle_state(orc, sc)
+    pairs = orc.green_apply(st, s, 2, 1.0, sc.min_pos, sc.max_pos, sc.res_log2, sc.n * 40)
+    rng = np.random.default_rng(5)
+    radius = rng.uniform(0.8, 3.2, sc.n).astype(np.float32)
+    drawn = dict(radius=radius, inverse_mass=(1.0 / (2.0 * radius) ** 2).astype(np.float32),
+                 target_radius=rng.uniform(0.7, 4.5, sc.n).astype(np.float32), transferring=(rng.random(sc.n) < 0.1).astype(np.uint32))
+    for k, v in drawn.items():
+        getattr(st, k)[:] = v
+    return sc, s, st, pairs, drawn
+
+
+def test_two_dimensions_conserve_area_weighted_mass(orc):
+    sc, s, st, pairs, _ = _two_d(orc)
+    T = orc.Transfers(2 * sc.n)
+    mass0 = (1.0 / st.inverse_mass.astype(np.float64)).sum()
+    orc.update_transfers_full(st, s, 2, pairs, T, hidden_cap=2 * sc.n)
+    assert T.n > 50 and st.n > sc.n
+    for _ in range(2):
+        orc.particle_transfer_apply(st, T, 2, float(DT))
+    assert T.n == 0 and abs((1.0 / st.inverse_mass.astype(np.float64)).sum() / mass0 - 1.0) < 1e-5
+
+
+@pytest.mark.gpu
+def test_split_merge_two_dimensions_matches_oracle(gpu, orc):
+    sc, s, st, pairs, drawn = _two_d(orc)
+    ctx = gpu.Context(dims=2)
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    L = gpu.ParticleLists(ctx, sc.arrays, capacity=2 * sc.n, neighbor_capacity=sc.n * 40)
+    gpu.neighborhood_green(ctx).set_data(L).set_range_scale(1.0).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply()
+    assert np.array_equal(L.read_pairs(), pairs)
+    for k, v in drawn.items():
+        L.write(k, v)
+    T, TL = orc.Transfers(2 * sc.n), gpu.TransferList(ctx, 2 * sc.n)
+    orc.update_transfers_full(st, s, 2, pairs, T, hidden_cap=2 * sc.n)
+    gpu.update_transfers(ctx).set_data(L, TL).apply()
+    _same_lists(L, st, T, TL)
+    op = gpu.particle_transfer(ctx).set_data(L, TL)
+    for _ in range(2):
+        orc.particle_transfer_apply(st, T, 2, float(DT))
+        op.apply(float(DT))
+        _same_lists(L, st, T, TL)
+
+
 @pytest.mark.gpu
 def test_every_particle_a_candidate(gpu, orc):
     """the substep in which the whole interior becomes a candidate at once: a jitter-free lattice (every nearest-neighbour
