@@ -116,6 +116,48 @@ def uniform_block(side=64, r=1.0, jitter=0.0, seed=1234, dims=3, res_log2=None, 
     return sc
 
 
+def waterfall_boxes(mn, mx, r, dims=3, wall=4.0):
+    """source/waterfall.cpp:28-48: the top pool (closed: left, floor, right, lid, and the two z walls in 3-D) plus the bottom pool,
+    shifted by wMin - wMax in x and y (left, floor, right, two z walls) -- 11 boxes in 3-D, 7 in 2-D"""
+    mn = np.asarray(mn, np.float32); mx = np.asarray(mx, np.float32)
+    w_min = mn - np.float32(wall)
+    w_max = mx + np.float32(wall) + np.array([0, 2 * r, 0], np.float32)
+    shift = w_min - w_max
+    shift[2] = 0.0
+    top = [
+        (w_min, (w_min[0] + wall, w_max[1], w_max[2])),
+        (w_min, (w_max[0], w_min[1] + wall, w_max[2])),
+        ((w_max[0] - wall, w_min[1], w_min[2]), w_max),
+        ((w_min[0], w_max[1] - wall, w_min[2]), w_max),
+    ]
+    bottom = [(np.asarray(a, np.float32) + shift, np.asarray(b, np.float32) + shift) for a, b in top[:3]]
+    boxes = top + bottom
+    if dims > 2:
+        z = [(w_min, (w_max[0], w_max[1], w_min[2] + wall)), ((w_min[0], w_min[1], w_max[2] - wall), w_max)]
+        boxes += z + [(np.asarray(a, np.float32) + shift, np.asarray(b, np.float32) + shift) for a, b in z]
+    bmin = np.zeros((len(boxes), 4), np.float32); bmax = np.zeros((len(boxes), 4), np.float32)
+    for i, (a, b) in enumerate(boxes):
+        bmin[i, :3] = a; bmax[i, :3] = b
+    return bmin, bmax
+
+
+def waterfall(nx=252, ny=252, nz=252, r=1.0, jitter=0.05, seed=17, adaptive=False):
+    """configs[3]: the waterfall scene (source/waterfall.cpp:6-48) -- a block of fluid filling the top pool, 11 collision boxes
+    (the user opens the pool at run time in the reference; here it stays closed, what counts is the box_collision load).
+    252^3 = 16 003 008 particles at full size."""
+    ext = np.array([nx, ny, nz], np.float32) * 2 * r
+    mn = np.zeros(3, np.float32)
+    arrays = _lattice_state((nx, ny, nz), mn + r, r, jitter, seed)
+    margin = 6.0 * r + 4.0
+    lo = [float(v - margin) for v in mn]
+    hi = [float(v + margin) for v in ext + np.array([0, 2 * r, 0], np.float32)]
+    sc = Scene(name=f"waterfall_{nx}x{ny}x{nz}", dims=3, arrays=shuffle_state(arrays, seed), min_pos=tuple(lo), max_pos=tuple(hi),
+               res_log2=_res_for(max(h - l for l, h in zip(lo, hi)), 4.5 * r), basic_pbf=not adaptive, solver_iterations=4,
+               smallest_target_radius=r)
+    sc.box_min, sc.box_max = waterfall_boxes(mn, ext, r, 3)
+    return sc
+
+
 def shuffle_state(arrays, seed=7):
     """Random permutation of the hidden slots (index list stays the identity): exercises the sort/reorder."""
     n = arrays["index_list"].shape[0]

@@ -61,6 +61,10 @@ def make_scene(name, world=1):
         return scenes.uniform_block(32, jitter=0.1, shuffle=True), dict(adaptive=False, pairs_per_particle=40)
     if name.startswith("uniform_"):  # configs[4]: uniform-block sweep, e.g. uniform_100 / 160 / 256
         return scenes.uniform_block(int(name.split("_")[1]), jitter=0.1, shuffle=True), dict(adaptive=False, pairs_per_particle=40)
+    if name == "waterfall_16M":     # configs[3]: 252^3 particles in the closed top pool, 11 collision boxes (waterfall.cpp:28-48)
+        return scenes.waterfall(252, 252, 252), dict(adaptive=False, pairs_per_particle=40)
+    if name == "waterfall_64k":
+        return scenes.waterfall(40, 40, 40), dict(adaptive=False, pairs_per_particle=40)
     if name == "waterdrop_4M":      # configs[2]
         return scenes.waterdrop(204), dict(adaptive=True, pairs_per_particle=260)
     raise SystemExit(f"unknown workload {name}")

@@ -40,3 +40,27 @@ def test_algorithmic_bytes_follow_the_survey():
     assert per["hash_sort"] == 20 * n + 16 * n * passes and per["reorder"] == 152 * n and per["cell_ranges"] == 4 * n + 8 * cells
     assert per["density_lambda"] == 8 * pk + 56 * n and per["apply_delta"] == 8 * pk + 40 * n and per["box_collision"] == 36 * n
     assert sub == (196 + 16 * passes) * n + 16 * cells + 8 * p + iters * (16 * pk + 132 * n) + 8 * p + 8 * pk + 12 * n
+
+
+def test_waterfall_scene_has_eleven_boxes_and_keeps_its_fluid(orc):
+    """configs[3] (source/waterfall.cpp:28-48): 4 + 3 walls in the plane, 2 + 2 in z; the closed top pool holds the block through
+    oracle substeps with the integrator on (box_collision against all eleven boxes every iteration)"""
+    sc = scenes.waterfall(10, 10, 10)
+    assert sc.box_min.shape == (11, 4) and np.all(sc.box_max[:, :3] > sc.box_min[:, :3])
+    shift = sc.box_min[4, :3] - sc.box_min[0, :3]                      # bottom pool = top pool moved down and to the left
+    assert shift[0] < 0 and shift[1] < 0 and shift[2] == 0
+    assert np.allclose(sc.box_max[4, :3] - sc.box_max[0, :3], shift) and np.allclose(sc.box_min[9, :3] - sc.box_min[7, :3], shift)
+    assert scenes.waterfall_boxes((0, 0, 0), (20, 20, 20), 1.0, dims=2)[0].shape == (7, 4)
+    st = orc.State(**{k: v.copy() for k, v in sc.arrays.items()})
+    s = orc.default_settings()
+    for _ in range(5):
+        orc.substep(st, s, dims=3, basic_pbf=True, solver_iterations=4, min_pos=sc.min_pos, max_pos=sc.max_pos, res_log2=sc.res_log2,
+                    box_min4=sc.box_min, box_max4=sc.box_max, cap=sc.n * 80, integrate=True)
+    pos = st.position[:, :3].astype(np.float64) / 262144.0
+    inner_lo, inner_hi = sc.box_max[0, 0], sc.box_min[2, 0]             # between the left and the right wall of the top pool
+    assert np.all(pos[:, 0] > inner_lo - 1e-3) and np.all(pos[:, 0] < inner_hi + 1e-3)
+    assert np.all(pos[:, 1] > sc.box_max[1, 1] - 1e-3) and np.all(pos > np.asarray(sc.min_pos)) and np.all(pos < np.asarray(sc.max_pos))
+
+
+def test_waterfall_full_size():
+    assert 252 ** 3 == 16_003_008 and bench.make_scene("waterfall_64k")[0].n == 64000
