@@ -33,8 +33,10 @@
  *     UNPINNED by the reference -- it has no enabled test for
  *     them (test.cpp:533-583 return true) and its GLSL cannot be compiled or
  *     run in this image (no glslang, no Vulkan).  Cross-checked only by the
- *     brute-force search and hand-derived micro cases (tests/test_oracle_kats.py,
- *     tests/test_transfers.py).  Merge / split decisions are a race in the
+ *     brute-force search and known answers derived by hand from the shader text
+ *     (closed forms for two particles under the Gauss kernels, an exact box push-out,
+ *     spread_kernel_width / velocity_handling / update_transfers / merge / split micro
+ *     cases: tests/test_oracle_kats.py, tests/test_transfers.py).  Merge / split decisions are a race in the
  *     reference (atomicExchange); the restatement runs the invocations in
  *     ascending id order.
  *

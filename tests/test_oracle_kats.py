@@ -252,3 +252,107 @@ def test_substep_runs_and_conserves_particles(orc):
                         res_log2=sc.res_log2, box_min4=sc.box_min, box_max4=sc.box_max, cap=sc.n * 64)
     assert len(pairs) > 0 and st.n == sc.n
     assert sorted(st.inverse_mass.tolist()) == sorted(sc.arrays["inverse_mass"].tolist())
+
+
+def test_incompressibility_two_particles_closed_form(orc):
+    """Two equal particles 1.5 apart, kernel width 3, Gauss kernels, D = 3 -- every quantity of incompressibility_0..3.comp in
+    closed form (float64), independent of the restatement's code:
+      W(r) = H exp(-r^2 pi H^(2/3)), H = 0.6 / (h/2)^3                              kernels.glsl:84-89,104
+      density = m (W(0) + W(d)); g = -2 W(d) d pi H^(2/3) along the pair           incompressibility_0.comp:43, _1.comp:52-58, kernels.glsl:91-97
+      lambda = (1 - density) / (|g|^2 m + |m g|^2 / m + 0.01)   (rest density 1)   incompressibility_2.comp:72-98
+      own shift = m g lambda / m, neighbour shift = g lambda                       incompressibility_2.comp:106-109, _3.comp:66
+    Both particles end up |g lambda| further out on each side, twice (own shift + the neighbour's push)."""
+    d, h, m = 1.5, 3.0, 8.0
+    pos = np.zeros((2, 4), np.int32)
+    pos[1, 0] = int(d * 262144)
+    st = orc.State(index_list=np.arange(2, dtype=np.uint32), position=pos.copy(), velocity=np.zeros((2, 4), np.float32),
+                   inverse_mass=np.full(2, 1.0 / m, np.float32), radius=np.ones(2, np.float32), pos_backup=pos.copy(),
+                   transferring=np.zeros(2, np.uint32), target_radius=np.ones(2, np.float32), kernel_width=np.full(2, h, np.float32),
+                   boundariness=np.ones(2, np.float32), boundary_distance=np.full(2, 262144, np.uint32))
+    s = orc.default_settings()
+    s.mHeightKernelId, s.mGradientKernelId, s.mSmallestTargetRadius = 1, 1, 1.0
+    aux = orc.incompressibility_apply(st, s, 3, np.array([[0, 1], [1, 0]], np.uint32), want_aux=True)
+    H = 0.6 / (h / 2.0) ** 3
+    iv = np.pi * H ** (2.0 / 3.0)
+    W0, Wd = H, H * np.exp(-d * d * iv)
+    g = 2.0 * Wd * d * iv                                             # magnitude; points from the neighbour towards the particle
+    density = m * (W0 + Wd)
+    lam = (1.0 - density) / (g * g * m + (m * g) ** 2 / m + 0.01)
+    assert density > 1.0 and lam < 0.0
+    assert np.all(np.abs(aux["density"].astype(np.int64) - int(density * 262144)) <= 2)
+    assert np.all(np.abs(np.abs(aux["grad_sum"][:, 0].astype(np.int64)) - int(m * g * 262144)) <= 2) and np.all(aux["grad_sum"][:, 1:] == 0)
+    assert aux["grad_sum"][0, 0] < 0 < aux["grad_sum"][1, 0]            # particle 0 sees its neighbour at +x: gradient along -x
+    assert np.all(np.abs(aux["sq_grad_sum"].astype(np.int64) - int(g * g * m * 262144)) <= 2)
+    # lambda is formed from the truncated fixed-point sums (incompressibility_2.comp:67-69): the closed form to 1e-3, the same
+    # expression over the integers checked above to float accuracy
+    assert np.allclose(aux["lam"], lam, rtol=1e-3)
+    dq, gq, sq = aux["density"][0] / 262144.0, aux["grad_sum"][0, 0] / 262144.0, aux["sq_grad_sum"][0] / 262144.0
+    lam = (1.0 - dq) / (sq + gq * gq / m + 0.01)
+    assert np.allclose(aux["lam"], lam, rtol=1e-5)
+    shift = 2.0 * g * (-lam) * 262144                                 # own shift + the push from the neighbour's pair
+    assert abs((pos[0, 0] - st.position[0, 0]) - shift) <= 3 and abs((st.position[1, 0] - pos[1, 0]) - shift) <= 3
+    assert np.all(st.position[:, 1:3] == 0)
+
+
+def test_box_collision_exact_push_out(orc):
+    """id 0 at (1.2, 0, 0) with radius 1, box [1, 9] x [-5, 5]^2 (box_collision.comp:44-57): the jitter of the min faces is
+    hash31(0 * x - 0 - 0) = hash31(0) = 0, so the inflated min face sits at exactly 0; penetration 1.2 along x against about 6
+    along y and z and 8.8 to the max face -> the particle lands on x = 0 exactly.  The same particle outside the inflated box
+    (x = -0.5) only goes through the re-quantisation (:59)."""
+    def run(x):
+        pos = np.zeros((1, 4), np.int32)
+        pos[0, 0] = int(round(x * 262144))
+        st = orc.State(index_list=np.zeros(1, np.uint32), position=pos, velocity=np.zeros((1, 4), np.float32), inverse_mass=np.full(1, 0.125, np.float32),
+                       radius=np.ones(1, np.float32), pos_backup=pos.copy(), transferring=np.zeros(1, np.uint32), target_radius=np.ones(1, np.float32),
+                       kernel_width=np.full(1, 4.0, np.float32), boundariness=np.ones(1, np.float32), boundary_distance=np.full(1, 262144, np.uint32))
+        orc.box_collision(st, np.array([[1, -5, -5, 0]], np.float32), np.array([[9, 5, 5, 0]], np.float32))
+        return st.position[0, :3].tolist()
+    assert run(1.2) == [0, 0, 0]
+    assert run(-0.5) == [-131072, 0, 0]
+
+
+def _pair_state(orc, xs, radii, widths):
+    n = len(xs)
+    pos = np.zeros((n, 4), np.int32)
+    pos[:, 0] = [int(round(x * 262144)) for x in xs]
+    radii = np.asarray(radii, np.float32)
+    return orc.State(index_list=np.arange(n, dtype=np.uint32), position=pos, velocity=np.zeros((n, 4), np.float32),
+                     inverse_mass=(1.0 / (2.0 * radii) ** 3).astype(np.float32), radius=radii, pos_backup=pos.copy(),
+                     transferring=np.zeros(n, np.uint32), target_radius=radii.copy(), kernel_width=np.asarray(widths, np.float32),
+                     boundariness=np.ones(n, np.float32), boundary_distance=(radii * 262144).astype(np.uint32))
+
+
+def test_spread_kernel_width_hand_derived(orc):
+    """radius 1 (width 4) and radius 2 (width 8) six units apart (kernel_width_init.comp:33-35, kernel_width.comp:46-60,
+    uint_to_float_but_gradual.comp:21-38):
+      pair (0,1): 6 - 4 = 2 beyond the small kernel, 2 / (4 * 0.5) = 1 -> influence 0; 6 > max(4, 4) -> the pair is dropped
+      pair (1,0): inside the large kernel -> influence 1 -> particle 0 is asked for width 8; 6 <= 8 -> the pair stays
+    fixed-point widths {8, 8} * 2^18; particle 0 moves from 4 towards 8 by one relative step, particle 1 stays at 8."""
+    st = _pair_state(orc, [0.0, 6.0], [1.0, 2.0], [4.0, 8.0])
+    s = orc.default_settings()
+    s.mBaseKernelWidthOnTargetRadius = 0
+    kept, kwfx = orc.spread_kernel_width_apply(st, s, np.array([[0, 1], [1, 0]], np.uint32))
+    assert kept.tolist() == [[1, 0]] and kwfx.tolist() == [8 * 262144, 8 * 262144]
+    step = np.float32(4.0) * (np.float32(1.0) + np.float32(s.mKernelWidthAdaptionSpeed))
+    assert 4.0 < step < 8.0 and st.kernel_width.tolist() == [step, 8.0]
+    # half way into the fall-off: 5 units apart -> (5 - 4) / 2 = 0.5 -> the large particle is asked for 4 * 0.5 = 2 (below its own 8)
+    st = _pair_state(orc, [0.0, 5.0], [1.0, 2.0], [4.0, 8.0])
+    kept, kwfx = orc.spread_kernel_width_apply(st, s, np.array([[0, 1]], np.uint32))
+    assert kept.tolist() == [] and kwfx.tolist() == [4 * 262144, 8 * 262144]
+
+
+def test_velocity_handling_hand_derived(orc):
+    """infer_velocity.comp:32, apply_acceleration.comp:28, apply_velocity.comp:31 with mLastDeltaTime == dt (velocity_handling.cpp:
+    15-31): v = (pos - backup) / (dt 2^18), v += a dt, pos += ivec3(v (dt 2^18)), backup = the old position"""
+    dt = np.float32(1.0 / 60.0)
+    st = _pair_state(orc, [0.5], [1.0], [4.0])
+    st.position[0, 1] = 65536
+    st.pos_backup[:] = 0
+    orc.velocity_handling(st, float(dt), (0.0, -10.0, 0.0))
+    k = dt * np.float32(262144.0)
+    v = np.array([131072, 65536, 0], np.float32) / k
+    v[1] += np.float32(-10.0) * dt
+    assert st.velocity[0, :3].tolist() == v.tolist() and abs(float(v[0]) - 30.0) < 1e-4 and abs(float(v[1]) - (15.0 - 1.0 / 6.0)) < 1e-4
+    assert st.pos_backup[0, :3].tolist() == [131072, 65536, 0]
+    assert st.position[0, :3].tolist() == [131072 + int(v[0] * k), 65536 + int(v[1] * k), 0]
+    assert abs(st.position[0, 0] - 262144) <= 1 and abs(st.position[0, 1] - (131072 - 728)) <= 1   # 0.5 + 30/60 ; 0.25 + 14.8333/60
