@@ -356,3 +356,26 @@ def test_velocity_handling_hand_derived(orc):
     assert st.pos_backup[0, :3].tolist() == [131072, 65536, 0]
     assert st.position[0, :3].tolist() == [131072 + int(v[0] * k), 65536 + int(v[1] * k), 0]
     assert abs(st.position[0, 0] - 262144) <= 1 and abs(st.position[0, 1] - (131072 - 728)) <= 1   # 0.5 + 30/60 ; 0.25 + 14.8333/60
+
+
+@pytest.mark.parametrize("dims", [3, 2])
+def test_kernels_are_normalised_and_gradients_are_their_derivatives(orc, dims):
+    """kernels.glsl:3-123, independent of the restatement's code: every height kernel integrates to 1 over its support in 3-D
+    (Gauss: no cut-off, integrated to 2.5 h); in 2-D the dimension-aware ones do (Gauss, cone, quadratic spike) while cubic and
+    poly6 keep their 3-D constants (the reference's behaviour: 0.70 and 0.62); the gradient kernel with the same id is the
+    radial derivative of the height kernel (cubic, Gauss, cone, quadratic spike; id 2 pairs poly6 with spiky)."""
+    s = orc.default_settings()
+    h = 2.0
+    for hk in range(5):
+        s.mHeightKernelId = s.mGradientKernelId = hk
+        rs = np.linspace(1e-4, 2.5 * h if hk == 1 else h * 1.0001, 3000)
+        w = np.array([orc.kernel_height(s, dims, [r, 0, 0], h) for r in rs])
+        integral = np.trapezoid(w * (4 * np.pi * rs ** 2 if dims == 3 else 2 * np.pi * rs), rs)
+        expected = 1.0 if dims == 3 or hk in (1, 3, 4) else (0.7 if hk == 0 else 0.6152)
+        assert abs(integral - expected) < 2e-3, (hk, integral)
+        if hk == 2:
+            continue
+        for r in (0.3 * h, 0.6 * h, 0.9 * h):
+            fd = (orc.kernel_height(s, dims, [r + 1e-3, 0, 0], h) - orc.kernel_height(s, dims, [r - 1e-3, 0, 0], h)) / 2e-3
+            g = orc.kernel_gradient(s, dims, [r, 0, 0], h)
+            assert abs(g[0] - fd) <= 2e-3 * abs(fd) + 1e-5 and g[1] == 0 and g[2] == 0, (hk, r, g, fd)
