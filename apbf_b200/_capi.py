@@ -117,6 +117,7 @@ SIGNATURES = {
     "apbf_particle_transfer_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Transfers), C.c_float, vp]),
     "apbf_transfers_follow_reorder": (C.c_int, [vp, C.POINTER(Transfers), vp, vp, C.c_uint32]),
     "apbf_kernel_width_from_boundary_distance": (C.c_int, [vp, C.POINTER(Fluid)]),
+    "apbf_uint_to_float_with_indexed_lower_bound": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint32, C.c_float, C.c_float, C.c_float]),
     "apbf_box_collision_apply": (C.c_int, [vp, C.POINTER(Particles), vp, vp, C.c_uint32]),
     "apbf_velocity_handling_apply": (C.c_int, [vp, C.POINTER(Particles), C.c_float, C.c_float, f32p]),
     "apbf_sim_create": (C.c_int, [vp, C.POINTER(SimConfig), C.POINTER(vp)]),

@@ -412,6 +412,20 @@ int apbf_update_transfers_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_nei
 	return APBF_OK;
 }
 
+int apbf_uint_to_float_with_indexed_lower_bound(apbf_ctx* ctx, const uint32_t* in_uint, float* out_float, const uint32_t* index_list,
+                                                const float* lower_bound, const uint32_t* len, uint32_t capacity, float factor,
+                                                float lower_bound_factor, float max_adaption_step)
+{
+	if (!ctx) return APBF_ERR_INVALID;
+	APBF_REQUIRE(ctx, in_uint && out_float && index_list && lower_bound && len);
+	if (capacity == 0) return APBF_OK;
+	apbf_prof_scope ps(ctx, PROF_KW_MISC);
+	k_kw_from_boundary_distance<<<apbf_grid(ctx, capacity, 256), 256, 0, ctx->stream>>>(index_list, len, in_uint, lower_bound, out_float, factor,
+	                                                                                  lower_bound_factor, max_adaption_step);
+	APBF_LAUNCHED(ctx);
+	return APBF_OK;
+}
+
 int apbf_kernel_width_from_boundary_distance(apbf_ctx* ctx, apbf_fluid* fluid)
 {
 	if (!ctx) return APBF_ERR_INVALID;

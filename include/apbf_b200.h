@@ -296,6 +296,12 @@ int apbf_transfers_follow_reorder(apbf_ctx* ctx, apbf_transfers* transfers, cons
 /* pool.cpp:77-80: shader_provider::uint_to_float_with_indexed_lower_bound(boundary_distance -> kernel_width, factor
  * targetRadiusScaleFactor / POS_RESOLUTION, lower bound radius * KERNEL_SCALE, step kernelWidthAdaptionSpeed) */
 int apbf_kernel_width_from_boundary_distance(apbf_ctx* ctx, apbf_fluid* fluid);
+/* shader_provider::uint_to_float_with_indexed_lower_bound (source/shader_provider.h:27, uint_to_float_with_indexed_lower_bound.comp:
+ * 32-44) with its own arguments: out[id] = max(move_towards(out[id], in[id] * factor, max_adaption_step),
+ * lower_bound[index_list[id]] * lower_bound_factor) for id < *len */
+int apbf_uint_to_float_with_indexed_lower_bound(apbf_ctx* ctx, const uint32_t* in_uint, float* out_float, const uint32_t* index_list,
+                                                const float* lower_bound, const uint32_t* len, uint32_t capacity, float factor,
+                                                float lower_bound_factor, float max_adaption_step);
 /* pbd::box_collision::set_data(particles, boxMin, boxMax).apply() (source/box_collision.cpp:12-24); boxes are vec4
  * device arrays, n_boxes host-known (user_controlled_boxes owns them, <= 64) */
 int apbf_box_collision_apply(apbf_ctx* ctx, apbf_particles* particles, const float* box_min4, const float* box_max4,

@@ -74,6 +74,14 @@ namespace pbd
 		{
 			check(apbf_write_sequence(context(), aOut.as<uint32_t>(), aLength.as<uint32_t>(), static_cast<uint32_t>(aOut.bytes / 4), aStart, aStep, 1u));
 		}
+		/// shader_provider.h:27 (pool.cpp:77-80 calls it with the boundary distance, the kernel width, the particle index list and the radii)
+		static void uint_to_float_with_indexed_lower_bound(const buffer& aInUintBuffer, const buffer& aOutFloatBuffer, const buffer& aInIndexList, const buffer& aInLowerBound,
+		                                                   const buffer& aInUintBufferLength, float aFactor, float aLowerBoundFactor, float aMaxAdationStep)
+		{
+			check(apbf_uint_to_float_with_indexed_lower_bound(context(), aInUintBuffer.as<uint32_t>(), aOutFloatBuffer.as<float>(), aInIndexList.as<uint32_t>(), aInLowerBound.as<float>(),
+			                                                  aInUintBufferLength.as<uint32_t>(), static_cast<uint32_t>(std::min(aInUintBuffer.bytes, aOutFloatBuffer.bytes) / 4), aFactor,
+			                                                  aLowerBoundFactor, aMaxAdationStep));
+		}
 		static void write_sequence_float(const buffer& aOut, const buffer& aLength, float aStart, float aStep)
 		{
 			check(apbf_write_sequence_float(context(), aOut.as<float>(), aLength.as<uint32_t>(), static_cast<uint32_t>(aOut.bytes / 4), aStart, aStep));
