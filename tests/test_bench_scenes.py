@@ -64,3 +64,20 @@ def test_waterfall_scene_has_eleven_boxes_and_keeps_its_fluid(orc):
 
 def test_waterfall_full_size():
     assert 252 ** 3 == 16_003_008 and bench.make_scene("waterfall_64k")[0].n == 64000
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm: the oracle on the host cores, kind "port"): one JSON line on stdout with the keys
+    the driver reads"""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--workload", "uniform_32"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["config"]["workload"] == "uniform_32"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
