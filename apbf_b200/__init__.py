@@ -15,7 +15,7 @@ from ._capi import Settings
 
 __all__ = ["Context", "ParticleLists", "neighborhood_green", "neighborhood_binary_search", "incompressibility",
            "spread_kernel_width", "box_collision", "velocity_handling", "algorithms", "Sim", "Settings", "TransferList",
-           "update_transfers", "particle_transfer"]
+           "update_transfers", "particle_transfer", "NeighborList"]
 
 _HIDDEN = (("position", np.int32, 4), ("velocity", np.float32, 4), ("inverse_mass", np.float32, 1),
            ("radius", np.float32, 1), ("pos_backup", np.int32, 4), ("transferring", np.uint32, 1))
@@ -150,6 +150,39 @@ class ParticleLists:
         self.words[0] = n
         self.words[1] = nh
         self.pairs = torch.zeros((self.neighbor_capacity, 2), dtype=torch.int32, device=dev)
+        self._pair_word = self.words.data_ptr() + 8
+        self._forget_pairs()   # torch recycles device addresses: nothing an earlier list left behind applies to this buffer
+
+    def _forget_pairs(self):
+        if getattr(self.ctx, "handle", None) and getattr(self, "pairs", None) is not None:
+            nb = _capi.Neighbors(self.pairs.data_ptr(), self._pair_word, self.neighbor_capacity)
+            self.ctx.lib.apbf_neighbors_release(self.ctx.handle, C.byref(nb))
+
+    def __del__(self):
+        try:
+            self._forget_pairs()
+        except Exception:
+            pass
+
+    def use_neighbors(self, other):
+        """operators of this object read / write the pair list of `other` (a NeighborList) from now on: set_data(fluid, neighbors)
+        of the reference takes the two lists separately"""
+        self._forget_pairs()
+        self.pairs, self._pair_word, self.neighbor_capacity = other.pairs, other.word.data_ptr(), other.capacity
+        self._keep = other
+        return self
+
+    def write_pairs(self, pairs):
+        """the caller's own pair list: pbd::neighbors::write() followed by the caller's writes.  pairs: host array [P, 2]"""
+        torch = _torch()
+        a = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        assert a.shape[0] <= self.neighbor_capacity
+        if a.shape[0]:
+            self.pairs[: a.shape[0]].copy_(torch.from_numpy(a.view(np.int32)).to(self.pairs.device))
+        word = (self.words[2:3] if self._pair_word == self.words.data_ptr() + 8 else self._keep.word)
+        word.fill_(int(a.shape[0]))
+        nb = self.neighbors()
+        _check(self.ctx, self.ctx.lib.apbf_neighbors_invalidate(self.ctx.handle, C.byref(nb)))
 
     # ---- C views --------------------------------------------------------------------------------------------------
     def _arr(self, name):
@@ -172,7 +205,7 @@ class ParticleLists:
         return f
 
     def neighbors(self):
-        return _capi.Neighbors(self.pairs.data_ptr(), self.words.data_ptr() + 8, self.neighbor_capacity)
+        return _capi.Neighbors(self.pairs.data_ptr(), self._pair_word, self.neighbor_capacity)
 
     def swap(self):
         """after a search: the reorder_out buffers hold the lists"""
@@ -184,6 +217,8 @@ class ParticleLists:
         return int(self.words[0].item())
 
     def pair_count(self):
+        if self._pair_word != self.words.data_ptr() + 8:
+            return int(self._keep.word.item())
         return int(self.words[2].item())
 
     def read(self, name):
@@ -206,6 +241,37 @@ class ParticleLists:
 
     def read_pairs(self):
         return self.pairs[:self.pair_count()].cpu().numpy().view(np.uint32)
+
+
+class NeighborList:
+    """a pbd::neighbors list of its own (gpu_list<8> + length word), e.g. a second list over the same particles"""
+
+    def __init__(self, ctx, capacity, pairs=None):
+        torch = _torch()
+        self.ctx, self.capacity = ctx, int(capacity)
+        dev = torch.device("cuda", ctx.device)
+        self.pairs = torch.zeros((self.capacity, 2), dtype=torch.int32, device=dev)
+        self.word = torch.zeros(4, dtype=torch.int32, device=dev)
+        nb = self.c()
+        ctx.lib.apbf_neighbors_release(ctx.handle, C.byref(nb))
+        if pairs is not None:
+            a = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+            self.pairs[: a.shape[0]].copy_(torch.from_numpy(a.view(np.int32)).to(dev))
+            self.word[0] = a.shape[0]
+
+    def c(self):
+        return _capi.Neighbors(self.pairs.data_ptr(), self.word.data_ptr(), self.capacity)
+
+    def read(self):
+        return self.pairs[: int(self.word[0].item())].cpu().numpy().view(np.uint32)
+
+    def __del__(self):
+        try:
+            if getattr(self.ctx, "handle", None):
+                nb = self.c()
+                self.ctx.lib.apbf_neighbors_release(self.ctx.handle, C.byref(nb))
+        except Exception:
+            pass
 
 
 class TransferList:
@@ -626,6 +692,16 @@ class Sim:
         c = C.c_uint32()
         _check(self.ctx, self.lib.apbf_sim_neighbor_count(self.handle, C.byref(c)))
         return c.value
+
+    def read_pairs(self):
+        """the scene's pair list as (id, idN) rows on the host: apbf_sim_neighbors() writes the public list on demand"""
+        nb = _capi.Neighbors()
+        _check(self.ctx, self.lib.apbf_sim_neighbors(self.handle, C.byref(nb)))
+        n = min(self.neighbor_count(), self.neighbor_capacity)
+        out = np.zeros((n, 2), np.uint32)
+        if n:
+            _check(self.ctx, self.lib.apbf_copy_bytes_to_host(self.ctx.handle, nb.pairs, out.ctypes.data, 8 * n))
+        return out
 
     def close(self):
         if getattr(self, "handle", None):

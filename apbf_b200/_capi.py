@@ -110,6 +110,9 @@ SIGNATURES = {
     "apbf_neighborhood_binary_search_spread_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), C.c_float, vp, vp]),
     "apbf_neighborhood_binary_search_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Array), C.POINTER(Neighbors),
                                                         C.c_float, C.POINTER(SearchDebug)]),
+    "apbf_neighbors_invalidate": (C.c_int, [vp, C.POINTER(Neighbors)]),
+    "apbf_neighbors_release": (C.c_int, [vp, C.POINTER(Neighbors)]),
+    "apbf_neighbors_prepare": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), vp]),
     "apbf_incompressibility_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), vp, vp]),
     "apbf_spread_kernel_width_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), vp]),
     "apbf_update_transfers_apply": (C.c_int, [vp, C.POINTER(Fluid), C.POINTER(Neighbors), vp]),

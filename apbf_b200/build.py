@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libapbf_b200.so")
-SOURCES = ["ctx.cu", "sort.cu", "keys.cu", "neighbors.cu", "solver.cu", "incompress.cu", "transfers.cu", "sim.cu", "mgpu.cu"]
+SOURCES = ["ctx.cu", "sort.cu", "keys.cu", "neighbors.cu", "nbrlist.cu", "solver.cu", "incompress.cu", "transfers.cu", "sim.cu", "mgpu.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: no FMA contraction anywhere, like the oracle's -ffp-contract=off (bit-exact neighbour tests depend on it)
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-fmad=false",

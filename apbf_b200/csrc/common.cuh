@@ -57,6 +57,7 @@ enum apbf_misc_word {
 	MW_PMAX = 23,            // binary search fused with the spread: largest |coordinate| of the list (float bits)
 	MW_MAX_INIT = 22,        // fused search + spread: largest initial kernel width (fixed point) over all particles
 	MW_STREAM_OVERFLOW = 21, // the hit stream ran out of blocks (only when the pair list overflows): the two-pass fill takes over
+	MW_REBUILD_LEN = 24,     // rebuild of a structure from a foreign pair list: min(list length, capacity)
 	MW_WORDS = 64
 };
 
@@ -66,6 +67,17 @@ enum apbf_prof_cat {
 	PROF_KW_COMPACT, PROF_KW_MISC, PROF_BOX, PROF_DENSITY_LAMBDA, PROF_APPLY_DELTA, PROF_COMMIT, PROF_VELOCITY, PROF_SOLVER_PREPARE, PROF_UPDATE_TRANSFERS, PROF_COUNT
 };
 struct apbf_prof_span { int cat; cudaEvent_t beg, end; };
+
+// a neighbour-list structure (CSR offsets + 4-byte list, neighbors.cuh) that is parked while another pair buffer's
+// structure is the active one
+struct apbf_nbr_entry {
+	const uint32_t* pairs = nullptr; // the public pair buffer the structure describes
+	apbf_scratch    offsets, nbl;
+	uint32_t*       words = nullptr; // parked device words: [0] = MW_N_ASYM
+	uint32_t        n_cap = 0;
+	bool            valid = false, public_written = false;
+	uint64_t        stamp = 0;
+};
 
 struct apbf_ctx {
 	bool          prof_on = false;
@@ -83,17 +95,20 @@ struct apbf_ctx {
 	std::string   last_error;
 	apbf_scratch  scratch[SLOT_COUNT];
 	std::vector<apbf_pool_block> pool;
-	// provenance of the neighbour list structure built by the last search (offsets/NB valid for this buffer)
+	// The ACTIVE neighbour-list structure (SLOT_OFFSETS, SLOT_NB, misc[MW_N_ASYM]) belongs to this public pair buffer; the
+	// structures of other pair buffers are parked in nbr_cache (neighbors.cuh: apbf_nbr_activate / apbf_nbr_ensure).
 	const uint32_t* nbr_struct_pairs = nullptr;
 	uint32_t        nbr_struct_n_cap = 0;
+	bool            nbr_valid = false;   // offsets + NB describe the list in nbr_struct_pairs
+	bool            nbr_public = false;  // ... and the public (id, idN) list has been written as well
+	uint64_t        nbr_clock = 0;
+	std::vector<apbf_nbr_entry> nbr_cache;
+	uint64_t        scratch_epoch = 0;   // bumped whenever a scratch slot is (re)allocated: captured graphs go stale
 	// multi-GPU slabs: ghost particles sort into a second key space and are searched through a second cell table
 	bool            mg_enabled = false;
 	// a following spread_kernel_width prunes pairs, which can turn a mirrored pair into an unmirrored one: ghosts then
 	// keep ALL their pairs onto owned particles until the prune has decided
 	bool            mg_ghost_all_pairs = false;
-	// whole-scene path (apbf_sim_*): nothing reads the public (id, idN) list between the search and the sweeps, which use the
-	// 4-byte NB list; the green search then skips the 8-byte stores (the list length is still set)
-	bool            skip_public_pairs = false;
 	uint32_t        stream_blocks_cap = 0; // testing aid: upper bound on the hit stream's blocks (0 = automatic)
 	uint32_t        match_grid_min = 16384; // merge / split matching: grid-wide rounds from this many candidates on
 	bool            search_stats = false; // fused search + spread: count the pairs of the unpruned list as well

@@ -1,6 +1,7 @@
 // ctx.cu -- context, buffer pool, byte copies (replaces shader_provider's recording state, gpu_list_data's pool
 // (source/gpu_list_data.cpp:6-45) and algorithms::copy_bytes (source/algorithms.cpp:4-36)).
 #include "common.cuh"
+#include "neighbors.cuh"
 
 int apbf_fail(apbf_ctx* ctx, int code, const char* what, const char* file, int line)
 {
@@ -63,6 +64,7 @@ void* apbf_ctx::scratch_get(int slot, size_t bytes)
 		return nullptr;
 	}
 	s.bytes = want;
+	scratch_epoch++;
 	if (slot == SLOT_MISC_WORDS) {
 		cudaMemset(s.ptr, 0, want);
 		const uint32_t none = 0xFFFFFFFFu;
@@ -123,6 +125,7 @@ void apbf_ctx_destroy(apbf_ctx* ctx)
 	for (auto e : ctx->prof_free) cudaEventDestroy(e);
 	for (auto& s : ctx->scratch) if (s.ptr) cudaFree(s.ptr);
 	for (auto& b : ctx->pool) cudaFree(b.ptr);
+	for (auto& e : ctx->nbr_cache) { if (e.offsets.ptr) cudaFree(e.offsets.ptr); if (e.nbl.ptr) cudaFree(e.nbl.ptr); if (e.words) cudaFree(e.words); }
 	delete ctx;
 }
 
@@ -232,6 +235,7 @@ int apbf_buffer_acquire(apbf_ctx* ctx, size_t bytes, void** out)
 	}
 	best->in_use = true;
 	*out = best->ptr;
+	apbf_nbr_forget(ctx, best->ptr); // a recycled buffer is a new list: whatever structure was known for this address is gone
 	return APBF_OK;
 }
 
@@ -239,7 +243,7 @@ int apbf_buffer_release(apbf_ctx* ctx, void* p)
 {
 	if (!ctx) return APBF_ERR_INVALID;
 	for (auto& b : ctx->pool)
-		if (b.ptr == p) { b.in_use = false; return APBF_OK; }
+		if (b.ptr == p) { b.in_use = false; apbf_nbr_forget(ctx, p); return APBF_OK; }
 	return apbf_fail(ctx, APBF_ERR_INVALID, "buffer not from this pool", __FILE__, __LINE__);
 }
 
@@ -247,6 +251,7 @@ int apbf_copy_bytes(apbf_ctx* ctx, const void* src, void* dst, size_t bytes)
 {
 	if (!ctx) return APBF_ERR_INVALID;
 	if (bytes == 0) return APBF_OK; // algorithms.cpp:6
+	apbf_nbr_touch(ctx, dst);
 	APBF_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
 	return APBF_OK;
 }
@@ -255,6 +260,7 @@ int apbf_copy_bytes_from_host(apbf_ctx* ctx, const void* src, void* dst, size_t 
 {
 	if (!ctx) return APBF_ERR_INVALID;
 	if (bytes == 0) return APBF_OK;
+	apbf_nbr_touch(ctx, dst);
 	APBF_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	return APBF_OK;
 }

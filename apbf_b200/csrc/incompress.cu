@@ -439,8 +439,7 @@ int apbf_solver_prepare(apbf_ctx* ctx, apbf_fluid* fluid)
 int apbf_solver_iteration(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors* nb, int flags, const float* box_min4,
                           const float* box_max4, uint32_t n_boxes, float* out_lambda, uint32_t* out_incomp)
 {
-	if (!apbf_nbr_struct_valid(ctx, nb))
-		return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, "neighbour list was not produced by this context's search", __FILE__, __LINE__);
+	APBF_TRY(apbf_nbr_ensure(ctx, fluid, nb)); // any pair list (incompressibility.h:11): foreign ones get their structure built here
 	sweep_args A;
 	APBF_TRY(fill_args(ctx, fluid, nb, A));
 	const uint32_t n_cap = fluid->particle.capacity;

@@ -1,5 +1,6 @@
 // keys.cu -- position keys (cell hash / 96-bit Morton code), cell ranges, and the list helper kernels.
 #include "keys.cuh"
+#include "neighbors.cuh"
 #include "sort.cuh"
 
 namespace {
@@ -274,6 +275,7 @@ int apbf_copy_scattered_read(apbf_ctx* ctx, const void* src, void* dst, const ui
 {
 	if (!ctx) return APBF_ERR_INVALID;
 	APBF_REQUIRE(ctx, src && dst && edit && edit_len && src != dst);
+	apbf_nbr_touch(ctx, dst); // (if dst is a pair list some operator knows: its content is changing)
 	return apbf_launch_gather(ctx, src, dst, edit, edit_len, capacity, stride_bytes);
 }
 
@@ -294,6 +296,7 @@ int apbf_append_list(apbf_ctx* ctx, void* target, const void* appending, const u
 {
 	if (!ctx) return APBF_ERR_INVALID;
 	APBF_REQUIRE(ctx, target && appending && target_len && appending_len && new_len && stride_bytes % 4 == 0);
+	apbf_nbr_touch(ctx, target);
 	if (appending_capacity > 0) {
 		k_append_list<<<apbf_grid(ctx, (size_t)appending_capacity * (stride_bytes / 4), 256), 256, 0, ctx->stream>>>(
 		    (uint32_t*)target, (const uint32_t*)appending, target_len, appending_len, new_len, target_capacity, stride_bytes / 4);
@@ -353,6 +356,7 @@ int apbf_copy_with_differing_stride(apbf_ctx* ctx, const void* src, void* dst, c
 {
 	if (!ctx) return APBF_ERR_INVALID;
 	APBF_REQUIRE(ctx, src && dst && len && src_stride_bytes % 4 == 0 && dst_stride_bytes % 4 == 0);
+	apbf_nbr_touch(ctx, dst);
 	if (capacity == 0) return APBF_OK;
 	uint32_t w = (src_stride_bytes < dst_stride_bytes ? src_stride_bytes : dst_stride_bytes) / 4;
 	k_copy_strided<<<apbf_grid(ctx, (size_t)capacity * w, 256), 256, 0, ctx->stream>>>((const uint32_t*)src, (uint32_t*)dst, len,

@@ -482,12 +482,11 @@ int apbf_sim_mg_phase(apbf_sim* sim, int phase, int iteration)
 			const bool adaptive = !c.basic_pbf && !s.mBaseKernelWidthOnBoundaryDistance; // spread_kernel_width will prune
 			sim->mg_fused = adaptive && !sim->no_fuse;
 			ctx->mg_ghost_all_pairs = adaptive && !sim->mg_fused;
-			ctx->skip_public_pairs = true; // (the sweeps and a separate spread work on NB + offsets)
+			// (the sweeps and a separate spread work on NB + offsets: no public pair list, write_public = false)
 			if (sim->mg_fused) // search + spread_kernel_width in one pass (pool.cpp:83-89), ghosts included
-				APBF_TRY(apbf_neighborhood_green_spread_apply(ctx, &sim->fluid, &sim->nb, 1.5f, c.min_pos, c.max_pos, c.res_log2, nullptr, nullptr));
+				APBF_TRY(apbf_green_search(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, 1.5f, c.min_pos, c.max_pos, c.res_log2, nullptr, true, nullptr, false));
 			else
-				APBF_TRY(apbf_neighborhood_green_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, unit_scale ? 1.0f : 1.5f, c.min_pos, c.max_pos, c.res_log2, nullptr));
-			ctx->skip_public_pairs = false;
+				APBF_TRY(apbf_green_search(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, unit_scale ? 1.0f : 1.5f, c.min_pos, c.max_pos, c.res_log2, nullptr, false, nullptr, false));
 			apbf_sim_swap_buffers(sim);
 			// old slot -> new id, for the send lists and the ghost slots (the search's sorted_index is still in scratch)
 			const uint32_t cap = c.particle_capacity;

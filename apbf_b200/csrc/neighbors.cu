@@ -1145,20 +1145,6 @@ k_regroup(const uint32_t* __restrict__ stream, uint32_t stream_blocks, const uin
 	if ((threadIdx.x & 31u) == 0u && n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
 }
 
-// the public (id, idN) list from the grouped 4-byte list: 8 lanes per particle walk its segment, coalesced on both sides
-// (writing the 8-byte pairs from the regroup scatters them over partially filled sectors and costs three times as much)
-__global__ void __launch_bounds__(256)
-k_expand_pairs(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ nbl, const uint32_t* __restrict__ len,
-               uint32_t* __restrict__ pairs, uint32_t cap)
-{
-	const uint32_t n = *len;
-	const unsigned sub = threadIdx.x & 7u;
-	for (uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; a < n; a += (gridDim.x * blockDim.x) >> 3) {
-		const uint32_t beg = min(offsets[a], cap), end = min(offsets[a + 1], cap);
-		for (uint32_t e = beg + sub; e < end; e += 8u) *(uint2*)(pairs + 2 * (size_t)e) = make_uint2(a, nbl[e] & NB_ID_MASK);
-	}
-}
-
 // ---- binary-search pair emit, two-pass form (overflow fallback of the stream form) ----------------------------------------
 template <bool FILL>
 __global__ void __launch_bounds__(128)
@@ -1234,6 +1220,16 @@ __global__ void k_clear_search_words(uint32_t* misc)
 {
 	misc[MW_N_ASYM] = 0u; misc[MW_TOTAL_PAIRS] = 0u; misc[MW_KEPT_PAIRS] = 0xFFFFFFFFu; misc[MW_OCC_CELLS] = 0u;
 	misc[MW_EMIT_TICKET0] = 0u; misc[MW_EMIT_TICKET1] = 0u; misc[MW_STREAM_CURSOR] = 0u; misc[MW_STREAM_OVERFLOW] = 0u; misc[MW_MAX_INIT] = 0u; misc[MW_PMAX] = 0u;
+}
+
+// offsets[id] for the ids between the list's length and its capacity: empty segments.  A list that grows afterwards (the copies
+// of update_transfers' splits, update_transfers.cpp:64-68) then finds its new particles without pairs instead of reading
+// entries the scan never wrote.
+__global__ void k_offsets_tail(uint32_t* __restrict__ offsets, const uint32_t* __restrict__ len, uint32_t n_cap)
+{
+	const uint32_t n = min(*len, n_cap);
+	const uint32_t total = offsets[n];
+	for (uint32_t id = n + 1u + blockIdx.x * blockDim.x + threadIdx.x; id <= n_cap; id += gridDim.x * blockDim.x) offsets[id] = total;
 }
 
 // shared front half of both searches: gather hidden arrays by sorted_index, rebuild the index list, gather per-id arrays
@@ -1324,15 +1320,19 @@ void launch_stream(int variant, bool stats, int dims, unsigned grid, cudaStream_
 	else launch_stream<EMIT_PLAIN, false>(dims, grid, st, A);
 }
 
+} // namespace
+
 // neighborhood_green::apply (neighborhood_green.cpp:27-77); fuse_kw: followed by spread_kernel_width::apply
 // (spread_kernel_width.cpp:12-26) on the same lists, with range == fluid->kernel_width as in pool.cpp:83-89
-int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb, float range_scale,
-                 const float min_pos[3], const float max_pos[3], uint32_t res_log2, const apbf_search_debug* dbg, bool fuse_kw,
-                 uint32_t* out_kw_fixed)
+int apbf_green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb, float range_scale,
+                      const float min_pos[3], const float max_pos[3], uint32_t res_log2, const apbf_search_debug* dbg, bool fuse_kw,
+                      uint32_t* out_kw_fixed, bool write_public)
 {
 	if (!ctx) return APBF_ERR_INVALID;
 	APBF_REQUIRE(ctx, fluid && range && nb && min_pos && max_pos);
 	APBF_REQUIRE(ctx, nb->pairs && nb->length && fluid->particle.length && fluid->particle.hidden_length);
+	APBF_TRY(apbf_nbr_activate(ctx, nb)); // SLOT_OFFSETS / SLOT_NB are this list's from here on
+	ctx->nbr_valid = false;
 	apbf_particles& p = fluid->particle;
 	cudaStream_t st = ctx->stream;
 	const uint32_t nh_cap = p.hidden_capacity, n_cap = p.capacity;
@@ -1433,6 +1433,8 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 		// fused: the counts are those of the pruned list; the size of the unpruned one is summed up by the count pass
 		APBF_TRY(apbf_scan_u32(ctx, counts, offsets, p.length, n_cap, false, nb->length, nb->capacity, misc + MW_FLAGS,
 		                       misc + (fuse_kw ? MW_KEPT_PAIRS : MW_TOTAL_PAIRS)));
+		k_offsets_tail<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>(offsets, p.length, n_cap);
+		APBF_LAUNCHED(ctx);
 	}
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
@@ -1440,10 +1442,7 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, nullptr, nbl, nb->capacity, misc,
 			                                                    variant == EMIT_FUSED_MG ? 1 : 0);
 			APBF_LAUNCHED(ctx);
-			if (!ctx->skip_public_pairs) {
-				k_expand_pairs<<<apbf_grid(ctx, (size_t)n_cap * 8, 256, 32), 256, 0, st>>>(offsets, nbl, p.length, nb->pairs, nb->capacity);
-				APBF_LAUNCHED(ctx);
-			}
+			if (write_public) APBF_TRY(apbf_launch_expand_pairs(ctx, offsets, nbl, p.length, n_cap, nb->pairs, nb->capacity));
 		}
 		if (variant != EMIT_FUSED_MG) { // (fused + slabs has no two-pass form: an overflow there only raises the sticky flag)
 			A.ticket = misc + MW_EMIT_TICKET1;
@@ -1452,8 +1451,8 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 			APBF_LAUNCHED(ctx);
 		}
 	}
-	ctx->nbr_struct_pairs = nb->pairs;
-	ctx->nbr_struct_n_cap = n_cap;
+	// (the two-pass fill writes the public list itself; it only runs when the hit stream overflowed, i.e. when the list is clamped)
+	apbf_nbr_built(ctx, nb, n_cap, write_public || two_pass);
 
 	if (dbg) {
 		if (dbg->sorted_key) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->sorted_key, skeys, sizeof(uint32_t) * (size_t)nh_cap, cudaMemcpyDeviceToDevice, st));
@@ -1472,15 +1471,13 @@ int green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf
 	return APBF_OK;
 }
 
-} // namespace
-
 extern "C" {
 
 int apbf_neighborhood_green_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb,
                                   float range_scale, const float min_pos[3], const float max_pos[3], uint32_t res_log2,
                                   const apbf_search_debug* dbg)
 {
-	return green_search(ctx, fluid, range, nb, range_scale, min_pos, max_pos, res_log2, dbg, false, nullptr);
+	return apbf_green_search(ctx, fluid, range, nb, range_scale, min_pos, max_pos, res_log2, dbg, false, nullptr, true);
 }
 
 int apbf_neighborhood_green_spread_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighbors* nb, float range_scale,
@@ -1489,21 +1486,22 @@ int apbf_neighborhood_green_spread_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_
 {
 	if (!ctx) return APBF_ERR_INVALID;
 	APBF_REQUIRE(ctx, fluid);
-	return green_search(ctx, fluid, &fluid->kernel_width, nb, range_scale, min_pos, max_pos, res_log2, dbg, true, out_kw_fixed);
+	return apbf_green_search(ctx, fluid, &fluid->kernel_width, nb, range_scale, min_pos, max_pos, res_log2, dbg, true, out_kw_fixed, true);
 }
 
 } // extern "C"
 
-namespace {
 // neighborhood_binary_search::apply (neighborhood_binary_search.cpp:22-75); fuse_kw: followed by spread_kernel_width::apply on
 // the same lists with range == fluid->kernel_width (pool.cpp:83-89 with NEIGHBORHOOD_TYPE 3)
-int binary_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb, float range_scale,
-                  const apbf_search_debug* dbg, bool fuse_kw, uint32_t* out_kw_fixed)
+int apbf_binary_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb, float range_scale,
+                       const apbf_search_debug* dbg, bool fuse_kw, uint32_t* out_kw_fixed, bool write_public)
 {
 	if (!ctx) return APBF_ERR_INVALID;
 	APBF_REQUIRE(ctx, fluid && range && nb);
 	APBF_REQUIRE(ctx, nb->pairs && nb->length && fluid->particle.length && fluid->particle.hidden_length);
 	APBF_REQUIRE(ctx, !ctx->mg_enabled); // slabs partition by the grid key of the Green search
+	APBF_TRY(apbf_nbr_activate(ctx, nb));
+	ctx->nbr_valid = false;
 	apbf_particles& p = fluid->particle;
 	cudaStream_t st = ctx->stream;
 	const uint32_t nh_cap = p.hidden_capacity, n_cap = p.capacity;
@@ -1605,16 +1603,15 @@ int binary_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apb
 		apbf_prof_scope ps(ctx, PROF_EMIT_SCAN);
 		APBF_TRY(apbf_scan_u32(ctx, counts, offsets, p.length, n_cap, false, nb->length, nb->capacity, misc + MW_FLAGS,
 		                       misc + (fuse_kw ? MW_KEPT_PAIRS : MW_TOTAL_PAIRS)));
+		k_offsets_tail<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>(offsets, p.length, n_cap);
+		APBF_LAUNCHED(ctx);
 	}
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
 		if (!two_pass) {
 			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, nullptr, nbl, nb->capacity, misc, fuse_kw ? 1 : 0);
 			APBF_LAUNCHED(ctx);
-			if (!ctx->skip_public_pairs) {
-				k_expand_pairs<<<apbf_grid(ctx, (size_t)n_cap * 8, 256, 32), 256, 0, st>>>(offsets, nbl, p.length, nb->pairs, nb->capacity);
-				APBF_LAUNCHED(ctx);
-			}
+			if (write_public) APBF_TRY(apbf_launch_expand_pairs(ctx, offsets, nbl, p.length, n_cap, nb->pairs, nb->capacity));
 		}
 		if (!fuse_kw) { // (the fused form has no two-pass fill behind it: a stream overflow raises the sticky flag)
 			k_bsearch_emit<true><<<grid, 128, 0, st>>>(new_index, new_pos, c[0], c[1], c[2], new_range, p.length, range_scale, nullptr,
@@ -1622,8 +1619,7 @@ int binary_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apb
 			APBF_LAUNCHED(ctx);
 		}
 	}
-	ctx->nbr_struct_pairs = nb->pairs;
-	ctx->nbr_struct_n_cap = n_cap;
+	apbf_nbr_built(ctx, nb, n_cap, write_public || two_pass);
 	if (dbg) {
 		if (dbg->sorted_index) APBF_CUDA(ctx, cudaMemcpyAsync(dbg->sorted_index, sidx, sizeof(uint32_t) * (size_t)nh_cap, cudaMemcpyDeviceToDevice, st));
 		for (int s = 0; s < 3; s++)
@@ -1638,14 +1634,13 @@ int binary_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apb
 	}
 	return APBF_OK;
 }
-} // namespace
 
 extern "C" {
 
 int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, apbf_neighbors* nb,
                                           float range_scale, const apbf_search_debug* dbg)
 {
-	return binary_search(ctx, fluid, range, nb, range_scale, dbg, false, nullptr);
+	return apbf_binary_search(ctx, fluid, range, nb, range_scale, dbg, false, nullptr, true);
 }
 
 int apbf_neighborhood_binary_search_spread_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighbors* nb, float range_scale,
@@ -1653,7 +1648,7 @@ int apbf_neighborhood_binary_search_spread_apply(apbf_ctx* ctx, apbf_fluid* flui
 {
 	if (!ctx) return APBF_ERR_INVALID;
 	APBF_REQUIRE(ctx, fluid);
-	return binary_search(ctx, fluid, &fluid->kernel_width, nb, range_scale, dbg, true, out_kw_fixed);
+	return apbf_binary_search(ctx, fluid, &fluid->kernel_width, nb, range_scale, dbg, true, out_kw_fixed, true);
 }
 
 } // extern "C"

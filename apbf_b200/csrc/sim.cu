@@ -2,6 +2,7 @@
 //   [velocity_handling] -> neighbour search -> [spread_kernel_width] -> solverIterations x (box_collision, incompressibility)
 // plus host <-> device transfer of the lists (the reference-facing call with host buffers).
 #include "common.cuh"
+#include "neighbors.cuh"
 #include "solver.cuh"
 
 #include "sim.cuh"
@@ -115,7 +116,7 @@ void apbf_sim_destroy(apbf_sim* sim)
 	if (!sim) return;
 	cudaStreamSynchronize(sim->ctx->stream);
 	for (void* p : sim->owned) cudaFree(p);
-	if (sim->ctx->nbr_struct_pairs == sim->nb.pairs) sim->ctx->nbr_struct_pairs = nullptr;
+	apbf_nbr_forget(sim->ctx, sim->nb.pairs);
 	delete sim;
 }
 
@@ -198,16 +199,12 @@ int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
 		const float scale = unit_scale ? 1.0f : 1.5f;
 		// pool.cpp:83-89.  Green search followed by spread_kernel_width runs as one fused pass (same lists, pair for pair)
 		const bool fused = adaptive && !ctx->mg_enabled && !sim->no_fuse;
-		ctx->skip_public_pairs = true; // nothing reads the (id, idN) list: the sweeps and a separate spread work on NB + offsets
-		if (c.use_binary_search && fused)
-			APBF_TRY(apbf_neighborhood_binary_search_spread_apply(ctx, &sim->fluid, &sim->nb, scale, dbg, nullptr));
-		else if (c.use_binary_search)                                                 // pool.cpp:83-84
-			APBF_TRY(apbf_neighborhood_binary_search_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, dbg));
-		else if (fused)
-			APBF_TRY(apbf_neighborhood_green_spread_apply(ctx, &sim->fluid, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, dbg, nullptr));
+		// Nothing reads the public (id, idN) list between the search and the sweeps, which work on NB + offsets: the search skips
+		// its 8-byte stores (write_public = false) and apbf_sim_neighbors() writes the list on demand.
+		if (c.use_binary_search)                                                      // pool.cpp:83-84
+			APBF_TRY(apbf_binary_search(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, dbg, fused, nullptr, false));
 		else
-			APBF_TRY(apbf_neighborhood_green_apply(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, dbg));
-		ctx->skip_public_pairs = false;
+			APBF_TRY(apbf_green_search(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, scale, c.min_pos, c.max_pos, c.res_log2, dbg, fused, nullptr, false));
 		apbf_sim_swap_buffers(sim);
 		if (transfers) // the transfers' source / target lists share the hidden particle data (pool.cpp:18-19)
 			APBF_TRY(apbf_transfers_follow_reorder(ctx, &sim->tr, sim->sorted_index, sim->fluid.particle.hidden_length, c.particle_capacity));
@@ -239,6 +236,8 @@ int apbf_sim_fluid(apbf_sim* sim, apbf_fluid* out)
 int apbf_sim_neighbors(apbf_sim* sim, apbf_neighbors* out)
 {
 	if (!sim || !out) return APBF_ERR_INVALID;
+	// the whole-scene substep keeps only the grouped structure; whoever asks for the list gets the (id, idN) pairs written now
+	APBF_TRY(apbf_nbr_materialize(sim->ctx, sim->fluid.particle.length, sim->cfg.particle_capacity, &sim->nb));
 	*out = sim->nb;
 	return APBF_OK;
 }

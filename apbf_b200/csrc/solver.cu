@@ -314,10 +314,9 @@ int apbf_spread_kernel_width_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighb
 	APBF_REQUIRE(ctx, fluid && nb);
 	apbf_particles& p = fluid->particle;
 	APBF_REQUIRE(ctx, p.index_list.data && p.length && p.position.data && p.radius.data && fluid->kernel_width.data && fluid->target_radius.data);
-	if (!apbf_nbr_struct_valid(ctx, nb))
-		return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, "neighbour list was not produced by this context's search", __FILE__, __LINE__);
 	const uint32_t n_cap = p.capacity;
 	if (n_cap == 0) return APBF_OK;
+	APBF_TRY(apbf_nbr_ensure(ctx, fluid, nb)); // any pair list (spread_kernel_width.h:10): foreign ones get their structure built here
 	cudaStream_t st = ctx->stream;
 	kw_args A;
 	memset(&A, 0, sizeof A);
@@ -371,6 +370,7 @@ int apbf_spread_kernel_width_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_neighb
 	APBF_LAUNCHED(ctx);
 	std::swap(ctx->scratch[SLOT_NB], ctx->scratch[SLOT_NB_TMP]);
 	std::swap(ctx->scratch[SLOT_OFFSETS], ctx->scratch[SLOT_KEEP_OFFSETS]);
+	apbf_nbr_built(ctx, nb, n_cap, true);
 	return APBF_OK;
 }
 
@@ -381,10 +381,9 @@ int apbf_update_transfers_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_nei
 	apbf_particles& p = fluid->particle;
 	APBF_REQUIRE(ctx, p.index_list.data && p.length && p.position.data && p.radius.data && fluid->boundary_distance.data &&
 	                      fluid->target_radius.data && fluid->boundariness.data);
-	if (!apbf_nbr_struct_valid(ctx, nb))
-		return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, "neighbour list was not produced by this context's search", __FILE__, __LINE__);
 	const uint32_t n_cap = p.capacity;
 	if (n_cap == 0) return APBF_OK;
+	APBF_TRY(apbf_nbr_ensure(ctx, fluid, nb)); // any pair list (update_transfers.h)
 	cudaStream_t st = ctx->stream;
 	apbf_prof_scope ps(ctx, PROF_UPDATE_TRANSFERS);
 	ut_args A;

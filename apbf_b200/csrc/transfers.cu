@@ -514,6 +514,8 @@ int apbf_update_transfers_split_merge_apply(apbf_ctx* ctx, apbf_fluid* fluid, co
 	APBF_LAUNCHED(ctx);
 	k_tm_lengths<<<1, 1, 0, st>>>(words, transfers->length, p.length, n_cap, p.hidden_length);
 	APBF_LAUNCHED(ctx);
+	// (the lists grew by the copies: they have no pairs -- the searches leave empty segments up to the capacity, k_offsets_tail --
+	// and the copies' index entries keep an identity index list an identity)
 	return APBF_OK;
 }
 
@@ -601,6 +603,10 @@ int apbf_particle_transfer_apply(apbf_ctx* ctx, apbf_fluid* fluid, apbf_transfer
 	if (out_hidden_edit) APBF_CUDA(ctx, cudaMemcpyAsync(out_hidden_edit, perm_h, w * nh_cap, cudaMemcpyDeviceToDevice, st));
 	k_pt_lengths<<<1, 1, 0, st>>>(words, p.hidden_length, p.length, transfers->length);
 	APBF_LAUNCHED(ctx);
+	// ids and hidden slots mean something else now: no neighbour structure describes these particles any more, and the cached
+	// "index list is the identity" flag of the last search is off until the next search re-derives it
+	apbf_nbr_particles_changed(ctx);
+	APBF_CUDA(ctx, cudaMemsetAsync(ctx->misc() + MW_IDENTITY, 0, 4, st));
 	return APBF_OK;
 }
 

@@ -117,6 +117,15 @@ class SlabDomain:
             # exchange at 4 ranks -- the exchanges are bound by NCCL's latency, not by the host calls around them.  Off by default.
             backend.init_comm(comm)
 
+    def n_owned(self):
+        return self.n_own
+
+    def reset(self, n_owned, gid_base=0):
+        """the lists were uploaded afresh: this rank owns the first n_owned entries again (global ids must be re-derived by
+        the caller if the bricks are not the initial ones)"""
+        self.n_own, self.gid_base = int(n_owned), int(gid_base)
+        self.b.set_counts(self.n_own, self.n_own, self.gid_base)
+
     # ---- one exchange of `what` for the current send lists / ghost slots ------------------------------------------------------
     def _refresh_ghosts(self, what):
         if self.world == 1:

@@ -141,7 +141,7 @@ def waterfall_boxes(mn, mx, r, dims=3, wall=4.0):
     return bmin, bmax
 
 
-def waterfall(nx=252, ny=252, nz=252, r=1.0, jitter=0.05, seed=17, adaptive=False):
+def waterfall(nx=252, ny=252, nz=252, r=1.0, jitter=0.05, seed=17, adaptive=False, res_log2=None):
     """configs[3]: the waterfall scene (source/waterfall.cpp:6-48) -- a block of fluid filling the top pool, 11 collision boxes
     (the user opens the pool at run time in the reference; here it stays closed, what counts is the box_collision load).
     252^3 = 16 003 008 particles at full size."""
@@ -151,9 +151,10 @@ def waterfall(nx=252, ny=252, nz=252, r=1.0, jitter=0.05, seed=17, adaptive=Fals
     margin = 6.0 * r + 4.0
     lo = [float(v - margin) for v in mn]
     hi = [float(v + margin) for v in ext + np.array([0, 2 * r, 0], np.float32)]
+    if res_log2 is None:   # cells of about one kernel width (4r): larger cells only add candidates to every distance-test batch
+        res_log2 = _res_for(max(h - l for l, h in zip(lo, hi)), 3.0 * r)
     sc = Scene(name=f"waterfall_{nx}x{ny}x{nz}", dims=3, arrays=shuffle_state(arrays, seed), min_pos=tuple(lo), max_pos=tuple(hi),
-               res_log2=_res_for(max(h - l for l, h in zip(lo, hi)), 4.5 * r), basic_pbf=not adaptive, solver_iterations=4,
-               smallest_target_radius=r)
+               res_log2=res_log2, basic_pbf=not adaptive, solver_iterations=4, smallest_target_radius=r)
     sc.box_min, sc.box_max = waterfall_boxes(mn, ext, r, 3)
     return sc
 

@@ -248,6 +248,22 @@ int apbf_neighborhood_binary_search_spread_apply(apbf_ctx* ctx, apbf_fluid* flui
 /* pbd::neighborhood_binary_search::set_data(...).set_range_scale(s).apply() (source/neighborhood_binary_search.cpp:22-75) */
 int apbf_neighborhood_binary_search_apply(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range,
                                           apbf_neighbors* neighbors, float range_scale, const apbf_search_debug* debug);
+/* ---- operators over a pair list: ANY pbd::neighbors list (source/incompressibility.h:11, spread_kernel_width.h:10,
+ * update_transfers.h) -- written by a search of this context, by another context, by the caller, copied, appended to, edited.
+ * The sweeps run on a grouped form of the list (CSR offsets + 4 bytes per pair) that a search of this context leaves behind for
+ * the buffer it filled; for every other list that form is built on the device from the (id, idN) pairs at the first use (a
+ * stable sort by id; pairs with an id beyond the particle list are dropped, duplicates are kept) and remembered per pair
+ * buffer -- a context holds any number of lists.  Library calls that write into a pair buffer (apbf_copy_bytes, apbf_append_list,
+ * apbf_copy_scattered_read, ...) or recycle it (apbf_buffer_acquire / _release) mark what is remembered as out of date.
+ * A caller that rewrites a pair buffer with its OWN kernels says so with apbf_neighbors_invalidate (pbd::gpu_list<8>::write()
+ * in include/apbf_pbd.hpp does). */
+/* the pair list at nb->pairs was written by somebody else since an operator last saw it */
+int apbf_neighbors_invalidate(apbf_ctx* ctx, const apbf_neighbors* nb);
+/* the buffer at nb->pairs is about to be freed or reused for something else */
+int apbf_neighbors_release(apbf_ctx* ctx, const apbf_neighbors* nb);
+/* build (or look up) the grouped form now instead of inside the next operator; out_pair_offsets (optional, device,
+ * [capacity + 1]): pairs of id occupy [offsets[id], offsets[id + 1]) of the list sorted by id */
+int apbf_neighbors_prepare(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors* nb, uint32_t* out_pair_offsets);
 /* pbd::incompressibility::set_data(fluid, neighbors).apply() (source/incompressibility.cpp:12-45).  Works on the
  * arrays' `data` buffers in place.  Optional outputs (may be NULL): lambda[capacity], incomp_data[capacity*8]
  * ({ivec3 gradSum; uint density; uint sqGradSum; pad x3}, incompressibility_0.comp:6-13). */
@@ -359,10 +375,13 @@ void apbf_sim_destroy(apbf_sim* sim);
 int  apbf_sim_upload(apbf_sim* sim, const apbf_host_state* host);
 /* device -> host copy (members that are NULL are skipped); synchronises */
 int  apbf_sim_download(apbf_sim* sim, apbf_host_state* host);
-/* n_substeps x pool::update: [velocity_handling] -> neighbour search -> [spread_kernel_width] ->
- * solver_iterations x (box_collision, incompressibility).  Fully asynchronous. */
+/* n_substeps x pool::update (pool.cpp:67-106): [velocity_handling] -> [particle_transfer, cfg.transfers] -> [kernel width from
+ * the boundary distance, cfg.update_transfers] -> neighbour search -> [spread_kernel_width] -> solver_iterations x
+ * (box_collision, incompressibility) -> [update_transfers, with the merge / split decisions if cfg.transfers].  Fully asynchronous.
+ * The search keeps the pair list in its grouped form only; apbf_sim_neighbors() writes the (id, idN) pairs when asked. */
 int  apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps);
-/* views of the device-resident lists for callers that want to run single operators on them */
+/* views of the device-resident lists for callers that want to run single operators on them (apbf_sim_neighbors enqueues the
+ * kernel that writes the public (id, idN) list if the last substep has not) */
 int  apbf_sim_fluid(apbf_sim* sim, apbf_fluid* out_fluid);
 int  apbf_sim_neighbors(apbf_sim* sim, apbf_neighbors* out_neighbors);
 /* pair count of the last search (device -> host read, synchronises) */

@@ -238,8 +238,17 @@ namespace pbd
 			}
 			return data;
 		}
-		/// write access: makes the storage unique and at least requested_length() long, keeping the content
-		gpu_list& write() { if (mRequestedLength != 0 || mData) { if (!unique_and_large_enough(mRequestedLength)) fresh_storage(mRequestedLength, true); } return *this; }
+		/// write access: makes the storage unique and at least requested_length() long, keeping the content.  For a pair list
+		/// (Stride 8) the caller may be about to rewrite pairs with kernels of its own: whatever the operators remember about
+		/// this buffer is out of date from here on (they rebuild it from the pairs at their next apply()).
+		gpu_list& write()
+		{
+			make_unique();
+			if (Stride == 8 && mData) { apbf_neighbors nb{ mData->mBuffer.template as<uint32_t>(), mData->mLength.template as<uint32_t>(), capacity() }; apbf_neighbors_invalidate(shader_provider::context(), &nb); }
+			return *this;
+		}
+		/// what write() does to the storage, without telling the operators that the content changes (used by the operators themselves)
+		gpu_list& make_unique() { if (mRequestedLength != 0 || mData) { if (!unique_and_large_enough(mRequestedLength)) fresh_storage(mRequestedLength, true); } return *this; }
 
 		/// gpu_list<4> only: interprets the values as uint and sorts them ascending; the owner follows the permutation
 		void sort(size_t aValueUpperBound = std::numeric_limits<uint32_t>::max())
@@ -596,7 +605,7 @@ namespace pbd
 		}
 		inline apbf_neighbors neighbors_view(neighbors& n)
 		{
-			n.write();
+			n.make_unique();
 			if (n.empty()) throw std::runtime_error("the neighbour list has no requested length");
 			return apbf_neighbors{ n.buffer().as<uint32_t>(), n.length().as<uint32_t>(), n.capacity() };
 		}

@@ -353,43 +353,74 @@ static inline float distance3(const float a[3], const float b[3])
 	return length3(d);
 }
 
+/* neighborhood_green.comp:50-87 for ONE invocation (particle id).  out == NULL counts; otherwise the pairs are written at
+ * out[2 * (base + k)] for k < found while base + k < cap (neighbor_add.glsl:23-24 clamps the list at its capacity). */
+static uint32_t green_one(const uint32_t* index_list, const int32_t* pos4, const float* range, const uint32_t* cell_start,
+                          const uint32_t* cell_end, uint32_t id, float range_scale, const float mn[3], const float mx[3],
+                          uint32_t res, int D, uint32_t* out, uint32_t base, uint32_t cap)
+{
+	float r = range[id] * range_scale;
+	uint32_t idx = index_list[id];
+	float pos[3], lo[3], hi[3];
+	uint32_t found = 0u;
+	posf(pos4, idx, pos);
+	for (int d = 0; d < 3; d++) { lo[d] = pos[d] - r; hi[d] = pos[d] + r; }
+	uint32_t gmin[3], gmax[3];
+	map_to_grid(lo, mn, mx, res, gmin);
+	map_to_grid(hi, mn, mx, res, gmax);
+	if (D < 2) { gmin[1] = gmax[1] = 0u; }
+	if (D < 3) { gmin[2] = gmax[2] = 0u; }
+	/* the reference's cell walk: x fastest, then y, then z (neighborhood_green.comp:69-79) */
+	for (uint32_t cz = gmin[2]; ; cz++) {
+		for (uint32_t cy = gmin[1]; ; cy++) {
+			for (uint32_t cx = gmin[0]; ; cx++) {
+				uint32_t cell[3] = { cx, cy, cz };
+				uint32_t h = zhash(cell, res, D);
+				for (uint32_t idN = cell_start[h]; idN < cell_end[h]; idN++) {
+					float posN[3];
+					posf(pos4, index_list[idN], posN);
+					if (id == idN || distance3(pos, posN) > r) continue;
+					if (out && base + found < cap) { out[2 * (size_t)(base + found)] = id; out[2 * (size_t)(base + found) + 1] = idN; }
+					found++;
+				}
+				if (cx >= gmax[0]) break;
+			}
+			if (cy >= gmax[1]) break;
+		}
+		if (cz >= gmax[2]) break;
+	}
+	return found;
+}
+
+/* One shader invocation per particle appends its pairs with an atomic counter (neighbor_add.glsl:11-25): the order of the list
+ * across invocations is whatever the schedule gives.  The restatement returns the order of a sequential run (ascending id, each
+ * id's pairs in its own discovery order).  With more than one host thread the invocations run in parallel in two passes --
+ * count per id, running sum, every id writes its own segment -- which yields exactly that list. */
 uint32_t orc_neighborhood_green_pairs(const uint32_t* index_list, const int32_t* pos4, const float* range,
                                       const uint32_t* cell_start, const uint32_t* cell_end, uint32_t n,
                                       float range_scale, const float mn[3], const float mx[3],
                                       uint32_t res, int D, uint32_t* out_pairs, uint32_t cap)
 { /* neighborhood_green.comp:50-87 */
-	pair_sink sink = { out_pairs, cap, 0u };
-	for (uint32_t id = 0; id < n; id++) {
-		float r = range[id] * range_scale;
-		uint32_t idx = index_list[id];
-		float pos[3], lo[3], hi[3];
-		posf(pos4, idx, pos);
-		for (int d = 0; d < 3; d++) { lo[d] = pos[d] - r; hi[d] = pos[d] + r; }
-		uint32_t gmin[3], gmax[3];
-		map_to_grid(lo, mn, mx, res, gmin);
-		map_to_grid(hi, mn, mx, res, gmax);
-		if (D < 2) { gmin[1] = gmax[1] = 0u; }
-		if (D < 3) { gmin[2] = gmax[2] = 0u; }
-		/* the reference's cell walk: x fastest, then y, then z (neighborhood_green.comp:69-79) */
-		for (uint32_t cz = gmin[2]; ; cz++) {
-			for (uint32_t cy = gmin[1]; ; cy++) {
-				for (uint32_t cx = gmin[0]; ; cx++) {
-					uint32_t cell[3] = { cx, cy, cz };
-					uint32_t h = zhash(cell, res, D);
-					for (uint32_t idN = cell_start[h]; idN < cell_end[h]; idN++) {
-						float posN[3];
-						posf(pos4, index_list[idN], posN);
-						if (id == idN || distance3(pos, posN) > r) continue;
-						add_pair(&sink, id, idN);
-					}
-					if (cx >= gmax[0]) break;
-				}
-				if (cy >= gmax[1]) break;
-			}
-			if (cz >= gmax[2]) break;
+	if (g_threads <= 1) {
+		uint32_t len = 0u;
+		for (uint32_t id = 0; id < n; id++) {
+			uint32_t f = green_one(index_list, pos4, range, cell_start, cell_end, id, range_scale, mn, mx, res, D, out_pairs, len, cap);
+			len = (f > cap - len) ? cap : len + f; /* saturates at the capacity like the clamp */
 		}
+		return len;
 	}
-	return sink.len;
+	uint64_t* off = (uint64_t*)malloc(sizeof(uint64_t) * ((size_t)n + 1));
+#pragma omp parallel for num_threads(g_threads) schedule(dynamic, 256)
+	for (uint32_t id = 0; id < n; id++)
+		off[id + 1] = green_one(index_list, pos4, range, cell_start, cell_end, id, range_scale, mn, mx, res, D, NULL, 0u, 0u);
+	off[0] = 0u;
+	for (uint32_t id = 0; id < n; id++) off[id + 1] += off[id];
+#pragma omp parallel for num_threads(g_threads) schedule(dynamic, 256)
+	for (uint32_t id = 0; id < n; id++)
+		if (off[id] < cap) green_one(index_list, pos4, range, cell_start, cell_end, id, range_scale, mn, mx, res, D, out_pairs, (uint32_t)off[id], cap);
+	uint32_t len = off[n] > cap ? cap : (uint32_t)off[n];
+	free(off);
+	return len;
 }
 
 uint32_t orc_neighborhood_brute_force_pairs(const uint32_t* index_list, const int32_t* pos4, const float* range,
@@ -464,52 +495,78 @@ static uint32_t lower_bound96(const uint32_t* c0, const uint32_t* c1, const uint
 	return lo;
 }
 
+/* neighborhood_binary_search.comp:166-276 for ONE invocation; out == NULL counts (see green_one) */
+static uint32_t bsearch_one(const uint32_t* index_list, const int32_t* pos4, const uint32_t* c0, const uint32_t* c1, const uint32_t* c2,
+                            const float* range, uint32_t n, uint32_t id, float range_scale, uint32_t* out, uint32_t base, uint32_t cap)
+{
+	const u96 xMask3 = u96_make(011111111111u, 022222222222u, 04444444444u);
+	const u96 yMask3 = u96_make(022222222222u, 04444444444u, 011111111111u);
+	const u96 zMask3 = u96_make(04444444444u, 011111111111u, 022222222222u);
+	uint32_t found = 0u;
+	float r = range[id] * range_scale;
+	uint32_t idx = index_list[id];
+	const int32_t* iPos = &pos4[4 * idx];
+	u96 code;
+	encode96(iPos, code.v);
+	uint32_t digits = f2u(ceilf(log2f(r * R_POS))) * 3u;
+	u96 mask;
+	mask.v[0] = (digits < 32u ? 1u << digits : 0u) - 1u;
+	mask.v[1] = (digits < 64u ? 1u << ((digits > 32u ? digits : 32u) - 32u) : 0u) - 1u;
+	mask.v[2] = (digits < 96u ? 1u << ((digits > 64u ? digits : 64u) - 64u) : 0u) - 1u;
+	u96 center = u96_make(code.v[0] - (code.v[0] & mask.v[0]), code.v[1] - (code.v[1] & mask.v[1]), code.v[2] - (code.v[2] & mask.v[2]));
+	u96 step = plus96(mask, u96_make(1u, 0u, 0u));
+	u96 xs[3], ys[3], zs[3];
+	xs[0] = and96(minus96(and96(center, xMask3), step), xMask3);
+	xs[2] = and96(plus96(or96(center, not96(xMask3)), step), xMask3);
+	ys[0] = and96(minus96(and96(center, yMask3), leftShift96(step, 1u)), yMask3);
+	ys[2] = and96(plus96(or96(center, not96(yMask3)), leftShift96(step, 1u)), yMask3);
+	zs[0] = and96(minus96(and96(center, zMask3), leftShift96(step, 2u)), zMask3);
+	zs[2] = and96(plus96(or96(center, not96(zMask3)), leftShift96(step, 2u)), zMask3);
+	xs[1] = and96(center, xMask3);
+	ys[1] = and96(center, yMask3);
+	zs[1] = and96(center, zMask3);
+	float pos[3] = { (float)iPos[0] / R_POS, (float)iPos[1] / R_POS, (float)iPos[2] / R_POS };
+	for (int cz = 0; cz < 3; cz++) for (int cy = 0; cy < 3; cy++) for (int cx = 0; cx < 3; cx++) {
+		u96 cellCode = or96(or96(xs[cx], ys[cy]), zs[cz]);
+		u96 cellLast = or96(cellCode, mask);
+		uint32_t idN = lower_bound96(c0, c1, c2, n, cellCode);
+		for (; idN < n; idN++) {
+			if (greater96(u96_make(c0[idN], c1[idN], c2[idN]), cellLast)) break;
+			float posN[3];
+			posf(pos4, index_list[idN], posN);
+			if (id != idN && distance3(pos, posN) <= r) {
+				if (out && base + found < cap) { out[2 * (size_t)(base + found)] = id; out[2 * (size_t)(base + found) + 1] = idN; }
+				found++;
+			}
+		}
+	}
+	return found;
+}
+
 uint32_t orc_neighborhood_binary_search_pairs(const uint32_t* index_list, const int32_t* pos4,
                                               const uint32_t* c0, const uint32_t* c1, const uint32_t* c2,
                                               const float* range, uint32_t n, float range_scale,
                                               uint32_t* out_pairs, uint32_t cap)
-{ /* neighborhood_binary_search.comp:166-276 (DIMENSIONS forced to 3, :4-5) */
-	pair_sink sink = { out_pairs, cap, 0u };
-	const u96 xMask3 = u96_make(011111111111u, 022222222222u, 04444444444u);
-	const u96 yMask3 = u96_make(022222222222u, 04444444444u, 011111111111u);
-	const u96 zMask3 = u96_make(04444444444u, 011111111111u, 022222222222u);
-	for (uint32_t id = 0; id < n; id++) {
-		float r = range[id] * range_scale;
-		uint32_t idx = index_list[id];
-		const int32_t* iPos = &pos4[4 * idx];
-		u96 code;
-		encode96(iPos, code.v);
-		uint32_t digits = f2u(ceilf(log2f(r * R_POS))) * 3u;
-		u96 mask;
-		mask.v[0] = (digits < 32u ? 1u << digits : 0u) - 1u;
-		mask.v[1] = (digits < 64u ? 1u << ((digits > 32u ? digits : 32u) - 32u) : 0u) - 1u;
-		mask.v[2] = (digits < 96u ? 1u << ((digits > 64u ? digits : 64u) - 64u) : 0u) - 1u;
-		u96 center = u96_make(code.v[0] - (code.v[0] & mask.v[0]), code.v[1] - (code.v[1] & mask.v[1]), code.v[2] - (code.v[2] & mask.v[2]));
-		u96 step = plus96(mask, u96_make(1u, 0u, 0u));
-		u96 xs[3], ys[3], zs[3];
-		xs[0] = and96(minus96(and96(center, xMask3), step), xMask3);
-		xs[2] = and96(plus96(or96(center, not96(xMask3)), step), xMask3);
-		ys[0] = and96(minus96(and96(center, yMask3), leftShift96(step, 1u)), yMask3);
-		ys[2] = and96(plus96(or96(center, not96(yMask3)), leftShift96(step, 1u)), yMask3);
-		zs[0] = and96(minus96(and96(center, zMask3), leftShift96(step, 2u)), zMask3);
-		zs[2] = and96(plus96(or96(center, not96(zMask3)), leftShift96(step, 2u)), zMask3);
-		xs[1] = and96(center, xMask3);
-		ys[1] = and96(center, yMask3);
-		zs[1] = and96(center, zMask3);
-		float pos[3] = { (float)iPos[0] / R_POS, (float)iPos[1] / R_POS, (float)iPos[2] / R_POS };
-		for (int cz = 0; cz < 3; cz++) for (int cy = 0; cy < 3; cy++) for (int cx = 0; cx < 3; cx++) {
-			u96 cellCode = or96(or96(xs[cx], ys[cy]), zs[cz]);
-			u96 cellLast = or96(cellCode, mask);
-			uint32_t idN = lower_bound96(c0, c1, c2, n, cellCode);
-			for (; idN < n; idN++) {
-				if (greater96(u96_make(c0[idN], c1[idN], c2[idN]), cellLast)) break;
-				float posN[3];
-				posf(pos4, index_list[idN], posN);
-				if (id != idN && distance3(pos, posN) <= r) add_pair(&sink, id, idN);
-			}
+{ /* neighborhood_binary_search.comp:166-276 (DIMENSIONS forced to 3, :4-5); list order as in orc_neighborhood_green_pairs */
+	if (g_threads <= 1) {
+		uint32_t len = 0u;
+		for (uint32_t id = 0; id < n; id++) {
+			uint32_t f = bsearch_one(index_list, pos4, c0, c1, c2, range, n, id, range_scale, out_pairs, len, cap);
+			len = (f > cap - len) ? cap : len + f;
 		}
+		return len;
 	}
-	return sink.len;
+	uint64_t* off = (uint64_t*)malloc(sizeof(uint64_t) * ((size_t)n + 1));
+#pragma omp parallel for num_threads(g_threads) schedule(dynamic, 256)
+	for (uint32_t id = 0; id < n; id++) off[id + 1] = bsearch_one(index_list, pos4, c0, c1, c2, range, n, id, range_scale, NULL, 0u, 0u);
+	off[0] = 0u;
+	for (uint32_t id = 0; id < n; id++) off[id + 1] += off[id];
+#pragma omp parallel for num_threads(g_threads) schedule(dynamic, 256)
+	for (uint32_t id = 0; id < n; id++)
+		if (off[id] < cap) bsearch_one(index_list, pos4, c0, c1, c2, range, n, id, range_scale, out_pairs, (uint32_t)off[id], cap);
+	uint32_t len = off[n] > cap ? cap : (uint32_t)off[n];
+	free(off);
+	return len;
 }
 
 /* ---------------------------------------------------------------------------------- */
@@ -811,8 +868,13 @@ uint32_t orc_spread_kernel_width_apply(orc_state* st, const orc_settings* s, uin
 		kwfx[id] = f2u(orig * ORC_KERNEL_WIDTH_RESOLUTION);
 	}
 	uint32_t kept = 0u;
-	for (uint32_t e = 0; e < n_pairs; e++) { /* kernel_width.comp:27-61; sequential so the kept order is the input order */
-		uint32_t n0 = pairs[2 * e], n1 = pairs[2 * e + 1];
+	/* kernel_width.comp:27-61, one invocation per pair.  The atomicMax result does not depend on the order; the kept pairs
+	 * are returned in the order of the input list (the reference appends them in schedule order).  Parallel form: keep flags,
+	 * running sum, scatter -- the same list as the sequential loop. */
+	uint8_t* keep = (uint8_t*)malloc(n_pairs ? n_pairs : 1);
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+	for (uint32_t e = 0; e < n_pairs; e++) {
+		uint32_t n0 = pairs[2 * (size_t)e], n1 = pairs[2 * (size_t)e + 1];
 		uint32_t idx = st->index_list[n0], idxN = st->index_list[n1];
 		const int32_t* pos = &st->position[4 * idx];
 		const int32_t* posN = &st->position[4 * idxN];
@@ -827,9 +889,13 @@ uint32_t orc_spread_kernel_width_apply(orc_state* st, const orc_settings* s, uin
 		float distanceFromKernel = dist - orig;
 		float influence = fmaxf_(0.0f, 1.0f - fmaxf_(0.0f, distanceFromKernel / (orig * ORC_KERNEL_WIDTH_PROPAGATION_FACTOR)));
 		uint32_t v = f2u(orig * influence * ORC_KERNEL_WIDTH_RESOLUTION);
-		if (v > kwfx[n1]) kwfx[n1] = v;
-		if (dist <= cutoff) { pairs[2 * kept] = n0; pairs[2 * kept + 1] = n1; kept++; }
+		uint32_t cur = __atomic_load_n(&kwfx[n1], __ATOMIC_RELAXED);           /* atomicMax, kernel_width.comp:53 */
+		while (v > cur && !__atomic_compare_exchange_n(&kwfx[n1], &cur, v, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+		keep[e] = dist <= cutoff;                                               /* :57 */
 	}
+	for (uint32_t e = 0; e < n_pairs; e++)
+		if (keep[e]) { pairs[2 * (size_t)kept] = pairs[2 * (size_t)e]; pairs[2 * (size_t)kept + 1] = pairs[2 * (size_t)e + 1]; kept++; }
+	free(keep);
 	for (uint32_t id = 0; id < n; id++) { /* uint_to_float_but_gradual.comp:29-39; mLowerBound = -inf (shader_provider.h:26) */
 		float value = (float)kwfx[id] * (1.0f / ORC_KERNEL_WIDTH_RESOLUTION);
 		value = move_towards_rel(st->kernel_width[id], value, s->mKernelWidthAdaptionSpeed);
@@ -866,17 +932,29 @@ void orc_update_transfers_apply(orc_state* st, const orc_settings* s, const uint
 		min_nd[id] = 0xFFFFFFFFu;
 		nearest[id] = 0xFFFFFFFFu;                                    /* not initialised by the reference */
 	}
-	for (uint32_t e = 0; e < n_pairs; e++) {                          /* find_split_and_merge_1.comp:21-34 */
-		uint32_t n0 = pairs[2 * e], n1 = pairs[2 * e + 1];
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+	for (uint32_t e = 0; e < n_pairs; e++) {                          /* find_split_and_merge_1.comp:21-34 (atomicMin: any order) */
+		uint32_t n0 = pairs[2 * (size_t)e], n1 = pairs[2 * (size_t)e + 1];
 		uint32_t dist = pair_dist_units(st, n0, n1);
 		uint32_t v = old_bd[n1] + dist;                               /* uint arithmetic: wraps like the shader */
-		if (v < st->boundary_distance[n0]) st->boundary_distance[n0] = v;
-		if (dist < min_nd[n0]) min_nd[n0] = dist;
+		uint32_t cur = __atomic_load_n(&st->boundary_distance[n0], __ATOMIC_RELAXED);
+		while (v < cur && !__atomic_compare_exchange_n(&st->boundary_distance[n0], &cur, v, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+		cur = __atomic_load_n(&min_nd[n0], __ATOMIC_RELAXED);
+		while (dist < cur && !__atomic_compare_exchange_n(&min_nd[n0], &cur, dist, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
 	}
-	for (uint32_t e = 0; e < n_pairs; e++) {                          /* find_split_and_merge_2.comp:21-37 */
-		uint32_t n0 = pairs[2 * e], n1 = pairs[2 * e + 1];
-		/* every pair at the minimum distance writes; in list order the last one stays */
-		if (pair_dist_units(st, n0, n1) == min_nd[n0]) nearest[n0] = n1;
+	{ /* find_split_and_merge_2.comp:21-37: every pair at the minimum distance writes; in list order the last one stays.
+	   * Parallel form: the largest pair index at the minimum distance per id, then its idN. */
+		uint32_t* last = (uint32_t*)malloc(sizeof(uint32_t) * (n ? n : 1));
+		for (uint32_t id = 0; id < n; id++) last[id] = 0xFFFFFFFFu;
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+		for (uint32_t e = 0; e < n_pairs; e++) {
+			uint32_t n0 = pairs[2 * (size_t)e], n1 = pairs[2 * (size_t)e + 1];
+			if (pair_dist_units(st, n0, n1) != min_nd[n0]) continue;
+			uint32_t cur = __atomic_load_n(&last[n0], __ATOMIC_RELAXED);
+			while ((cur == 0xFFFFFFFFu || e > cur) && !__atomic_compare_exchange_n(&last[n0], &cur, e, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+		}
+		for (uint32_t id = 0; id < n; id++) if (last[id] != 0xFFFFFFFFu) nearest[id] = pairs[2 * (size_t)last[id] + 1];
+		free(last);
 	}
 	for (uint32_t id = 0; id < n; id++) {                             /* find_split_and_merge_3.comp:55-84 */
 		uint32_t idx = st->index_list[id];

@@ -1,0 +1,168 @@
+"""Parity checker (TEST INFRASTRUCTURE, like everything under oracle/): one substep of a scene on the CUDA path -- called
+through the C-ABI via the Python front-end -- next to the CPU oracle on the same state, quantity by quantity.
+
+Used by tests/test_parity_at_size.py (asserts the bars) and by bench.py's cpu_baseline leg (prints the numbers as the
+`parity` block of the bench line, on a bounded sample of the workload being timed).  Never on a product path.
+
+Bars:
+  * keys, sort order, cell tables, re-ordered lists, pair list (compared IN ORDER, hence also as sets), fixed-point kernel
+    widths, kept pairs after the prune, new kernel widths: bit-exact;
+  * integer accumulators of incompressibility_1 (units of 2^-18): |d| <= 1 unit + 1e-5 relative -- one unit is what a last-bit
+    difference between CUDA's and glibc's expf / the reciprocal mass does to ONE truncated pair contribution;
+  * lambda: 1e-5 relative wherever the accumulators agree exactly;
+  * position shift of one iteration: 8 units of 2^-18 + 1e-5 of the largest shift.
+"""
+import time
+
+import numpy as np
+
+from . import oracle as orc
+
+
+def _acc_report(ga, ea):
+    out = {}
+    for k in ("density", "sq_grad_sum"):
+        d = np.abs(ga[k].astype(np.int64) - ea[k].astype(np.int64))
+        out[k] = {"max_units": int(d.max()), "frac_equal": float((d == 0).mean()),
+                  "max_rel": float((d / np.maximum(ea[k].astype(np.float64), 1.0)).max()),
+                  "within_bar": bool(np.all(d <= 1 + 1e-5 * ea[k].astype(np.float64)))}
+    d = np.abs(ga["grad_sum"].astype(np.int64) - ea["grad_sum"].astype(np.int64))
+    out["grad_sum"] = {"max_units": int(d.max()), "frac_equal": float((d == 0).all(axis=1).mean()),
+                       "within_bar": bool(np.all(d <= 1 + 1e-5 * np.abs(ea["grad_sum"]).max()))}
+    same = (ga["density"] == ea["density"]) & (ga["sq_grad_sum"] == ea["sq_grad_sum"]) & np.all(ga["grad_sum"] == ea["grad_sum"], axis=1)
+    rel = np.abs(ga["lam"] - ea["lam"]) / np.maximum(np.abs(ea["lam"]), 1e-30)
+    out["lambda"] = {"max_rel_where_accumulators_equal": float(rel[same].max()) if same.any() else 0.0, "max_rel_all": float(rel.max()),
+                     "frac_bit_equal": float((ga["lam"] == ea["lam"]).mean()), "frac_accumulators_equal": float(same.mean())}
+    out["lambda"]["within_bar"] = out["lambda"]["max_rel_where_accumulators_equal"] <= 1e-5
+    return out
+
+
+def _shift_report(got_pos, exp_pos, before_pos):
+    se = exp_pos[:, :3].astype(np.int64) - before_pos[:, :3]
+    sg = got_pos[:, :3].astype(np.int64) - before_pos[:, :3]
+    err = np.abs(sg - se)
+    mx = int(np.abs(se).max()) if len(se) else 0
+    return {"max_shift_units": mx, "max_err_units": int(err.max()) if len(err) else 0, "mean_err_units": float(err.mean()) if len(err) else 0.0,
+            "frac_exact": float((err == 0).all(axis=1).mean()) if len(err) else 1.0,
+            "max_err_rel_to_max_shift": float(err.max() / max(mx, 1)) if len(err) else 0.0,
+            "within_bar": bool(len(err) == 0 or err.max() <= 8 + 1e-5 * mx)}
+
+
+def operator_parity(gpu, sc, *, adaptive, hk=1, gk=1, search="green", pairs_per_particle=None, threads=None):
+    """search (+ spread_kernel_width when adaptive) + ONE incompressibility iteration, operator by operator on both sides.
+    Returns the report dict; every `*_bit_exact` must be True and every `within_bar` must be True for the parity bar."""
+    if threads:
+        orc.set_threads(threads)
+    s = orc.default_settings()
+    s.mHeightKernelId, s.mGradientKernelId = hk, gk
+    s.mBaseKernelWidthOnBoundaryDistance = 0 if adaptive else 1
+    s.mSmallestTargetRadius = sc.smallest_target_radius
+    scale = 1.5 if adaptive else 1.0
+    cap = sc.n * int(pairs_per_particle or (700 if adaptive else 80))
+    t0 = time.perf_counter()
+    st = orc.State(**{k: v.copy() for k, v in sc.arrays.items()})
+    if search == "green":
+        ep, aux = orc.green_apply(st, s, sc.dims, scale, sc.min_pos, sc.max_pos, sc.res_log2, cap, want_aux=True)
+    else:
+        ep, aux = orc.binary_search_apply(st, s, scale, cap, want_aux=True)
+    n_searched = len(ep)
+    ekw = None
+    if adaptive:
+        ep, ekw = orc.spread_kernel_width_apply(st, s, ep)
+    out = {"scene": sc.name, "particles": int(sc.n), "search": search, "adaptive": bool(adaptive), "kernels": [hk, gk],
+           "pairs_searched": int(n_searched), "pairs": int(len(ep))}
+
+    ctx = gpu.Context(dims=sc.dims)
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    # the fused search + spread only has to hold the pruned list; the unfused search the whole one
+    L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=(len(ep) + 16) if adaptive else cap)
+    if search == "green":
+        op = (gpu.neighborhood_green_spread if adaptive else gpu.neighborhood_green)(ctx).set_data(L).set_range_scale(scale)
+        op.set_position_range(sc.min_pos, sc.max_pos, sc.res_log2)
+    else:
+        op = (gpu.neighborhood_binary_search_spread if adaptive else gpu.neighborhood_binary_search)(ctx).set_data(L).set_range_scale(scale)
+    dbg = op.apply(debug=True)
+    if adaptive:
+        out["kernel_width_fixed_bit_exact"] = bool(np.array_equal(dbg, ekw))
+        out["kernel_width_bit_exact"] = bool(np.array_equal(L.read("kernel_width"), st.kernel_width))
+    elif search == "green":
+        out["sorted_keys_bit_exact"] = bool(np.array_equal(dbg["sorted_key"], aux["sorted_hash"]))
+        out["sort_order_bit_exact"] = bool(np.array_equal(dbg["sorted_index"], aux["sorted_index"]))
+        out["cell_tables_bit_exact"] = bool(np.array_equal(dbg["cell_start"], aux["cell_start"]) and np.array_equal(dbg["cell_end"], aux["cell_end"]))
+    else:
+        out["sort_order_bit_exact"] = bool(np.array_equal(dbg["sorted_index"], aux["sorted_index"]))
+        out["codes_bit_exact"] = bool(all(np.array_equal(dbg[f"code{i}"], aux[f"code{i}"]) for i in range(3)))
+    got = L.read_all()
+    out["lists_bit_exact"] = bool(all(np.array_equal(got[f], getattr(st, f)) for f, _, _ in orc.State.FIELDS))
+    out["pair_list_bit_exact_in_order"] = bool(np.array_equal(L.read_pairs(), ep))
+    out["device_flags"] = int(ctx.device_flags())
+
+    before = st.position.copy()
+    ea = orc.incompressibility_apply(st, s, sc.dims, ep, want_aux=True)
+    ga = gpu.incompressibility(ctx).set_data(L).apply(debug=True)
+    out.update(_acc_report(ga, ea))
+    out["position_shift"] = _shift_report(L.read("position"), st.position, before)
+    out["boundariness_max_abs"] = float(np.abs(L.read("boundariness") - st.boundariness).max())
+    out["seconds"] = round(time.perf_counter() - t0, 2)
+    out["ok"] = bool(all(v for k, v in out.items() if k.endswith("_bit_exact") or k.endswith("_in_order")) and out["device_flags"] == 0 and
+                     all(out[k]["within_bar"] for k in ("density", "sq_grad_sum", "grad_sum", "lambda", "position_shift")))
+    return out
+
+
+def substep_parity(gpu, sc, *, adaptive, substeps=1, pairs_per_particle=None, search="green", update_transfers=False, threads=None,
+                   hk=1, gk=1):
+    """`substeps` whole substeps of pool::update (integrator on) through apbf_sim_* next to orc.substep from the same state.
+    Bar after the first substep: pair list in order, kernel widths and index list bit-exact.  Positions: with the cubic / poly6 /
+    spiky kernels every accumulator is bit-exact (no expf), so whole substeps -- wall contacts included -- must agree to the
+    bit, substep after substep.  With the Gauss kernels (expf) a 1-unit difference after the first iteration meets
+    box_collision.comp:46-47, whose wall jitter is a chaotic hash of the position (up to 0.05 = 13107 units): particles in
+    wall contact then differ by whole jitters, so for Gauss the position figures are reported, and barred only in the
+    operator-level form (operator_parity: one iteration on identical inputs)."""
+    if threads:
+        orc.set_threads(threads)
+    s = orc.default_settings()
+    s.mHeightKernelId, s.mGradientKernelId = hk, gk
+    s.mBaseKernelWidthOnBoundaryDistance = 0 if adaptive else 1
+    s.mSmallestTargetRadius = sc.smallest_target_radius
+    s.mMerge = s.mSplit = 0
+    ppp = int(pairs_per_particle or (260 if adaptive else 60))
+    cap = sc.n * ppp
+    st = orc.State(**{k: v.copy() for k, v in sc.arrays.items()})
+    kw = dict(dims=sc.dims, basic_pbf=not adaptive and not update_transfers, solver_iterations=sc.solver_iterations, min_pos=sc.min_pos, max_pos=sc.max_pos,
+              res_log2=sc.res_log2, box_min4=sc.box_min, box_max4=sc.box_max, cap=sc.n * (700 if adaptive else 80), integrate=True,
+              use_binary_search=(search == "binary"), update_transfers=update_transfers)
+    ctx = gpu.Context(dims=sc.dims)
+    ctx.set_settings(gpu.Settings.from_buffer_copy(bytes(s)))
+    sim = gpu.Sim(ctx, sc, neighbor_capacity=cap, integrate=True, basic_pbf=kw["basic_pbf"], use_binary_search=(search == "binary"),
+                  update_transfers=update_transfers)
+    sim.upload(sc.arrays)
+    out = {"scene": sc.name, "particles": int(sc.n), "adaptive": bool(adaptive), "search": search, "kernels": [hk, gk], "substeps": []}
+    host = gpu.empty_host_arrays(sc.n)
+    t_cpu = 0.0
+    for k in range(substeps):
+        t0 = time.perf_counter()
+        ep = orc.substep(st, s, **kw)
+        t_cpu += time.perf_counter() - t0
+        sim.substep(1)
+        assert sim.download(host) == sc.n
+        row = {"pairs": int(len(ep)), "pair_count_equal": bool(sim.neighbor_count() == len(ep))}
+        if k == 0:
+            row["pair_list_bit_exact_in_order"] = bool(np.array_equal(sim.read_pairs(), ep))
+            row["kernel_width_bit_exact"] = bool(np.array_equal(host["kernel_width"], st.kernel_width))
+            row["index_list_bit_exact"] = bool(np.array_equal(host["index_list"], st.index_list))
+        d = np.abs(host["position"][:, :3].astype(np.int64) - st.position[:, :3])
+        row["position_max_err_units"] = int(d.max())
+        row["position_mean_err_units"] = float(d.mean())
+        row["position_frac_exact"] = float((d == 0).all(axis=1).mean())
+        v = np.abs(host["velocity"][:, :3] - st.velocity[:, :3])
+        row["velocity_max_abs"] = float(v.max())
+        out["substeps"].append(row)
+    first = out["substeps"][0]
+    out["cpu_seconds_per_substep"] = round(t_cpu / max(substeps, 1), 3)
+    out["device_flags"] = int(ctx.device_flags())
+    exact_kernels = hk != 1 and gk != 1
+    out["positions_bit_exact_every_substep"] = bool(all(r["position_max_err_units"] == 0 for r in out["substeps"]))
+    out["ok"] = bool(first["pair_list_bit_exact_in_order"] and first["kernel_width_bit_exact"] and first["index_list_bit_exact"] and
+                     out["device_flags"] == 0 and (out["positions_bit_exact_every_substep"] or not exact_kernels))
+    sim.close()
+    return out
