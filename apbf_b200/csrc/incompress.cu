@@ -35,7 +35,7 @@ struct sweep_args {
 	const uint32_t* nbl;           // idN | (unmirrored << 31) per pair
 	const uint32_t* offsets;
 	uint32_t        pair_cap;
-	int4*           P4;   // {x, y, z, bits(1 / inverse mass)} per id
+	int4*           P4;   // {x, y, z, bits(1 / inverse mass)} per id (written by the prologue only)
 	float4*         KG;   // {h, gradient c0, gradient c1, invRestDensity}
 	float4*         KH;   // {height c0, height c1, lambda divisor, inverse mass}
 	float4*         L4;   // {lambda, h, gradient c0, gradient c1}
@@ -127,6 +127,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
 			const uint32_t a = base + r * 4 + grp;
 			int dens = 0, sq = 0, gx = 0, gy = 0, gz = 0, cx = 0, cy = 0, cz = 0, cw = 0;
 			if (a < n) {
+				// (measured, r02c: the branch-free K-slot form of the apply sweep -- all gathers of a trip issued up front, t2_pairs --
+				// needs 57 registers here instead of 40 and runs 7 % SLOWER: this sweep is bound by instruction issue, the occupancy
+				// of the 40-register form hides the gather latency already.  The apply sweep gains 5 % from it and keeps it.)
 				const int4 ip = A.P4[a];
 				const float4 kg = A.KG[a], kh = A.KH[a];
 				kpar hp, gp;
@@ -150,7 +153,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
 						const float r2 = dot3(rx, ry, rz, rx, ry, rz);
 						float W; vec3f g;
 						pair_eval<HK, GK>(hp, gp, rx, ry, rz, r2, W, g);
-						// x / invMassN * 2^18 (:55-59): 2^18 is a power of two, so (x * mN) * 2^18 == x * (mN * 2^18) bit for bit
+						// x / invMassN * 2^18 (:55-59): 2^18 is a power of two, so (x * mN) * 2^18 == x * (mN * 2^18) bit for bit.
+						// (x * (1 / invMassN) instead of x / invMassN: identical whenever the mass is a power of two -- every scene seeded
+						// by initialize.cpp:16-27 with r a power of two; otherwise the product can differ from the quotient in the last
+						// bit, i.e. by one unit of 2^-18 in a truncated term now and then: inside the accumulators' parity bar, and
+						// measured by tests/test_gpu_parity.py::test_incompressibility_odd_masses.)
 						const float mNR = mN * R_INC;
 						dens += (int)f2u(W * mNR);                                               // :55
 						gx += f2i(g.x * mNR); gy += f2i(g.y * mNR); gz += f2i(g.z * mNR);        // :56-58
@@ -239,6 +246,57 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
 	}
 }
 
+// K x 8 pairs of one particle's segment per call: lane `sub` of the group takes the pairs e0, e0 + 8, ...  All 2 K gathers are
+// issued before the first pair is evaluated, and there is no branch in here for the compiler to sink a load into (with a `break`
+// per pair it did: LDG.128, ~60 instructions, LDG.128, ... -- the L2 latencies of a lane in a row).  A slot behind the segment's
+// end gathers the particle itself: r = 0, every gradient kernel is zero there, the slot adds nothing (and its "mirrored" bit is
+// clear, so it never takes the push path).
+template <int K, int GK, bool ASYM>
+__device__ __forceinline__ void t2_pairs(const sweep_args& A, uint32_t e0, uint32_t end, uint32_t a, const int4 ip, const float4 la, const float4 e0v,
+                                         bool filter, bool push_a, int& sx, int& sy, int& sz, int& hit)
+{
+	uint32_t nn[K];
+	int4 qq[K];
+	float4 ll[K];
+#pragma unroll
+	for (int u = 0; u < K; u++) nn[u] = (e0 + 8 * u < end) ? __ldg(A.nbl + e0 + 8 * u) : a;
+#pragma unroll
+	for (int u = 0; u < K; u++) { qq[u] = __ldg(A.P4 + (nn[u] & NB_ID_MASK)); ll[u] = __ldg(A.L4 + (nn[u] & NB_ID_MASK)); }
+#pragma unroll
+	for (int u = 0; u < K; u++) {
+		const uint32_t b = nn[u] & NB_ID_MASK;
+		const int4 iq = qq[u];
+		const float4 lb = ll[u];
+		const bool mirrored = !ASYM || (nn[u] & NB_UNMIRRORED) == 0u; // (no unmirrored pair in the list: nothing to test)
+		const int dxi = iq.x - ip.x, dyi = iq.y - ip.y, dzi = iq.z - ip.z;
+		const float rx = (float)dxi * INV_R_POS, ry = (float)dyi * INV_R_POS, rz = (float)dzi * INV_R_POS;
+		const float r2 = dot3(rx, ry, rz, rx, ry, rz);
+		if (filter) {
+			// filter_boundariness (incompressibility_3.comp:41-46): dot(emptyDirection, normalize(gradient)) > 0.6.
+			// Every kernel's gradient is a non-positive multiple of r, so normalize(gradient) = -r / |r| wherever
+			// the gradient is not zero: the test is dot(e0, r) < -0.6 |r|, evaluated without the square root.
+			bool nz = r2 >= 1.0e-8f;
+			// compact support: the gradient is zero outside h, and at |r| == h for all but the cone kernel
+			if (GK != 1) nz = nz && (GK == 3 ? !(sqrtf(r2) > la.y) : sqrtf(r2) < la.y);
+			const float d = dot3(e0v.x, e0v.y, e0v.z, rx, ry, rz);
+			if (nz && d < 0.0f && d * d > 0.36f * r2) hit = 1;
+		}
+		if (mirrored) { // the pair (b, a): b shifts a with b's lambda and b's kernel width, diff = pos_a - pos_b
+			kpar gp_b; gp_b.w = lb.y; gp_b.c0 = lb.z; gp_b.c1 = lb.w;
+			const vec3f g = kgrad_fast<GK>(gp_b, -rx, -ry, -rz, r2);
+			const float f = lb.x < 0.0f ? lb.x * R_POS : 0.0f; // (lambda >= 0 pushes nothing: x * 0 truncates to 0)
+			sx += f2i(g.x * f); sy += f2i(g.y * f); sz += f2i(g.z * f);
+		} else if (push_a) { // nobody gathers (a, b): push it like the reference does (:63-66)
+			kpar gp_a; gp_a.w = la.y; gp_a.c0 = la.z; gp_a.c1 = la.w;
+			const vec3f g = kgrad_fast<GK>(gp_a, rx, ry, rz, r2);
+			const float f = la.x * R_POS;
+			atomicAdd(&A.push[b].x, f2i(g.x * f));
+			atomicAdd(&A.push[b].y, f2i(g.y * f));
+			atomicAdd(&A.push[b].z, f2i(g.z * f));
+		}
+	}
+}
+
 // ---- T2 -------------------------------------------------------------------------------------------------------------------------
 // ASYM: the list holds unmirrored pairs (variable kernel widths), which push with integer atomics like the reference.  Both
 // forms are launched and the one that does not match the list's state returns at once: the host does not know the state
@@ -260,57 +318,24 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_apply_delta(sweep_args A)
 		for (int r = 0; r < 8; r++) {
 			const uint32_t a = base + r * 4 + grp;
 			int sx = 0, sy = 0, sz = 0, hit = 0;
-			if (a < n) {
-				const int4 ip = A.P4[a];
-				const float4 la = A.L4[a];
+			{
+				const bool live = a < n;
+				const uint32_t ac = live ? a : base;
+				const int4 ip = A.P4[ac];
+				const float4 la = A.L4[ac];
 				float4 e0v = make_float4(0.f, 0.f, 0.f, 0.f);
-				if (filter) e0v = A.E4[a];
+				if (filter) e0v = A.E4[ac];
 				const bool push_a = has_asym && la.x < 0.0f;
-				const uint32_t beg = min(A.offsets[a], A.pair_cap), end = min(A.offsets[a + 1], A.pair_cap);
-				for (uint32_t e0 = beg + sub; e0 < end; e0 += 8 * SWEEP_ILP) { // SWEEP_ILP pairs per lane in flight
-					uint32_t nn[SWEEP_ILP];
-					int4 qq[SWEEP_ILP];
-					float4 ll[SWEEP_ILP];
-#pragma unroll
-					for (int u = 0; u < SWEEP_ILP; u++) nn[u] = (e0 + 8 * u < end) ? A.nbl[e0 + 8 * u] : a;
-#pragma unroll
-					for (int u = 0; u < SWEEP_ILP; u++) { qq[u] = A.P4[nn[u] & NB_ID_MASK]; ll[u] = A.L4[nn[u] & NB_ID_MASK]; }
-#pragma unroll
-					for (int u = 0; u < SWEEP_ILP; u++) {
-						if (e0 + 8 * u >= end) break;
-						const uint32_t b = nn[u] & NB_ID_MASK;
-						const int4 iq = qq[u];
-						const float4 lb = ll[u];
-						const bool mirrored = !ASYM || (nn[u] & NB_UNMIRRORED) == 0u; // (no unmirrored pair in the list: nothing to test)
-						const int dxi = iq.x - ip.x, dyi = iq.y - ip.y, dzi = iq.z - ip.z;
-						const float rx = (float)dxi * INV_R_POS, ry = (float)dyi * INV_R_POS, rz = (float)dzi * INV_R_POS;
-						const float r2 = dot3(rx, ry, rz, rx, ry, rz);
-						if (filter) {
-							// filter_boundariness (incompressibility_3.comp:41-46): dot(emptyDirection, normalize(gradient)) > 0.6.
-							// Every kernel's gradient is a non-positive multiple of r, so normalize(gradient) = -r / |r| wherever
-							// the gradient is not zero: the test is dot(e0, r) < -0.6 |r|, evaluated without the square root.
-							bool nz = r2 >= 1.0e-8f;
-							// compact support: the gradient is zero outside h, and at |r| == h for all but the cone kernel
-							if (GK != 1) nz = nz && (GK == 3 ? !(sqrtf(r2) > la.y) : sqrtf(r2) < la.y);
-							const float d = dot3(e0v.x, e0v.y, e0v.z, rx, ry, rz);
-							if (nz && d < 0.0f && d * d > 0.36f * r2) hit = 1;
-						}
-						if (mirrored) { // the pair (b, a): b shifts a with b's lambda and b's kernel width, diff = pos_a - pos_b
-							if (lb.x < 0.0f) {
-								kpar gp_b; gp_b.w = lb.y; gp_b.c0 = lb.z; gp_b.c1 = lb.w;
-								const vec3f g = kgrad_fast<GK>(gp_b, -rx, -ry, -rz, r2);
-								const float f = lb.x * R_POS;
-								sx += f2i(g.x * f); sy += f2i(g.y * f); sz += f2i(g.z * f);
-							}
-						} else if (push_a) { // nobody gathers (a, b): push it like the reference does (:63-66)
-							kpar gp_a; gp_a.w = la.y; gp_a.c0 = la.z; gp_a.c1 = la.w;
-							const vec3f g = kgrad_fast<GK>(gp_a, rx, ry, rz, r2);
-							const float f = la.x * R_POS;
-							atomicAdd(&A.push[b].x, f2i(g.x * f));
-							atomicAdd(&A.push[b].y, f2i(g.y * f));
-							atomicAdd(&A.push[b].z, f2i(g.z * f));
-						}
-					}
+				const uint32_t beg = live ? min(A.offsets[a], A.pair_cap) : 0u, end = live ? min(A.offsets[a + 1], A.pair_cap) : 0u;
+				// the four groups of the warp walk their segments in lock step, 8 x SWEEP_ILP pairs per trip, as many trips as the
+				// longest of the four needs; the number of slots of the last trip is the same for the whole warp (no divergence)
+				const uint32_t longest = __reduce_max_sync(FULL, end - beg);
+				for (uint32_t done = 0; done < longest; done += 8 * SWEEP_ILP) {
+					const uint32_t e0 = beg + done + sub, left = longest - done;
+					if (left > 24u) t2_pairs<4, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, sx, sy, sz, hit);
+					else if (left > 16u) t2_pairs<3, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, sx, sy, sz, hit);
+					else if (left > 8u) t2_pairs<2, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, sx, sy, sz, hit);
+					else t2_pairs<1, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, sx, sy, sz, hit);
 				}
 			}
 			sx = sum8(sx); sy = sum8(sy); sz = sum8(sz); hit = sum8(hit);

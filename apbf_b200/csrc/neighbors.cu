@@ -988,23 +988,29 @@ k_green_stream(const emit_args A)
 						}
 						const uint32_t sq = cand - first; // this candidate is query sq of the chunk: id != idN, neighborhood_green.comp:83
 						const uint32_t live = cvalid ? ~(sq < 32u ? 1u << sq : 0u) : 0u;
-						if (FUSED && __any_sync(0xffffffffu, (((colU ^ colK) | (colMu ^ colM)) & live) != 0u)) {
-							// a pair of this batch sits in an ambiguity band: the whole batch again, prune on the integer form
-							const int4 ci4 = cvalid ? __ldg(A.i4 + cand) : make_int4(0, 0, 0, 0);
-							const float cutb = cvalid ? A.cutoff[cand] : -1.0f;
-							colK = 0u; colM = 0u;
-							for (uint32_t qi = 0; qi < cnt; qi++) {
-								const float4 qv = s_q[w][qi];
-								const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
-								const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-								const int4 ia = __ldg(A.i4 + first + qi);
-								// kernel_width.comp:36-38: integer subtract first, then to float; D2 = dist^2 * 2^36
-								const float ux = (float)(ci4.x - ia.x), uy = (float)(ci4.y - ia.y), uz = (float)(ci4.z - ia.z);
-								const float D2 = dot3(ux, uy, uz, ux, uy, uz);
-								const bool keep = !(d2 > s_T[w][qi]) && D2 <= A.cutoff[first + qi]; // :57
-								const bool mir = keep && !(d2 > c4.w) && D2 <= cutb;                 // (idN, id) survives as well
-								colK |= keep ? 1u << qi : 0u;
-								colM |= mir ? 1u << qi : 0u;
+						if (FUSED) {
+							// pairs in an ambiguity band (the "for sure" and the "at most" form of a test disagree): these -- and only
+							// these -- are decided again with the prune on the integer form (kernel_width.comp:36-38, :57).  On a lattice
+							// whose spacing divides the cutoff those are the six axis neighbours of every particle.
+							uint32_t amb = ((colU ^ colK) | (colMu ^ colM)) & live;
+							if (__any_sync(0xffffffffu, amb != 0u)) {
+								const int4 ci4 = cvalid ? __ldg(A.i4 + cand) : make_int4(0, 0, 0, 0);
+								const float cutb = cvalid ? A.cutoff[cand] : -1.0f;
+								while (amb) {
+									const uint32_t qi = (uint32_t)__ffs(amb) - 1u, bit = 1u << qi;
+									amb &= amb - 1u;
+									const float4 qv = s_q[w][qi];
+									const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
+									const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+									const int4 ia = __ldg(A.i4 + first + qi);
+									// integer subtract first, then to float; D2 = dist^2 * 2^36
+									const float ux = (float)(ci4.x - ia.x), uy = (float)(ci4.y - ia.y), uz = (float)(ci4.z - ia.z);
+									const float D2 = dot3(ux, uy, uz, ux, uy, uz);
+									const bool keep = !(d2 > s_T[w][qi]) && D2 <= A.cutoff[first + qi]; // :57
+									const bool mir = keep && !(d2 > c4.w) && D2 <= cutb;                 // (idN, id) survives as well
+									colK = keep ? (colK | bit) : (colK & ~bit);
+									colM = mir ? (colM | bit) : (colM & ~bit);
+								}
 							}
 						}
 						colK &= live; colM &= live;
@@ -1140,6 +1146,74 @@ k_regroup(const uint32_t* __restrict__ stream, uint32_t stream_blocks, const uin
 				n_asym += word[u] >> 31;
 			}
 		}
+	}
+	n_asym = __reduce_add_sync(0xffffffffu, n_asym);
+	if ((threadIdx.x & 31u) == 0u && n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
+}
+
+// The same pass with the stream blocks staged in shared memory by the bulk-copy engine (north_star: "TMA bulk copies where
+// cells are contiguous" -- the hit-stream block is the one contiguous, aligned 1056-byte unit on the search path): one thread
+// arms an mbarrier with the byte count and issues cp.async.bulk (SASS: UBLKCP.S.G + SYNCS.ARRIVE.TRANS64), U blocks in flight
+// per CTA; every thread then waits on the barrier's phase and takes its entry from shared memory.  The default
+// (APBF_REGROUP_TMA=0 selects the plain form); measured against it in profiles/r02_variants.md.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(SB_ENTRIES)
+k_regroup_tma(const uint32_t* __restrict__ stream, uint32_t stream_blocks, const uint32_t* __restrict__ offsets,
+              uint32_t* __restrict__ nbl, uint32_t cap, uint32_t* misc, int no_fallback)
+{
+	constexpr int U = 4;
+	__shared__ __align__(128) uint32_t s_blk[U][SB_WORDS];
+	__shared__ __align__(8) unsigned long long s_bar[U];
+	if (misc[MW_STREAM_OVERFLOW] != 0u) {
+		if (no_fallback && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(misc + MW_FLAGS, 1u);
+		return;
+	}
+	const uint32_t used = min(misc[MW_STREAM_CURSOR], stream_blocks);
+	if (threadIdx.x == 0) {
+#pragma unroll
+		for (int u = 0; u < U; u++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar[u])));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	uint32_t n_asym = 0u, phase = 0u;
+	for (uint32_t blk0 = blockIdx.x; blk0 < used; blk0 += U * gridDim.x) {
+		if (threadIdx.x == 0) {
+#pragma unroll
+			for (int u = 0; u < U; u++) {
+				const uint32_t blk = blk0 + u * gridDim.x;
+				if (blk < used) {
+					const uint32_t bar = smem_u32(&s_bar[u]);
+					asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(SB_WORDS * 4u) : "memory");
+					asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+					             :: "r"(smem_u32(&s_blk[u][0])), "l"(stream + (size_t)blk * SB_WORDS), "r"(SB_WORDS * 4u), "r"(bar) : "memory");
+				}
+			}
+		}
+		uint32_t o[U], word[U];
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			o[u] = 0xFFFFFFFFu;
+			const uint32_t blk = blk0 + u * gridDim.x;
+			if (blk >= used) continue;
+			const uint32_t bar = smem_u32(&s_bar[u]);
+			uint32_t done = 0u;
+			while (!done)
+				asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+				             : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+			const uint2 hdr = *(const uint2*)&s_blk[u][0];
+			word[u] = s_blk[u][SB_HEADER + threadIdx.x];
+			const uint32_t rk = s_blk[u][SB_HEADER + SB_ENTRIES + threadIdx.x];
+			if (threadIdx.x < hdr.y) o[u] = offsets[hdr.x + (rk >> SB_RANK_BITS)] + (rk & SB_RANK_MASK);
+		}
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			if (o[u] < cap) {
+				nbl[o[u]] = word[u];
+				n_asym += word[u] >> 31;
+			}
+		}
+		phase ^= 1u;
+		__syncthreads(); // everybody has read the staged blocks before the next round overwrites them
 	}
 	n_asym = __reduce_add_sync(0xffffffffu, n_asym);
 	if ((threadIdx.x & 31u) == 0u && n_asym) atomicAdd(misc + MW_N_ASYM, n_asym);
@@ -1418,6 +1492,8 @@ int apbf_green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range,
 	A.misc = misc; A.cull = cull; A.table_cells = max_hash; A.layers = emit_mode; A.i4 = K.i4; A.cutoff = K.cutoff; A.kwfx = kwfx;
 	A.qb4 = K.qb4; A.cell_maxw = K.cell_maxw; A.stream = stream; A.stream_blocks = stream_blocks;
 	static const int two_pass = getenv("APBF_TWO_PASS_EMIT") ? 1 : 0; // debugging aid: the count/fill emit instead of stream/regroup
+	// hit-stream blocks staged by the bulk-copy engine: 25 % faster at 5 x 10^8 pairs (2.61 -> 1.97 ms), the same at 3 x 10^7 (r02c)
+	static const int regroup_tma = getenv("APBF_REGROUP_TMA") ? atoi(getenv("APBF_REGROUP_TMA")) : 1;
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_COUNT);
 		if (fuse_kw) APBF_CUDA(ctx, cudaMemsetAsync(K.cell_maxw, 0, sizeof(uint32_t) * (size_t)max_hash * layers, st));
@@ -1439,8 +1515,9 @@ int apbf_green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range,
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
 		if (!two_pass) {
-			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, nullptr, nbl, nb->capacity, misc,
-			                                                    variant == EMIT_FUSED_MG ? 1 : 0);
+			if (regroup_tma) k_regroup_tma<<<ctx->num_sms * 8, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, nbl, nb->capacity, misc, variant == EMIT_FUSED_MG ? 1 : 0);
+			else k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, nullptr, nbl, nb->capacity, misc,
+			                                                         variant == EMIT_FUSED_MG ? 1 : 0);
 			APBF_LAUNCHED(ctx);
 			if (write_public) APBF_TRY(apbf_launch_expand_pairs(ctx, offsets, nbl, p.length, n_cap, nb->pairs, nb->capacity));
 		}
