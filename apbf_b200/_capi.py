@@ -150,6 +150,11 @@ SIGNATURES = {
     "apbf_mg_nccl_unique_id": (C.c_int, [vp]),
     "apbf_sim_mg_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
     "apbf_sim_mg_solve": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int]),
+    "apbf_sim_mg_halo_counts": (C.c_int, [vp, C.c_uint32, u32p]),
+    "apbf_sim_mg_loop_init": (C.c_int, [vp, C.c_uint32, C.c_uint32, u32p]),
+    "apbf_sim_mg_loop_reset": (C.c_int, [vp, C.c_uint32, C.c_uint32]),
+    "apbf_sim_mg_loop_stats": (C.c_int, [vp, u32p]),
+    "apbf_sim_mg_substep": (C.c_int, [vp, C.c_uint32]),
     "apbf_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
     "apbf_host_free_pinned": (C.c_int, [vp]),
 }

@@ -19,6 +19,7 @@
 #include "solver.cuh"
 #include "sort.cuh"
 #include <dlfcn.h>
+#include <algorithm>
 
 namespace {
 
@@ -581,13 +582,15 @@ int mg_exchange(apbf_sim* sim, const mg_lists& L, int what)
 	APBF_TRY(apbf_sim_mg_pack(sim, what, L.send_ids, L.n_send, stage_s));
 	APBF_NCCL(ctx, N->GroupStart());
 	size_t so = 0, ro = 0;
+	int first_err = 0; // the group is closed whatever a call inside it returned
 	for (int r = 0; r < sim->mg.world; r++) {
 		if (r == sim->mg.rank) continue;
-		if (L.send_counts[r]) APBF_NCCL(ctx, N->Send(stage_s + so * words, (size_t)L.send_counts[r] * words, NCCL_INT32, r, sim->nccl_comm, ctx->stream));
-		if (L.ghost_counts[r]) APBF_NCCL(ctx, N->Recv(stage_r + ro * words, (size_t)L.ghost_counts[r] * words, NCCL_INT32, r, sim->nccl_comm, ctx->stream));
+		if (L.send_counts[r]) { const int e = N->Send(stage_s + so * words, (size_t)L.send_counts[r] * words, NCCL_INT32, r, sim->nccl_comm, ctx->stream); if (e && !first_err) first_err = e; }
+		if (L.ghost_counts[r]) { const int e = N->Recv(stage_r + ro * words, (size_t)L.ghost_counts[r] * words, NCCL_INT32, r, sim->nccl_comm, ctx->stream); if (e && !first_err) first_err = e; }
 		so += L.send_counts[r]; ro += L.ghost_counts[r];
 	}
-	APBF_NCCL(ctx, N->GroupEnd());
+	{ const int e = N->GroupEnd(); if (e && !first_err) first_err = e; }
+	APBF_NCCL(ctx, first_err);
 	APBF_TRY(apbf_sim_mg_unpack(sim, what, L.ghost_ids, 0u, L.n_ghost, stage_r));
 	return APBF_OK;
 }
@@ -603,6 +606,13 @@ int apbf_mg_nccl_unique_id(void* out_id128)
 	if (N->GetUniqueId(&id) != 0) return APBF_ERR_CUDA;
 	memcpy(out_id128, &id, sizeof id);
 	return APBF_OK;
+}
+
+void apbf_sim_mg_comm_destroy(apbf_sim* sim)
+{
+	nccl_api* N = nccl();
+	if (sim && sim->nccl_comm && N && N->CommDestroy) N->CommDestroy(sim->nccl_comm);
+	if (sim) sim->nccl_comm = nullptr;
 }
 
 int apbf_sim_mg_comm_init(apbf_sim* sim, const void* id128, int rank, int world)
@@ -647,6 +657,519 @@ int apbf_sim_mg_solve(apbf_sim* sim, const uint32_t* send_ids_dev, const uint32_
 		APBF_TRY(apbf_sim_mg_phase(sim, 6, it));
 	}
 	return apbf_sim_mg_phase(sim, 7, 0);
+}
+
+} // extern "C"
+
+
+// =====================================================================================================================================
+// The whole substep of one scene in bricks inside the library (apbf_sim_mg_substep): pool::update (source/pool.cpp:67-106) cut where
+// data of other ranks is needed, everything -- kernels AND exchanges -- enqueued on the context's stream, no host read-back anywhere.
+//
+//   integrate owned -> ROUTE -> HALO -> search over owned + ghosts -> [widths to the ghosts] -> constants ->
+//   iterations x (prologue, packed positions to the ghosts, density / lambda sweep, lambdas to the ghosts, apply sweep) -> commit
+//
+// The host never learns how many particles migrate or how many ghosts there are: every count is a device word, every kernel is sized
+// by a capacity and reads its count on the device, and every message has a FIXED size (the capacity agreed at set-up, count in a
+// 16-byte header).  NVLink moves the padding for free (a few MB per exchange); what a substep pays for is the latency of eleven
+// grouped ncclSend / ncclRecv rounds.  Same order of the lists as the host-driven protocol (apbf_b200/multi_gpu.py), hence the same
+// results: N ranks == 1 rank, bit for bit.
+// =====================================================================================================================================
+namespace {
+
+enum mgl_word {
+	MGL_N_OWNED = 0, MGL_N_TOTAL = 1, MGL_GID_BASE = 2, MGL_MIGRATED = 3, MGL_FLAGS = 4, MGL_STAY_SRC = 5, MGL_STAY_DST = 6, MGL_STAY = 7,
+	MGL_ROUTE = 8,        // [8] particles of this rank per destination after the integrator
+	MGL_ARRIVE = 16,      // [8] arrivals per source
+	MGL_ARRIVE_DST = 24,  // [8] where the arrivals of source r go in the new order
+	MGL_HALO_SEND = 32,   // [8] ghosts this rank provides to rank r
+	MGL_HALO_RECV = 40,   // [8] ghosts this rank holds from rank r
+	MGL_GHOST_FIRST = 48, // [8] id of the first ghost from rank r (before the search's sort)
+	MGL_WORDS = 64
+};
+constexpr uint32_t MGL_FLAG_ROUTE_OVERFLOW = 1u, MGL_FLAG_HALO_OVERFLOW = 2u, MGL_FLAG_CAPACITY = 4u;
+constexpr uint32_t STATE_INT4 = 5u, HALO_INT4 = 3u; // 16-byte units per record
+
+struct mgl_bufs { int4* p[8]; };
+struct mgl_caps { uint32_t cap[8], off[8]; int world, rank; };
+
+__global__ void k_mgl_begin(uint32_t* __restrict__ words, uint32_t* len, uint32_t* hidden_len, uint32_t* misc)
+{
+	const uint32_t n = words[MGL_N_OWNED];
+	*len = n; *hidden_len = n;
+	misc[MW_N_OWNED] = n; misc[MW_GID_BASE] = words[MGL_GID_BASE];
+}
+
+// segment r of the lists (grouped by destination) -> send buffer r; thread (r, k)
+__global__ void k_mgl_pack_route(state_lists L, uint32_t* __restrict__ words, mgl_bufs B, int world, int rank, uint32_t route_cap)
+{
+	const uint32_t total = (uint32_t)world * route_cap;
+	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+		const int r = (int)(t / route_cap);
+		const uint32_t k = t - (uint32_t)r * route_cap;
+		if (r == rank) continue;
+		uint32_t start = 0u;
+		for (int q = 0; q < r; q++) start += words[MGL_ROUTE + q];
+		const uint32_t cnt = words[MGL_ROUTE + r];
+		if (k == 0u) {
+			B.p[r][0] = make_int4((int)min(cnt, route_cap), 0, 0, 0);
+			if (cnt > route_cap) atomicOr(words + MGL_FLAGS, MGL_FLAG_ROUTE_OVERFLOW);
+		}
+		if (k >= cnt) continue;
+		const uint32_t id = start + k;
+		int4* o = B.p[r] + 1 + STATE_INT4 * (size_t)k;
+		o[0] = L.pos[id]; o[1] = L.vel[id]; o[2] = L.backup[id];
+		o[3] = make_int4((int)L.inv_mass[id], (int)L.radius[id], (int)L.transferring[id], (int)L.target_radius[id]);
+		o[4] = make_int4((int)L.kernel_width[id], (int)L.boundariness[id], (int)L.boundary_distance[id], 0);
+	}
+}
+
+// new order of this rank's lists: [arrivals from lower ranks, rank after rank | stayers | arrivals from higher ranks] -- the order
+// the single-GPU sort sees them in (its sort is stable and the previous order was sorted by key, i.e. by rank first)
+__global__ void k_mgl_route_plan(uint32_t* __restrict__ words, mgl_bufs R, int world, int rank, uint32_t capacity)
+{
+	uint32_t low = 0u, high = 0u, start = 0u, total_out = 0u;
+	for (int r = 0; r < world; r++) {
+		const uint32_t a = r == rank ? 0u : (uint32_t)R.p[r][0].x;
+		words[MGL_ARRIVE + r] = a;
+		if (r < rank) low += a; else if (r > rank) high += a;
+		if (r < rank) start += words[MGL_ROUTE + r];
+		if (r != rank) total_out += words[MGL_ROUTE + r];
+	}
+	const uint32_t stay = words[MGL_ROUTE + rank];
+	uint32_t off_low = 0u, off_high = low + stay;
+	for (int r = 0; r < world; r++) {
+		if (r < rank) { words[MGL_ARRIVE_DST + r] = off_low; off_low += words[MGL_ARRIVE + r]; }
+		else if (r > rank) { words[MGL_ARRIVE_DST + r] = off_high; off_high += words[MGL_ARRIVE + r]; }
+	}
+	words[MGL_STAY_SRC] = start; words[MGL_STAY_DST] = low; words[MGL_STAY] = stay;
+	uint32_t n = low + stay + high;
+	if (n > capacity) { atomicOr(words + MGL_FLAGS, MGL_FLAG_CAPACITY); n = capacity; }
+	words[MGL_N_OWNED] = n;
+	words[MGL_MIGRATED] = total_out;
+}
+
+__global__ void k_mgl_copy_stayers(state_lists S, state_lists D, const uint32_t* __restrict__ words, uint32_t capacity)
+{
+	const uint32_t src0 = words[MGL_STAY_SRC], dst0 = words[MGL_STAY_DST], count = words[MGL_STAY];
+	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+		const uint32_t s = src0 + k, d = dst0 + k;
+		if (d >= capacity) continue;
+		D.pos[d] = S.pos[s]; D.vel[d] = S.vel[s]; D.backup[d] = S.backup[s];
+		D.inv_mass[d] = S.inv_mass[s]; D.radius[d] = S.radius[s]; D.transferring[d] = S.transferring[s];
+		D.target_radius[d] = S.target_radius[s]; D.kernel_width[d] = S.kernel_width[s]; D.boundariness[d] = S.boundariness[s];
+		D.boundary_distance[d] = S.boundary_distance[s];
+		D.index_list[d] = d;
+	}
+}
+
+__global__ void k_mgl_unpack_arrivals(state_lists D, const uint32_t* __restrict__ words, mgl_bufs R, int world, int rank, uint32_t route_cap, uint32_t capacity)
+{
+	const uint32_t total = (uint32_t)world * route_cap;
+	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+		const int r = (int)(t / route_cap);
+		const uint32_t k = t - (uint32_t)r * route_cap;
+		if (r == rank || k >= words[MGL_ARRIVE + r]) continue;
+		const uint32_t id = words[MGL_ARRIVE_DST + r] + k;
+		if (id >= capacity) continue;
+		const int4* o = R.p[r] + 1 + STATE_INT4 * (size_t)k;
+		D.pos[id] = o[0]; D.vel[id] = o[1]; D.backup[id] = o[2];
+		const int4 a = o[3], b = o[4];
+		D.inv_mass[id] = (uint32_t)a.x; D.radius[id] = (uint32_t)a.y; D.transferring[id] = (uint32_t)a.z; D.target_radius[id] = (uint32_t)a.w;
+		D.kernel_width[id] = (uint32_t)b.x; D.boundariness[id] = (uint32_t)b.y; D.boundary_distance[id] = (uint32_t)b.z;
+		D.index_list[id] = id;
+	}
+}
+
+// send lists: owned ids whose cell lies inside another rank's grown brick (block r of `ids` at C.off[r], at most C.cap[r] entries)
+__global__ void k_mgl_halo_lists(const int32_t* __restrict__ pos4, uint32_t* __restrict__ words, apbf_grid_params g, mg_boxes B, mgl_caps C,
+                                 uint32_t* __restrict__ ids)
+{
+	const uint32_t n_owned = words[MGL_N_OWNED];
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t base = blockIdx.x * blockDim.x; base < n_owned; base += stride) { // whole warps stay in the loop for the ballots
+		const uint32_t id = base + threadIdx.x;
+		uint32_t c[3] = { 0u, 0u, 0u };
+		if (id < n_owned) cell_of(pos4, id, g, c);
+		for (int r = 0; r < B.world; r++) {
+			if (r == B.rank) continue;
+			const bool inside = id < n_owned && c[0] >= B.lo[r][0] && c[0] <= B.hi[r][0] && c[1] >= B.lo[r][1] && c[1] <= B.hi[r][1] &&
+			                    c[2] >= B.lo[r][2] && c[2] <= B.hi[r][2];
+			const uint32_t m = __ballot_sync(0xffffffffu, inside);
+			if (m == 0u) continue;
+			uint32_t slot = 0u;
+			if (lane_id() == 0u) slot = atomicAdd(words + MGL_HALO_SEND + r, (uint32_t)__popc(m));
+			slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(m & ((1u << lane_id()) - 1u));
+			if (inside) {
+				if (slot < C.cap[r]) ids[C.off[r] + slot] = id;
+				else atomicOr(words + MGL_FLAGS, MGL_FLAG_HALO_OVERFLOW);
+			}
+		}
+	}
+}
+
+__global__ void k_mgl_pack_halo(halo_lists L, uint32_t* __restrict__ words, const uint32_t* __restrict__ ids, mgl_caps C, mgl_bufs B, uint32_t total)
+{
+	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+		int r = 0;
+		while (r + 1 < C.world && t >= C.off[r + 1]) r++;
+		if (r == C.rank) continue;
+		const uint32_t k = t - C.off[r];
+		if (k >= C.cap[r]) continue;
+		const uint32_t cnt = min(words[MGL_HALO_SEND + r], C.cap[r]);
+		if (k == 0u) {
+			B.p[r][0] = make_int4((int)cnt, (int)words[MGL_N_OWNED], 0, 0);
+			words[MGL_HALO_SEND + r] = cnt; // (clamped: the exchanges of the solver loop use it)
+		}
+		if (k >= cnt) continue;
+		const uint32_t id = ids[C.off[r] + k];
+		int4* o = B.p[r] + 1 + HALO_INT4 * (size_t)k;
+		o[0] = L.pos[id];
+		o[1] = make_int4((int)L.inv_mass[id], (int)L.radius[id], (int)L.kernel_width[id], (int)L.target_radius[id]);
+		o[2] = make_int4((int)L.boundary_distance[id], 0, 0, 0); // (update_transfers floods it across the bricks)
+	}
+}
+
+__global__ void k_mgl_halo_plan(uint32_t* __restrict__ words, mgl_bufs R, mgl_caps C, uint32_t capacity, uint32_t* len, uint32_t* hidden_len, uint32_t* misc)
+{
+	const uint32_t n_owned = words[MGL_N_OWNED];
+	uint32_t first = n_owned, gid = 0u;
+	for (int r = 0; r < C.world; r++) {
+		uint32_t cnt = 0u;
+		if (r != C.rank) {
+			cnt = min((uint32_t)R.p[r][0].x, C.cap[r]);
+			if (first + cnt > capacity) { atomicOr(words + MGL_FLAGS, MGL_FLAG_CAPACITY); cnt = capacity - first; }
+			if (r < C.rank) gid += (uint32_t)R.p[r][0].y;
+		}
+		words[MGL_HALO_RECV + r] = cnt;
+		words[MGL_GHOST_FIRST + r] = first;
+		first += cnt;
+	}
+	words[MGL_N_TOTAL] = first;
+	words[MGL_GID_BASE] = gid;
+	*len = first; *hidden_len = first;
+	misc[MW_N_OWNED] = n_owned; misc[MW_GID_BASE] = gid;
+}
+
+__global__ void k_mgl_unpack_halo(halo_lists_out L, const uint32_t* __restrict__ words, mgl_bufs R, mgl_caps C, uint32_t* __restrict__ ghost_ids, uint32_t total)
+{
+	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+		int r = 0;
+		while (r + 1 < C.world && t >= C.off[r + 1]) r++;
+		if (r == C.rank) continue;
+		const uint32_t k = t - C.off[r];
+		if (k >= words[MGL_HALO_RECV + r]) continue;
+		const uint32_t id = words[MGL_GHOST_FIRST + r] + k;
+		const int4* in = R.p[r] + 1 + HALO_INT4 * (size_t)k;
+		L.pos[id] = in[0];
+		const int4 a = in[1];
+		L.inv_mass[id] = (uint32_t)a.x; L.radius[id] = (uint32_t)a.y; L.kernel_width[id] = (uint32_t)a.z; L.target_radius[id] = (uint32_t)a.w;
+		L.boundary_distance[id] = (uint32_t)in[2].x;
+		L.index_list[id] = id;
+		ghost_ids[C.off[r] + k] = id;
+	}
+}
+
+// slots before the search's sort -> ids after it, for the send lists (which = MGL_HALO_SEND) or the ghost slots (MGL_HALO_RECV)
+__global__ void k_mgl_remap(uint32_t* __restrict__ ids, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ words, int which, mgl_caps C, uint32_t total)
+{
+	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+		int r = 0;
+		while (r + 1 < C.world && t >= C.off[r + 1]) r++;
+		if (r == C.rank || t - C.off[r] >= words[which + r]) continue;
+		ids[t] = inv[ids[t]];
+	}
+}
+
+// one quantity of the owners for their ghosts elsewhere: what = 1 kernel width, 2 packed solver position, 3 lambda, 4 position
+__global__ void k_mgl_pack(int what, const uint32_t* __restrict__ src4, const int4* __restrict__ src16, uint32_t stride4, const uint32_t* __restrict__ ids,
+                           const uint32_t* __restrict__ words, mgl_caps C, mgl_bufs B, uint32_t total)
+{
+	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+		int r = 0;
+		while (r + 1 < C.world && t >= C.off[r + 1]) r++;
+		const uint32_t k = t - C.off[r];
+		if (r == C.rank || k >= words[MGL_HALO_SEND + r]) continue;
+		const uint32_t id = ids[t];
+		if (what == 2 || what == 4) B.p[r][k] = src16[id];
+		else ((uint32_t*)B.p[r])[k] = src4[(size_t)id * stride4];
+	}
+}
+
+__global__ void k_mgl_unpack(int what, uint32_t* __restrict__ dst4, int4* __restrict__ dst16, float4* __restrict__ L4, const float4* __restrict__ KG,
+                             const uint32_t* __restrict__ ghost_ids, const uint32_t* __restrict__ words, mgl_caps C, mgl_bufs R, uint32_t total)
+{
+	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+		int r = 0;
+		while (r + 1 < C.world && t >= C.off[r + 1]) r++;
+		const uint32_t k = t - C.off[r];
+		if (r == C.rank || k >= words[MGL_HALO_RECV + r]) continue;
+		const uint32_t id = ghost_ids[t];
+		if (what == 2 || what == 4) dst16[id] = R.p[r][k];
+		else if (what == 1) dst4[id] = ((const uint32_t*)R.p[r])[k];
+		else { // a ghost's record for the apply sweep: {lambda from its owner, h, gradient c0, gradient c1 from the local constants}
+			const float4 kg = KG[id];
+			L4[id] = make_float4(__uint_as_float(((const uint32_t*)R.p[r])[k]), kg.x, kg.y, kg.z);
+		}
+	}
+}
+
+mgl_bufs bufs_of(void* const p[8]) { mgl_bufs b; for (int r = 0; r < 8; r++) b.p[r] = (int4*)p[r]; return b; }
+mgl_caps caps_of(const apbf_sim* sim)
+{
+	mgl_caps c;
+	for (int r = 0; r < 8; r++) { c.cap[r] = sim->mgl.halo_cap[r]; c.off[r] = sim->mgl.halo_off[r]; }
+	c.world = sim->mg.world; c.rank = sim->mg.rank;
+	return c;
+}
+
+// every peer gets `bytes_of(r)` bytes from send_buf[r] and delivers as many into recv_buf[r]: one grouped round on the context's stream.
+// The group is always closed, whatever an individual call returned.
+template <class F>
+int mgl_exchange(apbf_sim* sim, F bytes_of)
+{
+	apbf_ctx* ctx = sim->ctx;
+	nccl_api* N = nccl();
+	if (!N || !sim->nccl_comm) return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, "apbf_sim_mg_comm_init has not been called", __FILE__, __LINE__);
+	int first_err = N->GroupStart();
+	if (first_err != 0) return apbf_fail(ctx, APBF_ERR_CUDA, N->GetErrorString ? N->GetErrorString(first_err) : "ncclGroupStart", __FILE__, __LINE__);
+	for (int r = 0; r < sim->mg.world; r++) {
+		if (r == sim->mg.rank) continue;
+		const size_t words = (bytes_of(r) + 3) / 4;
+		int e = N->Send(sim->mgl.send_buf[r], words, NCCL_INT32, r, sim->nccl_comm, ctx->stream);
+		if (e != 0 && first_err == 0) first_err = e;
+		e = N->Recv(sim->mgl.recv_buf[r], words, NCCL_INT32, r, sim->nccl_comm, ctx->stream);
+		if (e != 0 && first_err == 0) first_err = e;
+	}
+	const int e = N->GroupEnd();
+	if (e != 0 && first_err == 0) first_err = e;
+	if (first_err != 0) return apbf_fail(ctx, APBF_ERR_CUDA, N->GetErrorString ? N->GetErrorString(first_err) : "nccl", __FILE__, __LINE__);
+	sim->mgl.exchanges++;
+	return APBF_OK;
+}
+
+int mgl_refresh(apbf_sim* sim, int what)
+{
+	apbf_ctx* ctx = sim->ctx;
+	const mgl_caps C = caps_of(sim);
+	const uint32_t total = sim->mgl.halo_total, cap = sim->cfg.particle_capacity;
+	if (total == 0u) return APBF_OK;
+	apbf_fluid& f = sim->fluid;
+	const uint32_t* src4 = nullptr; const int4* src16 = nullptr; uint32_t stride4 = 1u;
+	uint32_t* dst4 = nullptr; int4* dst16 = nullptr; float4* L4 = nullptr; const float4* KG = nullptr;
+	if (what == 1) { src4 = (const uint32_t*)f.kernel_width.data; dst4 = (uint32_t*)f.kernel_width.data; }
+	else if (what == 2) { src16 = dst16 = (int4*)ctx->scratch_get(SLOT_P4, sizeof(int4) * (size_t)cap); }
+	else if (what == 3) {
+		L4 = (float4*)ctx->scratch_get(SLOT_L4, sizeof(float4) * (size_t)cap);
+		KG = (const float4*)ctx->scratch_get(SLOT_KG, sizeof(float4) * (size_t)cap);
+		src4 = (const uint32_t*)L4; stride4 = 4u;
+	} else if (what == 4) { src16 = dst16 = (int4*)f.particle.position.data; }
+	else return apbf_fail(ctx, APBF_ERR_INVALID, "what", __FILE__, __LINE__);
+	const unsigned grid = apbf_grid(ctx, total, 256);
+	k_mgl_pack<<<grid, 256, 0, ctx->stream>>>(what, src4, src16, stride4, sim->mgl.send_ids, sim->mgl.words, C, bufs_of(sim->mgl.send_buf), total);
+	APBF_LAUNCHED(ctx);
+	const size_t elem = (what == 2 || what == 4) ? 16u : 4u;
+	APBF_TRY(mgl_exchange(sim, [&](int r) { return elem * (size_t)sim->mgl.halo_cap[r]; }));
+	k_mgl_unpack<<<grid, 256, 0, ctx->stream>>>(what, dst4, dst16, L4, KG, sim->mgl.ghost_ids, sim->mgl.words, C, bufs_of(sim->mgl.recv_buf), total);
+	APBF_LAUNCHED(ctx);
+	return APBF_OK;
+}
+
+mg_boxes grown_boxes(const apbf_sim* sim)
+{
+	const apbf_mg_state& m = sim->mg;
+	const uint32_t cells = 1u << sim->cfg.res_log2;
+	mg_boxes B;
+	memset(&B, 0, sizeof B);
+	B.world = m.world; B.rank = m.rank;
+	for (int r = 0; r < m.world; r++)
+		for (int d = 0; d < 3; d++) {
+			B.lo[r][d] = m.lo[r][d] > m.halo[d] ? m.lo[r][d] - m.halo[d] : 0u;
+			B.hi[r][d] = (d < sim->cfg.dims) ? (m.hi[r][d] + m.halo[d] < cells - 1u ? m.hi[r][d] + m.halo[d] : cells - 1u) : 0u;
+		}
+	return B;
+}
+
+} // namespace
+
+extern "C" {
+
+// Set-up helper (synchronises): how many of this rank's first n_owned particles every other rank needs as ghosts right now.  The
+// caller exchanges these numbers between the ranks and derives the per-peer message capacities from them.
+int apbf_sim_mg_halo_counts(apbf_sim* sim, uint32_t n_owned, uint32_t out_counts_host[8])
+{
+	if (!sim || !out_counts_host) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	APBF_REQUIRE(ctx, sim->mg.enabled && n_owned <= sim->cfg.particle_capacity);
+	apbf_grid_params g;
+	APBF_TRY(grid_of(sim, &g));
+	uint32_t* words = (uint32_t*)ctx->scratch_get(SLOT_MG_SEND, sizeof(uint32_t) * MGL_WORDS);
+	uint32_t* ids = (uint32_t*)ctx->scratch_get(SLOT_MG_RECV, 256);
+	if (!words || !ids) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+	APBF_CUDA(ctx, cudaMemsetAsync(words, 0, sizeof(uint32_t) * MGL_WORDS, ctx->stream));
+	APBF_CUDA(ctx, cudaMemcpyAsync(words + MGL_N_OWNED, &n_owned, 4, cudaMemcpyHostToDevice, ctx->stream));
+	mgl_caps C;
+	memset(&C, 0, sizeof C); // capacity 0 everywhere: count only
+	C.world = sim->mg.world; C.rank = sim->mg.rank;
+	if (n_owned > 0) {
+		k_mgl_halo_lists<<<apbf_grid(ctx, n_owned, 256), 256, 0, ctx->stream>>>((const int32_t*)sim->fluid.particle.position.data, words, g, grown_boxes(sim), C, ids);
+		APBF_LAUNCHED(ctx);
+	}
+	APBF_CUDA(ctx, cudaMemcpyAsync(out_counts_host, words + MGL_HALO_SEND, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	APBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return APBF_OK;
+}
+
+// Allocates the staging buffers of the library loop.  route_cap: particles per peer and substep that may change owner; halo_cap[r]:
+// ghost records exchanged with rank r -- the SAME number on both sides of a pair (it is the size of their messages).
+int apbf_sim_mg_loop_init(apbf_sim* sim, uint32_t n_owned, uint32_t route_cap, const uint32_t halo_cap[8])
+{
+	if (!sim || !halo_cap) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	APBF_REQUIRE(ctx, sim->mg.enabled && !sim->mgl.ready && n_owned <= sim->cfg.particle_capacity && route_cap > 0u);
+	apbf_mg_loop& M = sim->mgl;
+	M.route_cap = route_cap;
+	uint32_t off = 0u;
+	for (int r = 0; r < 8; r++) {
+		M.halo_cap[r] = (r < sim->mg.world && r != sim->mg.rank) ? halo_cap[r] : 0u;
+		M.halo_off[r] = off;
+		off += M.halo_cap[r];
+	}
+	M.halo_total = off;
+	auto dev_alloc = [&](void** p, size_t bytes) {
+		if (cudaMalloc(p, bytes ? bytes : 16) != cudaSuccess) return false;
+		sim->owned.push_back(*p);
+		return cudaMemsetAsync(*p, 0, bytes ? bytes : 16, ctx->stream) == cudaSuccess;
+	};
+	bool ok = dev_alloc((void**)&M.words, sizeof(uint32_t) * MGL_WORDS) && dev_alloc((void**)&M.send_ids, sizeof(uint32_t) * (size_t)(off + 1)) &&
+	          dev_alloc((void**)&M.ghost_ids, sizeof(uint32_t) * (size_t)(off + 1));
+	for (int r = 0; r < sim->mg.world && ok; r++) {
+		if (r == sim->mg.rank) continue;
+		const size_t bytes = 16 + std::max((size_t)route_cap * STATE_INT4 * 16, (size_t)M.halo_cap[r] * HALO_INT4 * 16);
+		M.buf_bytes[r] = bytes;
+		ok = dev_alloc(&M.send_buf[r], bytes) && dev_alloc(&M.recv_buf[r], bytes);
+	}
+	if (!ok) return apbf_fail(ctx, APBF_ERR_OOM, "cudaMalloc", __FILE__, __LINE__);
+	APBF_CUDA(ctx, cudaMemcpyAsync(M.words + MGL_N_OWNED, &n_owned, 4, cudaMemcpyHostToDevice, ctx->stream));
+	APBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	M.ready = true;
+	return APBF_OK;
+}
+
+// the lists were uploaded afresh: this rank owns their first n_owned entries, global ids start at gid_base
+int apbf_sim_mg_loop_reset(apbf_sim* sim, uint32_t n_owned, uint32_t gid_base)
+{
+	if (!sim) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	APBF_REQUIRE(ctx, sim->mgl.ready && n_owned <= sim->cfg.particle_capacity);
+	const uint32_t w[3] = { n_owned, n_owned, gid_base };
+	APBF_CUDA(ctx, cudaMemcpyAsync(sim->mgl.words + MGL_N_OWNED, w, sizeof w, cudaMemcpyHostToDevice, ctx->stream));
+	APBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // (w lives on this stack frame)
+	return APBF_OK;
+}
+
+// out[0] owned particles, [1] owned + ghosts, [2] global id of local id 0, [3] particles that left in the last substep,
+// [4] flags (1 migration buffer overflow, 2 ghost list overflow, 4 particle capacity exceeded), [5] exchanges so far; synchronises
+int apbf_sim_mg_loop_stats(apbf_sim* sim, uint32_t out[8])
+{
+	if (!sim || !out) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	APBF_REQUIRE(ctx, sim->mgl.ready);
+	uint32_t w[8];
+	APBF_CUDA(ctx, cudaMemcpyAsync(w, sim->mgl.words, sizeof w, cudaMemcpyDeviceToHost, ctx->stream));
+	APBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	out[0] = w[MGL_N_OWNED]; out[1] = w[MGL_N_TOTAL]; out[2] = w[MGL_GID_BASE]; out[3] = w[MGL_MIGRATED]; out[4] = w[MGL_FLAGS];
+	out[5] = (uint32_t)sim->mgl.exchanges; out[6] = 0u; out[7] = 0u;
+	return APBF_OK;
+}
+
+int apbf_sim_mg_substep(apbf_sim* sim, uint32_t n_substeps)
+{
+	if (!sim) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	APBF_REQUIRE(ctx, sim->mg.enabled && sim->mgl.ready);
+	apbf_mg_loop& M = sim->mgl;
+	const apbf_sim_config& c = sim->cfg;
+	const apbf_settings& s = ctx->settings;
+	const int world = sim->mg.world, rank = sim->mg.rank;
+	const uint32_t cap = c.particle_capacity;
+	cudaStream_t st = ctx->stream;
+	apbf_grid_params g;
+	APBF_TRY(grid_of(sim, &g));
+	const mgl_caps C = caps_of(sim);
+	const bool adaptive = !c.basic_pbf && !s.mBaseKernelWidthOnBoundaryDistance;
+	const bool default_mode = c.update_transfers && !c.basic_pbf && s.mBaseKernelWidthOnBoundaryDistance;
+	uint32_t* misc = ctx->misc();
+	for (uint32_t step = 0; step < n_substeps; step++) {
+		apbf_fluid& f = sim->fluid;
+		// ghosts of the last substep are dropped: the lists are the owned particles again
+		k_mgl_begin<<<1, 1, 0, st>>>(M.words, f.particle.length, f.particle.hidden_length, misc);
+		APBF_LAUNCHED(ctx);
+		if (c.integrate) APBF_TRY(apbf_sim_mg_phase(sim, 0, 0));
+		if (default_mode) APBF_TRY(apbf_sim_mg_phase(sim, 8, 0));
+		if (world > 1) {
+			// ---- ROUTE: particles that left the brick change owner with their full state -------------------------------------------
+			APBF_TRY(apbf_sim_mg_route(sim, M.words + MGL_ROUTE)); // grouped by destination in the current buffers; counts on the device
+			k_mgl_pack_route<<<apbf_grid(ctx, (size_t)world * M.route_cap, 256), 256, 0, st>>>(lists_of(sim, false), M.words, bufs_of(M.send_buf), world, rank, M.route_cap);
+			APBF_LAUNCHED(ctx);
+			APBF_TRY(mgl_exchange(sim, [&](int) { return 16 + (size_t)M.route_cap * STATE_INT4 * 16; }));
+			k_mgl_route_plan<<<1, 1, 0, st>>>(M.words, bufs_of(M.recv_buf), world, rank, cap);
+			APBF_LAUNCHED(ctx);
+			k_mgl_copy_stayers<<<apbf_grid(ctx, cap, 256), 256, 0, st>>>(lists_of(sim, false), lists_of(sim, true), M.words, cap);
+			APBF_LAUNCHED(ctx);
+			k_mgl_unpack_arrivals<<<apbf_grid(ctx, (size_t)world * M.route_cap, 256), 256, 0, st>>>(lists_of(sim, true), M.words, bufs_of(M.recv_buf), world, rank, M.route_cap, cap);
+			APBF_LAUNCHED(ctx);
+			apbf_sim_swap_buffers(sim);
+			k_mgl_begin<<<1, 1, 0, st>>>(M.words, f.particle.length, f.particle.hidden_length, misc);
+			APBF_LAUNCHED(ctx);
+			// ---- HALO: owned particles inside another rank's grown brick go there as ghosts ----------------------------------------
+			APBF_CUDA(ctx, cudaMemsetAsync(M.words + MGL_HALO_SEND, 0, sizeof(uint32_t) * 8, st));
+			k_mgl_halo_lists<<<apbf_grid(ctx, cap, 256), 256, 0, st>>>((const int32_t*)f.particle.position.data, M.words, g, grown_boxes(sim), C, M.send_ids);
+			APBF_LAUNCHED(ctx);
+			const halo_lists hl{ (const int4*)f.particle.position.data, (const uint32_t*)f.particle.inverse_mass.data, (const uint32_t*)f.particle.radius.data,
+			                     (const uint32_t*)f.kernel_width.data, (const uint32_t*)f.target_radius.data, (const uint32_t*)f.boundary_distance.data };
+			k_mgl_pack_halo<<<apbf_grid(ctx, M.halo_total, 256), 256, 0, st>>>(hl, M.words, M.send_ids, C, bufs_of(M.send_buf), M.halo_total);
+			APBF_LAUNCHED(ctx);
+			APBF_TRY(mgl_exchange(sim, [&](int r) { return 16 + (size_t)M.halo_cap[r] * HALO_INT4 * 16; }));
+			k_mgl_halo_plan<<<1, 1, 0, st>>>(M.words, bufs_of(M.recv_buf), C, cap, f.particle.length, f.particle.hidden_length, misc);
+			APBF_LAUNCHED(ctx);
+			const halo_lists_out ho{ (int4*)f.particle.position.data, (uint32_t*)f.particle.inverse_mass.data, (uint32_t*)f.particle.radius.data,
+			                         (uint32_t*)f.kernel_width.data, (uint32_t*)f.target_radius.data, (uint32_t*)f.boundary_distance.data,
+			                         (uint32_t*)f.particle.index_list.data };
+			k_mgl_unpack_halo<<<apbf_grid(ctx, M.halo_total, 256), 256, 0, st>>>(ho, M.words, bufs_of(M.recv_buf), C, M.ghost_ids, M.halo_total);
+			APBF_LAUNCHED(ctx);
+		}
+		APBF_TRY(apbf_sim_mg_phase(sim, 1, 0)); // search over owned + ghosts (+ the fused spread_kernel_width); leaves old slot -> new id
+		if (world > 1 && M.halo_total > 0u) {
+			const uint32_t* inv = (const uint32_t*)ctx->scratch_get(SLOT_MG_INV, sizeof(uint32_t) * (size_t)cap);
+			if (!inv) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+			k_mgl_remap<<<apbf_grid(ctx, M.halo_total, 256), 256, 0, st>>>(M.send_ids, inv, M.words, MGL_HALO_SEND, C, M.halo_total);
+			APBF_LAUNCHED(ctx);
+			k_mgl_remap<<<apbf_grid(ctx, M.halo_total, 256), 256, 0, st>>>(M.ghost_ids, inv, M.words, MGL_HALO_RECV, C, M.halo_total);
+			APBF_LAUNCHED(ctx);
+		}
+		if (adaptive) {
+			APBF_TRY(apbf_sim_mg_phase(sim, 2, 0));
+			if (world > 1) APBF_TRY(mgl_refresh(sim, 1)); // the owners' new widths overwrite the ghosts'
+		}
+		APBF_TRY(apbf_sim_mg_phase(sim, 3, 0));
+		for (int it = 0; it < c.solver_iterations; it++) {
+			APBF_TRY(apbf_sim_mg_phase(sim, 4, it));
+			if (world > 1) APBF_TRY(mgl_refresh(sim, 2));
+			APBF_TRY(apbf_sim_mg_phase(sim, 5, it));
+			if (world > 1) APBF_TRY(mgl_refresh(sim, 3));
+			APBF_TRY(apbf_sim_mg_phase(sim, 6, it));
+		}
+		APBF_TRY(apbf_sim_mg_phase(sim, 7, 0));
+		if (c.update_transfers && !c.basic_pbf) {
+			if (world > 1) APBF_TRY(mgl_refresh(sim, 4)); // distances are taken after the solver
+			APBF_TRY(apbf_sim_mg_phase(sim, 9, 0));
+		}
+		// the lists a caller sees (apbf_sim_download) are this rank's own particles: the ghosts sit behind them and are dropped
+		k_mgl_begin<<<1, 1, 0, st>>>(M.words, sim->fluid.particle.length, sim->fluid.particle.hidden_length, misc);
+		APBF_LAUNCHED(ctx);
+	}
+	return APBF_OK;
 }
 
 } // extern "C"

@@ -115,6 +115,7 @@ void apbf_sim_destroy(apbf_sim* sim)
 {
 	if (!sim) return;
 	cudaStreamSynchronize(sim->ctx->stream);
+	apbf_sim_mg_comm_destroy(sim); // the library's own NCCL communicator, if one was made
 	for (void* p : sim->owned) cudaFree(p);
 	apbf_nbr_forget(sim->ctx, sim->nb.pairs);
 	delete sim;

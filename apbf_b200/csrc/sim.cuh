@@ -10,6 +10,22 @@ struct apbf_mg_state {
 	uint32_t n_owned = 0, n_total = 0;
 };
 
+// staging of the library-driven slab loop (apbf_sim_mg_substep, mgpu.cu): fixed-size messages, every count a device word
+struct apbf_mg_loop {
+	bool      ready = false;
+	uint32_t  route_cap = 0;             // particles per peer and substep that may change owner
+	uint32_t  halo_cap[8] = {};          // ghost records exchanged with rank r (the same number on both sides of a pair)
+	uint32_t  halo_off[8] = {};          // block of rank r in send_ids / ghost_ids
+	uint32_t  halo_total = 0;
+	uint32_t* words = nullptr;           // device words (mgl_word)
+	uint32_t* send_ids = nullptr;        // owned ids this rank provides as ghosts, block per destination
+	uint32_t* ghost_ids = nullptr;       // ids of the ghosts this rank holds, block per source
+	void*     send_buf[8] = {};
+	void*     recv_buf[8] = {};
+	size_t    buf_bytes[8] = {};
+	uint64_t  exchanges = 0;
+};
+
 struct apbf_sim {
 	apbf_ctx*       ctx;
 	apbf_sim_config cfg;
@@ -22,9 +38,11 @@ struct apbf_sim {
 	void*           nccl_comm = nullptr; // slabs: the library's own communicator (apbf_sim_mg_comm_init)
 	std::vector<void*> owned;
 	apbf_mg_state   mg;
+	apbf_mg_loop    mgl;
 	apbf_transfers  tr = {};             // cfg.transfers: the transfer list (pool.cpp:8)
 	uint32_t*       sorted_index = nullptr; // cfg.transfers: the search's permutation of the hidden list, for the transfers to follow
 };
 
+extern "C" void apbf_sim_mg_comm_destroy(apbf_sim* sim); // mgpu.cu (internal: called by apbf_sim_destroy)
 // data <-> reorder_out of every list (after a search or a re-partition)
 void apbf_sim_swap_buffers(apbf_sim* sim);

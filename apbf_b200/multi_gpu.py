@@ -405,3 +405,70 @@ def owner_rank_of_positions(position, min_pos, max_pos, res_log2, dims, world):
         bit = (cell[:, axis] >> np.uint32(res_log2 - 1 - level)) & 1
         rank = (rank << 1) | bit.astype(np.int64)
     return rank
+
+
+class LibraryDomain:
+    """One scene in bricks with the whole substep -- route, halo, search, solve and every exchange between the ranks -- driven by the
+    library (apbf_sim_mg_substep, csrc/mgpu.cu): one C call per substep, everything on the context's stream, no host read-back.
+    Python's part is set-up plumbing: the 128-byte NCCL id and the per-pair message capacities travel through torch.distributed."""
+
+    def __init__(self, sim, n_owned, world, rank, halo_range, ghost_capacity, adaptive, solver_iterations, headroom=2.0):
+        import torch
+        import torch.distributed as dist
+        from . import _check
+        self.torch, self._check = torch, _check
+        self.sim, self.lib, self.ctx = sim, sim.lib, sim.ctx
+        self.world, self.rank = world, rank
+        dev = torch.device("cuda", sim.ctx.device)
+        self._ck(self.lib.apbf_sim_mg_enable(sim.handle, rank, world, C.c_float(halo_range)))
+        if world > 1:
+            buf = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                self._ck(self.lib.apbf_mg_nccl_unique_id(buf.data_ptr()))
+            t = buf.to(dev)
+            dist.broadcast(t, 0)
+            buf = t.cpu()
+            self._ck(self.lib.apbf_sim_mg_comm_init(sim.handle, buf.data_ptr(), rank, world))
+        # how many ghosts each pair of ranks exchanges right now -> message capacities, the same number on both sides of a pair
+        counts = (C.c_uint32 * 8)()
+        self._ck(self.lib.apbf_sim_mg_halo_counts(sim.handle, int(n_owned), counts))
+        mine = torch.tensor([int(counts[r]) for r in range(8)], dtype=torch.int64, device=dev)
+        if world > 1:
+            allc = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allc, mine)
+            m = [a.tolist() for a in allc]
+        else:
+            m = [mine.tolist()]
+        caps = (C.c_uint32 * 8)()
+        for r in range(world):
+            if r != rank:
+                caps[r] = int(max(4096, headroom * max(m[rank][r], m[r][rank]) + 1024))
+        self.halo_caps = [int(caps[r]) for r in range(8)]
+        self.route_cap = int(max(4096, n_owned // 64))
+        self._ck(self.lib.apbf_sim_mg_loop_init(sim.handle, int(n_owned), self.route_cap, caps))
+        self.ghost_capacity = int(ghost_capacity)
+
+    def _ck(self, rc):
+        self._check(self.ctx, rc)
+
+    def substep(self, n=1):
+        self._ck(self.lib.apbf_sim_mg_substep(self.sim.handle, int(n)))
+
+    def _stats(self):
+        w = (C.c_uint32 * 8)()
+        self._ck(self.lib.apbf_sim_mg_loop_stats(self.sim.handle, w))
+        return [int(x) for x in w]
+
+    def n_owned(self):
+        return self._stats()[0]
+
+    def reset(self, n_owned, gid_base=0):
+        self._ck(self.lib.apbf_sim_mg_loop_reset(self.sim.handle, int(n_owned), int(gid_base)))
+
+    @property
+    def stats(self):
+        w = self._stats()
+        if w[4]:
+            raise RuntimeError(f"slab loop capacity exceeded (flags {w[4]}: 1 migration buffer, 2 ghost list, 4 particle capacity)")
+        return dict(owned=w[0], ghosts=w[1] - w[0], gid_base=w[2], migrated=w[3], exchanges=w[5], route_cap=self.route_cap,
+                    halo_caps=self.halo_caps[: self.world])

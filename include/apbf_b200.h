@@ -431,6 +431,21 @@ int  apbf_sim_mg_comm_init(apbf_sim* sim, const void* id128, int rank, int world
 int  apbf_sim_mg_solve(apbf_sim* sim, const uint32_t* send_ids_dev, const uint32_t* send_counts, const uint32_t* ghost_ids_dev,
                        const uint32_t* ghost_counts, int exchange_kernel_width, int iterations);
 
+/* ---- the slab protocol driven by the library itself --------------------------------------------------------------------------
+ * apbf_sim_mg_substep = pool::update (pool.cpp:67-106) of ONE scene in bricks, with route, halo, search, solve and every exchange
+ * between the ranks (grouped ncclSend / ncclRecv on the library's own communicator, apbf_sim_mg_comm_init) enqueued on the context's
+ * stream by this one call.  No host read-back: every count is a device word and every message has the fixed size agreed at set-up.
+ * Set-up, once per scene and rank: apbf_sim_mg_enable, apbf_sim_upload of the rank's brick, apbf_sim_mg_comm_init,
+ * apbf_sim_mg_halo_counts (synchronous; the caller exchanges the numbers between the ranks and picks halo_cap[r] >= both directions
+ * of the pair (rank, r), with head-room), apbf_sim_mg_loop_init. */
+int  apbf_sim_mg_halo_counts(apbf_sim* sim, uint32_t n_owned, uint32_t out_counts_host[8]);
+int  apbf_sim_mg_loop_init(apbf_sim* sim, uint32_t n_owned, uint32_t route_cap, const uint32_t halo_cap[8]);
+int  apbf_sim_mg_loop_reset(apbf_sim* sim, uint32_t n_owned, uint32_t gid_base);
+/* out[0] owned particles, [1] owned + ghosts, [2] global id of local id 0, [3] particles that left in the last substep, [4] flags
+ * (1 migration buffer overflow, 2 ghost list overflow, 4 particle capacity exceeded: raise the capacities), [5] exchanges so far */
+int  apbf_sim_mg_loop_stats(apbf_sim* sim, uint32_t out[8]);
+int  apbf_sim_mg_substep(apbf_sim* sim, uint32_t n_substeps);
+
 /* pinned host memory helpers for callers without a CUDA runtime of their own */
 int  apbf_host_alloc_pinned(size_t bytes, void** out_host_ptr);
 int  apbf_host_free_pinned(void* host_ptr);

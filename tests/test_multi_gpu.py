@@ -17,7 +17,7 @@ def _scene(adaptive, side):
     return sc
 
 
-def _worker(rank, world, port, adaptive, side, steps, out_dir, default_mode=False):
+def _worker(rank, world, port, adaptive, side, steps, out_dir, default_mode=False, library=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     import torch
@@ -35,19 +35,22 @@ def _worker(rank, world, port, adaptive, side, steps, out_dir, default_mode=Fals
     ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if adaptive else 1, mSmallestTargetRadius=sc.smallest_target_radius)
     cap = sc.n                      # room for every particle plus ghosts on one rank
     sim = apbf_b200.Sim(ctx, sc, capacity=cap, neighbor_capacity=cap * (700 if adaptive or default_mode else 80), integrate=True,
-                        basic_pbf=not (adaptive or default_mode))
+                        basic_pbf=not (adaptive or default_mode), update_transfers=default_mode)
     sim.upload(mine, n=n_own)
     halo_range = float(sc.arrays["kernel_width"].max()) * (1.5 if adaptive else 1.0) * 1.05
-    backend = multi_gpu.CudaRankBackend(sim, n_own, world, rank, halo_range, ghost_capacity=cap)
-    dom = multi_gpu.SlabDomain(backend, multi_gpu.TorchComm(torch.device("cuda", rank)), adaptive=adaptive, solver_iterations=4, integrate=True,
-                               update_transfers=default_mode, width_from_boundary_distance=default_mode)
+    if library:   # the whole substep inside the library: apbf_sim_mg_substep
+        dom = multi_gpu.LibraryDomain(sim, n_own, world, rank, halo_range, ghost_capacity=cap, adaptive=adaptive, solver_iterations=4, headroom=4.0)
+    else:         # the same protocol driven from Python, exchange by exchange
+        backend = multi_gpu.CudaRankBackend(sim, n_own, world, rank, halo_range, ghost_capacity=cap)
+        dom = multi_gpu.SlabDomain(backend, multi_gpu.TorchComm(torch.device("cuda", rank)), adaptive=adaptive, solver_iterations=4, integrate=True,
+                                   update_transfers=default_mode, width_from_boundary_distance=default_mode)
     migrated = 0
     for _ in range(steps):
         dom.substep()
         migrated += dom.stats["migrated"]
     out = apbf_b200.empty_host_arrays(cap)
     n = sim.download(out)
-    assert n == dom.n_own, (n, dom.n_own)
+    assert n == dom.n_owned(), (n, dom.n_owned())
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), migrated=migrated, ghosts=dom.stats["ghosts"], flags=ctx.device_flags(),
              **{k: v[:n] for k, v in out.items()})
     dist.barrier()
@@ -55,8 +58,9 @@ def _worker(rank, world, port, adaptive, side, steps, out_dir, default_mode=Fals
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("library", [False, True])
 @pytest.mark.parametrize("adaptive,side,default_mode", [(False, 24, False), (True, 20, False), (False, 20, True)])
-def test_n_rank_equals_one_rank(tmp_path, adaptive, side, default_mode):
+def test_n_rank_equals_one_rank(tmp_path, adaptive, side, default_mode, library):
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -64,8 +68,8 @@ def test_n_rank_equals_one_rank(tmp_path, adaptive, side, default_mode):
     import apbf_b200
     world = 4 if torch.cuda.device_count() >= 4 else 2
     steps = 3
-    port = 29500 + (os.getpid() % 1000) + int(adaptive) + 2 * int(default_mode)
-    mp.spawn(_worker, args=(world, port, adaptive, side, steps, str(tmp_path), default_mode), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 1000) + int(adaptive) + 2 * int(default_mode) + 4 * int(library)
+    mp.spawn(_worker, args=(world, port, adaptive, side, steps, str(tmp_path), default_mode, library), nprocs=world, join=True)
     sc = _scene(adaptive or default_mode, side)
     ctx = apbf_b200.Context(dims=sc.dims)
     ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if adaptive else 1, mSmallestTargetRadius=sc.smallest_target_radius)
