@@ -837,6 +837,22 @@ k_green_stream(const emit_args A)
 					gmax[0] = max(gmax[0], gmin[0]); gmax[1] = max(gmax[1], gmin[1]); gmax[2] = max(gmax[2], gmin[2]);
 					if (FUSED) qb = A.qb4[id];
 				}
+				if (SEARCH == 0) {
+					// A search box at least as wide as the whole grid on some axis: the reference walks aliased cells a second time
+					// there and appends those pairs twice (neighborhood_green.comp:69-79 + :40-47); every cell is
+					// visited once here.  The caller is told through sticky flag bit 2 (apbf_ctx_device_flags).  (The box of the
+					// reference: with the search range itself, not the cutoff the fused pass may have shrunk it to.)
+					bool wide = false;
+					if (valid) {
+						const float pq[3] = { me.x, me.y, me.z };
+#pragma unroll
+						for (int d = 0; d < DIMS; d++) {
+							const uint32_t lo = apbf_map_axis(pq[d] - r_lane, g, d), hi = apbf_map_axis(pq[d] + r_lane, g, d);
+							wide = wide || (hi >= lo && hi - lo >= axis_cap);
+						}
+					}
+					if (__any_sync(0xffffffffu, wide) && lane == 0u) atomicOr(A.misc + MW_FLAGS, 4u);
+				}
 				__syncwarp();
 				s_q[w][lane] = make_float4(me.x, me.y, me.z, FUSED ? qb.x : me.w);
 				if (FUSED) { s_u[w][lane] = qb.y; s_T[w][lane] = me.w; }

@@ -76,6 +76,17 @@ def _res_for(extent, cell):
     return res
 
 
+def _res_near(extent, h):
+    """the resolution whose cell size extent / 2^res is closest to h (in ratio): cells much larger than the search range add
+    candidates to every distance-test batch, cells much smaller add cells to every walk (measured: profiles/r02_variants.md)"""
+    best, res = None, 1
+    for k in range(1, 10):
+        d = abs(np.log((extent / (1 << k)) / h))
+        if best is None or d < best:
+            best, res = d, k
+    return res
+
+
 def pool_walls(mn, mx, r, dims=3, wall=4.0):
     """source/pool.cpp:30-40"""
     mn = np.asarray(mn, np.float32); mx = np.asarray(mx, np.float32)
@@ -105,8 +116,8 @@ def uniform_block(side=64, r=1.0, jitter=0.0, seed=1234, dims=3, res_log2=None, 
     origin = (-(side - 1) * r, -(side - 1) * r, -(side - 1) * r if dims == 3 else 0.0)
     arrays = _lattice_state(counts, origin, r, jitter, seed, dims)
     lo = -(half + 4 * r); hi = half + 4 * r
-    if res_log2 is None:
-        res_log2 = _res_for(hi - lo, 4.0 * r)
+    if res_log2 is None:   # (blocks below 100^3 keep the rule the golden fixtures of tests/golden were seeded with)
+        res_log2 = _res_near(hi - lo, 4.0 * r) if side >= 100 else _res_for(hi - lo, 4.0 * r)
     if shuffle:
         arrays = shuffle_state(arrays, seed)
     sc = Scene(name=f"uniform_{side}^{dims}" + ("_jitter" if jitter else ""), dims=dims, arrays=arrays,
@@ -114,6 +125,56 @@ def uniform_block(side=64, r=1.0, jitter=0.0, seed=1234, dims=3, res_log2=None, 
                solver_iterations=4, smallest_target_radius=r)
     sc.box_min, sc.box_max = pool_walls((-half - wall_gap,) * 3, (half + wall_gap,) * 3, r, dims)
     return sc
+
+
+def uniform_block_brick(side, rank, world, r=1.0, jitter=0.1, seed=1234, res_log2=None):
+    """The particles of uniform_block(side) that ONE rank of a brick partition owns (apbf_b200/multi_gpu.py: the bricks are the
+    halves of the search grid along z, then y, then x), generated without ever holding the whole scene: at 400^3 = 64 M
+    particles eight ranks each seeding the full lattice would need ~100 GB of host memory.  `side` must be even: the block is
+    centred on the origin and the cuts are the coordinate planes, so a lattice site belongs to the half its index says (the
+    jitter is smaller than r).  The jitter is a hash of the global lattice index: the union over the ranks is one well-defined
+    scene, whatever the number of ranks.  Returns (scene with the brick's arrays, total number of particles)."""
+    assert side % 2 == 0 and world in (1, 2, 4, 8) and jitter < r
+    lw = {1: 0, 2: 1, 4: 2, 8: 3}[world]
+    lo, hi = [0, 0, 0], [side, side, side]
+    for b in range(lw):
+        axis = 2 - b                                  # bit 0 of the rank (MSB first): z, then y, then x
+        half = (rank >> (lw - 1 - b)) & 1
+        lo[axis], hi[axis] = (side // 2, side) if half else (0, side // 2)
+    gx, gy, gz = np.meshgrid(np.arange(lo[0], hi[0], dtype=np.uint32), np.arange(lo[1], hi[1], dtype=np.uint32),
+                             np.arange(lo[2], hi[2], dtype=np.uint32), indexing="ij")
+    g = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], axis=1)
+    del gx, gy, gz
+    n = g.shape[0]
+    gid = (g[:, 0].astype(np.uint64) * np.uint64(side) + g[:, 1].astype(np.uint64)) * np.uint64(side) + g[:, 2].astype(np.uint64)
+    pos = np.float32(-(side - 1) * r) + np.float32(2.0 * r) * g.astype(np.float32)
+    del g
+    if jitter:
+      with np.errstate(over="ignore"):
+        for d in range(3):
+            h = (gid * np.uint64(3) + np.uint64(d) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+            h ^= h >> np.uint64(33); h *= np.uint64(0xFF51AFD7ED558CCD); h ^= h >> np.uint64(33); h *= np.uint64(0xC4CEB9FE1A85EC53); h ^= h >> np.uint64(33)
+            u = (h >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / (1 << 24))          # [0, 1)
+            pos[:, d] += (u * np.float32(2.0 * jitter) - np.float32(jitter)).astype(np.float32)
+    del gid
+    ipos = np.zeros((n, 4), np.int32)
+    ipos[:, :3] = np.trunc(pos * np.float32(POS_RESOLUTION)).astype(np.int32)
+    del pos
+    radius = np.full(n, r, np.float32)
+    arrays = dict(index_list=np.arange(n, dtype=np.uint32), position=ipos, velocity=np.zeros((n, 4), np.float32),
+                  inverse_mass=np.full(n, 1.0 / (2.0 * r) ** 3, np.float32), radius=radius, pos_backup=ipos.copy(),
+                  transferring=np.zeros(n, np.uint32), target_radius=radius.copy(), kernel_width=np.full(n, r * KERNEL_SCALE, np.float32),
+                  boundariness=np.ones(n, np.float32), boundary_distance=np.full(n, int(r * POS_RESOLUTION), np.uint32))
+    perm = np.random.default_rng(seed + rank).permutation(n)       # hidden slots in random order: exercises the sort / reorder
+    arrays = {k: (v if k == "index_list" else v[perm]) for k, v in arrays.items()}
+    half = side * r
+    glo, ghi = -(half + 4 * r), half + 4 * r
+    if res_log2 is None:
+        res_log2 = _res_near(ghi - glo, 4.0 * r)
+    sc = Scene(name=f"uniform_{side}^3_jitter_brick{rank}of{world}", dims=3, arrays=arrays, min_pos=(glo,) * 3, max_pos=(ghi,) * 3, res_log2=res_log2,
+               basic_pbf=True, solver_iterations=4, smallest_target_radius=r)
+    sc.box_min, sc.box_max = pool_walls((-half,) * 3, (half,) * 3, r, 3)
+    return sc, side ** 3
 
 
 def waterfall_boxes(mn, mx, r, dims=3, wall=4.0):

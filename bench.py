@@ -41,7 +41,7 @@ SLAB_DAM_BREAK = {2: dict(nx=100, ny=100, nz=200), 4: dict(nx=100, ny=200, nz=20
 # bounded sample of each workload for the CPU arm (the oracle needs ~10 us per particle-substep and thread)
 CPU_SAMPLE = {"dam_break_1M": "dam_break_262k", "uniform_64": "uniform_64", "dam_break_1M_default_mode": "dam_break_64k_default_mode",
               "dam_break_1M_split_merge": "dam_break_64k_split_merge", "waterfall_16M": "waterfall_262k", "waterdrop_4M": "waterdrop_500k",
-              "uniform_256": "uniform_64", "uniform_160": "uniform_64", "uniform_100": "uniform_64"}
+              "uniform_256": "uniform_64", "uniform_200": "uniform_64", "uniform_160": "uniform_64", "uniform_100": "uniform_64"}
 
 
 def make_scene(name, world=1, res_log2=None):
@@ -390,7 +390,8 @@ def run_operators(gpu, torch, workload, steps, search="green", device=0):
 def run_extras(gpu, torch, peak, device, quick):
     """the configs of BASELINE.json the headline is not quoted on, a few steps each (N = 1)"""
     out = {}
-    plan = [("uniform_64", "green"), ("uniform_256", "green"), ("waterdrop_4M", "green"), ("waterfall_16M", "green"), ("dam_break_1M", "binary")]
+    plan = [("uniform_64", "green"), ("uniform_200", "green"), ("uniform_256", "green"), ("waterdrop_4M", "green"), ("waterfall_16M", "green"),
+            ("dam_break_1M", "binary")]
     if quick:
         plan = [("uniform_64", "green")]
     for wl, search in plan:

@@ -20,16 +20,16 @@ def _brick_arrays(sc, rank, world, multi_gpu):
 class SlabRun:
     """one scene in bricks on this rank: Sim + the slab protocol (library loop by default, Python loop with --mg-python)"""
 
-    def __init__(self, gpu, torch, sc, meta, rank, world, local_rank, python_loop, ghost_frac=None):
+    def __init__(self, gpu, torch, sc, meta, rank, world, local_rank, python_loop, ghost_frac=None, brick_arrays=None, n_total=None):
         from apbf_b200 import multi_gpu
         self.gpu, self.torch, self.sc, self.meta = gpu, torch, sc, meta
         self.ctx = gpu.Context(device=local_rank, dims=sc.dims)
         self.ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if meta["adaptive"] else 1, mSmallestTargetRadius=sc.smallest_target_radius)
-        arrays = _brick_arrays(sc, rank, world, multi_gpu)
+        arrays = brick_arrays if brick_arrays is not None else _brick_arrays(sc, rank, world, multi_gpu)   # (a scene seeded brick by brick)
         self.n = len(arrays["position"])
-        self.n_total = sc.n
+        self.n_total = int(n_total if n_total is not None else sc.n)
         # ghosts: the layers of particles within the halo range of the brick's faces
-        halo_range = float(sc.arrays["kernel_width"].max()) * (1.5 if meta["adaptive"] else 1.0) * 1.05
+        halo_range = float(arrays["kernel_width"].max()) * (1.5 if meta["adaptive"] else 1.0) * 1.05
         side = max(self.n, 1) ** (1.0 / 3.0)
         layers = halo_range / 2.0 + 1.0
         self.ghost_cap = int(max(400_000 if self.n <= 1_200_000 else 0, 6.0 * side * side * layers * 1.3)) if ghost_frac is None else int(self.n * ghost_frac)
@@ -181,15 +181,19 @@ def run(args, rank, world, local_rank, peak, peak_src, emit, ClockSampler, make_
     if not args.no_mg_extra:
         parity = n_rank_parity(gpu, torch, dist, rank, world, local_rank, make_scene, args.mg_python)
         # configs[4] at 8 M particles per GPU: uniform_200 on one GPU's worth per rank (uniform_400 = 64 M on 8 GPUs)
+        from apbf_b200 import scenes
         side = {2: 252, 4: 318, 8: 400}[world]
-        big, bmeta = make_scene(f"uniform_{side}", world)
-        brun = SlabRun(gpu, torch, big, bmeta, rank, world, local_rank, args.mg_python)
+        big, big_total = scenes.uniform_block_brick(side, rank, world)       # this rank's brick only: the whole lattice never exists on one host
+        bmeta = dict(adaptive=False, pairs_per_particle=40, slab=True)
+        brun = SlabRun(gpu, torch, big, bmeta, rank, world, local_rank, args.mg_python, brick_arrays=big.arrays, n_total=big_total)
         bms = _time_steps(torch, dist, brun, 5, 3)
         bstats = brun.sim.stats()
         bflags = brun.ctx.device_flags()
-        extra = {f"uniform_{side}_in_bricks": {"particles_total": int(big.n), "particles_per_gpu": int(big.n // world), "ms_per_step": bms / 5,
-                                               "value": big.n * 5 / (bms * 1e-3), "pairs_rank0": bstats["pairs_kept"], "device_flags": bflags,
-                                               "ghost_capacity": brun.ghost_cap, "slab": dict(brun.dom.stats) if hasattr(brun.dom, "stats") else {}}}
+        extra = {f"uniform_{side}_in_bricks": {"particles_total": int(big_total), "particles_per_gpu": int(big_total // world), "res_log2": big.res_log2,
+                                               "ms_per_step": bms / 5, "value": big_total * 5 / (bms * 1e-3), "pairs_rank0": bstats["pairs_kept"],
+                                               "device_flags": bflags, "ghost_capacity": brun.ghost_cap, "driver": brun.driver[:7],
+                                               "slab": dict(brun.dom.stats) if hasattr(brun.dom, "stats") else {},
+                                               "compare_with": "extra.uniform_200 of the N = 1 line (8 M particles on one GPU)"}}
         brun.close()
 
     if rank == 0:

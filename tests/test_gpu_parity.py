@@ -687,3 +687,28 @@ def test_incompressibility_odd_masses(gpu, orc):
     print({k: (v.get("max_units", v.get("max_err_units")), round(v.get("frac_equal", v.get("frac_exact", 0.0)), 4)) for k, v in rep.items() if k != "lambda"})
     for k in ("density", "sq_grad_sum", "grad_sum", "lambda", "position_shift"):
         assert rep[k]["within_bar"], (k, rep[k])
+
+
+def test_search_box_wider_than_the_grid_is_flagged(gpu, orc):
+    """neighborhood_green.comp:69-79 walks gridMin..gridMax with cell hashes that keep only the low `res` bits per axis: a box
+    at least 2^res cells wide visits aliased cells twice and the reference appends those pairs twice.  The kernels visit every
+    cell once; the result is the reference's list with the duplicates removed, and sticky flag bit 2 tells the caller."""
+    sc = scenes.uniform_block(6, jitter=0.2, shuffle=True, res_log2=1)      # 2 x 2 x 2 cells, range 4 = more than the grid
+    s = orc.default_settings()
+    st = oracle_state(orc, sc)
+    epairs = orc.green_apply(st, s, 3, 3.0, sc.min_pos, sc.max_pos, sc.res_log2, sc.n * sc.n * 8)
+    ctx = gpu.Context()
+    L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=sc.n * sc.n)
+    gpu.neighborhood_green(ctx).set_data(L).set_range_scale(3.0).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2).apply()
+    assert ctx.device_flags() & 4
+    got = L.read_pairs()
+    key = lambda p: p[:, 0].astype(np.uint64) << np.uint64(32) | p[:, 1].astype(np.uint64)
+    assert len(epairs) > len(got)                                            # the oracle restates the duplicates
+    assert len(np.unique(key(got))) == len(got)
+    assert np.array_equal(np.unique(key(epairs)), np.sort(key(got)))
+    # and a box inside the grid leaves the flag alone
+    ctx2 = gpu.Context()
+    sc2 = scenes.uniform_block(12, jitter=0.2, shuffle=True)
+    L2 = gpu.ParticleLists(ctx2, sc2.arrays, neighbor_capacity=sc2.n * 80)
+    gpu.neighborhood_green(ctx2).set_data(L2).set_range_scale(1.0).set_position_range(sc2.min_pos, sc2.max_pos, sc2.res_log2).apply()
+    assert ctx2.device_flags() == 0
