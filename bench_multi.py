@@ -29,7 +29,8 @@ class SlabRun:
         self.n = len(arrays["position"])
         self.n_total = int(n_total if n_total is not None else sc.n)
         # ghosts: the layers of particles within the halo range of the brick's faces
-        halo_range = float(arrays["kernel_width"].max()) * (1.5 if meta["adaptive"] else 1.0) * 1.05
+        kw_max = float(arrays["kernel_width"].max()) if self.n else float(sc.arrays["kernel_width"].max())
+        halo_range = kw_max * (1.5 if meta["adaptive"] else 1.0) * 1.05
         side = max(self.n, 1) ** (1.0 / 3.0)
         layers = halo_range / 2.0 + 1.0
         self.ghost_cap = int(max(400_000 if self.n <= 1_200_000 else 0, 6.0 * side * side * layers * 1.3)) if ghost_frac is None else int(self.n * ghost_frac)
@@ -76,11 +77,14 @@ def _time_steps(torch, dist, run, steps, warmup):
 
 
 def n_rank_parity(gpu, torch, dist, rank, world, local_rank, make_scene, python_loop):
-    """a 125 000-particle dam break (adaptive) and a 64^3 uniform block: N ranks in bricks vs rank 0 alone, 3 substeps, every
-    list compared bit for bit after gathering the bricks in rank order"""
+    """the headline's dam break at half the edge length (adaptive; 125 000 particles per rank, balanced over the bricks like the
+    full-size scene) and a 48^3 uniform block: N ranks in bricks vs rank 0 alone, 3 substeps, every list compared bit for bit
+    after gathering the bricks in rank order"""
     from apbf_b200 import scenes
+    import bench
+    half = {k: (v // 2 if k in ("nx", "ny", "nz") else v) for k, v in bench.SLAB_DAM_BREAK[world].items() if k != "res_log2"}
     out = {}
-    for name, sc, meta in (("dam_break_125k_adaptive", scenes.dam_break(50, 50, 50 * (2 if world > 1 else 1), adaptive=True), dict(adaptive=True, pairs_per_particle=150)),
+    for name, sc, meta in ((f"dam_break_{world}x125k_adaptive", scenes.dam_break(adaptive=True, **half), dict(adaptive=True, pairs_per_particle=150)),
                            ("uniform_48", scenes.uniform_block(48, jitter=0.1, shuffle=True), dict(adaptive=False, pairs_per_particle=40))):
         run = SlabRun(gpu, torch, sc, meta, rank, world, local_rank, python_loop, ghost_frac=1.5)
         for _ in range(3):
