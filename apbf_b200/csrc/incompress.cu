@@ -3,7 +3,7 @@
 //
 // The reference scatters every pair's contribution with integer atomics (5 per pair in pass 1, 3 per pair in pass 3) and
 // spills a 16-byte gradient per pair between the passes.  All accumulators are integers, so any summation order gives
-// the same bits.  Here a warp owns 32 consecutive particles; 8 lanes walk one particle's contiguous pair segment at a
+// the same bits.  Here a warp owns 32 consecutive particles; 4 lanes walk one particle's contiguous pair segment at a
 // time and accumulate in registers, then the per-particle sums are transposed so that all 32 lanes finish one particle
 // each:
 //   prologue  (k_begin_iteration): [pending deltas] + [box_collision] + pack {position, mass} per id into P4
@@ -20,7 +20,11 @@
 namespace {
 
 constexpr int SWEEP_THREADS = 256; // 8 warps = 256 particles per CTA tile
-constexpr int SWEEP_ILP = 4;       // pairs one lane has in flight: 8 lanes x 4 cover a typical 30-pair segment in one go
+constexpr int SWEEP_ILP = 4;       // pairs one lane has in flight
+// Lanes per particle.  Four lanes walk one particle's segment, eight particles per round, four rounds per warp tile: a segment of
+// 25 pairs (the dam break's mean) costs 7 slots per lane = 28 pair slots, where eight lanes per particle cost 4 x 8 = 32; the
+// shuffle reductions shrink from three stages to two and the transposes from eight rounds to four (r02: -12 % on both sweeps).
+constexpr int LPP = 4, PPR = 32 / LPP, ROUNDS = 32 / PPR;
 #define R_INC APBF_INCOMPRESSIBILITY_DATA_RESOLUTION
 #define FULL 0xffffffffu
 
@@ -42,6 +46,7 @@ struct sweep_args {
 	float4*         E4;   // {emptyDirection.xyz, 0}  (boundariness method 2)
 	int4*           delta;
 	int4*           push;
+	float*          kp;   // Gauss gradient kernel only: per pair (a, b) the scalar k with grad W_a(r) = k * r, written by T1, reused by T2
 	const float4*   bmin;
 	const float4*   bmax;
 	uint32_t        n_boxes;
@@ -58,11 +63,10 @@ __device__ __forceinline__ float move_towards_abs(float oldValue, float newValue
 	return oldValue + glsl_min(maxStep, glsl_max(-maxStep, step));
 }
 
-__device__ __forceinline__ int sum8(int v) // the 8 lanes of a group hold the same total afterwards
+__device__ __forceinline__ int sum_group(int v) // the LPP lanes of a group hold the same total afterwards
 {
-	v += __shfl_xor_sync(FULL, v, 1);
-	v += __shfl_xor_sync(FULL, v, 2);
-	v += __shfl_xor_sync(FULL, v, 4);
+#pragma unroll
+	for (int o = 1; o < LPP; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
 	return v;
 }
 
@@ -113,18 +117,18 @@ __global__ void k_begin_iteration(sweep_args A)
 
 // ---- T1 -------------------------------------------------------------------------------------------------------------------------
 template <int HK, int GK, bool COM>
-__global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
+__global__ void __launch_bounds__(SWEEP_THREADS, (HK == 1 && GK == 1 && !COM) ? 5 : 1) k_density_lambda(sweep_args A)
 {
 	const uint32_t n = min(*A.len, A.misc[MW_N_OWNED]); // owned particles only; a ghost's lambda arrives by halo exchange
 	const bool has_asym = A.misc[MW_N_ASYM] != 0u;
-	const unsigned lane = threadIdx.x & 31u, sub = lane & 7u, grp = lane >> 3;
+	const unsigned lane = threadIdx.x & 31u, sub = lane & (LPP - 1u), grp = lane / LPP;
 	const uint32_t warps_per_grid = gridDim.x * (SWEEP_THREADS / 32);
 	for (uint32_t tile = blockIdx.x * (SWEEP_THREADS / 32) + (threadIdx.x >> 5); (size_t)tile * 32 < n; tile += warps_per_grid) {
 		const uint32_t base = tile * 32u;
 		int my_dens = 0, my_sq = 0, my_gx = 0, my_gy = 0, my_gz = 0, my_cx = 0, my_cy = 0, my_cz = 0, my_cw = 0;
 #pragma unroll 1
-		for (int r = 0; r < 8; r++) { // round r: group g sweeps particle base + 4r + g
-			const uint32_t a = base + r * 4 + grp;
+		for (int r = 0; r < ROUNDS; r++) { // round r: group g sweeps particle base + PPR r + g
+			const uint32_t a = base + r * PPR + grp;
 			int dens = 0, sq = 0, gx = 0, gy = 0, gz = 0, cx = 0, cy = 0, cz = 0, cw = 0;
 			if (a < n) {
 				// (measured, r02c: the branch-free K-slot form of the apply sweep -- all gathers of a trip issued up front, t2_pairs --
@@ -136,23 +140,24 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
 				hp.w = kg.x; hp.c0 = kh.x; hp.c1 = kh.y;
 				gp.w = kg.x; gp.c0 = kg.y; gp.c1 = kg.z;
 				const uint32_t beg = min(A.offsets[a], A.pair_cap), end = min(A.offsets[a + 1], A.pair_cap);
-				for (uint32_t e0 = beg + sub; e0 < end; e0 += 8 * SWEEP_ILP) { // SWEEP_ILP pairs per lane in flight
+				for (uint32_t e0 = beg + sub; e0 < end; e0 += LPP * SWEEP_ILP) { // SWEEP_ILP pairs per lane in flight
 					uint32_t bb[SWEEP_ILP];
 					int4 qq[SWEEP_ILP];
 #pragma unroll
-					for (int u = 0; u < SWEEP_ILP; u++) bb[u] = (e0 + 8 * u < end) ? A.nbl[e0 + 8 * u] & NB_ID_MASK : a;
+					for (int u = 0; u < SWEEP_ILP; u++) bb[u] = (e0 + LPP * u < end) ? A.nbl[e0 + LPP * u] & NB_ID_MASK : a;
 #pragma unroll
 					for (int u = 0; u < SWEEP_ILP; u++) qq[u] = A.P4[bb[u]];
 #pragma unroll
 					for (int u = 0; u < SWEEP_ILP; u++) {
-						if (e0 + 8 * u >= end) break;
+						if (e0 + LPP * u >= end) break;
 						const int4 iq = qq[u];
 						const float mN = __int_as_float(iq.w); // neighbour's mass = 1 / inverse mass
 						const int dxi = iq.x - ip.x, dyi = iq.y - ip.y, dzi = iq.z - ip.z; // int subtract first, incompressibility_1.comp:51
 						const float rx = (float)dxi * INV_R_POS, ry = (float)dyi * INV_R_POS, rz = (float)dzi * INV_R_POS;
 						const float r2 = dot3(rx, ry, rz, rx, ry, rz);
-						float W; vec3f g;
-						pair_eval<HK, GK>(hp, gp, rx, ry, rz, r2, W, g);
+						float W, gk; vec3f g;
+						pair_eval<HK, GK>(hp, gp, rx, ry, rz, r2, W, g, gk);
+						if (GK == 1) A.kp[e0 + LPP * u] = gk; // the apply sweep's gradient of this pair and, between equal widths, of its mirror
 						// x / invMassN * 2^18 (:55-59): 2^18 is a power of two, so (x * mN) * 2^18 == x * (mN * 2^18) bit for bit.
 						// (x * (1 / invMassN) instead of x / invMassN: identical whenever the mass is a power of two -- every scene seeded
 						// by initialize.cpp:16-27 with r a power of two; otherwise the product can differ from the quotient in the last
@@ -170,11 +175,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
 					}
 				}
 			}
-			dens = sum8(dens); sq = sum8(sq); gx = sum8(gx); gy = sum8(gy); gz = sum8(gz);
-			if (COM) { cx = sum8(cx); cy = sum8(cy); cz = sum8(cz); cw = sum8(cw); }
-			// transpose: lane j finishes particle base + j; its sums sit in group j & 3 during round j >> 2
-			const int src = (int)(lane & 3u) * 8;
-			const bool mine = (lane >> 2) == (unsigned)r;
+			dens = sum_group(dens); sq = sum_group(sq); gx = sum_group(gx); gy = sum_group(gy); gz = sum_group(gz);
+			if (COM) { cx = sum_group(cx); cy = sum_group(cy); cz = sum_group(cz); cw = sum_group(cw); }
+			// transpose: lane j finishes particle base + j; its sums sit in group j % PPR during round j / PPR
+			const int src = (int)(lane % PPR) * LPP;
+			const bool mine = (lane / PPR) == (unsigned)r;
 			int t;
 			t = __shfl_sync(FULL, dens, src); if (mine) my_dens = t;
 			t = __shfl_sync(FULL, sq, src);   if (mine) my_sq = t;
@@ -246,20 +251,25 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_density_lambda(sweep_args A)
 	}
 }
 
-// K x 8 pairs of one particle's segment per call: lane `sub` of the group takes the pairs e0, e0 + 8, ...  All 2 K gathers are
+// K x LPP pairs of one particle's segment per call: lane `sub` of the group takes the pairs e0, e0 + LPP, ...  All 2 K gathers are
 // issued before the first pair is evaluated, and there is no branch in here for the compiler to sink a load into (with a `break`
 // per pair it did: LDG.128, ~60 instructions, LDG.128, ... -- the L2 latencies of a lane in a row).  A slot behind the segment's
 // end gathers the particle itself: r = 0, every gradient kernel is zero there, the slot adds nothing (and its "mirrored" bit is
 // clear, so it never takes the push path).
 template <int K, int GK, bool ASYM>
 __device__ __forceinline__ void t2_pairs(const sweep_args& A, uint32_t e0, uint32_t end, uint32_t a, const int4 ip, const float4 la, const float4 e0v,
-                                         bool filter, bool push_a, int& sx, int& sy, int& sz, int& hit)
+                                         bool filter, bool push_a, bool kp_ok, int& sx, int& sy, int& sz, int& hit)
 {
 	uint32_t nn[K];
 	int4 qq[K];
 	float4 ll[K];
+	float kk[K];
 #pragma unroll
-	for (int u = 0; u < K; u++) nn[u] = (e0 + 8 * u < end) ? __ldg(A.nbl + e0 + 8 * u) : a;
+	for (int u = 0; u < K; u++) nn[u] = (e0 + LPP * u < end) ? __ldg(A.nbl + e0 + LPP * u) : a;
+	if (GK == 1) {
+#pragma unroll
+		for (int u = 0; u < K; u++) kk[u] = (e0 + LPP * u < end) ? __ldg(A.kp + e0 + LPP * u) : 0.0f;
+	}
 #pragma unroll
 	for (int u = 0; u < K; u++) { qq[u] = __ldg(A.P4 + (nn[u] & NB_ID_MASK)); ll[u] = __ldg(A.L4 + (nn[u] & NB_ID_MASK)); }
 #pragma unroll
@@ -283,12 +293,26 @@ __device__ __forceinline__ void t2_pairs(const sweep_args& A, uint32_t e0, uint3
 		}
 		if (mirrored) { // the pair (b, a): b shifts a with b's lambda and b's kernel width, diff = pos_a - pos_b
 			kpar gp_b; gp_b.w = lb.y; gp_b.c0 = lb.z; gp_b.c1 = lb.w;
-			const vec3f g = kgrad_fast<GK>(gp_b, -rx, -ry, -rz, r2);
+			vec3f g;
+			if (GK == 1) {
+				// Gauss: grad W_b(-r) = k_b * (-r), and k_b depends on b's width and |r|^2 alone.  Between particles of equal width
+				// it is the very number T1 computed for (a, b) -- same constants, same r2 bits -- so it is read back (4 bytes,
+				// coalesced) instead of evaluated again (dot product, expf, three products: 19 of this loop's 50 instructions).
+				float k = kk[u];
+				if (lb.y != la.y) k = gauss_k(gp_b, r2);
+				g.x = k * -rx; g.y = k * -ry; g.z = k * -rz;
+			} else {
+				g = kgrad_fast<GK>(gp_b, -rx, -ry, -rz, r2);
+			}
 			const float f = lb.x < 0.0f ? lb.x * R_POS : 0.0f; // (lambda >= 0 pushes nothing: x * 0 truncates to 0)
 			sx += f2i(g.x * f); sy += f2i(g.y * f); sz += f2i(g.z * f);
 		} else if (push_a) { // nobody gathers (a, b): push it like the reference does (:63-66)
 			kpar gp_a; gp_a.w = la.y; gp_a.c0 = la.z; gp_a.c1 = la.w;
-			const vec3f g = kgrad_fast<GK>(gp_a, rx, ry, rz, r2);
+			vec3f g;
+			if (GK == 1) { // a's own kernel: what T1 stored -- unless a is a ghost (slabs), whose segment T1 never walked
+				const float k = kp_ok ? kk[u] : gauss_k(gp_a, r2);
+				g.x = k * rx; g.y = k * ry; g.z = k * rz;
+			} else g = kgrad_fast<GK>(gp_a, rx, ry, rz, r2);
 			const float f = la.x * R_POS;
 			atomicAdd(&A.push[b].x, f2i(g.x * f));
 			atomicAdd(&A.push[b].y, f2i(g.y * f));
@@ -298,25 +322,24 @@ __device__ __forceinline__ void t2_pairs(const sweep_args& A, uint32_t e0, uint3
 }
 
 // ---- T2 -------------------------------------------------------------------------------------------------------------------------
-// ASYM: the list holds unmirrored pairs (variable kernel widths), which push with integer atomics like the reference.  Both
-// forms are launched and the one that does not match the list's state returns at once: the host does not know the state
-// without a read-back, and the form without the push path needs fewer registers.
+// ASYM: the list holds unmirrored pairs (variable kernel widths), which push with integer atomics like the reference.  The host
+// does not know the list's state without a read-back, so the kernel holds both forms and takes the one that matches (one launch:
+// the second, empty launch of 3907 CTAs used to cost 5.5 us per iteration; both forms fit the same 64 registers).
 template <int GK, bool ASYM>
-__global__ void __launch_bounds__(SWEEP_THREADS, 4) k_apply_delta(sweep_args A)
+__device__ __forceinline__ void apply_delta_body(const sweep_args& A)
 {
-	if ((A.misc[MW_N_ASYM] != 0u) != ASYM) return;
 	const uint32_t n = *A.len;
 	const uint32_t n_own = min(n, A.misc[MW_N_OWNED]); // a ghost's segment holds only unmirrored pairs onto owned particles: push part only
 	const bool filter = A.s.mBoundarinessCalculationMethod == 2;
 	constexpr bool has_asym = ASYM;
-	const unsigned lane = threadIdx.x & 31u, sub = lane & 7u, grp = lane >> 3;
+	const unsigned lane = threadIdx.x & 31u, sub = lane & (LPP - 1u), grp = lane / LPP;
 	const uint32_t warps_per_grid = gridDim.x * (SWEEP_THREADS / 32);
 	for (uint32_t tile = blockIdx.x * (SWEEP_THREADS / 32) + (threadIdx.x >> 5); (size_t)tile * 32 < n; tile += warps_per_grid) {
 		const uint32_t base = tile * 32u;
 		int my_sx = 0, my_sy = 0, my_sz = 0, my_hit = 0;
 #pragma unroll 1
-		for (int r = 0; r < 8; r++) {
-			const uint32_t a = base + r * 4 + grp;
+		for (int r = 0; r < ROUNDS; r++) {
+			const uint32_t a = base + r * PPR + grp;
 			int sx = 0, sy = 0, sz = 0, hit = 0;
 			{
 				const bool live = a < n;
@@ -326,21 +349,22 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_apply_delta(sweep_args A)
 				float4 e0v = make_float4(0.f, 0.f, 0.f, 0.f);
 				if (filter) e0v = A.E4[ac];
 				const bool push_a = has_asym && la.x < 0.0f;
+				const bool kp_ok = ac < n_own; // T1 walked this particle's segment: its Gauss scalars are in A.kp
 				const uint32_t beg = live ? min(A.offsets[a], A.pair_cap) : 0u, end = live ? min(A.offsets[a + 1], A.pair_cap) : 0u;
-				// the four groups of the warp walk their segments in lock step, 8 x SWEEP_ILP pairs per trip, as many trips as the
-				// longest of the four needs; the number of slots of the last trip is the same for the whole warp (no divergence)
+				// the PPR groups of the warp walk their segments in lock step, LPP x SWEEP_ILP pairs per trip, as many trips as the
+				// longest of them needs; the number of slots of the last trip is the same for the whole warp (no divergence)
 				const uint32_t longest = __reduce_max_sync(FULL, end - beg);
-				for (uint32_t done = 0; done < longest; done += 8 * SWEEP_ILP) {
+				for (uint32_t done = 0; done < longest; done += LPP * SWEEP_ILP) {
 					const uint32_t e0 = beg + done + sub, left = longest - done;
-					if (left > 24u) t2_pairs<4, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, sx, sy, sz, hit);
-					else if (left > 16u) t2_pairs<3, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, sx, sy, sz, hit);
-					else if (left > 8u) t2_pairs<2, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, sx, sy, sz, hit);
-					else t2_pairs<1, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, sx, sy, sz, hit);
+					if (left > 3u * LPP) t2_pairs<4, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, kp_ok, sx, sy, sz, hit);
+					else if (left > 2u * LPP) t2_pairs<3, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, kp_ok, sx, sy, sz, hit);
+					else if (left > 1u * LPP) t2_pairs<2, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, kp_ok, sx, sy, sz, hit);
+					else t2_pairs<1, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, kp_ok, sx, sy, sz, hit);
 				}
 			}
-			sx = sum8(sx); sy = sum8(sy); sz = sum8(sz); hit = sum8(hit);
-			const int src = (int)(lane & 3u) * 8;
-			const bool mine = (lane >> 2) == (unsigned)r;
+			sx = sum_group(sx); sy = sum_group(sy); sz = sum_group(sz); hit = sum_group(hit);
+			const int src = (int)(lane % PPR) * LPP;
+			const bool mine = (lane / PPR) == (unsigned)r;
 			int t;
 			t = __shfl_sync(FULL, sx, src);  if (mine) my_sx = t;
 			t = __shfl_sync(FULL, sy, src);  if (mine) my_sy = t;
@@ -354,6 +378,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_apply_delta(sweep_args A)
 		A.delta[a] = d;
 		if (filter && my_hit) A.boundariness[a] = 0.0f;
 	}
+}
+
+template <int GK>
+__global__ void __launch_bounds__(SWEEP_THREADS, 4) k_apply_delta(sweep_args A)
+{
+	if (A.misc[MW_N_ASYM] != 0u) apply_delta_body<GK, true>(A);
+	else apply_delta_body<GK, false>(A);
 }
 
 // position += delta (+ pushes); xyz only, w is the caller's
@@ -396,6 +427,10 @@ int fill_args(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors* nb, sweep_
 	A.E4 = (float4*)ctx->scratch_get(SLOT_G4, sizeof(float4) * (size_t)n_cap);
 	A.delta = (int4*)ctx->scratch_get(SLOT_DELTA, sizeof(int4) * (size_t)n_cap);
 	A.push = (int4*)ctx->scratch_get(SLOT_PUSH, sizeof(int4) * (size_t)n_cap);
+	if (nb && ctx->settings.mGradientKernelId == 1) {
+		A.kp = (float*)ctx->scratch_get(SLOT_KP, sizeof(float) * (size_t)(nb->capacity ? nb->capacity : 1u));
+		if (!A.kp) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+	}
 	A.misc = ctx->misc();
 	A.s = ctx->settings;
 	A.D = (float)ctx->dims;
@@ -503,11 +538,11 @@ int apbf_solver_iteration(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors
 	if (run_all || (flags & ITER_RUN_T2)) {
 		apbf_prof_scope ps(ctx, PROF_APPLY_DELTA);
 		switch (A.s.mGradientKernelId) {
-			case 0: k_apply_delta<0, false><<<grid, SWEEP_THREADS, 0, st>>>(A); k_apply_delta<0, true><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
-			case 1: k_apply_delta<1, false><<<grid, SWEEP_THREADS, 0, st>>>(A); k_apply_delta<1, true><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
-			case 2: k_apply_delta<2, false><<<grid, SWEEP_THREADS, 0, st>>>(A); k_apply_delta<2, true><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
-			case 3: k_apply_delta<3, false><<<grid, SWEEP_THREADS, 0, st>>>(A); k_apply_delta<3, true><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
-			case 4: k_apply_delta<4, false><<<grid, SWEEP_THREADS, 0, st>>>(A); k_apply_delta<4, true><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+			case 0: k_apply_delta<0><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+			case 1: k_apply_delta<1><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+			case 2: k_apply_delta<2><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+			case 3: k_apply_delta<3><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
+			case 4: k_apply_delta<4><<<grid, SWEEP_THREADS, 0, st>>>(A); break;
 		}
 		APBF_LAUNCHED(ctx);
 	}

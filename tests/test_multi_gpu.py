@@ -17,7 +17,7 @@ def _scene(adaptive, side):
     return sc
 
 
-def _worker(rank, world, port, adaptive, side, steps, out_dir, default_mode=False, library=False):
+def _worker(rank, world, port, adaptive, side, steps, out_dir, default_mode=False, library=False, transport=None):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     import torch
@@ -39,7 +39,9 @@ def _worker(rank, world, port, adaptive, side, steps, out_dir, default_mode=Fals
     sim.upload(mine, n=n_own)
     halo_range = float(sc.arrays["kernel_width"].max()) * (1.5 if adaptive else 1.0) * 1.05
     if library:   # the whole substep inside the library: apbf_sim_mg_substep
-        dom = multi_gpu.LibraryDomain(sim, n_own, world, rank, halo_range, ghost_capacity=cap, adaptive=adaptive, solver_iterations=4, headroom=4.0)
+        dom = multi_gpu.LibraryDomain(sim, n_own, world, rank, halo_range, ghost_capacity=cap, adaptive=adaptive, solver_iterations=4, headroom=4.0,
+                                         transport=transport)
+        assert dom.transport == transport, (dom.transport, transport)   # no silent change of transport
     else:         # the same protocol driven from Python, exchange by exchange
         backend = multi_gpu.CudaRankBackend(sim, n_own, world, rank, halo_range, ghost_capacity=cap)
         dom = multi_gpu.SlabDomain(backend, multi_gpu.TorchComm(torch.device("cuda", rank)), adaptive=adaptive, solver_iterations=4, integrate=True,
@@ -58,9 +60,14 @@ def _worker(rank, world, port, adaptive, side, steps, out_dir, default_mode=Fals
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("library", [False, True])
+@pytest.mark.parametrize("driver", ["python", "library_p2p", "library_nccl"])
 @pytest.mark.parametrize("adaptive,side,default_mode", [(False, 24, False), (True, 20, False), (False, 20, True)])
-def test_n_rank_equals_one_rank(tmp_path, adaptive, side, default_mode, library):
+def test_n_rank_equals_one_rank(tmp_path, adaptive, side, default_mode, driver):
+    """driver: the protocol exchange by exchange from Python over torch.distributed; the library's own loop (apbf_sim_mg_substep) with
+    the peer-to-peer transport (pack kernels store into the receiver's buffer over NVLink, flags instead of NCCL); the same loop over
+    grouped ncclSend / ncclRecv"""
+    library = driver != "python"
+    transport = {"python": None, "library_p2p": "p2p", "library_nccl": "nccl"}[driver]
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -68,8 +75,8 @@ def test_n_rank_equals_one_rank(tmp_path, adaptive, side, default_mode, library)
     import apbf_b200
     world = 4 if torch.cuda.device_count() >= 4 else 2
     steps = 3
-    port = 29500 + (os.getpid() % 1000) + int(adaptive) + 2 * int(default_mode) + 4 * int(library)
-    mp.spawn(_worker, args=(world, port, adaptive, side, steps, str(tmp_path), default_mode, library), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 1000) + int(adaptive) + 2 * int(default_mode) + 4 * ["python", "library_p2p", "library_nccl"].index(driver)
+    mp.spawn(_worker, args=(world, port, adaptive, side, steps, str(tmp_path), default_mode, library, transport), nprocs=world, join=True)
     sc = _scene(adaptive or default_mode, side)
     ctx = apbf_b200.Context(dims=sc.dims)
     ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if adaptive else 1, mSmallestTargetRadius=sc.smallest_target_radius)
