@@ -64,7 +64,8 @@ enum apbf_misc_word {
 // per-kernel-category device timing (CUDA events on the context stream), off by default
 enum apbf_prof_cat {
 	PROF_HASH_SORT = 0, PROF_REORDER, PROF_CELL_RANGES, PROF_EMIT_COUNT, PROF_EMIT_SCAN, PROF_EMIT_FILL, PROF_KW_SPREAD,
-	PROF_KW_COMPACT, PROF_KW_MISC, PROF_BOX, PROF_DENSITY_LAMBDA, PROF_APPLY_DELTA, PROF_COMMIT, PROF_VELOCITY, PROF_SOLVER_PREPARE, PROF_UPDATE_TRANSFERS, PROF_COUNT
+	PROF_KW_COMPACT, PROF_KW_MISC, PROF_BOX, PROF_DENSITY_LAMBDA, PROF_APPLY_DELTA, PROF_COMMIT, PROF_VELOCITY, PROF_SOLVER_PREPARE, PROF_UPDATE_TRANSFERS,
+	PROF_MG_ROUTE, PROF_MG_HALO, PROF_MG_EXCHANGE, PROF_COUNT
 };
 struct apbf_prof_span { int cat; cudaEvent_t beg, end; };
 
@@ -106,6 +107,7 @@ struct apbf_ctx {
 	uint64_t        scratch_epoch = 0;   // bumped whenever a scratch slot is (re)allocated: captured graphs go stale
 	// multi-GPU slabs: ghost particles sort into a second key space and are searched through a second cell table
 	bool            mg_enabled = false;
+	uint32_t        mg_lo[3] = { 0u, 0u, 0u }, mg_hi[3] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }; // this rank's brick in cells, inclusive
 	// a following spread_kernel_width prunes pairs, which can turn a mirrored pair into an unmirrored one: ghosts then
 	// keep ALL their pairs onto owned particles until the prune has decided
 	bool            mg_ghost_all_pairs = false;
@@ -118,12 +120,13 @@ struct apbf_ctx {
 };
 
 int apbf_fail(apbf_ctx* ctx, int code, const char* what, const char* file, int line);
-void apbf_prof_begin(apbf_ctx* ctx, int cat);
-void apbf_prof_end(apbf_ctx* ctx);
-struct apbf_prof_scope { // RAII: times everything enqueued while it is alive
+int  apbf_prof_begin(apbf_ctx* ctx, int cat);   // returns the span's number
+void apbf_prof_end(apbf_ctx* ctx, int span);
+struct apbf_prof_scope { // RAII: times everything enqueued while it is alive; scopes may nest (the slab sections hold the search's)
 	apbf_ctx* c;
-	apbf_prof_scope(apbf_ctx* ctx, int cat) : c(ctx) { if (c->prof_on) apbf_prof_begin(c, cat); }
-	~apbf_prof_scope() { if (c->prof_on) apbf_prof_end(c); }
+	int       span = -1;
+	apbf_prof_scope(apbf_ctx* ctx, int cat) : c(ctx) { if (c->prof_on) span = apbf_prof_begin(c, cat); }
+	~apbf_prof_scope() { if (span >= 0) apbf_prof_end(c, span); }
 };
 
 #define APBF_CUDA(ctx, expr)                                                                   \

@@ -21,7 +21,7 @@ static cudaEvent_t prof_event(apbf_ctx* ctx)
 	return e;
 }
 
-void apbf_prof_begin(apbf_ctx* ctx, int cat)
+int apbf_prof_begin(apbf_ctx* ctx, int cat)
 {
 	apbf_prof_span sp;
 	sp.cat = cat;
@@ -29,11 +29,12 @@ void apbf_prof_begin(apbf_ctx* ctx, int cat)
 	sp.end = prof_event(ctx);
 	cudaEventRecord(sp.beg, ctx->stream);
 	ctx->prof_spans.push_back(sp);
+	return (int)ctx->prof_spans.size() - 1;
 }
 
-void apbf_prof_end(apbf_ctx* ctx)
+void apbf_prof_end(apbf_ctx* ctx, int span)
 {
-	if (!ctx->prof_spans.empty()) cudaEventRecord(ctx->prof_spans.back().end, ctx->stream);
+	if (span >= 0 && (size_t)span < ctx->prof_spans.size()) cudaEventRecord(ctx->prof_spans[(size_t)span].end, ctx->stream);
 }
 
 static void prof_collect(apbf_ctx* ctx)
@@ -196,7 +197,8 @@ int apbf_ctx_profile(apbf_ctx* ctx, int enable)
 
 static const char* const k_prof_names[PROF_COUNT] = {
 	"hash_sort", "reorder", "cell_ranges", "emit_count", "emit_scan", "emit_fill", "kw_spread", "kw_compact", "kw_misc",
-	"box_collision", "density_lambda", "apply_delta", "commit", "velocity", "solver_prepare", "update_transfers"
+	"box_collision", "density_lambda", "apply_delta", "commit", "velocity", "solver_prepare", "update_transfers",
+	"mg_route", "mg_halo", "mg_exchange" // slab sections (mgpu.cu); mg_route and mg_halo contain their own exchange
 };
 
 int apbf_ctx_profile_read(apbf_ctx* ctx, int category, const char** out_name, double* out_ms, uint64_t* out_calls)

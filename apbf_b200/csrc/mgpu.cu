@@ -252,6 +252,7 @@ int apbf_sim_mg_enable(apbf_sim* sim, int rank, int world, float halo_range)
 		m.halo[d] = (d < dims && cell > 0.0f) ? (uint32_t)ceilf(halo_range / cell) + 1u : 0u; // +1: rounding of the cell map
 	}
 	ctx->mg_enabled = world > 1;
+	for (int d = 0; d < 3; d++) { ctx->mg_lo[d] = m.lo[rank][d]; ctx->mg_hi[d] = m.hi[rank][d]; }
 	return APBF_OK;
 }
 
@@ -275,9 +276,11 @@ int apbf_sim_mg_set_counts(apbf_sim* sim, uint32_t n_owned, uint32_t n_total, ui
 
 // Groups the owned particles by destination rank (stable: local order is kept inside a group) into the lists' other buffers
 // and swaps; counts_dev[world] receives the group sizes.  Call with lengths == n_owned.
-int apbf_sim_mg_route(apbf_sim* sim, uint32_t* counts_dev)
+// destination rank of every owned particle, particles per destination, and the stable order by destination (perm: SLOT_TMP_VALS).
+// move_lists: also bring every list into that order (the Python-driven protocol packs contiguous segments); the library's own loop
+// packs and compacts THROUGH perm instead, which saves one copy of the whole state per substep.
+static int route_plan_and_move(apbf_sim* sim, uint32_t* counts_dev, bool move_lists)
 {
-	if (!sim || !counts_dev) return APBF_ERR_INVALID;
 	apbf_ctx* ctx = sim->ctx;
 	APBF_REQUIRE(ctx, sim->mg.enabled);
 	cudaStream_t st = ctx->stream;
@@ -297,6 +300,7 @@ int apbf_sim_mg_route(apbf_sim* sim, uint32_t* counts_dev)
 	else k_route_keys<2><<<apbf_grid(ctx, cap, 256), 256, 0, st>>>((const int32_t*)sim->fluid.particle.position.data, len, g, key_bits, (uint32_t)lw, dest, counts_dev);
 	APBF_LAUNCHED(ctx);
 	APBF_TRY(apbf_radix_sort_pairs(ctx, dest, nullptr, sdest, perm, len, cap, lw > 0 ? lw : 1));
+	if (!move_lists) return APBF_OK;
 	apbf_fluid& f = sim->fluid;
 	apbf_reorder_table t; // every list of the scene in one pass (16-byte loads), like the search's own reorder
 	memset(&t, 0, sizeof t);
@@ -309,6 +313,12 @@ int apbf_sim_mg_route(apbf_sim* sim, uint32_t* counts_dev)
 	APBF_TRY(apbf_write_sequence(ctx, (uint32_t*)f.particle.index_list.reorder_out, len, cap, 0u, 1u, 1u));
 	apbf_sim_swap_buffers(sim);
 	return APBF_OK;
+}
+
+int apbf_sim_mg_route(apbf_sim* sim, uint32_t* counts_dev)
+{
+	if (!sim || !counts_dev) return APBF_ERR_INVALID;
+	return route_plan_and_move(sim, counts_dev, true);
 }
 
 int apbf_sim_mg_pack_state(apbf_sim* sim, uint32_t first, uint32_t count, void* out)
@@ -757,7 +767,8 @@ __global__ void k_mgl_begin(uint32_t* __restrict__ words, uint32_t* len, uint32_
 }
 
 // segment r of the lists (grouped by destination) -> send buffer r; thread (r, k)
-__global__ void k_mgl_pack_route(state_lists L, uint32_t* __restrict__ words, mgl_bufs B, int world, int rank, uint32_t route_cap, mgl_sig S)
+// (perm: the lists' stable order by destination; segment r of it = the particles that go to rank r)
+__global__ void k_mgl_pack_route(state_lists L, const uint32_t* __restrict__ perm, uint32_t* __restrict__ words, mgl_bufs B, int world, int rank, uint32_t route_cap, mgl_sig S)
 {
 	const uint32_t total = (uint32_t)world * route_cap;
 	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -772,7 +783,7 @@ __global__ void k_mgl_pack_route(state_lists L, uint32_t* __restrict__ words, mg
 			if (cnt > route_cap) atomicOr(words + MGL_FLAGS, MGL_FLAG_ROUTE_OVERFLOW);
 		}
 		if (k >= cnt) continue;
-		const uint32_t id = start + k;
+		const uint32_t id = perm[start + k];
 		int4* o = B.p[r] + 1 + STATE_INT4 * (size_t)k;
 		o[0] = L.pos[id]; o[1] = L.vel[id]; o[2] = L.backup[id];
 		o[3] = make_int4((int)L.inv_mass[id], (int)L.radius[id], (int)L.transferring[id], (int)L.target_radius[id]);
@@ -808,11 +819,11 @@ __global__ void k_mgl_route_plan(uint32_t* __restrict__ words, mgl_bufs R, int w
 	words[MGL_MIGRATED] = total_out;
 }
 
-__global__ void k_mgl_copy_stayers(state_lists S, state_lists D, const uint32_t* __restrict__ words, uint32_t capacity)
+__global__ void k_mgl_copy_stayers(state_lists S, state_lists D, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ words, uint32_t capacity)
 {
 	const uint32_t src0 = words[MGL_STAY_SRC], dst0 = words[MGL_STAY_DST], count = words[MGL_STAY];
 	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
-		const uint32_t s = src0 + k, d = dst0 + k;
+		const uint32_t s = perm[src0 + k], d = dst0 + k; // (the stayers keep their order: perm is increasing over them)
 		if (d >= capacity) continue;
 		D.pos[d] = S.pos[s]; D.vel[d] = S.vel[s]; D.backup[d] = S.backup[s];
 		D.inv_mass[d] = S.inv_mass[s]; D.radius[d] = S.radius[s]; D.transferring[d] = S.transferring[s];
@@ -1066,6 +1077,7 @@ int mgl_refresh(apbf_sim* sim, int what)
 	} else if (what == 4) { src16 = dst16 = (int4*)f.particle.position.data; }
 	else return apbf_fail(ctx, APBF_ERR_INVALID, "what", __FILE__, __LINE__);
 	const unsigned grid = apbf_grid(ctx, total, 256);
+	apbf_prof_scope ps(ctx, PROF_MG_EXCHANGE);
 	const mgl_sig S = mgl_begin_exchange(sim);
 	k_mgl_pack<<<grid, 256, 0, ctx->stream>>>(what, src4, src16, stride4, sim->mgl.send_ids, sim->mgl.words, C, send_bufs(sim, S), total, S);
 	APBF_LAUNCHED(ctx);
@@ -1290,21 +1302,26 @@ int apbf_sim_mg_substep(apbf_sim* sim, uint32_t n_substeps)
 		if (default_mode) APBF_TRY(apbf_sim_mg_phase(sim, 8, 0));
 		if (world > 1) {
 			// ---- ROUTE: particles that left the brick change owner with their full state -------------------------------------------
-			APBF_TRY(apbf_sim_mg_route(sim, M.words + MGL_ROUTE)); // grouped by destination in the current buffers; counts on the device
+			{
+			apbf_prof_scope ps_route(ctx, PROF_MG_ROUTE);
+			APBF_TRY(route_plan_and_move(sim, M.words + MGL_ROUTE, false)); // perm = stable order by destination; counts on the device
+			const uint32_t* perm = (const uint32_t*)ctx->scratch_get(SLOT_TMP_VALS, sizeof(uint32_t) * (size_t)cap);
 			const mgl_sig SR = mgl_begin_exchange(sim);
-			k_mgl_pack_route<<<apbf_grid(ctx, (size_t)world * M.route_cap, 256), 256, 0, st>>>(lists_of(sim, false), M.words, send_bufs(sim, SR), world, rank, M.route_cap, SR);
+			k_mgl_pack_route<<<apbf_grid(ctx, (size_t)world * M.route_cap, 256), 256, 0, st>>>(lists_of(sim, false), perm, M.words, send_bufs(sim, SR), world, rank, M.route_cap, SR);
 			APBF_LAUNCHED(ctx);
 			APBF_TRY(mgl_exchange(sim, [&](int) { return 16 + (size_t)M.route_cap * STATE_INT4 * 16; }));
 			k_mgl_route_plan<<<1, 32, 0, st>>>(M.words, recv_bufs(sim, SR), world, rank, cap, SR);
 			APBF_LAUNCHED(ctx);
-			k_mgl_copy_stayers<<<apbf_grid(ctx, cap, 256), 256, 0, st>>>(lists_of(sim, false), lists_of(sim, true), M.words, cap);
+			k_mgl_copy_stayers<<<apbf_grid(ctx, cap, 256), 256, 0, st>>>(lists_of(sim, false), lists_of(sim, true), perm, M.words, cap);
 			APBF_LAUNCHED(ctx);
 			k_mgl_unpack_arrivals<<<apbf_grid(ctx, (size_t)world * M.route_cap, 256), 256, 0, st>>>(lists_of(sim, true), M.words, recv_bufs(sim, SR), world, rank, M.route_cap, cap);
 			APBF_LAUNCHED(ctx);
 			apbf_sim_swap_buffers(sim);
 			k_mgl_begin<<<1, 1, 0, st>>>(M.words, f.particle.length, f.particle.hidden_length, misc);
 			APBF_LAUNCHED(ctx);
+			}
 			// ---- HALO: owned particles inside another rank's grown brick go there as ghosts ----------------------------------------
+			apbf_prof_scope ps_halo(ctx, PROF_MG_HALO);
 			APBF_CUDA(ctx, cudaMemsetAsync(M.words + MGL_HALO_SEND, 0, sizeof(uint32_t) * 8, st));
 			k_mgl_halo_lists<<<apbf_grid(ctx, cap, 256), 256, 0, st>>>((const int32_t*)f.particle.position.data, M.words, g, grown_boxes(sim), C, M.send_ids);
 			APBF_LAUNCHED(ctx);

@@ -247,6 +247,7 @@ struct emit_args {
 	int             cull;
 	uint32_t        table_cells;
 	uint32_t        layers;
+	uint32_t        mg_lo[3], mg_hi[3]; // slabs: this rank's brick in cells (inclusive) -- a box inside it cannot hold a ghost
 	// EMIT_FUSED
 	const int4*     i4;      // {ipos.xyz, bits(original kernel width)} per id
 	const float*    cutoff;  // prune threshold (kernel_width.comp:57) on the squared distance in integer units, per id
@@ -891,7 +892,16 @@ k_green_stream(const emit_args A)
 				const uint32_t nxy = ext[0] * ext[1], ncell = SEARCH == 1 ? 27u : nxy * ext[2];
 				const float inv_nxy = 1.0f / (float)nxy, inv_nx = 1.0f / (float)ext[0];
 				const bool ghost_run = MG && first >= n_owned;
-				const uint32_t n_layers = layers > 1u ? 2u : 1u;
+				// Slabs: ghosts live in the second cell table (their keys carry one extra bit).  It is walked only when it can matter:
+				// a ghost's own candidates are owned particles (first table only), and a box of owned queries that lies inside this
+				// rank's brick holds no cell of another rank.  Interior chunks -- nearly all of them -- walk one table like one GPU does.
+				uint32_t n_layers = layers > 1u ? 2u : 1u;
+				if (MG && n_layers == 2u) {
+					bool inside = true;
+#pragma unroll
+					for (int d = 0; d < DIMS; d++) inside = inside && umin[d] >= A.mg_lo[d] && umin[d] + ext[d] - 1u <= A.mg_hi[d];
+					if (ghost_run || inside) n_layers = 1u;
+				}
 				uint32_t bs_first = 0u, bs_cnt = 0u;
 				if (SEARCH == 1 && lane < 27u) {
 					// the 27 cells around the chunk's cell, in the reference's loop order (z outer, x inner), as ranges of the
@@ -1506,6 +1516,7 @@ int apbf_green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range,
 	A.q4 = q4; A.key_id = key_id; A.range = new_range; A.cell_start = cs; A.cell_end = ce; A.len = p.length; A.g = g;
 	A.range_scale = range_scale; A.counts = counts; A.offsets = offsets; A.pairs = nb->pairs; A.nbl = nbl; A.cap = nb->capacity;
 	A.misc = misc; A.cull = cull; A.table_cells = max_hash; A.layers = emit_mode; A.i4 = K.i4; A.cutoff = K.cutoff; A.kwfx = kwfx;
+	for (int d = 0; d < 3; d++) { A.mg_lo[d] = ctx->mg_lo[d]; A.mg_hi[d] = ctx->mg_hi[d]; }
 	A.qb4 = K.qb4; A.cell_maxw = K.cell_maxw; A.stream = stream; A.stream_blocks = stream_blocks;
 	static const int two_pass = getenv("APBF_TWO_PASS_EMIT") ? 1 : 0; // debugging aid: the count/fill emit instead of stream/regroup
 	// hit-stream blocks staged by the bulk-copy engine: 25 % faster at 5 x 10^8 pairs (2.61 -> 1.97 ms), the same at 3 x 10^7 (r02c)
