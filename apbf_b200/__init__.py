@@ -676,6 +676,15 @@ class Sim:
     def substep(self, n=1):
         _check(self.ctx, self.lib.apbf_sim_substep(self.handle, n))
 
+    def set_graphs(self, enable):
+        """replay substeps as captured CUDA graphs (on by default, see apbf_sim_set_graphs)"""
+        _check(self.ctx, self.lib.apbf_sim_set_graphs(self.handle, 1 if enable else 0))
+
+    def graph_replays(self):
+        c = C.c_uint64()
+        _check(self.ctx, self.lib.apbf_sim_graph_replays(self.handle, C.byref(c)))
+        return c.value
+
     def stats(self):
         w = (C.c_uint32 * 4)()
         _check(self.ctx, self.lib.apbf_sim_stats(self.handle, w))

@@ -51,6 +51,7 @@ int apbf_sim_create(apbf_ctx* ctx, const apbf_sim_config* cfg, apbf_sim** out_si
 	sim->cfg = *cfg;
 	sim->last_dt = 1.0f;
 	sim->no_fuse = getenv("APBF_NO_FUSE") != nullptr; // debugging aid: search and spread_kernel_width as two operators
+	if (const char* g = getenv("APBF_SIM_GRAPHS")) sim->graphs_on = atoi(g) != 0; // 0: enqueue every substep launch by launch
 	sim->boxes = nullptr;
 	memset(&sim->fluid, 0, sizeof sim->fluid);
 	memset(&sim->nb, 0, sizeof sim->nb);
@@ -116,6 +117,8 @@ void apbf_sim_destroy(apbf_sim* sim)
 	if (!sim) return;
 	cudaStreamSynchronize(sim->ctx->stream);
 	apbf_sim_mg_comm_destroy(sim); // the library's own NCCL communicator, if one was made
+	for (apbf_sim_graph& g : sim->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+	if (sim->capture_stream) cudaStreamDestroy(sim->capture_stream);
 	for (void* p : sim->owned) cudaFree(p);
 	apbf_nbr_forget(sim->ctx, sim->nb.pairs);
 	delete sim;
@@ -170,22 +173,24 @@ int apbf_sim_download(apbf_sim* sim, apbf_host_state* h)
 	return APBF_OK;
 }
 
-int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
+} // extern "C"
+
+namespace {
+
+// ---- one substep, enqueued on the context's stream ----------------------------------------------------------------------------------
+int substep_once(apbf_sim* sim)
 {
-	if (!sim) return APBF_ERR_INVALID;
 	apbf_ctx* ctx = sim->ctx;
 	const apbf_sim_config& c = sim->cfg;
-	APBF_TRY(apbf_ctx_set_dimensions(ctx, c.dims));
 	const apbf_settings& s = ctx->settings;
 	const bool unit_scale = c.basic_pbf || s.mBaseKernelWidthOnBoundaryDistance;     // pool.cpp:83
 	const bool adaptive = !c.basic_pbf && !s.mBaseKernelWidthOnBoundaryDistance;     // pool.cpp:87
 	const bool transfers = c.transfers && !c.basic_pbf && (s.mMerge || s.mSplit);    // pool.cpp:73, :99
-	if (transfers && ctx->mg_enabled) return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, "merge / split is not available on slabs", __FILE__, __LINE__);
 	apbf_search_debug follow;
 	memset(&follow, 0, sizeof follow);
 	follow.sorted_index = sim->sorted_index;
 	const apbf_search_debug* dbg = transfers ? &follow : nullptr;
-	for (uint32_t step = 0; step < n_substeps; step++) {
+	{
 		if (c.integrate) {                                                            // pool.cpp:71
 			APBF_TRY(apbf_velocity_handling_apply(ctx, &sim->fluid.particle, c.dt, sim->last_dt, c.accel));
 			sim->last_dt = c.dt;
@@ -223,6 +228,153 @@ int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
 			APBF_TRY(apbf_update_transfers_split_merge_apply(ctx, &sim->fluid, &sim->nb, &sim->tr, c.split_duration, nullptr));
 		else if (c.update_transfers && !c.basic_pbf)
 			APBF_TRY(apbf_update_transfers_apply(ctx, &sim->fluid, &sim->nb, nullptr));
+	}
+	return APBF_OK;
+}
+
+// ---- substeps as CUDA graphs ----------------------------------------------------------------------------------------------------------
+// Every launch of a substep is length-agnostic (lengths are device words, grids come from capacities), so a substep is the same
+// sequence of ~36 launches every time -- except that each search swaps the two buffers of every list.  A graph is therefore captured
+// per buffer parity, keyed by everything on the host that shapes the launches; any change (settings, a re-allocated scratch slot,
+// another pair list made active, profiling switched on) simply misses the key and the substep is enqueued launch by launch again.
+uint64_t fnv(uint64_t h, const void* p, size_t n)
+{
+	const unsigned char* b = (const unsigned char*)p;
+	for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+	return h;
+}
+
+uint64_t state_key(const apbf_sim* sim)
+{
+	const apbf_ctx* ctx = sim->ctx;
+	const apbf_fluid& f = sim->fluid;
+	uint64_t h = 1469598103934665603ull;
+	const void* ptrs[] = { f.particle.index_list.data, f.particle.position.data, f.particle.velocity.data, f.particle.inverse_mass.data,
+	                       f.particle.radius.data, f.particle.pos_backup.data, f.particle.transferring.data, f.target_radius.data,
+	                       f.kernel_width.data, f.boundariness.data, f.boundary_distance.data, sim->nb.pairs, ctx->nbr_struct_pairs, ctx->stream };
+	h = fnv(h, ptrs, sizeof ptrs);
+	h = fnv(h, &ctx->settings, sizeof ctx->settings);
+	h = fnv(h, &sim->cfg, sizeof sim->cfg);
+	const uint64_t words[] = { ctx->scratch_epoch, (uint64_t)ctx->dims, (uint64_t)ctx->nbr_struct_n_cap, (uint64_t)ctx->nbr_valid, (uint64_t)ctx->nbr_public,
+	                           (uint64_t)ctx->stream_blocks_cap, (uint64_t)ctx->match_grid_min, (uint64_t)sim->no_fuse, (uint64_t)ctx->num_sms };
+	h = fnv(h, words, sizeof words);
+	h = fnv(h, &sim->last_dt, sizeof sim->last_dt);
+	return h ? h : 1ull;
+}
+
+void drop_graphs(apbf_sim* sim)
+{
+	for (apbf_sim_graph& g : sim->graphs) {
+		if (g.exec) cudaGraphExecDestroy(g.exec);
+		g = apbf_sim_graph();
+	}
+}
+
+// 1: the substep ran as a graph; 0: not this time (enqueue it the ordinary way); < 0: error
+int substep_as_graph(apbf_sim* sim)
+{
+	apbf_ctx* ctx = sim->ctx;
+	cudaStream_t st = ctx->stream;
+	const uint64_t key = state_key(sim);
+	for (apbf_sim_graph& g : sim->graphs) {
+		if (g.exec && g.key == key) {
+			if (cudaGraphLaunch(g.exec, st) != cudaSuccess) { cudaGetLastError(); drop_graphs(sim); return 0; }
+			// what the captured call did on the host
+			apbf_sim_swap_buffers(sim);
+			sim->last_dt = sim->cfg.integrate ? sim->cfg.dt : sim->last_dt;
+			ctx->nbr_struct_pairs = g.nbr_pairs; ctx->nbr_struct_n_cap = g.nbr_n_cap; ctx->nbr_valid = g.nbr_valid; ctx->nbr_public = g.nbr_public;
+			ctx->launches += g.launches;
+			sim->graph_replays++;
+			return 1;
+		}
+	}
+	if (key == sim->bad_key) return 0;
+	bool seen = false;
+	for (uint64_t k : sim->seen_keys) seen = seen || k == key;
+	if (!seen) { // first visit of this state: run it the ordinary way (scratch slots may still be growing)
+		for (int i = 3; i > 0; i--) sim->seen_keys[i] = sim->seen_keys[i - 1];
+		sim->seen_keys[0] = key;
+		return 0;
+	}
+	// second visit: capture.  Nothing executes during the capture, the graph is launched afterwards.
+	const uint64_t epoch0 = ctx->scratch_epoch, launches0 = ctx->launches;
+	const float last_dt0 = sim->last_dt;
+	// recorded on a stream of the scene's own (the context's stream may be the legacy default stream, which cannot capture; the
+	// nodes do not remember the stream) and launched into the context's stream afterwards
+	if (!sim->capture_stream && cudaStreamCreateWithFlags(&sim->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
+		cudaGetLastError(); sim->capture_stream = nullptr; sim->bad_key = key; return 0;
+	}
+	if (cudaStreamBeginCapture(sim->capture_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); sim->bad_key = key; return 0; }
+	ctx->stream = sim->capture_stream;
+	const int rc = substep_once(sim);
+	ctx->stream = st;
+	cudaGraph_t graph = nullptr;
+	const cudaError_t ce = cudaStreamEndCapture(sim->capture_stream, &graph);
+	cudaGraphExec_t exec = nullptr;
+	bool ok = rc == APBF_OK && ce == cudaSuccess && graph && ctx->scratch_epoch == epoch0;
+	if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+	if (graph) cudaGraphDestroy(graph);
+	if (!ok) { // the host went through a substep, the device did not: put the host back and let the ordinary path run
+		cudaGetLastError();
+		if (exec) cudaGraphExecDestroy(exec);
+		apbf_sim_swap_buffers(sim);
+		sim->last_dt = last_dt0;
+		ctx->launches = launches0;
+		ctx->nbr_valid = false; // (whatever the capture recorded about the pair list did not happen)
+		sim->bad_key = key;
+		return rc != APBF_OK ? rc : 0;
+	}
+	apbf_sim_graph* slot = &sim->graphs[0];
+	if (slot->exec && !sim->graphs[1].exec) slot = &sim->graphs[1];
+	else if (slot->exec && sim->graphs[1].exec) { // both taken by stale states: start over
+		drop_graphs(sim);
+		slot = &sim->graphs[0];
+	}
+	slot->key = key; slot->exec = exec; slot->launches = ctx->launches - launches0;
+	slot->nbr_pairs = ctx->nbr_struct_pairs; slot->nbr_n_cap = ctx->nbr_struct_n_cap; slot->nbr_valid = ctx->nbr_valid; slot->nbr_public = ctx->nbr_public;
+	if (cudaGraphLaunch(exec, st) != cudaSuccess) return apbf_fail(ctx, APBF_ERR_CUDA, "cudaGraphLaunch", __FILE__, __LINE__);
+	sim->graph_replays++;
+	return 1;
+}
+
+} // namespace
+
+extern "C" {
+
+int apbf_sim_set_graphs(apbf_sim* sim, int enable)
+{
+	if (!sim) return APBF_ERR_INVALID;
+	sim->graphs_on = enable ? 1 : 0;
+	if (!enable) drop_graphs(sim);
+	return APBF_OK;
+}
+
+int apbf_sim_graph_replays(const apbf_sim* sim, uint64_t* out)
+{
+	if (!sim || !out) return APBF_ERR_INVALID;
+	*out = sim->graph_replays;
+	return APBF_OK;
+}
+
+int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
+{
+	if (!sim) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	const apbf_sim_config& c = sim->cfg;
+	APBF_TRY(apbf_ctx_set_dimensions(ctx, c.dims));
+	const apbf_settings& s = ctx->settings;
+	const bool transfers = c.transfers && !c.basic_pbf && (s.mMerge || s.mSplit);    // pool.cpp:73, :99
+	if (transfers && ctx->mg_enabled) return apbf_fail(ctx, APBF_ERR_UNSUPPORTED, "merge / split is not available on slabs", __FILE__, __LINE__);
+	// graphs: not while the passes are being timed or counted (events / extra launches), not with merge / split (their lists swap
+	// buffers on their own schedule), not on slabs (apbf_sim_mg_substep drives those)
+	const bool may_graph = sim->graphs_on && !ctx->prof_on && !ctx->search_stats && !transfers && !ctx->mg_enabled;
+	for (uint32_t step = 0; step < n_substeps; step++) {
+		if (may_graph) {
+			const int g = substep_as_graph(sim);
+			if (g < 0) return g;
+			if (g == 1) continue;
+		}
+		APBF_TRY(substep_once(sim));
 	}
 	return APBF_OK;
 }

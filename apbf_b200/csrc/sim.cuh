@@ -38,6 +38,17 @@ struct apbf_mg_loop {
 	uint32_t  seq = 0;                    // exchanges so far (the same on every rank: the protocol is symmetric)
 };
 
+// One substep captured as a CUDA graph (sim.cu).  A graph is valid for exactly the host state it was captured in -- which of the
+// two buffers of every list is current, the scratch allocations, the settings -- summarised in `key`.
+struct apbf_sim_graph {
+	uint64_t        key = 0;
+	cudaGraphExec_t exec = nullptr;
+	uint64_t        launches = 0;       // kernels in the graph (apbf_ctx_launch_count keeps counting)
+	const uint32_t* nbr_pairs = nullptr; // the context's neighbour-structure book-keeping after the substep
+	uint32_t        nbr_n_cap = 0;
+	bool            nbr_valid = false, nbr_public = false;
+};
+
 struct apbf_sim {
 	apbf_ctx*       ctx;
 	apbf_sim_config cfg;
@@ -51,6 +62,12 @@ struct apbf_sim {
 	std::vector<void*> owned;
 	apbf_mg_state   mg;
 	apbf_mg_loop    mgl;
+	int             graphs_on = 1;       // replay captured substeps (apbf_sim_set_graphs; APBF_SIM_GRAPHS=0 turns it off)
+	apbf_sim_graph  graphs[2];           // one per buffer parity
+	cudaStream_t    capture_stream = nullptr; // captures are recorded here (the caller's stream may be the legacy default stream, which cannot capture)
+	uint64_t        seen_keys[4] = {};   // states met recently: a state met twice is worth a capture
+	uint64_t        bad_key = 0;         // a capture of this state failed: do not try again
+	uint64_t        graph_replays = 0;
 	apbf_transfers  tr = {};             // cfg.transfers: the transfer list (pool.cpp:8)
 	uint32_t*       sorted_index = nullptr; // cfg.transfers: the search's permutation of the hidden list, for the transfers to follow
 };

@@ -135,10 +135,12 @@ def run(args, rank, world, local_rank, peak, peak_src, emit, ClockSampler, make_
     dist.barrier(); torch.cuda.synchronize()
     ctx = run_.ctx
     launches0 = ctx.launch_count
-    ctx.profile(True)
-    ms = _time_steps(torch, dist, run_, args.steps, 0)
-    ctx.profile(False)
+    ms = _time_steps(torch, dist, run_, args.steps, 0)          # the timed region: nothing but the substeps on the stream
     launches = ctx.launch_count - launches0
+    prof_steps = max(3, min(args.steps, 20))                     # per-pass durations: further substeps with events around every pass
+    ctx.profile(True)
+    prof_ms = _time_steps(torch, dist, run_, prof_steps, 0)
+    ctx.profile(False)
     prof = ctx.profile_read()
     stats = run_.sim.stats()
     if meta["adaptive"]:
@@ -201,9 +203,22 @@ def run(args, rank, world, local_rank, peak, peak_src, emit, ClockSampler, make_
                                                "slab": dict(brun.dom.stats) if hasattr(brun.dom, "stats") else {},
                                                "compare_with": "extra.uniform_200 of the N = 1 line (8 M particles on one GPU)"}}
         brun.close()
+        # configs[3]: the waterfall scene (11 collision boxes), 252^3 = 16 M particles in all, slab-partitioned over the N GPUs
+        # (compare with extra.waterfall_16M of the N = 1 line: the same scene on one GPU -- strong scaling)
+        wsc = scenes.waterfall()
+        wmeta = dict(adaptive=False, pairs_per_particle=40, slab=True)
+        wrun = SlabRun(gpu, torch, wsc, wmeta, rank, world, local_rank, args.mg_python)
+        wms = _time_steps(torch, dist, wrun, 5, 3)
+        wstats = wrun.sim.stats()
+        extra["waterfall_16M_in_bricks"] = {"particles_total": int(wsc.n), "particles_this_rank": int(wrun.n), "res_log2": wsc.res_log2, "collision_boxes": int(len(wsc.box_min)),
+                                            "ms_per_step": wms / 5, "value": wsc.n * 5 / (wms * 1e-3), "pairs_rank0": wstats["pairs_kept"],
+                                            "device_flags": wrun.ctx.device_flags(), "scaling": "strong (one 16 M scene over N GPUs)",
+                                            "slab": dict(wrun.dom.stats) if hasattr(wrun.dom, "stats") else {},
+                                            "compare_with": "extra.waterfall_16M of the N = 1 line"}
+        wrun.close()
 
     if rank == 0:
-        r = dict(sc=sc, meta=meta, n=n_local, ms=ms, steps=args.steps, prof=prof, stats=stats)
+        r = dict(sc=sc, meta=meta, n=n_local, ms=ms, steps=args.steps, prof=prof, prof_ms=prof_ms, stats=stats)
         roof, passes = roofline_of(r, peak, args.workload, world)
         roof["peak_source"] = peak_src
         line = {

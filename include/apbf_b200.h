@@ -380,6 +380,13 @@ int  apbf_sim_download(apbf_sim* sim, apbf_host_state* host);
  * (box_collision, incompressibility) -> [update_transfers, with the merge / split decisions if cfg.transfers].  Fully asynchronous.
  * The search keeps the pair list in its grouped form only; apbf_sim_neighbors() writes the (id, idN) pairs when asked. */
 int  apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps);
+/* A substep is the same ~36 launches every time (lengths are device words), so after two ordinary substeps apbf_sim_substep
+ * captures it as a CUDA graph -- one per buffer parity, the search swaps the two buffers of every list -- and replays that from
+ * then on; a change of settings, capacities or scratch allocations falls back to ordinary launches and captures again.  On by
+ * default (off while apbf_ctx_profile times the passes, with merge / split, and on slabs); enable = 0 turns it off for this scene,
+ * the environment variable APBF_SIM_GRAPHS=0 for all.  apbf_sim_graph_replays: substeps that ran as a graph so far. */
+int  apbf_sim_set_graphs(apbf_sim* sim, int enable);
+int  apbf_sim_graph_replays(const apbf_sim* sim, uint64_t* out_count);
 /* views of the device-resident lists for callers that want to run single operators on them (apbf_sim_neighbors enqueues the
  * kernel that writes the public (id, idN) list if the last substep has not) */
 int  apbf_sim_fluid(apbf_sim* sim, apbf_fluid* out_fluid);

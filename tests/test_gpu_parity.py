@@ -712,3 +712,33 @@ def test_search_box_wider_than_the_grid_is_flagged(gpu, orc):
     L2 = gpu.ParticleLists(ctx2, sc2.arrays, neighbor_capacity=sc2.n * 80)
     gpu.neighborhood_green(ctx2).set_data(L2).set_range_scale(1.0).set_position_range(sc2.min_pos, sc2.max_pos, sc2.res_log2).apply()
     assert ctx2.device_flags() == 0
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_graph_replay_equals_ordinary_launches(gpu, adaptive):
+    """apbf_sim_substep replays captured CUDA graphs from the third pair of substeps on: same bits as launch by launch, also
+    after a fresh upload in between (lengths are device words, the graphs do not know them)"""
+    sc = scenes.dam_break(20, 20, 20, adaptive=True) if adaptive else scenes.uniform_block(24, jitter=0.2, shuffle=True)
+    out = {}
+    for graphs in (False, True):
+        ctx = gpu.Context(dims=sc.dims)
+        ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if adaptive else 1, mSmallestTargetRadius=sc.smallest_target_radius)
+        sim = gpu.Sim(ctx, sc, neighbor_capacity=sc.n * (300 if adaptive else 80), integrate=True, basic_pbf=not adaptive)
+        sim.set_graphs(graphs)
+        sim.upload(sc.arrays)
+        sim.substep(7)
+        host = gpu.empty_host_arrays(sc.n)
+        assert sim.download(host) == sc.n
+        half = {k: v[: sc.n // 2].copy() for k, v in host.items()}      # carry on with half of the particles
+        half["index_list"] = np.arange(sc.n // 2, dtype=np.uint32)
+        sim.upload(half, n=sc.n // 2)
+        sim.substep(4)
+        host2 = gpu.empty_host_arrays(sc.n)
+        assert sim.download(host2) == sc.n // 2
+        out[graphs] = (host, host2, sim.graph_replays(), sim.neighbor_count())
+        sim.close(); ctx.close()
+    assert out[False][2] == 0 and out[True][2] >= 6
+    assert out[False][3] == out[True][3]
+    for a, b in ((out[False][0], out[True][0]), (out[False][1], out[True][1])):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
