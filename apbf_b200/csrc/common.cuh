@@ -23,7 +23,7 @@ enum apbf_scratch_slot {
 	SLOT_PAIRS_TMP, SLOT_NB_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4, SLOT_KG, SLOT_KH, SLOT_Q4, SLOT_KEY_ID, SLOT_EDIT_COUNTS, SLOT_EDIT_OFFSETS, SLOT_MG_INV, SLOT_I4, SLOT_CUTOFF, SLOT_QB4, SLOT_STREAM, SLOT_TILE_FIRST, SLOT_TILE_TOTAL, SLOT_OLD_BOUNDARY_DIST, SLOT_CELL_MAXW, SLOT_MG_SEND, SLOT_MG_RECV,
 	SLOT_TM_NEAREST, SLOT_TM_FLAGS, SLOT_TM_OFFS, SLOT_TM_SRC, SLOT_TM_TGT, SLOT_TM_CID, SLOT_TM_CSRC, SLOT_TM_CTGT, SLOT_TM_STATE, SLOT_TM_RANK,
 	SLOT_TM_OWNER, SLOT_TM_WORDS, SLOT_TM_KEEP_H, SLOT_TM_OFFS_H, SLOT_TM_PERM_H, SLOT_TM_KEEP_I, SLOT_TM_OFFS_I, SLOT_TM_PERM_I, SLOT_TM_KEEP_R,
-	SLOT_TM_OFFS_R, SLOT_TM_PERM_R, SLOT_KP,
+	SLOT_TM_OFFS_R, SLOT_TM_PERM_R, SLOT_KP, SLOT_PL,
 	SLOT_COUNT
 };
 
@@ -58,6 +58,7 @@ enum apbf_misc_word {
 	MW_MAX_INIT = 22,        // fused search + spread: largest initial kernel width (fixed point) over all particles
 	MW_STREAM_OVERFLOW = 21, // the hit stream ran out of blocks (only when the pair list overflows): the two-pass fill takes over
 	MW_REBUILD_LEN = 24,     // rebuild of a structure from a foreign pair list: min(list length, capacity)
+	MW_H_NONUNIFORM = 25,    // solver constants: 1 if two particles of the list differ in kernel width (bitwise), else 0
 	MW_WORDS = 64
 };
 

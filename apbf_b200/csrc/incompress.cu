@@ -46,6 +46,7 @@ struct sweep_args {
 	float4*         E4;   // {emptyDirection.xyz, 0}  (boundariness method 2)
 	int4*           delta;
 	int4*           push;
+	int4*           PL;   // {x, y, z, bits(lambda < 0 ? lambda * 2^18 : 0)}: all the apply sweep needs of a neighbour when every width is equal
 	float*          kp;   // Gauss gradient kernel only: per pair (a, b) the scalar k with grad W_a(r) = k * r, written by T1, reused by T2
 	const float4*   bmin;
 	const float4*   bmax;
@@ -79,6 +80,7 @@ __global__ void k_prepare_consts(sweep_args A)
 	for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
 		const uint32_t idx = ident ? a : A.index_list[a];
 		const float w = A.kernel_width[a], invMass = A.inv_mass[idx], radius = A.radius[idx];
+		if (__float_as_uint(w) != __float_as_uint(A.kernel_width[0])) A.misc[MW_H_NONUNIFORM] = 1u; // (cleared by the host before the launch)
 		const kpar hp = height_params<HK>(w, A.D);
 		const kpar gp = grad_params<GK>(w, A.D);
 		const float invRestDensity = pow_rn(2.0f * radius, A.D) * invMass;                                   // incompressibility_2.comp:81
@@ -235,6 +237,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (HK == 1 && GK == 1 && !COM) ? 
 		lam /= kh.z;                                                                              // :97-98
 		if (A.out_lambda) A.out_lambda[a] = lam;
 		A.L4[a] = make_float4(lam, kw, kg.y, kg.z);
+		if (GK == 1) { // the one-gather record of the apply sweep (equal widths)
+			const int4 pa = A.P4[a];
+			A.PL[a] = make_int4(pa.x, pa.y, pa.z, __float_as_int(lam < 0.0f ? lam * R_POS : 0.0f));
+		}
 		// the particle's own shift (:100-109); the neighbours' shifts are added by T2
 		int sx = 0, sy = 0, sz = 0;
 		if (lam < 0.0f) {
@@ -321,11 +327,42 @@ __device__ __forceinline__ void t2_pairs(const sweep_args& A, uint32_t e0, uint3
 	}
 }
 
+// The same for a list in which every particle has the same kernel width (and no unmirrored pair), Gauss gradient: the scalar of
+// every pair is what T1 stored, so a neighbour contributes its position and its lambda -- ONE 16-byte gather per pair instead of two.
+// The sweeps are bound by the L1's gather wavefronts (ncu: 77 % of peak in the two-gather form), not by instruction issue.
+template <int K>
+__device__ __forceinline__ void t2_pairs_uniform(const sweep_args& A, uint32_t e0, uint32_t end, uint32_t a, const int4 ip, const float4 e0v,
+                                                 bool filter, int& sx, int& sy, int& sz, int& hit)
+{
+	uint32_t nn[K];
+	int4 qq[K];
+	float kk[K];
+#pragma unroll
+	for (int u = 0; u < K; u++) nn[u] = (e0 + LPP * u < end) ? __ldg(A.nbl + e0 + LPP * u) & NB_ID_MASK : a;
+#pragma unroll
+	for (int u = 0; u < K; u++) kk[u] = (e0 + LPP * u < end) ? __ldg(A.kp + e0 + LPP * u) : 0.0f;
+#pragma unroll
+	for (int u = 0; u < K; u++) qq[u] = __ldg(A.PL + nn[u]);
+#pragma unroll
+	for (int u = 0; u < K; u++) {
+		const int4 iq = qq[u];
+		const int dxi = iq.x - ip.x, dyi = iq.y - ip.y, dzi = iq.z - ip.z;
+		const float rx = (float)dxi * INV_R_POS, ry = (float)dyi * INV_R_POS, rz = (float)dzi * INV_R_POS;
+		if (filter) { // (see t2_pairs)
+			const float r2 = dot3(rx, ry, rz, rx, ry, rz);
+			const float d = dot3(e0v.x, e0v.y, e0v.z, rx, ry, rz);
+			if (r2 >= 1.0e-8f && d < 0.0f && d * d > 0.36f * r2) hit = 1;
+		}
+		const float k = kk[u], f = __int_as_float(iq.w);
+		sx += f2i((k * -rx) * f); sy += f2i((k * -ry) * f); sz += f2i((k * -rz) * f);
+	}
+}
+
 // ---- T2 -------------------------------------------------------------------------------------------------------------------------
 // ASYM: the list holds unmirrored pairs (variable kernel widths), which push with integer atomics like the reference.  The host
 // does not know the list's state without a read-back, so the kernel holds both forms and takes the one that matches (one launch:
 // the second, empty launch of 3907 CTAs used to cost 5.5 us per iteration; both forms fit the same 64 registers).
-template <int GK, bool ASYM>
+template <int GK, bool ASYM, bool UNIFORM>
 __device__ __forceinline__ void apply_delta_body(const sweep_args& A)
 {
 	const uint32_t n = *A.len;
@@ -356,7 +393,13 @@ __device__ __forceinline__ void apply_delta_body(const sweep_args& A)
 				const uint32_t longest = __reduce_max_sync(FULL, end - beg);
 				for (uint32_t done = 0; done < longest; done += LPP * SWEEP_ILP) {
 					const uint32_t e0 = beg + done + sub, left = longest - done;
-					if (left > 3u * LPP) t2_pairs<4, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, kp_ok, sx, sy, sz, hit);
+					if (UNIFORM) {
+						if (left > 3u * LPP) t2_pairs_uniform<4>(A, e0, end, ac, ip, e0v, filter, sx, sy, sz, hit);
+						else if (left > 2u * LPP) t2_pairs_uniform<3>(A, e0, end, ac, ip, e0v, filter, sx, sy, sz, hit);
+						else if (left > 1u * LPP) t2_pairs_uniform<2>(A, e0, end, ac, ip, e0v, filter, sx, sy, sz, hit);
+						else t2_pairs_uniform<1>(A, e0, end, ac, ip, e0v, filter, sx, sy, sz, hit);
+					}
+					else if (left > 3u * LPP) t2_pairs<4, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, kp_ok, sx, sy, sz, hit);
 					else if (left > 2u * LPP) t2_pairs<3, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, kp_ok, sx, sy, sz, hit);
 					else if (left > 1u * LPP) t2_pairs<2, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, kp_ok, sx, sy, sz, hit);
 					else t2_pairs<1, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, kp_ok, sx, sy, sz, hit);
@@ -383,8 +426,9 @@ __device__ __forceinline__ void apply_delta_body(const sweep_args& A)
 template <int GK>
 __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_apply_delta(sweep_args A)
 {
-	if (A.misc[MW_N_ASYM] != 0u) apply_delta_body<GK, true>(A);
-	else apply_delta_body<GK, false>(A);
+	if (A.misc[MW_N_ASYM] != 0u) apply_delta_body<GK, true, false>(A);
+	else if (GK == 1 && A.misc[MW_H_NONUNIFORM] == 0u) apply_delta_body<GK, false, true>(A);
+	else apply_delta_body<GK, false, false>(A);
 }
 
 // position += delta (+ pushes); xyz only, w is the caller's
@@ -429,7 +473,8 @@ int fill_args(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors* nb, sweep_
 	A.push = (int4*)ctx->scratch_get(SLOT_PUSH, sizeof(int4) * (size_t)n_cap);
 	if (nb && ctx->settings.mGradientKernelId == 1) {
 		A.kp = (float*)ctx->scratch_get(SLOT_KP, sizeof(float) * (size_t)(nb->capacity ? nb->capacity : 1u));
-		if (!A.kp) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+		A.PL = (int4*)ctx->scratch_get(SLOT_PL, sizeof(int4) * (size_t)n_cap);
+		if (!A.kp || !A.PL) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 	}
 	A.misc = ctx->misc();
 	A.s = ctx->settings;
@@ -486,6 +531,7 @@ int apbf_solver_prepare(apbf_ctx* ctx, apbf_fluid* fluid)
 	if (n_cap == 0) return APBF_OK;
 	apbf_prof_scope ps(ctx, PROF_SOLVER_PREPARE);
 	const unsigned grid = apbf_grid(ctx, n_cap, 256);
+	APBF_CUDA(ctx, cudaMemsetAsync(A.misc + MW_H_NONUNIFORM, 0, sizeof(uint32_t), ctx->stream));
 	switch (A.s.mHeightKernelId) {
 		case 0: return launch_prepare<0>(ctx, A, grid);
 		case 1: return launch_prepare<1>(ctx, A, grid);

@@ -170,13 +170,18 @@ __global__ void k_unpack_16(int4* __restrict__ dst, const uint32_t* __restrict__
 	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) dst[ids[k]] = in[k];
 }
 // a ghost's record for the apply sweep: {lambda from its owner, h, gradient c0, gradient c1 from the local constants}
+// (PL: the one-gather record {position, lambda * 2^18 or 0} of the apply sweep's equal-width form, incompress.cu; the ghost's packed
+// position arrived with the previous exchange)
 __global__ void k_unpack_lambda(float4* __restrict__ L4, const float4* __restrict__ KG, const uint32_t* __restrict__ ids, uint32_t count,
-                                const float* __restrict__ in)
+                                const float* __restrict__ in, const int4* __restrict__ P4, int4* __restrict__ PL)
 {
 	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
 		const uint32_t id = ids[k];
 		const float4 kg = KG[id];
-		L4[id] = make_float4(in[k], kg.x, kg.y, kg.z);
+		const float lam = in[k];
+		L4[id] = make_float4(lam, kg.x, kg.y, kg.z);
+		const int4 p = P4[id];
+		PL[id] = make_int4(p.x, p.y, p.z, __float_as_int(lam < 0.0f ? lam * R_POS : 0.0f));
 	}
 }
 
@@ -443,7 +448,8 @@ int apbf_sim_mg_unpack(apbf_sim* sim, int what, const uint32_t* ids_dev, uint32_
 		k_unpack_16<<<grid, 256, 0, st>>>((int4*)ctx->scratch_get(SLOT_P4, sizeof(int4) * (size_t)cap), ids_dev, count, (const int4*)in);
 	} else if (what == 3) {
 		k_unpack_lambda<<<grid, 256, 0, st>>>((float4*)ctx->scratch_get(SLOT_L4, sizeof(float4) * (size_t)cap),
-		                                      (const float4*)ctx->scratch_get(SLOT_KG, sizeof(float4) * (size_t)cap), ids_dev, count, (const float*)in);
+		                                      (const float4*)ctx->scratch_get(SLOT_KG, sizeof(float4) * (size_t)cap), ids_dev, count, (const float*)in,
+		                                      (const int4*)ctx->scratch_get(SLOT_P4, sizeof(int4) * (size_t)cap), (int4*)ctx->scratch_get(SLOT_PL, sizeof(int4) * (size_t)cap));
 	} else if (what == 4) {
 		k_unpack_16<<<grid, 256, 0, st>>>((int4*)f.particle.position.data, ids_dev, count, (const int4*)in);
 	} else {
@@ -971,7 +977,7 @@ __global__ void k_mgl_pack(int what, const uint32_t* __restrict__ src4, const in
 }
 
 __global__ void k_mgl_unpack(int what, uint32_t* __restrict__ dst4, int4* __restrict__ dst16, float4* __restrict__ L4, const float4* __restrict__ KG,
-                             const uint32_t* __restrict__ ghost_ids, const uint32_t* __restrict__ words, mgl_caps C, mgl_bufs R, uint32_t total, mgl_sig S)
+                             const int4* __restrict__ P4, int4* __restrict__ PL, const uint32_t* __restrict__ ghost_ids, const uint32_t* __restrict__ words, mgl_caps C, mgl_bufs R, uint32_t total, mgl_sig S)
 {
 	mgl_wait(S);
 	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -984,7 +990,10 @@ __global__ void k_mgl_unpack(int what, uint32_t* __restrict__ dst4, int4* __rest
 		else if (what == 1) dst4[id] = ((const uint32_t*)R.p[r])[k];
 		else { // a ghost's record for the apply sweep: {lambda from its owner, h, gradient c0, gradient c1 from the local constants}
 			const float4 kg = KG[id];
-			L4[id] = make_float4(__uint_as_float(((const uint32_t*)R.p[r])[k]), kg.x, kg.y, kg.z);
+			const float lam = __uint_as_float(((const uint32_t*)R.p[r])[k]);
+			L4[id] = make_float4(lam, kg.x, kg.y, kg.z);
+			const int4 p = P4[id]; // (refreshed by the exchange before the density sweep)
+			PL[id] = make_int4(p.x, p.y, p.z, __float_as_int(lam < 0.0f ? lam * R_POS : 0.0f));
 		}
 	}
 }
@@ -1068,11 +1077,15 @@ int mgl_refresh(apbf_sim* sim, int what)
 	apbf_fluid& f = sim->fluid;
 	const uint32_t* src4 = nullptr; const int4* src16 = nullptr; uint32_t stride4 = 1u;
 	uint32_t* dst4 = nullptr; int4* dst16 = nullptr; float4* L4 = nullptr; const float4* KG = nullptr;
+	const int4* P4 = nullptr; int4* PL = nullptr;
 	if (what == 1) { src4 = (const uint32_t*)f.kernel_width.data; dst4 = (uint32_t*)f.kernel_width.data; }
 	else if (what == 2) { src16 = dst16 = (int4*)ctx->scratch_get(SLOT_P4, sizeof(int4) * (size_t)cap); }
 	else if (what == 3) {
 		L4 = (float4*)ctx->scratch_get(SLOT_L4, sizeof(float4) * (size_t)cap);
 		KG = (const float4*)ctx->scratch_get(SLOT_KG, sizeof(float4) * (size_t)cap);
+		P4 = (const int4*)ctx->scratch_get(SLOT_P4, sizeof(int4) * (size_t)cap);
+		PL = (int4*)ctx->scratch_get(SLOT_PL, sizeof(int4) * (size_t)cap);
+		if (!P4 || !PL) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 		src4 = (const uint32_t*)L4; stride4 = 4u;
 	} else if (what == 4) { src16 = dst16 = (int4*)f.particle.position.data; }
 	else return apbf_fail(ctx, APBF_ERR_INVALID, "what", __FILE__, __LINE__);
@@ -1083,7 +1096,7 @@ int mgl_refresh(apbf_sim* sim, int what)
 	APBF_LAUNCHED(ctx);
 	const size_t elem = (what == 2 || what == 4) ? 16u : 4u;
 	APBF_TRY(mgl_exchange(sim, [&](int r) { return elem * (size_t)sim->mgl.halo_cap[r]; }));
-	k_mgl_unpack<<<grid, 256, 0, ctx->stream>>>(what, dst4, dst16, L4, KG, sim->mgl.ghost_ids, sim->mgl.words, C, recv_bufs(sim, S), total, S);
+	k_mgl_unpack<<<grid, 256, 0, ctx->stream>>>(what, dst4, dst16, L4, KG, P4, PL, sim->mgl.ghost_ids, sim->mgl.words, C, recv_bufs(sim, S), total, S);
 	APBF_LAUNCHED(ctx);
 	return APBF_OK;
 }

@@ -446,7 +446,11 @@ class LibraryDomain:
             if r != rank:
                 caps[r] = int(max(4096, headroom * max(m[rank][r], m[r][rank]) + 1024))
         self.halo_caps = [int(caps[r]) for r in range(8)]
-        self.route_cap = int(max(4096, n_owned // 64))
+        # (message sizes are part of the protocol: every rank must use the same migration capacity)
+        rc_t = torch.tensor([max(4096, int(n_owned) // 64)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(rc_t, op=dist.ReduceOp.MAX)
+        self.route_cap = int(rc_t.item())
         self._ck(self.lib.apbf_sim_mg_loop_init(sim.handle, int(n_owned), self.route_cap, caps))
         self.ghost_capacity = int(ghost_capacity)
         self.transport = "nccl"
