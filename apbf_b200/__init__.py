@@ -676,6 +676,14 @@ class Sim:
     def substep(self, n=1):
         _check(self.ctx, self.lib.apbf_sim_substep(self.handle, n))
 
+    def step_host(self, arrays_in, n, arrays_out=None):
+        """host buffers in -> one substep -> host buffers out with the copies overlapped with the work (apbf_sim_step_host);
+        returns the number of particles that came back"""
+        hi = self.host_state(arrays_in, n)
+        ho = self.host_state(arrays_out if arrays_out is not None else arrays_in, 0)
+        _check(self.ctx, self.lib.apbf_sim_step_host(self.handle, C.byref(hi), C.byref(ho)))
+        return ho.n
+
     def set_graphs(self, enable):
         """replay substeps as captured CUDA graphs (on by default, see apbf_sim_set_graphs)"""
         _check(self.ctx, self.lib.apbf_sim_set_graphs(self.handle, 1 if enable else 0))

@@ -155,6 +155,7 @@ SIGNATURES = {
     "apbf_sim_mg_loop_reset": (C.c_int, [vp, C.c_uint32, C.c_uint32]),
     "apbf_sim_mg_loop_stats": (C.c_int, [vp, u32p]),
     "apbf_sim_mg_substep": (C.c_int, [vp, C.c_uint32]),
+    "apbf_sim_step_host": (C.c_int, [vp, C.POINTER(HostState), C.POINTER(HostState)]),
     "apbf_sim_set_graphs": (C.c_int, [vp, C.c_int]),
     "apbf_sim_graph_replays": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
     "apbf_sim_mg_p2p_export": (C.c_int, [vp, vp]),

@@ -115,6 +115,10 @@ struct apbf_ctx {
 	uint32_t        stream_blocks_cap = 0; // testing aid: upper bound on the hit stream's blocks (0 = automatic)
 	uint32_t        match_grid_min = 16384; // merge / split matching: grid-wide rounds from this many candidates on
 	bool            search_stats = false; // fused search + spread: count the pairs of the unpruned list as well
+	// apbf_sim_step_host: the Green search waits for this event before it re-orders the lists (the small lists are still being
+	// uploaded on a second stream while positions are hashed and sorted) and records that one right after (from there on every list
+	// but positions, widths and boundariness is final: their download overlaps the solver)
+	cudaEvent_t     hook_wait_before_reorder = nullptr, hook_record_after_reorder = nullptr;
 
 	void* scratch_get(int slot, size_t bytes);
 	uint32_t* misc() { return (uint32_t*)scratch_get(SLOT_MISC_WORDS, MW_WORDS * sizeof(uint32_t)); }
@@ -178,6 +182,31 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
 // < 0.52 ulp) except on near-ties, whereas CUDA's powf is only good to a few ulp.  Every value derived from it feeds a
 // float -> fixed-point truncation, where a last-bit difference becomes a whole unit.
 __device__ __forceinline__ float pow_rn(float x, float y) { return (float)pow((double)x, (double)y); }
+// The exponents the per-particle constants meet are DIMENSIONS, 2 / DIMENSIONS and DIMENSIONS / 2 with DIMENSIONS 2 or 3.  Where the
+// exponent is exact in float (2, 3, 1, 1.5) a product of two or three factors resp. x * sqrt(x) in double precision is within an ulp
+// or two of the true power, like pow() itself, so after the ONE rounding to float they agree with it except where the true value
+// lies within ~2^-50 relative of a float rounding boundary (probability ~1e-8 per call, the same as CUDA's pow against glibc's).
+// 2.0f / 3.0f is NOT 2/3 -- the shader's pow(x, 2.0 / DIMENSIONS) has the rounded exponent, and x^(that) differs from cbrt(x)^2 in
+// the last float bit every other time -- so that one stays a pow().  pow() costs ~200 FP64 instructions per call, the products a
+// handful (solver_prepare: 62 -> 33 us per 10^6 particles).
+__device__ __forceinline__ float pow_int_rn(float x, float d) // x^d for d = DIMENSIONS
+{
+	const double t = (double)x;
+	if (d == 3.0f) return (float)(t * t * t);
+	if (d == 2.0f) return (float)(t * t);
+	return pow_rn(x, d);
+}
+__device__ __forceinline__ float pow_2_over_d_rn(float x, float d) // x^(2/d)
+{
+	if (d == 2.0f) return x;
+	return pow_rn(x, 2.0f / d);
+}
+__device__ __forceinline__ float pow_d_over_2_rn(float x, float d) // x^(d/2)
+{
+	if (d == 3.0f && x >= 0.0f) { const double t = (double)x; return (float)(t * sqrt(t)); }
+	if (d == 2.0f) return x;
+	return pow_rn(x, d / 2.0f);
+}
 __device__ __forceinline__ uint32_t f2u(float f) { return (uint32_t)f; } // cvt.rzi.u32.f32: negative/NaN -> 0, saturating
 __device__ __forceinline__ int32_t f2i(float f) { return (int32_t)f; }   // cvt.rzi.s32.f32: NaN -> 0, saturating
 

@@ -83,8 +83,8 @@ __global__ void k_prepare_consts(sweep_args A)
 		if (__float_as_uint(w) != __float_as_uint(A.kernel_width[0])) A.misc[MW_H_NONUNIFORM] = 1u; // (cleared by the host before the launch)
 		const kpar hp = height_params<HK>(w, A.D);
 		const kpar gp = grad_params<GK>(w, A.D);
-		const float invRestDensity = pow_rn(2.0f * radius, A.D) * invMass;                                   // incompressibility_2.comp:81
-		const float lamDiv = pow_rn(2.0f * A.s.mSmallestTargetRadius, A.D) / invRestDensity * invMass;      // :98
+		const float invRestDensity = pow_int_rn(2.0f * radius, A.D) * invMass;                               // incompressibility_2.comp:81
+		const float lamDiv = pow_int_rn(2.0f * A.s.mSmallestTargetRadius, A.D) / invRestDensity * invMass;  // :98
 		A.KG[a] = make_float4(w, gp.c0, gp.c1, invRestDensity);
 		A.KH[a] = make_float4(hp.c0, hp.c1, lamDiv, invMass);
 	}

@@ -23,10 +23,10 @@ __device__ __forceinline__ kpar height_params(float w, float D)
 	kpar p; p.w = w; p.c0 = 0.f; p.c1 = 0.f;
 	if (HK == 0) p.c0 = 8.0f / (APBF_PI * w * w * w);                      // k, kernels.glsl:23
 	if (HK == 1) {                                                          // :104 + :86-88
-		float height = 0.6f / pow_rn(w / 2.0f, D);
-		float iv = pow_rn(height, 2.0f / D);
+		float height = 0.6f / pow_int_rn(w / 2.0f, D);
+		float iv = pow_2_over_d_rn(height, D);
 		p.c0 = iv * APBF_PI;          // invDoubleVariance
-		p.c1 = pow_rn(iv, D / 2.0f);    // normalisation
+		p.c1 = pow_d_over_2_rn(iv, D);  // normalisation
 	}
 	if (HK == 2) { p.c0 = w * w; p.c1 = 64.0f * APBF_PI * pow_rn(w, 9.0f); } // :6,8
 	if (HK == 3) p.c0 = 3.0f / (APBF_PI * pow_rn(w, D));                     // :50
@@ -40,10 +40,10 @@ __device__ __forceinline__ kpar grad_params(float w, float D)
 	kpar p; p.w = w; p.c0 = 0.f; p.c1 = 0.f;
 	if (GK == 0) p.c0 = 48.0f / (APBF_PI * w * w * w);                     // l, :39
 	if (GK == 1) {                                                          // :117 + :93-96 (+ :86-88 via gauss_kernel_height)
-		float height = 0.6f / pow_rn(w / 2.0f, D);
-		float iv = pow_rn(height, 2.0f / D);
+		float height = 0.6f / pow_int_rn(w / 2.0f, D);
+		float iv = pow_2_over_d_rn(height, D);
 		p.c0 = iv * APBF_PI;
-		p.c1 = pow_rn(iv, D / 2.0f);
+		p.c1 = pow_d_over_2_rn(iv, D);
 	}
 	if (GK == 2) p.c0 = APBF_PI * pow_rn(w, 6.0f);                           // :15
 	if (GK == 3) p.c0 = 3.0f / (APBF_PI * pow_rn(w, D + 1.0f));              // :56

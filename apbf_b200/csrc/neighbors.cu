@@ -1487,7 +1487,9 @@ int apbf_green_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range,
 	// permute hidden arrays, index list and per-id arrays (:54-56)
 	{
 		apbf_prof_scope ps(ctx, PROF_REORDER);
+		if (ctx->hook_wait_before_reorder) APBF_CUDA(ctx, cudaStreamWaitEvent(st, ctx->hook_wait_before_reorder, 0));
 		APBF_TRY(reorder_lists(ctx, fluid, range, sidx));
+		if (ctx->hook_record_after_reorder) APBF_CUDA(ctx, cudaEventRecord(ctx->hook_record_after_reorder, st));
 	}
 	const uint32_t* new_index = (const uint32_t*)p.index_list.reorder_out;
 	const int32_t* new_pos = (const int32_t*)p.position.reorder_out;

@@ -119,6 +119,8 @@ void apbf_sim_destroy(apbf_sim* sim)
 	apbf_sim_mg_comm_destroy(sim); // the library's own NCCL communicator, if one was made
 	for (apbf_sim_graph& g : sim->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
 	if (sim->capture_stream) cudaStreamDestroy(sim->capture_stream);
+	if (sim->copy_stream) cudaStreamDestroy(sim->copy_stream);
+	for (cudaEvent_t e : { sim->ev_fork, sim->ev_up, sim->ev_lists, sim->ev_down }) if (e) cudaEventDestroy(e);
 	for (void* p : sim->owned) cudaFree(p);
 	apbf_nbr_forget(sim->ctx, sim->nb.pairs);
 	delete sim;
@@ -376,6 +378,76 @@ int apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps)
 		}
 		APBF_TRY(substep_once(sim));
 	}
+	return APBF_OK;
+}
+
+// Host buffers in, one substep, host buffers out -- the reference-facing call when the scene lives in host memory -- with the
+// copies overlapped with the work instead of bracketing it:
+//   * positions, velocities and position back-ups go up first on the context's stream (velocity_handling and the hash + sort need
+//     nothing else); the seven small lists follow on a second stream and are waited for right before the search re-orders the lists;
+//   * from the re-order on, every list but positions, kernel widths and boundariness (and what update_transfers writes) is final:
+//     those 56 of 80 bytes per particle come down on the second stream while emit and solver run; the rest follows the last kernel.
+// Same results as apbf_sim_upload + apbf_sim_substep(1) + apbf_sim_download (which is what runs for configurations whose particle
+// count can change -- merge / split -- or that use the binary search or slabs).  host_in / host_out should be pinned; they may be the
+// same buffers.  Synchronises before it returns.
+int apbf_sim_step_host(apbf_sim* sim, const apbf_host_state* in, apbf_host_state* out)
+{
+	if (!sim || !in || !out) return APBF_ERR_INVALID;
+	apbf_ctx* ctx = sim->ctx;
+	const apbf_sim_config& c = sim->cfg;
+	const apbf_settings& s = ctx->settings;
+	const bool transfers = c.transfers && !c.basic_pbf && (s.mMerge || s.mSplit);
+	if (transfers || c.use_binary_search || ctx->mg_enabled || ctx->prof_on) {
+		APBF_TRY(apbf_sim_upload(sim, in));
+		APBF_TRY(apbf_sim_substep(sim, 1));
+		return apbf_sim_download(sim, out);
+	}
+	APBF_REQUIRE(ctx, in->n <= c.particle_capacity);
+	APBF_TRY(apbf_ctx_set_dimensions(ctx, c.dims));
+	if (!sim->copy_stream) {
+		APBF_CUDA(ctx, cudaStreamCreateWithFlags(&sim->copy_stream, cudaStreamNonBlocking));
+		for (cudaEvent_t* e : { &sim->ev_fork, &sim->ev_up, &sim->ev_lists, &sim->ev_down }) APBF_CUDA(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+	}
+	cudaStream_t st = ctx->stream, cs = sim->copy_stream;
+	const size_t n = in->n;
+	struct item { const void* src; void* dst; size_t stride; };
+	// ---- up ----
+	APBF_CUDA(ctx, cudaEventRecord(sim->ev_fork, st)); // (the second stream starts behind whatever the context's stream still holds)
+	APBF_CUDA(ctx, cudaStreamWaitEvent(cs, sim->ev_fork, 0));
+	{
+		apbf_fluid& f = sim->fluid;
+		const item first[] = { { in->position, f.particle.position.data, 16 }, { in->velocity, f.particle.velocity.data, 16 }, { in->pos_backup, f.particle.pos_backup.data, 16 } };
+		const item rest[] = { { in->inverse_mass, f.particle.inverse_mass.data, 4 }, { in->radius, f.particle.radius.data, 4 }, { in->transferring, f.particle.transferring.data, 4 },
+		                      { in->target_radius, f.target_radius.data, 4 }, { in->kernel_width, f.kernel_width.data, 4 }, { in->boundariness, f.boundariness.data, 4 },
+		                      { in->boundary_distance, f.boundary_distance.data, 4 }, { in->index_list, f.particle.index_list.data, 4 } };
+		for (const item& it : first) if (it.src && n) APBF_CUDA(ctx, cudaMemcpyAsync(it.dst, it.src, it.stride * n, cudaMemcpyHostToDevice, st));
+		for (const item& it : rest) if (it.src && n) APBF_CUDA(ctx, cudaMemcpyAsync(it.dst, it.src, it.stride * n, cudaMemcpyHostToDevice, cs));
+		k_set_lengths<<<1, 1, 0, st>>>(f.particle.length, f.particle.hidden_length, (uint32_t)n);
+		APBF_LAUNCHED(ctx);
+		if (!in->index_list) APBF_TRY(apbf_write_sequence(ctx, (uint32_t*)f.particle.index_list.data, f.particle.length, c.particle_capacity, 0u, 1u, 1u));
+		APBF_CUDA(ctx, cudaEventRecord(sim->ev_up, cs));
+	}
+	// ---- one substep, launch by launch (the two hooks sit inside the search) ----
+	ctx->hook_wait_before_reorder = sim->ev_up;
+	ctx->hook_record_after_reorder = sim->ev_lists;
+	const int rc = substep_once(sim);
+	ctx->hook_wait_before_reorder = ctx->hook_record_after_reorder = nullptr;
+	APBF_TRY(rc);
+	// ---- down ----
+	apbf_fluid& f = sim->fluid; // (after the search's buffer swap)
+	out->n = (uint32_t)n;
+	const bool late_tr = c.update_transfers && !c.basic_pbf; // update_transfers writes these two after the solver
+	const item early[] = { { f.particle.velocity.data, out->velocity, 16 }, { f.particle.pos_backup.data, out->pos_backup, 16 }, { f.particle.inverse_mass.data, out->inverse_mass, 4 },
+	                       { f.particle.radius.data, out->radius, 4 }, { f.particle.transferring.data, out->transferring, 4 }, { f.particle.index_list.data, out->index_list, 4 },
+	                       { late_tr ? nullptr : f.target_radius.data, out->target_radius, 4 }, { late_tr ? nullptr : f.boundary_distance.data, out->boundary_distance, 4 } };
+	const item late[] = { { f.particle.position.data, out->position, 16 }, { f.kernel_width.data, out->kernel_width, 4 }, { f.boundariness.data, out->boundariness, 4 },
+	                      { late_tr ? f.target_radius.data : nullptr, out->target_radius, 4 }, { late_tr ? f.boundary_distance.data : nullptr, out->boundary_distance, 4 } };
+	APBF_CUDA(ctx, cudaStreamWaitEvent(cs, sim->ev_lists, 0));
+	for (const item& it : early) if (it.src && it.dst && n) APBF_CUDA(ctx, cudaMemcpyAsync(it.dst, it.src, it.stride * n, cudaMemcpyDeviceToHost, cs));
+	for (const item& it : late) if (it.src && it.dst && n) APBF_CUDA(ctx, cudaMemcpyAsync(it.dst, it.src, it.stride * n, cudaMemcpyDeviceToHost, st));
+	APBF_CUDA(ctx, cudaEventRecord(sim->ev_down, cs));
+	APBF_CUDA(ctx, cudaStreamWaitEvent(st, sim->ev_down, 0)); // the context's stream stays the one ordered stream of work
+	APBF_CUDA(ctx, cudaStreamSynchronize(st));
 	return APBF_OK;
 }
 

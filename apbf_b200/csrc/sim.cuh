@@ -64,6 +64,8 @@ struct apbf_sim {
 	apbf_mg_loop    mgl;
 	int             graphs_on = 1;       // replay captured substeps (apbf_sim_set_graphs; APBF_SIM_GRAPHS=0 turns it off)
 	apbf_sim_graph  graphs[2];           // one per buffer parity
+	cudaStream_t    copy_stream = nullptr;     // apbf_sim_step_host: second stream for the copies that overlap the substep
+	cudaEvent_t     ev_fork = nullptr, ev_up = nullptr, ev_lists = nullptr, ev_down = nullptr;
 	cudaStream_t    capture_stream = nullptr; // captures are recorded here (the caller's stream may be the legacy default stream, which cannot capture)
 	uint64_t        seen_keys[4] = {};   // states met recently: a state met twice is worth a capture
 	uint64_t        bad_key = 0;         // a capture of this state failed: do not try again

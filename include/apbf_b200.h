@@ -380,6 +380,12 @@ int  apbf_sim_download(apbf_sim* sim, apbf_host_state* host);
  * (box_collision, incompressibility) -> [update_transfers, with the merge / split decisions if cfg.transfers].  Fully asynchronous.
  * The search keeps the pair list in its grouped form only; apbf_sim_neighbors() writes the (id, idN) pairs when asked. */
 int  apbf_sim_substep(apbf_sim* sim, uint32_t n_substeps);
+/* host buffers in -> one substep -> host buffers out, the copies overlapped with the work: positions, velocities and back-ups go up
+ * first, the small lists follow on a second stream while the positions are hashed and sorted; from the search's re-order on, every
+ * list the solver does not touch (56 of 80 bytes per particle) comes down while emit and solver run.  Same results as
+ * apbf_sim_upload + apbf_sim_substep(1) + apbf_sim_download, which is what runs with merge / split, the binary search or slabs.
+ * host_in and host_out (pinned memory) may be the same buffers; out->n is set; synchronises. */
+int  apbf_sim_step_host(apbf_sim* sim, const apbf_host_state* host_in, apbf_host_state* host_out);
 /* A substep is the same ~36 launches every time (lengths are device words), so after two ordinary substeps apbf_sim_substep
  * captures it as a CUDA graph -- one per buffer parity, the search swaps the two buffers of every list -- and replays that from
  * then on; a change of settings, capacities or scratch allocations falls back to ordinary launches and captures again.  On by

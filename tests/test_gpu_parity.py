@@ -742,3 +742,29 @@ def test_graph_replay_equals_ordinary_launches(gpu, adaptive):
     for a, b in ((out[False][0], out[True][0]), (out[False][1], out[True][1])):
         for k in a:
             assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("mode", ["basic", "adaptive", "default_mode"])
+def test_step_host_equals_upload_substep_download(gpu, mode):
+    """apbf_sim_step_host overlaps the copies with the substep (second stream, events inside the search): same bits, every list"""
+    adaptive = mode == "adaptive"
+    sc = scenes.dam_break(20, 20, 20, adaptive=True) if mode != "basic" else scenes.uniform_block(24, jitter=0.2, shuffle=True)
+    res = {}
+    for overlapped in (False, True):
+        ctx = gpu.Context(dims=sc.dims)
+        ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if adaptive else 1, mSmallestTargetRadius=sc.smallest_target_radius)
+        sim = gpu.Sim(ctx, sc, neighbor_capacity=sc.n * (300 if mode != "basic" else 80), integrate=True, basic_pbf=mode == "basic",
+                      update_transfers=mode == "default_mode")
+        host = {k: v.copy() for k, v in sc.arrays.items()}
+        host = {**gpu.empty_host_arrays(sc.n), **host}
+        n = sc.n
+        for _ in range(4):
+            if overlapped:
+                n = sim.step_host(host, n)
+            else:
+                sim.upload(host, n=n); sim.substep(1); n = sim.download(host)
+        res[overlapped] = ({k: np.array(v[:n]).copy() for k, v in host.items()}, n)
+        sim.close(); ctx.close()
+    assert res[False][1] == res[True][1] == sc.n
+    for k in res[False][0]:
+        assert np.array_equal(res[False][0][k], res[True][0][k]), k
