@@ -363,7 +363,7 @@ def roofline_of(r, peak, workload, world=1):
     return roof, passes
 
 
-def run_operators(gpu, torch, workload, steps, search="green", device=0):
+def run_operators(gpu, torch, workload, steps, search="green", device=0, fused_search=False):
     """one substep the way a scene of the reference calls it (pool.cpp:67-106): operator after operator through the drop-in
     surface, every list in its public format -- instead of the fused whole-scene call"""
     sc, meta = make_scene(workload)
@@ -371,10 +371,11 @@ def run_operators(gpu, torch, workload, steps, search="green", device=0):
     ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if meta["adaptive"] else 1, mSmallestTargetRadius=sc.smallest_target_radius)
     L = gpu.ParticleLists(ctx, sc.arrays, neighbor_capacity=sc.n * meta["pairs_per_particle"])
     vel = gpu.velocity_handling(ctx).set_data(L).set_acceleration((0.0, -10.0, 0.0))
+    fused_search = fused_search and meta["adaptive"]    # search + spread_kernel_width as ONE operator (not a class of the reference)
     if search == "green":
-        nbh = gpu.neighborhood_green(ctx).set_data(L).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2)
+        nbh = (gpu.neighborhood_green_spread if fused_search else gpu.neighborhood_green)(ctx).set_data(L).set_position_range(sc.min_pos, sc.max_pos, sc.res_log2)
     else:
-        nbh = gpu.neighborhood_binary_search(ctx).set_data(L)
+        nbh = (gpu.neighborhood_binary_search_spread if fused_search else gpu.neighborhood_binary_search)(ctx).set_data(L)
     nbh.set_range_scale(1.5 if meta["adaptive"] else 1.0)
     spread = gpu.spread_kernel_width(ctx).set_data(L)
     box = gpu.box_collision(ctx).set_data(L, sc.box_min, sc.box_max)
@@ -383,7 +384,7 @@ def run_operators(gpu, torch, workload, steps, search="green", device=0):
     def substep():
         vel.apply(1.0 / 60.0)
         nbh.apply()
-        if meta["adaptive"]:
+        if meta["adaptive"] and not fused_search:
             spread.apply()
         for _ in range(sc.solver_iterations):
             box.apply()
@@ -400,7 +401,8 @@ def run_operators(gpu, torch, workload, steps, search="green", device=0):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     out = {"ms_per_step": ms, "value": sc.n / (ms * 1e-3), "particles": sc.n, "pairs": L.pair_count(), "search": search,
-           "what": "velocity_handling, neighborhood_*::apply, spread_kernel_width::apply, 4 x (box_collision::apply, incompressibility::apply)"}
+           "what": ("velocity_handling, neighborhood_*_spread::apply (search + spread_kernel_width as one operator), " if fused_search else
+                    "velocity_handling, neighborhood_*::apply, spread_kernel_width::apply, ") + "4 x (box_collision::apply, incompressibility::apply); every list in its public format"}
     del L
     ctx.close()
     torch.cuda.empty_cache()
@@ -431,6 +433,7 @@ def run_extras(gpu, torch, peak, device, quick):
     if not quick:
         for search in ("green", "binary"):
             out[f"dam_break_1M_operator_by_operator_{search}"] = run_operators(gpu, torch, "dam_break_1M", 6, search, device)
+        out["dam_break_1M_operator_by_operator_green_fused_search"] = run_operators(gpu, torch, "dam_break_1M", 6, "green", device, fused_search=True)
     return out
 
 
