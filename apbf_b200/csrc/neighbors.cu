@@ -716,36 +716,66 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, unsigned lane)
 //   MODE 2: colK, colU                (fused prune, all thresholds equal)
 //   MODE 3: colK, colM, colU, colMu   (fused prune, per-particle thresholds)
 // "d2 > K" is false for a NaN distance, i.e. NaN is accepted, like !(distance > range) in neighborhood_green.comp:83.
+// Two queries per step with packed f32x2 arithmetic (sm_100: FADD2 / FMUL2 issue at the rate of their scalar forms,
+// tools/microbench/pipes.cu): the chunk's queries sit in shared memory as pairs -- sa[j] = {x0, x1, y0, y1}, sb[j] = {z0, z1, K0, K1},
+// su[j] = {U0, U1} -- so that one 16-byte load yields two aligned register pairs.  Differences and squares are packed (6
+// instructions for two queries instead of 12); the two sums stay SCALAR adds: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 even under -fmad=false (seen in the SASS), and a fused sum of squares is not the oracle's distance.  Same bits as the
+// scalar loop: every operation is the same IEEE operation on the same operands.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+{
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+__device__ __forceinline__ void sq_diff2(unsigned long long q, float c, float& lo, float& hi) // (q - {c, c})^2 per half
+{
+	unsigned long long d;
+	const unsigned long long cc = pack2(c, c);
+	asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(q), "l"(cc));
+	asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(d) : "l"(d));
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(d));
+}
+
 template <int MODE>
-__device__ __forceinline__ void chunk_tests(const float4* __restrict__ sq, const float* __restrict__ su, uint32_t cnt, const float4 c4,
+__device__ __forceinline__ void chunk_tests(const float4* __restrict__ sa, const float4* __restrict__ sb, const float2* __restrict__ su, uint32_t cnt, const float4 c4,
                                             float Kb, float Ub, uint32_t& colK, uint32_t& colM, uint32_t& colU, uint32_t& colMu)
 {
 	uint32_t bit = 1u;
-#pragma unroll 4
-	for (uint32_t qi = 0; qi < cnt; qi++) {
-		const float4 qv = sq[qi];
-		const float dx = __fsub_rn(qv.x, c4.x), dy = __fsub_rn(qv.y, c4.y), dz = __fsub_rn(qv.z, c4.z);
-		const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+	const uint32_t npairs = (cnt + 1u) >> 1; // (a slot behind the last query holds K = U = -1: it never passes a test)
+#pragma unroll 2
+	for (uint32_t j = 0; j < npairs; j++) {
+		const float4 a = sa[j], b = sb[j];
+		float x0, x1, y0, y1, z0, z1;
+		sq_diff2(pack2(a.x, a.y), c4.x, x0, x1);
+		sq_diff2(pack2(a.z, a.w), c4.y, y0, y1);
+		sq_diff2(pack2(b.x, b.y), c4.z, z0, z1);
+		const float d0 = __fadd_rn(__fadd_rn(x0, y0), z0), d1 = __fadd_rn(__fadd_rn(x1, y1), z1);
+		const uint32_t bit1 = bit + bit;
 		if (MODE == 0) {
-			asm("{\n\t.reg .pred pk;\n\tsetp.gt.f32 pk, %1, %2;\n\t@!pk or.b32 %0, %0, %3;\n\t}"
-			    : "+r"(colK) : "f"(d2), "f"(qv.w), "r"(bit));
+			asm("{\n\t.reg .pred p0, p1;\n\tsetp.gt.f32 p0, %1, %2;\n\tsetp.gt.f32 p1, %3, %4;\n\t@!p0 or.b32 %0, %0, %5;\n\t@!p1 or.b32 %0, %0, %6;\n\t}"
+			    : "+r"(colK) : "f"(d0), "f"(b.z), "f"(d1), "f"(b.w), "r"(bit), "r"(bit1));
 		} else if (MODE == 1) {
-			asm("{\n\t.reg .pred pk, pm;\n\tsetp.gt.f32 pk, %2, %3;\n\tsetp.gt.or.f32 pm, %2, %4, pk;\n\t"
-			    "@!pk or.b32 %0, %0, %5;\n\t@!pm or.b32 %1, %1, %5;\n\t}"
-			    : "+r"(colK), "+r"(colM) : "f"(d2), "f"(qv.w), "f"(Kb), "r"(bit));
+			asm("{\n\t.reg .pred pk, pm, qk, qm;\n\tsetp.gt.f32 pk, %2, %3;\n\tsetp.gt.or.f32 pm, %2, %6, pk;\n\tsetp.gt.f32 qk, %4, %5;\n\tsetp.gt.or.f32 qm, %4, %6, qk;\n\t"
+			    "@!pk or.b32 %0, %0, %7;\n\t@!pm or.b32 %1, %1, %7;\n\t@!qk or.b32 %0, %0, %8;\n\t@!qm or.b32 %1, %1, %8;\n\t}"
+			    : "+r"(colK), "+r"(colM) : "f"(d0), "f"(b.z), "f"(d1), "f"(b.w), "f"(Kb), "r"(bit), "r"(bit1));
 		} else if (MODE == 2) {
-			const float ua = su[qi];
-			asm("{\n\t.reg .pred pk, pu;\n\tsetp.gt.f32 pk, %2, %3;\n\tsetp.gt.f32 pu, %2, %4;\n\t"
-			    "@!pk or.b32 %0, %0, %5;\n\t@!pu or.b32 %1, %1, %5;\n\t}"
-			    : "+r"(colK), "+r"(colU) : "f"(d2), "f"(qv.w), "f"(ua), "r"(bit));
+			const float2 u = su[j];
+			asm("{\n\t.reg .pred pk, pu, qk, qu;\n\tsetp.gt.f32 pk, %2, %3;\n\tsetp.gt.f32 pu, %2, %4;\n\tsetp.gt.f32 qk, %5, %6;\n\tsetp.gt.f32 qu, %5, %7;\n\t"
+			    "@!pk or.b32 %0, %0, %8;\n\t@!pu or.b32 %1, %1, %8;\n\t@!qk or.b32 %0, %0, %9;\n\t@!qu or.b32 %1, %1, %9;\n\t}"
+			    : "+r"(colK), "+r"(colU) : "f"(d0), "f"(b.z), "f"(u.x), "f"(d1), "f"(b.w), "f"(u.y), "r"(bit), "r"(bit1));
 		} else {
-			const float ua = su[qi];
+			const float2 u = su[j];
 			asm("{\n\t.reg .pred pk, pm, pu, pn;\n\tsetp.gt.f32 pk, %4, %5;\n\tsetp.gt.or.f32 pm, %4, %6, pk;\n\t"
 			    "setp.gt.f32 pu, %4, %7;\n\tsetp.gt.or.f32 pn, %4, %8, pu;\n\t"
 			    "@!pk or.b32 %0, %0, %9;\n\t@!pm or.b32 %1, %1, %9;\n\t@!pu or.b32 %2, %2, %9;\n\t@!pn or.b32 %3, %3, %9;\n\t}"
-			    : "+r"(colK), "+r"(colM), "+r"(colU), "+r"(colMu) : "f"(d2), "f"(qv.w), "f"(Kb), "f"(ua), "f"(Ub), "r"(bit));
+			    : "+r"(colK), "+r"(colM), "+r"(colU), "+r"(colMu) : "f"(d0), "f"(b.z), "f"(Kb), "f"(u.x), "f"(Ub), "r"(bit));
+			asm("{\n\t.reg .pred pk, pm, pu, pn;\n\tsetp.gt.f32 pk, %4, %5;\n\tsetp.gt.or.f32 pm, %4, %6, pk;\n\t"
+			    "setp.gt.f32 pu, %4, %7;\n\tsetp.gt.or.f32 pn, %4, %8, pu;\n\t"
+			    "@!pk or.b32 %0, %0, %9;\n\t@!pm or.b32 %1, %1, %9;\n\t@!pu or.b32 %2, %2, %9;\n\t@!pn or.b32 %3, %3, %9;\n\t}"
+			    : "+r"(colK), "+r"(colM), "+r"(colU), "+r"(colMu) : "f"(d1), "f"(b.w), "f"(Kb), "f"(u.y), "f"(Ub), "r"(bit1));
 		}
-		bit += bit;
+		bit = bit1 + bit1;
 	}
 	if (MODE == 0) colM = colK;
 	if (MODE == 2) { colM = colK; colMu = colU; }
@@ -761,7 +791,10 @@ k_green_stream(const emit_args A)
 	__shared__ float4 s_q[EMIT_WARPS][32];                       // {x, y, z, K}: K = T (plain) or min(T, C - hw) (fused)
 	__shared__ float s_u[FUSED ? EMIT_WARPS : 1][32];            // U = min(T, C + hw)
 	__shared__ float s_T[FUSED ? EMIT_WARPS : 1][32];            // threshold of the range test alone
-	__shared__ uint32_t s_cand[EMIT_WARPS][32], s_colM[EMIT_WARPS][32];
+	__shared__ uint32_t s_cand[EMIT_WARPS][32];
+	// the same queries as pairs for the packed test loop (chunk_tests): {x0, x1, y0, y1}, {z0, z1, K0, K1}, {U0, U1}
+	__shared__ __align__(16) float4 s_qa[EMIT_WARPS][16], s_qb[EMIT_WARPS][16];
+	__shared__ __align__(8) float2 s_u2[FUSED ? EMIT_WARPS : 1][16];
 	const apbf_grid_params& g = A.g;
 	const uint32_t n = *A.len;
 	const uint32_t n_owned = MG ? A.misc[MW_N_OWNED] : 0xFFFFFFFFu;
@@ -857,6 +890,12 @@ k_green_stream(const emit_args A)
 				__syncwarp();
 				s_q[w][lane] = make_float4(me.x, me.y, me.z, FUSED ? qb.x : me.w);
 				if (FUSED) { s_u[w][lane] = qb.y; s_T[w][lane] = me.w; }
+				{
+					float* pa = (float*)&s_qa[w][lane >> 1] + (lane & 1u);
+					float* pb = (float*)&s_qb[w][lane >> 1] + (lane & 1u);
+					pa[0] = me.x; pa[2] = me.y; pb[0] = me.z; pb[2] = FUSED ? qb.x : me.w;
+					if (FUSED) ((float*)&s_u2[w][lane >> 1])[lane & 1u] = qb.y;
+				}
 				__syncwarp();
 				uint32_t my_mx = FUSED ? f2u(qb.w * APBF_KERNEL_WIDTH_RESOLUTION) : 0u; // kernel_width_init.comp:35
 				uint32_t my_cnt = 0u;
@@ -1005,11 +1044,11 @@ k_green_stream(const emit_args A)
 							// all thresholds of the chunk and of the batch equal: the mirrored test is the query's own test
 							const bool uni = q_uniform && __all_sync(0xffffffffu, !cvalid || (Kb == qK && (!FUSED || cb.y == qU)));
 							if (FUSED) {
-								if (uni) chunk_tests<2>(s_q[w], s_u[w], cnt, c4, Kb, cb.y, colK, colM, colU, colMu);
-								else chunk_tests<3>(s_q[w], s_u[w], cnt, c4, Kb, cb.y, colK, colM, colU, colMu);
+								if (uni) chunk_tests<2>(s_qa[w], s_qb[w], s_u2[w], cnt, c4, Kb, cb.y, colK, colM, colU, colMu);
+								else chunk_tests<3>(s_qa[w], s_qb[w], s_u2[w], cnt, c4, Kb, cb.y, colK, colM, colU, colMu);
 							} else {
-								if (uni) chunk_tests<0>(s_q[w], nullptr, cnt, c4, Kb, 0.0f, colK, colM, colU, colMu);
-								else chunk_tests<1>(s_q[w], nullptr, cnt, c4, Kb, 0.0f, colK, colM, colU, colMu);
+								if (uni) chunk_tests<0>(s_qa[w], s_qb[w], nullptr, cnt, c4, Kb, 0.0f, colK, colM, colU, colMu);
+								else chunk_tests<1>(s_qa[w], s_qb[w], nullptr, cnt, c4, Kb, 0.0f, colK, colM, colU, colMu);
 							}
 						}
 						const uint32_t sq = cand - first; // this candidate is query sq of the chunk: id != idN, neighborhood_green.comp:83
@@ -1069,8 +1108,11 @@ k_green_stream(const emit_args A)
 						// ---- lane = query again: append the hits to the chunk's stream ---------------------------------------------
 						if (__any_sync(0xffffffffu, colK != 0u)) {
 							s_cand[w][lane] = cand;
-							s_colM[w][lane] = colM;
+							// is the mirrored pair (idN, id) kept for every hit of the batch?  (equal widths: always)  Then no entry carries the
+							// "unmirrored" flag and the mirrored bits need not be transposed.
+							const bool all_mirrored = __all_sync(0xffffffffu, (colK & ~colM) == 0u);
 							const uint32_t rowK = transpose32(colK, lane); // bit j: candidate j of the batch
+							const uint32_t rowM = all_mirrored ? rowK : transpose32(colM, lane);
 							const uint32_t c = (uint32_t)__popc(rowK);
 							uint32_t inc = c;
 #pragma unroll
@@ -1093,18 +1135,24 @@ k_green_stream(const emit_args A)
 							}
 							if (my_cnt + c > SB_RANK_MASK) A.misc[MW_STREAM_OVERFLOW] = 1u; // the rank field is full: two-pass fill
 							__syncwarp();
+							// this query's hits, in candidate order, go to entries tp, tp + 1, ... of the chunk's stream: {idN | flag, lane | rank} as one
+							// 8-byte store; the block's address is worked out once and again only where the run crosses into the next block
 							uint32_t m = rowK, tp = tile_pos + (inc - c), rk = (lane << SB_RANK_BITS) | (my_cnt & SB_RANK_MASK);
+							uint2* B = nullptr;
+							bool need_block = true;
 							while (m) {
 								const uint32_t j = (uint32_t)__ffs(m) - 1u;
 								m &= m - 1u;
-								const uint32_t o = tp >> SB_SHIFT;
-								const uint32_t blk = o < n_before ? last_blk : base + (o - n_before);
-								if (blk < A.stream_blocks) {
-									uint32_t* B = A.stream + (size_t)blk * SB_WORDS + SB_HEADER;
-									B[tp & (SB_ENTRIES - 1u)] = s_cand[w][j] | (((s_colM[w][j] >> lane) & 1u) ? 0u : NB_UNMIRRORED);
-									B[SB_ENTRIES + (tp & (SB_ENTRIES - 1u))] = rk;
+								if (need_block) {
+									const uint32_t o = tp >> SB_SHIFT;
+									const uint32_t blk = o < n_before ? last_blk : base + (o - n_before);
+									B = blk < A.stream_blocks ? (uint2*)(A.stream + (size_t)blk * SB_WORDS + SB_HEADER) : nullptr;
 								}
+								uint32_t word = s_cand[w][j];
+								if (!all_mirrored && ((rowM >> j) & 1u) == 0u) word |= NB_UNMIRRORED;
+								if (B) B[tp & (SB_ENTRIES - 1u)] = make_uint2(word, rk);
 								tp++; rk++;
+								need_block = (tp & (SB_ENTRIES - 1u)) == 0u;
 							}
 							my_cnt += c;
 							if (need > n_before) { last_blk = base + (need - n_before) - 1u; n_alloc = need; }
@@ -1151,8 +1199,9 @@ k_regroup(const uint32_t* __restrict__ stream, uint32_t stream_blocks, const uin
 			if (blk < used) {
 				const uint32_t* B = stream + (size_t)blk * SB_WORDS;
 				hdr[u] = *(const uint2*)B;
-				word[u] = B[SB_HEADER + threadIdx.x];
-				rk[u] = B[SB_HEADER + SB_ENTRIES + threadIdx.x];
+				const uint2 e = ((const uint2*)(B + SB_HEADER))[threadIdx.x]; // entries are {idN | flag, lane | rank} pairs
+				word[u] = e.x;
+				rk[u] = e.y;
 			}
 		}
 		uint32_t o[U], id[U];
@@ -1227,8 +1276,9 @@ k_regroup_tma(const uint32_t* __restrict__ stream, uint32_t stream_blocks, const
 				asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
 				             : "=r"(done) : "r"(bar), "r"(phase) : "memory");
 			const uint2 hdr = *(const uint2*)&s_blk[u][0];
-			word[u] = s_blk[u][SB_HEADER + threadIdx.x];
-			const uint32_t rk = s_blk[u][SB_HEADER + SB_ENTRIES + threadIdx.x];
+			const uint2 e = ((const uint2*)&s_blk[u][SB_HEADER])[threadIdx.x];
+			word[u] = e.x;
+			const uint32_t rk = e.y;
 			if (threadIdx.x < hdr.y) o[u] = offsets[hdr.x + (rk >> SB_RANK_BITS)] + (rk & SB_RANK_MASK);
 		}
 #pragma unroll
