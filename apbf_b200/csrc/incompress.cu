@@ -26,6 +26,7 @@ constexpr int SWEEP_ILP = 4;       // pairs one lane has in flight
 // shuffle reductions shrink from three stages to two and the transposes from eight rounds to four (r02: -12 % on both sweeps).
 constexpr int LPP = 4, PPR = 32 / LPP, ROUNDS = 32 / PPR;
 #define R_INC APBF_INCOMPRESSIBILITY_DATA_RESOLUTION
+#define R2_MIN_UNSCALED (1.0e-8f * 68719476736.0f) // "dist < 0.0001" (kernels.glsl:93) on the squared distance of the unscaled integer difference
 #define FULL 0xffffffffu
 
 struct sweep_args {
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (HK == 1 && GK == 1 && !COM) ? 
 				kpar hp, gp;
 				hp.w = kg.x; hp.c0 = kh.x; hp.c1 = kh.y;
 				gp.w = kg.x; gp.c0 = kg.y; gp.c1 = kg.z;
+				const float c0s = gp.c0 * (INV_R_POS * INV_R_POS); // Gauss: c0 * 2^-36, see below
 				const uint32_t beg = min(A.offsets[a], A.pair_cap), end = min(A.offsets[a + 1], A.pair_cap);
 				for (uint32_t e0 = beg + sub; e0 < end; e0 += LPP * SWEEP_ILP) { // SWEEP_ILP pairs per lane in flight
 					uint32_t bb[SWEEP_ILP];
@@ -155,11 +157,23 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (HK == 1 && GK == 1 && !COM) ? 
 						const int4 iq = qq[u];
 						const float mN = __int_as_float(iq.w); // neighbour's mass = 1 / inverse mass
 						const int dxi = iq.x - ip.x, dyi = iq.y - ip.y, dzi = iq.z - ip.z; // int subtract first, incompressibility_1.comp:51
-						const float rx = (float)dxi * INV_R_POS, ry = (float)dyi * INV_R_POS, rz = (float)dzi * INV_R_POS;
-						const float r2 = dot3(rx, ry, rz, rx, ry, rz);
 						float W, gk; vec3f g;
-						pair_eval<HK, GK>(hp, gp, rx, ry, rz, r2, W, g, gk);
-						if (GK == 1) A.kp[e0 + LPP * u] = gk; // the apply sweep's gradient of this pair and, between equal widths, of its mirror
+						if (HK == 1 && GK == 1) {
+							// Gauss / Gauss, the reference's default: the 2^-18 of the fixed-point positions is a power of two and commutes with
+							// every rounding on the way, so it is applied to the per-particle constant and to the gradient scalar instead of to
+							// the three differences (identical bits: F2 = r2 * 2^36, c0s = c0 * 2^-36, gks = gk * 2^-18, all exact scalings).
+							const float fx = (float)dxi, fy = (float)dyi, fz = (float)dzi;
+							const float F2 = dot3(fx, fy, fz, fx, fy, fz);
+							W = expf(-F2 * c0s) * gp.c1;
+							gk = F2 >= R2_MIN_UNSCALED ? (-2.0f * W * gp.c0) * INV_R_POS : 0.0f;
+							g.x = gk * fx; g.y = gk * fy; g.z = gk * fz;
+						} else {
+							const float rx = (float)dxi * INV_R_POS, ry = (float)dyi * INV_R_POS, rz = (float)dzi * INV_R_POS;
+							const float r2 = dot3(rx, ry, rz, rx, ry, rz);
+							pair_eval<HK, GK>(hp, gp, rx, ry, rz, r2, W, g, gk);
+							gk *= INV_R_POS;
+						}
+						if (GK == 1) A.kp[e0 + LPP * u] = gk; // (scaled by 2^-18: times the INTEGER difference it is the apply sweep's gradient of this pair and, between equal widths, of its mirror)
 						// x / invMassN * 2^18 (:55-59): 2^18 is a power of two, so (x * mN) * 2^18 == x * (mN * 2^18) bit for bit.
 						// (x * (1 / invMassN) instead of x / invMassN: identical whenever the mass is a power of two -- every scene seeded
 						// by initialize.cpp:16-27 with r a power of two; otherwise the product can differ from the quotient in the last
@@ -304,9 +318,9 @@ __device__ __forceinline__ void t2_pairs(const sweep_args& A, uint32_t e0, uint3
 				// Gauss: grad W_b(-r) = k_b * (-r), and k_b depends on b's width and |r|^2 alone.  Between particles of equal width
 				// it is the very number T1 computed for (a, b) -- same constants, same r2 bits -- so it is read back (4 bytes,
 				// coalesced) instead of evaluated again (dot product, expf, three products: 19 of this loop's 50 instructions).
-				float k = kk[u];
-				if (lb.y != la.y) k = gauss_k(gp_b, r2);
-				g.x = k * -rx; g.y = k * -ry; g.z = k * -rz;
+				float k = kk[u]; // (T1 stored it times 2^-18: it multiplies the unscaled difference)
+				if (lb.y != la.y) k = gauss_k(gp_b, r2) * INV_R_POS;
+				g.x = k * -(float)dxi; g.y = k * -(float)dyi; g.z = k * -(float)dzi;
 			} else {
 				g = kgrad_fast<GK>(gp_b, -rx, -ry, -rz, r2);
 			}
@@ -316,8 +330,8 @@ __device__ __forceinline__ void t2_pairs(const sweep_args& A, uint32_t e0, uint3
 			kpar gp_a; gp_a.w = la.y; gp_a.c0 = la.z; gp_a.c1 = la.w;
 			vec3f g;
 			if (GK == 1) { // a's own kernel: what T1 stored -- unless a is a ghost (slabs), whose segment T1 never walked
-				const float k = kp_ok ? kk[u] : gauss_k(gp_a, r2);
-				g.x = k * rx; g.y = k * ry; g.z = k * rz;
+				const float k = kp_ok ? kk[u] : gauss_k(gp_a, r2) * INV_R_POS;
+				g.x = k * (float)dxi; g.y = k * (float)dyi; g.z = k * (float)dzi;
 			} else g = kgrad_fast<GK>(gp_a, rx, ry, rz, r2);
 			const float f = la.x * R_POS;
 			atomicAdd(&A.push[b].x, f2i(g.x * f));
@@ -327,34 +341,80 @@ __device__ __forceinline__ void t2_pairs(const sweep_args& A, uint32_t e0, uint3
 	}
 }
 
+// ---- list segments staged in shared memory by the bulk-copy engine ------------------------------------------------------------------
+// A round of the sweep walks the segments of 8 consecutive particles: ONE contiguous piece of the pair list (~200 entries).  Read
+// directly, the 8 groups of a load instruction touch 8 different 128-byte lines -- a line of 32 entries costs 8 L1 wavefronts instead
+// of one, and the list loads are two fifths of all wavefronts of this sweep, which is what bounds it (ncu: l1tex data-pipe wavefronts
+// 65 % of peak, issue slots 50 %).  So one lane arms an mbarrier and issues cp.async.bulk for the round's piece of NB and of the
+// gradient scalars (16-byte aligned start: the piece begins up to three entries early); the lanes then read their entries from
+// shared memory.  Rounds longer than STAGE_CAP entries read the lists directly as before.
+constexpr uint32_t STAGE_CAP = 256u;
+struct sweep_stage {
+	uint32_t           nb[SWEEP_THREADS / 32][STAGE_CAP + 4u];
+	float              kp[SWEEP_THREADS / 32][STAGE_CAP + 4u];
+	unsigned long long bar[SWEEP_THREADS / 32];
+};
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void stage_init(sweep_stage& S)
+{
+	if ((threadIdx.x & 31u) == 0u) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(&S.bar[threadIdx.x >> 5])));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	__syncthreads();
+}
+// all lanes of the warp call; E0 .. E1: the round's entries.  Returns true if they are in S (entry e at index e - A0, A0 = E0 & ~3).
+__device__ __forceinline__ bool stage_round(sweep_stage& S, const uint32_t* nbl, const float* kp, uint32_t E0, uint32_t E1, uint32_t& phase)
+{
+	const uint32_t A0 = E0 & ~3u;
+	if (E1 <= E0 || E1 - A0 > STAGE_CAP) return false;
+	const unsigned w = threadIdx.x >> 5;
+	__syncwarp(); // everybody is done with the previous round's entries
+	if ((threadIdx.x & 31u) == 0u) {
+		const uint32_t bytes = ((E1 - A0) * 4u + 15u) & ~15u, bar = smem_addr(&S.bar[w]);
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy reads before, async-proxy writes after
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(2u * bytes) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		             :: "r"(smem_addr(&S.nb[w][0])), "l"(nbl + A0), "r"(bytes), "r"(bar) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		             :: "r"(smem_addr(&S.kp[w][0])), "l"(kp + A0), "r"(bytes), "r"(bar) : "memory");
+	}
+	const uint32_t bar = smem_addr(&S.bar[w]);
+	uint32_t done = 0u;
+	while (!done)
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+	phase ^= 1u;
+	return true;
+}
+
 // The same for a list in which every particle has the same kernel width (and no unmirrored pair), Gauss gradient: the scalar of
 // every pair is what T1 stored, so a neighbour contributes its position and its lambda -- ONE 16-byte gather per pair instead of two.
 // The sweeps are bound by the L1's gather wavefronts (ncu: 77 % of peak in the two-gather form), not by instruction issue.
+// (nbp / kpp: the lists -- in global memory, or the round's staged piece shifted so that the same entry numbers index it)
 template <int K>
-__device__ __forceinline__ void t2_pairs_uniform(const sweep_args& A, uint32_t e0, uint32_t end, uint32_t a, const int4 ip, const float4 e0v,
-                                                 bool filter, int& sx, int& sy, int& sz, int& hit)
+__device__ __forceinline__ void t2_pairs_uniform(const sweep_args& A, const uint32_t* nbp, const float* kpp, uint32_t e0, uint32_t end, uint32_t a,
+                                                 const int4 ip, const float4 e0v, bool filter, int& sx, int& sy, int& sz, int& hit)
 {
 	uint32_t nn[K];
 	int4 qq[K];
 	float kk[K];
 #pragma unroll
-	for (int u = 0; u < K; u++) nn[u] = (e0 + LPP * u < end) ? __ldg(A.nbl + e0 + LPP * u) & NB_ID_MASK : a;
+	for (int u = 0; u < K; u++) nn[u] = (e0 + LPP * u < end) ? nbp[e0 + LPP * u] & NB_ID_MASK : a;
 #pragma unroll
-	for (int u = 0; u < K; u++) kk[u] = (e0 + LPP * u < end) ? __ldg(A.kp + e0 + LPP * u) : 0.0f;
+	for (int u = 0; u < K; u++) kk[u] = (e0 + LPP * u < end) ? kpp[e0 + LPP * u] : 0.0f;
 #pragma unroll
 	for (int u = 0; u < K; u++) qq[u] = __ldg(A.PL + nn[u]);
 #pragma unroll
 	for (int u = 0; u < K; u++) {
 		const int4 iq = qq[u];
 		const int dxi = iq.x - ip.x, dyi = iq.y - ip.y, dzi = iq.z - ip.z;
-		const float rx = (float)dxi * INV_R_POS, ry = (float)dyi * INV_R_POS, rz = (float)dzi * INV_R_POS;
-		if (filter) { // (see t2_pairs)
-			const float r2 = dot3(rx, ry, rz, rx, ry, rz);
-			const float d = dot3(e0v.x, e0v.y, e0v.z, rx, ry, rz);
-			if (r2 >= 1.0e-8f && d < 0.0f && d * d > 0.36f * r2) hit = 1;
+		const float fx = (float)dxi, fy = (float)dyi, fz = (float)dzi; // unscaled: the 2^-18 sits in k (exact, see T1)
+		if (filter) { // (see t2_pairs; both sides of every comparison carry the same power of two)
+			const float F2 = dot3(fx, fy, fz, fx, fy, fz);
+			const float d = dot3(e0v.x, e0v.y, e0v.z, fx, fy, fz);
+			if (F2 >= R2_MIN_UNSCALED && d < 0.0f && d * d > 0.36f * F2) hit = 1;
 		}
 		const float k = kk[u], f = __int_as_float(iq.w);
-		sx += f2i((k * -rx) * f); sy += f2i((k * -ry) * f); sz += f2i((k * -rz) * f);
+		sx += f2i((k * -fx) * f); sy += f2i((k * -fy) * f); sz += f2i((k * -fz) * f);
 	}
 }
 
@@ -363,8 +423,9 @@ __device__ __forceinline__ void t2_pairs_uniform(const sweep_args& A, uint32_t e
 // does not know the list's state without a read-back, so the kernel holds both forms and takes the one that matches (one launch:
 // the second, empty launch of 3907 CTAs used to cost 5.5 us per iteration; both forms fit the same 64 registers).
 template <int GK, bool ASYM, bool UNIFORM>
-__device__ __forceinline__ void apply_delta_body(const sweep_args& A)
+__device__ __forceinline__ void apply_delta_body(const sweep_args& A, sweep_stage& S)
 {
+	uint32_t phase = 0u;
 	const uint32_t n = *A.len;
 	const uint32_t n_own = min(n, A.misc[MW_N_OWNED]); // a ghost's segment holds only unmirrored pairs onto owned particles: push part only
 	const bool filter = A.s.mBoundarinessCalculationMethod == 2;
@@ -391,13 +452,23 @@ __device__ __forceinline__ void apply_delta_body(const sweep_args& A)
 				// the PPR groups of the warp walk their segments in lock step, LPP x SWEEP_ILP pairs per trip, as many trips as the
 				// longest of them needs; the number of slots of the last trip is the same for the whole warp (no divergence)
 				const uint32_t longest = __reduce_max_sync(FULL, end - beg);
+				const uint32_t* nbp = A.nbl;
+				const float* kpp = A.kp;
+				if (UNIFORM) { // the round's piece of the lists: staged by the copy engine (see stage_round)
+					const uint32_t E0 = __reduce_min_sync(FULL, live ? beg : 0xFFFFFFFFu), E1 = __reduce_max_sync(FULL, end);
+					if (stage_round(S, A.nbl, A.kp, E0, E1, phase)) {
+						const unsigned w = threadIdx.x >> 5;
+						nbp = S.nb[w] - (E0 & ~3u);
+						kpp = S.kp[w] - (E0 & ~3u);
+					}
+				}
 				for (uint32_t done = 0; done < longest; done += LPP * SWEEP_ILP) {
 					const uint32_t e0 = beg + done + sub, left = longest - done;
 					if (UNIFORM) {
-						if (left > 3u * LPP) t2_pairs_uniform<4>(A, e0, end, ac, ip, e0v, filter, sx, sy, sz, hit);
-						else if (left > 2u * LPP) t2_pairs_uniform<3>(A, e0, end, ac, ip, e0v, filter, sx, sy, sz, hit);
-						else if (left > 1u * LPP) t2_pairs_uniform<2>(A, e0, end, ac, ip, e0v, filter, sx, sy, sz, hit);
-						else t2_pairs_uniform<1>(A, e0, end, ac, ip, e0v, filter, sx, sy, sz, hit);
+						if (left > 3u * LPP) t2_pairs_uniform<4>(A, nbp, kpp, e0, end, ac, ip, e0v, filter, sx, sy, sz, hit);
+						else if (left > 2u * LPP) t2_pairs_uniform<3>(A, nbp, kpp, e0, end, ac, ip, e0v, filter, sx, sy, sz, hit);
+						else if (left > 1u * LPP) t2_pairs_uniform<2>(A, nbp, kpp, e0, end, ac, ip, e0v, filter, sx, sy, sz, hit);
+						else t2_pairs_uniform<1>(A, nbp, kpp, e0, end, ac, ip, e0v, filter, sx, sy, sz, hit);
 					}
 					else if (left > 3u * LPP) t2_pairs<4, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, kp_ok, sx, sy, sz, hit);
 					else if (left > 2u * LPP) t2_pairs<3, GK, ASYM>(A, e0, end, ac, ip, la, e0v, filter, push_a, kp_ok, sx, sy, sz, hit);
@@ -426,9 +497,11 @@ __device__ __forceinline__ void apply_delta_body(const sweep_args& A)
 template <int GK>
 __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_apply_delta(sweep_args A)
 {
-	if (A.misc[MW_N_ASYM] != 0u) apply_delta_body<GK, true, false>(A);
-	else if (GK == 1 && A.misc[MW_H_NONUNIFORM] == 0u) apply_delta_body<GK, false, true>(A);
-	else apply_delta_body<GK, false, false>(A);
+	__shared__ __align__(16) sweep_stage S;
+	stage_init(S);
+	if (A.misc[MW_N_ASYM] != 0u) apply_delta_body<GK, true, false>(A, S);
+	else if (GK == 1 && A.misc[MW_H_NONUNIFORM] == 0u) apply_delta_body<GK, false, true>(A, S);
+	else apply_delta_body<GK, false, false>(A, S);
 }
 
 // position += delta (+ pushes); xyz only, w is the caller's
