@@ -114,6 +114,12 @@ class Context:
         _check(self, self.lib.apbf_ctx_device_flags(self.handle, C.byref(f)))
         return f.value
 
+    def list_state(self):
+        """which form of the passes the last search / solver iteration selected on the device (apbf_ctx_list_state)"""
+        w = (C.c_uint32 * 4)()
+        _check(self, self.lib.apbf_ctx_list_state(self.handle, w))
+        return {"pairs_unmirrored": int(w[0]), "kernel_widths_uniform": bool(w[1]), "thresholds_uniform": bool(w[2]), "occupied_cells": int(w[3])}
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.apbf_ctx_destroy(self.handle)

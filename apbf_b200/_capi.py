@@ -79,6 +79,7 @@ SIGNATURES = {
     "apbf_ctx_set_stream_blocks": (C.c_int, [vp, C.c_uint32]),
     "apbf_ctx_set_match_grid_min": (C.c_int, [vp, C.c_uint32]),
     "apbf_ctx_device_flags": (C.c_int, [vp, u32p]),
+    "apbf_ctx_list_state": (C.c_int, [vp, u32p]),
     "apbf_ctx_profile": (C.c_int, [vp, C.c_int]),
     "apbf_ctx_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "apbf_buffer_acquire": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),

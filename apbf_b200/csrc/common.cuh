@@ -59,6 +59,9 @@ enum apbf_misc_word {
 	MW_STREAM_OVERFLOW = 21, // the hit stream ran out of blocks (only when the pair list overflows): the two-pass fill takes over
 	MW_REBUILD_LEN = 24,     // rebuild of a structure from a foreign pair list: min(list length, capacity)
 	MW_H_NONUNIFORM = 25,    // solver constants: 1 if two particles of the list differ in kernel width (bitwise), else 0
+	MW_THR_MIN = 26,         // last Green search: smallest / largest bit pattern over all ids of {T, K, U, cutoff} (4 + 4 words): every
+	MW_THR_MAX = 30,         //   test threshold is the same for everybody -- hence every kept pair is mirrored -- iff min >= max in all four
+	MW_INDEX_NONIDENT = 34,  // re-order of the lists: 1 if the index list going in is NOT the identity over all hidden particles
 	MW_WORDS = 64
 };
 

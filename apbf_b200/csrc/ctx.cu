@@ -220,6 +220,20 @@ int apbf_ctx_device_flags(apbf_ctx* ctx, uint32_t* out_flags)
 	return APBF_OK;
 }
 
+int apbf_ctx_list_state(apbf_ctx* ctx, uint32_t out[4])
+{
+	if (!ctx || !out) return APBF_ERR_INVALID;
+	uint32_t w[MW_WORDS];
+	APBF_CUDA(ctx, cudaMemcpyAsync(w, ctx->misc(), sizeof w, cudaMemcpyDeviceToHost, ctx->stream));
+	APBF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	out[0] = w[MW_N_ASYM];
+	out[1] = w[MW_H_NONUNIFORM] == 0u ? 1u : 0u;
+	out[2] = 1u;
+	for (int k = 0; k < 4; k++) if (w[MW_THR_MIN + k] < w[MW_THR_MAX + k]) out[2] = 0u;
+	out[3] = w[MW_OCC_CELLS];
+	return APBF_OK;
+}
+
 // best-fit pool like gpu_list_data::get_list (source/gpu_list_data.cpp:6-45)
 int apbf_buffer_acquire(apbf_ctx* ctx, size_t bytes, void** out)
 {

@@ -78,16 +78,34 @@ __global__ void k_prepare_consts(sweep_args A)
 {
 	const uint32_t n = *A.len;
 	const bool ident = A.misc[MW_IDENTITY] != 0u;
-	for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
-		const uint32_t idx = ident ? a : A.index_list[a];
-		const float w = A.kernel_width[a], invMass = A.inv_mass[idx], radius = A.radius[idx];
-		if (__float_as_uint(w) != __float_as_uint(A.kernel_width[0])) A.misc[MW_H_NONUNIFORM] = 1u; // (cleared by the host before the launch)
-		const kpar hp = height_params<HK>(w, A.D);
-		const kpar gp = grad_params<GK>(w, A.D);
-		const float invRestDensity = pow_int_rn(2.0f * radius, A.D) * invMass;                               // incompressibility_2.comp:81
-		const float lamDiv = pow_int_rn(2.0f * A.s.mSmallestTargetRadius, A.D) / invRestDensity * invMass;  // :98
-		A.KG[a] = make_float4(w, gp.c0, gp.c1, invRestDensity);
-		A.KH[a] = make_float4(hp.c0, hp.c1, lamDiv, invMass);
+	const float w0 = n ? A.kernel_width[0] : 0.0f;
+	// The constants are functions of (kernel width, inverse mass, radius) alone, and ~600 instructions of double-precision
+	// arithmetic per particle.  A thread keeps its last inputs and results: while the whole warp sees the inputs it saw in its
+	// previous trip (one particle class: every trip but the first), nothing is recomputed -- same bits by construction.
+	float pw = 0.0f, pim = 0.0f, pr = 0.0f;
+	float4 kg = make_float4(0.f, 0.f, 0.f, 0.f), kh = kg;
+	bool have = false;
+	for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) { // (warp-uniform trip count)
+		const uint32_t a = base + threadIdx.x;
+		const bool live = a < n;
+		float w = pw, invMass = pim, radius = pr;
+		if (live) {
+			const uint32_t idx = ident ? a : A.index_list[a];
+			w = A.kernel_width[a]; invMass = A.inv_mass[idx]; radius = A.radius[idx];
+			if (__float_as_uint(w) != __float_as_uint(w0)) A.misc[MW_H_NONUNIFORM] = 1u; // (cleared by the host before the launch)
+		}
+		const bool same = have && __float_as_uint(w) == __float_as_uint(pw) && __float_as_uint(invMass) == __float_as_uint(pim) &&
+		                  __float_as_uint(radius) == __float_as_uint(pr);
+		if (!__all_sync(FULL, same)) {
+			const kpar hp = height_params<HK>(w, A.D);
+			const kpar gp = grad_params<GK>(w, A.D);
+			const float invRestDensity = pow_int_rn(2.0f * radius, A.D) * invMass;                               // incompressibility_2.comp:81
+			const float lamDiv = pow_int_rn(2.0f * A.s.mSmallestTargetRadius, A.D) / invRestDensity * invMass;  // :98
+			kg = make_float4(w, gp.c0, gp.c1, invRestDensity);
+			kh = make_float4(hp.c0, hp.c1, lamDiv, invMass);
+			pw = w; pim = invMass; pr = radius; have = true;
+		}
+		if (live) { A.KG[a] = kg; A.KH[a] = kh; }
 	}
 }
 
@@ -432,7 +450,9 @@ __device__ __forceinline__ void apply_delta_body(const sweep_args& A, sweep_stag
 	constexpr bool has_asym = ASYM;
 	const unsigned lane = threadIdx.x & 31u, sub = lane & (LPP - 1u), grp = lane / LPP;
 	const uint32_t warps_per_grid = gridDim.x * (SWEEP_THREADS / 32);
-	for (uint32_t tile = blockIdx.x * (SWEEP_THREADS / 32) + (threadIdx.x >> 5); (size_t)tile * 32 < n; tile += warps_per_grid) {
+	// (without unmirrored pairs the ghosts' segments are empty: the tiles behind the owned particles have nothing to do)
+	const uint32_t n_walk = ASYM ? n : n_own;
+	for (uint32_t tile = blockIdx.x * (SWEEP_THREADS / 32) + (threadIdx.x >> 5); (size_t)tile * 32 < n_walk; tile += warps_per_grid) {
 		const uint32_t base = tile * 32u;
 		int my_sx = 0, my_sy = 0, my_sz = 0, my_hit = 0;
 #pragma unroll 1
@@ -603,7 +623,7 @@ int apbf_solver_prepare(apbf_ctx* ctx, apbf_fluid* fluid)
 	const uint32_t n_cap = fluid->particle.capacity;
 	if (n_cap == 0) return APBF_OK;
 	apbf_prof_scope ps(ctx, PROF_SOLVER_PREPARE);
-	const unsigned grid = apbf_grid(ctx, n_cap, 256);
+	const unsigned grid = apbf_grid(ctx, n_cap, 256, 4); // (few, long-lived threads: k_prepare_consts re-uses its last results)
 	APBF_CUDA(ctx, cudaMemsetAsync(A.misc + MW_H_NONUNIFORM, 0, sizeof(uint32_t), ctx->stream));
 	switch (A.s.mHeightKernelId) {
 		case 0: return launch_prepare<0>(ctx, A, grid);

@@ -20,9 +20,10 @@ namespace {
 // ---- fused reorder of all hidden arrays -------------------------------------------------------------------------------
 using reorder_table = apbf_reorder_table;
 
-__global__ void __launch_bounds__(256) k_reorder(reorder_table t, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ len)
+__global__ void __launch_bounds__(256) k_reorder(reorder_table t, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ len, uint32_t* clear_word)
 {
 	const uint32_t n = *len;
+	if (clear_word && blockIdx.x == 0 && threadIdx.x == 0) *clear_word = 0u; // (MW_INDEX_NONIDENT: raised by k_mark_members, the next launch)
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const uint32_t s = perm[i];
 		int4 v16[4];
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(256) k_reorder(reorder_table t, const uint32_t
 
 int apbf_launch_reorder(apbf_ctx* ctx, const apbf_reorder_table& t, const uint32_t* perm, const uint32_t* len, uint32_t cap)
 {
-	k_reorder<<<apbf_grid(ctx, cap, 256), 256, 0, ctx->stream>>>(t, perm, len);
+	k_reorder<<<apbf_grid(ctx, cap, 256), 256, 0, ctx->stream>>>(t, perm, len, nullptr);
 	APBF_LAUNCHED(ctx);
 	return APBF_OK;
 }
@@ -50,15 +51,27 @@ int apbf_launch_reorder(apbf_ctx* ctx, const apbf_reorder_table& t, const uint32
 namespace {
 
 // ---- index list after the hidden permutation (indexed_list.h:289-308 + :276-286 for a permutation edit) ------------------
-__global__ void k_mark_members(const uint32_t* __restrict__ index_list, const uint32_t* __restrict__ len, uint32_t* __restrict__ mark)
+// The usual case -- every hidden particle is a member and id i points at slot i (what a search leaves behind: the lists come out
+// sorted) -- needs no marks, flags, scan or compaction: the new index list is the identity again and the ids move exactly like
+// their slots.  k_mark_members finds out (MW_INDEX_NONIDENT, cleared by k_reorder before); the passes behind it return at once
+// when the word is still 0, and k_compact_members writes the two trivial lists.
+__global__ void k_mark_members(const uint32_t* __restrict__ index_list, const uint32_t* __restrict__ len, const uint32_t* __restrict__ hidden_len,
+                               uint32_t* __restrict__ mark, uint32_t* misc)
 {
 	const uint32_t n = *len;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mark[index_list[i]] = i + 1u;
+	bool other = blockIdx.x == 0 && threadIdx.x == 0 && n != *hidden_len;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const uint32_t s = index_list[i];
+		mark[s] = i + 1u;
+		other = other || s != i;
+	}
+	if (other) misc[MW_INDEX_NONIDENT] = 1u;
 }
 
 __global__ void k_member_flags(const uint32_t* __restrict__ sorted_index, const uint32_t* __restrict__ mark,
-                               const uint32_t* __restrict__ hidden_len, uint32_t* __restrict__ flags)
+                               const uint32_t* __restrict__ hidden_len, uint32_t* __restrict__ flags, const uint32_t* __restrict__ misc)
 {
+	if (misc[MW_INDEX_NONIDENT] == 0u) return;
 	const uint32_t n = *hidden_len;
 	for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < n; h += gridDim.x * blockDim.x)
 		flags[h] = mark[sorted_index[h]] != 0u ? 1u : 0u;
@@ -70,6 +83,13 @@ __global__ void k_compact_members(const uint32_t* __restrict__ sorted_index, con
                                   uint32_t* __restrict__ id_perm, uint32_t index_cap, uint32_t* misc)
 {
 	const uint32_t n = *hidden_len;
+	if (misc[MW_INDEX_NONIDENT] == 0u) { // identity in: identity out, ids follow their slots
+		for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < n; h += gridDim.x * blockDim.x) {
+			if (h < index_cap) { new_index_list[h] = h; id_perm[h] = sorted_index[h]; }
+			if (h == 0) misc[MW_IDENTITY] = 1u;
+		}
+		return;
+	}
 	for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < n; h += gridDim.x * blockDim.x) {
 		uint32_t m = mark[sorted_index[h]];
 		if (m != 0u) {
@@ -163,41 +183,82 @@ __device__ __forceinline__ float4 prune_record(float T, float cut, float orig, i
 	return qb;
 }
 
-__global__ void k_build_q4(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const uint32_t* __restrict__ hidden_key,
-                           const float* __restrict__ range, float range_scale, const uint32_t* __restrict__ len,
-                           float4* __restrict__ q4, uint32_t* __restrict__ key_id, uint32_t* __restrict__ misc, const build_kw_args K)
+__global__ void __launch_bounds__(256)
+k_build_q4(const uint32_t* __restrict__ index_list, const int32_t* __restrict__ pos4, const uint32_t* __restrict__ hidden_key,
+           const float* __restrict__ range, float range_scale, const uint32_t* __restrict__ len,
+           float4* __restrict__ q4, uint32_t* __restrict__ key_id, uint32_t* __restrict__ misc, const build_kw_args K)
 {
+	// Device-wide scalars (occupied cells, largest initial width, smallest / largest thresholds) are reduced per thread, per warp
+	// and per CTA before they touch their word -- and only if they would change it: an atomic on one address costs ~0.1 us,
+	// one per warp (37 000 of them) used to be most of this kernel's time.
+	__shared__ uint32_t s_red[8][10];
 	const bool ident = misc[MW_IDENTITY] != 0u;
 	const uint32_t n = *len;
+	const unsigned lane = lane_id();
 	uint32_t max_init = 0u; // fused: the largest initial width (kernel_width_init.comp:35) this thread has seen
-	for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
-		const uint32_t idx = ident ? id : index_list[id];
-		const int4 ip = ldg_int4(pos4, idx);
-		q4[id] = make_float4((float)ip.x * INV_R_POS, (float)ip.y * INV_R_POS, (float)ip.z * INV_R_POS,
-		                     sqrt_threshold(range[id] * range_scale));
-		if (K.i4) {
-			const float orig = glsl_max(K.radius[idx], K.base_on_target_radius ? K.target_radius[id] : 0.0f) * APBF_KERNEL_SCALE;
-			K.i4[id] = make_int4(ip.x, ip.y, ip.z, __float_as_int(orig));
-			// dist <= cutoff (kernel_width.comp:57) with dist = sqrt(d2) is d2 <= sqrt_threshold(cutoff); d2 = D2 * 2^-36 exactly,
-			// D2 the same sum over the unscaled integer differences (powers of two commute with the roundings)
-			const float cut = glsl_max(orig, K.kernel_width[id]);
-			K.cutoff[id] = cut == cut ? sqrt_threshold(cut) * 68719476736.0f : -1.0f; // dist <= NaN keeps nothing
-			const float4 qb = prune_record(sqrt_threshold(range[id] * range_scale), cut, orig, ip, K.pmax);
-			K.qb4[id] = qb;
-			atomicMax(K.cell_maxw + hidden_key[idx], f2u(orig * APBF_KERNEL_WIDTH_RESOLUTION)); // (keys of ghosts index the second table)
-			max_init = max(max_init, f2u(orig * APBF_KERNEL_WIDTH_RESOLUTION));
+	uint32_t occ = 0u;      // occupied cells = ids whose key differs from their predecessor's (the emit sizes its query blocks with it)
+	uint32_t thr_lo[4] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, thr_hi[4] = { 0u, 0u, 0u, 0u }; // bits of {T, K, U, cutoff}
+	for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) { // (warp-uniform trip count)
+		const uint32_t id = base + threadIdx.x;
+		const bool live = id < n;
+		uint32_t key = 0xFFFFFFFFu, width_fx = 0u;
+		if (live) {
+			const uint32_t idx = ident ? id : index_list[id];
+			const int4 ip = ldg_int4(pos4, idx);
+			const float T = sqrt_threshold(range[id] * range_scale);
+			q4[id] = make_float4((float)ip.x * INV_R_POS, (float)ip.y * INV_R_POS, (float)ip.z * INV_R_POS, T);
+			thr_lo[0] = min(thr_lo[0], __float_as_uint(T)); thr_hi[0] = max(thr_hi[0], __float_as_uint(T));
+			if (K.i4) {
+				const float orig = glsl_max(K.radius[idx], K.base_on_target_radius ? K.target_radius[id] : 0.0f) * APBF_KERNEL_SCALE;
+				K.i4[id] = make_int4(ip.x, ip.y, ip.z, __float_as_int(orig));
+				// dist <= cutoff (kernel_width.comp:57) with dist = sqrt(d2) is d2 <= sqrt_threshold(cutoff); d2 = D2 * 2^-36 exactly,
+				// D2 the same sum over the unscaled integer differences (powers of two commute with the roundings)
+				const float cut = glsl_max(orig, K.kernel_width[id]);
+				const float cutoff = cut == cut ? sqrt_threshold(cut) * 68719476736.0f : -1.0f; // dist <= NaN keeps nothing
+				K.cutoff[id] = cutoff;
+				const float4 qb = prune_record(T, cut, orig, ip, K.pmax);
+				K.qb4[id] = qb;
+				const uint32_t tb[3] = { __float_as_uint(qb.x), __float_as_uint(qb.y), __float_as_uint(cutoff) };
+#pragma unroll
+				for (int k = 0; k < 3; k++) { thr_lo[k + 1] = min(thr_lo[k + 1], tb[k]); thr_hi[k + 1] = max(thr_hi[k + 1], tb[k]); }
+				width_fx = f2u(orig * APBF_KERNEL_WIDTH_RESOLUTION);
+				max_init = max(max_init, width_fx);
+			}
+			key = hidden_key[idx];
+			key_id[id] = key;
+			if (id == 0u || hidden_key[ident ? id - 1u : index_list[id - 1u]] != key) occ++;
 		}
-		const uint32_t key = hidden_key[idx];
-		key_id[id] = key;
-		// occupied cells = ids whose key differs from their predecessor's (the emit sizes its query blocks with it)
-		const bool head = id == 0u || hidden_key[ident ? id - 1u : index_list[id - 1u]] != key;
-		const uint32_t heads = __ballot_sync(__activemask(), head);
-		if (head && (heads & ((1u << lane_id()) - 1u)) == 0u) atomicAdd(misc + MW_OCC_CELLS, (uint32_t)__popc(heads));
+		if (K.i4) {
+			// largest initial width per cell (keys of ghosts index the second table): the lanes of a cell -- neighbours in the sorted
+			// list -- agree on their maximum, one of them publishes it
+			const uint32_t grp = __match_any_sync(0xffffffffu, key);
+			const uint32_t mx = __reduce_max_sync(grp, width_fx);
+			if (live && lane == (uint32_t)__ffs(grp) - 1u && mx > K.cell_maxw[key]) atomicMax(K.cell_maxw + key, mx);
+		}
 	}
-	if (K.i4) {
-		const uint32_t m = __activemask();
-		max_init = __reduce_max_sync(m, max_init);
-		if ((m & ((1u << lane_id()) - 1u)) == 0u && max_init) atomicMax(misc + MW_MAX_INIT, max_init);
+	uint32_t red[10];
+	red[0] = __reduce_add_sync(0xffffffffu, occ);
+	red[1] = __reduce_max_sync(0xffffffffu, max_init);
+#pragma unroll
+	for (int k = 0; k < 4; k++) { red[2 + k] = __reduce_min_sync(0xffffffffu, thr_lo[k]); red[6 + k] = __reduce_max_sync(0xffffffffu, thr_hi[k]); }
+	if (lane == 0u) {
+#pragma unroll
+		for (int k = 0; k < 10; k++) s_red[threadIdx.x >> 5][k] = red[k];
+	}
+	__syncthreads();
+	if (threadIdx.x < 10u) {
+		const uint32_t k = threadIdx.x;
+		uint32_t v = s_red[0][k];
+		for (uint32_t w = 1; w < blockDim.x / 32u; w++) {
+			const uint32_t x = s_red[w][k];
+			v = k == 0u ? v + x : (k >= 2u && k < 6u) ? min(v, x) : max(v, x);
+		}
+		// are the test thresholds the same for every id?  (then "the mirrored pair is kept" is the same test as "the pair is kept"
+		// for every pair of the list: slabs skip their ghost queries, which exist only to find unmirrored pairs)
+		volatile uint32_t* word = misc + (k == 0u ? MW_OCC_CELLS : k == 1u ? MW_MAX_INIT : k < 6u ? MW_THR_MIN + (k - 2u) : MW_THR_MAX + (k - 6u));
+		if (k == 0u) { if (v) atomicAdd((uint32_t*)word, v); }
+		else if (k >= 2u && k < 6u) { if (v < *word) atomicMin((uint32_t*)word, v); }
+		else if (v > *word) atomicMax((uint32_t*)word, v);
 	}
 }
 
@@ -812,6 +873,14 @@ k_green_stream(const emit_args A)
 		csz[d] = g.ext[d] / g.scale;
 		eps[d] = 1.0e-3f * csz[d] + 1.0e-5f * (fabsf(g.mn[d]) + fabsf(g.ext[d])); // rounding of the cell map, generously
 	}
+	// Slabs: a ghost is a query only for unmirrored pairs onto owned particles.  When every id has the same thresholds (k_build_q4)
+	// there is no such pair -- (idN, id) passes exactly the tests (id, idN) passes -- and the ghosts' chunks are skipped.
+	bool skip_ghost_queries = false;
+	if (MG && !STATS && SEARCH == 0 && (FUSED || layers != 3u)) {
+		skip_ghost_queries = true;
+#pragma unroll
+		for (int k = 0; k < 4; k++) skip_ghost_queries = skip_ghost_queries && A.misc[MW_THR_MIN + k] >= A.misc[MW_THR_MAX + k];
+	}
 	uint32_t n_searched = 0;
 	for (;;) {
 		uint32_t win = 0;
@@ -846,6 +915,13 @@ k_green_stream(const emit_args A)
 				const uint32_t first = blk_first + c0, cnt = min(chunk_len, blk_len - c0);
 				const uint32_t id = first + lane;
 				const bool valid = lane < cnt;
+				if (MG && skip_ghost_queries && first >= n_owned) {
+					if (valid) {
+						A.counts[id] = 0u;
+						if (FUSED) A.kwfx[id] = f2u(A.qb4[id].w * APBF_KERNEL_WIDTH_RESOLUTION); // (the owner's new width replaces it)
+					}
+					continue;
+				}
 				float4 me = make_float4(0.f, 0.f, 0.f, -1.0f);
 				float4 qb = make_float4(-1.0f, -1.0f, 0.0f, 0.0f);
 				uint32_t gmin[3] = { 0u, 0u, 0u }, gmax[3] = { 0u, 0u, 0u };
@@ -1370,6 +1446,7 @@ __global__ void k_clear_search_words(uint32_t* misc)
 {
 	misc[MW_N_ASYM] = 0u; misc[MW_TOTAL_PAIRS] = 0u; misc[MW_KEPT_PAIRS] = 0xFFFFFFFFu; misc[MW_OCC_CELLS] = 0u;
 	misc[MW_EMIT_TICKET0] = 0u; misc[MW_EMIT_TICKET1] = 0u; misc[MW_STREAM_CURSOR] = 0u; misc[MW_STREAM_OVERFLOW] = 0u; misc[MW_MAX_INIT] = 0u; misc[MW_PMAX] = 0u;
+	for (int k = 0; k < 4; k++) { misc[MW_THR_MIN + k] = 0xFFFFFFFFu; misc[MW_THR_MAX + k] = 0u; }
 }
 
 // offsets[id] for the ids between the list's length and its capacity: empty segments.  A list that grows afterwards (the copies
@@ -1400,7 +1477,7 @@ int reorder_lists(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, con
 		APBF_REQUIRE(ctx, a->data && a->reorder_out && a->data != a->reorder_out);
 		t.src4[t.n4] = (const uint32_t*)a->data; t.dst4[t.n4] = (uint32_t*)a->reorder_out; t.n4++;
 	}
-	k_reorder<<<apbf_grid(ctx, nh_cap, 256), 256, 0, st>>>(t, sorted_index, p.hidden_length);
+	k_reorder<<<apbf_grid(ctx, nh_cap, 256), 256, 0, st>>>(t, sorted_index, p.hidden_length, ctx->misc() + MW_INDEX_NONIDENT);
 	APBF_LAUNCHED(ctx);
 
 	// index list and the permutation of the ids
@@ -1411,11 +1488,11 @@ int reorder_lists(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range, con
 	uint32_t* id_perm = (uint32_t*)ctx->scratch_get(SLOT_TMP_VALS2, sizeof(uint32_t) * (size_t)n_cap);
 	if (!mark || !flags || !offs || !id_perm) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 	APBF_CUDA(ctx, cudaMemsetAsync(mark, 0, sizeof(uint32_t) * (size_t)nh_cap, st));
-	k_mark_members<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>((const uint32_t*)p.index_list.data, p.length, mark);
+	k_mark_members<<<apbf_grid(ctx, n_cap, 256), 256, 0, st>>>((const uint32_t*)p.index_list.data, p.length, p.hidden_length, mark, ctx->misc());
 	APBF_LAUNCHED(ctx);
-	k_member_flags<<<apbf_grid(ctx, nh_cap, 256), 256, 0, st>>>(sorted_index, mark, p.hidden_length, flags);
+	k_member_flags<<<apbf_grid(ctx, nh_cap, 256), 256, 0, st>>>(sorted_index, mark, p.hidden_length, flags, ctx->misc());
 	APBF_LAUNCHED(ctx);
-	APBF_TRY(apbf_scan_u32(ctx, flags, offs, p.hidden_length, nh_cap, false, nullptr, 0xFFFFFFFFu, nullptr, nullptr));
+	APBF_TRY(apbf_scan_u32(ctx, flags, offs, p.hidden_length, nh_cap, false, nullptr, 0xFFFFFFFFu, nullptr, nullptr, ctx->misc() + MW_INDEX_NONIDENT));
 	k_compact_members<<<apbf_grid(ctx, nh_cap, 256), 256, 0, st>>>(sorted_index, mark, offs, p.hidden_length, p.length,
 	                                                               (uint32_t*)p.index_list.reorder_out, id_perm, n_cap, ctx->misc());
 	APBF_LAUNCHED(ctx);

@@ -15,4 +15,5 @@ int apbf_reference_sort_bits(uint32_t upper_bound);
 // result[i] = sum_{j<=i} values[j] (inclusive) or sum_{j<i} (exclusive); optionally writes the grand total
 // to *total_out (device) -- clamped to total_clamp -- and raises flag bit 0 in *flags_out when it was clamped.
 int apbf_scan_u32(apbf_ctx* ctx, const uint32_t* values, uint32_t* result, const uint32_t* count, uint32_t max_count,
-                  bool inclusive, uint32_t* total_out, uint32_t total_clamp, uint32_t* flags_out, uint32_t* raw_total_out);
+                  bool inclusive, uint32_t* total_out, uint32_t total_clamp, uint32_t* flags_out, uint32_t* raw_total_out,
+                  const uint32_t* run_if = nullptr); // run_if: device word; the scan does nothing when it is 0

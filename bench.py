@@ -286,6 +286,7 @@ def run_single(gpu, torch, workload, steps, warmup, *, device=0, search="green",
     prof_ms = p0.elapsed_time(p1)
     prof = ctx.profile_read()
     stats = sim.stats()
+    stats = dict(stats, list_state=ctx.list_state())
     clocks = sampler.stop() if sampler else None
     if meta["adaptive"] and stats_pass:
         # the fused search never builds the unpruned list; one more (untimed) substep counts what it would have held
@@ -487,7 +488,7 @@ def run_gpu(args, rank, world, local_rank):
         "config": {"workload": args.workload, "scene": sc.name, "particles_per_gpu": n, "adaptive_kernel_width": meta["adaptive"],
                    "solver_iterations": sc.solver_iterations, "search": args.search, "res_log2": sc.res_log2,
                    "pairs_searched": stats["pairs_searched"], "pairs_kept": stats["pairs_kept"],
-                   "pairs_unmirrored": stats["pairs_unmirrored"], "device_flags": r["flags"],
+                   "pairs_unmirrored": stats["pairs_unmirrored"], "device_flags": r["flags"], "list_state": stats.get("list_state"),
                    "multi_gpu": "single" if world == 1 else "independent replicas",
                    "l2": "working set (lists + pair list) exceeds the 126 MB L2" if (76 * n + 8 * stats["pairs_searched"]) > 126e6
                          else "working set fits L2; no flush between steps"},

@@ -143,6 +143,7 @@ def run(args, rank, world, local_rank, peak, peak_src, emit, ClockSampler, make_
     ctx.profile(False)
     prof = ctx.profile_read()
     stats = run_.sim.stats()
+    list_state = ctx.list_state()   # which form of the passes the device selected (ghost queries skipped, one-gather apply sweep, ...)
     if meta["adaptive"]:
         ctx.set_search_stats(True)
         run_.step()
@@ -227,7 +228,7 @@ def run(args, rank, world, local_rank, peak, peak_src, emit, ClockSampler, make_
             "config": {"workload": args.workload, "scene": sc.name, "particles_per_gpu": n_local, "particles_total": int(sc.n),
                        "adaptive_kernel_width": meta["adaptive"], "solver_iterations": sc.solver_iterations, "search": "green", "res_log2": sc.res_log2,
                        "pairs_searched": stats["pairs_searched"], "pairs_kept": stats["pairs_kept"], "pairs_unmirrored": stats["pairs_unmirrored"],
-                       "device_flags": flags, "multi_gpu": "one scene in bricks (top bits of the cell key), ghost particles, halo exchange every solver iteration",
+                       "device_flags": flags, "list_state": list_state, "multi_gpu": "one scene in bricks (top bits of the cell key), ghost particles, halo exchange every solver iteration",
                        "driver": driver, "slab": slab_stats,
                        "l2": "working set (lists + pair list) exceeds the 126 MB L2"},
             "gpu_launches": launches,

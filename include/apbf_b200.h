@@ -100,6 +100,10 @@ int  apbf_ctx_profile(apbf_ctx* ctx, int enable);
 int  apbf_ctx_profile_read(apbf_ctx* ctx, int category, const char** out_name, double* out_ms, uint64_t* out_calls);
 /* sticky device-side status word: bit 0 = neighbour list overflow (neighbor_add.glsl:23-24 clamp hit). Synchronises. */
 int  apbf_ctx_device_flags(apbf_ctx* ctx, uint32_t* out_flags);
+/* which form of the passes the lists of the last search / solver iteration selected on the device (diagnostics; no counterpart in
+ * the reference; synchronises): out[0] = pairs without a mirrored pair in the list, out[1] = 1 if every particle has the same
+ * kernel width (bitwise), out[2] = 1 if every id had the same search / prune thresholds, out[3] = occupied grid cells. */
+int  apbf_ctx_list_state(apbf_ctx* ctx, uint32_t out[4]);
 
 /* ---- buffers: gpu_list_data::get_list best-fit pool (source/gpu_list_data.cpp:6-45) + algorithms::copy_bytes -- */
 int apbf_buffer_acquire(apbf_ctx* ctx, size_t bytes, void** out_dev_ptr);
