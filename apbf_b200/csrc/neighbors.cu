@@ -852,7 +852,6 @@ k_green_stream(const emit_args A)
 	__shared__ float4 s_q[EMIT_WARPS][32];                       // {x, y, z, K}: K = T (plain) or min(T, C - hw) (fused)
 	__shared__ float s_u[FUSED ? EMIT_WARPS : 1][32];            // U = min(T, C + hw)
 	__shared__ float s_T[FUSED ? EMIT_WARPS : 1][32];            // threshold of the range test alone
-	__shared__ uint32_t s_cand[EMIT_WARPS][32];
 	// the same queries as pairs for the packed test loop (chunk_tests): {x0, x1, y0, y1}, {z0, z1, K0, K1}, {U0, U1}
 	__shared__ __align__(16) float4 s_qa[EMIT_WARPS][16], s_qb[EMIT_WARPS][16];
 	__shared__ __align__(8) float2 s_u2[FUSED ? EMIT_WARPS : 1][16];
@@ -1183,7 +1182,6 @@ k_green_stream(const emit_args A)
 						}
 						// ---- lane = query again: append the hits to the chunk's stream ---------------------------------------------
 						if (__any_sync(0xffffffffu, colK != 0u)) {
-							s_cand[w][lane] = cand;
 							// is the mirrored pair (idN, id) kept for every hit of the batch?  (equal widths: always)  Then no entry carries the
 							// "unmirrored" flag and the mirrored bits need not be transposed.
 							const bool all_mirrored = __all_sync(0xffffffffu, (colK & ~colM) == 0u);
@@ -1210,30 +1208,34 @@ k_green_stream(const emit_args A)
 									if (base + i < A.stream_blocks) *(uint2*)(A.stream + (size_t)(base + i) * SB_WORDS) = make_uint2(first, SB_ENTRIES);
 							}
 							if (my_cnt + c > SB_RANK_MASK) A.misc[MW_STREAM_OVERFLOW] = 1u; // the rank field is full: two-pass fill
-							__syncwarp();
-							// this query's hits, in candidate order, go to entries tp, tp + 1, ... of the chunk's stream: {idN | flag, lane | rank} as one
-							// 8-byte store; the block's address is worked out once and again only where the run crosses into the next block
-							uint32_t m = rowK, tp = tile_pos + (inc - c), rk = (lane << SB_RANK_BITS) | (my_cnt & SB_RANK_MASK);
-							uint2* B = nullptr;
-							bool need_block = true;
-							while (m) {
-								const uint32_t j = (uint32_t)__ffs(m) - 1u;
-								m &= m - 1u;
-								if (need_block) {
-									const uint32_t o = tp >> SB_SHIFT;
-									const uint32_t blk = o < n_before ? last_blk : base + (o - n_before);
-									B = blk < A.stream_blocks ? (uint2*)(A.stream + (size_t)blk * SB_WORDS + SB_HEADER) : nullptr;
-								}
-								uint32_t word = s_cand[w][j];
+							// This query's hits, in candidate order, go to entries tp, tp + 1, ... of the chunk's stream as 8-byte stores
+							// {idN | flag, lane | rank}.  The loop is uniform over the warp -- as many trips as the busiest query has hits, a
+							// query with fewer sits out -- so the candidate's id comes by shuffle from the lane that loaded it, and a trip is
+							// ~15 instructions (the per-lane `while (bits)` form with its shared-memory look-up was 40: a fifth of this
+							// kernel's instructions).  A run of <= 32 entries crosses at most one block boundary: both block addresses are
+							// worked out beforehand.  (After an overflow the stream is thrown away: writes without a block go to block 0.)
+							const uint32_t tp = tile_pos + (inc - c), o0 = tp >> SB_SHIFT;
+							const uint32_t blk0 = o0 < n_before ? last_blk : base + (o0 - n_before), blk1 = base + (o0 + 1u - n_before);
+							uint2* P = (uint2*)(A.stream + (size_t)(blk0 < A.stream_blocks ? blk0 : 0u) * SB_WORDS + SB_HEADER) + (tp & (SB_ENTRIES - 1u));
+							uint2* const P1 = (uint2*)(A.stream + (size_t)(blk1 < A.stream_blocks ? blk1 : 0u) * SB_WORDS + SB_HEADER);
+							const uint32_t cross = SB_ENTRIES - (tp & (SB_ENTRIES - 1u)); // entries of the run that still fit its first block
+							const uint32_t trips = __reduce_max_sync(0xffffffffu, c);
+							uint32_t m = rowK, rk = (lane << SB_RANK_BITS) | (my_cnt & SB_RANK_MASK);
+							for (uint32_t it = 0; it < trips; it++) {
+								const bool act = m != 0u;
+								const uint32_t j = act ? (uint32_t)__ffs(m) - 1u : 0u;
+								uint32_t word = __shfl_sync(0xffffffffu, cand, (int)j);
 								if (!all_mirrored && ((rowM >> j) & 1u) == 0u) word |= NB_UNMIRRORED;
-								if (B) B[tp & (SB_ENTRIES - 1u)] = make_uint2(word, rk);
-								tp++; rk++;
-								need_block = (tp & (SB_ENTRIES - 1u)) == 0u;
+								if (act) {
+									if (it == cross) P = P1;
+									*P = make_uint2(word, rk);
+									P++; rk++;
+								}
+								m &= m - 1u;
 							}
 							my_cnt += c;
 							if (need > n_before) { last_blk = base + (need - n_before) - 1u; n_alloc = need; }
 							tile_pos += tot;
-							__syncwarp();
 						}
 					}
 				}
