@@ -230,11 +230,13 @@ def shuffle_state(arrays, seed=7):
     return out
 
 
-def dam_break(nx=100, ny=100, nz=100, r=1.0, jitter=0.05, seed=99, adaptive=True, blocks=1, center_y=False, res_log2=None):
+def dam_break(nx=100, ny=100, nz=100, r=1.0, jitter=0.05, seed=99, adaptive=True, blocks=1, center_y=False, res_log2=None, grid="pool"):
     """configs[1]: a block occupying one third of a pool floor (walls per pool.cpp:30-40), adaptive widths.
     Multi-GPU variants (bench.py --gpus N; bricks = halves of the grid along z, then y, then x): `blocks=2` puts a second,
     mirrored block at the far end of the pool (the pool is twice as long, the blocks still cover a third of the floor) so
-    that the x halves hold the same number of particles; `center_y` makes the grid's y range symmetric about the block."""
+    that the x halves hold the same number of particles; `center_y` makes the grid's y range symmetric about the block.
+    grid: "pool" = the search grid spans the pool plus a margin per axis, like pool.cpp:48 (the golden fixtures and the parity
+    scenes were seeded with it); "cube" = equal extents on all axes (what bench.py times)."""
     ext = np.array([nx, ny, nz], np.float32) * 2 * r
     pool_min = np.array([0, 0, 0], np.float32)
     pool_max = np.array([3 * blocks * ext[0], 1.5 * ext[1], ext[2]], np.float32)
@@ -250,6 +252,15 @@ def dam_break(nx=100, ny=100, nz=100, r=1.0, jitter=0.05, seed=99, adaptive=True
         cy = 0.5 * float(ext[1])
         half = max(cy - lo[1], hi[1] - cy)
         lo[1], hi[1] = cy - half, cy + half
+    if grid == "cube":
+        # set_position_range takes ONE resolution for all axes (neighborhood_green.cpp:19): bounds that hug a 600 x 300 x 200 pool
+        # give cells of 4.8 x 2.5 x 1.7 r at 128 cells per axis, and a walk of one cutoff around a block of cells visits four
+        # times the cells a cubic grid needs.  "cube": every axis gets the longest extent, centred where it was (the bricks of
+        # the multi-GPU runs cut the grid in halves, so the fluid stays symmetric about the cuts).  Measured at 10^6 particles:
+        # emit 0.71 -> 0.58 ms (profiles/r02_variants.md).
+        half = 0.5 * max(h - l for l, h in zip(lo, hi))
+        mid = [0.5 * (l + h) for l, h in zip(lo, hi)]
+        lo = [m - half for m in mid]; hi = [m + half for m in mid]
     if res_log2 is None:
         # per-axis grid bounds (cells need not be cubes); resolution so that the widest cell is about 0.75 x search range
         res_log2 = _res_for(max(h - l for l, h in zip(lo, hi)), 4.5 * r)

@@ -36,8 +36,10 @@ UNIT = "particle-substeps/s"
 
 # one scene across N GPUs (weak scaling, 10^6 particles per GPU): the bricks are the halves of the search grid along z, then y,
 # then x (apbf_b200/multi_gpu.py), so the dam-break grows along those axes and stays symmetric about the cutting planes
-SLAB_DAM_BREAK = {2: dict(nx=100, ny=100, nz=200), 4: dict(nx=100, ny=200, nz=200, center_y=True, res_log2=8),
+SLAB_DAM_BREAK = {2: dict(nx=100, ny=100, nz=200), 4: dict(nx=100, ny=200, nz=200, center_y=True),
                   8: dict(nx=100, ny=200, nz=200, blocks=2, center_y=True)}
+# search grid of the timed dam breaks: equal extents on all axes, i.e. cubic cells of 4.8 r (scenes.dam_break, grid="cube")
+DAM_BREAK_GRID = "cube"
 # bounded sample of each workload for the CPU arm (the oracle needs ~10 us per particle-substep and thread)
 CPU_SAMPLE = {"dam_break_1M": "dam_break_262k", "uniform_64": "uniform_64", "dam_break_1M_default_mode": "dam_break_64k_default_mode",
               "dam_break_1M_split_merge": "dam_break_64k_split_merge", "waterfall_16M": "waterfall_262k", "waterdrop_4M": "waterdrop_500k",
@@ -48,25 +50,25 @@ def make_scene(name, world=1, res_log2=None):
     """BASELINE.json configs -> synthetic scenes (apbf_b200/scenes.py)"""
     rl = dict(res_log2=res_log2) if res_log2 else {}
     if name == "dam_break_1M" and world in SLAB_DAM_BREAK:
-        return scenes.dam_break(adaptive=True, **{**SLAB_DAM_BREAK[world], **rl}), dict(adaptive=True, pairs_per_particle=150, slab=True)
+        return scenes.dam_break(adaptive=True, grid=DAM_BREAK_GRID, **{**SLAB_DAM_BREAK[world], **rl}), dict(adaptive=True, pairs_per_particle=150, slab=True)
     if name == "dam_break_1M":      # configs[1]: pool scene dam-break, 1M particles, adaptive kernel width
-        return scenes.dam_break(100, 100, 100, adaptive=True, **rl), dict(adaptive=True, pairs_per_particle=150)
+        return scenes.dam_break(100, 100, 100, adaptive=True, grid=DAM_BREAK_GRID, **rl), dict(adaptive=True, pairs_per_particle=150)
     if name == "dam_break_1M_default_mode":   # the reference's default adaptive mode: kernel width from the boundary distance
         # (pool.cpp:77-80) + update_transfers after the solver (pool.cpp:99-102, merge and split off); no spread_kernel_width
-        return scenes.dam_break(100, 100, 100, adaptive=True, **rl), dict(adaptive=False, basic_pbf=False, update_transfers=True, pairs_per_particle=60)
+        return scenes.dam_break(100, 100, 100, adaptive=True, grid=DAM_BREAK_GRID, **rl), dict(adaptive=False, basic_pbf=False, update_transfers=True, pairs_per_particle=60)
     if name == "dam_break_1M_split_merge":   # the default mode with settings::merge / settings::split on (pool.cpp:73-75, :99-102;
         # SURVEY 8f row 3): particle_transfer after velocity_handling, merge / split decisions after the solver; room for 25 % copies
-        return scenes.dam_break(100, 100, 100, adaptive=True, **rl), dict(adaptive=False, basic_pbf=False, update_transfers=True, transfers=True,
+        return scenes.dam_break(100, 100, 100, adaptive=True, grid=DAM_BREAK_GRID, **rl), dict(adaptive=False, basic_pbf=False, update_transfers=True, transfers=True,
                                                                           pairs_per_particle=60, capacity_factor=1.25)
     if name == "dam_break_64k_split_merge":
-        return scenes.dam_break(40, 40, 40, adaptive=True), dict(adaptive=False, basic_pbf=False, update_transfers=True, transfers=True,
+        return scenes.dam_break(40, 40, 40, adaptive=True, grid=DAM_BREAK_GRID), dict(adaptive=False, basic_pbf=False, update_transfers=True, transfers=True,
                                                                  pairs_per_particle=60, capacity_factor=1.25)
     if name == "dam_break_64k_default_mode":
-        return scenes.dam_break(40, 40, 40, adaptive=True), dict(adaptive=False, basic_pbf=False, update_transfers=True, pairs_per_particle=60)
+        return scenes.dam_break(40, 40, 40, adaptive=True, grid=DAM_BREAK_GRID), dict(adaptive=False, basic_pbf=False, update_transfers=True, pairs_per_particle=60)
     if name == "dam_break_64k":
-        return scenes.dam_break(40, 40, 40, adaptive=True), dict(adaptive=True, pairs_per_particle=150)
+        return scenes.dam_break(40, 40, 40, adaptive=True, grid=DAM_BREAK_GRID), dict(adaptive=True, pairs_per_particle=150)
     if name == "dam_break_262k":    # bounded sample of configs[1] for the CPU arm and the parity block: 64^3, the size of configs[0]
-        return scenes.dam_break(64, 64, 64, adaptive=True), dict(adaptive=True, pairs_per_particle=150)
+        return scenes.dam_break(64, 64, 64, adaptive=True, grid=DAM_BREAK_GRID), dict(adaptive=True, pairs_per_particle=150)
     if name == "uniform_64":        # configs[0]: uniform 64^3 block, fixed kernel width (jittered lattice)
         return scenes.uniform_block(64, jitter=0.1, shuffle=True, **rl), dict(adaptive=False, pairs_per_particle=40)
     if name == "uniform_32":
@@ -487,6 +489,7 @@ def run_gpu(args, rank, world, local_rank):
         "dtype": "f32+i32", "data": "synthetic",
         "config": {"workload": args.workload, "scene": sc.name, "particles_per_gpu": n, "adaptive_kernel_width": meta["adaptive"],
                    "solver_iterations": sc.solver_iterations, "search": args.search, "res_log2": sc.res_log2,
+                   "grid_cell": [round((h - l) / (1 << sc.res_log2), 3) for l, h in zip(sc.min_pos, sc.max_pos)],
                    "pairs_searched": stats["pairs_searched"], "pairs_kept": stats["pairs_kept"],
                    "pairs_unmirrored": stats["pairs_unmirrored"], "device_flags": r["flags"], "list_state": stats.get("list_state"),
                    "multi_gpu": "single" if world == 1 else "independent replicas",

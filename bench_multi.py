@@ -86,7 +86,7 @@ def n_rank_parity(gpu, torch, dist, rank, world, local_rank, make_scene, python_
     import bench
     half = {k: (v // 2 if k in ("nx", "ny", "nz") else v) for k, v in bench.SLAB_DAM_BREAK[world].items() if k != "res_log2"}
     out = {}
-    for name, sc, meta in ((f"dam_break_{world}x125k_adaptive", scenes.dam_break(adaptive=True, **half), dict(adaptive=True, pairs_per_particle=150)),
+    for name, sc, meta in ((f"dam_break_{world}x125k_adaptive", scenes.dam_break(adaptive=True, grid=bench.DAM_BREAK_GRID, **half), dict(adaptive=True, pairs_per_particle=150)),
                            ("uniform_48", scenes.uniform_block(48, jitter=0.1, shuffle=True), dict(adaptive=False, pairs_per_particle=40))):
         run = SlabRun(gpu, torch, sc, meta, rank, world, local_rank, python_loop, ghost_frac=1.5)
         for _ in range(3):
@@ -227,6 +227,7 @@ def run(args, rank, world, local_rank, peak, peak_src, emit, ClockSampler, make_
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
             "config": {"workload": args.workload, "scene": sc.name, "particles_per_gpu": n_local, "particles_total": int(sc.n),
                        "adaptive_kernel_width": meta["adaptive"], "solver_iterations": sc.solver_iterations, "search": "green", "res_log2": sc.res_log2,
+                       "grid_cell": [round((h - l) / (1 << sc.res_log2), 3) for l, h in zip(sc.min_pos, sc.max_pos)],
                        "pairs_searched": stats["pairs_searched"], "pairs_kept": stats["pairs_kept"], "pairs_unmirrored": stats["pairs_unmirrored"],
                        "device_flags": flags, "list_state": list_state, "multi_gpu": "one scene in bricks (top bits of the cell key), ghost particles, halo exchange every solver iteration",
                        "driver": driver, "slab": slab_stats,
