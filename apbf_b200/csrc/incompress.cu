@@ -57,7 +57,15 @@ struct sweep_args {
 	uint32_t*       out_incomp;
 	apbf_settings   s;
 	float           D;
+	int             t2_tail;        // apply sweep, equal-width form: 0 = store the shift, 1 = commit it + next prologue (box, pack), 2 = commit it
+	int             skip_if_t2_did; // prologue / commit launch: the apply sweep before was asked to do this work (t2_tail != 0)
 };
+
+// does the apply sweep run in its equal-width form (apply_delta_body<GK, false, true>)?  The same words k_apply_delta dispatches on.
+__device__ __forceinline__ bool t2_uniform_form(const sweep_args& A)
+{
+	return A.s.mGradientKernelId == 1 && A.misc[MW_N_ASYM] == 0u && A.misc[MW_H_NONUNIFORM] == 0u;
+}
 
 __device__ __forceinline__ float move_towards_abs(float oldValue, float newValue, float maxStep) // incompressibility_2.comp:37-41
 {
@@ -113,6 +121,7 @@ __global__ void k_prepare_consts(sweep_args A)
 template <bool COMMIT, bool BOX>
 __global__ void k_begin_iteration(sweep_args A)
 {
+	if (A.skip_if_t2_did && t2_uniform_form(A)) return; // the apply sweep before has committed, collided and packed already
 	const uint32_t n = *A.len;
 	const bool ident = A.misc[MW_IDENTITY] != 0u;
 	const bool has_asym = A.misc[MW_N_ASYM] != 0u;
@@ -509,7 +518,21 @@ __device__ __forceinline__ void apply_delta_body(const sweep_args& A, sweep_stag
 		if (a >= n_own) continue;
 		int4 d = A.delta[a]; // the particle's own shift from T1
 		d.x += my_sx; d.y += my_sy; d.z += my_sz;
-		A.delta[a] = d;
+		if (UNIFORM && A.t2_tail != 0) {
+			// the shift is complete (no pushes in this form): commit it, and run the next iteration's prologue for this particle
+			// (k_begin_iteration<true, true>, which returns at once when it sees that this form ran).  Nobody else reads P4[a]
+			// or the position in this sweep: neighbours are gathered from PL.
+			const uint32_t idx = A.misc[MW_IDENTITY] != 0u ? a : A.index_list[a];
+			int4 p = *((const int4*)A.pos4 + idx);
+			p.x += d.x; p.y += d.y; p.z += d.z;
+			if (A.t2_tail == 1) {
+				float px = (float)p.x * INV_R_POS, py = (float)p.y * INV_R_POS, pz = (float)p.z * INV_R_POS; // box_collision.comp:36-60
+				box_push(px, py, pz, a + A.misc[MW_GID_BASE], A.radius[idx], A.bmin, A.bmax, A.n_boxes);
+				p.x = f2i(px * R_POS); p.y = f2i(py * R_POS); p.z = f2i(pz * R_POS);
+				A.P4[a] = make_int4(p.x, p.y, p.z, A.P4[a].w);
+			}
+			*((int4*)A.pos4 + idx) = p;
+		} else A.delta[a] = d;
 		if (filter && my_hit) A.boundariness[a] = 0.0f;
 	}
 }
@@ -527,6 +550,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 4) k_apply_delta(sweep_args A)
 // position += delta (+ pushes); xyz only, w is the caller's
 __global__ void k_commit_delta(sweep_args A)
 {
+	if (A.skip_if_t2_did && t2_uniform_form(A)) return; // the apply sweep has committed already
 	const uint32_t n = min(*A.len, A.misc[MW_N_OWNED]);
 	const bool ident = A.misc[MW_IDENTITY] != 0u;
 	const bool has_asym = A.misc[MW_N_ASYM] != 0u;
@@ -651,6 +675,8 @@ int apbf_solver_iteration(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors
 	cudaStream_t st = ctx->stream;
 	const unsigned egrid = apbf_grid(ctx, n_cap, 256);
 	const bool run_all = (flags & (ITER_RUN_BEGIN | ITER_RUN_T1 | ITER_RUN_T2)) == 0;
+	A.skip_if_t2_did = (flags & ITER_SKIP_IF_T2_DID) ? 1 : 0;
+	A.t2_tail = (flags & ITER_T2_COMMIT) ? ((flags & ITER_T2_NEXT_BOX) ? 1 : 2) : 0;
 	if (run_all || (flags & ITER_RUN_BEGIN)) {
 		apbf_prof_scope ps(ctx, (flags & ITER_BEGIN_BOX) ? PROF_BOX : PROF_COMMIT);
 		const bool c = flags & ITER_BEGIN_COMMIT, b = flags & ITER_BEGIN_BOX;
@@ -687,6 +713,7 @@ int apbf_solver_iteration(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors
 	}
 	if (flags & ITER_END_COMMIT) {
 		apbf_prof_scope ps(ctx, PROF_COMMIT);
+		A.skip_if_t2_did = (flags & ITER_T2_COMMIT) ? 1 : 0; // (this call's own apply sweep)
 		k_commit_delta<<<egrid, 256, 0, st>>>(A);
 		APBF_LAUNCHED(ctx);
 	}
@@ -700,5 +727,5 @@ extern "C" int apbf_incompressibility_apply(apbf_ctx* ctx, apbf_fluid* fluid, co
 	APBF_REQUIRE(ctx, fluid && nb);
 	// a stand-alone call knows nothing about what changed since the last one: recompute the constants every time
 	APBF_TRY(apbf_solver_prepare(ctx, fluid));
-	return apbf_solver_iteration(ctx, fluid, nb, ITER_END_COMMIT, nullptr, nullptr, 0u, out_lambda, out_incomp_data);
+	return apbf_solver_iteration(ctx, fluid, nb, ITER_END_COMMIT | ITER_T2_COMMIT, nullptr, nullptr, 0u, out_lambda, out_incomp_data);
 }

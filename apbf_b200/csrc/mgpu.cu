@@ -516,10 +516,24 @@ int apbf_sim_mg_phase(apbf_sim* sim, int phase, int iteration)
 		}
 		case 2: return sim->mg_fused ? APBF_OK : apbf_spread_kernel_width_apply(ctx, &sim->fluid, &sim->nb, nullptr);
 		case 3: return apbf_solver_prepare(ctx, &sim->fluid);
-		case 4: return apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_BEGIN | ITER_BEGIN_BOX | (iteration > 0 ? ITER_BEGIN_COMMIT : 0), bmin, bmax, c.n_boxes, nullptr, nullptr);
+		// (phases 10 / 11: the apply sweep commits and runs the next prologue itself where it can -- solver.cuh, ITER_T2_COMMIT; the
+		// prologue / commit launch behind it is told to return at once in that case)
+		case 4: {
+			const int skip = sim->mg_t2_tail_pending && iteration > 0 ? ITER_SKIP_IF_T2_DID : 0;
+			sim->mg_t2_tail_pending = false;
+			return apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_BEGIN | ITER_BEGIN_BOX | (iteration > 0 ? ITER_BEGIN_COMMIT : 0) | skip, bmin, bmax, c.n_boxes, nullptr, nullptr);
+		}
 		case 5: return apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_T1, bmin, bmax, c.n_boxes, nullptr, nullptr);
 		case 6: return apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_T2, bmin, bmax, c.n_boxes, nullptr, nullptr);
-		case 7: return apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_BEGIN | ITER_BEGIN_COMMIT, nullptr, nullptr, 0u, nullptr, nullptr);
+		case 10: // apply sweep, another iteration follows     case 11: apply sweep of the last iteration
+		case 11:
+			sim->mg_t2_tail_pending = true;
+			return apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_T2 | ITER_T2_COMMIT | (phase == 10 ? ITER_T2_NEXT_BOX : 0), bmin, bmax, c.n_boxes, nullptr, nullptr);
+		case 7: {
+			const int skip = sim->mg_t2_tail_pending ? ITER_SKIP_IF_T2_DID : 0;
+			sim->mg_t2_tail_pending = false;
+			return apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_BEGIN | ITER_BEGIN_COMMIT | skip, nullptr, nullptr, 0u, nullptr, nullptr);
+		}
 		case 8: return apbf_kernel_width_from_boundary_distance(ctx, &sim->fluid); // pool.cpp:77-80 (owned particles; call before ROUTE)
 		case 9: return apbf_update_transfers_apply(ctx, &sim->fluid, &sim->nb, nullptr); // pool.cpp:99-102, after the ghosts' positions came in
 	}
@@ -675,7 +689,7 @@ int apbf_sim_mg_solve(apbf_sim* sim, const uint32_t* send_ids_dev, const uint32_
 		APBF_TRY(mg_exchange(sim, L, 2));
 		APBF_TRY(apbf_sim_mg_phase(sim, 5, it));
 		APBF_TRY(mg_exchange(sim, L, 3));
-		APBF_TRY(apbf_sim_mg_phase(sim, 6, it));
+		APBF_TRY(apbf_sim_mg_phase(sim, it + 1 < iterations ? 10 : 11, it));
 	}
 	return apbf_sim_mg_phase(sim, 7, 0);
 }
@@ -1089,7 +1103,8 @@ int mgl_refresh(apbf_sim* sim, int what)
 		src4 = (const uint32_t*)L4; stride4 = 4u;
 	} else if (what == 4) { src16 = dst16 = (int4*)f.particle.position.data; }
 	else return apbf_fail(ctx, APBF_ERR_INVALID, "what", __FILE__, __LINE__);
-	const unsigned grid = apbf_grid(ctx, total, 256);
+	// (at most two CTAs per SM: every CTA of a pack kernel ends with an atomic on one counter, and a message is a few hundred KB)
+	const unsigned grid = apbf_grid(ctx, total, 256, 2);
 	apbf_prof_scope ps(ctx, PROF_MG_EXCHANGE);
 	const mgl_sig S = mgl_begin_exchange(sim);
 	k_mgl_pack<<<grid, 256, 0, ctx->stream>>>(what, src4, src16, stride4, sim->mgl.send_ids, sim->mgl.words, C, send_bufs(sim, S), total, S);
@@ -1320,7 +1335,7 @@ int apbf_sim_mg_substep(apbf_sim* sim, uint32_t n_substeps)
 			APBF_TRY(route_plan_and_move(sim, M.words + MGL_ROUTE, false)); // perm = stable order by destination; counts on the device
 			const uint32_t* perm = (const uint32_t*)ctx->scratch_get(SLOT_TMP_VALS, sizeof(uint32_t) * (size_t)cap);
 			const mgl_sig SR = mgl_begin_exchange(sim);
-			k_mgl_pack_route<<<apbf_grid(ctx, (size_t)world * M.route_cap, 256), 256, 0, st>>>(lists_of(sim, false), perm, M.words, send_bufs(sim, SR), world, rank, M.route_cap, SR);
+			k_mgl_pack_route<<<apbf_grid(ctx, (size_t)world * M.route_cap, 256, 2), 256, 0, st>>>(lists_of(sim, false), perm, M.words, send_bufs(sim, SR), world, rank, M.route_cap, SR);
 			APBF_LAUNCHED(ctx);
 			APBF_TRY(mgl_exchange(sim, [&](int) { return 16 + (size_t)M.route_cap * STATE_INT4 * 16; }));
 			k_mgl_route_plan<<<1, 32, 0, st>>>(M.words, recv_bufs(sim, SR), world, rank, cap, SR);
@@ -1341,7 +1356,7 @@ int apbf_sim_mg_substep(apbf_sim* sim, uint32_t n_substeps)
 			const halo_lists hl{ (const int4*)f.particle.position.data, (const uint32_t*)f.particle.inverse_mass.data, (const uint32_t*)f.particle.radius.data,
 			                     (const uint32_t*)f.kernel_width.data, (const uint32_t*)f.target_radius.data, (const uint32_t*)f.boundary_distance.data };
 			const mgl_sig SH = mgl_begin_exchange(sim);
-			k_mgl_pack_halo<<<apbf_grid(ctx, M.halo_total, 256), 256, 0, st>>>(hl, M.words, M.send_ids, C, send_bufs(sim, SH), M.halo_total, SH);
+			k_mgl_pack_halo<<<apbf_grid(ctx, M.halo_total, 256, 2), 256, 0, st>>>(hl, M.words, M.send_ids, C, send_bufs(sim, SH), M.halo_total, SH);
 			APBF_LAUNCHED(ctx);
 			APBF_TRY(mgl_exchange(sim, [&](int r) { return 16 + (size_t)M.halo_cap[r] * HALO_INT4 * 16; }));
 			k_mgl_halo_plan<<<1, 32, 0, st>>>(M.words, recv_bufs(sim, SH), C, cap, f.particle.length, f.particle.hidden_length, misc, SH);
@@ -1371,7 +1386,7 @@ int apbf_sim_mg_substep(apbf_sim* sim, uint32_t n_substeps)
 			if (world > 1) APBF_TRY(mgl_refresh(sim, 2));
 			APBF_TRY(apbf_sim_mg_phase(sim, 5, it));
 			if (world > 1) APBF_TRY(mgl_refresh(sim, 3));
-			APBF_TRY(apbf_sim_mg_phase(sim, 6, it));
+			APBF_TRY(apbf_sim_mg_phase(sim, it + 1 < c.solver_iterations ? 10 : 11, it));
 		}
 		APBF_TRY(apbf_sim_mg_phase(sim, 7, 0));
 		if (c.update_transfers && !c.basic_pbf) {

@@ -222,7 +222,8 @@ int substep_once(apbf_sim* sim)
 		// box collision + the previous iteration's position update ride in the next iteration's prologue.
 		if (c.solver_iterations > 0) APBF_TRY(apbf_solver_prepare(ctx, &sim->fluid));
 		for (int it = 0; it < c.solver_iterations; it++) {
-			const int flags = ITER_BEGIN_BOX | (it > 0 ? ITER_BEGIN_COMMIT : 0) | (it == c.solver_iterations - 1 ? ITER_END_COMMIT : 0);
+			const bool last = it == c.solver_iterations - 1;
+			const int flags = ITER_BEGIN_BOX | (it > 0 ? ITER_BEGIN_COMMIT | ITER_SKIP_IF_T2_DID : 0) | (last ? ITER_END_COMMIT : ITER_T2_NEXT_BOX) | ITER_T2_COMMIT;
 			APBF_TRY(apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, flags, sim->boxes,
 			                               sim->boxes ? sim->boxes + 4 * (size_t)c.n_boxes : nullptr, c.n_boxes, nullptr, nullptr));
 		}

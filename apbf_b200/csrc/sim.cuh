@@ -58,6 +58,7 @@ struct apbf_sim {
 	float           last_dt;  // velocity_handling::mLastDeltaTime (velocity_handling.h:18)
 	bool            no_fuse;
 	bool            mg_fused = false; // slabs: the last search ran fused with spread_kernel_width
+	bool mg_t2_tail_pending = false; // apbf_sim_mg_phase: the last apply sweep was launched in its committing form (phases 10 / 11)
 	void*           nccl_comm = nullptr; // slabs: the library's own communicator (apbf_sim_mg_comm_init)
 	std::vector<void*> owned;
 	apbf_mg_state   mg;

@@ -7,7 +7,13 @@ enum apbf_iter_flags {
 	ITER_BEGIN_BOX = 2,    // box_collision fused into the prologue (pool.cpp:93)
 	ITER_END_COMMIT = 4,   // add this iteration's deltas to the positions before returning
 	// multi-GPU: run only part of the iteration (halo exchanges happen in between); none of the three set = all of them
-	ITER_RUN_BEGIN = 8, ITER_RUN_T1 = 16, ITER_RUN_T2 = 32
+	ITER_RUN_BEGIN = 8, ITER_RUN_T1 = 16, ITER_RUN_T2 = 32,
+	// The apply sweep may finish the iteration itself: in its equal-width form (one record per neighbour, nobody reads the
+	// packed positions of others) every lane ends up with its particle's complete shift, so it adds it to the position right
+	// away (ITER_T2_COMMIT) and, if another iteration follows, runs that iteration's box collision and packs the new position
+	// (ITER_T2_NEXT_BOX; pass the boxes).  Whether the sweep takes that form is decided on the device; the prologue / commit
+	// launch that would otherwise do the work is told with ITER_SKIP_IF_T2_DID to return at once in that case.
+	ITER_T2_COMMIT = 64, ITER_T2_NEXT_BOX = 128, ITER_SKIP_IF_T2_DID = 256
 };
 
 // per-particle constants that only depend on kernel width / radius / inverse mass (exact double-precision pow);

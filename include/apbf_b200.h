@@ -435,7 +435,8 @@ int  apbf_sim_mg_unpack(apbf_sim* sim, int what, const uint32_t* ids_dev, uint32
 /* after the search: slots before the sort -> ids after it (first != 0xFFFFFFFF: ids_dev[k] = first + k beforehand) */
 int  apbf_sim_mg_remap(apbf_sim* sim, uint32_t* ids_dev, uint32_t count, uint32_t first);
 /* phase: 0 integrate, 1 search, 2 spread_kernel_width, 3 solver constants, 4 iteration prologue, 5 density/lambda sweep,
- * 6 apply sweep, 7 final commit (pool.cpp:67-106 cut where the halo exchanges happen) */
+ * 6 apply sweep, 7 final commit (pool.cpp:67-106 cut where the halo exchanges happen); 10 / 11 = phase 6 in the form that also
+ * commits the shifts and (10) runs the next iteration's prologue where the list allows it -- phases 4 and 7 then return at once */
 int  apbf_sim_mg_phase(apbf_sim* sim, int phase, int iteration);
 /* The library's own NCCL communicator for the halo exchanges (libnccl.so.2 is bound at run time with dlopen; nothing links
  * against it).  Rank 0 creates the id, the caller distributes its 128 bytes, every rank of the node calls comm_init. */
