@@ -233,7 +233,7 @@ int apbf_sim_mg_enable(apbf_sim* sim, int rank, int world, float halo_range)
 	if (!sim) return APBF_ERR_INVALID;
 	apbf_ctx* ctx = sim->ctx;
 	APBF_REQUIRE(ctx, world == 1 || world == 2 || world == 4 || world == 8);
-	APBF_REQUIRE(ctx, rank >= 0 && rank < world && halo_range >= 0.0f && !sim->cfg.use_binary_search);
+	APBF_REQUIRE(ctx, rank >= 0 && rank < world && halo_range >= 0.0f);
 	const int dims = sim->cfg.dims;
 	const uint32_t res = sim->cfg.res_log2, cells = 1u << res;
 	int lw = 0;
@@ -500,7 +500,9 @@ int apbf_sim_mg_phase(apbf_sim* sim, int phase, int iteration)
 			sim->mg_fused = adaptive && !sim->no_fuse;
 			ctx->mg_ghost_all_pairs = adaptive && !sim->mg_fused;
 			// (the sweeps and a separate spread work on NB + offsets: no public pair list, write_public = false)
-			if (sim->mg_fused) // search + spread_kernel_width in one pass (pool.cpp:83-89), ghosts included
+			if (c.use_binary_search) // NEIGHBORHOOD_TYPE 3 over owned particles + ghosts (the bricks themselves are cells of the Green grid)
+				APBF_TRY(apbf_binary_search(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, sim->mg_fused ? 1.5f : (unit_scale ? 1.0f : 1.5f), nullptr, sim->mg_fused, nullptr, false));
+			else if (sim->mg_fused) // search + spread_kernel_width in one pass (pool.cpp:83-89), ghosts included
 				APBF_TRY(apbf_green_search(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, 1.5f, c.min_pos, c.max_pos, c.res_log2, nullptr, true, nullptr, false));
 			else
 				APBF_TRY(apbf_green_search(ctx, &sim->fluid, &sim->fluid.kernel_width, &sim->nb, unit_scale ? 1.0f : 1.5f, c.min_pos, c.max_pos, c.res_log2, nullptr, false, nullptr, false));
@@ -508,7 +510,7 @@ int apbf_sim_mg_phase(apbf_sim* sim, int phase, int iteration)
 			// old slot -> new id, for the send lists and the ghost slots (the search's sorted_index is still in scratch)
 			const uint32_t cap = c.particle_capacity;
 			uint32_t* inv = (uint32_t*)ctx->scratch_get(SLOT_MG_INV, sizeof(uint32_t) * (size_t)cap);
-			const uint32_t* sidx = (const uint32_t*)ctx->scratch_get(SLOT_TMP_VALS, sizeof(uint32_t) * (size_t)cap);
+			const uint32_t* sidx = (const uint32_t*)ctx->scratch_get(c.use_binary_search ? SLOT_SORT_VALS_A : SLOT_TMP_VALS, sizeof(uint32_t) * (size_t)cap);
 			if (!inv || !sidx) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
 			k_inverse_perm<<<apbf_grid(ctx, cap, 256), 256, 0, ctx->stream>>>(sidx, sim->fluid.particle.hidden_length, inv);
 			APBF_LAUNCHED(ctx);

@@ -617,9 +617,9 @@ __device__ __forceinline__ u96 or96(u96 a, u96 b) { return mk96(a.v[0] | b.v[0],
 __device__ __forceinline__ u96 not96(u96 a) { return mk96(~a.v[0], ~a.v[1], ~a.v[2]); }
 
 __device__ __forceinline__ uint32_t lower_bound96(const uint32_t* __restrict__ c0, const uint32_t* __restrict__ c1,
-                                                  const uint32_t* __restrict__ c2, uint32_t n, u96 code)
-{
-	uint32_t lo = 0u, hi = n;
+                                                  const uint32_t* __restrict__ c2, uint32_t n, u96 code, uint32_t from = 0u)
+{ // over the ids [from, n)
+	uint32_t lo = from, hi = n;
 	while (lo < hi) {
 		uint32_t mid = lo + ((hi - lo) >> 1);
 		if (greater96(code, mk96(__ldg(c0 + mid), __ldg(c1 + mid), __ldg(c2 + mid)))) lo = mid + 1u; else hi = mid;
@@ -628,9 +628,9 @@ __device__ __forceinline__ uint32_t lower_bound96(const uint32_t* __restrict__ c
 }
 
 __device__ __forceinline__ uint32_t upper_bound96(const uint32_t* __restrict__ c0, const uint32_t* __restrict__ c1,
-                                                  const uint32_t* __restrict__ c2, uint32_t n, u96 code)
-{ // first index whose code is greater than `code`
-	uint32_t lo = 0u, hi = n;
+                                                  const uint32_t* __restrict__ c2, uint32_t n, u96 code, uint32_t from = 0u)
+{ // first index in [from, n) whose code is greater than `code`
+	uint32_t lo = from, hi = n;
 	while (lo < hi) {
 		uint32_t mid = lo + ((hi - lo) >> 1);
 		if (greater96(mk96(__ldg(c0 + mid), __ldg(c1 + mid), __ldg(c2 + mid)), code)) hi = mid; else lo = mid + 1u;
@@ -684,6 +684,14 @@ __global__ void k_max_abs_coord(const uint32_t* __restrict__ index_list, const i
 	if ((am & ((1u << lane_id()) - 1u)) == 0u) atomicMax(misc + MW_PMAX, mx);
 }
 
+// slabs: 1 for the slots behind the owned particles (the ghosts), 0 otherwise -- the key of one more stable pass after the
+// three code sections, so that owned particles keep the dense ids [0, n_owned) and the ghosts follow, both in code order
+__global__ void k_ghost_key(const uint32_t* __restrict__ slots, const uint32_t* __restrict__ len, const uint32_t* __restrict__ misc, uint32_t* __restrict__ key)
+{
+	const uint32_t n = *len, n_owned = misc[MW_N_OWNED];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) key[i] = slots[i] >= n_owned ? 1u : 0u;
+}
+
 // binary search, per id: packed float position + threshold of "d <= range" (a NaN range rejects everything here), and a flag
 // where the particle's cell (level and centre) differs from its predecessor's: the stream emit takes runs of equal cells as
 // its chunks of queries
@@ -710,7 +718,7 @@ __global__ void k_build_bq(const uint32_t* __restrict__ index_list, const int32_
 			K.qb4[id] = prune_record(T, cut, orig, ip, pm);
 		}
 		uint32_t h = 1u;
-		if (id > 0u) {
+		if (id > 0u && id != misc[MW_N_OWNED]) { // (slabs: the ghosts sit behind the owned particles, in code order of their own; no run spans both)
 			const bs_cell a = bs_cell_of(ip, r);
 			const bs_cell b = bs_cell_of(ldg_int4(pos4, ident ? id - 1u : index_list[id - 1u]), range[id - 1u] * range_scale);
 			h = (a.center.v[0] != b.center.v[0] || a.center.v[1] != b.center.v[1] || a.center.v[2] != b.center.v[2] ||
@@ -1014,23 +1022,29 @@ k_green_stream(const emit_args A)
 					bool inside = true;
 #pragma unroll
 					for (int d = 0; d < DIMS; d++) inside = inside && umin[d] >= A.mg_lo[d] && umin[d] + ext[d] - 1u <= A.mg_hi[d];
+					if (SEARCH == 1) inside = false; // (no grid: the ghosts' code ranges are looked up for every chunk of owned queries)
 					if (ghost_run || inside) n_layers = 1u;
 				}
-				uint32_t bs_first = 0u, bs_cnt = 0u;
+				uint32_t bs_first = 0u, bs_cnt = 0u, bs_first_g = 0u, bs_cnt_g = 0u;
 				if (SEARCH == 1 && lane < 27u) {
 					// the 27 cells around the chunk's cell, in the reference's loop order (z outer, x inner), as ranges of the
 					// sorted codes: [first code >= cell, first code > cell | mask)
 					const bool ident = A.misc[MW_IDENTITY] != 0u;
 					const bs_cell c = bs_cell_of(ldg_int4(A.pos4, ident ? first : A.index_list[first]), A.range[first] * A.range_scale);
 					const u96 cell = bs_neighbor_cell(c, (int)(lane % 3u), (int)((lane / 3u) % 3u), (int)(lane / 9u));
-					bs_first = lower_bound96(A.c0, A.c1, A.c2, n, cell);
-					bs_cnt = upper_bound96(A.c0, A.c1, A.c2, n, or96(cell, c.mask)) - bs_first;
+					const uint32_t n_own = MG ? min(n_owned, n) : n; // slabs: owned ids [0, n_own) and ghost ids [n_own, n) are each in code order
+					bs_first = lower_bound96(A.c0, A.c1, A.c2, n_own, cell);
+					bs_cnt = upper_bound96(A.c0, A.c1, A.c2, n_own, or96(cell, c.mask)) - bs_first;
+					if (MG && n_layers == 2u) {
+						bs_first_g = lower_bound96(A.c0, A.c1, A.c2, n, cell, n_own);
+						bs_cnt_g = upper_bound96(A.c0, A.c1, A.c2, n, or96(cell, c.mask), n_own) - bs_first_g;
+					}
 				}
 				for (uint32_t cbase = 0; cbase < ncell * n_layers; cbase += 32) {
 					uint32_t ci = cbase + lane;
 					uint32_t c_first = 0u, c_cnt = 0u;
-					if (SEARCH == 1) {
-						c_first = bs_first; c_cnt = bs_cnt;
+					if (SEARCH == 1) { // first trip: the 27 ranges of owned ids; second trip (slabs): those of the ghosts
+						c_first = cbase == 0u ? bs_first : bs_first_g; c_cnt = cbase == 0u ? bs_cnt : bs_cnt_g;
 					} else if (ci < ncell * n_layers) {
 						const uint32_t table_off = ci >= ncell ? A.table_cells : 0u;
 						if (ci >= ncell) ci -= ncell;
@@ -1734,7 +1748,8 @@ int apbf_binary_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range
 	if (!ctx) return APBF_ERR_INVALID;
 	APBF_REQUIRE(ctx, fluid && range && nb);
 	APBF_REQUIRE(ctx, nb->pairs && nb->length && fluid->particle.length && fluid->particle.hidden_length);
-	APBF_REQUIRE(ctx, !ctx->mg_enabled); // slabs partition by the grid key of the Green search
+	// (slabs: ownership is a matter of the Green grid's key -- mgpu.cu -- whatever search runs over owned particles + ghosts)
+	const bool mg = ctx->mg_enabled;
 	APBF_TRY(apbf_nbr_activate(ctx, nb));
 	ctx->nbr_valid = false;
 	apbf_particles& p = fluid->particle;
@@ -1767,6 +1782,13 @@ int apbf_binary_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range
 			APBF_TRY(apbf_radix_sort_pairs(ctx, code, cur, scode, dst, p.hidden_length, nh_cap, 32));
 			cur = dst;
 		}
+		if (mg) { // owned first, ghosts behind them (idx_b = SLOT_SORT_VALS_A holds the final order)
+			k_ghost_key<<<apbf_grid(ctx, nh_cap, 256), 256, 0, st>>>(cur, p.hidden_length, misc, code);
+			APBF_LAUNCHED(ctx);
+			uint32_t* dst = ping[1];
+			APBF_TRY(apbf_radix_sort_pairs(ctx, code, cur, scode, dst, p.hidden_length, nh_cap, 1));
+			cur = dst;
+		}
 	}
 	const uint32_t* sidx = cur;
 	{
@@ -1782,7 +1804,7 @@ int apbf_binary_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range
 	APBF_LAUNCHED(ctx);
 	const unsigned grid = apbf_grid(ctx, n_cap, 128, 16);
 	static const int two_pass_env = getenv("APBF_TWO_PASS_EMIT") ? 1 : 0; // debugging aid: per-thread count/fill instead of stream/regroup
-	const int two_pass = two_pass_env && !fuse_kw;
+	const int two_pass = two_pass_env && !fuse_kw && !mg;
 	build_kw_args K;
 	memset(&K, 0, sizeof K);
 	uint32_t* kwfx = nullptr;
@@ -1822,13 +1844,17 @@ int apbf_binary_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range
 			emit_args A;
 			memset(&A, 0, sizeof A);
 			A.q4 = q4; A.key_id = key_id; A.range = new_range; A.len = p.length; A.range_scale = range_scale; A.counts = counts;
-			A.offsets = offsets; A.pairs = nb->pairs; A.nbl = nbl; A.cap = nb->capacity; A.misc = misc; A.table_cells = 1u; A.layers = 1u;
+			A.offsets = offsets; A.pairs = nb->pairs; A.nbl = nbl; A.cap = nb->capacity; A.misc = misc; A.table_cells = 1u;
+			A.layers = !mg ? 1u : (ctx->mg_ghost_all_pairs && !fuse_kw ? 3u : 2u);
 			A.g.ext[0] = A.g.ext[1] = A.g.ext[2] = 1.0f; A.g.scale = 1.0f; A.g.res = 1u; A.g.dims = 3; // (no grid in this search)
 			A.stream = stream; A.stream_blocks = stream_blocks; A.ticket = misc + MW_EMIT_TICKET0;
 			A.c0 = c[0]; A.c1 = c[1]; A.c2 = c[2]; A.pos4 = new_pos; A.index_list = new_index;
 			A.i4 = K.i4; A.cutoff = K.cutoff; A.qb4 = K.qb4; A.kwfx = kwfx;
 			const unsigned sgrid = apbf_grid(ctx, n_cap, EMIT_WARPS * 32, 4);
-			if (!fuse_kw) k_green_stream<EMIT_PLAIN, 3, false, 1><<<sgrid, EMIT_WARPS * 32, 0, st>>>(A);
+			if (mg && !fuse_kw) k_green_stream<EMIT_MG, 3, false, 1><<<sgrid, EMIT_WARPS * 32, 0, st>>>(A);
+			else if (mg && ctx->search_stats) k_green_stream<EMIT_FUSED_MG, 3, true, 1><<<sgrid, EMIT_WARPS * 32, 0, st>>>(A);
+			else if (mg) k_green_stream<EMIT_FUSED_MG, 3, false, 1><<<sgrid, EMIT_WARPS * 32, 0, st>>>(A);
+			else if (!fuse_kw) k_green_stream<EMIT_PLAIN, 3, false, 1><<<sgrid, EMIT_WARPS * 32, 0, st>>>(A);
 			else if (ctx->search_stats) k_green_stream<EMIT_FUSED, 3, true, 1><<<sgrid, EMIT_WARPS * 32, 0, st>>>(A);
 			else k_green_stream<EMIT_FUSED, 3, false, 1><<<sgrid, EMIT_WARPS * 32, 0, st>>>(A);
 			APBF_LAUNCHED(ctx);
@@ -1844,11 +1870,11 @@ int apbf_binary_search(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_array* range
 	{
 		apbf_prof_scope ps(ctx, PROF_EMIT_FILL);
 		if (!two_pass) {
-			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, nullptr, nbl, nb->capacity, misc, fuse_kw ? 1 : 0);
+			k_regroup<<<ctx->num_sms * 16, SB_ENTRIES, 0, st>>>(stream, stream_blocks, offsets, nullptr, nbl, nb->capacity, misc, fuse_kw || mg ? 1 : 0);
 			APBF_LAUNCHED(ctx);
 			if (write_public) APBF_TRY(apbf_launch_expand_pairs(ctx, offsets, nbl, p.length, n_cap, nb->pairs, nb->capacity));
 		}
-		if (!fuse_kw) { // (the fused form has no two-pass fill behind it: a stream overflow raises the sticky flag)
+		if (!fuse_kw && !mg) { // (the fused form and slabs have no two-pass fill behind them: a stream overflow raises the sticky flag)
 			k_bsearch_emit<true><<<grid, 128, 0, st>>>(new_index, new_pos, c[0], c[1], c[2], new_range, p.length, range_scale, nullptr,
 			                                           offsets, nb->pairs, nb->capacity, nbl, misc, two_pass ? 0 : 1);
 			APBF_LAUNCHED(ctx);

@@ -36,7 +36,7 @@ class SlabRun:
         self.ghost_cap = int(max(400_000 if self.n <= 1_200_000 else 0, 6.0 * side * side * layers * 1.3)) if ghost_frac is None else int(self.n * ghost_frac)
         self.capacity = int(self.n * 1.1) + self.ghost_cap
         self.sim = gpu.Sim(self.ctx, sc, capacity=self.capacity, neighbor_capacity=self.capacity * meta["pairs_per_particle"], integrate=True,
-                           basic_pbf=not meta["adaptive"])
+                           basic_pbf=not meta["adaptive"], use_binary_search=(meta.get("search") == "binary"))
         self.sim.upload(arrays, n=self.n)
         self.arrays = arrays
         if python_loop or not hasattr(multi_gpu, "LibraryDomain"):
@@ -126,6 +126,7 @@ def run(args, rank, world, local_rank, peak, peak_src, emit, ClockSampler, make_
     import apbf_b200 as gpu
 
     sc, meta = make_scene(args.workload, world, args.res_log2)
+    meta = dict(meta, search=args.search)   # --search binary: the reference's compiled default search over owned particles + ghosts
     if not meta.get("slab"):
         raise SystemExit(f"workload {args.workload} has no brick layout: use --replicas")
     run_ = SlabRun(gpu, torch, sc, meta, rank, world, local_rank, args.mg_python)
@@ -226,7 +227,7 @@ def run(args, rank, world, local_rank, peak, peak_src, emit, ClockSampler, make_
             "metric": METRIC, "value": sc.n * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
             "config": {"workload": args.workload, "scene": sc.name, "particles_per_gpu": n_local, "particles_total": int(sc.n),
-                       "adaptive_kernel_width": meta["adaptive"], "solver_iterations": sc.solver_iterations, "search": "green", "res_log2": sc.res_log2,
+                       "adaptive_kernel_width": meta["adaptive"], "solver_iterations": sc.solver_iterations, "search": args.search, "res_log2": sc.res_log2,
                        "grid_cell": [round((h - l) / (1 << sc.res_log2), 3) for l, h in zip(sc.min_pos, sc.max_pos)],
                        "pairs_searched": stats["pairs_searched"], "pairs_kept": stats["pairs_kept"], "pairs_unmirrored": stats["pairs_unmirrored"],
                        "device_flags": flags, "list_state": list_state, "multi_gpu": "one scene in bricks (top bits of the cell key), ghost particles, halo exchange every solver iteration",

@@ -415,7 +415,9 @@ int  apbf_sim_stats(apbf_sim* sim, uint32_t out[4]);
  * No reference counterpart (the reference is single-device); device side of the protocol described in
  * apbf_b200/csrc/mgpu.cu.  One apbf_sim per rank; the host moves the staging buffers between ranks (NCCL send/recv).
  * rank = top log2(world) bits of the particle's cell key (world in {1, 2, 4, 8}); halo_range = upper bound of
- * range_scale * kernel width over the whole scene. */
+ * range_scale * kernel width over the whole scene.  The bricks are cells of the Green grid (cfg.min_pos / max_pos / res_log2)
+ * whichever search the scene uses: with cfg.use_binary_search the owned particles and the ghosts are each sorted by their 96-bit
+ * code (one more stable pass keeps the owned ids dense) and a chunk's 27 code ranges are looked up in both. */
 int  apbf_sim_mg_enable(apbf_sim* sim, int rank, int world, float halo_range);
 int  apbf_sim_mg_brick(apbf_sim* sim, int rank, uint32_t out_lo[3], uint32_t out_hi[3], uint32_t out_halo[3]);
 /* list lengths = n_total (owned + ghosts), ids >= n_owned are ghosts, global id of local id 0 (box_collision hashes the id) */

@@ -9,15 +9,17 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _scene(adaptive, side):
+def _scene(adaptive, side, binary=False):
     from apbf_b200 import scenes
-    sc = scenes.waterdrop(side, jitter=0.1, wall_gap=6.0) if adaptive else scenes.uniform_block(side, jitter=0.2, shuffle=True, wall_gap=0.0)
+    # (binary search: a particle's id is its rank in Morton-code order, which one GPU and a brick number differently, and the wall
+    # jitter of box_collision.comp:46-47 hashes the id -- those cases keep the particles out of wall contact)
+    sc = scenes.waterdrop(side, jitter=0.1, wall_gap=6.0) if adaptive else scenes.uniform_block(side, jitter=0.2, shuffle=True, wall_gap=6.0 if binary else 0.0)
     sc.arrays["position"][:, 3] = np.arange(sc.n, dtype=np.int32)
     sc.arrays["pos_backup"][:, :3] -= np.array([6000000, 7200000, 9000000], np.int32)  # velocity_handling starts with mLastDeltaTime = 1 (velocity_handling.h:18)
     return sc
 
 
-def _worker(rank, world, port, adaptive, side, steps, out_dir, default_mode=False, library=False, transport=None):
+def _worker(rank, world, port, adaptive, side, steps, out_dir, default_mode=False, library=False, transport=None, binary=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     import torch
@@ -26,7 +28,7 @@ def _worker(rank, world, port, adaptive, side, steps, out_dir, default_mode=Fals
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import apbf_b200
     from apbf_b200 import multi_gpu
-    sc = _scene(adaptive or default_mode, side)
+    sc = _scene(adaptive or default_mode, side, binary)
     owner = multi_gpu.owner_rank_of_positions(sc.arrays["position"], sc.min_pos, sc.max_pos, sc.res_log2, sc.dims, world)
     mine = {k: np.ascontiguousarray(v[owner == rank]) for k, v in sc.arrays.items()}
     n_own = len(mine["position"])
@@ -35,7 +37,7 @@ def _worker(rank, world, port, adaptive, side, steps, out_dir, default_mode=Fals
     ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if adaptive else 1, mSmallestTargetRadius=sc.smallest_target_radius)
     cap = sc.n                      # room for every particle plus ghosts on one rank
     sim = apbf_b200.Sim(ctx, sc, capacity=cap, neighbor_capacity=cap * (700 if adaptive or default_mode else 80), integrate=True,
-                        basic_pbf=not (adaptive or default_mode), update_transfers=default_mode)
+                        basic_pbf=not (adaptive or default_mode), update_transfers=default_mode, use_binary_search=binary)
     sim.upload(mine, n=n_own)
     halo_range = float(sc.arrays["kernel_width"].max()) * (1.5 if adaptive else 1.0) * 1.05
     if library:   # the whole substep inside the library: apbf_sim_mg_substep
@@ -60,9 +62,17 @@ def _worker(rank, world, port, adaptive, side, steps, out_dir, default_mode=Fals
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("adaptive,side", [(False, 24), (True, 20)])
+def test_n_rank_equals_one_rank_binary_search(tmp_path, adaptive, side):
+    """the reference's compiled default search (NEIGHBORHOOD_TYPE 3, neighborhood_binary_search.cpp:22-75) over owned particles +
+    ghosts: fixed widths, and adaptive widths (search fused with spread_kernel_width); library loop, peer-to-peer transport"""
+    test_n_rank_equals_one_rank(tmp_path, adaptive, side, False, "library_p2p", binary=True)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("driver", ["python", "library_p2p", "library_nccl"])
 @pytest.mark.parametrize("adaptive,side,default_mode", [(False, 24, False), (True, 20, False), (False, 20, True)])
-def test_n_rank_equals_one_rank(tmp_path, adaptive, side, default_mode, driver):
+def test_n_rank_equals_one_rank(tmp_path, adaptive, side, default_mode, driver, binary=False):
     """driver: the protocol exchange by exchange from Python over torch.distributed; the library's own loop (apbf_sim_mg_substep) with
     the peer-to-peer transport (pack kernels store into the receiver's buffer over NVLink, flags instead of NCCL); the same loop over
     grouped ncclSend / ncclRecv"""
@@ -76,12 +86,12 @@ def test_n_rank_equals_one_rank(tmp_path, adaptive, side, default_mode, driver):
     world = 4 if torch.cuda.device_count() >= 4 else 2
     steps = 3
     port = 29500 + (os.getpid() % 1000) + int(adaptive) + 2 * int(default_mode) + 4 * ["python", "library_p2p", "library_nccl"].index(driver)
-    mp.spawn(_worker, args=(world, port, adaptive, side, steps, str(tmp_path), default_mode, library, transport), nprocs=world, join=True)
-    sc = _scene(adaptive or default_mode, side)
+    mp.spawn(_worker, args=(world, port + (16 if binary else 0), adaptive, side, steps, str(tmp_path), default_mode, library, transport, binary), nprocs=world, join=True)
+    sc = _scene(adaptive or default_mode, side, binary)
     ctx = apbf_b200.Context(dims=sc.dims)
     ctx.set_settings(mBaseKernelWidthOnBoundaryDistance=0 if adaptive else 1, mSmallestTargetRadius=sc.smallest_target_radius)
     sim = apbf_b200.Sim(ctx, sc, neighbor_capacity=sc.n * (700 if adaptive or default_mode else 80), integrate=True,
-                        basic_pbf=not (adaptive or default_mode), update_transfers=default_mode)
+                        basic_pbf=not (adaptive or default_mode), update_transfers=default_mode, use_binary_search=binary)
     sim.upload(sc.arrays)
     sim.substep(steps)
     exp = apbf_b200.empty_host_arrays(sc.n)
