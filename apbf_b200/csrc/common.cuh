@@ -23,7 +23,7 @@ enum apbf_scratch_slot {
 	SLOT_PAIRS_TMP, SLOT_NB_TMP, SLOT_BOXES, SLOT_HIDDEN_FLAGS, SLOT_HIDDEN_OFFS, SLOT_IDENTITY, SLOT_COM4, SLOT_KG, SLOT_KH, SLOT_Q4, SLOT_KEY_ID, SLOT_EDIT_COUNTS, SLOT_EDIT_OFFSETS, SLOT_MG_INV, SLOT_I4, SLOT_CUTOFF, SLOT_QB4, SLOT_STREAM, SLOT_TILE_FIRST, SLOT_TILE_TOTAL, SLOT_OLD_BOUNDARY_DIST, SLOT_CELL_MAXW, SLOT_MG_SEND, SLOT_MG_RECV,
 	SLOT_TM_NEAREST, SLOT_TM_FLAGS, SLOT_TM_OFFS, SLOT_TM_SRC, SLOT_TM_TGT, SLOT_TM_CID, SLOT_TM_CSRC, SLOT_TM_CTGT, SLOT_TM_STATE, SLOT_TM_RANK,
 	SLOT_TM_OWNER, SLOT_TM_WORDS, SLOT_TM_KEEP_H, SLOT_TM_OFFS_H, SLOT_TM_PERM_H, SLOT_TM_KEEP_I, SLOT_TM_OFFS_I, SLOT_TM_PERM_I, SLOT_TM_KEEP_R,
-	SLOT_TM_OFFS_R, SLOT_TM_PERM_R, SLOT_KP, SLOT_PL,
+	SLOT_TM_OFFS_R, SLOT_TM_PERM_R, SLOT_KP, SLOT_PL, SLOT_MG_TILES,
 	SLOT_COUNT
 };
 

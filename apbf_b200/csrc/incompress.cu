@@ -57,6 +57,8 @@ struct sweep_args {
 	uint32_t*       out_incomp;
 	apbf_settings   s;
 	float           D;
+	const uint32_t* tile_flags;     // slabs: 1 per boundary tile (see ITER_TILES_*)
+	int             tile_filter;    // 0 = every tile, 1 = interior tiles only, 2 = boundary tiles only
 	int             t2_tail;        // apply sweep, equal-width form: 0 = store the shift, 1 = commit it + next prologue (box, pack), 2 = commit it
 	int             skip_if_t2_did; // prologue / commit launch: the apply sweep before was asked to do this work (t2_tail != 0)
 };
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, (HK == 1 && GK == 1 && !COM) ? 
 	const uint32_t warps_per_grid = gridDim.x * (SWEEP_THREADS / 32);
 	for (uint32_t tile = blockIdx.x * (SWEEP_THREADS / 32) + (threadIdx.x >> 5); (size_t)tile * 32 < n; tile += warps_per_grid) {
 		const uint32_t base = tile * 32u;
+		if (A.tile_filter != 0 && (A.tile_flags[tile] != 0u || base + 31u >= n) != (A.tile_filter == 2)) continue;
 		int my_dens = 0, my_sq = 0, my_gx = 0, my_gy = 0, my_gz = 0, my_cx = 0, my_cy = 0, my_cz = 0, my_cw = 0;
 #pragma unroll 1
 		for (int r = 0; r < ROUNDS; r++) { // round r: group g sweeps particle base + PPR r + g
@@ -463,6 +466,7 @@ __device__ __forceinline__ void apply_delta_body(const sweep_args& A, sweep_stag
 	const uint32_t n_walk = ASYM ? n : n_own;
 	for (uint32_t tile = blockIdx.x * (SWEEP_THREADS / 32) + (threadIdx.x >> 5); (size_t)tile * 32 < n_walk; tile += warps_per_grid) {
 		const uint32_t base = tile * 32u;
+		if (A.tile_filter != 0 && (A.tile_flags[tile] != 0u || base + 31u >= n_own) != (A.tile_filter == 2)) continue;
 		int my_sx = 0, my_sy = 0, my_sz = 0, my_hit = 0;
 #pragma unroll 1
 		for (int r = 0; r < ROUNDS; r++) {
@@ -675,6 +679,11 @@ int apbf_solver_iteration(apbf_ctx* ctx, apbf_fluid* fluid, const apbf_neighbors
 	cudaStream_t st = ctx->stream;
 	const unsigned egrid = apbf_grid(ctx, n_cap, 256);
 	const bool run_all = (flags & (ITER_RUN_BEGIN | ITER_RUN_T1 | ITER_RUN_T2)) == 0;
+	if (flags & (ITER_TILES_INTERIOR | ITER_TILES_BOUNDARY)) {
+		A.tile_filter = (flags & ITER_TILES_BOUNDARY) ? 2 : 1;
+		A.tile_flags = (const uint32_t*)ctx->scratch_get(SLOT_MG_TILES, sizeof(uint32_t) * ((size_t)n_cap / 32u + 2u));
+		if (!A.tile_flags) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+	}
 	A.skip_if_t2_did = (flags & ITER_SKIP_IF_T2_DID) ? 1 : 0;
 	A.t2_tail = (flags & ITER_T2_COMMIT) ? ((flags & ITER_T2_NEXT_BOX) ? 1 : 2) : 0;
 	if (run_all || (flags & ITER_RUN_BEGIN)) {

@@ -752,14 +752,16 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
 	return v;
 }
 
-// tail of a pack kernel (every thread of every CTA gets here): the thread's stores into the peers' buffers are fenced at system
-// scope, the CTA that finishes last raises the flags
+// tail of a pack kernel (every thread of every CTA gets here): the CTA's stores into the peers' buffers are ordered before thread
+// 0 by the barrier and made visible at system scope by ITS fence (cumulativity: one MEMBAR.SYS per CTA); the CTA that finishes last
+// raises the flags.  Measured (profiles/r02_variants.md, 2 GPUs, 49 000 ghosts each way): a pack kernel takes 19 us, 5 of them the
+// fence, ~0 the counter, and the same whether a message is 0.2 or 0.8 MB; the unpack kernel with its wait 5.6 us.
 __device__ __forceinline__ void mgl_signal(const mgl_sig& S)
 {
 	if (!S.on) return;
-	__threadfence_system();
 	__syncthreads();
 	if (threadIdx.x == 0) {
+		__threadfence_system();
 		if (atomicAdd(S.done, 1u) == gridDim.x - 1u) {
 			atomicExch(S.done, 0u);
 			__threadfence_system();
@@ -966,12 +968,17 @@ __global__ void k_mgl_unpack_halo(halo_lists_out L, const uint32_t* __restrict__
 }
 
 // slots before the search's sort -> ids after it, for the send lists (which = MGL_HALO_SEND) or the ghost slots (MGL_HALO_RECV)
-__global__ void k_mgl_remap(uint32_t* __restrict__ ids, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ words, int which, mgl_caps C, uint32_t total)
+// tiles: (send lists only) flags the tile of 32 consecutive ids each sent particle is in -- an owned particle can only have a ghost
+// neighbour if it is some other rank's ghost itself (the halo is as wide on both sides of a face), so these are the BOUNDARY tiles
+// of the sweeps and every other tile of owned particles works without the halo exchange that is in flight
+__global__ void k_mgl_remap(uint32_t* __restrict__ ids, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ words, int which, mgl_caps C, uint32_t total,
+                            uint32_t* __restrict__ tiles)
 {
 	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
 		int r = 0;
 		while (r + 1 < C.world && t >= C.off[r + 1]) r++;
 		if (r == C.rank || t - C.off[r] >= words[which + r]) continue;
+		if (tiles) tiles[inv[ids[t]] >> 5] = 1u;
 		ids[t] = inv[ids[t]];
 	}
 }
@@ -1084,7 +1091,10 @@ int mgl_exchange(apbf_sim* sim, F bytes_of)
 	return APBF_OK;
 }
 
-int mgl_refresh(apbf_sim* sim, int what)
+// one quantity of the owners to their ghosts elsewhere, in two halves: send = pack kernel (stores into the peers' buffers and raises
+// their flags; NCCL transport: into the send buffers), recv = [NCCL group] + unpack kernel (waits for the peers' flags).  Whatever is
+// enqueued between the two runs while the messages travel.
+int mgl_refresh_part(apbf_sim* sim, int what, bool send, bool recv, mgl_sig& S)
 {
 	apbf_ctx* ctx = sim->ctx;
 	const mgl_caps C = caps_of(sim);
@@ -1108,14 +1118,24 @@ int mgl_refresh(apbf_sim* sim, int what)
 	// (at most two CTAs per SM: every CTA of a pack kernel ends with an atomic on one counter, and a message is a few hundred KB)
 	const unsigned grid = apbf_grid(ctx, total, 256, 2);
 	apbf_prof_scope ps(ctx, PROF_MG_EXCHANGE);
-	const mgl_sig S = mgl_begin_exchange(sim);
-	k_mgl_pack<<<grid, 256, 0, ctx->stream>>>(what, src4, src16, stride4, sim->mgl.send_ids, sim->mgl.words, C, send_bufs(sim, S), total, S);
-	APBF_LAUNCHED(ctx);
-	const size_t elem = (what == 2 || what == 4) ? 16u : 4u;
-	APBF_TRY(mgl_exchange(sim, [&](int r) { return elem * (size_t)sim->mgl.halo_cap[r]; }));
-	k_mgl_unpack<<<grid, 256, 0, ctx->stream>>>(what, dst4, dst16, L4, KG, P4, PL, sim->mgl.ghost_ids, sim->mgl.words, C, recv_bufs(sim, S), total, S);
-	APBF_LAUNCHED(ctx);
+	if (send) {
+		S = mgl_begin_exchange(sim);
+		k_mgl_pack<<<grid, 256, 0, ctx->stream>>>(what, src4, src16, stride4, sim->mgl.send_ids, sim->mgl.words, C, send_bufs(sim, S), total, S);
+		APBF_LAUNCHED(ctx);
+	}
+	if (recv) {
+		const size_t elem = (what == 2 || what == 4) ? 16u : 4u;
+		APBF_TRY(mgl_exchange(sim, [&](int r) { return elem * (size_t)sim->mgl.halo_cap[r]; }));
+		k_mgl_unpack<<<grid, 256, 0, ctx->stream>>>(what, dst4, dst16, L4, KG, P4, PL, sim->mgl.ghost_ids, sim->mgl.words, C, recv_bufs(sim, S), total, S);
+		APBF_LAUNCHED(ctx);
+	}
 	return APBF_OK;
+}
+
+int mgl_refresh(apbf_sim* sim, int what)
+{
+	mgl_sig S;
+	return mgl_refresh_part(sim, what, true, true, S);
 }
 
 mg_boxes grown_boxes(const apbf_sim* sim)
@@ -1373,9 +1393,12 @@ int apbf_sim_mg_substep(apbf_sim* sim, uint32_t n_substeps)
 		if (world > 1 && M.halo_total > 0u) {
 			const uint32_t* inv = (const uint32_t*)ctx->scratch_get(SLOT_MG_INV, sizeof(uint32_t) * (size_t)cap);
 			if (!inv) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
-			k_mgl_remap<<<apbf_grid(ctx, M.halo_total, 256), 256, 0, st>>>(M.send_ids, inv, M.words, MGL_HALO_SEND, C, M.halo_total);
+			uint32_t* tiles = (uint32_t*)ctx->scratch_get(SLOT_MG_TILES, sizeof(uint32_t) * ((size_t)cap / 32u + 2u));
+			if (!tiles) return apbf_fail(ctx, APBF_ERR_OOM, "scratch", __FILE__, __LINE__);
+			APBF_CUDA(ctx, cudaMemsetAsync(tiles, 0, sizeof(uint32_t) * ((size_t)cap / 32u + 2u), st));
+			k_mgl_remap<<<apbf_grid(ctx, M.halo_total, 256), 256, 0, st>>>(M.send_ids, inv, M.words, MGL_HALO_SEND, C, M.halo_total, tiles);
 			APBF_LAUNCHED(ctx);
-			k_mgl_remap<<<apbf_grid(ctx, M.halo_total, 256), 256, 0, st>>>(M.ghost_ids, inv, M.words, MGL_HALO_RECV, C, M.halo_total);
+			k_mgl_remap<<<apbf_grid(ctx, M.halo_total, 256), 256, 0, st>>>(M.ghost_ids, inv, M.words, MGL_HALO_RECV, C, M.halo_total, nullptr);
 			APBF_LAUNCHED(ctx);
 		}
 		if (adaptive) {
@@ -1383,12 +1406,36 @@ int apbf_sim_mg_substep(apbf_sim* sim, uint32_t n_substeps)
 			if (world > 1) APBF_TRY(mgl_refresh(sim, 1)); // the owners' new widths overwrite the ghosts'
 		}
 		APBF_TRY(apbf_sim_mg_phase(sim, 3, 0));
+		// Every iteration needs two exchanges -- the owners' packed positions before the density sweep, their lambdas before the apply
+		// sweep -- and each costs a round trip between the GPUs.  Both hide behind work that does not need them: the sweeps run over the
+		// INTERIOR tiles (no particle of theirs can have a ghost neighbour, k_mgl_remap) while the messages travel and over the BOUNDARY
+		// tiles after the unpack kernel has seen the peers' flags.  OFF by default (APBF_MG_OVERLAP=1 turns it on): at 10^6 particles per
+		// GPU the two extra launches per sweep cost more (+27 us each) than the wait they hide -- an exchange is 19 us of pack kernel and
+		// 5.6 us of unpack kernel, its wait included, so there is hardly any wait to hide (2.43 ms without, 2.61 ms with, 2 GPUs).
+		static const bool overlap = getenv("APBF_MG_OVERLAP") != nullptr && atoi(getenv("APBF_MG_OVERLAP")) != 0;
+		const float* bmin = sim->boxes;
+		const float* bmax = sim->boxes ? sim->boxes + 4 * (size_t)c.n_boxes : nullptr;
 		for (int it = 0; it < c.solver_iterations; it++) {
+			const bool last = it + 1 == c.solver_iterations;
 			APBF_TRY(apbf_sim_mg_phase(sim, 4, it));
+			if (world > 1 && M.halo_total > 0u && overlap) {
+				const int t2 = ITER_RUN_T2 | ITER_T2_COMMIT | (last ? 0 : ITER_T2_NEXT_BOX);
+				mgl_sig S;
+				APBF_TRY(mgl_refresh_part(sim, 2, true, false, S));
+				APBF_TRY(apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_T1 | ITER_TILES_INTERIOR, bmin, bmax, c.n_boxes, nullptr, nullptr));
+				APBF_TRY(mgl_refresh_part(sim, 2, false, true, S));
+				APBF_TRY(apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, ITER_RUN_T1 | ITER_TILES_BOUNDARY, bmin, bmax, c.n_boxes, nullptr, nullptr));
+				APBF_TRY(mgl_refresh_part(sim, 3, true, false, S));
+				APBF_TRY(apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, t2 | ITER_TILES_INTERIOR, bmin, bmax, c.n_boxes, nullptr, nullptr));
+				APBF_TRY(mgl_refresh_part(sim, 3, false, true, S));
+				APBF_TRY(apbf_solver_iteration(ctx, &sim->fluid, &sim->nb, t2 | ITER_TILES_BOUNDARY, bmin, bmax, c.n_boxes, nullptr, nullptr));
+				sim->mg_t2_tail_pending = true;
+				continue;
+			}
 			if (world > 1) APBF_TRY(mgl_refresh(sim, 2));
 			APBF_TRY(apbf_sim_mg_phase(sim, 5, it));
 			if (world > 1) APBF_TRY(mgl_refresh(sim, 3));
-			APBF_TRY(apbf_sim_mg_phase(sim, it + 1 < c.solver_iterations ? 10 : 11, it));
+			APBF_TRY(apbf_sim_mg_phase(sim, last ? 11 : 10, it));
 		}
 		APBF_TRY(apbf_sim_mg_phase(sim, 7, 0));
 		if (c.update_transfers && !c.basic_pbf) {

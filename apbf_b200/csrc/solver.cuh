@@ -13,7 +13,11 @@ enum apbf_iter_flags {
 	// away (ITER_T2_COMMIT) and, if another iteration follows, runs that iteration's box collision and packs the new position
 	// (ITER_T2_NEXT_BOX; pass the boxes).  Whether the sweep takes that form is decided on the device; the prologue / commit
 	// launch that would otherwise do the work is told with ITER_SKIP_IF_T2_DID to return at once in that case.
-	ITER_T2_COMMIT = 64, ITER_T2_NEXT_BOX = 128, ITER_SKIP_IF_T2_DID = 256
+	ITER_T2_COMMIT = 64, ITER_T2_NEXT_BOX = 128, ITER_SKIP_IF_T2_DID = 256,
+	// slabs: a sweep over part of the tiles (32 consecutive particles each).  BOUNDARY = tiles that hold a particle some other rank has
+	// as a ghost -- the only owned particles that can have ghost neighbours -- or a ghost; INTERIOR = the rest, which needs nothing
+	// from the halo exchange that is in flight (mgpu.cu: the exchanges hide behind the interior sweeps).  Flags: SLOT_MG_TILES.
+	ITER_TILES_INTERIOR = 512, ITER_TILES_BOUNDARY = 1024
 };
 
 // per-particle constants that only depend on kernel width / radius / inverse mass (exact double-precision pow);

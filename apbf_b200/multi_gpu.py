@@ -454,6 +454,7 @@ class LibraryDomain:
         self._ck(self.lib.apbf_sim_mg_loop_init(sim.handle, int(n_owned), self.route_cap, caps))
         self.ghost_capacity = int(ghost_capacity)
         self.transport = "nccl"
+        self.transport_note = ""
         if world > 1 and transport == "p2p":
             # every rank describes its receive buffers (CUDA IPC handle + offsets); the table of all ranks goes back into the library
             blob_bytes = 512  # APBF_MG_P2P_BLOB_BYTES
@@ -463,6 +464,8 @@ class LibraryDomain:
             dist.all_gather(allb, blob.to(dev))
             table = torch.cat([b.cpu() for b in allb]).contiguous()
             rc = self.lib.apbf_sim_mg_p2p_import(sim.handle, table.data_ptr())
+            if rc != 0:   # (kept for the bench line: why this scene fell back to NCCL)
+                self.transport_note = self.lib.apbf_ctx_last_error(self.ctx.handle).decode(errors="replace")
             ok = torch.tensor([1 if rc == 0 else 0, -(1 if rc == 0 else 0)], dtype=torch.int64, device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # [min, -max]: all ranks or none, the two transports do not mix
             if int(ok[0].item()) == 1:
@@ -493,4 +496,4 @@ class LibraryDomain:
         if w[4]:
             raise RuntimeError(f"slab loop capacity exceeded (flags {w[4]}: 1 migration buffer, 2 ghost list, 4 particle capacity)")
         return dict(owned=w[0], ghosts=w[1] - w[0], gid_base=w[2], migrated=w[3], exchanges=w[5], route_cap=self.route_cap,
-                    halo_caps=self.halo_caps[: self.world], transport=self.transport)
+                    halo_caps=self.halo_caps[: self.world], transport=self.transport, **({"transport_note": self.transport_note} if self.transport_note else {}))
