@@ -261,6 +261,9 @@ def dam_break(nx=100, ny=100, nz=100, r=1.0, jitter=0.05, seed=99, adaptive=True
         half = 0.5 * max(h - l for l, h in zip(lo, hi))
         mid = [0.5 * (l + h) for l, h in zip(lo, hi)]
         lo = [m - half for m in mid]; hi = [m + half for m in mid]
+    if res_log2 is None and grid == "cube":
+        # cubic cells: the resolution whose cell edge is closest to 1.1 kernel widths (4.8 r at 620 r, 3.2 r rather than 6.4 r at 820 r)
+        res_log2 = _res_near(max(h - l for l, h in zip(lo, hi)), 4.4 * r)
     if res_log2 is None:
         # per-axis grid bounds (cells need not be cubes); resolution so that the widest cell is about 0.75 x search range
         res_log2 = _res_for(max(h - l for l, h in zip(lo, hi)), 4.5 * r)

@@ -98,7 +98,9 @@ int  apbf_ctx_set_match_grid_min(apbf_ctx* ctx, uint32_t min_candidates);
  * synchronises with the recorded events. */
 int  apbf_ctx_profile(apbf_ctx* ctx, int enable);
 int  apbf_ctx_profile_read(apbf_ctx* ctx, int category, const char** out_name, double* out_ms, uint64_t* out_calls);
-/* sticky device-side status word: bit 0 = neighbour list overflow (neighbor_add.glsl:23-24 clamp hit). Synchronises. */
+/* sticky device-side status word: bit 0 = neighbour list overflow (neighbor_add.glsl:23-24 clamp hit); bit 2 = a search box was
+ * at least as wide as the whole grid on some axis: the reference walks aliased cells twice there and lists those pairs twice
+ * (neighborhood_green.comp:69-79), this library lists every pair once.  Synchronises. */
 int  apbf_ctx_device_flags(apbf_ctx* ctx, uint32_t* out_flags);
 /* which form of the passes the lists of the last search / solver iteration selected on the device (diagnostics; no counterpart in
  * the reference; synchronises): out[0] = pairs without a mirrored pair in the list, out[1] = 1 if every particle has the same
