@@ -228,8 +228,9 @@ def cpu_baseline_and_parity(gpu, workload, search):
     sub0 = parity.substep_parity(gpu, sc, adaptive=meta["adaptive"], substeps=2, search=search, pairs_per_particle=meta["pairs_per_particle"], threads=threads,
                                  hk=0, gk=0)
     par = {"sample": f"{sample}: {sc.n} particles, same workload", "checker": "oracle/apbf_oracle.c (CPU restatement of the shaders; parity unpinned for the physics passes)",
-           "bars": "bit-exact: keys, order, cell tables, lists, pair list in order, kernel widths; accumulators 1 unit of 2^-18 + 1e-5 rel; "
-                   "lambda 1e-5 rel where the accumulators agree; position shift of one iteration 8 units + 5e-5 of the largest shift",
+           "bars": f"bit-exact: keys, order, cell tables, lists, pair list in order, kernel widths; accumulators {parity.ACC_UNITS} units of 2^-18 + 1e-5 rel; "
+                   f"lambda 1e-5 rel where the accumulators agree; position shift of one iteration {parity.SHIFT_UNITS} units + {parity.SHIFT_REL:g} of the largest shift "
+                   "(oracle/parity.py, BASELINE.md section 3)",
            "ok": bool(ops["ok"] and sub["ok"] and sub0["ok"]),
            "one_iteration_operator_by_operator": ops, "whole_substeps_gauss": sub, "whole_substeps_cubic": sub0}
     return base, par

@@ -13,19 +13,41 @@ import bench  # noqa: E402
 from apbf_b200 import multi_gpu, scenes  # noqa: E402
 
 
+@pytest.mark.parametrize("grid", ["pool", "cube"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_slab_dam_break_is_balanced(world):
+def test_slab_dam_break_is_balanced(world, grid):
     """same construction as bench.SLAB_DAM_BREAK at a tenth of the edge length: every brick owns the same number of particles
-    (the bricks are the halves of the grid along z, then y, then x: the top bits of the cell key)"""
+    (the bricks are the halves of the grid along z, then y, then x: the top bits of the cell key), with the pool-hugging grid and
+    with the equal-extent grid bench.py times (every axis keeps its centre, so the cuts stay where they were)"""
     args = dict(bench.SLAB_DAM_BREAK[world])
     for k in ("nx", "ny", "nz"):
         args[k] //= 5
     args.pop("res_log2", None)
-    sc = scenes.dam_break(adaptive=True, **args)
+    sc = scenes.dam_break(adaptive=True, grid=grid, **args)
     owner = multi_gpu.owner_rank_of_positions(sc.arrays["position"], sc.min_pos, sc.max_pos, sc.res_log2, sc.dims, world)
     counts = np.bincount(owner, minlength=world)
     assert counts.sum() == sc.n and counts.min() > 0
     assert counts.max() - counts.min() <= 0.02 * sc.n / world, counts
+
+
+def test_timed_dam_break_searches_on_cubic_cells():
+    """bench.py's dam breaks: equal extents on all axes around the same centres as the pool-hugging grid, cell edge within a
+    factor 1.5 of 1.1 kernel widths at every GPU count; the particles themselves do not depend on the grid"""
+    assert bench.DAM_BREAK_GRID == "cube"
+    for world in (1, 2, 4, 8):
+        args = dict(bench.SLAB_DAM_BREAK.get(world, dict(nx=100, ny=100, nz=100)))
+        for k in ("nx", "ny", "nz"):
+            args[k] //= 10
+        pool = scenes.dam_break(adaptive=True, grid="pool", **args)
+        cube = scenes.dam_break(adaptive=True, grid="cube", **args)
+        ext = [h - l for l, h in zip(cube.min_pos, cube.max_pos)]
+        assert max(ext) - min(ext) < 1e-3 * max(ext)
+        assert np.allclose([0.5 * (l + h) for l, h in zip(cube.min_pos, cube.max_pos)], [0.5 * (l + h) for l, h in zip(pool.min_pos, pool.max_pos)])
+        assert all(cl <= pl + 1e-4 and ch >= ph - 1e-4 for cl, ch, pl, ph in zip(cube.min_pos, cube.max_pos, pool.min_pos, pool.max_pos))
+        assert all(np.array_equal(cube.arrays[k], pool.arrays[k]) for k in pool.arrays)
+    # the resolution rule at the full-size extents (620, 620, 820, 1220 r)
+    for extent, res in ((620.0, 7), (820.0, 8), (1220.0, 8)):
+        assert scenes._res_near(extent, 4.4) == res and 4.4 / 1.5 < extent / (1 << res) < 4.4 * 1.5
 
 
 def test_full_size_slab_scenes_have_a_million_particles_per_gpu():
