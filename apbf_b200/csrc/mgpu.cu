@@ -752,6 +752,11 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
 	return v;
 }
 
+// reads of a received message: with the pull transport the message sits in the SENDER's memory and is read over NVLink; ld.cv
+// never takes a line an earlier kernel left in this SM's L1 (the buffer is rewritten every other exchange)
+__device__ __forceinline__ int4 msg_ld(const int4* p) { return __ldcv(p); }
+__device__ __forceinline__ uint32_t msg_ld(const uint32_t* p) { return __ldcv(p); }
+
 // tail of a pack kernel (every thread of every CTA gets here): the CTA's stores into the peers' buffers are ordered before thread
 // 0 by the barrier and made visible at system scope by ITS fence (cumulativity: one MEMBAR.SYS per CTA); the CTA that finishes last
 // raises the flags.  Measured (profiles/r02_variants.md, 2 GPUs, 49 000 ghosts each way): a pack kernel takes 19 us, 5 of them the
@@ -824,7 +829,7 @@ __global__ void k_mgl_route_plan(uint32_t* __restrict__ words, mgl_bufs R, int w
 	if (threadIdx.x != 0u) return;
 	uint32_t low = 0u, high = 0u, start = 0u, total_out = 0u;
 	for (int r = 0; r < world; r++) {
-		const uint32_t a = r == rank ? 0u : (uint32_t)R.p[r][0].x;
+		const uint32_t a = r == rank ? 0u : (uint32_t)msg_ld(R.p[r]).x;
 		words[MGL_ARRIVE + r] = a;
 		if (r < rank) low += a; else if (r > rank) high += a;
 		if (r < rank) start += words[MGL_ROUTE + r];
@@ -867,8 +872,8 @@ __global__ void k_mgl_unpack_arrivals(state_lists D, const uint32_t* __restrict_
 		const uint32_t id = words[MGL_ARRIVE_DST + r] + k;
 		if (id >= capacity) continue;
 		const int4* o = R.p[r] + 1 + STATE_INT4 * (size_t)k;
-		D.pos[id] = o[0]; D.vel[id] = o[1]; D.backup[id] = o[2];
-		const int4 a = o[3], b = o[4];
+		D.pos[id] = msg_ld(o); D.vel[id] = msg_ld(o + 1); D.backup[id] = msg_ld(o + 2);
+		const int4 a = msg_ld(o + 3), b = msg_ld(o + 4);
 		D.inv_mass[id] = (uint32_t)a.x; D.radius[id] = (uint32_t)a.y; D.transferring[id] = (uint32_t)a.z; D.target_radius[id] = (uint32_t)a.w;
 		D.kernel_width[id] = (uint32_t)b.x; D.boundariness[id] = (uint32_t)b.y; D.boundary_distance[id] = (uint32_t)b.z;
 		D.index_list[id] = id;
@@ -934,9 +939,10 @@ __global__ void k_mgl_halo_plan(uint32_t* __restrict__ words, mgl_bufs R, mgl_ca
 	for (int r = 0; r < C.world; r++) {
 		uint32_t cnt = 0u;
 		if (r != C.rank) {
-			cnt = min((uint32_t)R.p[r][0].x, C.cap[r]);
+			const int4 hdr = msg_ld(R.p[r]);
+			cnt = min((uint32_t)hdr.x, C.cap[r]);
 			if (first + cnt > capacity) { atomicOr(words + MGL_FLAGS, MGL_FLAG_CAPACITY); cnt = capacity - first; }
-			if (r < C.rank) gid += (uint32_t)R.p[r][0].y;
+			if (r < C.rank) gid += (uint32_t)hdr.y;
 		}
 		words[MGL_HALO_RECV + r] = cnt;
 		words[MGL_GHOST_FIRST + r] = first;
@@ -958,10 +964,10 @@ __global__ void k_mgl_unpack_halo(halo_lists_out L, const uint32_t* __restrict__
 		if (k >= words[MGL_HALO_RECV + r]) continue;
 		const uint32_t id = words[MGL_GHOST_FIRST + r] + k;
 		const int4* in = R.p[r] + 1 + HALO_INT4 * (size_t)k;
-		L.pos[id] = in[0];
-		const int4 a = in[1];
+		L.pos[id] = msg_ld(in);
+		const int4 a = msg_ld(in + 1);
 		L.inv_mass[id] = (uint32_t)a.x; L.radius[id] = (uint32_t)a.y; L.kernel_width[id] = (uint32_t)a.z; L.target_radius[id] = (uint32_t)a.w;
-		L.boundary_distance[id] = (uint32_t)in[2].x;
+		L.boundary_distance[id] = (uint32_t)msg_ld(in + 2).x;
 		L.index_list[id] = id;
 		ghost_ids[C.off[r] + k] = id;
 	}
@@ -1009,11 +1015,11 @@ __global__ void k_mgl_unpack(int what, uint32_t* __restrict__ dst4, int4* __rest
 		const uint32_t k = t - C.off[r];
 		if (r == C.rank || k >= words[MGL_HALO_RECV + r]) continue;
 		const uint32_t id = ghost_ids[t];
-		if (what == 2 || what == 4) dst16[id] = R.p[r][k];
-		else if (what == 1) dst4[id] = ((const uint32_t*)R.p[r])[k];
+		if (what == 2 || what == 4) dst16[id] = msg_ld(R.p[r] + k);
+		else if (what == 1) dst4[id] = msg_ld((const uint32_t*)R.p[r] + k);
 		else { // a ghost's record for the apply sweep: {lambda from its owner, h, gradient c0, gradient c1 from the local constants}
 			const float4 kg = KG[id];
-			const float lam = __uint_as_float(((const uint32_t*)R.p[r])[k]);
+			const float lam = __uint_as_float(msg_ld((const uint32_t*)R.p[r] + k));
 			L4[id] = make_float4(lam, kg.x, kg.y, kg.z);
 			const int4 p = P4[id]; // (refreshed by the exchange before the density sweep)
 			PL[id] = make_int4(p.x, p.y, p.z, __float_as_int(lam < 0.0f ? lam * R_POS : 0.0f));
@@ -1041,17 +1047,32 @@ mgl_sig mgl_begin_exchange(apbf_sim* sim)
 	return S;
 }
 // where the pack kernels of exchange S write / where its messages are read
+// Peer to peer, two ways round.  PUSH: a message is stored into the RECEIVER's arena (slot [source][parity]) and read there.  PULL
+// (APBF_MG_P2P_PULL=1): it is written into the SENDER's own arena (slot [destination][parity]; the pairs size their messages
+// alike, so the same offsets serve) and the receiver's unpack kernel reads it over NVLink once its flag is up -- the pack kernel
+// then has no remote store to drain but the flag.  The two-buffer argument at mgl_sig holds either way: a slot is rewritten two
+// exchanges later, after this rank has waited for the reader's next flag, which the reader raised after it had read.
+bool mgl_pull()
+{
+	static const bool pull = getenv("APBF_MG_P2P_PULL") != nullptr && atoi(getenv("APBF_MG_P2P_PULL")) != 0;
+	return pull;
+}
+int4* mgl_local_slot(const apbf_sim* sim, int r, uint32_t parity)
+{
+	return (r != sim->mg.rank && r < sim->mg.world) ? (int4*)((char*)sim->mgl.arena + sim->mgl.recv_off[r][parity]) : nullptr;
+}
 mgl_bufs send_bufs(const apbf_sim* sim, const mgl_sig& S)
 {
 	mgl_bufs b;
-	for (int r = 0; r < 8; r++) b.p[r] = (int4*)(sim->mgl.p2p ? sim->mgl.remote_recv[r][S.seq & 1u] : sim->mgl.send_buf[r]);
+	for (int r = 0; r < 8; r++)
+		b.p[r] = !sim->mgl.p2p ? (int4*)sim->mgl.send_buf[r] : mgl_pull() ? mgl_local_slot(sim, r, S.seq & 1u) : (int4*)sim->mgl.remote_recv[r][S.seq & 1u];
 	return b;
 }
 mgl_bufs recv_bufs(const apbf_sim* sim, const mgl_sig& S)
 {
 	mgl_bufs b;
 	for (int r = 0; r < 8; r++)
-		b.p[r] = (int4*)(sim->mgl.p2p ? (r != sim->mg.rank && r < sim->mg.world ? (char*)sim->mgl.arena + sim->mgl.recv_off[r][S.seq & 1u] : nullptr) : sim->mgl.recv_buf[r]);
+		b.p[r] = !sim->mgl.p2p ? (int4*)sim->mgl.recv_buf[r] : mgl_pull() ? (int4*)sim->mgl.remote_recv[r][S.seq & 1u] : mgl_local_slot(sim, r, S.seq & 1u);
 	return b;
 }
 mgl_caps caps_of(const apbf_sim* sim)
